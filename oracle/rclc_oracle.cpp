@@ -1,0 +1,934 @@
+// oracle/rclc_oracle.cpp — TEST INFRASTRUCTURE ONLY (CPU oracle; see rclc_oracle.h header note).
+//
+// CPU restatement of the zhijianglu/RCLC calibration hot path, function by function, each citing
+// the reference file:line it follows. Third-party arithmetic (PCL, Ceres, Eigen) is restated from
+// the published algorithms. PARITY UNPINNED (no reference tests exist).
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off: the reference is built without -march
+// flags, so x86-64 baseline SSE2, no FMA contraction — every a*b+c below is two roundings).
+#define RCLC_CONFIG_IMPLEMENTATION
+#include "rclc_oracle.h"
+#include "ceres_lm.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <random>
+#include <vector>
+
+namespace {
+
+struct P4 { float x, y, z, i; };
+
+inline const float* rec(const void* base, int stride, int64_t k)
+{
+    return reinterpret_cast<const float*>(static_cast<const char*>(base) + k * (int64_t)stride);
+}
+inline float* rec(void* base, int stride, int64_t k)
+{
+    return reinterpret_cast<float*>(static_cast<char*>(base) + k * (int64_t)stride);
+}
+inline float rec_i(const void* base, int stride, int ioff, int64_t k)
+{
+    float v;
+    std::memcpy(&v, static_cast<const char*>(base) + k * (int64_t)stride + ioff, 4);
+    return v;
+}
+
+std::vector<P4> load_cloud(const void* pts, int stride, int ioff, int64_t n)
+{
+    std::vector<P4> c(n);
+    for (int64_t k = 0; k < n; ++k) {
+        const float* r = rec(pts, stride, k);
+        c[k] = {r[0], r[1], r[2], rec_i(pts, stride, ioff, k)};
+    }
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// include/utils.h:286-316  generate_std_corners. Expressions kept in the reference's order.
+// ---------------------------------------------------------------------------------------------
+struct Target { double x, y; bool is_row; };
+
+void generate_std_corners(const rclc_config& c, std::vector<Target>& row_points, std::vector<Target>& col_points)
+{
+    const int bx = c.board_width, by = c.board_height;
+    const int centroid_x_id = bx / 2;
+    const int centroid_y_id = by / 2;
+    const double s = c.gride_side_length;
+    const double row_shift_x = centroid_x_id * s;
+    const double row_shift_y = double(centroid_y_id - 1) * s;
+    for (int r = 0; r < by - 1; ++r)
+        for (int cc = 0; cc < bx; ++cc)
+            row_points.push_back({s / 2.0 + cc * s - row_shift_x, r * s - row_shift_y, true});
+    const double col_shift_y = double(centroid_y_id) * s;
+    const double col_shift_x = double(centroid_x_id - 1) * s;
+    for (int cc = 0; cc < bx - 1; ++cc)
+        for (int r = 0; r < by; ++r)
+            col_points.push_back({cc * s - col_shift_x, s / 2.0 + r * s - col_shift_y, false});
+}
+
+// Residual-block order of opt_grid_fitting.h:78-94 : all col targets, then all row targets.
+std::vector<Target> problem_targets(const rclc_config& c)
+{
+    std::vector<Target> rows, cols;
+    generate_std_corners(c, rows, cols);
+    std::vector<Target> t(cols);
+    t.insert(t.end(), rows.begin(), rows.end());
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// include/opt/board_fitting_cost.h:34-62  radii
+// ---------------------------------------------------------------------------------------------
+struct Radii { double neighbour_radius, cost_radius2, cost_gradient_radius2; };
+
+Radii make_radii(const rclc_config& c)
+{
+    Radii r;
+    const double factor = std::sqrt(2.0);
+    r.neighbour_radius = c.neighbour_radius_rate * c.gride_side_length;
+    double cost_radius = c.cost_radius_rate * c.gride_side_length;
+    double cost_gradient_radius = cost_radius * factor;
+    if (!(r.neighbour_radius > cost_gradient_radius)) {
+        cost_gradient_radius = 0.9 * r.neighbour_radius;
+        cost_radius = cost_gradient_radius / factor;
+    }
+    r.cost_radius2 = cost_radius * cost_radius;
+    r.cost_gradient_radius2 = cost_gradient_radius * cost_gradient_radius;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// board_fitting_cost.h:264-280  update_neighbour_points == pcl::KdTreeFLANN::radiusSearch.
+// FLANN (kdtree_single_index.h, L2_Simple<float>): squared distance accumulated in float over
+// x,y,z in that order, kept when dist < (float)(radius*radius) (strict). Exhaustive restatement;
+// neighbour order = ascending original index (PCL returns them sorted by distance; order only
+// affects fp64 summation order inside Evaluate).
+// ---------------------------------------------------------------------------------------------
+inline bool flann_within(float qx, float qy, float qz, const P4& p, float r2)
+{
+    float result = 0.0f, diff;
+    diff = qx - p.x; result += diff * diff;
+    diff = qy - p.y; result += diff * diff;
+    diff = qz - p.z; result += diff * diff;
+    return result < r2;
+}
+
+void build_neighbours(const std::vector<P4>& cloud, const std::vector<Target>& targets, double neighbour_radius,
+                      std::vector<std::vector<int>>& nb)
+{
+    const float r2 = static_cast<float>(neighbour_radius * neighbour_radius);
+    nb.assign(targets.size(), {});
+    // uniform-grid acceleration with an exact final test (same result as exhaustive search)
+    for (size_t t = 0; t < targets.size(); ++t) nb[t].reserve(cloud.size() / 20 + 16);
+    const double reach = neighbour_radius * 1.01 + 1e-6;
+    for (int k = 0; k < (int)cloud.size(); ++k) {
+        const P4& p = cloud[k];
+        for (size_t t = 0; t < targets.size(); ++t) {
+            if (std::fabs((double)p.x - targets[t].x) > reach || std::fabs((double)p.y - targets[t].y) > reach) continue;
+            if (flann_within((float)targets[t].x, (float)targets[t].y, 0.0f, p, r2)) nb[t].push_back(k);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// board_fitting_cost.h:74-262  BOARD_FITTING_COST::Evaluate for one target.
+// acc16 (optional): cost sum d,u,l,r | cost cnt d,u,l,r | interval sum d,u,l,r | interval cnt d,u,l,r
+// ---------------------------------------------------------------------------------------------
+void evaluate_target(const Target& tg, const std::vector<P4>& cloud, const std::vector<int>& nb, const Radii& rad,
+                     const double* params, double* residual, double* jac3, double* acc16)
+{
+    const double theta = (params[2] * double(M_PI)) / (180.0);                              // :80
+    // :82,113  Eigen::Quaternion(w,0,0,z).matrix(): tz=2z, twz=tz*w, tzz=tz*z
+    const double qw = std::cos(theta / 2.0), qz = std::sin(theta / 2.0);
+    const double tz = 2.0 * qz, twz = tz * qw, tzz = tz * qz;
+    const double R00 = 1.0 - (0.0 + tzz), R01 = 0.0 - twz, R10 = 0.0 + twz, R11 = 1.0 - (0.0 + tzz);
+    const double tx = params[0], ty = params[1];
+
+    double cs[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};   // cost intensity / cnt: down, up, left, right
+    double is[4] = {0, 0, 0, 0}, ic[4] = {0, 0, 0, 0};   // interval
+    const double ref_x = tg.x, ref_y = tg.y;
+    for (size_t j = 0; j < nb.size(); ++j) {                                                // :124
+        const P4& p = cloud[nb[j]];
+        const double neig_x = double(p.x), neig_y = double(p.y), neig_intensity = double(p.i);
+        const double vx = neig_x + tx, vy = neig_y + ty;                                     // :133
+        const double xt = R00 * vx + R01 * vy;       // third term R02*(0+0) == +0 exactly
+        const double yt = R10 * vx + R11 * vy;
+        const double dx = std::max(double(10e-15), std::fabs(ref_x - xt));                   // :138
+        const double dy = std::max(double(10e-15), std::fabs(ref_y - yt));
+        const double distance_2 = dx * dx + dy * dy;
+        if (distance_2 > rad.cost_gradient_radius2) continue;                                // :142
+        const bool in_cost = distance_2 < rad.cost_radius2;
+        const int ud = (yt > ref_y) ? 0 : 1;                                                 // :147 down : up
+        const int lr = (xt > ref_x) ? 3 : 2;                                                 // :178 right : left
+        if (in_cost) { cs[ud] += neig_intensity; cc[ud] += 1; cs[lr] += neig_intensity; cc[lr] += 1; }
+        else         { is[ud] += neig_intensity; ic[ud] += 1; is[lr] += neig_intensity; ic[lr] += 1; }
+    }
+    const double C_d = cs[0] / cc[0], C_u = cs[1] / cc[1], C_l = cs[2] / cc[2], C_r = cs[3] / cc[3];   // :211-214
+    const double dC_d = is[0] / ic[0], dC_u = is[1] / ic[1], dC_l = is[2] / ic[2], dC_r = is[3] / ic[3];
+    const double cost_ud = std::fabs(C_d - C_u);
+    const double cost_lr = std::fabs(C_r - C_l);
+    const double gradient_x = std::fabs(C_r - dC_r) - std::fabs(C_l - dC_l);                 // :224
+    const double gradient_y = std::fabs(C_d - dC_d) - std::fabs(C_u - dC_u);
+    residual[0] = tg.is_row ? 1.0 - std::tanh((cost_ud) / 100.0) : 1.0 - std::tanh((cost_lr) / 100.0);  // :227-236
+    if (jac3) {
+        const double dp_dtheta1 = -tx * std::cos(theta) - ty * std::sin(theta);              // :252
+        const double dp_dtheta2 = tx * std::sin(theta) - ty * std::cos(theta);
+        jac3[0] = gradient_x;
+        jac3[1] = gradient_y;
+        jac3[2] = gradient_x * dp_dtheta1 + gradient_y * dp_dtheta2;
+    }
+    if (acc16) {
+        for (int k = 0; k < 4; ++k) { acc16[k] = cs[k]; acc16[4 + k] = cc[k]; acc16[8 + k] = is[k]; acc16[12 + k] = ic[k]; }
+    }
+}
+
+struct GridProblem {
+    const std::vector<P4>* cloud;
+    std::vector<Target> targets;
+    std::vector<std::vector<int>> nb;
+    Radii rad;
+    double huber_a;
+    int64_t evaluate_calls = 0;
+
+    // ProgramEvaluator::Evaluate over the residual blocks (1 residual, 3 params each, shared loss).
+    bool evaluate(const double* x, double* cost, double* residuals, double* jac)
+    {
+        const int m = (int)targets.size();
+        double total = 0;
+        bool ok = true;
+        for (int t = 0; t < m; ++t) {
+            double r, j[3];
+            evaluate_target(targets[t], *cloud, nb[t], rad, x, &r, jac ? j : nullptr, nullptr);
+            evaluate_calls++;
+            if (!std::isfinite(r)) ok = false;                                 // IsEvaluationValid
+            if (jac && !(std::isfinite(j[0]) && std::isfinite(j[1]) && std::isfinite(j[2]))) ok = false;
+            if (!ok) return false;
+            total += orc::apply_loss_1d(huber_a, &r, jac ? j : nullptr, 3);
+            if (residuals) residuals[t] = r;
+            if (jac) { jac[t * 3 + 0] = j[0]; jac[t * 3 + 1] = j[1]; jac[t * 3 + 2] = j[2]; }
+        }
+        *cost = total;
+        return true;
+    }
+};
+
+// include/utils.h:273-284  SE2_to_SE3<float>: double quaternion matrix cast to float, row-major out.
+void se2_to_se3f(double x, double y, double yaw_ang, float T[16])
+{
+    const double ang = (yaw_ang * double(M_PI)) / double(180.0);
+    const double qw = std::cos(ang / 2.0), qz = std::sin(ang / 2.0);
+    const double tz = 2.0 * qz, twz = tz * qw, tzz = tz * qz;
+    const double R[9] = {1.0 - (0.0 + tzz), 0.0 - twz, 0.0, 0.0 + twz, 1.0 - (0.0 + tzz), 0.0, 0.0, 0.0, 1.0};
+    for (int k = 0; k < 16; ++k) T[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) T[r * 4 + c] = (float)R[r * 3 + c];
+    T[3] = (float)x;
+    T[7] = (float)y;
+    T[11] = 0.0f;
+}
+
+// pcl::transformPointCloud(cloud, cloud, Eigen::Matrix4f) — float, ((m0*x + m1*y) + m2*z) + m3
+// (PCL <= 1.9 scalar form; PCL's SSE form differs in association only. Unpinned: this is the definition.)
+inline void transform_point_f(const float T[16], float& x, float& y, float& z)
+{
+    const float nx = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
+    const float ny = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
+    const float nz = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
+    x = nx; y = ny; z = nz;
+}
+
+void mat4f_mul(const float A[16], const float B[16], float C[16])
+{
+    float out[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            float s = A[r * 4 + 0] * B[0 * 4 + c];
+            s = s + A[r * 4 + 1] * B[1 * 4 + c];
+            s = s + A[r * 4 + 2] * B[2 * 4 + c];
+            s = s + A[r * 4 + 3] * B[3 * 4 + c];
+            out[r * 4 + c] = s;
+        }
+    std::memcpy(C, out, sizeof(out));
+}
+
+void mat4d_mul(const double A[16], const double B[16], double C[16])
+{
+    double out[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += A[r * 4 + k] * B[k * 4 + c];
+            out[r * 4 + c] = s;
+        }
+    std::memcpy(C, out, sizeof(out));
+}
+
+// General 4x4 inverse by cofactors (Eigen::Matrix4d::inverse() is the cofactor form as well).
+bool inverse4(const double m[16], double inv_out[16])
+{
+    double inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    if (det == 0) return false;
+    const double id = 1.0 / det;
+    for (int i = 0; i < 16; i++) inv_out[i] = inv[i] * id;
+    return true;
+}
+
+// include/utils.h:47-66  calc_transfered_standard_corners
+void transfered_standard_corners(const rclc_config& c, const double T_laser_base[16], double* out)
+{
+    const double s = c.gride_side_length;
+    const double first_corner_x = double(int((c.board_width - 1) / 2)) * s;
+    const double first_corner_y = double(int((c.board_height - 1) / 2)) * s;
+    int k = 0;
+    for (int row = 0; row < c.board_height - 1; ++row)
+        for (int col = 0; col < c.board_width - 1; ++col) {
+            const double p[4] = {first_corner_x - double(col) * s, first_corner_y - double(row) * s, 0, 1};
+            for (int r = 0; r < 3; ++r) {
+                double v = 0;
+                for (int q = 0; q < 4; ++q) v += T_laser_base[r * 4 + q] * p[q];
+                out[k * 3 + r] = v;
+            }
+            ++k;
+        }
+}
+
+// Eigen::Quaternion::toRotationMatrix (templated so the pose cost can run it on Jets)
+template <typename T>
+void quat_to_R(const T& w, const T& x, const T& y, const T& z, T R[9])
+{
+    const T tx = T(2) * x, ty = T(2) * y, tz = T(2) * z;
+    const T twx = tx * w, twy = ty * w, twz = tz * w;
+    const T txx = tx * x, txy = ty * x, txz = tz * x;
+    const T tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = T(1) - (tyy + tzz); R[1] = txy - twz;          R[2] = txz + twy;
+    R[3] = txy + twz;          R[4] = T(1) - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;          R[7] = tyz + twx;          R[8] = T(1) - (txx + tyy);
+}
+
+// ceres::Jet<double, N> — the operations POSE_REPRJ_COST needs.
+template <int N>
+struct Jet {
+    double a;
+    double v[N];
+    Jet() : a(0) { for (int i = 0; i < N; ++i) v[i] = 0; }
+    Jet(double s) : a(s) { for (int i = 0; i < N; ++i) v[i] = 0; }   // NOLINT
+    Jet(double s, int k) : a(s) { for (int i = 0; i < N; ++i) v[i] = 0; v[k] = 1.0; }
+};
+template <int N> Jet<N> operator+(const Jet<N>& f, const Jet<N>& g) { Jet<N> h; h.a = f.a + g.a; for (int i = 0; i < N; ++i) h.v[i] = f.v[i] + g.v[i]; return h; }
+template <int N> Jet<N> operator-(const Jet<N>& f, const Jet<N>& g) { Jet<N> h; h.a = f.a - g.a; for (int i = 0; i < N; ++i) h.v[i] = f.v[i] - g.v[i]; return h; }
+template <int N> Jet<N> operator*(const Jet<N>& f, const Jet<N>& g) { Jet<N> h; h.a = f.a * g.a; for (int i = 0; i < N; ++i) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
+template <int N> Jet<N> operator/(const Jet<N>& f, const Jet<N>& g)
+{
+    // jet.h: g_a_inverse = 1/g.a; f_a_by_g_a = f.a * g_a_inverse; v = (f.v - f_a_by_g_a * g.v) * g_a_inverse
+    Jet<N> h;
+    const double g_a_inverse = 1.0 / g.a;
+    const double f_a_by_g_a = f.a * g_a_inverse;
+    h.a = f_a_by_g_a;
+    for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - f_a_by_g_a * g.v[i]) * g_a_inverse;
+    return h;
+}
+template <int N> Jet<N> jsqrt(const Jet<N>& f)
+{
+    Jet<N> h;
+    const double tmp = std::sqrt(f.a);
+    const double two_a_inverse = 1.0 / (2.0 * tmp);
+    h.a = tmp;
+    for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * two_a_inverse;
+    return h;
+}
+inline double jsqrt(double f) { return std::sqrt(f); }
+template <int N> bool operator>(const Jet<N>& f, const Jet<N>& g) { return f.a > g.a; }
+
+// ---------------------------------------------------------------------------------------------
+// include/opt/pose_reprj_cost.hpp:28-55  POSE_REPRJ_COST::operator()
+// Small fixed-size Eigen products/reductions associate as a0 + (a1 + a2) (redux_novec_unroller).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+T pose_residual(const T* q, const T* t, const double* pc, const double* img, int C)
+{
+    T R[9];
+    quat_to_R(q[3], q[0], q[1], q[2], R);
+    T residual = T(0);
+    T depth_max = T(0);
+    for (int i = 0; i < C; ++i) {
+        const T p0 = T(pc[i * 3 + 0]), p1 = T(pc[i * 3 + 1]), p2 = T(pc[i * 3 + 2]);
+        const T X = (R[0] * p0 + (R[1] * p1 + R[2] * p2)) + t[0];
+        const T Y = (R[3] * p0 + (R[4] * p1 + R[5] * p2)) + t[1];
+        const T Z = (R[6] * p0 + (R[7] * p1 + R[8] * p2)) + t[2];
+        const T depth_norm = jsqrt(X * X + (Y * Y + Z * Z));
+        if (depth_norm > depth_max) depth_max = depth_norm;
+        const T e0 = T(img[i * 2 + 0]) - X / Z;
+        const T e1 = T(img[i * 2 + 1]) - Y / Z;
+        const T error = jsqrt(e0 * e0 + e1 * e1) / depth_norm;
+        residual = residual + error;
+    }
+    residual = residual * depth_max;
+    return residual;
+}
+
+// ceres::EigenQuaternionParameterization (storage x,y,z,w)
+void quat_plus(const double* x, const double* delta, double* out)
+{
+    const double norm_delta = std::sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+    if (norm_delta > 0.0) {
+        const double s = std::sin(norm_delta) / norm_delta;
+        const double dw = std::cos(norm_delta), dx = s * delta[0], dy = s * delta[1], dz = s * delta[2];
+        const double xw = x[3], xx = x[0], xy = x[1], xz = x[2];
+        // Eigen quaternion product a*b
+        const double w = dw * xw - dx * xx - dy * xy - dz * xz;
+        const double X = dw * xx + dx * xw + dy * xz - dz * xy;
+        const double Y = dw * xy + dy * xw + dz * xx - dx * xz;
+        const double Z = dw * xz + dz * xw + dx * xy - dy * xx;
+        out[0] = X; out[1] = Y; out[2] = Z; out[3] = w;
+    } else {
+        for (int i = 0; i < 4; ++i) out[i] = x[i];
+    }
+}
+void quat_plus_jacobian(const double* x, double* J /*4x3 row-major*/)
+{
+    J[0] = x[3];  J[1] = x[2];   J[2] = -x[1];
+    J[3] = -x[2]; J[4] = x[3];   J[5] = x[0];
+    J[6] = x[1];  J[7] = -x[0];  J[8] = x[3];
+    J[9] = -x[0]; J[10] = -x[1]; J[11] = -x[2];
+}
+
+// Residual + 1x6 local Jacobian (AutoDiffCostFunction<POSE_REPRJ_COST,1,4,3> then
+// LocalParameterization::MultiplyByJacobian) for one frame.
+void pose_block(const double* Tcl, const double* pc, const double* img, int C, double* r, double* j6)
+{
+    typedef Jet<7> J7;
+    J7 q[4], t[3];
+    for (int k = 0; k < 4; ++k) q[k] = J7(Tcl[k], k);
+    for (int k = 0; k < 3; ++k) t[k] = J7(Tcl[4 + k], 4 + k);
+    const J7 res = pose_residual<J7>(q, t, pc, img, C);
+    *r = res.a;
+    if (j6) {
+        double P[12];
+        quat_plus_jacobian(Tcl, P);
+        for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += res.v[k] * P[k * 3 + c];
+            j6[c] = s;
+        }
+        for (int c = 0; c < 3; ++c) j6[3 + c] = res.v[4 + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PCL SampleConsensusModelPlane (sac_model_plane.hpp) in float, no FMA.
+// ---------------------------------------------------------------------------------------------
+bool plane_from_triplet(const float* p0, const float* p1, const float* p2, float coeff[4])
+{
+    const float a0 = p1[0] - p0[0], a1 = p1[1] - p0[1], a2 = p1[2] - p0[2];
+    const float b0 = p2[0] - p0[0], b1 = p2[1] - p0[1], b2 = p2[2] - p0[2];
+    const float d0 = a0 / b0, d1 = a1 / b1, d2 = a2 / b2;
+    if ((d0 == d1) && (d2 == d1)) return false;                       // collinearity check
+    float c0 = a1 * b2 - a2 * b1;
+    float c1 = a2 * b0 - a0 * b2;
+    float c2 = a0 * b1 - a1 * b0;
+    // model_coefficients.normalize() on a Vector4f with [3]=0: squaredNorm then divide by sqrt.
+    // Eigen SSE2 packet reduction: (c0^2 + c2^2) + (c1^2 + 0)
+    const float n2 = (c0 * c0 + c2 * c2) + (c1 * c1 + 0.0f);
+    const float nrm = std::sqrt(n2);
+    c0 = c0 / nrm; c1 = c1 / nrm; c2 = c2 / nrm;
+    // d = -1 * coeff.dot(p0) with coeff[3]=0, p0[3]=1:  (c0*x + c2*z) + (c1*y + 0*1)
+    const float dot = (c0 * p0[0] + c2 * p0[2]) + (c1 * p0[1] + 0.0f);
+    coeff[0] = c0; coeff[1] = c1; coeff[2] = c2; coeff[3] = -1.0f * dot;
+    return true;
+}
+inline float plane_dot(const float c[4], const float* p)
+{
+    // Eigen Vector4f dot, SSE2 predux: (c0*x + c2*z) + (c1*y + c3*1)
+    return (c[0] * p[0] + c[2] * p[2]) + (c[1] * p[1] + c[3] * 1.0f);
+}
+inline bool plane_inlier(const float c[4], const float* p, double thr)
+{
+    return (double)std::fabs(plane_dot(c, p)) < thr;                  // std::abs(float) < double threshold
+}
+
+// 3x3 symmetric eigen decomposition (Jacobi rotations, double): smallest eigenvalue's vector.
+void smallest_eigenvector(const double cov[9], double evec[3])
+{
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) a[r][c] = cov[r * 3 + c];
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                const double th = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - s * akq;
+                    a[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - s * aqk;
+                    a[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - s * vkq;
+                    v[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    int best = 0;
+    for (int k = 1; k < 3; ++k) if (a[k][k] < a[best][best]) best = k;
+    for (int k = 0; k < 3; ++k) evec[k] = v[k][best];
+}
+
+inline int cv_round(double v) { return (int)std::nearbyint(v); }   // cvRound: round-half-even (SSE2 cvtsd2si)
+
+} // namespace
+
+extern "C" {
+
+int orc_generate_targets(const rclc_config* cfg, double* targets_xy, int32_t* is_row, int32_t* n_targets)
+{
+    const std::vector<Target> t = problem_targets(*cfg);
+    for (size_t k = 0; k < t.size(); ++k) {
+        targets_xy[2 * k] = t[k].x;
+        targets_xy[2 * k + 1] = t[k].y;
+        is_row[k] = t[k].is_row ? 1 : 0;
+    }
+    *n_targets = (int32_t)t.size();
+    return 0;
+}
+
+int orc_gridfit_eval(const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n,
+                     const double pose[3], double* residuals, double* jac, double* acc)
+{
+    const std::vector<P4> cloud = load_cloud(pts, stride, ioff, n);
+    const std::vector<Target> targets = problem_targets(*cfg);
+    const Radii rad = make_radii(*cfg);
+    std::vector<std::vector<int>> nb;
+    build_neighbours(cloud, targets, rad.neighbour_radius, nb);
+    for (size_t t = 0; t < targets.size(); ++t)
+        evaluate_target(targets[t], cloud, nb[t], rad, pose, &residuals[t], jac ? &jac[3 * t] : nullptr,
+                        acc ? &acc[16 * t] : nullptr);
+    return 0;
+}
+
+int orc_gridfit_cost(const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n,
+                     const double pose[3], double* cost)
+{
+    const std::vector<P4> cloud = load_cloud(pts, stride, ioff, n);
+    GridProblem gp;
+    gp.cloud = &cloud;
+    gp.targets = problem_targets(*cfg);
+    gp.rad = make_radii(*cfg);
+    gp.huber_a = cfg->gridfit_huber_a;
+    build_neighbours(cloud, gp.targets, gp.rad.neighbour_radius, gp.nb);
+    return gp.evaluate(pose, cost, nullptr, nullptr) ? 0 : 1;
+}
+
+// include/opt/opt_grid_fitting.h:25-132
+int orc_gridfit_solve(const rclc_config* cfg, void* pts_io, int stride, int ioff, int64_t n,
+                      double* T_bl_io, double* corners_out, orc_gridfit_report* rep)
+{
+    // :32-38 optional UniformSampling is handled by the caller (shipped config: radius 0 => skipped)
+    if (cfg->apply_noise_test) {                                               // :47-56
+        float Tn[16];
+        se2_to_se3f(cfg->noise_x, cfg->noise_y, cfg->noise_yaml, Tn);
+        for (int64_t k = 0; k < n; ++k) { float* r = rec(pts_io, stride, k); transform_point_f(Tn, r[0], r[1], r[2]); }
+        double Tnd[16];
+        for (int k = 0; k < 16; ++k) Tnd[k] = (double)Tn[k];
+        mat4d_mul(Tnd, T_bl_io, T_bl_io);
+    }
+    std::vector<P4> pc_iter = load_cloud(pts_io, stride, ioff, n);             // :60-61
+    float T_base_laser[16];
+    for (int k = 0; k < 16; ++k) T_base_laser[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+
+    GridProblem gp;
+    gp.cloud = &pc_iter;
+    gp.targets = problem_targets(*cfg);
+    gp.rad = make_radii(*cfg);
+    gp.huber_a = cfg->gridfit_huber_a;
+    const int m = (int)gp.targets.size();
+
+    orc::LMOptions opt;                                                        // :96-101
+    opt.linear_solver = orc::DENSE_QR;
+    opt.max_num_iterations = cfg->gridfit_max_lm_iters;
+    opt.function_tolerance = cfg->gridfit_function_tol;
+
+    if (rep) { std::memset(rep, 0, sizeof(*rep)); }
+    bool shouldQuit = false;
+    int iter = 0;
+    while (!shouldQuit) {                                                      // :68
+        double T_se2_wl[3] = {0.0, 0.0, 0.0};
+        build_neighbours(pc_iter, gp.targets, gp.rad.neighbour_radius, gp.nb); // :75-94 (kd-tree + per-target radius search)
+        orc::LMProblem P;
+        P.m = m; P.n = 3; P.nl = 3;
+        P.evaluate = [&](const double* x, double* cost, double* r, double* j) { return gp.evaluate(x, cost, r, j); };
+        const orc::LMSummary sum = orc::lm_minimize(P, opt, T_se2_wl);         // :103
+        float T_w1_w0[16];
+        se2_to_se3f(T_se2_wl[0], T_se2_wl[1], T_se2_wl[2], T_w1_w0);           // :105-106
+        for (auto& p : pc_iter) transform_point_f(T_w1_w0, p.x, p.y, p.z);     // :107
+        const double decrease_rate = (sum.initial_cost - sum.final_cost) / sum.initial_cost;   // :113
+        iter++;
+        if (rep) {
+            if (iter == 1) { rep->first_initial_cost = sum.initial_cost; for (int k = 0; k < 3; ++k) rep->se2_first[k] = T_se2_wl[k]; }
+            rep->last_final_cost = sum.final_cost;
+            rep->pose_evals += sum.num_cost_evals;
+            rep->lm_iterations += sum.num_iterations;
+            if (sum.termination == orc::FAILURE) rep->status = 1;
+        }
+        if ((std::fabs(decrease_rate) < 1e-6) || iter > cfg->max_iter_time) {  // :116
+            if (decrease_rate > 0) mat4f_mul(T_w1_w0, T_base_laser, T_base_laser);
+            shouldQuit = true;
+        } else {
+            mat4f_mul(T_w1_w0, T_base_laser, T_base_laser);
+        }
+    }
+    double Tbld[16], final_T_base_laser[16], final_T_laser_base[16];
+    for (int k = 0; k < 16; ++k) Tbld[k] = (double)T_base_laser[k];
+    mat4d_mul(Tbld, T_bl_io, final_T_base_laser);                              // :129
+    if (!inverse4(final_T_base_laser, final_T_laser_base)) return 2;           // :130
+    transfered_standard_corners(*cfg, final_T_laser_base, corners_out);        // :131
+    if (rep) {
+        rep->outer_iterations = iter;
+        rep->evaluate_calls = gp.evaluate_calls;
+        std::memcpy(rep->T_base_laser, T_base_laser, sizeof(T_base_laser));
+    }
+    return 0;
+}
+
+// src/GMMFit.cpp:7-108 + src/GaussianFunction.cpp:7-23
+int orc_gmm_fit_1d(const void* intensity, int stride, int64_t n, int K, int iters,
+                   double* mu, double* sigma, double* priors_out)
+{
+    std::vector<double> x(n);
+    for (int64_t i = 0; i < n; ++i) x[i] = (double)*rec(intensity, stride, i);   // pc_process.h:605-606 float->double
+    std::vector<double> priors(K, 1.0 / double(K));                              // :29-31
+    std::vector<double> L((size_t)n * K), P((size_t)n * K);
+    for (int itr = 0; itr < iters; ++itr) {                                      // :37
+        for (int k = 0; k < K; ++k) {                                            // :46-50
+            const double factor = 1.0 / (sigma[k] * std::sqrt(2.0 * M_PI));
+            const double sigma_sqr = sigma[k] * sigma[k];
+            for (int64_t i = 0; i < n; ++i)
+                L[i * K + k] = factor * std::exp(-1.0 / (2 * sigma_sqr) * (x[i] - mu[k]) * (x[i] - mu[k]));
+        }
+        for (int64_t i = 0; i < n; ++i) {                                        // :59-65
+            double p_x = 0;
+            for (int k = 0; k < K; ++k) p_x += L[i * K + k] * priors[k];
+            for (int k = 0; k < K; ++k) P[i * K + k] = (L[i * K + k] * priors[k]) / p_x;
+        }
+        std::vector<double> denoms(K);
+        for (int k = 0; k < K; ++k) {                                            // :73-93
+            double denom = 0, mu_num = 0;
+            for (int64_t i = 0; i < n; ++i) denom += P[i * K + k];
+            for (int64_t i = 0; i < n; ++i) mu_num += P[i * K + k] * x[i];
+            const double mu_new = mu_num / denom;
+            double sig_num = 0;
+            for (int64_t i = 0; i < n; ++i) sig_num += P[i * K + k] * ((x[i] - mu_new) * (x[i] - mu_new));
+            mu[k] = mu_new;
+            sigma[k] = std::sqrt(sig_num / denom);
+            denoms[k] = denom;
+        }
+        for (int k = 0; k < K; ++k) priors[k] = denoms[k] / double(n);           // :98-101
+    }
+    if (priors_out) for (int k = 0; k < K; ++k) priors_out[k] = priors[k];
+    return 0;
+}
+
+// include/pc_process.h:41-57
+int orc_plane_project(void* pts_io, int stride, int64_t n, const double plane[4])
+{
+    for (int64_t k = 0; k < n; ++k) {
+        float* pt = rec(pts_io, stride, k);
+        const double d0 = (double)(pt[0] / pt[2]);          // Vector2d(pt.x / pt.z, ...) : float division, then widened
+        const double d1 = (double)(pt[1] / pt[2]);
+        pt[2] = (float)(-plane[3] / (plane[0] * d0 + plane[1] * d1 + plane[2]));
+        pt[0] = (float)((double)pt[2] * d0);                // float * double -> double -> float
+        pt[1] = (float)((double)pt[2] * d1);
+    }
+    return 0;
+}
+
+int orc_transform_cloud(void* pts_io, int stride, int64_t n, const float T[16])
+{
+    for (int64_t k = 0; k < n; ++k) { float* r = rec(pts_io, stride, k); transform_point_f(T, r[0], r[1], r[2]); }
+    return 0;
+}
+
+int orc_ransac_score(const void* pts, int stride, int64_t n, const int32_t* triplets, int H,
+                     double thr, float* planes_out, int32_t* valid_out, int32_t* counts_out)
+{
+    for (int h = 0; h < H; ++h) {
+        float c[4] = {0, 0, 0, 0};
+        const bool ok = plane_from_triplet(rec(pts, stride, triplets[3 * h]), rec(pts, stride, triplets[3 * h + 1]),
+                                           rec(pts, stride, triplets[3 * h + 2]), c);
+        int32_t cnt = 0;
+        if (ok)
+            for (int64_t k = 0; k < n; ++k) cnt += plane_inlier(c, rec(pts, stride, k), thr) ? 1 : 0;
+        for (int q = 0; q < 4; ++q) planes_out[4 * h + q] = c[q];
+        valid_out[h] = ok ? 1 : 0;
+        counts_out[h] = cnt;
+    }
+    return 0;
+}
+
+int orc_plane_select(const void* pts, int stride, int64_t n, const float plane[4], double thr, uint8_t* mask_out)
+{
+    for (int64_t k = 0; k < n; ++k) mask_out[k] = plane_inlier(plane, rec(pts, stride, k), thr) ? 1 : 0;
+    return 0;
+}
+
+// pcl/sample_consensus/impl/ransac.hpp computeModel
+int orc_ransac_replay(const int32_t* counts, const int32_t* valid, int H, int64_t n_indices,
+                      int max_iterations, double probability, int32_t* best_out, int32_t* iters_out)
+{
+    int iterations = 0;
+    int n_best = -INT32_MAX;
+    double k = 1.0;
+    int skipped = 0;
+    const int max_skip = max_iterations * 10;
+    const double log_probability = std::log(1.0 - probability);
+    const double one_over_indices = 1.0 / static_cast<double>(n_indices);
+    int best = -1, h = 0;
+    while (iterations < k && skipped < max_skip) {
+        if (h >= H) break;                              // hypothesis list exhausted
+        const int cur = h++;
+        if (!valid[cur]) { ++skipped; continue; }
+        if (counts[cur] > n_best) {
+            n_best = counts[cur];
+            best = cur;
+            const double w = static_cast<double>(n_best) * one_over_indices;
+            double p_no_outliers = 1.0 - std::pow(w, 3.0);
+            p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+            p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+            k = log_probability / std::log(p_no_outliers);
+        }
+        ++iterations;
+        if (iterations > max_iterations) break;
+    }
+    *best_out = best;
+    *iters_out = iterations;
+    return 0;
+}
+
+int orc_plane_refine(const void* pts, int stride, int64_t n, const uint8_t* mask, const float plane_in[4],
+                     float plane_out[4], float centroid_out[3])
+{
+    // computeMeanAndCovarianceMatrix single pass; accumulation in double (PCL's Scalar differs by
+    // version; unpinned), normalised the same way: accu /= n; cov = E[xx'] - mean mean'.
+    double accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t cnt = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        if (!mask[k]) continue;
+        const float* p = rec(pts, stride, k);
+        const double x = p[0], y = p[1], z = p[2];
+        accu[0] += x * x; accu[1] += x * y; accu[2] += x * z; accu[3] += y * y; accu[4] += y * z; accu[5] += z * z;
+        accu[6] += x; accu[7] += y; accu[8] += z;
+        ++cnt;
+    }
+    if (cnt <= 3) { for (int q = 0; q < 4; ++q) plane_out[q] = plane_in[q]; centroid_out[0] = centroid_out[1] = centroid_out[2] = 0; return 0; }
+    for (int q = 0; q < 9; ++q) accu[q] /= (double)cnt;
+    double cov[9];
+    cov[0] = accu[0] - accu[6] * accu[6];
+    cov[1] = accu[1] - accu[6] * accu[7];
+    cov[2] = accu[2] - accu[6] * accu[8];
+    cov[4] = accu[3] - accu[7] * accu[7];
+    cov[5] = accu[4] - accu[7] * accu[8];
+    cov[8] = accu[5] - accu[8] * accu[8];
+    cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+    double ev[3];
+    smallest_eigenvector(cov, ev);
+    // sign convention: keep the hemisphere of the input model (eigenvector sign is arbitrary)
+    if (ev[0] * plane_in[0] + ev[1] * plane_in[1] + ev[2] * plane_in[2] < 0) { ev[0] = -ev[0]; ev[1] = -ev[1]; ev[2] = -ev[2]; }
+    plane_out[0] = (float)ev[0]; plane_out[1] = (float)ev[1]; plane_out[2] = (float)ev[2];
+    centroid_out[0] = (float)accu[6]; centroid_out[1] = (float)accu[7]; centroid_out[2] = (float)accu[8];
+    const float dot = (plane_out[0] * centroid_out[0] + plane_out[2] * centroid_out[2]) + (plane_out[1] * centroid_out[1] + 0.0f);
+    plane_out[3] = -1.0f * dot;
+    return 0;
+}
+
+int orc_ransac_draw_triplets(int64_t n_indices, int H, int32_t* triplets_out)
+{
+    // SampleConsensusModel: boost::mt19937 rng(12345), uniform_int<>(0, INT_MAX) => rng()>>1;
+    // drawIndexSample: swap(idx[i], idx[i + rnd() % (size - i)]) for i in 0..2 on a persistent shuffled index list.
+    std::mt19937 rng(12345u);
+    std::vector<int32_t> idx(n_indices);
+    for (int64_t i = 0; i < n_indices; ++i) idx[i] = (int32_t)i;
+    for (int h = 0; h < H; ++h) {
+        for (int i = 0; i < 3; ++i) {
+            const uint32_t r = rng() >> 1;
+            std::swap(idx[i], idx[i + (r % (n_indices - i))]);
+        }
+        for (int i = 0; i < 3; ++i) triplets_out[3 * h + i] = idx[i];
+    }
+    return 0;
+}
+
+int orc_pose_eval(const double* pc_corners, const double* img_norm, int F, int C,
+                  const double Tcl[7], double* residuals, double* jac6)
+{
+    for (int f = 0; f < F; ++f)
+        pose_block(Tcl, pc_corners + (size_t)f * C * 3, img_norm + (size_t)f * C * 2, C, &residuals[f],
+                   jac6 ? &jac6[6 * f] : nullptr);
+    return 0;
+}
+
+// include/opt/opt_reprj_calib.h:21-66
+int orc_pose_refine(const rclc_config* cfg, const double* pc_corners, const double* img_norm, int F, int C,
+                    double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations)
+{
+    orc::LMProblem P;
+    P.m = F; P.n = 7; P.nl = 6;
+    const double huber_a = cfg->pose_huber_a;
+    P.evaluate = [&](const double* x, double* cost, double* r, double* j) {
+        double total = 0;
+        for (int f = 0; f < F; ++f) {
+            double rr, j6[6];
+            pose_block(x, pc_corners + (size_t)f * C * 3, img_norm + (size_t)f * C * 2, C, &rr, j ? j6 : nullptr);
+            if (!std::isfinite(rr)) return false;
+            if (j) for (int c = 0; c < 6; ++c) if (!std::isfinite(j6[c])) return false;
+            total += orc::apply_loss_1d(huber_a, &rr, j ? j6 : nullptr, 6);
+            if (r) r[f] = rr;
+            if (j) for (int c = 0; c < 6; ++c) j[f * 6 + c] = j6[c];
+        }
+        *cost = total;
+        return true;
+    };
+    P.plus = [](const double* x, const double* d, double* out) {
+        quat_plus(x, d, out);
+        for (int k = 0; k < 3; ++k) out[4 + k] = x[4 + k] + d[3 + k];
+    };
+    orc::LMOptions opt;
+    opt.linear_solver = orc::DENSE_NORMAL_CHOLESKY;
+    opt.max_num_iterations = cfg->pose_max_lm_iters;
+    opt.function_tolerance = cfg->pose_function_tol;
+    const orc::LMSummary sum = orc::lm_minimize(P, opt, Tcl_io);
+    if (initial_cost) *initial_cost = sum.initial_cost;
+    if (final_cost) *final_cost = sum.final_cost;
+    if (iterations) *iterations = sum.num_iterations;
+    return sum.termination == orc::FAILURE ? 1 : 0;
+}
+
+// apps/Calibrate.cpp:134-148, include/PinholeCam.h:93-110
+int orc_project_colorize(const rclc_config* cfg, const void* pts, int stride, int64_t n, const float T_cl[16],
+                         const uint8_t* bgr, uint8_t* rgb_out, int32_t* pix_out, uint8_t* infov_out)
+{
+    const int W = cfg->cam_width, Hh = cfg->cam_height;
+    for (int64_t k = 0; k < n; ++k) {
+        const float* p = rec(pts, stride, k);
+        float x = p[0], y = p[1], z = p[2];
+        transform_point_f(T_cl, x, y, z);                                                 // Calibrate.cpp:134
+        const double X = x, Y = y, Z = z;
+        const double u = cv_round((X / Z) * cfg->fx + cfg->cx);                           // PinholeCam.h:96-98
+        const double v = cv_round((Y / Z) * cfg->fy + cfg->cy);
+        const bool in = !(u < 0 || v < 0 || u >= W || v >= Hh);                           // :101-110
+        if (pix_out) { pix_out[2 * k] = (int32_t)u; pix_out[2 * k + 1] = (int32_t)v; }
+        if (infov_out) infov_out[k] = in ? 1 : 0;
+        if (in && rgb_out && bgr) {
+            const uint8_t* px = bgr + ((int64_t)(int)v * W + (int)u) * 3;                 // img.at<Vec3b>(pix.y(), pix.x())
+            rgb_out[3 * k + 0] = px[2];
+            rgb_out[3 * k + 1] = px[1];
+            rgb_out[3 * k + 2] = px[0];
+        }
+    }
+    return 0;
+}
+
+int orc_quat_to_R(const double q[4], double R[9])
+{
+    quat_to_R<double>(q[0], q[1], q[2], q[3], R);
+    return 0;
+}
+
+// include/utils.h:422-442
+int orc_R_to_euler(const double R[9], double rpy[3])
+{
+    const double sy = std::sqrt(R[0] * R[0] + R[3] * R[3]);
+    const bool singular = sy < 1e-6;
+    if (!singular) {
+        rpy[0] = std::atan2(R[7], R[8]);
+        rpy[1] = std::atan2(-R[6], sy);
+        rpy[2] = std::atan2(R[3], R[0]);
+    } else {
+        rpy[0] = std::atan2(-R[5], R[4]);
+        rpy[1] = std::atan2(-R[6], sy);
+        rpy[2] = 0;
+    }
+    return 0;
+}
+
+int orc_inverse4(const double T[16], double Tinv[16]) { return inverse4(T, Tinv) ? 0 : 1; }
+
+// include/opt/opt_plane_param.hpp:24-88
+int orc_plane_fit(const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
+                  int32_t* iterations, int64_t* n_used)
+{
+    std::vector<double> xyz;
+    for (int64_t k = 0; k < n; ++k) {
+        if (rec_i(pts, stride, ioff, k) < cfg->plane_reflactive_thd) continue;            // :56 (float < double)
+        const float* p = rec(pts, stride, k);
+        xyz.push_back(p[0]); xyz.push_back(p[1]); xyz.push_back(p[2]);
+    }
+    const int m = (int)(xyz.size() / 3);
+    if (n_used) *n_used = m;
+    double abcd[4] = {0.1, 0.1, 1, 1};                                                    // :49
+    const double huber_a = cfg->plane_huber_a;
+    orc::LMProblem P;
+    P.m = m; P.n = 4; P.nl = 4;
+    P.evaluate = [&](const double* x, double* cost, double* r, double* j) {
+        double total = 0;
+        const double a = x[0], b = x[1], c = x[2], d = x[3];
+        const double nn = a * a + b * b + c * c;
+        const double nrm = std::sqrt(nn);
+        for (int i = 0; i < m; ++i) {
+            const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
+            const double e = a * X + b * Y + c * Z + d;
+            double rr = std::fabs(e) / nrm;                                               // :35-38
+            double j4[4];
+            if (j) {
+                // Jet: d|e| = sign(e) de ; d(1/nrm) = -(a,b,c)/nrm^3
+                const double sg = (e < 0) ? -1.0 : 1.0;   // ceres abs(Jet): f.a < 0 ? -f : f
+                const double ae = std::fabs(e);
+                j4[0] = (sg * X) / nrm - ae * a / (nn * nrm);
+                j4[1] = (sg * Y) / nrm - ae * b / (nn * nrm);
+                j4[2] = (sg * Z) / nrm - ae * c / (nn * nrm);
+                j4[3] = sg / nrm;
+            }
+            if (!std::isfinite(rr)) return false;
+            total += orc::apply_loss_1d(huber_a, &rr, j ? j4 : nullptr, 4);
+            if (r) r[i] = rr;
+            if (j) for (int q = 0; q < 4; ++q) j[i * 4 + q] = j4[q];
+        }
+        *cost = total;
+        return true;
+    };
+    orc::LMOptions opt;                     // :75-77: DENSE_QR, everything else Ceres defaults (50 its, ftol 1e-6)
+    opt.linear_solver = orc::DENSE_QR;
+    const orc::LMSummary sum = orc::lm_minimize(P, opt, abcd);
+    for (int q = 0; q < 4; ++q) plane_out[q] = abcd[q];
+    if (iterations) *iterations = sum.num_iterations;
+    return sum.termination == orc::FAILURE ? 1 : 0;
+}
+
+} // extern "C"

@@ -1,0 +1,242 @@
+"""CPU tests of the oracle against independent numpy restatements of the same reference lines, and
+against ground truth of the synthetic inputs. (The reference has no tests on the hot path.)"""
+import numpy as np
+import pytest
+
+from rclc_b200 import synth
+
+
+def np_evaluate(cfg, pts, pose):
+    """Brute-force numpy restatement of BOARD_FITTING_COST::Evaluate (board_fitting_cost.h:74-262)
+    and update_neighbour_points (:264-280), written independently of oracle/rclc_oracle.cpp."""
+    from oracle import pyoracle as O
+    xy, is_row = O.generate_targets(cfg)
+    side = cfg.gride_side_length
+    nr = cfg.neighbour_radius_rate * side
+    cr = cfg.cost_radius_rate * side
+    gr = cr * np.sqrt(2.0)
+    r2f = np.float32(nr * nr)
+    x, y, z, inten = (pts[:, k] for k in range(4))
+    th = pose[2] * np.pi / 180.0
+    qw, qz = np.cos(th / 2), np.sin(th / 2)
+    tz = 2.0 * qz
+    twz, tzz = tz * qw, tz * qz
+    R00 = 1.0 - tzz; R01 = -twz; R10 = twz; R11 = 1.0 - tzz
+    vx = x.astype(np.float64) + pose[0]
+    vy = y.astype(np.float64) + pose[1]
+    xt = R00 * vx + R01 * vy
+    yt = R10 * vx + R11 * vy
+    I = inten.astype(np.float64)
+    res = np.zeros(len(xy)); jac = np.zeros((len(xy), 3))
+    for t, (tx, ty) in enumerate(xy):
+        dxf = np.float32(tx) - x; dyf = np.float32(ty) - y; dzf = np.float32(0) - z
+        d2f = (dxf * dxf + dyf * dyf) + dzf * dzf
+        nb = d2f < r2f
+        dx = np.maximum(1e-14, np.abs(tx - xt)); dy = np.maximum(1e-14, np.abs(ty - yt))
+        d2 = dx * dx + dy * dy
+        ing = nb & ~(d2 > gr * gr)
+        inc = ing & (d2 < cr * cr)
+        ini = ing & ~(d2 < cr * cr)
+        down = yt > ty; right = xt > tx
+
+        def mean(m):
+            return I[m].sum() / m.sum() if m.sum() else np.nan
+        C_d, C_u, C_l, C_r = mean(inc & down), mean(inc & ~down), mean(inc & ~right), mean(inc & right)
+        dC_d, dC_u, dC_l, dC_r = mean(ini & down), mean(ini & ~down), mean(ini & ~right), mean(ini & right)
+        gx = abs(C_r - dC_r) - abs(C_l - dC_l)
+        gy = abs(C_d - dC_d) - abs(C_u - dC_u)
+        res[t] = 1.0 - np.tanh(abs(C_d - C_u) / 100.0) if is_row[t] else 1.0 - np.tanh(abs(C_r - C_l) / 100.0)
+        d1 = -pose[0] * np.cos(th) - pose[1] * np.sin(th)
+        d2_ = pose[0] * np.sin(th) - pose[1] * np.cos(th)
+        jac[t] = (gx, gy, gx * d1 + gy * d2_)
+    return res, jac
+
+
+@pytest.mark.parametrize("pose", [(0.0, 0.0, 0.0), (0.004, -0.003, 0.7), (-0.02, 0.015, -2.5)])
+@pytest.mark.parametrize("pattern", ["raster", "rosette"])
+def test_evaluate_matches_numpy(oracle, ocfg, pose, pattern):
+    pts = synth.board_frame_cloud(30000, 7, pert=(0.006, 0.004, 0.5), pattern=pattern)
+    r0, j0 = oracle.gridfit_eval(ocfg, pts, pose)
+    r1, j1 = np_evaluate(ocfg, pts, np.array(pose))
+    # sums over <= 2000 doubles in different order: 1e-13 relative on means
+    np.testing.assert_allclose(r0, r1, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(j0, j1, rtol=1e-9, atol=1e-10)
+
+
+def test_evaluate_shipped_board_8x5(oracle, ocfg):
+    """Shipped cfg/config_real.yaml board is 8x5 (asymmetric target lattice, SURVEY C-12)."""
+    import copy
+    cfg = copy.copy(ocfg)
+    cfg.board_height = 5
+    assert cfg.n_targets() == 7 * 5 + 8 * 4
+    pts = synth.board_frame_cloud(30000, 3, W=8, H=5, pert=(0.003, -0.002, 0.2))
+    r0, j0 = oracle.gridfit_eval(cfg, pts, (0.001, 0.002, 0.1))
+    r1, j1 = np_evaluate(cfg, pts, np.array((0.001, 0.002, 0.1)))
+    np.testing.assert_allclose(r0, r1, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(j0, j1, rtol=1e-9, atol=1e-10)
+
+
+def test_empty_halfdisc_gives_nan(oracle, ocfg):
+    """0/0 -> NaN residual (board_fitting_cost.h:211-219, SURVEY C-2): keep only the left half of the board."""
+    pts = synth.board_frame_cloud(20000, 5)
+    pts = pts[pts[:, 0] < -0.05]
+    r, _ = oracle.gridfit_eval(ocfg, pts, (0, 0, 0))
+    assert np.isnan(r).any() and np.isfinite(r).any()
+    rc, corners, rep, _ = oracle.gridfit_solve(ocfg, pts)
+    assert rep.status == 1
+
+
+def test_noise_test_recovery(oracle, ocfg):
+    """The reference's own sanity procedure (apply_noise_test, opt_grid_fitting.h:47-56, yaml:68-71):
+    shift the board by a known (1 cm, 1 cm, 0 deg) and expect the fit to pull the corners back."""
+    pts = synth.board_frame_cloud(60000, 11, pert=(0.01, 0.01, 0.0))
+    rc, corners, rep, _ = oracle.gridfit_solve(ocfg, pts)
+    assert rc == 0 and rep.status == 0
+    assert rep.last_final_cost < rep.first_initial_cost
+    # Corners of the truth lattice expressed in the stored (perturbed) frame: p = truth - t
+    W, H, s = ocfg.board_width, ocfg.board_height, ocfg.gride_side_length
+    fx, fy = ((W - 1) // 2) * s, ((H - 1) // 2) * s
+    exp = np.array([[fx - c * s - 0.01, fy - r * s - 0.01, 0.0] for r in range(H - 1) for c in range(W - 1)])
+    # The translation is recovered to ~1 mm (lattice centre); the yaw is NOT reliably recovered: the
+    # reference's heuristic yaw "Jacobian" (board_fitting_cost.h:252-254) is a linear combination of
+    # the x and y columns, so yaw only moves as a by-product of accepted x/y steps.
+    centre_err = np.linalg.norm(corners.mean(axis=0) - exp.mean(axis=0))
+    assert centre_err < 0.0015, centre_err       # the unfitted lattice is 14 mm off
+    assert rep.outer_iterations <= ocfg.max_iter_time + 1
+
+
+def np_gmm(x, mu, sigma, iters=10):
+    """numpy restatement of GMMFit::fit_1d (src/GMMFit.cpp:29-103)."""
+    x = x.astype(np.float64); mu = np.array(mu, float); sigma = np.array(sigma, float)
+    K = len(mu); pri = np.full(K, 1.0 / K)
+    for _ in range(iters):
+        L = np.stack([1.0 / (sigma[k] * np.sqrt(2 * np.pi)) * np.exp(-1.0 / (2 * sigma[k] ** 2) * (x - mu[k]) * (x - mu[k]))
+                      for k in range(K)], axis=1)
+        px = L @ pri
+        P = L * pri / px[:, None]
+        for k in range(K):
+            den = P[:, k].sum()
+            m = (P[:, k] * x).sum() / den
+            sigma[k] = np.sqrt((P[:, k] * ((x - m) * (x - m))).sum() / den)
+            mu[k] = m
+        pri = P.sum(axis=0) / len(x)
+    return mu, sigma, pri
+
+
+def test_gmm_matches_numpy_and_truth(oracle):
+    pts = synth.board_frame_cloud(50000, 21)
+    mu, sg, pri = oracle.gmm_fit_1d(pts[:, 3], [15, 100], [15, 15])
+    mu1, sg1, pri1 = np_gmm(pts[:, 3], [15, 100], [15, 15])
+    np.testing.assert_allclose(mu, mu1, rtol=1e-11)
+    np.testing.assert_allclose(sg, sg1, rtol=1e-10)
+    np.testing.assert_allclose(pri, pri1, rtol=1e-11)
+    assert abs(mu[0] - 15) < 0.5 and abs(mu[1] - 100) < 1.0 and abs(pri.sum() - 1) < 1e-12
+
+
+def test_plane_project(oracle):
+    rng = np.random.default_rng(3)
+    n = 1000
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 2] = rng.uniform(3, 6, n); pts[:, 0] = rng.uniform(-1, 1, n); pts[:, 1] = rng.uniform(-1, 1, n)
+    plane = np.array([0.1, -0.2, 1.0, -4.5])
+    out = oracle.plane_project(pts, plane)
+    d = out[:, :3].astype(np.float64) @ plane[:3] + plane[3]
+    assert np.abs(d).max() < 5e-6                      # on the plane up to float storage
+    np.testing.assert_allclose(out[:, 0] / out[:, 2], pts[:, 0] / pts[:, 2], rtol=3e-7)   # same ray
+
+
+def test_ransac_counts_and_replay(oracle):
+    rng = np.random.default_rng(5)
+    n = 5000
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = 4.0 + rng.normal(0, 0.01, n); pts[:, 1] = rng.uniform(-1, 1, n); pts[:, 2] = rng.uniform(-1, 1, n)
+    pts[: n // 3, :3] = rng.uniform(-3, 3, (n // 3, 3)) + [4, 0, 0]
+    tr = oracle.ransac_draw_triplets(n, 64)
+    assert tr.min() >= 0 and tr.max() < n and all(len(set(t)) == 3 for t in tr.tolist())
+    planes, valid, counts = oracle.ransac_score(pts, tr, 0.08)
+    for h in range(0, 64, 7):
+        c = planes[h]
+        dot = (c[0] * pts[:, 0] + c[2] * pts[:, 2]) + (c[1] * pts[:, 1] + c[3] * np.float32(1))
+        assert counts[h] == int((np.abs(dot).astype(np.float64) < 0.08).sum())
+        assert abs(np.linalg.norm(c[:3]) - 1) < 1e-6
+        np.testing.assert_array_equal(oracle.plane_select(pts, c, 0.08), (np.abs(dot).astype(np.float64) < 0.08))
+    best, iters = oracle.ransac_replay(counts, valid, n)
+    assert best >= 0 and counts[best] == counts[: iters + 8].max() or counts[best] >= counts[:iters].max()
+    assert iters <= 64
+    mask = oracle.plane_select(pts, planes[best], 0.08)
+    ref, cen = oracle.plane_refine(pts, mask, planes[best])
+    assert abs(abs(ref[0]) - 1) < 1e-3 and abs(cen[0] - 4.0) < 0.2
+
+
+def test_pose_jacobian_and_refine(oracle, ocfg):
+    rng = np.random.default_rng(9)
+    F, Cn = 6, 35
+    # GT extrinsic: small rotation + translation; corners 3-6 m in front (camera frame z forward)
+    q = np.array([0.02, -0.015, 0.01, 0.0]); q[3] = np.sqrt(1 - (q[:3] ** 2).sum())
+    t = np.array([0.07, -0.08, 0.02])
+    R = oracle.quat_to_R([q[3], q[0], q[1], q[2]])
+    pc = np.zeros((F, Cn, 3)); img = np.zeros((F, Cn, 2))
+    for f in range(F):
+        base = np.array([rng.uniform(-1, 1), rng.uniform(-0.6, 0.6), rng.uniform(3.5, 5.5)])
+        g = np.array([[0.3 - 0.1 * c, 0.2 - 0.1 * r, 0.0] for r in range(5) for c in range(7)])
+        a = rng.uniform(-0.3, 0.3, 3)
+        Rb = oracle.quat_to_R(np.r_[np.sqrt(1 - (a ** 2).sum() / 4), a / 2])
+        pc[f] = g @ Rb.T + base
+        Pc = pc[f] @ R.T + t
+        img[f] = Pc[:, :2] / Pc[:, 2:3] + rng.normal(0, 1e-4, (Cn, 2))
+    Tcl = np.r_[q, t]
+    r0, j0 = oracle.pose_eval(pc, img, Tcl)
+    # finite differences in the tangent space of EigenQuaternionParameterization
+    def plus(T, d):
+        dq = d[:3]; nd = np.linalg.norm(dq)
+        if nd > 0:
+            s = np.sin(nd) / nd; dw, dv = np.cos(nd), s * dq
+            xw, xv = T[3], T[:3]
+            w = dw * xw - dv @ xv
+            v = dw * xv + xw * dv + np.cross(dv, xv)
+            qn = np.r_[v, w]
+        else:
+            qn = T[:4]
+        return np.r_[qn, T[4:] + d[3:]]
+    h = 1e-6
+    for c in range(6):
+        d = np.zeros(6); d[c] = h
+        rp, _ = oracle.pose_eval(pc, img, plus(Tcl, d)); rm, _ = oracle.pose_eval(pc, img, plus(Tcl, -d))
+        np.testing.assert_allclose((rp - rm) / (2 * h), j0[:, c], rtol=2e-4, atol=1e-6)
+    # refine from a perturbed start
+    T0 = plus(Tcl, np.array([0.01, -0.008, 0.006, 0.03, -0.02, 0.04]))
+    rc, T1, c0, c1, its = oracle.pose_refine(ocfg, pc, img, T0)
+    assert rc == 0 and c1 < c0
+    assert np.abs(T1[4:] - t).max() < 2e-3 and np.abs(T1[:4] - q).max() < 5e-4
+
+
+def test_project_colorize(oracle, ocfg):
+    pts = synth.frustum_cloud(20000, 2)
+    img = synth.noise_image(4, ocfg.cam_width, ocfg.cam_height)
+    T = np.eye(4, dtype=np.float32); T[0, 3] = 0.05
+    rgb, pix, infov = oracle.project_colorize(ocfg, pts, T, img)
+    X = pts[:, 0] + np.float32(0.05)
+    u = np.rint(X.astype(np.float64) / pts[:, 2] * ocfg.fx + ocfg.cx)
+    v = np.rint(pts[:, 1].astype(np.float64) / pts[:, 2] * ocfg.fy + ocfg.cy)
+    np.testing.assert_array_equal(pix[:, 0], u.astype(np.int32)); np.testing.assert_array_equal(pix[:, 1], v.astype(np.int32))
+    exp_in = (u >= 0) & (v >= 0) & (u < ocfg.cam_width) & (v < ocfg.cam_height)
+    np.testing.assert_array_equal(infov.astype(bool), exp_in)
+    assert 0.3 < exp_in.mean() < 0.95
+    k = np.nonzero(exp_in)[0]
+    np.testing.assert_array_equal(rgb[k], img[v[k].astype(int), u[k].astype(int)][:, ::-1])
+
+
+def test_plane_fit(oracle, ocfg):
+    rng = np.random.default_rng(12)
+    n = 20000
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = rng.uniform(-0.4, 0.4, n); pts[:, 1] = rng.uniform(-0.3, 0.3, n)
+    nrm = np.array([0.15, -0.1, 1.0]); nrm /= np.linalg.norm(nrm)
+    pts[:, 2] = (4.0 - nrm[0] * pts[:, 0] - nrm[1] * pts[:, 1]) / nrm[2] + rng.normal(0, 0.004, n)
+    pts[:, 3] = np.where(rng.uniform(size=n) < 0.5, 15, 110)
+    rc, plane, its, used = oracle.plane_fit(ocfg, pts)
+    assert rc == 0 and used == int((pts[:, 3] >= 100).sum())
+    p = plane / np.linalg.norm(plane[:3])
+    if p[2] < 0: p = -p
+    np.testing.assert_allclose(p[:3], nrm, atol=2e-3)
+    assert abs(-p[3] - 4.0 * 1.0) < 5e-3

@@ -170,7 +170,7 @@ def test_ransac_counts_and_replay(oracle):
 
 def test_pose_jacobian_and_refine(oracle, ocfg):
     rng = np.random.default_rng(9)
-    F, Cn = 6, 35
+    F, Cn = 20, 35       # 5 frames (the reference's cap, Calibrate.cpp:82) is under-determined
     # GT extrinsic: small rotation + translation; corners 3-6 m in front (camera frame z forward)
     q = np.array([0.02, -0.015, 0.01, 0.0]); q[3] = np.sqrt(1 - (q[:3] ** 2).sum())
     t = np.array([0.07, -0.08, 0.02])
@@ -198,7 +198,7 @@ def test_pose_jacobian_and_refine(oracle, ocfg):
         else:
             qn = T[:4]
         return np.r_[qn, T[4:] + d[3:]]
-    h = 1e-6
+    h = 1e-8
     for c in range(6):
         d = np.zeros(6); d[c] = h
         rp, _ = oracle.pose_eval(pc, img, plus(Tcl, d)); rm, _ = oracle.pose_eval(pc, img, plus(Tcl, -d))
@@ -207,7 +207,7 @@ def test_pose_jacobian_and_refine(oracle, ocfg):
     T0 = plus(Tcl, np.array([0.01, -0.008, 0.006, 0.03, -0.02, 0.04]))
     rc, T1, c0, c1, its = oracle.pose_refine(ocfg, pc, img, T0)
     assert rc == 0 and c1 < c0
-    assert np.abs(T1[4:] - t).max() < 2e-3 and np.abs(T1[:4] - q).max() < 5e-4
+    assert np.abs(T1[4:] - t).max() < 1e-3 and np.abs(T1[:4] - q).max() < 1e-4
 
 
 def test_project_colorize(oracle, ocfg):

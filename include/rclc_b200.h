@@ -1,0 +1,134 @@
+/*
+ * rclc_b200.h — C ABI of the B200-native calibration hot path (librclc_b200.so).
+ *
+ * The reference (zhijianglu/RCLC) has no plugin/FFI layer: its operators are header-inline C++
+ * with PCL/Eigen/Ceres types in the signatures. Each entry point below replaces
+ * one of those operators with plain pointers and sizes; the C++ shims in rclc_b200/host/ give them
+ * back the reference's names and argument meaning (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - every function returns an int status (RCLC_OK == 0), never throws, never exits;
+ *  - `rclc_ctx` owns one CUDA stream + scratch, so concurrent host threads (the reference calls its
+ *    operators inside `#pragma omp parallel for` over frames) use one ctx each;
+ *  - point clouds are byte pointers to records of `stride` bytes, float x,y,z at offsets 0,4,8 and
+ *    float intensity at byte offset `ioff` (float4 {x,y,z,I}: 16/12; pcl::PointXYZI: 32/16);
+ *  - functions without a `_dev` suffix take HOST pointers and do their own H2D/D2H copies;
+ *    `rclc_batch_*` keeps frames resident in HBM across calls;
+ *  - there is NO CPU fallback: without a CUDA device every compute call returns RCLC_ERR_CUDA.
+ */
+#ifndef RCLC_B200_H
+#define RCLC_B200_H
+
+#include <stdint.h>
+#include "rclc_config.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    RCLC_OK = 0,
+    RCLC_ERR_CUDA = 1,          /* CUDA runtime error (rclc_last_error_string has details)      */
+    RCLC_ERR_INVALID = 2,       /* bad argument                                                 */
+    RCLC_ERR_UNSUPPORTED = 3,   /* configuration outside what the kernels implement             */
+    RCLC_ERR_NUMERIC = 4        /* NaN residual etc. (the reference would print and carry on)   */
+};
+
+typedef struct rclc_ctx rclc_ctx;
+typedef struct rclc_batch rclc_batch;
+
+/* Mirrors what opt_grid_fitting prints/returns (opt_grid_fitting.h:112-131) plus solver counters. */
+typedef struct rclc_gridfit_report {
+    int32_t outer_iterations;     /* executions of the while body, opt_grid_fitting.h:68        */
+    int32_t status;               /* 0 ok; 1 = a Ceres solve ended in FAILURE (NaN residual)     */
+    int64_t pose_evals;           /* distinct (x,y,yaw) poses at which all residuals were evaluated */
+    int64_t lm_iterations;        /* Ceres iterations summed over outer iterations                */
+    double  first_initial_cost;   /* Summary::initial_cost of the first solve                     */
+    double  last_final_cost;      /* Summary::final_cost of the last solve                        */
+    double  se2_first[3];         /* (x, y, yaw deg) of the first solve                           */
+    float   T_base_laser[16];     /* accumulated float transform, row-major                       */
+} rclc_gridfit_report;
+
+const char* rclc_last_error_string(void);
+int rclc_version(void);
+uint64_t rclc_config_sizeof(void);
+
+/* ---- context ---- */
+int rclc_ctx_create(int device, rclc_ctx** out);
+int rclc_ctx_destroy(rclc_ctx* ctx);
+int rclc_ctx_synchronize(rclc_ctx* ctx);
+void* rclc_ctx_stream(rclc_ctx* ctx);               /* cudaStream_t the ctx launches on          */
+int rclc_ctx_device_info(rclc_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* l2_bytes);
+/* CUDA-event stopwatch on the ctx stream (bench.py times kernels on the stream that launches them). */
+int rclc_ctx_timer_start(rclc_ctx* ctx);
+int rclc_ctx_timer_stop_ms(rclc_ctx* ctx, float* ms_out);   /* records stop, synchronises, returns ms */
+int rclc_ctx_flush_l2(rclc_ctx* ctx);               /* writes a buffer larger than L2            */
+int64_t rclc_ctx_kernel_launches(rclc_ctx* ctx);    /* kernels launched by this ctx so far       */
+
+/* ---- utils.h:286-316 generate_std_corners: col targets then row targets (opt_grid_fitting.h:78-94) ---- */
+int rclc_generate_targets(const rclc_config* cfg, double* targets_xy, int32_t* is_row, int32_t* n_targets);
+
+/* ---- BOARD_FITTING_COST::Evaluate x all targets (board_fitting_cost.h:74-280) at one pose.
+ * residuals[nt], jac[nt*3] (may be NULL), acc[nt*16] (may be NULL): cost sum d,u,l,r | cost count
+ * d,u,l,r | interval sum d,u,l,r | interval count d,u,l,r. ---- */
+int rclc_gridfit_eval(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n,
+                      const double pose[3], double* residuals, double* jac, double* acc);
+
+/* ---- opt_grid_fitting (opt_grid_fitting.h:25-132). T_bl row-major 4x4 in/out; corners (W-1)(H-1) x 3. ---- */
+int rclc_gridfit_solve(rclc_ctx* ctx, const rclc_config* cfg, void* pts_io, int stride, int ioff, int64_t n,
+                       double* T_bl_io, double* corners_out, rclc_gridfit_report* report);
+
+/* ---- frames resident in HBM ---- */
+int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, int64_t max_pts_per_frame, rclc_batch** out);
+int rclc_batch_destroy(rclc_batch* b);
+/* host -> device (pinned staging inside); frame f gets n points */
+int rclc_batch_upload(rclc_batch* b, int32_t frame, const void* pts_host, int stride, int ioff, int64_t n);
+/* device float4 {x,y,z,I} -> batch storage */
+int rclc_batch_set_frame_dev(rclc_batch* b, int32_t frame, const void* pts_dev_float4, int64_t n);
+int64_t rclc_batch_total_points(rclc_batch* b);
+/* bins every frame's cloud by lattice cell (once per cloud state); then single-pose passes */
+int rclc_batch_bin(rclc_batch* b);
+int rclc_batch_sweep(rclc_batch* b, const double* poses /* F*3 */);           /* accumulate only (async) */
+int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* acc); /* F*nt[, *3, *16] */
+/* full solve for all frames (async LM state machine on device); outputs on host */
+int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl /* F*16 or NULL */, double* T_bl_out /* F*16 or NULL */,
+                             double* corners_out /* F*nc*3 */, rclc_gridfit_report* reports /* F */);
+/* K5 on a resident, binned frame: P poses -> robustified cost per pose */
+int rclc_batch_multistart(rclc_batch* b, int32_t frame, const double* poses, int32_t P, double* cost_out);
+/* GMMFit::fit_1d on every frame's intensities; mu/sigma in-out F*2, priors F*2 */
+int rclc_batch_gmm_fit(rclc_batch* b, double* mu_io, double* sigma_io, double* priors_out);
+
+/* ---- GMMFit::fit_1d (src/GMMFit.cpp:7-108), K == 2 ---- */
+int rclc_gmm_fit_1d(rclc_ctx* ctx, const void* intensity, int stride, int64_t n, int K, int iters,
+                    double* mu_io, double* sigma_io, double* priors_out);
+
+/* ---- pc_plane_prj (pc_process.h:41-57), in place ---- */
+int rclc_plane_project(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const double plane[4]);
+/* ---- pcl::transformPointCloud(Matrix4f) in place, row-major T ---- */
+int rclc_transform_cloud(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const float T[16]);
+
+/* ---- PCL SACSegmentation scoring (BoardSegmentation.cpp:64-72,90): H index triplets -> planes, validity, inlier counts ---- */
+int rclc_ransac_plane_score(rclc_ctx* ctx, const void* pts, int stride, int64_t n, const int32_t* triplets, int32_t H,
+                            double thr, float* planes_out, int32_t* valid_out, int32_t* counts_out);
+/* selectWithinDistance mask + optimizeModelCoefficients (centroid, covariance, smallest eigenvector) */
+int rclc_ransac_plane_select(rclc_ctx* ctx, const void* pts, int stride, int64_t n, const float plane[4], double thr,
+                             uint8_t* mask_out, float refined_out[4], float centroid_out[3], int64_t* n_inliers);
+
+/* ---- pose_reprj_opt (opt_reprj_calib.h:21-66). Tcl = (qx,qy,qz,qw,tx,ty,tz) in/out ---- */
+int rclc_pose_eval(rclc_ctx* ctx, const double* pc_corners, const double* img_norm, int32_t F, int32_t C,
+                   const double Tcl[7], double* residuals, double* jac6);
+int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_corners, const double* img_norm,
+                     int32_t F, int32_t C, double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations);
+
+/* ---- colourise loop (Calibrate.cpp:134-148, PinholeCam.h:93-110) ---- */
+int rclc_project_colorize(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int64_t n,
+                          const float T_cl[16], const uint8_t* bgr, uint8_t* rgb_out, int32_t* pix_out, uint8_t* infov_out);
+
+/* ---- multi-start pose search: P poses x one frame -> robustified cost per pose (K5) ---- */
+int rclc_gridfit_multistart(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n,
+                            const double* poses, int32_t P, double* cost_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCLC_B200_H */

@@ -502,7 +502,8 @@ void smallest_eigenvector(const double cov[9], double evec[3])
     for (int k = 0; k < 3; ++k) evec[k] = v[k][best];
 }
 
-inline int cv_round(double v) { return (int)std::nearbyint(v); }   // cvRound: round-half-even (SSE2 cvtsd2si)
+// cvRound: SSE2 cvtsd2si — round-half-even, 0x80000000 ("integer indefinite") for NaN / out of range
+inline int cv_round(double v) { return (std::fabs(v) < 2147483648.0) ? (int)std::nearbyint(v) : INT32_MIN; }
 
 } // namespace
 

@@ -1,0 +1,138 @@
+// api.cu — context lifecycle, timing helpers and small shared host utilities of the C ABI.
+#define RCLC_CONFIG_IMPLEMENTATION
+#include "common.cuh"
+
+namespace rclc {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+
+__global__ void k_pack_passthrough() {}
+
+int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, float4* dst)
+{
+    RCLC_CHECK(stride >= 16 && ioff + 4 <= stride && ioff >= 12, RCLC_ERR_INVALID, "bad stride/ioff");
+    if (n == 0) return RCLC_OK;
+    if (stride == 16 && ioff == 12) {
+        // already float4: a pageable->device copy stages internally; use our pinned buffer for async behaviour
+        RCLC_TRY(ctx->h_pin.reserve((size_t)n * 16));
+        std::memcpy(ctx->h_pin.p, pts, (size_t)n * 16);
+    } else {
+        RCLC_TRY(ctx->h_pin.reserve((size_t)n * 16));
+        float* o = ctx->h_pin.as<float>();
+        const char* src = static_cast<const char*>(pts);
+        for (int64_t k = 0; k < n; ++k) {
+            const char* r = src + k * (int64_t)stride;
+            std::memcpy(o + 4 * k, r, 12);
+            std::memcpy(o + 4 * k + 3, r + ioff, 4);
+        }
+    }
+    RCLC_CUDA(cudaMemcpyAsync(dst, ctx->h_pin.p, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    // the pinned buffer is reused by the next call: wait for the copy
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RCLC_OK;
+}
+
+__global__ void k_fill(float4* p, size_t n, float v)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) p[i] = make_float4(v, v, v, v);
+}
+
+} // namespace rclc
+
+extern "C" {
+
+const char* rclc_last_error_string(void) { return rclc::g_last_error.c_str(); }
+int rclc_version(void) { return 100; }
+uint64_t rclc_config_sizeof(void) { return sizeof(rclc_config); }
+
+int rclc_ctx_create(int device, rclc_ctx** out)
+{
+    RCLC_CHECK(out != nullptr, RCLC_ERR_INVALID, "out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        rclc::set_last_error(std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+        return RCLC_ERR_CUDA;
+    }
+    RCLC_CHECK(device >= 0 && device < count, RCLC_ERR_INVALID, "device index out of range");
+    RCLC_CUDA(cudaSetDevice(device));
+    rclc_ctx* c = new rclc_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    RCLC_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->l2_bytes = prop.l2CacheSize;
+    RCLC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    RCLC_CUDA(cudaEventCreate(&c->ev0));
+    RCLC_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return RCLC_OK;
+}
+
+int rclc_ctx_destroy(rclc_ctx* c)
+{
+    if (!c) return RCLC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_pts.release(); c->d_tmp.release(); c->d_tmp2.release(); c->d_out.release(); c->d_flush.release();
+    c->h_pin.release(); c->h_pin2.release();
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return RCLC_OK;
+}
+
+int rclc_ctx_synchronize(rclc_ctx* c)
+{
+    RCLC_CHECK(c, RCLC_ERR_INVALID, "ctx is null");
+    RCLC_CUDA(cudaStreamSynchronize(c->stream));
+    return RCLC_OK;
+}
+
+void* rclc_ctx_stream(rclc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int rclc_ctx_device_info(rclc_ctx* c, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* l2_bytes)
+{
+    RCLC_CHECK(c, RCLC_ERR_INVALID, "ctx is null");
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (l2_bytes) *l2_bytes = c->l2_bytes;
+    return RCLC_OK;
+}
+
+int rclc_ctx_timer_start(rclc_ctx* c)
+{
+    RCLC_CHECK(c, RCLC_ERR_INVALID, "ctx is null");
+    RCLC_CUDA(cudaEventRecord(c->ev0, c->stream));
+    return RCLC_OK;
+}
+
+int rclc_ctx_timer_stop_ms(rclc_ctx* c, float* ms_out)
+{
+    RCLC_CHECK(c && ms_out, RCLC_ERR_INVALID, "null argument");
+    RCLC_CUDA(cudaEventRecord(c->ev1, c->stream));
+    RCLC_CUDA(cudaEventSynchronize(c->ev1));
+    RCLC_CUDA(cudaEventElapsedTime(ms_out, c->ev0, c->ev1));
+    return RCLC_OK;
+}
+
+int rclc_ctx_flush_l2(rclc_ctx* c)
+{
+    RCLC_CHECK(c, RCLC_ERR_INVALID, "ctx is null");
+    const size_t bytes = (size_t)std::max<int64_t>(c->l2_bytes * 2, 256ll << 20);
+    RCLC_TRY(c->d_flush.reserve(bytes));
+    rclc::k_fill<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_flush.as<float4>(), bytes / 16, 1.0f);
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+int64_t rclc_ctx_kernel_launches(rclc_ctx* c) { return c ? c->launches : 0; }
+
+} // extern "C"

@@ -1,0 +1,194 @@
+// gmm.cu — K3: 1-D, 2-component Gaussian-mixture EM on laser reflectance.
+//
+// Replaces GMMFit::fit_1d (src/GMMFit.cpp:7-108) + GaussianFunction::eval (src/GaussianFunction.cpp:7-23).
+// The reference makes six passes and allocates two N x K matrices per iteration; here an iteration is
+// two streaming passes (posterior + first moments, then second moment about the NEW mean, as
+// GMMFit.cpp:79-85 does) with warp-shuffle / block reductions. Reductions are two-stage and
+// fixed-order (per-CTA partials, last CTA folds them), so results are deterministic.
+#include "gridfit.cuh"
+
+namespace rclc {
+
+constexpr int kGmmThreads = 256;
+constexpr int kGmmMaxCtas = 1184;      // 148 SMs x 8
+
+struct GmmState {          // per frame
+    double mu[2], sigma[2], prior[2];
+    double mu_new[2], denom[2];
+    unsigned int counter;
+    unsigned int pad;
+};
+
+struct GmmView {
+    const float* x;            // intensity base
+    int64_t frame_stride;      // in floats
+    int elem_stride;           // in floats (1 or 4)
+    const int64_t* n_pts;      // [F]
+    GmmState* st;              // [F]
+    double* partials;          // [F][kGmmMaxCtas][4]
+};
+
+// posterior P(k | x) exactly as GMMFit.cpp:45-65 evaluates it (no FMA contraction)
+__device__ __forceinline__ void posterior(double x, const double* mu, const double* inv2s2, const double* factor,
+                                          const double* prior, double& p0, double& p1)
+{
+    const double d0 = __dsub_rn(x, mu[0]), d1 = __dsub_rn(x, mu[1]);
+    const double l0 = __dmul_rn(factor[0], exp(__dmul_rn(__dmul_rn(inv2s2[0], d0), d0)));
+    const double l1 = __dmul_rn(factor[1], exp(__dmul_rn(__dmul_rn(inv2s2[1], d1), d1)));
+    const double a0 = __dmul_rn(l0, prior[0]), a1 = __dmul_rn(l1, prior[1]);
+    const double px = __dadd_rn(a0, a1);
+    p0 = __ddiv_rn(a0, px);
+    p1 = __ddiv_rn(a1, px);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kGmmThreads) k_gmm_pass(GmmView v)
+{
+    const int f = blockIdx.y;
+    const int64_t n = v.n_pts[f];
+    GmmState& st = v.st[f];
+    if (n == 0) return;
+    __shared__ double s_par[12];
+    __shared__ double s_red[kGmmThreads / 32][4];
+    __shared__ bool s_last;
+    if (threadIdx.x < 2) {
+        const int k = threadIdx.x;
+        const double sg = st.sigma[k];
+        s_par[k] = st.mu[k];
+        s_par[2 + k] = __ddiv_rn(-1.0, __dmul_rn(2.0, __dmul_rn(sg, sg)));                 // -1.0 / (2*sigma_sqr)
+        s_par[4 + k] = __ddiv_rn(1.0, __dmul_rn(sg, sqrt(2.0 * 3.14159265358979323846)));  // 1/(sigma*sqrt(2 pi))
+        s_par[6 + k] = st.prior[k];
+        s_par[8 + k] = st.mu_new[k];
+    }
+    __syncthreads();
+    const float* x = v.x + (size_t)f * v.frame_stride;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int64_t i = blockIdx.x * (int64_t)kGmmThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kGmmThreads) {
+        const double xi = (double)__ldg(x + i * v.elem_stride);
+        double p0, p1;
+        posterior(xi, s_par, s_par + 2, s_par + 4, s_par + 6, p0, p1);
+        if (PASS == 0) {
+            a0 += p0; a1 += p1;
+            a2 += __dmul_rn(p0, xi); a3 += __dmul_rn(p1, xi);
+        } else {
+            const double e0 = __dsub_rn(xi, s_par[8]), e1 = __dsub_rn(xi, s_par[9]);
+            a0 += __dmul_rn(p0, __dmul_rn(e0, e0));
+            a1 += __dmul_rn(p1, __dmul_rn(e1, e1));
+        }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[warp][0] = a0; s_red[warp][1] = a1; s_red[warp][2] = a2; s_red[warp][3] = a3; }
+    __syncthreads();
+    double* part = v.partials + ((size_t)f * kGmmMaxCtas + blockIdx.x) * 4;
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int w = 0; w < kGmmThreads / 32; ++w) t += s_red[w][threadIdx.x];
+        part[threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // last CTA: fold the per-CTA partials in a fixed order
+    if (warp == 0) {
+        double t[4] = {0, 0, 0, 0};
+        const double* all = v.partials + (size_t)f * kGmmMaxCtas * 4;
+        for (unsigned int c = lane; c < gridDim.x; c += 32)
+            for (int q = 0; q < 4; ++q) t[q] += all[(size_t)c * 4 + q];
+        for (int q = 0; q < 4; ++q) t[q] = warp_sum(t[q]);
+        if (lane == 0) {
+            if (PASS == 0) {
+                for (int k = 0; k < 2; ++k) { st.denom[k] = t[k]; st.mu_new[k] = t[2 + k] / t[k]; }      // GMMFit.cpp:75-79
+            } else {
+                for (int k = 0; k < 2; ++k) {
+                    st.mu[k] = st.mu_new[k];
+                    st.sigma[k] = sqrt(t[k] / st.denom[k]);                                              // :85-92
+                    st.prior[k] = st.denom[k] / double(n);                                               // :98-101
+                }
+            }
+            st.counter = 0;
+        }
+    }
+}
+
+static int gmm_run(rclc_ctx* ctx, GmmView v, int F, int64_t max_n, int iters)
+{
+    const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>((max_n + kGmmThreads * 8 - 1) / (kGmmThreads * 8), kGmmMaxCtas));
+    for (int it = 0; it < iters; ++it) {
+        k_gmm_pass<0><<<dim3(ctas, F), kGmmThreads, 0, ctx->stream>>>(v);
+        k_gmm_pass<1><<<dim3(ctas, F), kGmmThreads, 0, ctx->stream>>>(v);
+        ctx->launches += 2;
+    }
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+static int gmm_solve(rclc_ctx* ctx, const float* d_x, int64_t frame_stride, int elem_stride, const int64_t* d_npts, int F,
+                     int64_t max_n, int iters, double* mu_io, double* sigma_io, double* priors_out)
+{
+    const size_t st_bytes = sizeof(GmmState) * F, part_bytes = (size_t)F * kGmmMaxCtas * 4 * 8;
+    RCLC_TRY(ctx->d_out.reserve(st_bytes + part_bytes + 256));
+    std::vector<GmmState> h(F);
+    for (int f = 0; f < F; ++f) {
+        std::memset(&h[f], 0, sizeof(GmmState));
+        for (int k = 0; k < 2; ++k) { h[f].mu[k] = mu_io[2 * f + k]; h[f].sigma[k] = sigma_io[2 * f + k]; h[f].prior[k] = 0.5; }
+    }
+    GmmView v;
+    v.x = d_x; v.frame_stride = frame_stride; v.elem_stride = elem_stride; v.n_pts = d_npts;
+    v.st = ctx->d_out.as<GmmState>();
+    v.partials = reinterpret_cast<double*>(static_cast<char*>(ctx->d_out.p) + ((st_bytes + 255) & ~(size_t)255));
+    RCLC_CUDA(cudaMemcpyAsync(v.st, h.data(), st_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));          // h is pageable
+    RCLC_TRY(gmm_run(ctx, v, F, max_n, iters));
+    RCLC_CUDA(cudaMemcpyAsync(h.data(), v.st, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < F; ++f)
+        for (int k = 0; k < 2; ++k) {
+            mu_io[2 * f + k] = h[f].mu[k];
+            sigma_io[2 * f + k] = h[f].sigma[k];
+            if (priors_out) priors_out[2 * f + k] = h[f].prior[k];
+        }
+    return RCLC_OK;
+}
+
+} // namespace rclc
+
+using namespace rclc;
+
+extern "C" {
+
+int rclc_gmm_fit_1d(rclc_ctx* ctx, const void* intensity, int stride, int64_t n, int K, int iters,
+                    double* mu_io, double* sigma_io, double* priors_out)
+{
+    RCLC_CHECK(ctx && intensity && mu_io && sigma_io && n > 0 && stride >= 4, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CHECK(K == 2, RCLC_ERR_UNSUPPORTED, "only K == 2 is implemented (every call site in the reference uses 2)");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    RCLC_TRY(ctx->h_pin.reserve((size_t)n * 4 + 64));
+    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 4 + 64));
+    float* hp = ctx->h_pin.as<float>();
+    const char* src = static_cast<const char*>(intensity);
+    if (stride == 4) std::memcpy(hp, src, (size_t)n * 4);
+    else for (int64_t i = 0; i < n; ++i) std::memcpy(hp + i, src + i * (int64_t)stride, 4);
+    int64_t* h_n = reinterpret_cast<int64_t*>(hp + ((n + 1) & ~(int64_t)1));
+    *h_n = n;
+    char* dbase = static_cast<char*>(ctx->d_pts.p);
+    RCLC_CUDA(cudaMemcpyAsync(dbase, hp, (size_t)n * 4 + 16, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t* d_n = reinterpret_cast<const int64_t*>(dbase + ((n + 1) & ~(int64_t)1) * 4);
+    return gmm_solve(ctx, reinterpret_cast<const float*>(dbase), 0, 1, d_n, 1, n, iters, mu_io, sigma_io, priors_out);
+}
+
+int rclc_batch_gmm_fit(rclc_batch* b, double* mu_io, double* sigma_io, double* priors_out)
+{
+    RCLC_CHECK(b && mu_io && sigma_io, RCLC_ERR_INVALID, "null argument");
+    RCLC_CUDA(cudaSetDevice(b->ctx->device));
+    int64_t max_n = 0;
+    for (int64_t n : b->h_npts) max_n = std::max(max_n, n);
+    // intensity is the .w lane of the resident float4 cloud (pc_process.h:603-606 copies it out; here it is read in place)
+    return gmm_solve(b->ctx, reinterpret_cast<const float*>(b->d_pristine) + 3, b->v.frame_stride * 4, 4, b->d_npts, b->n_frames,
+                     max_n, b->cfg.gmm_iters, mu_io, sigma_io, priors_out);
+}
+
+} // extern "C"

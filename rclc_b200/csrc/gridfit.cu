@@ -1,0 +1,1248 @@
+// gridfit.cu — K4: reflectance-guided grid fitting on device.
+//
+// Replaces, for a batch of frames resident in HBM:
+//   BOARD_FITTING_COST::Evaluate x 82 targets        include/opt/board_fitting_cost.h:74-262
+//   BOARD_FITTING_COST::update_neighbour_points      include/opt/board_fitting_cost.h:264-280 (kd-tree radius search)
+//   ceres::Solve as configured                        include/opt/opt_grid_fitting.h:96-103 (trust-region LM)
+//   opt_grid_fitting outer re-linearisation loop     include/opt/opt_grid_fitting.h:60-131
+//   generate_std_corners / SE2_to_SE3 / calc_transfered_standard_corners   include/utils.h:286-316, 273-284, 47-66
+//
+// Kernels (one launch covers every active frame of the batch; blockIdx.y = frame):
+//   k_count / k_scatter  move the cloud by the last solved SE(2) (float, like pcl::transformPointCloud)
+//                        and counting-sort it into lattice cells with exact per-point neighbour masks
+//   k_sweep              streams 16 B/point, accumulates the 16 sums of every target (HBM-bound)
+//   k_lm                 residuals + heuristic Jacobian + Huber corrector + 3x3 normal equations and the
+//                        Ceres LM accept/reject/radius state machine; also the outer loop bookkeeping
+//
+// Arithmetic that decides class membership is done exactly as the reference does it (double maths on
+// float-stored points, explicit _rn intrinsics so nvcc cannot contract a*b+c into an FMA the x86
+// reference build does not use). Sums of float intensities in double are exact for realistic data, so
+// the accumulator tables do not depend on summation order.
+#include "gridfit.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
+namespace rclc {
+
+// ------------------------------------------------------------------------------------------------
+// Host geometry
+// ------------------------------------------------------------------------------------------------
+struct HostGeom {
+    GridGeom g;
+    std::vector<double2> tgt_xy;
+    std::vector<float2> tgt_xyf;
+    std::vector<uint8_t> is_row;
+    std::vector<int16_t> cell_cand;
+};
+
+// include/utils.h:286-316 — same expressions, same order, so the doubles are bit-identical.
+static void make_targets(const rclc_config& c, std::vector<double2>& xy, std::vector<uint8_t>& is_row)
+{
+    const int bx = c.board_width, by = c.board_height;
+    const int cxid = bx / 2, cyid = by / 2;
+    const double s = c.gride_side_length;
+    const double col_shift_y = double(cyid) * s;
+    const double col_shift_x = double(cxid - 1) * s;
+    for (int cc = 0; cc < bx - 1; ++cc)
+        for (int r = 0; r < by; ++r) {
+            xy.push_back(make_double2(cc * s - col_shift_x, s / 2.0 + r * s - col_shift_y));
+            is_row.push_back(0);
+        }
+    const double row_shift_x = cxid * s;
+    const double row_shift_y = double(cyid - 1) * s;
+    for (int r = 0; r < by - 1; ++r)
+        for (int cc = 0; cc < bx; ++cc) {
+            xy.push_back(make_double2(s / 2.0 + cc * s - row_shift_x, r * s - row_shift_y));
+            is_row.push_back(1);
+        }
+}
+
+static int build_geom(const rclc_config& c, HostGeom& hg)
+{
+    RCLC_CHECK(c.board_width >= 2 && c.board_height >= 2 && c.gride_side_length > 0, RCLC_ERR_INVALID, "bad board size");
+    make_targets(c, hg.tgt_xy, hg.is_row);
+    GridGeom& g = hg.g;
+    g.nt = (int)hg.tgt_xy.size();
+    g.nc = (c.board_width - 1) * (c.board_height - 1);
+    RCLC_CHECK(g.nt <= kMaxTargets, RCLC_ERR_UNSUPPORTED, "too many targets");
+    g.board_w = c.board_width;
+    g.board_h = c.board_height;
+    g.side = c.gride_side_length;
+    // board_fitting_cost.h:41-59
+    const double factor = std::sqrt(2.0);
+    const double neighbour_radius = c.neighbour_radius_rate * c.gride_side_length;
+    double cost_radius = c.cost_radius_rate * c.gride_side_length;
+    double cost_gradient_radius = cost_radius * factor;
+    if (!(neighbour_radius > cost_gradient_radius)) {
+        cost_gradient_radius = 0.9 * neighbour_radius;
+        cost_radius = cost_gradient_radius / factor;
+    }
+    g.rc2 = cost_radius * cost_radius;
+    g.rg2 = cost_gradient_radius * cost_gradient_radius;
+    g.rn2f = static_cast<float>(neighbour_radius * neighbour_radius);
+    g.huber_a = c.gridfit_huber_a;
+    g.function_tol = c.gridfit_function_tol;
+    g.max_lm_iters = c.gridfit_max_lm_iters;
+    g.max_iter_time = c.max_iter_time;
+    // Lattice: all targets sit on odd-parity sites of the half-square lattice (unit g = side/2). The
+    // candidate enumeration below needs every target outside a cell's 4x4 site window to be farther
+    // than the kd-tree radius from any point of the cell: 2 g > neighbour_radius.
+    g.g = c.gride_side_length / 2.0;
+    g.inv_g = 1.0 / g.g;
+    RCLC_CHECK(neighbour_radius < 1.98 * g.g, RCLC_ERR_UNSUPPORTED,
+               "neighbour_radius_rate must be < 0.99 (cell candidate window)");
+    RCLC_CHECK(c.uniform_sampling_radius == 0.0, RCLC_ERR_UNSUPPORTED,
+               "uniform_sampling_radius != 0 is not implemented on device (shipped config uses 0)");
+    int imin = INT32_MAX, imax = INT32_MIN, jmin = INT32_MAX, jmax = INT32_MIN;
+    std::vector<int> si(g.nt), sj(g.nt);
+    for (int t = 0; t < g.nt; ++t) {
+        si[t] = (int)std::lround(hg.tgt_xy[t].x * g.inv_g);
+        sj[t] = (int)std::lround(hg.tgt_xy[t].y * g.inv_g);
+        RCLC_CHECK(std::fabs(hg.tgt_xy[t].x - si[t] * g.g) < 1e-9 && std::fabs(hg.tgt_xy[t].y - sj[t] * g.g) < 1e-9,
+                   RCLC_ERR_UNSUPPORTED, "targets are not on the half-square lattice");
+        imin = std::min(imin, si[t]); imax = std::max(imax, si[t]);
+        jmin = std::min(jmin, sj[t]); jmax = std::max(jmax, sj[t]);
+        hg.tgt_xyf.push_back(make_float2((float)hg.tgt_xy[t].x, (float)hg.tgt_xy[t].y));
+    }
+    g.i0 = imin - 2;
+    g.j0 = jmin - 2;
+    g.ncx = imax - imin + 4;
+    g.ncy = jmax - jmin + 4;
+    g.ncells = g.ncx * g.ncy;
+    RCLC_CHECK(g.ncells <= kMaxCells, RCLC_ERR_UNSUPPORTED, "board too large for the cell table");
+    hg.cell_cand.assign((size_t)g.ncells * kCand, -1);
+    for (int b = 0; b < g.ncy; ++b)
+        for (int a = 0; a < g.ncx; ++a) {
+            const int ia = g.i0 + a, ja = g.j0 + b;     // cell spans sites [ia, ia+1] x [ja, ja+1]
+            int k = 0;
+            for (int t = 0; t < g.nt; ++t) {
+                const int di = si[t] - ia, dj = sj[t] - ja;
+                if (di < -1 || di > 2 || dj < -1 || dj > 2) continue;
+                RCLC_CHECK(k < kCand, RCLC_ERR_UNSUPPORTED, "more than 8 candidate targets per cell");
+                hg.cell_cand[((size_t)b * g.ncx + a) * kCand + k++] = (int16_t)t;
+            }
+        }
+    return RCLC_OK;
+}
+
+static PoseCoef host_pose_coef(const double pose[3])
+{
+    // board_fitting_cost.h:80-82,113 with Eigen's toRotationMatrix for q = (w,0,0,z)
+    PoseCoef pc;
+    const double theta = (pose[2] * double(M_PI)) / (180.0);
+    const double qw = std::cos(theta / 2.0), qz = std::sin(theta / 2.0);
+    const double tz = 2.0 * qz, twz = tz * qw, tzz = tz * qz;
+    pc.r00 = 1.0 - (0.0 + tzz);
+    pc.r01 = 0.0 - twz;
+    pc.r10 = 0.0 + twz;
+    pc.r11 = 1.0 - (0.0 + tzz);
+    pc.tx = pose[0];
+    pc.ty = pose[1];
+    pc.yaw_deg = pose[2];
+    return pc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell_of(const GridGeom& g, float x, float y)
+{
+    const int ci = (int)floor((double)x * g.inv_g) - g.i0;
+    const int cj = (int)floor((double)y * g.inv_g) - g.j0;
+    if (ci < 0 || cj < 0 || ci >= g.ncx || cj >= g.ncy) return -1;
+    return cj * g.ncx + ci;
+}
+
+// FLANN L2_Simple<float> over (x,y,z), kept when dist < radius^2 (board_fitting_cost.h:273).
+__device__ __forceinline__ uint32_t neighbour_mask(const BatchView& bv, int cell, float x, float y, float z)
+{
+    uint32_t m = 0;
+    const int16_t* cand = bv.cell_cand + (size_t)cell * kCand;
+#pragma unroll
+    for (int k = 0; k < kCand; ++k) {
+        const int t = cand[k];
+        if (t < 0) continue;
+        const float2 q = bv.tgt_xyf[t];
+        const float dx = __fsub_rn(q.x, x), dy = __fsub_rn(q.y, y), dz = __fsub_rn(0.0f, z);
+        float r = __fmul_rn(dx, dx);
+        r = __fadd_rn(r, __fmul_rn(dy, dy));
+        r = __fadd_rn(r, __fmul_rn(dz, dz));
+        if (r < bv.geom.rn2f) m |= (1u << k);
+    }
+    return m;
+}
+
+__device__ __forceinline__ void pose_coef_dev(double x, double y, double yaw, PoseCoef& pc)
+{
+    const double theta = __ddiv_rn(__dmul_rn(yaw, 3.14159265358979323846), 180.0);
+    const double half = __ddiv_rn(theta, 2.0);
+    const double qw = cos(half), qz = sin(half);
+    const double tz = __dmul_rn(2.0, qz), twz = __dmul_rn(tz, qw), tzz = __dmul_rn(tz, qz);
+    pc.r00 = __dsub_rn(1.0, tzz);
+    pc.r01 = __dsub_rn(0.0, twz);
+    pc.r10 = twz;
+    pc.r11 = __dsub_rn(1.0, tzz);
+    pc.tx = x;
+    pc.ty = y;
+    pc.yaw_deg = yaw;
+}
+
+// Block-wide exclusive scan of data[0..n) in shared memory (n <= kMaxCells). Returns the total.
+template <int T>
+__device__ int block_exclusive_scan(int* data, int n, int* s_part /* [T] */)
+{
+    const int tid = threadIdx.x;
+    const int per = (n + T - 1) / T;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += data[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over T partials
+    for (int off = 1; off < T; off <<= 1) {
+        int v = (tid >= off) ? s_part[tid - off] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    const int total = s_part[T - 1];
+    int run = s_part[tid] - sum;
+    for (int i = lo; i < hi; ++i) {
+        const int v = data[i];
+        data[i] = run;
+        run += v;
+    }
+    __syncthreads();
+    return total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_init: working copy + control/LM state for a fresh solve (or a fresh binning)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_copy_frames(BatchView bv, const float4* __restrict__ pristine)
+{
+    const int f = blockIdx.y;
+    const int64_t n = bv.n_pts[f];
+    const float4* src = pristine + (size_t)f * bv.frame_stride;
+    float4* dst = bv.raw + (size_t)f * bv.frame_stride;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __ldg(src + i);
+}
+
+__device__ void reset_lm_for_outer(LmState& s, FrameCtl& c)
+{
+    s.phase = PH_EVAL_INIT;
+    for (int k = 0; k < 3; ++k) { s.x[k] = 0; s.cand[k] = 0; s.best[k] = 0; }
+    pose_coef_dev(0.0, 0.0, 0.0, c.pose);
+    c.sweep_active = 1;
+}
+
+__global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*16 or null */)
+{
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nc = bv.geom.ncells;
+    for (int c = tid; c < nc; c += blockDim.x) { bv.hist[(size_t)f * nc + c] = 0; bv.cursor[(size_t)f * nc + c] = 0; }
+    for (int k = tid; k < bv.geom.nt * 16; k += blockDim.x) bv.acc[(size_t)f * bv.geom.nt * 16 + k] = 0.0;
+    if (tid == 0) {
+        FrameCtl& c = bv.ctl[f];
+        LmState& s = bv.lm[f];
+        c.rebin = 1;
+        c.n_items = 0;
+        c.n_binned = 0;
+        for (int k = 0; k < 8; ++k) c.move[k] = 0.f;
+        c.move[0] = 1.f;
+        c.move[5] = 1.f;
+        s.outer_iter = 0;
+        s.status = 0;
+        for (int k = 0; k < 16; ++k) {
+            s.T_base_laser[k] = (k % 5 == 0) ? 1.f : 0.f;
+            s.T_bl[k] = T_bl ? T_bl[(size_t)f * 16 + k] : ((k % 5 == 0) ? 1.0 : 0.0);
+        }
+        s.rep.outer_iterations = 0; s.rep.status = 0; s.rep.pose_evals = 0; s.rep.lm_iterations = 0;
+        s.rep.first_initial_cost = 0; s.rep.last_final_cost = 0;
+        for (int k = 0; k < 3; ++k) s.rep.se2_first[k] = 0;
+        reset_lm_for_outer(s, c);
+        if (bv.n_pts[f] == 0) { s.phase = PH_DONE; c.sweep_active = 0; c.rebin = 0; s.status = 2; s.rep.status = 2; atomicAdd(bv.n_done, 1); }
+        if (f == 0 && false) *bv.n_done = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count / k_scatter: move (float) + counting sort by lattice cell
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
+{
+    const int f = blockIdx.y;
+    const FrameCtl& c = bv.ctl[f];
+    if (!c.rebin) return;
+    const int64_t n = bv.n_pts[f];
+    const int64_t base = (int64_t)blockIdx.x * kBinChunk;
+    if (base >= n) return;
+    __shared__ int s_hist[kMaxCells];
+    const int nc = bv.geom.ncells;
+    for (int k = threadIdx.x; k < nc; k += kBinThreads) s_hist[k] = 0;
+    __syncthreads();
+    const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
+    const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
+    const float4* src = bv.raw + (size_t)f * bv.frame_stride;
+#pragma unroll
+    for (int p = 0; p < kBinP; ++p) {
+        const int64_t idx = base + p * kBinThreads + threadIdx.x;
+        if (idx < n) {
+            const float4 q = __ldg(src + idx);
+            const float x = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
+            const float y = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
+            const int cell = cell_of(bv.geom, x, y);
+            if (cell >= 0) atomicAdd(&s_hist[cell], 1);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nc; k += kBinThreads)
+        if (s_hist[k]) atomicAdd(&bv.hist[(size_t)f * nc + k], s_hist[k]);
+}
+
+__global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
+{
+    const int f = blockIdx.y;
+    FrameCtl& c = bv.ctl[f];
+    if (!c.rebin) return;
+    const int64_t n = bv.n_pts[f];
+    const int64_t base = (int64_t)blockIdx.x * kBinChunk;
+    if (base >= n && blockIdx.x != 0) return;
+    __shared__ int s_off[kMaxCells];
+    __shared__ int s_loc[kMaxCells];
+    __shared__ int s_part[kBinThreads];
+    const int nc = bv.geom.ncells;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < nc; k += kBinThreads) { s_off[k] = bv.hist[(size_t)f * nc + k]; s_loc[k] = 0; }
+    __syncthreads();
+    const int total = block_exclusive_scan<kBinThreads>(s_off, nc, s_part);
+
+    const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
+    const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
+    float4* raw = bv.raw + (size_t)f * bv.frame_stride;
+    float4* dstb = bv.binned + (size_t)f * bv.frame_stride;
+    float px[kBinP], py[kBinP], pz[kBinP], pi[kBinP];
+    int pcell[kBinP], prank[kBinP];
+#pragma unroll
+    for (int p = 0; p < kBinP; ++p) {
+        const int64_t idx = base + p * kBinThreads + tid;
+        pcell[p] = -1;
+        if (idx < n) {
+            const float4 q = raw[idx];
+            px[p] = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
+            py[p] = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
+            pz[p] = q.z;
+            pi[p] = q.w;
+            raw[idx] = make_float4(px[p], py[p], pz[p], pi[p]);
+            pcell[p] = cell_of(bv.geom, px[p], py[p]);
+            if (pcell[p] >= 0) prank[p] = atomicAdd(&s_loc[pcell[p]], 1);
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < nc; k += kBinThreads) {
+        const int cnt = s_loc[k];
+        if (cnt) s_loc[k] = atomicAdd(&bv.cursor[(size_t)f * nc + k], cnt);     // base of this CTA inside the cell
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < kBinP; ++p) {
+        if (pcell[p] >= 0) {
+            const int dst = s_off[pcell[p]] + s_loc[pcell[p]] + prank[p];
+            const uint32_t mask = neighbour_mask(bv, pcell[p], px[p], py[p], pz[p]);
+            dstb[dst] = make_float4(px[p], py[p], pi[p], __uint_as_float(mask));
+        }
+    }
+    if (blockIdx.x == 0) {
+        // work items: chunks of <= kChunk points of one cell
+        __syncthreads();
+        for (int k = tid; k < nc; k += kBinThreads) {
+            const int cnt = bv.hist[(size_t)f * nc + k];
+            s_loc[k] = (cnt + kChunk - 1) / kChunk;
+        }
+        __syncthreads();
+        // s_off must survive: scan s_loc into item offsets
+        const int n_items = block_exclusive_scan<kBinThreads>(s_loc, nc, s_part);
+        int4* items = bv.items + (size_t)f * bv.max_items;
+        for (int k = tid; k < nc; k += kBinThreads) {
+            const int cnt = bv.hist[(size_t)f * nc + k];
+            int pos = s_loc[k];
+            for (int j = 0; j * kChunk < cnt; ++j)
+                items[pos++] = make_int4(k, s_off[k] + j * kChunk, min(kChunk, cnt - j * kChunk), 0);
+        }
+        if (tid == 0) { c.n_items = n_items; c.n_binned = total; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sweep: the hot loop. One CTA = one chunk (<= kChunk points) of one lattice cell.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSweepThreads) k_sweep(BatchView bv)
+{
+    const int f = blockIdx.y;
+    const FrameCtl& c = bv.ctl[f];
+    if (!c.sweep_active) return;
+    const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;      // frame whose points are read
+    const int item = blockIdx.x;
+    if (item >= c.n_items) return;
+    const int4 it = bv.items[(size_t)fd * bv.max_items + item];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSweepThreads / 32;
+
+    __shared__ double s_part[NW][kCand][16];
+    __shared__ int s_tid[kCand];
+    __shared__ double s_rx[kCand], s_ry[kCand];
+    if (tid < kCand) {
+        const int t = bv.cell_cand[(size_t)it.x * kCand + tid];
+        s_tid[tid] = t;
+        if (t >= 0) { const double2 r = bv.tgt_xy[t]; s_rx[tid] = r.x; s_ry[tid] = r.y; }
+    }
+    for (int k = tid; k < NW * kCand * 16; k += kSweepThreads) (&s_part[0][0][0])[k] = 0.0;
+
+    const PoseCoef pc = c.pose;
+    const double rg2 = bv.geom.rg2, rc2 = bv.geom.rc2;
+    const float4* src = bv.binned + (size_t)fd * bv.frame_stride + it.y;
+    double xt[kSweepP], yt[kSweepP];
+    float inten[kSweepP];
+    uint32_t mk[kSweepP];
+    uint32_t any_mask = 0;
+#pragma unroll
+    for (int p = 0; p < kSweepP; ++p) {
+        const int idx = p * kSweepThreads + tid;
+        mk[p] = 0;
+        xt[p] = 0; yt[p] = 0; inten[p] = 0;
+        if (idx < it.z) {
+            const float4 q = __ldg(src + idx);
+            // board_fitting_cost.h:132-133  R * (p + t), double maths on float-stored points
+            const double vx = __dadd_rn((double)q.x, pc.tx), vy = __dadd_rn((double)q.y, pc.ty);
+            xt[p] = __dadd_rn(__dmul_rn(pc.r00, vx), __dmul_rn(pc.r01, vy));
+            yt[p] = __dadd_rn(__dmul_rn(pc.r10, vx), __dmul_rn(pc.r11, vy));
+            inten[p] = q.z;
+            mk[p] = __float_as_uint(q.w);
+            any_mask |= mk[p];
+        }
+    }
+    any_mask = __reduce_or_sync(0xffffffffu, any_mask);
+    __syncthreads();
+
+    for (int k = 0; k < kCand; ++k) {
+        if (s_tid[k] < 0 || !((any_mask >> k) & 1u)) continue;          // warp-uniform
+        const double ref_x = s_rx[k], ref_y = s_ry[k];
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;   // cost d,u,l,r | interval d,u,l,r
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+#pragma unroll
+        for (int p = 0; p < kSweepP; ++p) {
+            if (!((mk[p] >> k) & 1u)) continue;
+            const double dx = fmax(1e-14, fabs(__dsub_rn(ref_x, xt[p])));          // :138-139
+            const double dy = fmax(1e-14, fabs(__dsub_rn(ref_y, yt[p])));
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));     // :140
+            if (d2 > rg2) continue;                                                // :142
+            const bool in_cost = d2 < rc2;                                         // :151
+            const bool down = yt[p] > ref_y;                                       // :147
+            const bool right = xt[p] > ref_x;                                      // :178
+            const double I = (double)inten[p];
+            if (in_cost) {
+                if (down) { s0 += I; c0++; } else { s1 += I; c1++; }
+                if (right) { s3 += I; c3++; } else { s2 += I; c2++; }
+            } else {
+                if (down) { s4 += I; c4++; } else { s5 += I; c5++; }
+                if (right) { s7 += I; c7++; } else { s6 += I; c6++; }
+            }
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        s4 = warp_sum(s4); s5 = warp_sum(s5); s6 = warp_sum(s6); s7 = warp_sum(s7);
+        c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3);
+        c4 = warp_sum(c4); c5 = warp_sum(c5); c6 = warp_sum(c6); c7 = warp_sum(c7);
+        if (lane == 0) {
+            double* o = s_part[warp][k];
+            o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = c0; o[5] = c1; o[6] = c2; o[7] = c3;
+            o[8] = s4; o[9] = s5; o[10] = s6; o[11] = s7; o[12] = c4; o[13] = c5; o[14] = c6; o[15] = c7;
+        }
+    }
+    __syncthreads();
+    {
+        const int k = tid >> 4, j = tid & 15;                       // 128 threads == 8 candidates x 16 accumulators
+        const int t = s_tid[k];
+        if (t >= 0) {
+            double v = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += s_part[w][k][j];
+            if (v != 0.0) atomicAdd(&bv.acc[((size_t)f * bv.geom.nt + t) * 16 + j], v);
+        }
+    }
+}
+static_assert(kSweepThreads == kCand * 16, "final reduction maps one thread to one (candidate, accumulator)");
+
+// ------------------------------------------------------------------------------------------------
+// Residual / Jacobian of one target from its 16 accumulators (board_fitting_cost.h:211-260)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void target_residual(const double* a, bool is_row, double tx, double ty, double cth, double sth,
+                                                double& r, double& j0, double& j1, double& j2)
+{
+    const double C_d = a[0] / a[4], C_u = a[1] / a[5], C_l = a[2] / a[6], C_r = a[3] / a[7];
+    const double dC_d = a[8] / a[12], dC_u = a[9] / a[13], dC_l = a[10] / a[14], dC_r = a[11] / a[15];
+    const double cost_ud = fabs(C_d - C_u);
+    const double cost_lr = fabs(C_r - C_l);
+    const double gradient_x = fabs(C_r - dC_r) - fabs(C_l - dC_l);
+    const double gradient_y = fabs(C_d - dC_d) - fabs(C_u - dC_u);
+    r = is_row ? 1.0 - tanh(cost_ud / 100.0) : 1.0 - tanh(cost_lr / 100.0);
+    const double dp1 = __dsub_rn(__dmul_rn(-tx, cth), __dmul_rn(ty, sth));
+    const double dp2 = __dsub_rn(__dmul_rn(tx, sth), __dmul_rn(ty, cth));
+    j0 = gradient_x;
+    j1 = gradient_y;
+    j2 = __dadd_rn(__dmul_rn(gradient_x, dp1), __dmul_rn(gradient_y, dp2));
+}
+
+__global__ void k_eval_out(BatchView bv)
+{
+    const int f = blockIdx.x;
+    const PoseCoef pc = bv.ctl[f].pose;
+    const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
+    const double cth = cos(theta), sth = sin(theta);
+    for (int t = threadIdx.x; t < bv.geom.nt; t += blockDim.x) {
+        double r, j0, j1, j2;
+        target_residual(bv.acc + ((size_t)f * bv.geom.nt + t) * 16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
+        double* o = bv.eval_out + ((size_t)f * bv.geom.nt + t) * 4;
+        o[0] = r; o[1] = j0; o[2] = j1; o[3] = j2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_lm: Ceres trust-region LM as a resumable state machine (one CTA per frame)
+// ------------------------------------------------------------------------------------------------
+struct EvalSums { double cost; double A[6]; double b[3]; int res_valid; int jac_valid; };
+
+__device__ void se2_to_se3f_dev(double x, double y, double yaw, float T[16])
+{
+    PoseCoef pc;
+    pose_coef_dev(x, y, yaw, pc);       // same quaternion matrix as utils.h:273-284
+    for (int k = 0; k < 16; ++k) T[k] = (k % 5 == 0) ? 1.f : 0.f;
+    T[0] = (float)pc.r00; T[1] = (float)pc.r01; T[4] = (float)pc.r10; T[5] = (float)pc.r11;
+    T[3] = (float)x;
+    T[7] = (float)y;
+}
+
+__device__ void mat4f_mul_dev(const float* A, const float* B, float* C)
+{
+    float out[16];
+    for (int r = 0; r < 4; ++r)
+        for (int cc = 0; cc < 4; ++cc) {
+            float s = __fmul_rn(A[r * 4 + 0], B[0 * 4 + cc]);
+            s = __fadd_rn(s, __fmul_rn(A[r * 4 + 1], B[1 * 4 + cc]));
+            s = __fadd_rn(s, __fmul_rn(A[r * 4 + 2], B[2 * 4 + cc]));
+            s = __fadd_rn(s, __fmul_rn(A[r * 4 + 3], B[3 * 4 + cc]));
+            out[r * 4 + cc] = s;
+        }
+    for (int k = 0; k < 16; ++k) C[k] = out[k];
+}
+
+__device__ bool inverse4_dev(const double* m, double* o)
+{
+    double inv[16];
+    inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+    inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+    inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+    inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+    inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+    inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+    inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+    inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+    inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+    inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+    inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+    inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+    inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+    inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+    inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+    inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    if (det == 0) return false;
+    const double id = 1.0 / det;
+    for (int i = 0; i < 16; i++) o[i] = inv[i] * id;
+    return true;
+}
+
+// Solve (As + diag(l^2)) y = bs for a 3x3 SPD system by Cholesky. Returns false on a non-positive pivot.
+__device__ bool chol3_solve(const double* A6 /*00,01,02,11,12,22*/, const double* l, const double* b, double* y)
+{
+    const double a00 = A6[0] + l[0] * l[0], a01 = A6[1], a02 = A6[2];
+    const double a11 = A6[3] + l[1] * l[1], a12 = A6[4], a22 = A6[5] + l[2] * l[2];
+    if (!(a00 > 0.0)) return false;
+    const double L00 = sqrt(a00), L10 = a01 / L00, L20 = a02 / L00;
+    const double d1 = a11 - L10 * L10;
+    if (!(d1 > 0.0)) return false;
+    const double L11 = sqrt(d1), L21 = (a12 - L20 * L10) / L11;
+    const double d2 = a22 - L20 * L20 - L21 * L21;
+    if (!(d2 > 0.0)) return false;
+    const double L22 = sqrt(d2);
+    const double z0 = b[0] / L00;
+    const double z1 = (b[1] - L10 * z0) / L11;
+    const double z2 = (b[2] - L20 * z0 - L21 * z1) / L22;
+    y[2] = z2 / L22;
+    y[1] = (z1 - L21 * y[2]) / L11;
+    y[0] = (z0 - L10 * y[1] - L20 * y[2]) / L00;
+    return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]);
+}
+
+__device__ void accept_eval(LmState& s, const EvalSums& e)
+{
+    s.x_cost = e.cost;
+    for (int k = 0; k < 6; ++k) s.Au[k] = e.A[k];
+    for (int k = 0; k < 3; ++k) s.bu[k] = e.b[k];
+    // gradient_max_norm = |x - Plus(x, -g)|_inf  (trust_region_minimizer.cc EvaluateGradientAndJacobian)
+    double gm = 0;
+    for (int k = 0; k < 3; ++k) {
+        const double xp = s.x[k] + (-e.b[k]);
+        gm = fmax(gm, fabs(s.x[k] - xp));
+    }
+    s.gmax = gm;
+}
+
+// Runs on one thread. Consumes the evaluation of ctl.pose and advances until the next pose needs a
+// sweep, the frame needs a re-bin, or the frame is done.
+__device__ void lm_advance(const GridGeom& g, LmState& s, FrameCtl& c, const EvalSums& e, double* corners, int* n_done)
+{
+    enum { T_CONV = 0, T_NOCONV = 1, T_FAIL = 2 };
+    bool terminate = false;
+    int term = T_CONV;
+    bool initial_failure = false;
+    s.rep.pose_evals++;
+    if (s.phase == PH_EVAL_INIT) {
+        c.rebin = 0;
+        s.n_lm_iterations_this_solve = 0;
+        if (!e.res_valid || !e.jac_valid) {
+            s.initial_cost = nan("");
+            s.min_iter_cost = nan("");
+            terminate = true; term = T_FAIL; initial_failure = true;
+        } else {
+            accept_eval(s, e);
+            for (int k = 0; k < 3; ++k) {
+                const double cn = (k == 0) ? e.A[0] : (k == 1) ? e.A[3] : e.A[5];
+                s.scale[k] = 1.0 / (1.0 + sqrt(cn));                              // jacobi scaling, computed once
+            }
+            s.initial_cost = s.x_cost;
+            s.min_iter_cost = s.x_cost;
+            s.minimum_cost = DBL_MAX;
+            s.step_is_successful = 1;
+            s.iteration = 0;
+            s.radius = 1e4;
+            s.decrease_factor = 2.0;
+            s.reuse_diagonal = 0;
+            s.num_consecutive_invalid = 0;
+            s.x_norm = 0.0;
+        }
+    } else {
+        const double cand_cost = e.res_valid ? e.cost : DBL_MAX;
+        double sn = 0;
+        for (int k = 0; k < 3; ++k) sn += (s.x[k] - s.cand[k]) * (s.x[k] - s.cand[k]);
+        if (sqrt(sn) <= 1e-8 * (s.x_norm + 1e-8)) { terminate = true; term = T_CONV; }               // parameter tolerance
+        else if (fabs(s.x_cost - cand_cost) <= g.function_tol * s.x_cost) { terminate = true; term = T_CONV; }   // function tolerance
+        else {
+            const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : (s.x_cost - cand_cost) / s.model_cost_change;
+            if (rel > 1e-3) {
+                for (int k = 0; k < 3; ++k) s.x[k] = s.cand[k];
+                s.x_norm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2]);
+                if (!e.jac_valid) { terminate = true; term = T_FAIL; }
+                else {
+                    accept_eval(s, e);
+                    s.step_is_successful = 1;
+                    const double q = 2.0 * rel - 1.0;
+                    s.radius = s.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+                    s.radius = fmin(1e16, s.radius);
+                    s.decrease_factor = 2.0;
+                    s.reuse_diagonal = 0;
+                    s.min_iter_cost = fmin(s.min_iter_cost, s.x_cost);
+                }
+            } else {
+                s.min_iter_cost = fmin(s.min_iter_cost, cand_cost);
+                s.radius = s.radius / s.decrease_factor;
+                s.decrease_factor *= 2.0;
+                s.reuse_diagonal = 1;
+                s.step_is_successful = 0;
+            }
+        }
+    }
+    while (!terminate) {
+        // FinalizeIterationAndCheckIfMinimizerCanContinue
+        if (s.step_is_successful && s.x_cost < s.minimum_cost) {
+            s.minimum_cost = s.x_cost;
+            for (int k = 0; k < 3; ++k) s.best[k] = s.x[k];
+        }
+        s.n_lm_iterations_this_solve++;
+        if (s.iteration >= g.max_lm_iters) { terminate = true; term = T_NOCONV; break; }
+        if (s.step_is_successful && s.gmax <= 1e-10) { terminate = true; term = T_CONV; break; }
+        if (s.radius <= 1e-32) { terminate = true; term = T_CONV; break; }
+        s.iteration++;
+        s.step_is_successful = 0;
+        // LevenbergMarquardtStrategy::ComputeStep on the jacobi-scaled normal equations
+        double As[6], bs[3], l[3], y[3];
+        const double* sc = s.scale;
+        As[0] = s.Au[0] * sc[0] * sc[0]; As[1] = s.Au[1] * sc[0] * sc[1]; As[2] = s.Au[2] * sc[0] * sc[2];
+        As[3] = s.Au[3] * sc[1] * sc[1]; As[4] = s.Au[4] * sc[1] * sc[2]; As[5] = s.Au[5] * sc[2] * sc[2];
+        for (int k = 0; k < 3; ++k) bs[k] = s.bu[k] * sc[k];
+        if (!s.reuse_diagonal) {
+            s.diag[0] = fmin(fmax(As[0], 1e-6), 1e32);
+            s.diag[1] = fmin(fmax(As[3], 1e-6), 1e32);
+            s.diag[2] = fmin(fmax(As[5], 1e-6), 1e32);
+        }
+        for (int k = 0; k < 3; ++k) l[k] = sqrt(s.diag[k] / s.radius);
+        bool valid = chol3_solve(As, l, bs, y);
+        s.reuse_diagonal = 1;
+        double mcc = 0;
+        double step[3];
+        if (valid) {
+            for (int k = 0; k < 3; ++k) step[k] = -y[k];
+            // model_cost_change = -(J step)'(r + J step / 2) = -(step'bs + step' As step / 2)
+            const double sAs = step[0] * (As[0] * step[0] + As[1] * step[1] + As[2] * step[2]) +
+                               step[1] * (As[1] * step[0] + As[3] * step[1] + As[4] * step[2]) +
+                               step[2] * (As[2] * step[0] + As[4] * step[1] + As[5] * step[2]);
+            mcc = -((step[0] * bs[0] + step[1] * bs[1] + step[2] * bs[2]) + 0.5 * sAs);
+            valid = mcc > 0.0;
+        }
+        if (!valid) {
+            if (++s.num_consecutive_invalid >= 5) { terminate = true; term = T_FAIL; break; }
+            s.radius *= 0.5;
+            s.min_iter_cost = fmin(s.min_iter_cost, s.x_cost);
+            continue;
+        }
+        s.num_consecutive_invalid = 0;
+        s.model_cost_change = mcc;
+        for (int k = 0; k < 3; ++k) s.cand[k] = s.x[k] + step[k] * sc[k];
+        pose_coef_dev(s.cand[0], s.cand[1], s.cand[2], c.pose);
+        c.sweep_active = 1;
+        s.phase = PH_EVAL_CAND;
+        return;
+    }
+
+    // ---- inner solve finished: opt_grid_fitting.h:105-125 ----
+    const double final_cost = fmin(s.initial_cost, s.min_iter_cost);
+    double xo[3] = {0.0, 0.0, 0.0};
+    if (term != T_FAIL) for (int k = 0; k < 3; ++k) xo[k] = s.best[k];
+    float Tw[16];
+    se2_to_se3f_dev(xo[0], xo[1], xo[2], Tw);
+    const double rate = (s.initial_cost - final_cost) / s.initial_cost;
+    s.outer_iter++;
+    if (s.outer_iter == 1) {
+        s.rep.first_initial_cost = s.initial_cost;
+        for (int k = 0; k < 3; ++k) s.rep.se2_first[k] = xo[k];
+    }
+    s.rep.last_final_cost = final_cost;
+    s.rep.lm_iterations += s.n_lm_iterations_this_solve;
+    if (term == T_FAIL) { s.status = 1; s.rep.status = 1; }
+    if (initial_failure) {
+        // x stays (0,0,0) -> identity move -> every remaining outer iteration repeats this failure.
+        const int remaining = g.max_iter_time + 1 - s.outer_iter;
+        if (remaining > 0) { s.rep.pose_evals += remaining; s.outer_iter += remaining; }
+    }
+    const bool quit = (fabs(rate) < 1e-6) || (s.outer_iter > g.max_iter_time);
+    if (quit) {
+        if (rate > 0) mat4f_mul_dev(Tw, s.T_base_laser, s.T_base_laser);
+        double Tb[16], Fm[16], Fi[16];
+        for (int k = 0; k < 16; ++k) Tb[k] = (double)s.T_base_laser[k];
+        for (int r = 0; r < 4; ++r)
+            for (int cc = 0; cc < 4; ++cc) {
+                double v = 0;
+                for (int k = 0; k < 4; ++k) v += Tb[r * 4 + k] * s.T_bl[k * 4 + cc];
+                Fm[r * 4 + cc] = v;
+            }
+        if (!inverse4_dev(Fm, Fi)) { s.status = 3; s.rep.status = 3; for (int k = 0; k < 16; ++k) Fi[k] = nan(""); }
+        // utils.h:47-66
+        const double sd = g.side;
+        const double fcx = double(int((g.board_w - 1) / 2)) * sd, fcy = double(int((g.board_h - 1) / 2)) * sd;
+        int kk = 0;
+        for (int row = 0; row < g.board_h - 1; ++row)
+            for (int col = 0; col < g.board_w - 1; ++col) {
+                const double p[4] = {fcx - double(col) * sd, fcy - double(row) * sd, 0.0, 1.0};
+                for (int r = 0; r < 3; ++r) {
+                    double v = 0;
+                    for (int q = 0; q < 4; ++q) v += Fi[r * 4 + q] * p[q];
+                    corners[kk * 3 + r] = v;
+                }
+                ++kk;
+            }
+        s.rep.outer_iterations = s.outer_iter;
+        for (int k = 0; k < 16; ++k) s.rep.T_base_laser[k] = s.T_base_laser[k];
+        s.phase = PH_DONE;
+        c.sweep_active = 0;
+        c.rebin = 0;
+        atomicAdd(n_done, 1);
+    } else {
+        mat4f_mul_dev(Tw, s.T_base_laser, s.T_base_laser);
+        c.move[0] = Tw[0]; c.move[1] = Tw[1]; c.move[2] = Tw[2]; c.move[3] = Tw[3];
+        c.move[4] = Tw[4]; c.move[5] = Tw[5]; c.move[6] = Tw[6]; c.move[7] = Tw[7];
+        c.rebin = 1;
+        reset_lm_for_outer(s, c);
+    }
+}
+
+constexpr int kLmThreads = 128;
+
+__global__ void __launch_bounds__(kLmThreads) k_lm(BatchView bv)
+{
+    const int f = blockIdx.x;
+    FrameCtl& c = bv.ctl[f];
+    LmState& s = bv.lm[f];
+    if (s.phase == PH_DONE || !c.sweep_active) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const GridGeom& g = bv.geom;
+    const PoseCoef pc = c.pose;
+    __shared__ double s_red[kLmThreads / 32][12];
+    __shared__ EvalSums s_eval;
+    const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
+    const double cth = cos(theta), sth = sin(theta);
+
+    double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cost, A00,A01,A02,A11,A12,A22, b0,b1,b2
+    int bad_r = 0, bad_j = 0;
+    double* acc = bv.acc + (size_t)f * g.nt * 16;
+    for (int t = tid; t < g.nt; t += kLmThreads) {
+        double r, j0, j1, j2;
+        target_residual(acc + (size_t)t * 16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
+        if (!isfinite(r)) bad_r = 1;
+        if (!(isfinite(j0) && isfinite(j1) && isfinite(j2))) bad_j = 1;
+        // HuberLoss + Corrector (rho'' <= 0 branch): cost 0.5 rho0, r *= sqrt(rho1), J *= sqrt(rho1)
+        const double sq = r * r, bb = g.huber_a * g.huber_a;
+        double rho0, rho1;
+        if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * g.huber_a * rr - bb; rho1 = fmax(DBL_MIN, g.huber_a / rr); }
+        else { rho0 = sq; rho1 = 1.0; }
+        const double w = sqrt(rho1);
+        r *= w; j0 *= w; j1 *= w; j2 *= w;
+        sums[0] += 0.5 * rho0;
+        sums[1] += j0 * j0; sums[2] += j0 * j1; sums[3] += j0 * j2;
+        sums[4] += j1 * j1; sums[5] += j1 * j2; sums[6] += j2 * j2;
+        sums[7] += j0 * r;  sums[8] += j1 * r;  sums[9] += j2 * r;
+    }
+    // consume + clear the accumulator table for the next sweep
+    __syncthreads();
+    for (int k = tid; k < g.nt * 16; k += kLmThreads) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sums[k] = warp_sum(sums[k]);
+    bad_r = __any_sync(0xffffffffu, bad_r);
+    bad_j = __any_sync(0xffffffffu, bad_j);
+    if (lane == 0) {
+        for (int k = 0; k < 10; ++k) s_red[warp][k] = sums[k];
+        s_red[warp][10] = bad_r;
+        s_red[warp][11] = bad_j;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        EvalSums e;
+        double tot[12];
+        for (int k = 0; k < 12; ++k) { tot[k] = 0; for (int w = 0; w < kLmThreads / 32; ++w) tot[k] += s_red[w][k]; }
+        e.cost = tot[0];
+        for (int k = 0; k < 6; ++k) e.A[k] = tot[1 + k];
+        for (int k = 0; k < 3; ++k) e.b[k] = tot[7 + k];
+        e.res_valid = tot[10] == 0.0;
+        e.jac_valid = e.res_valid && tot[11] == 0.0;
+        lm_advance(g, s, c, e, bv.corners + (size_t)f * g.nc * 3, bv.n_done);
+    }
+    __syncthreads();
+    if (c.rebin) {
+        const int nc = g.ncells;
+        for (int k = tid; k < nc; k += kLmThreads) { bv.hist[(size_t)f * nc + k] = 0; bv.cursor[(size_t)f * nc + k] = 0; }
+    }
+}
+
+__global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
+{
+    const int f = blockIdx.x;
+    for (int k = threadIdx.x; k < bv.geom.nt * 16; k += blockDim.x) bv.acc[(size_t)f * bv.geom.nt * 16 + k] = 0.0;
+    if (threadIdx.x == 0) {
+        bv.ctl[f].pose = poses[f];
+        bv.ctl[f].sweep_active = 1;
+        bv.ctl[f].rebin = 0;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// K5: multi-start grid-pose search — P poses x one frame's points -> robustified cost per pose.
+// Not in the reference: cost(p) = sum_k 0.5 * rho_Huber(r_k(p)^2) with r_k from
+// BOARD_FITTING_COST::Evaluate, i.e. what ceres::Problem::Evaluate would report at pose p.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, const PoseCoef* __restrict__ poses, int P, int frame)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    FrameCtl c;
+    c.sweep_active = 1;
+    c.rebin = 0;
+    c.n_items = bv.ctl[frame].n_items;
+    c.n_binned = bv.ctl[frame].n_binned;
+    for (int k = 0; k < 8; ++k) c.move[k] = 0.f;
+    c.pose = poses[p];
+    ctl_ms[p] = c;
+}
+
+__global__ void __launch_bounds__(kLmThreads) k_ms_cost(BatchView bv, double* __restrict__ cost_out)
+{
+    const int p = blockIdx.x;
+    const GridGeom& g = bv.geom;
+    const PoseCoef pc = bv.ctl[p].pose;
+    const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
+    const double cth = cos(theta), sth = sin(theta);
+    __shared__ double s_red[kLmThreads / 32][2];
+    double cost = 0, bad = 0;
+    const double* acc = bv.acc + (size_t)p * g.nt * 16;
+    for (int t = threadIdx.x; t < g.nt; t += kLmThreads) {
+        double r, j0, j1, j2;
+        target_residual(acc + (size_t)t * 16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
+        if (!isfinite(r)) bad = 1.0;
+        const double sq = r * r, bb = g.huber_a * g.huber_a;
+        cost += 0.5 * ((sq > bb) ? (2.0 * g.huber_a * sqrt(sq) - bb) : sq);
+    }
+    cost = warp_sum(cost);
+    bad = warp_sum(bad);
+    if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5][0] = cost; s_red[threadIdx.x >> 5][1] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double c = 0, b = 0;
+        for (int w = 0; w < kLmThreads / 32; ++w) { c += s_red[w][0]; b += s_red[w][1]; }
+        cost_out[p] = (b != 0.0) ? nan("") : c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side of the batch
+// ------------------------------------------------------------------------------------------------
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static dim3 bin_grid(const rclc_batch* b) { return dim3((unsigned)((b->max_pts + kBinChunk - 1) / kBinChunk), (unsigned)b->n_frames); }
+
+static int launch_rebin(rclc_batch* b)
+{
+    cudaStream_t st = b->ctx->stream;
+    k_count<<<bin_grid(b), kBinThreads, 0, st>>>(b->v);
+    k_scatter<<<bin_grid(b), kBinThreads, 0, st>>>(b->v);
+    b->ctx->launches += 2;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+static int launch_sweep(rclc_batch* b)
+{
+    k_sweep<<<dim3((unsigned)b->v.max_items, (unsigned)b->n_frames), kSweepThreads, 0, b->ctx->stream>>>(b->v);
+    b->ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+static int launch_init(rclc_batch* b, const double* d_Tbl)
+{
+    cudaStream_t st = b->ctx->stream;
+    RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, sizeof(int), st));
+    k_copy_frames<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((b->max_pts + 1023) / 1024, 4096)), (unsigned)b->n_frames), 256, 0, st>>>(b->v, b->d_pristine);
+    k_init_state<<<b->n_frames, 256, 0, st>>>(b->v, d_Tbl);
+    b->ctx->launches += 2;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+} // namespace rclc
+
+using namespace rclc;
+
+extern "C" {
+
+int rclc_generate_targets(const rclc_config* cfg, double* targets_xy, int32_t* is_row, int32_t* n_targets)
+{
+    RCLC_CHECK(cfg && targets_xy && is_row && n_targets, RCLC_ERR_INVALID, "null argument");
+    std::vector<double2> xy;
+    std::vector<uint8_t> ir;
+    make_targets(*cfg, xy, ir);
+    for (size_t k = 0; k < xy.size(); ++k) { targets_xy[2 * k] = xy[k].x; targets_xy[2 * k + 1] = xy[k].y; is_row[k] = ir[k]; }
+    *n_targets = (int32_t)xy.size();
+    return RCLC_OK;
+}
+
+int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, int64_t max_pts, rclc_batch** out)
+{
+    RCLC_CHECK(ctx && cfg && out, RCLC_ERR_INVALID, "null argument");
+    RCLC_CHECK(n_frames > 0 && max_pts > 0 && max_pts < (1ll << 31) - kChunk, RCLC_ERR_INVALID, "bad batch shape");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    HostGeom hg;
+    RCLC_TRY(build_geom(*cfg, hg));
+    rclc_batch* b = new rclc_batch();
+    b->ctx = ctx;
+    b->cfg = *cfg;
+    b->n_frames = n_frames;
+    b->max_pts = max_pts;
+    b->h_npts.assign(n_frames, 0);
+    BatchView& v = b->v;
+    v.geom = hg.g;
+    v.n_frames = n_frames;
+    v.fixed_frame = -1;
+    v.frame_stride = (int64_t)align256((size_t)max_pts * 16) / 16;
+    v.max_items = hg.g.ncells + (int)((max_pts + kChunk - 1) / kChunk);
+    const size_t F = n_frames, nt = hg.g.nt, ncell = hg.g.ncells;
+    auto fail = [&](const char* what) { set_last_error(what); rclc_batch_destroy(b); return RCLC_ERR_CUDA; };
+    const size_t big = F * (size_t)v.frame_stride * 16;
+    if (cudaMalloc(&b->d_pristine, big) != cudaSuccess) return fail("cudaMalloc pristine");
+    if (cudaMalloc(&v.raw, big) != cudaSuccess) return fail("cudaMalloc raw");
+    if (cudaMalloc(&v.binned, big) != cudaSuccess) return fail("cudaMalloc binned");
+    // small arrays in one block
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
+    const size_t o_npts = take(F * 8), o_hist = take(F * ncell * 4), o_cur = take(F * ncell * 4);
+    const size_t o_items = take(F * (size_t)v.max_items * 16), o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
+    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_txy = take(nt * 16), o_txyf = take(nt * 8);
+    const size_t o_row = take(nt), o_cand = take(ncell * kCand * 2), o_eval = take(F * nt * 4 * 8);
+    const size_t o_corn = take(F * (size_t)hg.g.nc * 3 * 8), o_gmm = take(F * 64 * 8 + 4096 * 8 * 8);
+    if (cudaMalloc(&b->d_block, off) != cudaSuccess) return fail("cudaMalloc block");
+    char* base = static_cast<char*>(b->d_block);
+    cudaMemsetAsync(base, 0, off, ctx->stream);
+    b->d_npts = reinterpret_cast<int64_t*>(base + o_npts);
+    v.n_pts = b->d_npts;
+    v.hist = reinterpret_cast<int*>(base + o_hist);
+    v.cursor = reinterpret_cast<int*>(base + o_cur);
+    v.items = reinterpret_cast<int4*>(base + o_items);
+    v.acc = reinterpret_cast<double*>(base + o_acc);
+    v.ctl = reinterpret_cast<FrameCtl*>(base + o_ctl);
+    v.lm = reinterpret_cast<LmState*>(base + o_lm);
+    v.n_done = reinterpret_cast<int*>(base + o_done);
+    v.tgt_xy = reinterpret_cast<double2*>(base + o_txy);
+    v.tgt_xyf = reinterpret_cast<float2*>(base + o_txyf);
+    v.tgt_is_row = reinterpret_cast<uint8_t*>(base + o_row);
+    v.cell_cand = reinterpret_cast<int16_t*>(base + o_cand);
+    v.eval_out = reinterpret_cast<double*>(base + o_eval);
+    v.corners = reinterpret_cast<double*>(base + o_corn);
+    b->d_gmm = reinterpret_cast<double*>(base + o_gmm);
+    cudaMemcpyAsync(base + o_txy, hg.tgt_xy.data(), nt * 16, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(base + o_txyf, hg.tgt_xyf.data(), nt * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(base + o_row, hg.is_row.data(), nt, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(base + o_cand, hg.cell_cand.data(), ncell * kCand * 2, cudaMemcpyHostToDevice, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail("batch setup copies");
+    *out = b;
+    return RCLC_OK;
+}
+
+int rclc_batch_destroy(rclc_batch* b)
+{
+    if (!b) return RCLC_OK;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    if (b->d_pristine) cudaFree(b->d_pristine);
+    if (b->v.raw) cudaFree(b->v.raw);
+    if (b->v.binned) cudaFree(b->v.binned);
+    if (b->d_block) cudaFree(b->d_block);
+    delete b;
+    return RCLC_OK;
+}
+
+static int set_npts(rclc_batch* b, int32_t frame, int64_t n)
+{
+    b->h_npts[frame] = n;
+    b->binned_valid = false;
+    RCLC_CUDA(cudaMemcpyAsync(b->d_npts + frame, &b->h_npts[frame], 8, cudaMemcpyHostToDevice, b->ctx->stream));
+    return RCLC_OK;
+}
+
+int rclc_batch_upload(rclc_batch* b, int32_t frame, const void* pts, int stride, int ioff, int64_t n)
+{
+    RCLC_CHECK(b && (pts || n == 0), RCLC_ERR_INVALID, "null argument");
+    RCLC_CHECK(frame >= 0 && frame < b->n_frames && n >= 0 && n <= b->max_pts, RCLC_ERR_INVALID, "frame/n out of range");
+    RCLC_TRY(upload_cloud_f4(b->ctx, pts, stride, ioff, n, b->d_pristine + (size_t)frame * b->v.frame_stride));
+    return set_npts(b, frame, n);
+}
+
+int rclc_batch_set_frame_dev(rclc_batch* b, int32_t frame, const void* pts_dev, int64_t n)
+{
+    RCLC_CHECK(b && (pts_dev || n == 0), RCLC_ERR_INVALID, "null argument");
+    RCLC_CHECK(frame >= 0 && frame < b->n_frames && n >= 0 && n <= b->max_pts, RCLC_ERR_INVALID, "frame/n out of range");
+    RCLC_CUDA(cudaMemcpyAsync(b->d_pristine + (size_t)frame * b->v.frame_stride, pts_dev, (size_t)n * 16,
+                              cudaMemcpyDeviceToDevice, b->ctx->stream));
+    return set_npts(b, frame, n);
+}
+
+int64_t rclc_batch_total_points(rclc_batch* b)
+{
+    int64_t t = 0;
+    if (b) for (int64_t n : b->h_npts) t += n;
+    return t;
+}
+
+int rclc_batch_bin(rclc_batch* b)
+{
+    RCLC_CHECK(b, RCLC_ERR_INVALID, "null batch");
+    RCLC_CUDA(cudaSetDevice(b->ctx->device));
+    RCLC_TRY(launch_init(b, nullptr));
+    RCLC_TRY(launch_rebin(b));
+    b->binned_valid = true;
+    return RCLC_OK;
+}
+
+int rclc_batch_sweep(rclc_batch* b, const double* poses)
+{
+    RCLC_CHECK(b && poses, RCLC_ERR_INVALID, "null argument");
+    RCLC_CHECK(b->binned_valid, RCLC_ERR_INVALID, "rclc_batch_bin must be called first");
+    rclc_ctx* ctx = b->ctx;
+    RCLC_TRY(ctx->h_pin2.reserve(sizeof(PoseCoef) * b->n_frames));
+    RCLC_TRY(ctx->d_tmp2.reserve(sizeof(PoseCoef) * b->n_frames));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));        // pinned staging reuse
+    PoseCoef* hp = ctx->h_pin2.as<PoseCoef>();
+    for (int f = 0; f < b->n_frames; ++f) hp[f] = host_pose_coef(poses + 3 * f);
+    RCLC_CUDA(cudaMemcpyAsync(ctx->d_tmp2.p, hp, sizeof(PoseCoef) * b->n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    k_set_pose<<<b->n_frames, 256, 0, ctx->stream>>>(b->v, ctx->d_tmp2.as<PoseCoef>());
+    ctx->launches += 1;
+    return launch_sweep(b);
+}
+
+int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* acc)
+{
+    RCLC_CHECK(b, RCLC_ERR_INVALID, "null batch");
+    rclc_ctx* ctx = b->ctx;
+    const size_t F = b->n_frames, nt = b->v.geom.nt;
+    k_eval_out<<<b->n_frames, 128, 0, ctx->stream>>>(b->v);
+    ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    std::vector<double> h(F * nt * 4);
+    RCLC_CUDA(cudaMemcpyAsync(h.data(), b->v.eval_out, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (acc) RCLC_CUDA(cudaMemcpyAsync(acc, b->v.acc, F * nt * 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < F * nt; ++k) {
+        if (residuals) residuals[k] = h[4 * k];
+        if (jac) { jac[3 * k] = h[4 * k + 1]; jac[3 * k + 1] = h[4 * k + 2]; jac[3 * k + 2] = h[4 * k + 3]; }
+    }
+    return RCLC_OK;
+}
+
+int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out, double* corners_out, rclc_gridfit_report* reports)
+{
+    RCLC_CHECK(b, RCLC_ERR_INVALID, "null batch");
+    rclc_ctx* ctx = b->ctx;
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    const int F = b->n_frames;
+    const GridGeom& g = b->v.geom;
+    double* d_Tbl = nullptr;
+    if (T_bl) {
+        RCLC_TRY(ctx->d_tmp2.reserve((size_t)F * 16 * 8));
+        d_Tbl = ctx->d_tmp2.as<double>();
+        RCLC_CUDA(cudaMemcpyAsync(d_Tbl, T_bl, (size_t)F * 16 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // opt_grid_fitting.h:47-56 apply_noise_test is a debugging aid that perturbs the input; the caller
+    // can apply it with rclc_transform_cloud. It is rejected here rather than silently ignored.
+    RCLC_CHECK(!b->cfg.apply_noise_test, RCLC_ERR_UNSUPPORTED, "apply_noise_test: perturb the input with rclc_transform_cloud instead");
+    RCLC_TRY(launch_init(b, d_Tbl));
+    b->binned_valid = false;
+    RCLC_TRY(ctx->h_pin2.reserve(64));
+    int* h_done = ctx->h_pin2.as<int>();
+    // Upper bound on rounds: every outer iteration needs at most max_lm_iters+2 evaluations.
+    const int64_t max_rounds = (int64_t)(g.max_iter_time + 2) * (g.max_lm_iters + 3);
+    const int rounds_per_check = 24;
+    int64_t rounds = 0;
+    for (;;) {
+        for (int r = 0; r < rounds_per_check; ++r) {
+            RCLC_TRY(launch_rebin(b));
+            RCLC_TRY(launch_sweep(b));
+            k_lm<<<F, kLmThreads, 0, ctx->stream>>>(b->v);
+            ctx->launches += 1;
+        }
+        rounds += rounds_per_check;
+        RCLC_CUDA(cudaGetLastError());
+        RCLC_CUDA(cudaMemcpyAsync(h_done, b->v.n_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (*h_done >= F) break;
+        RCLC_CHECK(rounds < max_rounds, RCLC_ERR_NUMERIC, "grid-fit state machine did not terminate");
+    }
+    std::vector<LmState> h_lm(F);
+    RCLC_CUDA(cudaMemcpyAsync(h_lm.data(), b->v.lm, sizeof(LmState) * F, cudaMemcpyDeviceToHost, ctx->stream));
+    if (corners_out)
+        RCLC_CUDA(cudaMemcpyAsync(corners_out, b->v.corners, (size_t)F * g.nc * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    int rc = RCLC_OK;
+    for (int f = 0; f < F; ++f) {
+        if (reports) reports[f] = h_lm[f].rep;
+        if (T_bl_out) for (int k = 0; k < 16; ++k) T_bl_out[(size_t)f * 16 + k] = h_lm[f].T_bl[k];
+    }
+    return rc;
+}
+
+int rclc_gridfit_eval(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n,
+                      const double pose[3], double* residuals, double* jac, double* acc)
+{
+    RCLC_CHECK(ctx && cfg && pts && pose && residuals && n > 0, RCLC_ERR_INVALID, "null argument");
+    rclc_batch* b = nullptr;
+    RCLC_TRY(rclc_batch_create(ctx, cfg, 1, n, &b));
+    int rc = rclc_batch_upload(b, 0, pts, stride, ioff, n);
+    if (rc == RCLC_OK) rc = rclc_batch_bin(b);
+    if (rc == RCLC_OK) rc = rclc_batch_sweep(b, pose);
+    if (rc == RCLC_OK) rc = rclc_batch_read_eval(b, residuals, jac, acc);
+    rclc_batch_destroy(b);
+    return rc;
+}
+
+int rclc_gridfit_solve(rclc_ctx* ctx, const rclc_config* cfg, void* pts_io, int stride, int ioff, int64_t n,
+                       double* T_bl_io, double* corners_out, rclc_gridfit_report* report)
+{
+    RCLC_CHECK(ctx && cfg && pts_io && corners_out && n > 0, RCLC_ERR_INVALID, "null argument");
+    rclc_batch* b = nullptr;
+    RCLC_TRY(rclc_batch_create(ctx, cfg, 1, n, &b));
+    int rc = rclc_batch_upload(b, 0, pts_io, stride, ioff, n);
+    rclc_gridfit_report rep;
+    if (rc == RCLC_OK) rc = rclc_batch_gridfit_solve(b, T_bl_io, nullptr, corners_out, &rep);
+    if (rc == RCLC_OK && report) *report = rep;
+    rclc_batch_destroy(b);
+    return rc;
+}
+
+int rclc_gridfit_multistart(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n,
+                            const double* poses, int32_t P, double* cost_out)
+{
+    RCLC_CHECK(ctx && cfg && pts && poses && cost_out && n > 0 && P > 0, RCLC_ERR_INVALID, "bad argument");
+    rclc_batch* b = nullptr;
+    RCLC_TRY(rclc_batch_create(ctx, cfg, 1, n, &b));
+    int rc = rclc_batch_upload(b, 0, pts, stride, ioff, n);
+    if (rc == RCLC_OK) rc = rclc_batch_bin(b);
+    if (rc == RCLC_OK) rc = rclc_batch_multistart(b, 0, poses, P, cost_out);
+    rclc_batch_destroy(b);
+    return rc;
+}
+
+int rclc_batch_multistart(rclc_batch* b, int32_t frame, const double* poses, int32_t P, double* cost_out)
+{
+    RCLC_CHECK(b && poses && cost_out && P > 0 && frame >= 0 && frame < b->n_frames, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CHECK(b->binned_valid, RCLC_ERR_INVALID, "rclc_batch_bin must be called first");
+    rclc_ctx* ctx = b->ctx;
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    const size_t nt = b->v.geom.nt;
+    const size_t o_ctl = (sizeof(PoseCoef) * P + 255) & ~(size_t)255;
+    const size_t o_acc = o_ctl + ((sizeof(FrameCtl) * P + 255) & ~(size_t)255);
+    const size_t o_cost = o_acc + (size_t)P * nt * 16 * 8;
+    RCLC_TRY(ctx->d_tmp.reserve(o_cost + (size_t)P * 8));
+    RCLC_TRY(ctx->h_pin2.reserve(sizeof(PoseCoef) * P));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    PoseCoef* hp = ctx->h_pin2.as<PoseCoef>();
+    for (int p = 0; p < P; ++p) hp[p] = host_pose_coef(poses + 3 * p);
+    char* base = static_cast<char*>(ctx->d_tmp.p);
+    PoseCoef* d_poses = reinterpret_cast<PoseCoef*>(base);
+    FrameCtl* d_ctl = reinterpret_cast<FrameCtl*>(base + o_ctl);
+    double* d_acc = reinterpret_cast<double*>(base + o_acc);
+    double* d_cost = reinterpret_cast<double*>(base + o_cost);
+    RCLC_CUDA(cudaMemcpyAsync(d_poses, hp, sizeof(PoseCoef) * P, cudaMemcpyHostToDevice, ctx->stream));
+    RCLC_CUDA(cudaMemsetAsync(d_acc, 0, (size_t)P * nt * 16 * 8, ctx->stream));
+    BatchView v = b->v;
+    k_ms_setup<<<(P + 127) / 128, 128, 0, ctx->stream>>>(b->v, d_ctl, d_poses, P, frame);
+    v.ctl = d_ctl;
+    v.acc = d_acc;
+    v.fixed_frame = frame;
+    v.n_frames = P;
+    // blockIdx.y is limited to 65535: sweep poses in slabs
+    for (int p0 = 0; p0 < P; p0 += 32768) {
+        const int np = std::min(32768, P - p0);
+        BatchView vs = v;
+        vs.ctl = d_ctl + p0;
+        vs.acc = d_acc + (size_t)p0 * nt * 16;
+        k_sweep<<<dim3((unsigned)b->v.max_items, (unsigned)np), kSweepThreads, 0, ctx->stream>>>(vs);
+        k_ms_cost<<<np, kLmThreads, 0, ctx->stream>>>(vs, d_cost + p0);
+        ctx->launches += 2;
+    }
+    ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    RCLC_CUDA(cudaMemcpyAsync(cost_out, d_cost, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RCLC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,120 @@
+// gridfit.cuh — data structures of the grid-fit path (K4/K5), shared by gridfit.cu and multistart.cu.
+//
+// Design: the reference evaluates 82 cost functors, each looping over its own
+// kd-tree neighbour copy (board_fitting_cost.h:124-210, 3.3*N point visits per sweep, fp64). Here a
+// frame's points are counting-sorted ONCE per outer iteration into the cells of the half-square
+// lattice on which all targets sit; a cell has at most 8 candidate targets, and each point carries an
+// 8-bit mask of exact (FLANN-equivalent) neighbour membership. A sweep then streams 16 B per point,
+// every CTA works on one cell, accumulates in registers and block-reduces — no atomics in the hot loop.
+#pragma once
+#include "common.cuh"
+
+namespace rclc {
+
+constexpr int kMaxTargets = 1024;
+constexpr int kMaxCells = 4096;
+constexpr int kCand = 8;                 // candidate targets per cell
+constexpr int kSweepThreads = 128;
+constexpr int kSweepP = 8;               // points per thread
+constexpr int kChunk = kSweepThreads * kSweepP;
+constexpr int kBinThreads = 256;
+constexpr int kBinP = 8;
+constexpr int kBinChunk = kBinThreads * kBinP;
+
+// Geometry derived from rclc_config on the host (gridfit.cu: build_geom).
+struct GridGeom {
+    int nt;                    // number of targets (col targets first, then row targets)
+    int nc;                    // number of corners
+    int ncx, ncy, ncells;      // lattice cells
+    int i0, j0;                // site index of cell (0,0)'s lower corner
+    double g, inv_g;           // lattice unit = side/2
+    double rc2, rg2;           // cost / gradient radius squared (board_fitting_cost.h:58-59)
+    float rn2f;                // (float)(neighbour_radius^2)  (FLANN radius)
+    double huber_a;
+    double function_tol;
+    int max_lm_iters;
+    int max_iter_time;
+    int board_w, board_h;
+    double side;
+};
+
+struct PoseCoef {              // R = Quaternion(cos(t/2),0,0,sin(t/2)).matrix(), t = (x,y)
+    double r00, r01, r10, r11, tx, ty;
+    double yaw_deg;
+};
+
+enum Phase { PH_EVAL_INIT = 1, PH_EVAL_CAND = 2, PH_DONE = 3 };
+
+// Per-frame control block read by the streaming kernels.
+struct FrameCtl {
+    int sweep_active;          // sweep kernels process this frame
+    int rebin;                 // count/scatter kernels process this frame (move + re-bin)
+    int n_items;               // work items (cell chunks) of the current binning
+    int n_binned;              // points that landed in a lattice cell
+    float move[8];             // T_w1_w0 rows 0,1: m00 m01 m02 m03 / m10 m11 m12 m13
+    PoseCoef pose;             // pose the next sweep evaluates
+};
+
+// Ceres TrustRegionMinimizer state + opt_grid_fitting outer-loop state, one per frame.
+struct LmState {
+    int phase;
+    int outer_iter;
+    int status;
+    int iteration;
+    int num_consecutive_invalid;
+    int reuse_diagonal;
+    int step_is_successful;
+    int n_lm_iterations_this_solve;
+    double x[3], cand[3], best[3];
+    double x_cost, x_norm, radius, decrease_factor;
+    double minimum_cost, initial_cost, min_iter_cost;
+    double Au[6], bu[3];       // unscaled J'J (00,01,02,11,12,22) and J'r at x
+    double scale[3], diag[3];
+    double model_cost_change;
+    double gmax;
+    float T_base_laser[16];
+    double T_bl[16];
+    rclc_gridfit_report rep;
+};
+
+struct BatchView {
+    GridGeom geom;
+    int n_frames;
+    int64_t frame_stride;          // float4 elements between frames in raw/binned
+    int max_items;                 // per frame
+    int fixed_frame;               // >= 0: every blockIdx.y of k_sweep reads this frame's points (multi-start sweep)
+    const int64_t* n_pts;          // [F]
+    float4* raw;                   // [F][frame_stride]   current pc_iter (x,y,z,I)
+    float4* binned;                // [F][frame_stride]   cell-sorted {x, y, I, mask bits}
+    int* hist;                     // [F][ncells]
+    int* cursor;                   // [F][ncells]
+    int4* items;                   // [F][max_items]  {cell, start, count, 0}
+    double* acc;                   // [F][nt][16]
+    FrameCtl* ctl;                 // [F]
+    LmState* lm;                   // [F]
+    int* n_done;                   // [1]
+    // geometry tables
+    const double2* tgt_xy;         // [nt]
+    const float2* tgt_xyf;         // [nt] (float)target  (FLANN query point)
+    const uint8_t* tgt_is_row;     // [nt]
+    const int16_t* cell_cand;      // [ncells][8] target index or -1
+    double* eval_out;              // [F][nt][4] residual, j0, j1, j2 (rclc_batch_read_eval)
+    double* corners;               // [F][nc][3]
+};
+
+} // namespace rclc
+
+struct rclc_batch {
+    rclc_ctx* ctx = nullptr;
+    rclc_config cfg;
+    rclc::BatchView v;
+    int n_frames = 0;
+    int64_t max_pts = 0;
+    std::vector<int64_t> h_npts;
+    float4* d_pristine = nullptr;     // [F][frame_stride] uploaded clouds (solve works on a copy)
+    void* d_block = nullptr;          // one allocation for the small arrays
+    int64_t* d_npts = nullptr;
+    bool binned_valid = false;
+    // GMM scratch
+    double* d_gmm = nullptr;
+};

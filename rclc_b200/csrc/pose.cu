@@ -1,0 +1,378 @@
+// pose.cu — K6: final extrinsic refinement (one scalar residual per frame, 7 parameters / 6 DoF).
+//
+// Replaces POSE_REPRJ_COST::operator() (include/opt/pose_reprj_cost.hpp:28-55, evaluated through
+// ceres::AutoDiffCostFunction<.,1,4,3>) and pose_reprj_opt (include/opt/opt_reprj_calib.h:21-66:
+// HuberLoss(0.2), EigenQuaternionParameterization, DENSE_NORMAL_CHOLESKY, 1000 iterations,
+// function_tolerance 1e-15). One thread per frame carries 7-wide dual numbers through the residual
+// (including the arg-max selection, exactly like Jets); the 6x6 normal equations J'J / J'r are
+// reduced across the CTA in shared memory and the Ceres LM step (Cholesky + accept/reject/radius
+// schedule) runs on device. The whole solve is ONE kernel launch — this path is latency-bound
+//  and is the site whose 6x6 system is all-reduced when frames are sharded.
+#include "common.cuh"
+
+#include <cfloat>
+
+namespace rclc {
+
+struct J7 {
+    double a;
+    double v[7];
+};
+__device__ __forceinline__ J7 jconst(double s) { J7 r; r.a = s; for (int i = 0; i < 7; ++i) r.v[i] = 0; return r; }
+__device__ __forceinline__ J7 jvar(double s, int k) { J7 r = jconst(s); r.v[k] = 1.0; return r; }
+__device__ __forceinline__ J7 operator+(const J7& f, const J7& g) { J7 h; h.a = f.a + g.a; for (int i = 0; i < 7; ++i) h.v[i] = f.v[i] + g.v[i]; return h; }
+__device__ __forceinline__ J7 operator-(const J7& f, const J7& g) { J7 h; h.a = f.a - g.a; for (int i = 0; i < 7; ++i) h.v[i] = f.v[i] - g.v[i]; return h; }
+__device__ __forceinline__ J7 operator*(const J7& f, const J7& g) { J7 h; h.a = f.a * g.a; for (int i = 0; i < 7; ++i) h.v[i] = f.a * g.v[i] + f.v[i] * g.a; return h; }
+__device__ __forceinline__ J7 operator/(const J7& f, const J7& g)
+{
+    J7 h;
+    const double gi = 1.0 / g.a, fg = f.a * gi;
+    h.a = fg;
+    for (int i = 0; i < 7; ++i) h.v[i] = (f.v[i] - fg * g.v[i]) * gi;
+    return h;
+}
+__device__ __forceinline__ J7 jsqrt(const J7& f)
+{
+    J7 h;
+    const double t = sqrt(f.a), ti = 1.0 / (2.0 * t);
+    h.a = t;
+    for (int i = 0; i < 7; ++i) h.v[i] = f.v[i] * ti;
+    return h;
+}
+
+// pose_reprj_cost.hpp:28-55 on Jets. q = (x,y,z,w) storage, Eigen::Quaternion{w,x,y,z}.matrix().
+__device__ void pose_block_dev(const double* Tcl, const double* pc, const double* img, int C, double& r, double* j6)
+{
+    J7 q[4], t[3];
+    for (int k = 0; k < 4; ++k) q[k] = jvar(Tcl[k], k);
+    for (int k = 0; k < 3; ++k) t[k] = jvar(Tcl[4 + k], 4 + k);
+    const J7 two = jconst(2.0), one = jconst(1.0);
+    const J7 &x = q[0], &y = q[1], &z = q[2], &w = q[3];
+    const J7 tx = two * x, ty = two * y, tz = two * z;
+    const J7 twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    const J7 R0 = one - (tyy + tzz), R1 = txy - twz, R2 = txz + twy;
+    const J7 R3 = txy + twz, R4 = one - (txx + tzz), R5 = tyz - twx;
+    const J7 R6 = txz - twy, R7 = tyz + twx, R8 = one - (txx + tyy);
+    J7 res = jconst(0.0), depth_max = jconst(0.0);
+    for (int i = 0; i < C; ++i) {
+        const J7 p0 = jconst(pc[3 * i]), p1 = jconst(pc[3 * i + 1]), p2 = jconst(pc[3 * i + 2]);
+        const J7 X = (R0 * p0 + (R1 * p1 + R2 * p2)) + t[0];
+        const J7 Y = (R3 * p0 + (R4 * p1 + R5 * p2)) + t[1];
+        const J7 Z = (R6 * p0 + (R7 * p1 + R8 * p2)) + t[2];
+        const J7 depth_norm = jsqrt(X * X + (Y * Y + Z * Z));
+        if (depth_norm.a > depth_max.a) depth_max = depth_norm;
+        const J7 e0 = jconst(img[2 * i]) - X / Z, e1 = jconst(img[2 * i + 1]) - Y / Z;
+        res = res + jsqrt(e0 * e0 + e1 * e1) / depth_norm;
+    }
+    res = res * depth_max;
+    r = res.a;
+    // EigenQuaternionParameterization::ComputeJacobian (4x3), local Jacobian = J_global * plus_jacobian
+    const double P[12] = {Tcl[3], Tcl[2], -Tcl[1], -Tcl[2], Tcl[3], Tcl[0], Tcl[1], -Tcl[0], Tcl[3], -Tcl[0], -Tcl[1], -Tcl[2]};
+    for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += res.v[k] * P[k * 3 + c];
+        j6[c] = s;
+    }
+    for (int c = 0; c < 3; ++c) j6[3 + c] = res.v[4 + c];
+}
+
+__device__ void quat_plus_dev(const double* x, const double* delta, double* out)
+{
+    const double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+    if (nd > 0.0) {
+        const double s = sin(nd) / nd;
+        const double dw = cos(nd), dx = s * delta[0], dy = s * delta[1], dz = s * delta[2];
+        const double xw = x[3], xx = x[0], xy = x[1], xz = x[2];
+        out[3] = dw * xw - dx * xx - dy * xy - dz * xz;
+        out[0] = dw * xx + dx * xw + dy * xz - dz * xy;
+        out[1] = dw * xy + dy * xw + dz * xx - dx * xz;
+        out[2] = dw * xz + dz * xw + dx * xy - dy * xx;
+    } else {
+        for (int i = 0; i < 4; ++i) out[i] = x[i];
+    }
+}
+__device__ void pose_plus(const double* x, const double* d, double* out)
+{
+    quat_plus_dev(x, d, out);
+    for (int k = 0; k < 3; ++k) out[4 + k] = x[4 + k] + d[3 + k];
+}
+
+constexpr int kPoseThreads = 256;
+struct PoseOut { double Tcl[7]; double initial_cost, final_cost; int iterations; int termination; };
+
+// Block-wide sum of NV values per thread -> s_out[NV] (fixed order)
+template <int NV>
+__device__ void block_sum(double* vals, double* s_warp /* [8][NV] */, double* s_out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) vals[k] = warp_sum(vals[k]);
+    if (lane == 0) for (int k = 0; k < NV; ++k) s_warp[warp * NV + k] = vals[k];
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double t = 0;
+        for (int w = 0; w < kPoseThreads / 32; ++w) t += s_warp[w * NV + threadIdx.x];
+        s_out[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
+// Evaluate all frames at s_x: cost, (optionally) J'J (21) and J'r (6). Returns validity flags via s_sum[28], [29].
+__device__ void pose_evaluate(const double* pc, const double* img, int F, int C, double huber_a, const double* s_x, bool want_jac,
+                              double* s_warp, double* s_sum)
+{
+    double v[30];
+    for (int k = 0; k < 30; ++k) v[k] = 0;
+    for (int f = threadIdx.x; f < F; f += kPoseThreads) {
+        double r, j[6];
+        pose_block_dev(s_x, pc + (size_t)f * C * 3, img + (size_t)f * C * 2, C, r, j);
+        if (!isfinite(r)) v[28] = 1.0;
+        for (int c = 0; c < 6; ++c) if (!isfinite(j[c])) v[29] = 1.0;
+        const double sq = r * r, bb = huber_a * huber_a;
+        double rho0, rho1;
+        if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
+        else { rho0 = sq; rho1 = 1.0; }
+        const double w = sqrt(rho1);
+        r *= w;
+        v[0] += 0.5 * rho0;
+        if (want_jac) {
+            int q = 1;
+            for (int a = 0; a < 6; ++a) j[a] *= w;
+            for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) v[q++] += j[a] * j[b];     // 21 entries: v[1..21]
+            for (int a = 0; a < 6; ++a) v[22 + a] += j[a] * r;                                 // v[22..27]
+        }
+    }
+    block_sum<30>(v, s_warp, s_sum);
+}
+
+__device__ bool chol6_solve(const double* A /*6x6 full*/, const double* b, double* y)
+{
+    double L[36];
+    for (int k = 0; k < 36; ++k) L[k] = 0;
+    for (int j = 0; j < 6; ++j) {
+        double d = A[j * 6 + j];
+        for (int k = 0; k < j; ++k) d -= L[j * 6 + k] * L[j * 6 + k];
+        if (!(d > 0.0)) return false;
+        d = sqrt(d);
+        L[j * 6 + j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = A[i * 6 + j];
+            for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
+            L[i * 6 + j] = s / d;
+        }
+    }
+    for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * y[k]; y[i] = s / L[i * 6 + i]; }
+    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * y[k]; y[i] = s / L[i * 6 + i]; }
+    for (int i = 0; i < 6; ++i) if (!isfinite(y[i])) return false;
+    return true;
+}
+
+// Ceres TrustRegionMinimizer (see oracle/ceres_lm.hpp for the published algorithm this mirrors)
+__global__ void __launch_bounds__(kPoseThreads) k_pose_refine(const double* __restrict__ pc, const double* __restrict__ img, int F, int C,
+                                                              double huber_a, double ftol, int max_iters, const double* __restrict__ T0,
+                                                              PoseOut* __restrict__ out)
+{
+    __shared__ double s_warp[(kPoseThreads / 32) * 30];
+    __shared__ double s_sum[30];
+    __shared__ double s_x[7], s_cand[7];
+    __shared__ int s_ctrl;           // 0 = evaluate candidate next, 1 = stop
+    // thread-0 state
+    double A[36], g[6], scale[6], diag[6], best[7];
+    double x_cost = 0, x_norm = 0, radius = 1e4, decrease_factor = 2.0, gmax = 0, model_cost_change = 0;
+    double minimum_cost = DBL_MAX, initial_cost = 0, min_iter_cost = 0;
+    int iteration = 0, ninvalid = 0, n_iters = 0, term = 1;
+    bool reuse_diagonal = false, step_ok = true, failed = false;
+    const int tid = threadIdx.x;
+    if (tid < 7) s_x[tid] = T0[tid];
+    __syncthreads();
+
+    auto take_eval = [&]() {          // thread 0: accept s_sum as the evaluation at s_x
+        x_cost = s_sum[0];
+        int q = 1;
+        for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { A[a * 6 + b] = s_sum[q]; A[b * 6 + a] = s_sum[q]; ++q; }
+        for (int a = 0; a < 6; ++a) g[a] = s_sum[22 + a];
+        double ng[6], xp[7];
+        for (int a = 0; a < 6; ++a) ng[a] = -g[a];
+        pose_plus(s_x, ng, xp);
+        gmax = 0;
+        for (int k = 0; k < 7; ++k) gmax = fmax(gmax, fabs(s_x[k] - xp[k]));
+    };
+
+    pose_evaluate(pc, img, F, C, huber_a, s_x, true, s_warp, s_sum);
+    if (tid == 0) {
+        if (s_sum[28] != 0.0 || s_sum[29] != 0.0) { failed = true; term = 2; initial_cost = nan(""); min_iter_cost = nan(""); s_ctrl = 1; }
+        else {
+            take_eval();
+            for (int a = 0; a < 6; ++a) scale[a] = 1.0 / (1.0 + sqrt(A[a * 6 + a]));
+            initial_cost = x_cost; min_iter_cost = x_cost;
+            x_norm = 0; for (int k = 0; k < 7; ++k) x_norm += s_x[k] * s_x[k];
+            x_norm = sqrt(x_norm);
+            for (int k = 0; k < 7; ++k) best[k] = s_x[k];
+            s_ctrl = 0;
+        }
+    }
+    __syncthreads();
+    bool stop = (s_ctrl == 1);
+    while (!stop) {
+        if (tid == 0) {
+            // Finalize + step computation loop (invalid steps do not need an evaluation)
+            bool need_eval = false;
+            while (!need_eval) {
+                if (step_ok && x_cost < minimum_cost) { minimum_cost = x_cost; for (int k = 0; k < 7; ++k) best[k] = s_x[k]; }
+                n_iters++;
+                if (iteration >= max_iters) { term = 1; break; }
+                if (step_ok && gmax <= 1e-10) { term = 0; break; }
+                if (radius <= 1e-32) { term = 0; break; }
+                iteration++;
+                step_ok = false;
+                double M[36], bs[6], y[6], step[6];
+                for (int a = 0; a < 6; ++a) { bs[a] = g[a] * scale[a]; for (int b = 0; b < 6; ++b) M[a * 6 + b] = A[a * 6 + b] * scale[a] * scale[b]; }
+                if (!reuse_diagonal) for (int a = 0; a < 6; ++a) diag[a] = fmin(fmax(M[a * 6 + a], 1e-6), 1e32);
+                double As[36];
+                for (int k = 0; k < 36; ++k) As[k] = M[k];
+                for (int a = 0; a < 6; ++a) { const double l = sqrt(diag[a] / radius); M[a * 6 + a] += l * l; }
+                bool valid = chol6_solve(M, bs, y);
+                reuse_diagonal = true;
+                double mcc = 0;
+                if (valid) {
+                    double sb = 0, sAs = 0;
+                    for (int a = 0; a < 6; ++a) step[a] = -y[a];
+                    for (int a = 0; a < 6; ++a) { sb += step[a] * bs[a]; double t = 0; for (int b = 0; b < 6; ++b) t += As[a * 6 + b] * step[b]; sAs += step[a] * t; }
+                    mcc = -(sb + 0.5 * sAs);
+                    valid = mcc > 0.0;
+                }
+                if (!valid) {
+                    if (++ninvalid >= 5) { term = 2; failed = true; break; }
+                    radius *= 0.5;
+                    min_iter_cost = fmin(min_iter_cost, x_cost);
+                    continue;
+                }
+                ninvalid = 0;
+                model_cost_change = mcc;
+                double delta[6];
+                for (int a = 0; a < 6; ++a) delta[a] = step[a] * scale[a];
+                pose_plus(s_x, delta, s_cand);
+                need_eval = true;
+            }
+            s_ctrl = need_eval ? 0 : 1;
+        }
+        __syncthreads();
+        if (s_ctrl == 1) break;
+        // evaluate the candidate (cost + Jacobian in one pass; Ceres evaluates the Jacobian again on acceptance)
+        pose_evaluate(pc, img, F, C, huber_a, s_cand, true, s_warp, s_sum);
+        if (tid == 0) {
+            const double cand_cost = (s_sum[28] == 0.0) ? s_sum[0] : DBL_MAX;
+            double sn = 0;
+            for (int k = 0; k < 7; ++k) sn += (s_x[k] - s_cand[k]) * (s_x[k] - s_cand[k]);
+            if (sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) { term = 0; s_ctrl = 1; }
+            else if (fabs(x_cost - cand_cost) <= ftol * x_cost) { term = 0; s_ctrl = 1; }
+            else {
+                const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : (x_cost - cand_cost) / model_cost_change;
+                if (rel > 1e-3) {
+                    for (int k = 0; k < 7; ++k) s_x[k] = s_cand[k];
+                    x_norm = 0; for (int k = 0; k < 7; ++k) x_norm += s_x[k] * s_x[k];
+                    x_norm = sqrt(x_norm);
+                    if (s_sum[29] != 0.0) { term = 2; failed = true; s_ctrl = 1; }
+                    else {
+                        take_eval();
+                        step_ok = true;
+                        const double q = 2.0 * rel - 1.0;
+                        radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - q * q * q));
+                        decrease_factor = 2.0;
+                        reuse_diagonal = false;
+                        min_iter_cost = fmin(min_iter_cost, x_cost);
+                    }
+                } else {
+                    min_iter_cost = fmin(min_iter_cost, cand_cost);
+                    radius = radius / decrease_factor;
+                    decrease_factor *= 2.0;
+                    reuse_diagonal = true;
+                    step_ok = false;
+                }
+            }
+        }
+        __syncthreads();
+        stop = (s_ctrl == 1);
+    }
+    if (tid == 0) {
+        for (int k = 0; k < 7; ++k) out->Tcl[k] = failed ? T0[k] : best[k];
+        out->initial_cost = initial_cost;
+        out->final_cost = fmin(initial_cost, min_iter_cost);
+        out->iterations = n_iters;
+        out->termination = term;
+    }
+}
+
+__global__ void k_pose_eval(const double* __restrict__ pc, const double* __restrict__ img, int F, int C, const double* __restrict__ Tcl,
+                            double* __restrict__ res, double* __restrict__ jac)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double r, j[6];
+    pose_block_dev(Tcl, pc + (size_t)f * C * 3, img + (size_t)f * C * 2, C, r, j);
+    res[f] = r;
+    for (int c = 0; c < 6; ++c) jac[6 * f + c] = j[c];
+}
+
+static int upload_pose_inputs(rclc_ctx* ctx, const double* pc, const double* img, int F, int C, const double* Tcl,
+                              double** d_pc, double** d_img, double** d_T)
+{
+    const size_t n_pc = (size_t)F * C * 3, n_img = (size_t)F * C * 2;
+    RCLC_TRY(ctx->d_tmp.reserve((n_pc + n_img + 8) * 8));
+    *d_pc = ctx->d_tmp.as<double>();
+    *d_img = *d_pc + n_pc;
+    *d_T = *d_img + n_img;
+    RCLC_CUDA(cudaMemcpyAsync(*d_pc, pc, n_pc * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RCLC_CUDA(cudaMemcpyAsync(*d_img, img, n_img * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RCLC_CUDA(cudaMemcpyAsync(*d_T, Tcl, 7 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return RCLC_OK;
+}
+
+} // namespace rclc
+
+using namespace rclc;
+
+extern "C" {
+
+int rclc_pose_eval(rclc_ctx* ctx, const double* pc_corners, const double* img_norm, int32_t F, int32_t C,
+                   const double Tcl[7], double* residuals, double* jac6)
+{
+    RCLC_CHECK(ctx && pc_corners && img_norm && Tcl && residuals && F > 0 && C > 0, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    double *d_pc, *d_img, *d_T;
+    RCLC_TRY(upload_pose_inputs(ctx, pc_corners, img_norm, F, C, Tcl, &d_pc, &d_img, &d_T));
+    RCLC_TRY(ctx->d_out.reserve((size_t)F * 7 * 8));
+    double* d_res = ctx->d_out.as<double>();
+    double* d_jac = d_res + F;
+    k_pose_eval<<<(F + 127) / 128, 128, 0, ctx->stream>>>(d_pc, d_img, F, C, d_T, d_res, d_jac);
+    ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    RCLC_CUDA(cudaMemcpyAsync(residuals, d_res, (size_t)F * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (jac6) RCLC_CUDA(cudaMemcpyAsync(jac6, d_jac, (size_t)F * 6 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RCLC_OK;
+}
+
+int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_corners, const double* img_norm,
+                     int32_t F, int32_t C, double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations)
+{
+    RCLC_CHECK(ctx && cfg && pc_corners && img_norm && Tcl_io && F > 0 && C > 0, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    double *d_pc, *d_img, *d_T;
+    RCLC_TRY(upload_pose_inputs(ctx, pc_corners, img_norm, F, C, Tcl_io, &d_pc, &d_img, &d_T));
+    RCLC_TRY(ctx->d_out.reserve(sizeof(PoseOut)));
+    k_pose_refine<<<1, kPoseThreads, 0, ctx->stream>>>(d_pc, d_img, F, C, cfg->pose_huber_a, cfg->pose_function_tol, cfg->pose_max_lm_iters,
+                                                      d_T, ctx->d_out.as<PoseOut>());
+    ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    PoseOut h;
+    RCLC_CUDA(cudaMemcpyAsync(&h, ctx->d_out.p, sizeof(PoseOut), cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 7; ++k) Tcl_io[k] = h.Tcl[k];
+    if (initial_cost) *initial_cost = h.initial_cost;
+    if (final_cost) *final_cost = h.final_cost;
+    if (iterations) *iterations = h.iterations;
+    return h.termination == 2 ? RCLC_ERR_NUMERIC : RCLC_OK;
+}
+
+} // extern "C"

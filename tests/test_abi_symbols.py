@@ -1,0 +1,76 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads, and exports every symbol include/rclc_b200.h declares.
+No compute is called here (there is no GPU in the CPU container and no CPU fallback in the product)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for hdr in ("rclc_b200.h", "rclc_config.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = src.split("#ifdef RCLC_CONFIG_IMPLEMENTATION")[0]
+        names |= set(re.findall(r"\b(rclc_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from rclc_b200 import build
+    return ctypes.CDLL(build.build())
+
+
+def test_header_declares_the_hot_path():
+    syms = declared_symbols()
+    for must in ("rclc_gridfit_eval", "rclc_gridfit_solve", "rclc_gmm_fit_1d", "rclc_ransac_plane_score", "rclc_pose_refine",
+                 "rclc_project_colorize", "rclc_gridfit_multistart", "rclc_plane_project", "rclc_batch_gridfit_solve"):
+        assert must in syms
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    missing = [s for s in declared_symbols() if not hasattr(built_lib, s)]
+    assert not missing, missing
+
+
+def test_config_layout_matches_ctypes(built_lib):
+    from rclc_b200 import capi
+    cfg = capi.config()          # asserts sizeof agreement
+    assert (cfg.board_width, cfg.board_height, cfg.max_iter_time) == (8, 6, 20)
+    assert cfg.fx == 1000.0 and cfg.cam_width == 1920 and cfg.pose_max_lm_iters == 1000
+
+
+def test_targets_match_oracle(built_lib, oracle, ocfg):
+    import numpy as np
+    from rclc_b200 import capi
+    xy, is_row = capi.generate_targets(capi.config())
+    xy0, is_row0 = oracle.generate_targets(ocfg)
+    assert np.array_equal(xy, xy0) and np.array_equal(is_row, is_row0)      # bit-identical doubles
+
+
+def test_no_cpu_fallback_without_device(built_lib):
+    """In the CPU container ctx creation must fail loudly (RCLC_ERR_CUDA); on a GPU box it succeeds."""
+    import torch
+    from rclc_b200 import capi
+    if torch.cuda.is_available():
+        capi.Context(0).close()
+    else:
+        with pytest.raises(capi.RclcError):
+            capi.Context(0)
+
+
+def test_product_does_not_reference_oracle():
+    """The oracle is test infrastructure: nothing under rclc_b200/ or include/ may mention it."""
+    bad = []
+    for base in ("rclc_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    if re.search(r"(pyoracle|rclc_oracle|librclc_oracle|from oracle|import oracle)", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad

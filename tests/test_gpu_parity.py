@@ -1,0 +1,274 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> librclc_b200.so), against the
+CPU oracle on identical seeded inputs. Bars (BASELINE.json north_star): accumulator tables / masks / counts /
+pixels bit-exact; grid residuals 1e-5 relative (we get ~1e-13); extrinsic 1e-4 rad / 0.1 mm."""
+import copy
+
+import numpy as np
+import pytest
+
+from rclc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from rclc_b200 import capi as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def ctx(capi):
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def cfg(capi):
+    return capi.config()
+
+
+POSES = [(0.0, 0.0, 0.0), (0.004, -0.003, 0.7), (-0.02, 0.015, -2.5), (0.03, 0.03, 4.0)]
+
+
+@pytest.mark.parametrize("pattern", ["raster", "rosette"])
+@pytest.mark.parametrize("pose", POSES)
+def test_gridfit_eval_bit_exact_accumulators(ctx, cfg, oracle, ocfg, pattern, pose):
+    pts = synth.board_frame_cloud(120000, 7, pert=(0.006, 0.004, 0.5), pattern=pattern)
+    r0, j0, a0 = oracle.gridfit_eval(ocfg, pts, pose, want_acc=True)
+    r1, j1, a1 = ctx.gridfit_eval(cfg, pts, pose, want_acc=True)
+    assert np.array_equal(a0, a1), np.abs(a0 - a1).max()          # sums and counts: bit-exact
+    np.testing.assert_allclose(r1, r0, rtol=1e-12, atol=1e-15)     # bar: 1e-5 relative
+    np.testing.assert_allclose(j1, j0, rtol=1e-10, atol=1e-10)
+
+
+def test_gridfit_eval_pcl_layout_and_8x5(ctx, cfg, oracle, ocfg):
+    """pcl::PointXYZI records (32 B, intensity at byte 16) and the shipped 8x5 board."""
+    c5, o5 = copy.copy(cfg), copy.copy(ocfg)
+    c5.board_height = 5; o5.board_height = 5
+    p4 = synth.board_frame_cloud(60000, 3, W=8, H=5, pert=(0.003, -0.002, 0.2))
+    p8 = np.zeros((len(p4), 8), np.float32)
+    p8[:, :3] = p4[:, :3]; p8[:, 3] = 1.0; p8[:, 4] = p4[:, 3]
+    pose = (0.001, 0.002, 0.1)
+    r0, j0, a0 = oracle.gridfit_eval(o5, p4, pose, want_acc=True)
+    r1, j1, a1 = ctx.gridfit_eval(c5, p8, pose, want_acc=True)
+    assert np.array_equal(a0, a1)
+    np.testing.assert_allclose(r1, r0, rtol=1e-12)
+
+
+def test_gridfit_eval_ragged_and_nan(ctx, cfg, oracle, ocfg):
+    """Half a board: some targets see empty half-discs -> NaN residuals exactly where the oracle has them."""
+    pts = synth.board_frame_cloud(40000, 5)
+    pts = pts[pts[:, 0] < -0.05]
+    r0, j0, a0 = oracle.gridfit_eval(ocfg, pts, (0, 0, 0), want_acc=True)
+    r1, j1, a1 = ctx.gridfit_eval(cfg, pts, (0, 0, 0), want_acc=True)
+    assert np.array_equal(a0, a1)
+    assert np.array_equal(np.isnan(r0), np.isnan(r1)) and np.isnan(r1).any()
+    np.testing.assert_allclose(r1[~np.isnan(r1)], r0[~np.isnan(r0)], rtol=1e-12)
+    # tiny cloud (fewer points than one CTA chunk), far-away points that fall outside the lattice
+    tiny = np.concatenate([pts[:37], np.array([[5.0, 5.0, 0.0, 50.0], [-3.0, 0.2, 0.0, 60.0]], np.float32)])
+    a0 = oracle.gridfit_eval(ocfg, tiny, (0.001, 0, 0), want_acc=True)[2]
+    a1 = ctx.gridfit_eval(cfg, tiny, (0.001, 0, 0), want_acc=True)[2]
+    assert np.array_equal(a0, a1)
+
+
+def _check_solve(corners, rep, oc, orep):
+    assert rep.outer_iterations == orep.outer_iterations
+    assert rep.pose_evals == orep.pose_evals and rep.lm_iterations == orep.lm_iterations
+    assert rep.status == orep.status
+    np.testing.assert_allclose(rep.first_initial_cost, orep.first_initial_cost, rtol=1e-11)
+    np.testing.assert_allclose(rep.last_final_cost, orep.last_final_cost, rtol=1e-11)
+    np.testing.assert_allclose(list(rep.se2_first), list(orep.se2_first), rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(np.array(rep.T_base_laser), np.array(orep.T_base_laser), rtol=0, atol=2e-7)
+    np.testing.assert_allclose(corners, oc, rtol=0, atol=1e-6)       # bar: 0.1 mm; we ask for 1 micron
+
+
+@pytest.mark.parametrize("seed,pert,pattern", [(11, (0.01, 0.01, 0.0), "raster"), (12, (0.008, -0.005, 0.6), "rosette"),
+                                               (13, (0.0, 0.0, 0.0), "raster"), (14, (-0.004, 0.011, -0.8), "raster")])
+def test_gridfit_solve_matches_oracle_trajectory(ctx, cfg, oracle, ocfg, seed, pert, pattern):
+    pts = synth.board_frame_cloud(100000, seed, pert=pert, pattern=pattern)
+    rc, oc, orep, _ = oracle.gridfit_solve(ocfg, pts)
+    assert rc == 0
+    corners, rep = ctx.gridfit_solve(cfg, pts)
+    _check_solve(corners, rep, oc, orep)
+
+
+def test_gridfit_solve_with_T_bl(ctx, cfg, oracle, ocfg):
+    pts = synth.board_frame_cloud(50000, 21, pert=(0.005, 0.0, 0.0))
+    a = 0.3
+    T_bl = np.array([[np.cos(a), -np.sin(a), 0, 0.5], [np.sin(a), np.cos(a), 0, -0.2], [0, 0, 1, 4.0], [0, 0, 0, 1]])
+    rc, oc, orep, _ = oracle.gridfit_solve(ocfg, pts, T_bl)
+    corners, rep = ctx.gridfit_solve(cfg, pts, T_bl)
+    _check_solve(corners, rep, oc, orep)
+
+
+def test_gridfit_solve_failure_status(ctx, cfg, oracle, ocfg):
+    pts = synth.board_frame_cloud(20000, 5)
+    pts = pts[pts[:, 0] < -0.05]
+    rc, oc, orep, _ = oracle.gridfit_solve(ocfg, pts)
+    corners, rep = ctx.gridfit_solve(cfg, pts)
+    assert rep.status == orep.status == 1
+    assert rep.outer_iterations == orep.outer_iterations and rep.pose_evals == orep.pose_evals
+    np.testing.assert_allclose(corners, oc, atol=1e-9)
+
+
+def test_batch_solve_ragged_frames(capi, ctx, cfg, oracle, ocfg):
+    sizes = [30000, 80000, 1000, 55555, 0, 64000]
+    frames = [synth.board_frame_cloud(max(n, 1), 100 + i, pert=(0.002 * i, -0.003, 0.1 * i))[:n] for i, n in enumerate(sizes)]
+    b = capi.Batch(ctx, cfg, len(sizes), max(sizes))
+    for f, p in enumerate(frames):
+        if len(p):
+            b.upload(f, p)
+    corners, reps = b.gridfit_solve()
+    for f, p in enumerate(frames):
+        if len(p) == 0:
+            assert reps[f].status == 2
+            continue
+        rc, oc, orep, _ = oracle.gridfit_solve(ocfg, p)
+        _check_solve(corners[f], reps[f], oc, orep)
+    # solving again from the resident (pristine) clouds gives identical answers
+    corners2, reps2 = b.gridfit_solve()
+    assert np.array_equal(corners, corners2)
+    mu, sg, pri = b.gmm_fit()
+    for f, p in enumerate(frames):
+        if len(p) < 10:
+            continue
+        m0, s0, p0 = oracle.gmm_fit_1d(p[:, 3], [15, 100], [15, 15])
+        np.testing.assert_allclose(mu[f], m0, rtol=1e-10); np.testing.assert_allclose(sg[f], s0, rtol=1e-9)
+        np.testing.assert_allclose(pri[f], p0, rtol=1e-10)
+    b.close()
+
+
+def test_batch_single_pose_pass(capi, ctx, cfg, oracle, ocfg):
+    frames, perts = synth.gridfit_batch(4, 50000, seed0=500)
+    b = capi.Batch(ctx, cfg, 4, 50000)
+    for f, p in enumerate(frames):
+        b.upload(f, p)
+    b.bin()
+    poses = np.array(perts)
+    b.sweep(poses)
+    res, jac, acc = b.read_eval(want_acc=True)
+    for f in range(4):
+        r0, j0, a0 = oracle.gridfit_eval(ocfg, frames[f], poses[f], want_acc=True)
+        assert np.array_equal(acc[f], a0)
+        np.testing.assert_allclose(res[f], r0, rtol=1e-12)
+    # multistart on the resident frame 2
+    P = synth.multistart_poses(4, 4, 4)
+    cost = b.multistart(2, P)
+    for k in range(0, len(P), 5):
+        np.testing.assert_allclose(cost[k], oracle.gridfit_cost(ocfg, frames[2], P[k]), rtol=1e-12)
+    assert int(np.argmin(cost)) == int(np.argmin([oracle.gridfit_cost(ocfg, frames[2], p) for p in P]))
+    b.close()
+
+
+def test_gmm_parity_and_labels(ctx, oracle):
+    pts = synth.board_frame_cloud(200000, 21)
+    mu, sg, pri = ctx.gmm_fit_1d(pts[:, 3], [15, 100], [15, 15])
+    m0, s0, p0 = oracle.gmm_fit_1d(pts[:, 3], [15, 100], [15, 15])
+    np.testing.assert_allclose(mu, m0, rtol=1e-11); np.testing.assert_allclose(sg, s0, rtol=1e-10)
+    np.testing.assert_allclose(pri, p0, rtol=1e-11)
+    # labels (PassThrough [3, thd] / [thd, 150], BoardSegmentation.cpp:140-157): identical except within 1 ulp of thd
+    for k in (1.7, 2.0):
+        t1, t0 = np.float32(mu[0] + k * sg[0]), np.float32(m0[0] + k * s0[0])
+        l1 = (pts[:, 3] >= 3) & (pts[:, 3] <= t1); l0 = (pts[:, 3] >= 3) & (pts[:, 3] <= t0)
+        diff = l1 != l0
+        assert np.all(np.abs(pts[diff, 3] - t0) <= np.spacing(t0))
+
+
+def test_plane_project_and_transform_bit_exact(ctx, oracle):
+    rng = np.random.default_rng(3)
+    n = 100003
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 2] = rng.uniform(3, 6, n); pts[:, 0] = rng.uniform(-1, 1, n); pts[:, 1] = rng.uniform(-1, 1, n); pts[:, 3] = rng.uniform(0, 150, n)
+    plane = np.array([0.1, -0.2, 1.0, -4.5])
+    assert np.array_equal(ctx.plane_project(pts, plane), oracle.plane_project(pts, plane))
+    a = 0.01
+    T = np.array([[np.cos(a), -np.sin(a), 0, 0.003], [np.sin(a), np.cos(a), 0, -0.002], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+    assert np.array_equal(ctx.transform_cloud(pts, T), oracle.transform_cloud(pts, T))
+    T3 = np.array([[0, -1, 0, 0.1], [0, 0, -1, 0.2], [1, 0, 0, 0.3], [0, 0, 0, 1]], np.float32)     # T_base (global.cpp:116-122)
+    assert np.array_equal(ctx.transform_cloud(pts, T3), oracle.transform_cloud(pts, T3))
+
+
+def test_ransac_counts_masks_bit_exact(ctx, oracle):
+    rng = np.random.default_rng(5)
+    n = 60000
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = 4.0 + rng.normal(0, 0.03, n); pts[:, 1] = rng.uniform(-1, 1, n); pts[:, 2] = rng.uniform(-1, 1, n)
+    pts[: n // 3, :3] = rng.uniform(-3, 3, (n // 3, 3)) + [4, 0, 0]
+    H = 800
+    tr = oracle.ransac_draw_triplets(n, H)
+    tr[5] = [7, 7, 9]                                        # degenerate sample -> invalid model
+    p0, v0, c0 = oracle.ransac_score(pts, tr, 0.08)
+    p1, v1, c1 = ctx.ransac_plane_score(pts, tr, 0.08)
+    assert np.array_equal(v0, v1) and v1[5] == 0
+    assert np.array_equal(p0.view(np.uint32), p1.view(np.uint32))      # planes bit-exact
+    assert np.array_equal(c0, c1)                                      # inlier counts exact
+    best, iters = oracle.ransac_replay(c1, v1, n)
+    m0 = oracle.plane_select(pts, p1[best], 0.08)
+    m1, ref1, cen1, ni = ctx.ransac_plane_select(pts, p1[best], 0.08)
+    assert np.array_equal(m0, m1) and ni == int(m0.sum()) == c1[best]
+    ref0, cen0 = oracle.plane_refine(pts, m0, p1[best])
+    np.testing.assert_allclose(ref1, ref0, rtol=0, atol=2e-7); np.testing.assert_allclose(cen1, cen0, rtol=0, atol=1e-6)
+    # masks with the refined model: identical except points within 1 ulp of the threshold
+    r0 = oracle.plane_select(pts, ref0, 0.08)
+    r1 = ctx.ransac_plane_select(pts, ref1, 0.08)[0]
+    if not np.array_equal(ref0, ref1):
+        assert (r0 != r1).mean() < 1e-4
+    else:
+        assert np.array_equal(r0, r1)
+
+
+def _pose_problem(oracle, F, seed=9, noise=1e-4):
+    rng = np.random.default_rng(seed)
+    Cn = 35
+    q = np.array([0.02, -0.015, 0.01, 0.0]); q[3] = np.sqrt(1 - (q[:3] ** 2).sum())
+    t = np.array([0.07, -0.08, 0.02])
+    R = oracle.quat_to_R([q[3], q[0], q[1], q[2]])
+    pc = np.zeros((F, Cn, 3)); img = np.zeros((F, Cn, 2))
+    for f in range(F):
+        base = np.array([rng.uniform(-1, 1), rng.uniform(-0.6, 0.6), rng.uniform(3.5, 5.5)])
+        g = np.array([[0.3 - 0.1 * c, 0.2 - 0.1 * r, 0.0] for r in range(5) for c in range(7)])
+        a = rng.uniform(-0.3, 0.3, 3)
+        Rb = oracle.quat_to_R(np.r_[np.sqrt(1 - (a ** 2).sum() / 4), a / 2])
+        pc[f] = g @ Rb.T + base
+        Pc = pc[f] @ R.T + t
+        img[f] = Pc[:, :2] / Pc[:, 2:3] + rng.normal(0, noise, (Cn, 2))
+    T0 = np.r_[q, t] + np.array([0.005, -0.004, 0.003, 0, 0.03, -0.02, 0.04]); T0[:4] /= np.linalg.norm(T0[:4])
+    return pc, img, T0, np.r_[q, t]
+
+
+@pytest.mark.parametrize("F", [5, 20, 256])
+def test_pose_eval_and_refine(ctx, cfg, oracle, ocfg, F):
+    pc, img, T0, Tgt = _pose_problem(oracle, F)
+    r0, j0 = oracle.pose_eval(pc, img, T0)
+    r1, j1 = ctx.pose_eval(pc, img, T0)
+    np.testing.assert_allclose(r1, r0, rtol=1e-12); np.testing.assert_allclose(j1, j0, rtol=1e-9, atol=1e-12)
+    rc0, Ta, c0a, c1a, ita = oracle.pose_refine(ocfg, pc, img, T0)
+    rc1, Tb, c0b, c1b, itb = ctx.pose_refine(cfg, pc, img, T0)
+    assert rc0 == rc1 == 0
+    np.testing.assert_allclose(c0b, c0a, rtol=1e-11)
+    # bar: extrinsic within 1e-4 rad and 0.1 mm of the reference path
+    assert np.abs(Tb[4:] - Ta[4:]).max() < 1e-4
+    dq = 2 * np.linalg.norm(Tb[:4] * np.sign(Tb[3]) - Ta[:4] * np.sign(Ta[3]))
+    assert dq < 1e-4
+    if F >= 20:
+        assert itb == ita and np.abs(Tb - Ta).max() < 1e-8
+
+
+def test_project_colorize_exact(ctx, cfg, oracle, ocfg):
+    pts = synth.frustum_cloud(300000, 2)
+    pts[:7, 2] = [0.0, -1.0, 1e-30, 5.0, -5.0, 0.0, 2.0]; pts[5, 0] = 0.0; pts[5, 1] = 0.0     # Z = 0, NaN, behind camera
+    img = synth.noise_image(4, cfg.cam_width, cfg.cam_height)
+    a = 0.02
+    T = np.array([[np.cos(a), 0, np.sin(a), 0.07], [0, 1, 0, -0.08], [-np.sin(a), 0, np.cos(a), 0.02], [0, 0, 0, 1]], np.float32)
+    rgb0, pix0, in0 = oracle.project_colorize(ocfg, pts, T, img)
+    rgb1, pix1, in1 = ctx.project_colorize(cfg, pts, T, img)
+    assert np.array_equal(in0, in1) and np.array_equal(pix0, pix1) and np.array_equal(rgb0, rgb1)
+    assert 0.2 < in1.mean() < 0.95
+
+
+def test_kernel_launch_counter(ctx, cfg):
+    before = ctx.kernel_launches()
+    ctx.gmm_fit_1d(np.linspace(5, 120, 1000, dtype=np.float32), [15, 100], [15, 15])
+    assert ctx.kernel_launches() - before == 20

@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the calibration hot path (contract in the task prompt, section 4).
+
+Metric (BASELINE.json): grid-fit residual evals/s in Mpts·poses/s = (board points x distinct poses at which all
+82 residuals were evaluated) / seconds / 1e6, on BASELINE configs[1]: 20 synthetic Avia/Horizon raster frames
+x 500k points, one step = GMM EM (GMMFit::fit_1d) + the full opt_grid_fitting solve of every frame.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference ...                     the reference's CPU path (oracle port) on host cores
+
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "grid-fit residual evals/s"
+UNIT = "Mpts·poses/s"
+WORKLOAD = "configs[1]: 20 synthetic Avia/Horizon raster frames x 500k pts, 8x6 board, GMM EM + grid fit"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=20)
+    ap.add_argument("--pts", type=int, default=500000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_frames(n_frames, n_pts, rank):
+    from rclc_b200 import synth
+    frames, perts = synth.gridfit_batch(n_frames, n_pts, seed0=1000 + 100 * rank, pattern="raster")
+    return frames, perts
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, during the timed region)
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (CPU port of the reference path), OpenMP-over-frames like the
+# reference (apps/Calibrate.cpp:90-92) — here a thread per frame, ctypes releases the GIL.
+# ----------------------------------------------------------------------------------------------------------
+def cpu_step(frames, cores):
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as O
+    cfg = O.config()
+
+    def one(p):
+        O.gmm_fit_1d(p[:, 3], [15, 100], [15, 15], cfg.gmm_iters)
+        rc, corners, rep, _ = O.gridfit_solve(cfg, p)
+        return len(p) * rep.pose_evals
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        work = sum(ex.map(one, frames))
+    return work, time.perf_counter() - t0
+
+
+def cpu_sample_frames(frames, cores):
+    """Bounded sample: about 10-30 s of CPU work. A 500k-point frame takes ~3 s on one core."""
+    n = max(1, min(len(frames), cores * 2))
+    return frames[:n]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames, _ = make_frames(args.frames, args.pts, 0)
+    sample = cpu_sample_frames(frames, cores)
+    for _ in range(args.warmup):
+        cpu_step(sample[:max(1, min(len(sample), cores))], cores)
+    work = secs = 0.0
+    for _ in range(args.steps):
+        w, s = cpu_step(sample, cores)
+        work += w; secs += s
+    value = work / secs / 1e6
+    desc = f"{len(sample)} of {len(frames)} frames x {args.pts} pts per step, GMM EM + full grid fit, thread per frame"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames": args.frames, "pts_per_frame": args.pts},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU restatement (oracle) of the reference path: PCL/Ceres/Eigen are absent, the reference cannot be built"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from rclc_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    cfg = capi.config()
+    ctx = capi.Context(local)
+    frames, perts = make_frames(args.frames, args.pts, rank)
+    F = len(frames)
+    batch = capi.Batch(ctx, cfg, F, max(len(p) for p in frames))
+    for f, p in enumerate(frames):
+        batch.upload(f, p)
+    total_pts = batch.total_points()
+    h2d_bytes = total_pts * 16
+    d2h_bytes = F * (cfg.n_corners() * 3 * 8 + 6 * 8 * 2) + F * 256
+
+    def step_resident():
+        batch.gmm_fit()
+        corners, reps = batch.gridfit_solve()
+        return sum(len(frames[f]) * reps[f].pose_evals for f in range(F)), corners
+
+    def step_e2e():
+        for f, p in enumerate(frames):
+            batch.upload(f, p)                       # host -> pinned -> device, every step
+        batch.gmm_fit()
+        corners, reps = batch.gridfit_solve()        # device -> host: corners + reports
+        return sum(len(frames[f]) * reps[f].pose_evals for f in range(F)), corners
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = ctx.kernel_launches()
+    ctx.timer_start()
+    work = 0
+    for _ in range(args.steps):
+        w, corners = step_resident()
+        work += w
+    ms = ctx.timer_stop_ms()
+    launches = ctx.kernel_launches() - l0
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    work_all = sum_over_ranks(float(work))
+    value = work_all / (ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region ----
+    step_e2e()
+    barrier()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    work_e = 0
+    for _ in range(args.steps):
+        w, _ = step_e2e()
+        work_e += w
+    ms_e = ctx.timer_stop_ms()
+    wall_e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    ms_e = max_over_ranks(max(ms_e, wall_e))
+    e2e_value = sum_over_ranks(float(work_e)) / (ms_e * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (k_sweep, 16 B per point·pose), timed alone, cold L2 ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    batch.bin()
+    poses = np.array(perts, dtype=np.float64)
+    for _ in range(3):
+        batch.sweep(poses)
+    ctx.synchronize()
+    durs = []
+    for _ in range(20):
+        ctx.flush_l2()
+        ctx.synchronize()
+        ctx.timer_start()
+        batch.sweep(poses)
+        durs.append(ctx.timer_stop_ms())
+    sweep_ms = float(np.median(durs))
+    achieved = total_pts * 16 / (sweep_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_sweep", "launch_ms": sweep_ms, "algorithmic_bytes_per_launch": total_pts * 16,
+                "peak_source": peak_src, "timing": "CUDA events on the ctx stream, L2 flushed before each launch, median of 20",
+                "single_pose_pass_Mpts_poses_per_s": total_pts / (sweep_ms * 1e-3) / 1e6}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": F, "pts_per_frame": args.pts,
+                       "l2": "working set 3 x %d MB per GPU exceeds the 126 MB L2; no flush between steps" % (total_pts * 16 // 2**20)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": ms_e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "calib_wall_ms": {"grid_fit_plus_gmm_per_step": ms / args.steps, "frames": F * world}}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = cpu_sample_frames(frames, cores)
+        w, s = cpu_step(sample, cores)
+        line["cpu_baseline"] = {"value": w / s / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{len(sample)} of {F} frames x {args.pts} pts, GMM EM + full grid fit, one thread per frame, {s:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    batch.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -252,8 +252,7 @@ def test_pose_eval_and_refine(ctx, cfg, oracle, ocfg, F):
     assert np.abs(Tb[4:] - Ta[4:]).max() < 1e-4
     dq = 2 * np.linalg.norm(Tb[:4] * np.sign(Tb[3]) - Ta[:4] * np.sign(Ta[3]))
     assert dq < 1e-4
-    if F >= 20:
-        assert itb == ita and np.abs(Tb - Ta).max() < 1e-8
+    assert itb == ita
 
 
 def test_project_colorize_exact(ctx, cfg, oracle, ocfg):

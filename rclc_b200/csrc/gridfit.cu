@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace rclc {
 
@@ -252,6 +253,9 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
         c.rebin = 1;
         c.n_items = 0;
         c.n_binned = 0;
+        c.use_exact = 0;
+        c.pad_ = 0;
+        bv.sweep_done[f] = 0;
         for (int k = 0; k < 8; ++k) c.move[k] = 0.f;
         c.move[0] = 1.f;
         c.move[5] = 1.f;
@@ -271,16 +275,18 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_count / k_scatter: move (float) + counting sort by lattice cell
+// k_count / k_scatter: move (float) + counting sort by lattice cell. Grid-stride over chunks so that the
+// (frequent) launches in which no frame needs a re-bin cost only a few hundred early-exit CTAs.
 // ------------------------------------------------------------------------------------------------
+constexpr int kBinGridX = 64;
+
 __global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
 {
     const int f = blockIdx.y;
     const FrameCtl& c = bv.ctl[f];
     if (!c.rebin) return;
     const int64_t n = bv.n_pts[f];
-    const int64_t base = (int64_t)blockIdx.x * kBinChunk;
-    if (base >= n) return;
+    if ((int64_t)blockIdx.x * kBinChunk >= n) return;
     __shared__ int s_hist[kMaxCells];
     const int nc = bv.geom.ncells;
     for (int k = threadIdx.x; k < nc; k += kBinThreads) s_hist[k] = 0;
@@ -288,15 +294,17 @@ __global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
     const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
     const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
     const float4* src = bv.raw + (size_t)f * bv.frame_stride;
+    for (int64_t base = (int64_t)blockIdx.x * kBinChunk; base < n; base += (int64_t)gridDim.x * kBinChunk) {
 #pragma unroll
-    for (int p = 0; p < kBinP; ++p) {
-        const int64_t idx = base + p * kBinThreads + threadIdx.x;
-        if (idx < n) {
-            const float4 q = __ldg(src + idx);
-            const float x = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
-            const float y = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
-            const int cell = cell_of(bv.geom, x, y);
-            if (cell >= 0) atomicAdd(&s_hist[cell], 1);
+        for (int p = 0; p < kBinP; ++p) {
+            const int64_t idx = base + p * kBinThreads + threadIdx.x;
+            if (idx < n) {
+                const float4 q = __ldg(src + idx);
+                const float x = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
+                const float y = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
+                const int cell = cell_of(bv.geom, x, y);
+                if (cell >= 0) atomicAdd(&s_hist[cell], 1);
+            }
         }
     }
     __syncthreads();
@@ -310,14 +318,15 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
     FrameCtl& c = bv.ctl[f];
     if (!c.rebin) return;
     const int64_t n = bv.n_pts[f];
-    const int64_t base = (int64_t)blockIdx.x * kBinChunk;
-    if (base >= n && blockIdx.x != 0) return;
+    if ((int64_t)blockIdx.x * kBinChunk >= n && blockIdx.x != 0) return;
     __shared__ int s_off[kMaxCells];
     __shared__ int s_loc[kMaxCells];
     __shared__ int s_part[kBinThreads];
+    __shared__ int s_bad;
     const int nc = bv.geom.ncells;
     const int tid = threadIdx.x;
-    for (int k = tid; k < nc; k += kBinThreads) { s_off[k] = bv.hist[(size_t)f * nc + k]; s_loc[k] = 0; }
+    for (int k = tid; k < nc; k += kBinThreads) s_off[k] = bv.hist[(size_t)f * nc + k];
+    if (tid == 0) s_bad = 0;
     __syncthreads();
     const int total = block_exclusive_scan<kBinThreads>(s_off, nc, s_part);
 
@@ -325,156 +334,74 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
     const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
     float4* raw = bv.raw + (size_t)f * bv.frame_stride;
     float4* dstb = bv.binned + (size_t)f * bv.frame_stride;
-    float px[kBinP], py[kBinP], pz[kBinP], pi[kBinP];
-    int pcell[kBinP], prank[kBinP];
+    for (int64_t base = (int64_t)blockIdx.x * kBinChunk; base < n; base += (int64_t)gridDim.x * kBinChunk) {
+        for (int k = tid; k < nc; k += kBinThreads) s_loc[k] = 0;
+        __syncthreads();
+        float px[kBinP], py[kBinP], pz[kBinP], pi[kBinP];
+        int pcell[kBinP], prank[kBinP];
+        bool bad = false;
 #pragma unroll
-    for (int p = 0; p < kBinP; ++p) {
-        const int64_t idx = base + p * kBinThreads + tid;
-        pcell[p] = -1;
-        if (idx < n) {
-            const float4 q = raw[idx];
-            px[p] = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
-            py[p] = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
-            pz[p] = q.z;
-            pi[p] = q.w;
-            raw[idx] = make_float4(px[p], py[p], pz[p], pi[p]);
-            pcell[p] = cell_of(bv.geom, px[p], py[p]);
-            if (pcell[p] >= 0) prank[p] = atomicAdd(&s_loc[pcell[p]], 1);
+        for (int p = 0; p < kBinP; ++p) {
+            const int64_t idx = base + p * kBinThreads + tid;
+            pcell[p] = -1;
+            if (idx < n) {
+                const float4 q = raw[idx];
+                px[p] = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
+                py[p] = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
+                pz[p] = q.z;
+                pi[p] = q.w;
+                raw[idx] = make_float4(px[p], py[p], pz[p], pi[p]);
+                pcell[p] = cell_of(bv.geom, px[p], py[p]);
+                if (pcell[p] >= 0) {
+                    prank[p] = atomicAdd(&s_loc[pcell[p]], 1);
+                    // the fast sweep carries counts inside its fp64 sums: exact for I in {0} U [2^-3, 256)
+                    bad |= !(pi[p] == 0.f || (pi[p] >= 0.125f && pi[p] < 256.f));
+                }
+            }
         }
-    }
-    __syncthreads();
-    for (int k = tid; k < nc; k += kBinThreads) {
-        const int cnt = s_loc[k];
-        if (cnt) s_loc[k] = atomicAdd(&bv.cursor[(size_t)f * nc + k], cnt);     // base of this CTA inside the cell
-    }
-    __syncthreads();
+        if (bad) s_bad = 1;
+        __syncthreads();
+        for (int k = tid; k < nc; k += kBinThreads) {
+            const int cnt = s_loc[k];
+            if (cnt) s_loc[k] = atomicAdd(&bv.cursor[(size_t)f * nc + k], cnt);     // base of this chunk inside the cell
+        }
+        __syncthreads();
 #pragma unroll
-    for (int p = 0; p < kBinP; ++p) {
-        if (pcell[p] >= 0) {
-            const int dst = s_off[pcell[p]] + s_loc[pcell[p]] + prank[p];
-            const uint32_t mask = neighbour_mask(bv, pcell[p], px[p], py[p], pz[p]);
-            dstb[dst] = make_float4(px[p], py[p], pi[p], __uint_as_float(mask));
+        for (int p = 0; p < kBinP; ++p) {
+            if (pcell[p] >= 0) {
+                const int dst = s_off[pcell[p]] + s_loc[pcell[p]] + prank[p];
+                const uint32_t mask = neighbour_mask(bv, pcell[p], px[p], py[p], pz[p]);
+                dstb[dst] = make_float4(px[p], py[p], pi[p], __uint_as_float(mask));
+            }
         }
+        __syncthreads();
     }
+    if (tid == 0 && s_bad) atomicOr(&c.use_exact, 1);
     if (blockIdx.x == 0) {
-        // work items: chunks of <= kChunk points of one cell
+        // work items: a cell with cnt points becomes ceil(cnt / kChunk) balanced chunks
         __syncthreads();
         for (int k = tid; k < nc; k += kBinThreads) {
             const int cnt = bv.hist[(size_t)f * nc + k];
             s_loc[k] = (cnt + kChunk - 1) / kChunk;
         }
         __syncthreads();
-        // s_off must survive: scan s_loc into item offsets
-        const int n_items = block_exclusive_scan<kBinThreads>(s_loc, nc, s_part);
+        const int n_items = block_exclusive_scan<kBinThreads>(s_loc, nc, s_part);     // s_off survives
         int4* items = bv.items + (size_t)f * bv.max_items;
         for (int k = tid; k < nc; k += kBinThreads) {
             const int cnt = bv.hist[(size_t)f * nc + k];
+            if (cnt == 0) continue;
+            const int nch = (cnt + kChunk - 1) / kChunk;
+            const int per = ((cnt + nch - 1) / nch + 31) & ~31;
             int pos = s_loc[k];
-            for (int j = 0; j * kChunk < cnt; ++j)
-                items[pos++] = make_int4(k, s_off[k] + j * kChunk, min(kChunk, cnt - j * kChunk), 0);
+            for (int j = 0; j < nch; ++j) {
+                const int st = j * per;
+                if (st >= cnt) { items[pos++] = make_int4(k, s_off[k], 0, 0); continue; }
+                items[pos++] = make_int4(k, s_off[k] + st, min(per, cnt - st), 0);
+            }
         }
         if (tid == 0) { c.n_items = n_items; c.n_binned = total; }
     }
 }
-
-// ------------------------------------------------------------------------------------------------
-// k_sweep: the hot loop. One CTA = one chunk (<= kChunk points) of one lattice cell.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kSweepThreads) k_sweep(BatchView bv)
-{
-    const int f = blockIdx.y;
-    const FrameCtl& c = bv.ctl[f];
-    if (!c.sweep_active) return;
-    const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;      // frame whose points are read
-    const int item = blockIdx.x;
-    if (item >= c.n_items) return;
-    const int4 it = bv.items[(size_t)fd * bv.max_items + item];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kSweepThreads / 32;
-
-    __shared__ double s_part[NW][kCand][16];
-    __shared__ int s_tid[kCand];
-    __shared__ double s_rx[kCand], s_ry[kCand];
-    if (tid < kCand) {
-        const int t = bv.cell_cand[(size_t)it.x * kCand + tid];
-        s_tid[tid] = t;
-        if (t >= 0) { const double2 r = bv.tgt_xy[t]; s_rx[tid] = r.x; s_ry[tid] = r.y; }
-    }
-    for (int k = tid; k < NW * kCand * 16; k += kSweepThreads) (&s_part[0][0][0])[k] = 0.0;
-
-    const PoseCoef pc = c.pose;
-    const double rg2 = bv.geom.rg2, rc2 = bv.geom.rc2;
-    const float4* src = bv.binned + (size_t)fd * bv.frame_stride + it.y;
-    double xt[kSweepP], yt[kSweepP];
-    float inten[kSweepP];
-    uint32_t mk[kSweepP];
-    uint32_t any_mask = 0;
-#pragma unroll
-    for (int p = 0; p < kSweepP; ++p) {
-        const int idx = p * kSweepThreads + tid;
-        mk[p] = 0;
-        xt[p] = 0; yt[p] = 0; inten[p] = 0;
-        if (idx < it.z) {
-            const float4 q = __ldg(src + idx);
-            // board_fitting_cost.h:132-133  R * (p + t), double maths on float-stored points
-            const double vx = __dadd_rn((double)q.x, pc.tx), vy = __dadd_rn((double)q.y, pc.ty);
-            xt[p] = __dadd_rn(__dmul_rn(pc.r00, vx), __dmul_rn(pc.r01, vy));
-            yt[p] = __dadd_rn(__dmul_rn(pc.r10, vx), __dmul_rn(pc.r11, vy));
-            inten[p] = q.z;
-            mk[p] = __float_as_uint(q.w);
-            any_mask |= mk[p];
-        }
-    }
-    any_mask = __reduce_or_sync(0xffffffffu, any_mask);
-    __syncthreads();
-
-    for (int k = 0; k < kCand; ++k) {
-        if (s_tid[k] < 0 || !((any_mask >> k) & 1u)) continue;          // warp-uniform
-        const double ref_x = s_rx[k], ref_y = s_ry[k];
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0, s7 = 0;   // cost d,u,l,r | interval d,u,l,r
-        int c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
-#pragma unroll
-        for (int p = 0; p < kSweepP; ++p) {
-            if (!((mk[p] >> k) & 1u)) continue;
-            const double dx = fmax(1e-14, fabs(__dsub_rn(ref_x, xt[p])));          // :138-139
-            const double dy = fmax(1e-14, fabs(__dsub_rn(ref_y, yt[p])));
-            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));     // :140
-            if (d2 > rg2) continue;                                                // :142
-            const bool in_cost = d2 < rc2;                                         // :151
-            const bool down = yt[p] > ref_y;                                       // :147
-            const bool right = xt[p] > ref_x;                                      // :178
-            const double I = (double)inten[p];
-            if (in_cost) {
-                if (down) { s0 += I; c0++; } else { s1 += I; c1++; }
-                if (right) { s3 += I; c3++; } else { s2 += I; c2++; }
-            } else {
-                if (down) { s4 += I; c4++; } else { s5 += I; c5++; }
-                if (right) { s7 += I; c7++; } else { s6 += I; c6++; }
-            }
-        }
-        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-        s4 = warp_sum(s4); s5 = warp_sum(s5); s6 = warp_sum(s6); s7 = warp_sum(s7);
-        c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3);
-        c4 = warp_sum(c4); c5 = warp_sum(c5); c6 = warp_sum(c6); c7 = warp_sum(c7);
-        if (lane == 0) {
-            double* o = s_part[warp][k];
-            o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = c0; o[5] = c1; o[6] = c2; o[7] = c3;
-            o[8] = s4; o[9] = s5; o[10] = s6; o[11] = s7; o[12] = c4; o[13] = c5; o[14] = c6; o[15] = c7;
-        }
-    }
-    __syncthreads();
-    {
-        const int k = tid >> 4, j = tid & 15;                       // 128 threads == 8 candidates x 16 accumulators
-        const int t = s_tid[k];
-        if (t >= 0) {
-            double v = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) v += s_part[w][k][j];
-            if (v != 0.0) atomicAdd(&bv.acc[((size_t)f * bv.geom.nt + t) * 16 + j], v);
-        }
-    }
-}
-static_assert(kSweepThreads == kCand * 16, "final reduction maps one thread to one (candidate, accumulator)");
 
 // ------------------------------------------------------------------------------------------------
 // Residual / Jacobian of one target from its 16 accumulators (board_fitting_cost.h:211-260)
@@ -778,28 +705,39 @@ __device__ void lm_advance(const GridGeom& g, LmState& s, FrameCtl& c, const Eva
     }
 }
 
-constexpr int kLmThreads = 128;
+constexpr int kLmThreads = kSweepThreads;
 
-__global__ void __launch_bounds__(kLmThreads) k_lm(BatchView bv)
+// One CTA: residuals + heuristic Jacobian + Huber corrector for every target from the accumulator table,
+// 3x3 normal equations reduced in shared memory, then the Ceres step / accept-reject / radius logic and the
+// opt_grid_fitting outer-loop bookkeeping on one thread. The frame's state is staged through shared memory.
+__device__ void lm_frame_step(const BatchView& bv, int f)
 {
-    const int f = blockIdx.x;
-    FrameCtl& c = bv.ctl[f];
-    LmState& s = bv.lm[f];
-    if (s.phase == PH_DONE || !c.sweep_active) return;
+    __shared__ LmState s_lm;
+    __shared__ FrameCtl s_ctl;
+    __shared__ double s_red[kLmThreads / 32][12];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const GridGeom& g = bv.geom;
-    const PoseCoef pc = c.pose;
-    __shared__ double s_red[kLmThreads / 32][12];
-    __shared__ EvalSums s_eval;
+    {
+        const int* gl = reinterpret_cast<const int*>(&bv.lm[f]);
+        int* sl = reinterpret_cast<int*>(&s_lm);
+        for (int k = tid; k < (int)(sizeof(LmState) / 4); k += kLmThreads) sl[k] = __ldcg(gl + k);
+        const int* gc = reinterpret_cast<const int*>(&bv.ctl[f]);
+        int* sc = reinterpret_cast<int*>(&s_ctl);
+        for (int k = tid; k < (int)(sizeof(FrameCtl) / 4); k += kLmThreads) sc[k] = __ldcg(gc + k);
+    }
+    __syncthreads();
+    const PoseCoef pc = s_ctl.pose;
     const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
     const double cth = cos(theta), sth = sin(theta);
-
     double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cost, A00,A01,A02,A11,A12,A22, b0,b1,b2
     int bad_r = 0, bad_j = 0;
     double* acc = bv.acc + (size_t)f * g.nt * 16;
     for (int t = tid; t < g.nt; t += kLmThreads) {
+        double a16[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a16[k] = __ldcg(acc + (size_t)t * 16 + k);
         double r, j0, j1, j2;
-        target_residual(acc + (size_t)t * 16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
+        target_residual(a16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
         if (!isfinite(r)) bad_r = 1;
         if (!(isfinite(j0) && isfinite(j1) && isfinite(j2))) bad_j = 1;
         // HuberLoss + Corrector (rho'' <= 0 branch): cost 0.5 rho0, r *= sqrt(rho1), J *= sqrt(rho1)
@@ -814,9 +752,8 @@ __global__ void __launch_bounds__(kLmThreads) k_lm(BatchView bv)
         sums[4] += j1 * j1; sums[5] += j1 * j2; sums[6] += j2 * j2;
         sums[7] += j0 * r;  sums[8] += j1 * r;  sums[9] += j2 * r;
     }
-    // consume + clear the accumulator table for the next sweep
     __syncthreads();
-    for (int k = tid; k < g.nt * 16; k += kLmThreads) acc[k] = 0.0;
+    for (int k = tid; k < g.nt * 16; k += kLmThreads) acc[k] = 0.0;      // consumed: clear for the next sweep
 #pragma unroll
     for (int k = 0; k < 10; ++k) sums[k] = warp_sum(sums[k]);
     bad_r = __any_sync(0xffffffffu, bad_r);
@@ -836,14 +773,288 @@ __global__ void __launch_bounds__(kLmThreads) k_lm(BatchView bv)
         for (int k = 0; k < 3; ++k) e.b[k] = tot[7 + k];
         e.res_valid = tot[10] == 0.0;
         e.jac_valid = e.res_valid && tot[11] == 0.0;
-        lm_advance(g, s, c, e, bv.corners + (size_t)f * g.nc * 3, bv.n_done);
+        lm_advance(g, s_lm, s_ctl, e, bv.corners + (size_t)f * g.nc * 3, bv.n_done);
     }
     __syncthreads();
-    if (c.rebin) {
+    {
+        int* gl = reinterpret_cast<int*>(&bv.lm[f]);
+        const int* sl = reinterpret_cast<const int*>(&s_lm);
+        for (int k = tid; k < (int)(sizeof(LmState) / 4); k += kLmThreads) gl[k] = sl[k];
+        int* gc = reinterpret_cast<int*>(&bv.ctl[f]);
+        const int* sc = reinterpret_cast<const int*>(&s_ctl);
+        for (int k = tid; k < (int)(sizeof(FrameCtl) / 4); k += kLmThreads) gc[k] = sc[k];
+    }
+    if (s_ctl.rebin) {
         const int nc = g.ncells;
         for (int k = tid; k < nc; k += kLmThreads) { bv.hist[(size_t)f * nc + k] = 0; bv.cursor[(size_t)f * nc + k] = 0; }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// k_sweep: the hot loop. One CTA = one chunk (<= kChunk points) of one lattice cell; blockIdx.y = frame.
+//
+//  * pose-aware culling: a candidate target is visited only if its gradient disc, pulled back through
+//    the trial pose, can touch the cell rectangle (typically 2-3 of the 8 candidates);
+//  * predicates in fp32 with a rigorous rounding-error bound E on the transformed coordinates and E2
+//    on the squared distance; a point whose fp32 value lies within the bound of ANY decision boundary
+//    (gradient circle, cost circle, the two half-plane lines) is re-evaluated exactly like the
+//    reference (double maths, no FMA contraction) — so the class of every point equals the oracle's;
+//  * 6 nested totals per candidate (in-disc, &down, &right, cost, cost&down, cost&right) accumulated in
+//    double; each addend is I + 2^17, so the COUNT rides in the high bits of the same exact sum (valid for
+//    I in {0} U [2^-3, 256) — k_scatter checks; other frames take the all-fp64 body);
+//  * the last CTA of a frame to finish runs the LM step (lm_frame_step) — no separate launch.
+// ------------------------------------------------------------------------------------------------
+constexpr double kCntUnit = 131072.0;           // 2^17 > 512 points x 256
+
+struct ExactClass { bool in, cost, down, right; };
+
+__device__ __noinline__ ExactClass classify_exact(const float4* __restrict__ src, int idx, const PoseCoef& pc, double ref_x, double ref_y,
+                                                  double rg2, double rc2)
+{
+    const float4 q = __ldg(src + idx);
+    const double vx = __dadd_rn((double)q.x, pc.tx), vy = __dadd_rn((double)q.y, pc.ty);      // board_fitting_cost.h:132-133
+    const double xt = __dadd_rn(__dmul_rn(pc.r00, vx), __dmul_rn(pc.r01, vy));
+    const double yt = __dadd_rn(__dmul_rn(pc.r10, vx), __dmul_rn(pc.r11, vy));
+    const double dx = fmax(1e-14, fabs(__dsub_rn(ref_x, xt)));                                // :138-139
+    const double dy = fmax(1e-14, fabs(__dsub_rn(ref_y, yt)));
+    const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));                        // :140
+    ExactClass e;
+    e.in = !(d2 > rg2);                                                                       // :142
+    e.cost = d2 < rc2;                                                                        // :151
+    e.down = yt > ref_y;                                                                      // :147
+    e.right = xt > ref_x;                                                                     // :178
+    return e;
+}
+
+// expands the 6 nested totals of one warp into the reference's 16 accumulators
+__device__ __forceinline__ void store_totals(double* o, double tI, double dI, double rI, double cI, double cdI, double crI,
+                                             double tN, double dN, double rN, double cN, double cdN, double crN)
+{
+    o[0] = cdI; o[1] = cI - cdI; o[2] = cI - crI; o[3] = crI;                                  // cost disc: down, up, left, right
+    o[4] = cdN; o[5] = cN - cdN; o[6] = cN - crN; o[7] = crN;
+    o[8] = dI - cdI; o[9] = (tI - dI) - (cI - cdI); o[10] = (tI - rI) - (cI - crI); o[11] = rI - crI;   // interval annulus
+    o[12] = dN - cdN; o[13] = (tN - dN) - (cN - cdN); o[14] = (tN - rN) - (cN - crN); o[15] = rN - crN;
+}
+
+__global__ void __launch_bounds__(kSweepThreads) k_sweep(BatchView bv)
+{
+    const int f = blockIdx.y;
+    const FrameCtl& c = bv.ctl[f];
+    if (!c.sweep_active) return;
+    const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;      // frame whose points are read
+    const int item = blockIdx.x;
+    const int n_items = c.n_items;
+    if (item >= max(n_items, 1)) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kSweepThreads / 32;
+    constexpr int P = kSweepP;
+
+    __shared__ double s_part[NW][kCand][16];
+    __shared__ int s_tid[kCand];
+    __shared__ double s_rx[kCand], s_ry[kCand];
+    __shared__ int s_act[kCand];
+    __shared__ int s_nact;
+    __shared__ float s_E;
+    __shared__ int s_last;
+
+    const PoseCoef pc = c.pose;
+    const double rg2 = bv.geom.rg2, rc2 = bv.geom.rc2;
+    if (n_items > 0) {
+        const int4 it = bv.items[(size_t)fd * bv.max_items + item];
+        const bool exact_body = bv.force_exact || c.use_exact;
+        if (tid < kCand) {
+            const int t = bv.cell_cand[(size_t)it.x * kCand + tid];
+            s_tid[tid] = t;
+            // cell rectangle in the (un-posed) frame the points are stored in, with a safety margin
+            const int ca = it.x % bv.geom.ncx, cb = it.x / bv.geom.ncx;
+            const double x0 = (bv.geom.i0 + ca) * bv.geom.g - 1e-6, x1 = (bv.geom.i0 + ca + 1) * bv.geom.g + 1e-6;
+            const double y0 = (bv.geom.j0 + cb) * bv.geom.g - 1e-6, y1 = (bv.geom.j0 + cb + 1) * bv.geom.g + 1e-6;
+            bool active = false;
+            if (t >= 0) {
+                const double2 r = bv.tgt_xy[t];
+                s_rx[tid] = r.x; s_ry[tid] = r.y;
+                // p' = R (p + t)  =>  |p' - ref| = |p - (R^T ref - t)|
+                const double cx = pc.r00 * r.x + pc.r10 * r.y - pc.tx, cy = pc.r01 * r.x + pc.r11 * r.y - pc.ty;
+                const double ex = fmax(fmax(x0 - cx, cx - x1), 0.0), ey = fmax(fmax(y0 - cy, cy - y1), 0.0);
+                const double reach = sqrt(rg2) + 1e-5;
+                active = exact_body || (ex * ex + ey * ey) <= reach * reach;
+            }
+            const unsigned b = __ballot_sync(0xffu, active);
+            if (active) s_act[__popc(b & ((1u << tid) - 1u))] = tid;
+            if (tid == 0) {
+                s_nact = __popc(b);
+                const double Bc = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))) + fabs(pc.tx) + fabs(pc.ty) + 0.1;
+                s_E = (float)(12.0 * 5.9604644775390625e-8 * Bc + 1e-9);
+            }
+        }
+        for (int k = tid; k < NW * kCand * 16; k += kSweepThreads) (&s_part[0][0][0])[k] = 0.0;
+        const float4* src = bv.binned + (size_t)fd * bv.frame_stride + it.y;
+        const int count = it.z;
+        const int np = (count + kSweepThreads - 1) / kSweepThreads;            // uniform trip count (<= P)
+        __syncthreads();
+        const int nact = s_nact;
+
+        if (!exact_body) {
+            const float r00f = (float)pc.r00, r01f = (float)pc.r01, r10f = (float)pc.r10, r11f = (float)pc.r11;
+            const float txf = (float)pc.tx, tyf = (float)pc.ty;
+            float xt[P], yt[P];
+            double io[P];
+            uint32_t mkw[P / 4];
+#pragma unroll
+            for (int w = 0; w < P / 4; ++w) mkw[w] = 0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                xt[p] = 0.f; yt[p] = 0.f; io[p] = 0.0;
+                if (p < np) {
+                    const int idx = p * kSweepThreads + tid;
+                    if (idx < count) {
+                        const float4 q = __ldg(src + idx);
+                        const float vx = q.x + txf, vy = q.y + tyf;
+                        xt[p] = fmaf(r00f, vx, r01f * vy);
+                        yt[p] = fmaf(r10f, vx, r11f * vy);
+                        io[p] = (double)q.z + kCntUnit;
+                        mkw[p >> 2] |= (__float_as_uint(q.w) & 0xffu) << (8 * (p & 3));
+                    }
+                }
+            }
+            const float E = s_E;
+            const float E2 = 2.9f * sqrtf((float)rg2) * E + 3e-7f * (float)rg2 + 2.f * E * E + 1e-9f;
+            const float rg2_hi = (float)rg2 + E2, rg2_lo = (float)rg2 - E2;   // [lo, hi]: uncertain band of the gradient circle
+            const float rc2f = (float)rc2;
+            for (int a = 0; a < nact; ++a) {
+                const int k = s_act[a];
+                const double ref_x = s_rx[k], ref_y = s_ry[k];
+                const float rxf = (float)ref_x, ryf = (float)ref_y;
+                double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;      // in, in&down, in&right, cost, cost&down, cost&right
+                uint32_t mk_k[P / 4];
+#pragma unroll
+                for (int w = 0; w < P / 4; ++w) mk_k[w] = mkw[w] >> k;      // bit 8*(p&3) of word p>>2 = membership of point p
+                uint32_t uncbits = 0;                                        // pairs that need the exact evaluation
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    if (p < np) {
+                        const float dxs = rxf - xt[p], dys = ryf - yt[p];
+                        const float d2 = fmaf(dxs, dxs, dys * dys);
+                        // pin  = member & certainly inside the gradient disc & farther than the error bound from the cost
+                        //        circle and from both half-plane lines  -> class decided in fp32
+                        // punc = member & possibly inside & not pin      -> exact re-evaluation after the loop
+                        asm("{\n\t"
+                            ".reg .pred pm, pin, pnin, pc, pid, pir, pcd, pcr, pu;\n\t"
+                            ".reg .f32 t, ax, ay;\n\t"
+                            ".reg .b32 mb;\n\t"
+                            "and.b32 mb, %7, %8;\n\t"
+                            "setp.ne.u32 pm, mb, 0;\n\t"
+                            "setp.lt.and.f32 pin, %9, %12, pm;\n\t"
+                            "sub.f32 t, %9, %14;\n\t"
+                            "abs.f32 t, t;\n\t"
+                            "setp.gt.and.f32 pin, t, %15, pin;\n\t"
+                            "abs.f32 ax, %10;\n\t"
+                            "abs.f32 ay, %11;\n\t"
+                            "setp.gt.and.f32 pin, ax, %16, pin;\n\t"
+                            "setp.gt.and.f32 pin, ay, %16, pin;\n\t"
+                            "not.pred pnin, pin;\n\t"
+                            "setp.le.and.f32 pu, %9, %13, pm;\n\t"
+                            "and.pred pu, pu, pnin;\n\t"
+                            "@pu or.b32 %6, %6, %18;\n\t"
+                            "setp.lt.and.f32 pc, %9, %14, pin;\n\t"
+                            "setp.lt.and.f32 pid, %11, 0f00000000, pin;\n\t"
+                            "setp.lt.and.f32 pir, %10, 0f00000000, pin;\n\t"
+                            "setp.lt.and.f32 pcd, %11, 0f00000000, pc;\n\t"
+                            "setp.lt.and.f32 pcr, %10, 0f00000000, pc;\n\t"
+                            "@pin add.rn.f64 %0, %0, %17;\n\t"
+                            "@pid add.rn.f64 %1, %1, %17;\n\t"
+                            "@pir add.rn.f64 %2, %2, %17;\n\t"
+                            "@pc  add.rn.f64 %3, %3, %17;\n\t"
+                            "@pcd add.rn.f64 %4, %4, %17;\n\t"
+                            "@pcr add.rn.f64 %5, %5, %17;\n\t"
+                            "}"
+                            : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(a4), "+d"(a5), "+r"(uncbits)
+                            : "r"(mk_k[p >> 2]), "r"(1u << (8 * (p & 3))), "f"(d2), "f"(dxs), "f"(dys), "f"(rg2_lo), "f"(rg2_hi), "f"(rc2f),
+                              "f"(E2), "f"(E), "d"(io[p]), "r"(1u << p));
+                    }
+                }
+                if (__any_sync(0xffffffffu, uncbits != 0)) {
+                    // rare: points within the fp32 error bound of a decision boundary, classified like the reference
+                    while (uncbits) {
+                        const int p = __ffs(uncbits) - 1;
+                        uncbits &= uncbits - 1;
+                        const int idx = p * kSweepThreads + tid;
+                        const ExactClass e = classify_exact(src, idx, pc, ref_x, ref_y, rg2, rc2);
+                        if (e.in) {
+                            const double v = (double)__ldg(src + idx).z + kCntUnit;
+                            a0 += v;
+                            if (e.down) a1 += v;
+                            if (e.right) a2 += v;
+                            if (e.cost) {
+                                a3 += v;
+                                if (e.down) a4 += v;
+                                if (e.right) a5 += v;
+                            }
+                        }
+                    }
+                }
+                a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
+                if (lane == 0) {
+                    // a = n * 2^17 + S with 0 <= S < 2^17 (<= 512 points, I < 256), everything exact
+                    const double inv = 1.0 / kCntUnit;
+                    const double n0 = (double)(long long)(a0 * inv), n1 = (double)(long long)(a1 * inv), n2 = (double)(long long)(a2 * inv);
+                    const double n3 = (double)(long long)(a3 * inv), n4 = (double)(long long)(a4 * inv), n5 = (double)(long long)(a5 * inv);
+                    store_totals(s_part[warp][k], a0 - n0 * kCntUnit, a1 - n1 * kCntUnit, a2 - n2 * kCntUnit, a3 - n3 * kCntUnit,
+                                 a4 - n4 * kCntUnit, a5 - n5 * kCntUnit, n0, n1, n2, n3, n4, n5);
+                }
+            }
+        } else {
+            // all-fp64 body: every predicate exactly as the reference, all candidates of the cell
+            for (int a = 0; a < nact; ++a) {
+                const int k = s_act[a];
+                const double ref_x = s_rx[k], ref_y = s_ry[k];
+                double tI = 0, dI = 0, rI = 0, cI = 0, cdI = 0, crI = 0;
+                int tN = 0, dN = 0, rN = 0, cN = 0, cdN = 0, crN = 0;
+                for (int idx = tid; idx < count; idx += kSweepThreads) {
+                    const float4 q = __ldg(src + idx);
+                    if (!((__float_as_uint(q.w) >> k) & 1u)) continue;
+                    const ExactClass e = classify_exact(src, idx, pc, ref_x, ref_y, rg2, rc2);
+                    if (!e.in) continue;
+                    const double I = (double)q.z;
+                    tI += I; tN++;
+                    if (e.down) { dI += I; dN++; }
+                    if (e.right) { rI += I; rN++; }
+                    if (e.cost) {
+                        cI += I; cN++;
+                        if (e.down) { cdI += I; cdN++; }
+                        if (e.right) { crI += I; crN++; }
+                    }
+                }
+                tI = warp_sum(tI); dI = warp_sum(dI); rI = warp_sum(rI); cI = warp_sum(cI); cdI = warp_sum(cdI); crI = warp_sum(crI);
+                tN = warp_sum(tN); dN = warp_sum(dN); rN = warp_sum(rN); cN = warp_sum(cN); cdN = warp_sum(cdN); crN = warp_sum(crN);
+                if (lane == 0) store_totals(s_part[warp][k], tI, dI, rI, cI, cdI, crI, tN, dN, rN, cN, cdN, crN);
+            }
+        }
+        __syncthreads();
+        {
+            const int k = tid >> 4, j = tid & 15;                       // 128 threads == 8 candidates x 16 accumulators
+            const int t = s_tid[k];
+            if (t >= 0) {
+                double v = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) v += s_part[w][k][j];
+                if (v != 0.0) atomicAdd(&bv.acc[((size_t)f * bv.geom.nt + t) * 16 + j], v);
+            }
+        }
+    }
+    if (!bv.fuse_lm) return;
+    // ---- fused LM step: the last CTA of this frame's sweep owns the complete accumulator table ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&bv.sweep_done[f], 1) == max(n_items, 1) - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) bv.sweep_done[f] = 0;
+    lm_frame_step(bv, f);
+}
+static_assert(kSweepThreads == kCand * 16, "final reduction maps one thread to one (candidate, accumulator)");
+static_assert(kSweepP % 4 == 0 && kSweepP * 32 * 256.0 <= kCntUnit, "count unit must exceed the largest per-warp intensity sum");
 
 __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
 {
@@ -871,6 +1082,8 @@ __global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, const PoseCoef* __res
     c.rebin = 0;
     c.n_items = bv.ctl[frame].n_items;
     c.n_binned = bv.ctl[frame].n_binned;
+    c.use_exact = bv.ctl[frame].use_exact;
+    c.pad_ = 0;
     for (int k = 0; k < 8; ++k) c.move[k] = 0.f;
     c.pose = poses[p];
     ctl_ms[p] = c;
@@ -909,7 +1122,11 @@ __global__ void __launch_bounds__(kLmThreads) k_ms_cost(BatchView bv, double* __
 // ------------------------------------------------------------------------------------------------
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static dim3 bin_grid(const rclc_batch* b) { return dim3((unsigned)((b->max_pts + kBinChunk - 1) / kBinChunk), (unsigned)b->n_frames); }
+static dim3 bin_grid(const rclc_batch* b)
+{
+    const int64_t chunks = (b->max_pts + kBinChunk - 1) / kBinChunk;
+    return dim3((unsigned)std::min<int64_t>(chunks, kBinGridX), (unsigned)b->n_frames);
+}
 
 static int launch_rebin(rclc_batch* b)
 {
@@ -921,9 +1138,11 @@ static int launch_rebin(rclc_batch* b)
     return RCLC_OK;
 }
 
-static int launch_sweep(rclc_batch* b)
+static int launch_sweep(rclc_batch* b, bool fuse_lm)
 {
-    k_sweep<<<dim3((unsigned)b->v.max_items, (unsigned)b->n_frames), kSweepThreads, 0, b->ctx->stream>>>(b->v);
+    BatchView v = b->v;
+    v.fuse_lm = fuse_lm ? 1 : 0;
+    k_sweep<<<dim3((unsigned)b->v.max_items, (unsigned)b->n_frames), kSweepThreads, 0, b->ctx->stream>>>(v);
     b->ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
@@ -970,10 +1189,13 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     b->n_frames = n_frames;
     b->max_pts = max_pts;
     b->h_npts.assign(n_frames, 0);
+    { const char* e = std::getenv("RCLC_SWEEP_EXACT"); b->sweep_exact = e && e[0] == '1'; }
     BatchView& v = b->v;
     v.geom = hg.g;
     v.n_frames = n_frames;
     v.fixed_frame = -1;
+    v.fuse_lm = 0;
+    v.force_exact = b->sweep_exact ? 1 : 0;
     v.frame_stride = (int64_t)align256((size_t)max_pts * 16) / 16;
     v.max_items = hg.g.ncells + (int)((max_pts + kChunk - 1) / kChunk);
     const size_t F = n_frames, nt = hg.g.nt, ncell = hg.g.ncells;
@@ -987,7 +1209,7 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
     const size_t o_npts = take(F * 8), o_hist = take(F * ncell * 4), o_cur = take(F * ncell * 4);
     const size_t o_items = take(F * (size_t)v.max_items * 16), o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
-    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_txy = take(nt * 16), o_txyf = take(nt * 8);
+    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_txy = take(nt * 16), o_txyf = take(nt * 8);
     const size_t o_row = take(nt), o_cand = take(ncell * kCand * 2), o_eval = take(F * nt * 4 * 8);
     const size_t o_corn = take(F * (size_t)hg.g.nc * 3 * 8), o_gmm = take(F * 64 * 8 + 4096 * 8 * 8);
     if (cudaMalloc(&b->d_block, off) != cudaSuccess) return fail("cudaMalloc block");
@@ -1002,6 +1224,7 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.ctl = reinterpret_cast<FrameCtl*>(base + o_ctl);
     v.lm = reinterpret_cast<LmState*>(base + o_lm);
     v.n_done = reinterpret_cast<int*>(base + o_done);
+    v.sweep_done = reinterpret_cast<int*>(base + o_sdone);
     v.tgt_xy = reinterpret_cast<double2*>(base + o_txy);
     v.tgt_xyf = reinterpret_cast<float2*>(base + o_txyf);
     v.tgt_is_row = reinterpret_cast<uint8_t*>(base + o_row);
@@ -1086,7 +1309,7 @@ int rclc_batch_sweep(rclc_batch* b, const double* poses)
     RCLC_CUDA(cudaMemcpyAsync(ctx->d_tmp2.p, hp, sizeof(PoseCoef) * b->n_frames, cudaMemcpyHostToDevice, ctx->stream));
     k_set_pose<<<b->n_frames, 256, 0, ctx->stream>>>(b->v, ctx->d_tmp2.as<PoseCoef>());
     ctx->launches += 1;
-    return launch_sweep(b);
+    return launch_sweep(b, false);
 }
 
 int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* acc)
@@ -1135,9 +1358,7 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     for (;;) {
         for (int r = 0; r < rounds_per_check; ++r) {
             RCLC_TRY(launch_rebin(b));
-            RCLC_TRY(launch_sweep(b));
-            k_lm<<<F, kLmThreads, 0, ctx->stream>>>(b->v);
-            ctx->launches += 1;
+            RCLC_TRY(launch_sweep(b, true));      // sweep + fused LM step (last CTA per frame)
         }
         rounds += rounds_per_check;
         RCLC_CUDA(cudaGetLastError());
@@ -1227,6 +1448,7 @@ int rclc_batch_multistart(rclc_batch* b, int32_t frame, const double* poses, int
     v.ctl = d_ctl;
     v.acc = d_acc;
     v.fixed_frame = frame;
+    v.fuse_lm = 0;
     v.n_frames = P;
     // blockIdx.y is limited to 65535: sweep poses in slabs
     for (int p0 = 0; p0 < P; p0 += 32768) {

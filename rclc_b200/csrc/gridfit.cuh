@@ -15,7 +15,7 @@ constexpr int kMaxTargets = 1024;
 constexpr int kMaxCells = 4096;
 constexpr int kCand = 8;                 // candidate targets per cell
 constexpr int kSweepThreads = 128;
-constexpr int kSweepP = 8;               // points per thread
+constexpr int kSweepP = 16;              // points per thread (registers: fp32 x', y' + fp64 intensity)
 constexpr int kChunk = kSweepThreads * kSweepP;
 constexpr int kBinThreads = 256;
 constexpr int kBinP = 8;
@@ -51,6 +51,8 @@ struct FrameCtl {
     int rebin;                 // count/scatter kernels process this frame (move + re-bin)
     int n_items;               // work items (cell chunks) of the current binning
     int n_binned;              // points that landed in a lattice cell
+    int use_exact;             // some intensity is outside {0} U [2^-3, 256): counts cannot ride in the fp64 sums -> all-fp64 body
+    int pad_;
     float move[8];             // T_w1_w0 rows 0,1: m00 m01 m02 m03 / m10 m11 m12 m13
     PoseCoef pose;             // pose the next sweep evaluates
 };
@@ -93,6 +95,9 @@ struct BatchView {
     FrameCtl* ctl;                 // [F]
     LmState* lm;                   // [F]
     int* n_done;                   // [1]
+    int* sweep_done;               // [F] CTAs of the current sweep that have finished (last one runs the LM step)
+    int fuse_lm;                   // 1: k_sweep's last CTA per frame advances the Ceres state machine
+    int force_exact;               // RCLC_SWEEP_EXACT=1
     // geometry tables
     const double2* tgt_xy;         // [nt]
     const float2* tgt_xyf;         // [nt] (float)target  (FLANN query point)
@@ -115,6 +120,7 @@ struct rclc_batch {
     void* d_block = nullptr;          // one allocation for the small arrays
     int64_t* d_npts = nullptr;
     bool binned_valid = false;
+    bool sweep_exact = false;         // RCLC_SWEEP_EXACT=1: run the all-fp64 v1 sweep (debug / A-B reference)
     // GMM scratch
     double* d_gmm = nullptr;
 };

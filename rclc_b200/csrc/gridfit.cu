@@ -245,7 +245,9 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
     const int f = blockIdx.x;
     const int tid = threadIdx.x;
     const int nc = bv.geom.ncells;
-    for (int c = tid; c < nc; c += blockDim.x) { bv.hist[(size_t)f * nc + c] = 0; bv.cursor[(size_t)f * nc + c] = 0; }
+    for (int c = tid; c < nc; c += blockDim.x) {
+        bv.hist[(size_t)f * nc + c] = 0; bv.cursor[(size_t)f * nc + c] = 0; bv.cellz2[(size_t)f * nc + c] = 0u;
+    }
     for (int k = tid; k < bv.geom.nt * 16; k += blockDim.x) bv.acc[(size_t)f * bv.geom.nt * 16 + k] = 0.0;
     if (tid == 0) {
         FrameCtl& c = bv.ctl[f];
@@ -312,11 +314,32 @@ __global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
         if (s_hist[k]) atomicAdd(&bv.hist[(size_t)f * nc + k], s_hist[k]);
 }
 
+// The sweep's read-only view of a frame (see SweepSnap).
+__device__ __forceinline__ void snapshot_frame(const BatchView& bv, int f)
+{
+    const FrameCtl& c = bv.ctl[f];
+    SweepSnap sn;
+    sn.sweep_active = c.sweep_active;
+    sn.n_items = c.n_items;
+    sn.use_exact = 0;
+    sn.pad_ = 0;
+    sn.pose = c.pose;
+    bv.snap[f] = sn;
+}
+
+// A cell's segment of `binned` is padded to a multiple of 32 points with sentinels that are far outside every
+// disc for every pose, so the sweep needs no tail predicate and a warp row never mixes two cells.
+__device__ __forceinline__ int pad32(int v) { return (v + 31) & ~31; }
+constexpr float kSentinelXY = 3.0e18f;      // (3e18)^2 * 2 is finite in fp32
+
 __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
 {
     const int f = blockIdx.y;
     FrameCtl& c = bv.ctl[f];
-    if (!c.rebin) return;
+    if (!c.rebin) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) snapshot_frame(bv, f);
+        return;
+    }
     const int64_t n = bv.n_pts[f];
     if ((int64_t)blockIdx.x * kBinChunk >= n && blockIdx.x != 0) return;
     __shared__ int s_off[kMaxCells];
@@ -325,15 +348,16 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
     __shared__ int s_bad;
     const int nc = bv.geom.ncells;
     const int tid = threadIdx.x;
-    for (int k = tid; k < nc; k += kBinThreads) s_off[k] = bv.hist[(size_t)f * nc + k];
+    for (int k = tid; k < nc; k += kBinThreads) s_off[k] = pad32(bv.hist[(size_t)f * nc + k]);
     if (tid == 0) s_bad = 0;
     __syncthreads();
-    const int total = block_exclusive_scan<kBinThreads>(s_off, nc, s_part);
+    block_exclusive_scan<kBinThreads>(s_off, nc, s_part);
 
     const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
     const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
     float4* raw = bv.raw + (size_t)f * bv.frame_stride;
     float4* dstb = bv.binned + (size_t)f * bv.frame_stride;
+    unsigned* cellz2 = bv.cellz2 + (size_t)f * nc;
     for (int64_t base = (int64_t)blockIdx.x * kBinChunk; base < n; base += (int64_t)gridDim.x * kBinChunk) {
         for (int k = tid; k < nc; k += kBinThreads) s_loc[k] = 0;
         __syncthreads();
@@ -372,26 +396,32 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
                 const int dst = s_off[pcell[p]] + s_loc[pcell[p]] + prank[p];
                 const uint32_t mask = neighbour_mask(bv, pcell[p], px[p], py[p], pz[p]);
                 dstb[dst] = make_float4(px[p], py[p], pi[p], __uint_as_float(mask));
+                const unsigned z2 = __float_as_uint(__fmul_rn(pz[p], pz[p]));          // >= 0: float order == uint order
+                if (z2 > cellz2[pcell[p]]) atomicMax(&cellz2[pcell[p]], z2);
             }
         }
         __syncthreads();
     }
     if (tid == 0 && s_bad) atomicOr(&c.use_exact, 1);
     if (blockIdx.x == 0) {
-        // work items: a cell with cnt points becomes ceil(cnt / kChunk) balanced chunks
+        // sentinels behind every cell's last point, then the work items: a cell with cnt (padded) points becomes
+        // ceil(cnt / kItemMax) balanced warp items, each a multiple of 32 points
         __syncthreads();
+        int total = 0;
         for (int k = tid; k < nc; k += kBinThreads) {
             const int cnt = bv.hist[(size_t)f * nc + k];
-            s_loc[k] = (cnt + kChunk - 1) / kChunk;
+            for (int j = cnt; j < pad32(cnt); ++j) dstb[s_off[k] + j] = make_float4(kSentinelXY, kSentinelXY, 0.f, __uint_as_float(0xffu));
+            s_loc[k] = (pad32(cnt) + kItemMax - 1) / kItemMax;
+            total += cnt;
         }
         __syncthreads();
         const int n_items = block_exclusive_scan<kBinThreads>(s_loc, nc, s_part);     // s_off survives
         int4* items = bv.items + (size_t)f * bv.max_items;
         for (int k = tid; k < nc; k += kBinThreads) {
-            const int cnt = bv.hist[(size_t)f * nc + k];
+            const int cnt = pad32(bv.hist[(size_t)f * nc + k]);
             if (cnt == 0) continue;
-            const int nch = (cnt + kChunk - 1) / kChunk;
-            const int per = ((cnt + nch - 1) / nch + 31) & ~31;
+            const int nch = (cnt + kItemMax - 1) / kItemMax;
+            const int per = pad32((cnt + nch - 1) / nch);
             int pos = s_loc[k];
             for (int j = 0; j < nch; ++j) {
                 const int st = j * per;
@@ -399,7 +429,19 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
                 items[pos++] = make_int4(k, s_off[k] + st, min(per, cnt - st), 0);
             }
         }
-        if (tid == 0) { c.n_items = n_items; c.n_binned = total; }
+        // n_binned: block reduction of the per-thread totals
+        __syncthreads();
+        s_part[tid] = total;
+        __syncthreads();
+        for (int off = kBinThreads / 2; off > 0; off >>= 1) {
+            if (tid < off) s_part[tid] += s_part[tid + off];
+            __syncthreads();
+        }
+        if (tid == 0) {
+            c.n_items = n_items; c.n_binned = s_part[0];
+            // c.use_exact is still being OR-ed by the other CTAs of this frame: the sweep reads it from ctl
+            snapshot_frame(bv, f);
+        }
     }
 }
 
@@ -705,34 +747,35 @@ __device__ void lm_advance(const GridGeom& g, LmState& s, FrameCtl& c, const Eva
     }
 }
 
-constexpr int kLmThreads = kSweepThreads;
+constexpr int kLmThreads = 128;         // k_ms_cost block size
 
-// One CTA: residuals + heuristic Jacobian + Huber corrector for every target from the accumulator table,
-// 3x3 normal equations reduced in shared memory, then the Ceres step / accept-reject / radius logic and the
-// opt_grid_fitting outer-loop bookkeeping on one thread. The frame's state is staged through shared memory.
-__device__ void lm_frame_step(const BatchView& bv, int f)
+struct LmStage { LmState lm; FrameCtl ctl; };
+
+// One WARP: residuals + heuristic Jacobian + Huber corrector for every target from the accumulator table, 3x3 normal
+// equations reduced with shuffles, then the Ceres step / accept-reject / radius logic and the opt_grid_fitting
+// outer-loop bookkeeping on lane 0. The frame's state is staged through the warp's slice of shared memory.
+__device__ __noinline__ void lm_frame_step(const BatchView& bv, int f, LmStage* stage)
 {
-    __shared__ LmState s_lm;
-    __shared__ FrameCtl s_ctl;
-    __shared__ double s_red[kLmThreads / 32][12];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31;
     const GridGeom& g = bv.geom;
+    LmState& s_lm = stage->lm;
+    FrameCtl& s_ctl = stage->ctl;
     {
         const int* gl = reinterpret_cast<const int*>(&bv.lm[f]);
         int* sl = reinterpret_cast<int*>(&s_lm);
-        for (int k = tid; k < (int)(sizeof(LmState) / 4); k += kLmThreads) sl[k] = __ldcg(gl + k);
+        for (int k = lane; k < (int)(sizeof(LmState) / 4); k += 32) sl[k] = __ldcg(gl + k);
         const int* gc = reinterpret_cast<const int*>(&bv.ctl[f]);
         int* sc = reinterpret_cast<int*>(&s_ctl);
-        for (int k = tid; k < (int)(sizeof(FrameCtl) / 4); k += kLmThreads) sc[k] = __ldcg(gc + k);
+        for (int k = lane; k < (int)(sizeof(FrameCtl) / 4); k += 32) sc[k] = __ldcg(gc + k);
     }
-    __syncthreads();
+    __syncwarp();
     const PoseCoef pc = s_ctl.pose;
     const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
     const double cth = cos(theta), sth = sin(theta);
     double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cost, A00,A01,A02,A11,A12,A22, b0,b1,b2
     int bad_r = 0, bad_j = 0;
     double* acc = bv.acc + (size_t)f * g.nt * 16;
-    for (int t = tid; t < g.nt; t += kLmThreads) {
+    for (int t = lane; t < g.nt; t += 32) {
         double a16[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) a16[k] = __ldcg(acc + (size_t)t * 16 + k);
@@ -752,67 +795,68 @@ __device__ void lm_frame_step(const BatchView& bv, int f)
         sums[4] += j1 * j1; sums[5] += j1 * j2; sums[6] += j2 * j2;
         sums[7] += j0 * r;  sums[8] += j1 * r;  sums[9] += j2 * r;
     }
-    __syncthreads();
-    for (int k = tid; k < g.nt * 16; k += kLmThreads) acc[k] = 0.0;      // consumed: clear for the next sweep
+    __syncwarp();
+    for (int k = lane; k < g.nt * 16; k += 32) acc[k] = 0.0;      // consumed: clear for the next sweep
 #pragma unroll
     for (int k = 0; k < 10; ++k) sums[k] = warp_sum(sums[k]);
     bad_r = __any_sync(0xffffffffu, bad_r);
     bad_j = __any_sync(0xffffffffu, bad_j);
     if (lane == 0) {
-        for (int k = 0; k < 10; ++k) s_red[warp][k] = sums[k];
-        s_red[warp][10] = bad_r;
-        s_red[warp][11] = bad_j;
-    }
-    __syncthreads();
-    if (tid == 0) {
         EvalSums e;
-        double tot[12];
-        for (int k = 0; k < 12; ++k) { tot[k] = 0; for (int w = 0; w < kLmThreads / 32; ++w) tot[k] += s_red[w][k]; }
-        e.cost = tot[0];
-        for (int k = 0; k < 6; ++k) e.A[k] = tot[1 + k];
-        for (int k = 0; k < 3; ++k) e.b[k] = tot[7 + k];
-        e.res_valid = tot[10] == 0.0;
-        e.jac_valid = e.res_valid && tot[11] == 0.0;
+        e.cost = sums[0];
+        for (int k = 0; k < 6; ++k) e.A[k] = sums[1 + k];
+        for (int k = 0; k < 3; ++k) e.b[k] = sums[7 + k];
+        e.res_valid = !bad_r;
+        e.jac_valid = e.res_valid && !bad_j;
         lm_advance(g, s_lm, s_ctl, e, bv.corners + (size_t)f * g.nc * 3, bv.n_done);
     }
-    __syncthreads();
+    __syncwarp();
     {
         int* gl = reinterpret_cast<int*>(&bv.lm[f]);
         const int* sl = reinterpret_cast<const int*>(&s_lm);
-        for (int k = tid; k < (int)(sizeof(LmState) / 4); k += kLmThreads) gl[k] = sl[k];
+        for (int k = lane; k < (int)(sizeof(LmState) / 4); k += 32) gl[k] = sl[k];
         int* gc = reinterpret_cast<int*>(&bv.ctl[f]);
         const int* sc = reinterpret_cast<const int*>(&s_ctl);
-        for (int k = tid; k < (int)(sizeof(FrameCtl) / 4); k += kLmThreads) gc[k] = sc[k];
+        for (int k = lane; k < (int)(sizeof(FrameCtl) / 4); k += 32) gc[k] = sc[k];
     }
     if (s_ctl.rebin) {
         const int nc = g.ncells;
-        for (int k = tid; k < nc; k += kLmThreads) { bv.hist[(size_t)f * nc + k] = 0; bv.cursor[(size_t)f * nc + k] = 0; }
+        for (int k = lane; k < nc; k += 32) {
+            bv.hist[(size_t)f * nc + k] = 0; bv.cursor[(size_t)f * nc + k] = 0; bv.cellz2[(size_t)f * nc + k] = 0u;
+        }
     }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_sweep: the hot loop. One CTA = one chunk (<= kChunk points) of one lattice cell; blockIdx.y = frame.
+// k_sweep: the hot loop. One WARP = one item (<= kItemMax points of one lattice cell, a multiple of 32);
+// blockIdx.y = frame, 4 independent warps per CTA.
 //
-//  * pose-aware culling: a candidate target is visited only if its gradient disc, pulled back through
-//    the trial pose, can touch the cell rectangle (typically 2-3 of the 8 candidates);
-//  * predicates in fp32 with a rigorous rounding-error bound E on the transformed coordinates and E2
-//    on the squared distance; a point whose fp32 value lies within the bound of ANY decision boundary
-//    (gradient circle, cost circle, the two half-plane lines) is re-evaluated exactly like the
-//    reference (double maths, no FMA contraction) — so the class of every point equals the oracle's;
-//  * 6 nested totals per candidate (in-disc, &down, &right, cost, cost&down, cost&right) accumulated in
-//    double; each addend is I + 2^17, so the COUNT rides in the high bits of the same exact sum (valid for
-//    I in {0} U [2^-3, 256) — k_scatter checks; other frames take the all-fp64 body);
+//  * staging: lane 0 pulls the item through a private ring of kStages x 4 KB shared-memory tiles with
+//    cp.async.bulk (TMA bulk copy) completing on an mbarrier; the other lanes only wait on the barrier phase;
+//  * pose-aware culling: a candidate target is live only if its gradient disc, pulled back through the trial
+//    pose, can touch the cell rectangle (2 of the 8 candidates for small poses, up to 4 for cm-sized ones);
+//  * the live candidates (<= 4 per pass) sit in the INNER loop with their six nested totals (in-disc, &down,
+//    &right, cost, cost&down, cost&right) in registers for the whole item: per point and candidate 2 compares +
+//    4 compare-and-ands + 6 predicated fp64 adds. Each addend is I + 2^17, so the COUNT rides in the high bits
+//    of the same exact sum (valid for I in {0} U [2^-3, 256) — k_scatter checks; other frames take the
+//    all-fp64 body);
+//  * exactness: predicates are evaluated in fp32; every lane tracks, per candidate, the minimum distance of its
+//    points to any decision boundary (two circles in d^2, two lines in dx, dy). Only if that minimum is inside
+//    the rigorous fp32 error bound (about 1e-7 m; a handful of lanes per sweep) the lane re-reads its points
+//    and corrects the sums of the points whose exact (reference, fp64, no FMA) class differs — so the
+//    accumulator tables equal the oracle's bit for bit;
 //  * the last CTA of a frame to finish runs the LM step (lm_frame_step) — no separate launch.
 // ------------------------------------------------------------------------------------------------
-constexpr double kCntUnit = 131072.0;           // 2^17 > 512 points x 256
+constexpr double kCntUnit = 131072.0;           // 2^17 > 512 points per lane x 256
+static_assert(kItemMax / 32 <= 512 && kItemMax % kTile == 0 && kTile % 32 == 0, "count unit / tiling");
 
 struct ExactClass { bool in, cost, down, right; };
 
-__device__ __noinline__ ExactClass classify_exact(const float4* __restrict__ src, int idx, const PoseCoef& pc, double ref_x, double ref_y,
-                                                  double rg2, double rc2)
+__device__ __forceinline__ ExactClass classify_exact(float qx, float qy, const PoseCoef& pc, double ref_x, double ref_y,
+                                                     double rg2, double rc2)
 {
-    const float4 q = __ldg(src + idx);
-    const double vx = __dadd_rn((double)q.x, pc.tx), vy = __dadd_rn((double)q.y, pc.ty);      // board_fitting_cost.h:132-133
+    const double vx = __dadd_rn((double)qx, pc.tx), vy = __dadd_rn((double)qy, pc.ty);      // board_fitting_cost.h:132-133
     const double xt = __dadd_rn(__dmul_rn(pc.r00, vx), __dmul_rn(pc.r01, vy));
     const double yt = __dadd_rn(__dmul_rn(pc.r10, vx), __dmul_rn(pc.r11, vy));
     const double dx = fmax(1e-14, fabs(__dsub_rn(ref_x, xt)));                                // :138-139
@@ -826,7 +870,7 @@ __device__ __noinline__ ExactClass classify_exact(const float4* __restrict__ src
     return e;
 }
 
-// expands the 6 nested totals of one warp into the reference's 16 accumulators
+// expands six nested totals into the reference's 16 accumulators
 __device__ __forceinline__ void store_totals(double* o, double tI, double dI, double rI, double cI, double cdI, double crI,
                                              double tN, double dN, double rN, double cN, double cdN, double crN)
 {
@@ -836,225 +880,597 @@ __device__ __forceinline__ void store_totals(double* o, double tI, double dI, do
     o[12] = dN - cdN; o[13] = (tN - dN) - (cN - cdN); o[14] = (tN - rN) - (cN - crN); o[15] = rN - crN;
 }
 
-__global__ void __launch_bounds__(kSweepThreads) k_sweep(BatchView bv)
+// ---- mbarrier / TMA bulk copy (PTX) ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    const int f = blockIdx.y;
-    const FrameCtl& c = bv.ctl[f];
-    if (!c.sweep_active) return;
-    const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;      // frame whose points are read
-    const int item = blockIdx.x;
-    const int n_items = c.n_items;
-    if (item >= max(n_items, 1)) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kSweepThreads / 32;
-    constexpr int P = kSweepP;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n\t"
+                 "DONE_%=:\n\t"
+                 "}" ::"r"(bar), "r"(parity) : "memory");
+}
 
-    __shared__ double s_part[NW][kCand][16];
-    __shared__ int s_tid[kCand];
-    __shared__ double s_rx[kCand], s_ry[kCand];
-    __shared__ int s_act[kCand];
-    __shared__ int s_nact;
-    __shared__ float s_E;
-    __shared__ int s_last;
+struct SweepConst {            // per-warp constants of one item
+    float r00, r01, r10, r11, tx, ty;     // fp32 pose
+    float rg2, rc2;                       // fp32 radii^2
+    float E, E2;                          // fp32 error bounds: coordinates, squared distance
+};
 
-    const PoseCoef pc = c.pose;
-    const double rg2 = bv.geom.rg2, rc2 = bv.geom.rc2;
-    if (n_items > 0) {
-        const int4 it = bv.items[(size_t)fd * bv.max_items + item];
-        const bool exact_body = bv.force_exact || c.use_exact;
-        if (tid < kCand) {
-            const int t = bv.cell_cand[(size_t)it.x * kCand + tid];
-            s_tid[tid] = t;
-            // cell rectangle in the (un-posed) frame the points are stored in, with a safety margin
-            const int ca = it.x % bv.geom.ncx, cb = it.x / bv.geom.ncx;
-            const double x0 = (bv.geom.i0 + ca) * bv.geom.g - 1e-6, x1 = (bv.geom.i0 + ca + 1) * bv.geom.g + 1e-6;
-            const double y0 = (bv.geom.j0 + cb) * bv.geom.g - 1e-6, y1 = (bv.geom.j0 + cb + 1) * bv.geom.g + 1e-6;
-            bool active = false;
-            if (t >= 0) {
-                const double2 r = bv.tgt_xy[t];
-                s_rx[tid] = r.x; s_ry[tid] = r.y;
-                // p' = R (p + t)  =>  |p' - ref| = |p - (R^T ref - t)|
-                const double cx = pc.r00 * r.x + pc.r10 * r.y - pc.tx, cy = pc.r01 * r.x + pc.r11 * r.y - pc.ty;
-                const double ex = fmax(fmax(x0 - cx, cx - x1), 0.0), ey = fmax(fmax(y0 - cy, cy - y1), 0.0);
-                const double reach = sqrt(rg2) + 1e-5;
-                active = exact_body || (ex * ex + ey * ey) <= reach * reach;
+// One (point, candidate) update. ptxas turns predicated fp64 adds into add + two selects (12 ALU-pipe selects per
+// pair), so the class is applied as a MULTIPLIER instead: m = +-1.0 / +-0.0 built from two compares, two selects
+// and four sign-xors on the high word (the low word is a constant zero), then six DFMAs:
+//   a[0] += [in] v          a[1] += [in] s_y v          a[2] += [in] s_x v        (s = -1 when down / right)
+//   a[3] += [cost] v        a[4] += [cost] s_y v        a[5] += [cost] s_x v
+// All products and sums are exact, so down = (a0 - a1) / 2 etc. are exact too (to_nested_totals).
+template <bool MASKED>
+__device__ __forceinline__ void accumulate6(double (&a)[6], float d2, float dxs, float dys, float rg2, float rc2, double v,
+                                            uint32_t maskbits, uint32_t bit)
+{
+    const uint32_t one = 0x3ff00000u;
+    const bool member = !MASKED || (maskbits & bit) != 0u;
+    const uint32_t hin = (member && d2 <= rg2) ? one : 0u;
+    const uint32_t hc = (member && d2 < rc2) ? one : 0u;
+    const uint32_t sy = __float_as_uint(dys) & 0x80000000u, sx = __float_as_uint(dxs) & 0x80000000u;
+    a[0] = fma(__hiloint2double((int)hin, 0), v, a[0]);
+    a[1] = fma(__hiloint2double((int)(hin ^ sy), 0), v, a[1]);
+    a[2] = fma(__hiloint2double((int)(hin ^ sx), 0), v, a[2]);
+    a[3] = fma(__hiloint2double((int)hc, 0), v, a[3]);
+    a[4] = fma(__hiloint2double((int)(hc ^ sy), 0), v, a[4]);
+    a[5] = fma(__hiloint2double((int)(hc ^ sx), 0), v, a[5]);
+}
+
+// signed sums -> the six nested totals (in, in&down, in&right, cost, cost&down, cost&right); exact
+__device__ __forceinline__ void to_nested_totals(double (&a)[6])
+{
+    a[1] = 0.5 * (a[0] - a[1]);
+    a[2] = 0.5 * (a[0] - a[2]);
+    a[4] = 0.5 * (a[3] - a[4]);
+    a[5] = 0.5 * (a[3] - a[5]);
+}
+
+// fp32 geometry of one (point, candidate) pair — the SAME intrinsics in the hot loop and in the fix-up, so both see
+// identical values (no contraction or re-association by the compiler).
+__device__ __forceinline__ void pose_point(const SweepConst& k, float qx, float qy, float& xt, float& yt)
+{
+    const float vx = __fadd_rn(qx, k.tx), vy = __fadd_rn(qy, k.ty);
+    xt = __fmaf_rn(k.r00, vx, __fmul_rn(k.r01, vy));
+    yt = __fmaf_rn(k.r10, vx, __fmul_rn(k.r11, vy));
+}
+__device__ __forceinline__ void pair_geom(float rx, float ry, float xt, float yt, float& dxs, float& dys, float& d2)
+{
+    dxs = __fsub_rn(rx, xt);
+    dys = __fsub_rn(ry, yt);
+    d2 = __fmaf_rn(dxs, dxs, __fmul_rn(dys, dys));
+}
+
+// Rare (about 1e-4 of the (point, candidate) pairs): the point is within the fp32 error bound of a decision boundary
+// of the candidate. Its class is re-evaluated with the reference's own arithmetic (fp64, no FMA) and, if it differs
+// from the fp32 class the hot loop has just used, the signed sums are corrected — every term is exact, so the
+// corrected sums equal what an all-fp64 sweep accumulates.
+// warp reduction of one candidate's six per-lane totals and the atomics into the frame's accumulator table
+__device__ __forceinline__ void flush_candidate(const double (&a)[6], double* __restrict__ acc_t, double* scratch16, int lane)
+{
+    double S[6];
+    int n[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        // a = n * 2^17 + S, 0 <= S < 2^17, everything exact
+        n[j] = (int)(a[j] * (1.0 / kCntUnit));
+        S[j] = fma(-(double)n[j], kCntUnit, a[j]);
+        n[j] = __reduce_add_sync(0xffffffffu, n[j]);
+        S[j] = warp_sum(S[j]);
+    }
+    if (lane == 0)
+        store_totals(scratch16, S[0], S[1], S[2], S[3], S[4], S[5], (double)n[0], (double)n[1], (double)n[2], (double)n[3],
+                     (double)n[4], (double)n[5]);
+    __syncwarp();
+    if (lane < 16) {
+        const double v = scratch16[lane];
+        if (v != 0.0) atomicAdd(acc_t + lane, v);
+    }
+    __syncwarp();
+}
+
+// ---- per-warp stream of 4 KB tiles through shared memory ----
+// The tiles of the warp's items (and of the repeated passes of an item with more than 4 live candidates) form ONE
+// sequence; lane 0 keeps kStages bulk copies in flight and runs ahead into the next item while the warp still
+// computes on (or flushes) the current one.
+struct ItemMeta {
+    int f;            // frame (accumulator / pose index)
+    int cell;
+    int count;        // points, multiple of 32 (0: nothing to stream)
+    const float4* gsrc;
+};
+
+static_assert((kStages & (kStages - 1)) == 0, "stage index is a mask of the tile counter");
+__device__ __forceinline__ int item_tiles(int count) { return (count + kTile - 1) / kTile; }
+
+// Consumer / producer cursors of the warp's stream (identical in every lane).
+struct StreamState {
+    uint32_t issued;       // tiles handed to the copy engine so far
+    uint32_t consumed;     // tiles the warp has finished reading
+    // producer: (current item: pass, tile), then (next item: tiles of its first pass — its number of passes is not
+    // known before it is set up)
+    int pass_cur, tile_cur, tile_nxt;
+    int npass_cur, count_cur, nt_cur;
+    int count_nxt, nt_nxt;
+    const float4* g_cur;
+    const float4* g_nxt;
+};
+
+struct WarpRing {
+    uint32_t tiles;        // shared address of this warp's kStages tiles
+    uint32_t bars;         // shared address of this warp's kStages mbarriers
+    const float4* gen;     // generic pointer to the tiles
+};
+
+__device__ __forceinline__ void ring_issue(const WarpRing& ring, uint32_t issued, const float4* gsrc, int count, int tile)
+{
+    const uint32_t st = issued & (kStages - 1);
+    const uint32_t bytes = (uint32_t)min(kTile, count - tile * kTile) * 16u;
+    mbar_expect_tx(ring.bars + st * 8, bytes);
+    bulk_g2s(ring.tiles + st * (kTile * 16), gsrc + (size_t)tile * kTile, bytes, ring.bars + st * 8);
+}
+
+// Issue copies until kStages are in flight or there is nothing left that may be issued.
+__device__ __forceinline__ void ring_fill(const WarpRing& ring, StreamState& s, int lane)
+{
+    while (s.issued - s.consumed < (uint32_t)kStages) {
+        if (s.pass_cur < s.npass_cur && s.nt_cur > 0) {
+            if (lane == 0) ring_issue(ring, s.issued, s.g_cur, s.count_cur, s.tile_cur);
+            if (++s.tile_cur == s.nt_cur) { s.tile_cur = 0; ++s.pass_cur; }
+        } else if (s.tile_nxt < s.nt_nxt) {
+            if (lane == 0) ring_issue(ring, s.issued, s.g_nxt, s.count_nxt, s.tile_nxt);
+            ++s.tile_nxt;
+        } else break;
+        ++s.issued;
+    }
+}
+
+// wait for the next tile of the stream; returns its generic address
+__device__ __forceinline__ const float4* ring_acquire(const WarpRing& ring, const StreamState& s)
+{
+    const uint32_t st = s.consumed & (kStages - 1);
+    mbar_wait(ring.bars + st * 8, (s.consumed / kStages) & 1u);
+    return ring.gen + st * kTile;
+}
+__device__ __forceinline__ void ring_release(const WarpRing& ring, StreamState& s, int lane)
+{
+    __syncwarp();
+    ++s.consumed;
+    ring_fill(ring, s, lane);
+}
+
+// Everything about the current item that is warp-uniform lives in the warp's slice of shared memory: the hot loop
+// (sweep_pass, a separate function so that its register allocation is its own) picks up what it needs from here.
+struct WarpCtx {
+    SweepConst k;
+    PoseCoef pc;
+    float rx[kCand], ry[kCand];      // live candidates of the item, in pass order
+    uint32_t bit[kCand];
+    int tk[kCand];
+    StreamState st;
+};
+
+struct Corr6 { double d[6]; };
+
+// Rare (about 1e-4 of the (point, candidate) pairs): the point is within the fp32 error bound of a decision boundary
+// of the candidate. Its class is re-evaluated with the reference's own arithmetic (fp64, no FMA) and, if it differs
+// from the fp32 class the hot loop has just used, the signed sums are corrected — every term is exact, so the
+// corrected sums equal what an all-fp64 sweep accumulates.
+template <bool MASKED>
+__device__ __noinline__ Corr6 correct_point(float4 q, const WarpCtx* wc, int c, const double2* __restrict__ tgt_xy, double rg2, double rc2)
+{
+    Corr6 a;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a.d[j] = 0.0;
+    const SweepConst k = wc->k;
+    float xt, yt, dxs, dys, d2;
+    pose_point(k, q.x, q.y, xt, yt);
+    pair_geom(wc->rx[c], wc->ry[c], xt, yt, dxs, dys, d2);
+    const bool near = fabsf(__fsub_rn(d2, k.rg2)) <= k.E2 || fabsf(__fsub_rn(d2, k.rc2)) <= k.E2 || fabsf(dxs) <= k.E || fabsf(dys) <= k.E;
+    if (!near) return a;
+    const bool member = !MASKED || ((__float_as_uint(q.w) & wc->bit[c]) != 0u);
+    if (!member) return a;
+    // what accumulate6 added
+    const double f_in = d2 <= k.rg2 ? 1.0 : 0.0, f_c = d2 < k.rc2 ? 1.0 : 0.0;
+    const double f_sy = (__float_as_uint(dys) & 0x80000000u) ? -1.0 : 1.0, f_sx = (__float_as_uint(dxs) & 0x80000000u) ? -1.0 : 1.0;
+    // what the reference adds
+    const double2 ref = tgt_xy[wc->tk[c]];
+    const PoseCoef pc = wc->pc;
+    const ExactClass e = classify_exact(q.x, q.y, pc, ref.x, ref.y, rg2, rc2);
+    const double e_in = e.in ? 1.0 : 0.0, e_c = (e.in && e.cost) ? 1.0 : 0.0;
+    const double e_sy = e.down ? -1.0 : 1.0, e_sx = e.right ? -1.0 : 1.0;
+    const double v = (double)q.z + kCntUnit;
+    a.d[0] = (e_in - f_in) * v;
+    a.d[1] = (e_in * e_sy - f_in * f_sy) * v;
+    a.d[2] = (e_in * e_sx - f_in * f_sx) * v;
+    a.d[3] = (e_c - f_c) * v;
+    a.d[4] = (e_c * e_sy - f_c * f_sy) * v;
+    a.d[5] = (e_c * e_sx - f_c * f_sx) * v;
+    return a;
+}
+
+// One pass over the current item with N live candidates (wc->rx[c0 .. c0+N)). Signed sums (see accumulate6) go to
+// acc_out[N][6] in the caller's local memory; the stream cursors are read from and written back to wc->st.
+template <int N, bool MASKED>
+__device__ __noinline__ void sweep_pass(WarpCtx* wc, int c0, WarpRing ring, const double2* __restrict__ tgt_xy, double rg2d, double rc2d,
+                                        double* __restrict__ acc_out)
+{
+    const int lane = threadIdx.x & 31;
+    const SweepConst k = wc->k;
+    StreamState s = wc->st;
+    float rx[N], ry[N];
+    uint32_t bit[N];
+    double acc[N][6];
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        rx[c] = wc->rx[c0 + c]; ry[c] = wc->ry[c0 + c]; bit[c] = wc->bit[c0 + c];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[c][j] = 0.0;
+    }
+    // distance of this lane's points to the nearest decision boundary since the last flagged row: circles (in d^2), lines
+    float mA = 3.0e38f, mB = 3.0e38f;
+    const int ntiles = s.nt_cur, count = s.count_cur;
+    for (int t = 0; t < ntiles; ++t) {
+        const uint32_t stg = s.consumed & (kStages - 1);
+        mbar_wait(ring.bars + stg * 8, (s.consumed / kStages) & 1u);
+        const uint32_t tile = ring.tiles + stg * (kTile * 16) + lane * 16;
+        const int rows = min(kTile, count - t * kTile) >> 5;
+        uint32_t flagged = 0;            // rows of this tile in which some lane came within the error bound of a boundary
+#pragma unroll(N <= 2 ? 2 : 1)
+        for (int r = 0; r < rows; ++r) {
+            const float4 q = lds_f4(tile + r * 512);
+            float xt, yt;
+            pose_point(k, q.x, q.y, xt, yt);
+            const double v = (double)q.z + kCntUnit;
+            const uint32_t mb = MASKED ? __float_as_uint(q.w) : 0u;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                float dxs, dys, d2;
+                pair_geom(rx[c], ry[c], xt, yt, dxs, dys, d2);
+                mA = fminf(mA, fminf(fabsf(__fsub_rn(d2, k.rg2)), fabsf(__fsub_rn(d2, k.rc2))));
+                mB = fminf(mB, fminf(fabsf(dxs), fabsf(dys)));
+                accumulate6<MASKED>(acc[c], d2, dxs, dys, k.rg2, k.rc2, v, mb, bit[c]);
             }
-            const unsigned b = __ballot_sync(0xffu, active);
-            if (active) s_act[__popc(b & ((1u << tid) - 1u))] = tid;
-            if (tid == 0) {
-                s_nact = __popc(b);
-                const double Bc = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))) + fabs(pc.tx) + fabs(pc.ty) + 0.1;
-                s_E = (float)(12.0 * 5.9604644775390625e-8 * Bc + 1e-9);
+            const bool hit = __any_sync(0xffffffffu, mA <= k.E2 || mB <= k.E);      // warp-uniform, no branch in the loop
+            flagged |= hit ? (1u << r) : 0u;
+            mA = hit ? 3.0e38f : mA;
+            mB = hit ? 3.0e38f : mB;
+        }
+        while (flagged) {                // cold: about 1 % of the rows
+            const int r = __ffs(flagged) - 1;
+            flagged &= flagged - 1;
+            const float4 q = lds_f4(tile + r * 512);
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                const Corr6 d = correct_point<MASKED>(q, wc, c0 + c, tgt_xy, rg2d, rc2d);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc[c][j] += d.d[j];
             }
         }
-        for (int k = tid; k < NW * kCand * 16; k += kSweepThreads) (&s_part[0][0][0])[k] = 0.0;
-        const float4* src = bv.binned + (size_t)fd * bv.frame_stride + it.y;
-        const int count = it.z;
-        const int np = (count + kSweepThreads - 1) / kSweepThreads;            // uniform trip count (<= P)
-        __syncthreads();
-        const int nact = s_nact;
+        ring_release(ring, s, lane);
+    }
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc_out[c * 6 + j] = acc[c][j];
+    }
+    __syncwarp();
+    if (lane == 0) wc->st = s;
+    __syncwarp();
+}
 
-        if (!exact_body) {
-            const float r00f = (float)pc.r00, r01f = (float)pc.r01, r10f = (float)pc.r10, r11f = (float)pc.r11;
-            const float txf = (float)pc.tx, tyf = (float)pc.ty;
-            float xt[P], yt[P];
-            double io[P];
-            uint32_t mkw[P / 4];
-#pragma unroll
-            for (int w = 0; w < P / 4; ++w) mkw[w] = 0;
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                xt[p] = 0.f; yt[p] = 0.f; io[p] = 0.0;
-                if (p < np) {
-                    const int idx = p * kSweepThreads + tid;
-                    if (idx < count) {
-                        const float4 q = __ldg(src + idx);
-                        const float vx = q.x + txf, vy = q.y + tyf;
-                        xt[p] = fmaf(r00f, vx, r01f * vy);
-                        yt[p] = fmaf(r10f, vx, r11f * vy);
-                        io[p] = (double)q.z + kCntUnit;
-                        mkw[p >> 2] |= (__float_as_uint(q.w) & 0xffu) << (8 * (p & 3));
-                    }
-                }
-            }
-            const float E = s_E;
-            const float E2 = 2.9f * sqrtf((float)rg2) * E + 3e-7f * (float)rg2 + 2.f * E * E + 1e-9f;
-            const float rg2_hi = (float)rg2 + E2, rg2_lo = (float)rg2 - E2;   // [lo, hi]: uncertain band of the gradient circle
-            const float rc2f = (float)rc2;
-            for (int a = 0; a < nact; ++a) {
-                const int k = s_act[a];
-                const double ref_x = s_rx[k], ref_y = s_ry[k];
-                const float rxf = (float)ref_x, ryf = (float)ref_y;
-                double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;      // in, in&down, in&right, cost, cost&down, cost&right
-                uint32_t mk_k[P / 4];
-#pragma unroll
-                for (int w = 0; w < P / 4; ++w) mk_k[w] = mkw[w] >> k;      // bit 8*(p&3) of word p>>2 = membership of point p
-                uint32_t uncbits = 0;                                        // pairs that need the exact evaluation
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    if (p < np) {
-                        const float dxs = rxf - xt[p], dys = ryf - yt[p];
-                        const float d2 = fmaf(dxs, dxs, dys * dys);
-                        // pin  = member & certainly inside the gradient disc & farther than the error bound from the cost
-                        //        circle and from both half-plane lines  -> class decided in fp32
-                        // punc = member & possibly inside & not pin      -> exact re-evaluation after the loop
-                        asm("{\n\t"
-                            ".reg .pred pm, pin, pnin, pc, pid, pir, pcd, pcr, pu;\n\t"
-                            ".reg .f32 t, ax, ay;\n\t"
-                            ".reg .b32 mb;\n\t"
-                            "and.b32 mb, %7, %8;\n\t"
-                            "setp.ne.u32 pm, mb, 0;\n\t"
-                            "setp.lt.and.f32 pin, %9, %12, pm;\n\t"
-                            "sub.f32 t, %9, %14;\n\t"
-                            "abs.f32 t, t;\n\t"
-                            "setp.gt.and.f32 pin, t, %15, pin;\n\t"
-                            "abs.f32 ax, %10;\n\t"
-                            "abs.f32 ay, %11;\n\t"
-                            "setp.gt.and.f32 pin, ax, %16, pin;\n\t"
-                            "setp.gt.and.f32 pin, ay, %16, pin;\n\t"
-                            "not.pred pnin, pin;\n\t"
-                            "setp.le.and.f32 pu, %9, %13, pm;\n\t"
-                            "and.pred pu, pu, pnin;\n\t"
-                            "@pu or.b32 %6, %6, %18;\n\t"
-                            "setp.lt.and.f32 pc, %9, %14, pin;\n\t"
-                            "setp.lt.and.f32 pid, %11, 0f00000000, pin;\n\t"
-                            "setp.lt.and.f32 pir, %10, 0f00000000, pin;\n\t"
-                            "setp.lt.and.f32 pcd, %11, 0f00000000, pc;\n\t"
-                            "setp.lt.and.f32 pcr, %10, 0f00000000, pc;\n\t"
-                            "@pin add.rn.f64 %0, %0, %17;\n\t"
-                            "@pid add.rn.f64 %1, %1, %17;\n\t"
-                            "@pir add.rn.f64 %2, %2, %17;\n\t"
-                            "@pc  add.rn.f64 %3, %3, %17;\n\t"
-                            "@pcd add.rn.f64 %4, %4, %17;\n\t"
-                            "@pcr add.rn.f64 %5, %5, %17;\n\t"
-                            "}"
-                            : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(a4), "+d"(a5), "+r"(uncbits)
-                            : "r"(mk_k[p >> 2]), "r"(1u << (8 * (p & 3))), "f"(d2), "f"(dxs), "f"(dys), "f"(rg2_lo), "f"(rg2_hi), "f"(rc2f),
-                              "f"(E2), "f"(E), "d"(io[p]), "r"(1u << p));
-                    }
-                }
-                if (__any_sync(0xffffffffu, uncbits != 0)) {
-                    // rare: points within the fp32 error bound of a decision boundary, classified like the reference
-                    while (uncbits) {
-                        const int p = __ffs(uncbits) - 1;
-                        uncbits &= uncbits - 1;
-                        const int idx = p * kSweepThreads + tid;
-                        const ExactClass e = classify_exact(src, idx, pc, ref_x, ref_y, rg2, rc2);
-                        if (e.in) {
-                            const double v = (double)__ldg(src + idx).z + kCntUnit;
-                            a0 += v;
-                            if (e.down) a1 += v;
-                            if (e.right) a2 += v;
-                            if (e.cost) {
-                                a3 += v;
-                                if (e.down) a4 += v;
-                                if (e.right) a5 += v;
-                            }
-                        }
-                    }
-                }
-                a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3); a4 = warp_sum(a4); a5 = warp_sum(a5);
-                if (lane == 0) {
-                    // a = n * 2^17 + S with 0 <= S < 2^17 (<= 512 points, I < 256), everything exact
-                    const double inv = 1.0 / kCntUnit;
-                    const double n0 = (double)(long long)(a0 * inv), n1 = (double)(long long)(a1 * inv), n2 = (double)(long long)(a2 * inv);
-                    const double n3 = (double)(long long)(a3 * inv), n4 = (double)(long long)(a4 * inv), n5 = (double)(long long)(a5 * inv);
-                    store_totals(s_part[warp][k], a0 - n0 * kCntUnit, a1 - n1 * kCntUnit, a2 - n2 * kCntUnit, a3 - n3 * kCntUnit,
-                                 a4 - n4 * kCntUnit, a5 - n5 * kCntUnit, n0, n1, n2, n3, n4, n5);
-                }
-            }
-        } else {
-            // all-fp64 body: every predicate exactly as the reference, all candidates of the cell
-            for (int a = 0; a < nact; ++a) {
-                const int k = s_act[a];
-                const double ref_x = s_rx[k], ref_y = s_ry[k];
-                double tI = 0, dI = 0, rI = 0, cI = 0, cdI = 0, crI = 0;
-                int tN = 0, dN = 0, rN = 0, cN = 0, cdN = 0, crN = 0;
-                for (int idx = tid; idx < count; idx += kSweepThreads) {
-                    const float4 q = __ldg(src + idx);
-                    if (!((__float_as_uint(q.w) >> k) & 1u)) continue;
-                    const ExactClass e = classify_exact(src, idx, pc, ref_x, ref_y, rg2, rc2);
-                    if (!e.in) continue;
-                    const double I = (double)q.z;
-                    tI += I; tN++;
-                    if (e.down) { dI += I; dN++; }
-                    if (e.right) { rI += I; rN++; }
-                    if (e.cost) {
-                        cI += I; cN++;
-                        if (e.down) { cdI += I; cdN++; }
-                        if (e.right) { crI += I; crN++; }
-                    }
-                }
-                tI = warp_sum(tI); dI = warp_sum(dI); rI = warp_sum(rI); cI = warp_sum(cI); cdI = warp_sum(cdI); crI = warp_sum(crI);
-                tN = warp_sum(tN); dN = warp_sum(dN); rN = warp_sum(rN); cN = warp_sum(cN); cdN = warp_sum(cdN); crN = warp_sum(crN);
-                if (lane == 0) store_totals(s_part[warp][k], tI, dI, rI, cI, cdI, crI, tN, dN, rN, cN, cdN, crN);
-            }
-        }
-        __syncthreads();
-        {
-            const int k = tid >> 4, j = tid & 15;                       // 128 threads == 8 candidates x 16 accumulators
-            const int t = s_tid[k];
-            if (t >= 0) {
-                double v = 0;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) v += s_part[w][k][j];
-                if (v != 0.0) atomicAdd(&bv.acc[((size_t)f * bv.geom.nt + t) * 16 + j], v);
-            }
+// all-fp64 body (frames whose intensities cannot carry the count, or RCLC_SWEEP_EXACT=1): every predicate exactly as
+// the reference; one candidate at a time, points straight from global memory.
+__device__ __noinline__ void sweep_item_exact(const BatchView& bv, const float4* __restrict__ gsrc, int count, int lane, const PoseCoef& pc,
+                                              int t, int kbit, double* __restrict__ acc_t, double* scratch16)
+{
+    const double2 ref = bv.tgt_xy[t];
+    double tI = 0, dI = 0, rI = 0, cI = 0, cdI = 0, crI = 0;
+    int tN = 0, dN = 0, rN = 0, cN = 0, cdN = 0, crN = 0;
+    for (int idx = lane; idx < count; idx += 32) {
+        const float4 q = __ldg(gsrc + idx);
+        if (!((__float_as_uint(q.w) >> kbit) & 1u)) continue;
+        if (q.x == kSentinelXY) continue;
+        const ExactClass e = classify_exact(q.x, q.y, pc, ref.x, ref.y, bv.geom.rg2, bv.geom.rc2);
+        if (!e.in) continue;
+        const double I = (double)q.z;
+        tI += I; tN++;
+        if (e.down) { dI += I; dN++; }
+        if (e.right) { rI += I; rN++; }
+        if (e.cost) {
+            cI += I; cN++;
+            if (e.down) { cdI += I; cdN++; }
+            if (e.right) { crI += I; crN++; }
         }
     }
-    if (!bv.fuse_lm) return;
-    // ---- fused LM step: the last CTA of this frame's sweep owns the complete accumulator table ----
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&bv.sweep_done[f], 1) == max(n_items, 1) - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (tid == 0) bv.sweep_done[f] = 0;
-    lm_frame_step(bv, f);
+    tI = warp_sum(tI); dI = warp_sum(dI); rI = warp_sum(rI); cI = warp_sum(cI); cdI = warp_sum(cdI); crI = warp_sum(crI);
+    tN = warp_sum(tN); dN = warp_sum(dN); rN = warp_sum(rN); cN = warp_sum(cN); cdN = warp_sum(cdN); crN = warp_sum(crN);
+    if (lane == 0) store_totals(scratch16, tI, dI, rI, cI, cdI, crI, tN, dN, rN, cN, cdN, crN);
+    __syncwarp();
+    if (lane < 16) {
+        const double v = scratch16[lane];
+        if (v != 0.0) atomicAdd(acc_t + lane, v);
+    }
+    __syncwarp();
 }
-static_assert(kSweepThreads == kCand * 16, "final reduction maps one thread to one (candidate, accumulator)");
-static_assert(kSweepP % 4 == 0 && kSweepP * 32 * 256.0 <= kCntUnit, "count unit must exceed the largest per-warp intensity sum");
+
+constexpr size_t kSweepSmemTiles = (size_t)kSweepWarps * kStages * kTile * 16;
+constexpr size_t kSweepSmem = kSweepSmemTiles + (size_t)kSweepWarps * kStages * 8 + (size_t)kSweepWarps * 16 * 8 +
+                              (size_t)kSweepWarps * sizeof(LmStage) + (size_t)kSweepWarps * sizeof(WarpCtx) +
+                              (size_t)(kMaxBatchFrames + 1) * 4;
+
+static_assert(kSweepSmem + 1024 <= 233472 / 4, "four CTAs per SM must fit in 228 KB of shared memory");
+
+// Work enumeration: global item index g -> (frame, item). Frames that are active but have no item (every point
+// outside the lattice) still get one empty item so that their LM step runs.
+struct WorkMap {
+    const int* pref;       // shared: exclusive prefix of items per frame, [n_frames + 1]
+    int n_frames;
+    int uniform;           // > 0: every frame has this many items
+    int total;
+    int f_hint;
+};
+
+__device__ __forceinline__ bool work_lookup(WorkMap& wm, int g, int& f, int& item)
+{
+    if (g >= wm.total) return false;
+    if (wm.uniform > 0) { f = g / wm.uniform; item = g - f * wm.uniform; return true; }
+    int ff = wm.f_hint;
+    while (g >= wm.pref[ff + 1]) ++ff;         // g grows monotonically per warp
+    wm.f_hint = ff;
+    f = ff;
+    item = g - wm.pref[ff];
+    return true;
+}
+
+__device__ __forceinline__ void load_item(const BatchView& bv, int f, int item, ItemMeta& m)
+{
+    const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;
+    const int n_items = bv.uniform_items > 0 ? bv.uniform_items : bv.snap[f].n_items;
+    m.f = f;
+    if (item < n_items) {
+        const int4 it = __ldg(bv.items + (size_t)fd * bv.max_items + item);
+        m.cell = it.x;
+        m.count = it.z;
+        m.gsrc = bv.binned + (size_t)fd * bv.frame_stride + it.y;
+    } else {
+        m.cell = 0; m.count = 0; m.gsrc = bv.binned;
+    }
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(BatchView bv)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    float4* s_tiles = reinterpret_cast<float4*>(s_dyn);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_dyn + kSweepSmemTiles);
+    double* s_scratch = reinterpret_cast<double*>(s_bars + kSweepWarps * kStages);
+    LmStage* s_stage = reinterpret_cast<LmStage*>(s_scratch + kSweepWarps * 16);
+    WarpCtx* s_wctx = reinterpret_cast<WarpCtx*>(s_stage + kSweepWarps);
+    int* s_pref = reinterpret_cast<int*>(s_wctx + kSweepWarps);
+
+    // ---- items per frame -> prefix (every CTA builds the same table from the pre-launch snapshot) ----
+    WorkMap wm;
+    wm.pref = s_pref;
+    wm.n_frames = bv.n_frames;
+    wm.uniform = bv.uniform_items;
+    wm.f_hint = 0;
+    if (wm.uniform > 0) {
+        wm.total = wm.uniform * bv.n_frames;
+    } else {
+        const int F = bv.n_frames;
+        for (int f = tid; f < F; f += kSweepThreads) {
+            const SweepSnap& sn = bv.snap[f];
+            s_pref[f + 1] = sn.sweep_active ? max(sn.n_items, 1) : 0;
+        }
+        if (tid == 0) s_pref[0] = 0;
+        __syncthreads();
+        if (warp == 0) {                      // inclusive scan of s_pref[1..F] by one warp, 32 frames at a time
+            int carry = 0;
+            for (int base = 1; base <= F; base += 32) {
+                const int idx = base + lane;
+                int v = idx <= F ? s_pref[idx] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+                if (idx <= F) s_pref[idx] = v + carry;
+                carry += __shfl_sync(0xffffffffu, v, 31);
+            }
+        }
+        __syncthreads();
+        wm.total = s_pref[F];
+    }
+    const int stride = gridDim.x * kSweepWarps;
+    int g = blockIdx.x * kSweepWarps + warp;
+    if (g >= wm.total) return;
+
+    WarpRing ring;
+    ring.tiles = smem_addr(s_tiles + (size_t)warp * kStages * kTile);
+    ring.bars = smem_addr(s_bars + warp * kStages);
+    ring.gen = s_tiles + (size_t)warp * kStages * kTile;
+    if (lane == 0) {
+        for (int st = 0; st < kStages; ++st) mbar_init(ring.bars + st * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    double* scratch16 = s_scratch + warp * 16;
+    WarpCtx* wc = s_wctx + warp;
+    const double rg2 = bv.geom.rg2, rc2 = bv.geom.rc2;
+    const float rn2 = bv.geom.rn2f;
+    const float rgf = sqrtf((float)rg2);
+
+    ItemMeta cur, nxt;
+    {
+        int f, item;
+        work_lookup(wm, g, f, item);
+        load_item(bv, f, item, cur);
+    }
+    nxt = cur;
+    StreamState st;
+    st.issued = 0; st.consumed = 0;
+    st.pass_cur = 0; st.tile_cur = 0; st.tile_nxt = 0;
+    st.npass_cur = 1; st.count_cur = cur.count; st.nt_cur = item_tiles(cur.count); st.g_cur = cur.gsrc;
+    st.count_nxt = 0; st.nt_nxt = 0; st.g_nxt = cur.gsrc;
+    ring_fill(ring, st, lane);          // first tiles of the first item are in flight from here on
+
+    for (;;) {
+        // ---- next item's metadata: the load is in flight while this item is set up and swept ----
+        bool have_nxt;
+        {
+            int f, item;
+            have_nxt = work_lookup(wm, g + stride, f, item);
+            if (have_nxt) load_item(bv, f, item, nxt);
+            st.count_nxt = have_nxt ? nxt.count : 0;
+            st.nt_nxt = item_tiles(st.count_nxt);
+            st.g_nxt = nxt.gsrc;
+        }
+        const int f = cur.f;
+        const SweepSnap& sn = bv.snap[f];
+        // (k_scatter may still have been OR-ing ctl.use_exact when it took the snapshot; the multi-start snapshot is final)
+        const bool exact_body = bv.force_exact || (bv.uniform_items > 0 ? sn.use_exact : bv.ctl[f].use_exact);
+        const PoseCoef pc = sn.pose;
+
+        // ---- live candidates of this cell under this pose (lane k < 8 examines candidate k) ----
+        int t = -1;
+        float rxf = 0.f, ryf = 0.f;
+        bool live = false;
+        // cell rectangle in the (un-posed) frame the points are stored in, with a safety margin
+        const int ca = cur.cell % bv.geom.ncx, cb = cur.cell / bv.geom.ncx;
+        const double x0 = (bv.geom.i0 + ca) * bv.geom.g - 1e-6, x1 = (bv.geom.i0 + ca + 1) * bv.geom.g + 1e-6;
+        const double y0 = (bv.geom.j0 + cb) * bv.geom.g - 1e-6, y1 = (bv.geom.j0 + cb + 1) * bv.geom.g + 1e-6;
+        if (lane < kCand && cur.count > 0) {
+            const float4 cf = __ldg(bv.cell_cand_f + (size_t)cur.cell * kCand + lane);
+            t = __float_as_int(cf.z);
+            if (t >= 0) {
+                rxf = cf.x; ryf = cf.y;
+                // p' = R (p + t)  =>  |p' - ref| = |p - (R^T ref - t)|
+                const double cx = pc.r00 * (double)rxf + pc.r10 * (double)ryf - pc.tx, cy = pc.r01 * (double)rxf + pc.r11 * (double)ryf - pc.ty;
+                const double ex = fmax(fmax(x0 - cx, cx - x1), 0.0), ey = fmax(fmax(y0 - cy, cy - y1), 0.0);
+                const double reach = sqrt(rg2) + 1e-5;
+                live = exact_body || (ex * ex + ey * ey) <= reach * reach;
+            }
+        }
+        const unsigned livebits = __ballot_sync(0xffffffffu, live);
+        const int nact = __popc(livebits);
+
+        if (exact_body || nact == 0) {
+            // the copy engine already holds this item's first tiles: drain them so the ring stays in step
+            st.npass_cur = 1;
+            for (int tt = 0; tt < st.nt_cur; ++tt) {
+                ring_acquire(ring, st);
+                ring_release(ring, st, lane);
+            }
+            for (int a = 0; a < nact; ++a) {
+                const int kl = __fns(livebits, 0, a + 1);
+                const int tk = __shfl_sync(0xffffffffu, t, kl);
+                sweep_item_exact(bv, cur.gsrc, cur.count, lane, pc, tk, kl, bv.acc + ((size_t)f * bv.geom.nt + tk) * 16, scratch16);
+            }
+        } else {
+            const float pmax = (float)sqrt(fmax(x0 * x0, x1 * x1) + fmax(y0 * y0, y1 * y1));
+            const float r00f = (float)pc.r00, txf = (float)pc.tx, tyf = (float)pc.ty;
+            // Can the kd-tree neighbour mask (3-D distance < neighbour_radius at pose 0, board_fitting_cost.h:273) exclude a
+            // point that the pose moves into a gradient disc? Not while (rg + max displacement)^2 + max z^2 < rn^2.
+            const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;
+            const float z2max = __uint_as_float(bv.cellz2[(size_t)fd * bv.geom.ncells + cur.cell]);
+            const float disp = sqrtf(fmaxf(0.f, 2.f - 2.f * r00f)) * pmax + fabsf(txf) + fabsf(tyf) + 1e-5f;
+            const bool masked = !((rgf + disp) * (rgf + disp) + z2max < rn2 * 0.9999f);
+            st.npass_cur = (nact + kPassCand - 1) / kPassCand;
+            ring_fill(ring, st, lane);
+            __syncwarp();
+            // the live candidates in pass order; lane j < nact publishes the j-th one
+            {
+                const int kl = __fns(livebits, 0, min(lane, nact - 1) + 1) & 31;
+                const int tkj = __shfl_sync(0xffffffffu, t, kl);
+                const float rxj = __shfl_sync(0xffffffffu, rxf, kl), ryj = __shfl_sync(0xffffffffu, ryf, kl);
+                if (lane < kCand) {
+                    wc->tk[lane] = tkj; wc->rx[lane] = rxj; wc->ry[lane] = ryj;
+                    wc->bit[lane] = lane < nact ? (1u << kl) : 0u;      // padding candidates (masked passes only) own no point
+                }
+            }
+            if (lane == 0) {
+                SweepConst k;
+                k.r00 = r00f; k.r01 = (float)pc.r01; k.r10 = (float)pc.r10; k.r11 = (float)pc.r11;
+                k.tx = txf; k.ty = tyf;
+                k.rg2 = (float)rg2; k.rc2 = (float)rc2;
+                const double Bc = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))) + fabs(pc.tx) + fabs(pc.ty) + 0.1;
+                k.E = (float)(12.0 * 5.9604644775390625e-8 * Bc + 1e-9);
+                k.E2 = 1.05f * (2.9f * sqrtf(k.rg2) * k.E + 3e-7f * k.rg2 + 2.f * k.E * k.E + 1e-9f);
+                wc->k = k;
+                wc->pc = pc;
+                wc->st = st;
+            }
+            __syncwarp();
+            for (int a0 = 0; a0 < nact; a0 += kPassCand) {
+                const int n = min(kPassCand, nact - a0);
+                double acc[kPassCand * 6];
+                if (masked) {
+                    if (n <= 2) sweep_pass<2, true>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
+                    else sweep_pass<4, true>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
+                } else {
+                    if (n == 1) sweep_pass<1, false>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
+                    else if (n == 2) sweep_pass<2, false>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
+                    else if (n == 3) sweep_pass<3, false>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
+                    else sweep_pass<4, false>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
+                }
+                for (int j = 0; j < n; ++j) {
+                    double a6[6];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) a6[q] = acc[j * 6 + q];
+                    to_nested_totals(a6);
+                    flush_candidate(a6, bv.acc + ((size_t)f * bv.geom.nt + wc->tk[a0 + j]) * 16, scratch16, lane);
+                }
+            }
+            st = wc->st;
+        }
+
+        // ---- fused LM step: the warp that finishes the frame's last item owns the complete accumulator table ----
+        if (bv.fuse_lm) {
+            __threadfence();
+            int last = 0;
+            if (lane == 0) last = (atomicAdd(&bv.sweep_done[f], 1) == max(sn.n_items, 1) - 1);
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                if (lane == 0) bv.sweep_done[f] = 0;
+                lm_frame_step(bv, f, s_stage + warp);
+            }
+        }
+
+        if (!have_nxt) break;
+        g += stride;
+        cur = nxt;
+        // the first pass of the new item may already be (partly) issued
+        st.pass_cur = (st.tile_nxt >= st.nt_nxt && st.nt_nxt > 0) ? 1 : 0;
+        st.tile_cur = (st.tile_nxt >= st.nt_nxt) ? 0 : st.tile_nxt;
+        st.tile_nxt = 0;
+        st.npass_cur = 1; st.count_cur = st.count_nxt; st.nt_cur = st.nt_nxt; st.g_cur = st.g_nxt;
+        st.count_nxt = 0; st.nt_nxt = 0;
+    }
+}
 
 __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
 {
@@ -1064,6 +1480,7 @@ __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
         bv.ctl[f].pose = poses[f];
         bv.ctl[f].sweep_active = 1;
         bv.ctl[f].rebin = 0;
+        snapshot_frame(bv, f);
     }
 }
 
@@ -1073,10 +1490,15 @@ __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
 // Not in the reference: cost(p) = sum_k 0.5 * rho_Huber(r_k(p)^2) with r_k from
 // BOARD_FITTING_COST::Evaluate, i.e. what ceres::Problem::Evaluate would report at pose p.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, const PoseCoef* __restrict__ poses, int P, int frame)
+__global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, SweepSnap* snap_ms, const PoseCoef* __restrict__ poses, int P, int frame)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
+    {
+        SweepSnap sn;
+        sn.sweep_active = 1; sn.n_items = bv.ctl[frame].n_items; sn.use_exact = bv.ctl[frame].use_exact; sn.pad_ = 0; sn.pose = poses[p];
+        snap_ms[p] = sn;
+    }
     FrameCtl c;
     c.sweep_active = 1;
     c.rebin = 0;
@@ -1138,11 +1560,14 @@ static int launch_rebin(rclc_batch* b)
     return RCLC_OK;
 }
 
+// persistent grid: 4 CTAs of 4 warps per SM, every warp walks the item list with stride gridDim.x * 4
+static int sweep_grid_x(const rclc_batch* b) { return b->ctx->sm_count * 4; }
+
 static int launch_sweep(rclc_batch* b, bool fuse_lm)
 {
     BatchView v = b->v;
     v.fuse_lm = fuse_lm ? 1 : 0;
-    k_sweep<<<dim3((unsigned)b->v.max_items, (unsigned)b->n_frames), kSweepThreads, 0, b->ctx->stream>>>(v);
+    k_sweep<<<sweep_grid_x(b), kSweepThreads, kSweepSmem, b->ctx->stream>>>(v);
     b->ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
@@ -1179,7 +1604,8 @@ int rclc_generate_targets(const rclc_config* cfg, double* targets_xy, int32_t* i
 int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, int64_t max_pts, rclc_batch** out)
 {
     RCLC_CHECK(ctx && cfg && out, RCLC_ERR_INVALID, "null argument");
-    RCLC_CHECK(n_frames > 0 && max_pts > 0 && max_pts < (1ll << 31) - kChunk, RCLC_ERR_INVALID, "bad batch shape");
+    RCLC_CHECK(n_frames > 0 && n_frames <= kMaxBatchFrames && max_pts > 0 && max_pts < (1ll << 30), RCLC_ERR_INVALID,
+               "bad batch shape (1..512 frames per batch)");
     RCLC_CUDA(cudaSetDevice(ctx->device));
     HostGeom hg;
     RCLC_TRY(build_geom(*cfg, hg));
@@ -1196,8 +1622,10 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.fixed_frame = -1;
     v.fuse_lm = 0;
     v.force_exact = b->sweep_exact ? 1 : 0;
-    v.frame_stride = (int64_t)align256((size_t)max_pts * 16) / 16;
-    v.max_items = hg.g.ncells + (int)((max_pts + kChunk - 1) / kChunk);
+    // every cell's segment of `binned` is padded to a multiple of 32 points
+    v.frame_stride = (int64_t)align256(((size_t)max_pts + 32 * (size_t)hg.g.ncells) * 16) / 16;
+    v.max_items = hg.g.ncells + (int)((max_pts + 32 * (int64_t)hg.g.ncells + kItemMax - 1) / kItemMax);
+    RCLC_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
     const size_t F = n_frames, nt = hg.g.nt, ncell = hg.g.ncells;
     auto fail = [&](const char* what) { set_last_error(what); rclc_batch_destroy(b); return RCLC_ERR_CUDA; };
     const size_t big = F * (size_t)v.frame_stride * 16;
@@ -1207,10 +1635,11 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     // small arrays in one block
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
-    const size_t o_npts = take(F * 8), o_hist = take(F * ncell * 4), o_cur = take(F * ncell * 4);
+    const size_t o_npts = take(F * 8), o_hist = take(F * ncell * 4), o_cur = take(F * ncell * 4), o_cmask = take(F * ncell * 4);
     const size_t o_items = take(F * (size_t)v.max_items * 16), o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
     const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_txy = take(nt * 16), o_txyf = take(nt * 8);
     const size_t o_row = take(nt), o_cand = take(ncell * kCand * 2), o_eval = take(F * nt * 4 * 8);
+    const size_t o_snap = take(F * sizeof(SweepSnap)), o_candf = take(ncell * kCand * 16);
     const size_t o_corn = take(F * (size_t)hg.g.nc * 3 * 8), o_gmm = take(F * 64 * 8 + 4096 * 8 * 8);
     if (cudaMalloc(&b->d_block, off) != cudaSuccess) return fail("cudaMalloc block");
     char* base = static_cast<char*>(b->d_block);
@@ -1219,6 +1648,7 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.n_pts = b->d_npts;
     v.hist = reinterpret_cast<int*>(base + o_hist);
     v.cursor = reinterpret_cast<int*>(base + o_cur);
+    v.cellz2 = reinterpret_cast<unsigned*>(base + o_cmask);
     v.items = reinterpret_cast<int4*>(base + o_items);
     v.acc = reinterpret_cast<double*>(base + o_acc);
     v.ctl = reinterpret_cast<FrameCtl*>(base + o_ctl);
@@ -1229,6 +1659,9 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.tgt_xyf = reinterpret_cast<float2*>(base + o_txyf);
     v.tgt_is_row = reinterpret_cast<uint8_t*>(base + o_row);
     v.cell_cand = reinterpret_cast<int16_t*>(base + o_cand);
+    v.cell_cand_f = reinterpret_cast<float4*>(base + o_candf);
+    v.snap = reinterpret_cast<SweepSnap*>(base + o_snap);
+    v.uniform_items = 0;
     v.eval_out = reinterpret_cast<double*>(base + o_eval);
     v.corners = reinterpret_cast<double*>(base + o_corn);
     b->d_gmm = reinterpret_cast<double*>(base + o_gmm);
@@ -1236,6 +1669,15 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     cudaMemcpyAsync(base + o_txyf, hg.tgt_xyf.data(), nt * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(base + o_row, hg.is_row.data(), nt, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(base + o_cand, hg.cell_cand.data(), ncell * kCand * 2, cudaMemcpyHostToDevice, ctx->stream);
+    std::vector<float4> candf(ncell * kCand);
+    for (size_t k = 0; k < candf.size(); ++k) {
+        const int t = hg.cell_cand[k];
+        int tb = t;
+        float tf;
+        std::memcpy(&tf, &tb, 4);
+        candf[k] = t >= 0 ? make_float4(hg.tgt_xyf[t].x, hg.tgt_xyf[t].y, tf, 0.f) : make_float4(0.f, 0.f, tf, 0.f);
+    }
+    cudaMemcpyAsync(base + o_candf, candf.data(), candf.size() * 16, cudaMemcpyHostToDevice, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail("batch setup copies");
     *out = b;
     return RCLC_OK;
@@ -1429,37 +1871,39 @@ int rclc_batch_multistart(rclc_batch* b, int32_t frame, const double* poses, int
     RCLC_CUDA(cudaSetDevice(ctx->device));
     const size_t nt = b->v.geom.nt;
     const size_t o_ctl = (sizeof(PoseCoef) * P + 255) & ~(size_t)255;
-    const size_t o_acc = o_ctl + ((sizeof(FrameCtl) * P + 255) & ~(size_t)255);
+    const size_t o_snap = o_ctl + ((sizeof(FrameCtl) * P + 255) & ~(size_t)255);
+    const size_t o_acc = o_snap + ((sizeof(SweepSnap) * P + 255) & ~(size_t)255);
     const size_t o_cost = o_acc + (size_t)P * nt * 16 * 8;
     RCLC_TRY(ctx->d_tmp.reserve(o_cost + (size_t)P * 8));
-    RCLC_TRY(ctx->h_pin2.reserve(sizeof(PoseCoef) * P));
+    RCLC_TRY(ctx->h_pin2.reserve(sizeof(PoseCoef) * P + 64));
+    // items of the (binned) frame: the persistent sweep enumerates P x n_items work items
+    int* h_items = reinterpret_cast<int*>(ctx->h_pin2.as<char>() + sizeof(PoseCoef) * P);
+    RCLC_CUDA(cudaMemcpyAsync(h_items, &b->v.ctl[frame].n_items, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n_items = std::max(*h_items, 1);
+    RCLC_CHECK((int64_t)n_items * P < (1ll << 31), RCLC_ERR_UNSUPPORTED, "too many (pose, item) pairs for one multi-start call");
     PoseCoef* hp = ctx->h_pin2.as<PoseCoef>();
     for (int p = 0; p < P; ++p) hp[p] = host_pose_coef(poses + 3 * p);
     char* base = static_cast<char*>(ctx->d_tmp.p);
     PoseCoef* d_poses = reinterpret_cast<PoseCoef*>(base);
     FrameCtl* d_ctl = reinterpret_cast<FrameCtl*>(base + o_ctl);
+    SweepSnap* d_snap = reinterpret_cast<SweepSnap*>(base + o_snap);
     double* d_acc = reinterpret_cast<double*>(base + o_acc);
     double* d_cost = reinterpret_cast<double*>(base + o_cost);
     RCLC_CUDA(cudaMemcpyAsync(d_poses, hp, sizeof(PoseCoef) * P, cudaMemcpyHostToDevice, ctx->stream));
     RCLC_CUDA(cudaMemsetAsync(d_acc, 0, (size_t)P * nt * 16 * 8, ctx->stream));
     BatchView v = b->v;
-    k_ms_setup<<<(P + 127) / 128, 128, 0, ctx->stream>>>(b->v, d_ctl, d_poses, P, frame);
+    k_ms_setup<<<(P + 127) / 128, 128, 0, ctx->stream>>>(b->v, d_ctl, d_snap, d_poses, P, frame);
     v.ctl = d_ctl;
+    v.snap = d_snap;
     v.acc = d_acc;
     v.fixed_frame = frame;
     v.fuse_lm = 0;
     v.n_frames = P;
-    // blockIdx.y is limited to 65535: sweep poses in slabs
-    for (int p0 = 0; p0 < P; p0 += 32768) {
-        const int np = std::min(32768, P - p0);
-        BatchView vs = v;
-        vs.ctl = d_ctl + p0;
-        vs.acc = d_acc + (size_t)p0 * nt * 16;
-        k_sweep<<<dim3((unsigned)b->v.max_items, (unsigned)np), kSweepThreads, 0, ctx->stream>>>(vs);
-        k_ms_cost<<<np, kLmThreads, 0, ctx->stream>>>(vs, d_cost + p0);
-        ctx->launches += 2;
-    }
+    v.uniform_items = n_items;
+    k_sweep<<<sweep_grid_x(b), kSweepThreads, kSweepSmem, ctx->stream>>>(v);
+    k_ms_cost<<<P, kLmThreads, 0, ctx->stream>>>(v, d_cost);
+    ctx->launches += 2;
     ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     RCLC_CUDA(cudaMemcpyAsync(cost_out, d_cost, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));

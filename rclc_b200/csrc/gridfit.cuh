@@ -4,8 +4,11 @@
 // kd-tree neighbour copy (board_fitting_cost.h:124-210, 3.3*N point visits per sweep, fp64). Here a
 // frame's points are counting-sorted ONCE per outer iteration into the cells of the half-square
 // lattice on which all targets sit; a cell has at most 8 candidate targets, and each point carries an
-// 8-bit mask of exact (FLANN-equivalent) neighbour membership. A sweep then streams 16 B per point,
-// every CTA works on one cell, accumulates in registers and block-reduces — no atomics in the hot loop.
+// 8-bit mask of exact (FLANN-equivalent) neighbour membership. Every cell's segment is padded to a
+// multiple of 32 points with far-away sentinels, so a warp row never straddles two cells. A sweep then
+// streams 16 B per point: one WARP owns one item (<= kItemMax points of one cell), pulls it through a
+// private TMA bulk-copy ring in shared memory and keeps the sums of its <= 4 live candidate targets in
+// registers — no atomics and no block barrier in the hot loop.
 #pragma once
 #include "common.cuh"
 
@@ -15,8 +18,12 @@ constexpr int kMaxTargets = 1024;
 constexpr int kMaxCells = 4096;
 constexpr int kCand = 8;                 // candidate targets per cell
 constexpr int kSweepThreads = 128;
-constexpr int kSweepP = 16;              // points per thread (registers: fp32 x', y' + fp64 intensity)
-constexpr int kChunk = kSweepThreads * kSweepP;
+constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr int kItemMax = 2048;           // points per warp item (<= 512 per lane: the count rides in the fp64 sum)
+constexpr int kTile = 256;               // points per TMA bulk copy (4 KB)
+constexpr int kStages = 2;               // ring depth per warp (power of two): one tile computing, one in flight
+constexpr int kPassCand = 4;             // candidates whose sums live in registers during one pass over an item
+constexpr int kMaxBatchFrames = 512;     // per-CTA prefix table of items per frame
 constexpr int kBinThreads = 256;
 constexpr int kBinP = 8;
 constexpr int kBinChunk = kBinThreads * kBinP;
@@ -57,6 +64,17 @@ struct FrameCtl {
     PoseCoef pose;             // pose the next sweep evaluates
 };
 
+// What one k_sweep launch needs to know about a frame. Written BEFORE the launch (k_scatter / k_set_pose /
+// k_ms_setup) and never during it: the fused LM step of a frame that finishes early rewrites FrameCtl while other
+// warps of the same launch are still enumerating work.
+struct SweepSnap {
+    int sweep_active;
+    int n_items;
+    int use_exact;
+    int pad_;
+    PoseCoef pose;
+};
+
 // Ceres TrustRegionMinimizer state + opt_grid_fitting outer-loop state, one per frame.
 struct LmState {
     int phase;
@@ -90,9 +108,12 @@ struct BatchView {
     float4* binned;                // [F][frame_stride]   cell-sorted {x, y, I, mask bits}
     int* hist;                     // [F][ncells]
     int* cursor;                   // [F][ncells]
-    int4* items;                   // [F][max_items]  {cell, start, count, 0}
+    unsigned* cellz2;              // [F][ncells] float bits of max z^2 over the cell's points (decides whether the neighbour mask can matter)
+    int4* items;                   // [F][max_items]  {cell, start, count (multiple of 32), 0}
     double* acc;                   // [F][nt][16]
     FrameCtl* ctl;                 // [F]
+    SweepSnap* snap;               // [F]   (multi-start: [P])
+    int uniform_items;             // > 0: every "frame" (pose) has this many items (multi-start sweep)
     LmState* lm;                   // [F]
     int* n_done;                   // [1]
     int* sweep_done;               // [F] CTAs of the current sweep that have finished (last one runs the LM step)
@@ -103,6 +124,7 @@ struct BatchView {
     const float2* tgt_xyf;         // [nt] (float)target  (FLANN query point)
     const uint8_t* tgt_is_row;     // [nt]
     const int16_t* cell_cand;      // [ncells][8] target index or -1
+    const float4* cell_cand_f;     // [ncells][8] {(float)target x, (float)target y, target index bits, 0}
     double* eval_out;              // [F][nt][4] residual, j0, j1, j2 (rclc_batch_read_eval)
     double* corners;               // [F][nc][3]
 };

@@ -64,6 +64,9 @@ int rclc_ctx_timer_start(rclc_ctx* ctx);
 int rclc_ctx_timer_stop_ms(rclc_ctx* ctx, float* ms_out);   /* records stop, synchronises, returns ms */
 int rclc_ctx_flush_l2(rclc_ctx* ctx);               /* writes a buffer larger than L2            */
 int64_t rclc_ctx_kernel_launches(rclc_ctx* ctx);    /* kernels launched by this ctx so far       */
+/* device time of the k_sweep kernel launched by the last rclc_batch_sweep (CUDA events recorded on the ctx stream
+ * immediately before and after that launch; synchronises on the second one) */
+int rclc_ctx_last_sweep_ms(rclc_ctx* ctx, float* ms_out);
 
 /* ---- utils.h:286-316 generate_std_corners: col targets then row targets (opt_grid_fitting.h:78-94) ---- */
 int rclc_generate_targets(const rclc_config* cfg, double* targets_xy, int32_t* is_row, int32_t* n_targets);

@@ -121,6 +121,11 @@ class Context:
     def kernel_launches(self):
         return lib().rclc_ctx_kernel_launches(self.h)
 
+    def last_sweep_ms(self):
+        ms = C.c_float()
+        _chk(lib().rclc_ctx_last_sweep_ms(self.h, C.byref(ms)))
+        return ms.value
+
     # ---- single-frame operators (host pointers in, host pointers out) ----
     def gridfit_eval(self, cfg, pts, pose, want_acc=False):
         pts, stride, ioff = _cloud(pts)

@@ -40,6 +40,16 @@ __global__ void k_fill(float4* p, size_t n, float v)
     for (; i < n; i += step) p[i] = make_float4(v, v, v, v);
 }
 
+// reads n float4 and keeps the loads alive through a (never taken) store
+__global__ void k_read_sink(const float4* __restrict__ p, size_t n, float* sink)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    float s = 0.f;
+    for (; i < n; i += step) { const float4 v = __ldcs(p + i); s += v.x + v.y + v.z + v.w; }
+    if (s == 123.456f) *sink = s;
+}
+
 } // namespace rclc
 
 extern "C" {
@@ -70,6 +80,8 @@ int rclc_ctx_create(int device, rclc_ctx** out)
     RCLC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     RCLC_CUDA(cudaEventCreate(&c->ev0));
     RCLC_CUDA(cudaEventCreate(&c->ev1));
+    RCLC_CUDA(cudaEventCreate(&c->evk0));
+    RCLC_CUDA(cudaEventCreate(&c->evk1));
     *out = c;
     return RCLC_OK;
 }
@@ -83,6 +95,8 @@ int rclc_ctx_destroy(rclc_ctx* c)
     c->h_pin.release(); c->h_pin2.release();
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->evk0);
+    cudaEventDestroy(c->evk1);
     cudaStreamDestroy(c->stream);
     delete c;
     return RCLC_OK;
@@ -126,13 +140,28 @@ int rclc_ctx_timer_stop_ms(rclc_ctx* c, float* ms_out)
 int rclc_ctx_flush_l2(rclc_ctx* c)
 {
     RCLC_CHECK(c, RCLC_ERR_INVALID, "ctx is null");
-    const size_t bytes = (size_t)std::max<int64_t>(c->l2_bytes * 2, 256ll << 20);
-    RCLC_TRY(c->d_flush.reserve(bytes));
-    rclc::k_fill<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_flush.as<float4>(), bytes / 16, 1.0f);
+    // Two regions of 2 x L2 each, READ alternately: every flush misses everywhere and leaves L2 full of CLEAN foreign
+    // lines. (A write flush leaves it full of dirty lines, and the kernel timed next would pay for their write-back.)
+    const size_t half = (size_t)std::max<int64_t>(c->l2_bytes * 2, 256ll << 20);
+    if (c->d_flush.cap < 2 * half + 256) {
+        RCLC_TRY(c->d_flush.reserve(2 * half + 256));
+        rclc::k_fill<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_flush.as<float4>(), (2 * half + 256) / 16, 1.0f);
+    }
+    c->flush_parity ^= 1;
+    const float4* region = c->d_flush.as<float4>() + (c->flush_parity ? half / 16 : 0);
+    rclc::k_read_sink<<<c->sm_count * 8, 256, 0, c->stream>>>(region, half / 16, reinterpret_cast<float*>(c->d_flush.as<char>() + 2 * half));
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
 }
 
 int64_t rclc_ctx_kernel_launches(rclc_ctx* c) { return c ? c->launches : 0; }
+
+int rclc_ctx_last_sweep_ms(rclc_ctx* c, float* ms_out)
+{
+    RCLC_CHECK(c && ms_out, RCLC_ERR_INVALID, "null argument");
+    RCLC_CUDA(cudaEventSynchronize(c->evk1));
+    RCLC_CUDA(cudaEventElapsedTime(ms_out, c->evk0, c->evk1));
+    return RCLC_OK;
+}
 
 } // extern "C"

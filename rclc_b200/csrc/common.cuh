@@ -66,9 +66,11 @@ struct rclc_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evk0 = nullptr, evk1 = nullptr;       // bracket the last k_sweep launched by rclc_batch_sweep
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     int64_t l2_bytes = 0;
     int64_t launches = 0;
+    int flush_parity = 0;
     rclc::Buf d_pts, d_tmp, d_tmp2, d_out, d_flush;   // device scratch
     rclc::Buf h_pin, h_pin2;                           // pinned staging
     rclc_ctx() { h_pin.pinned = true; h_pin2.pinned = true; }

@@ -112,7 +112,10 @@ static int build_geom(const rclc_config& c, HostGeom& hg)
     g.ncx = imax - imin + 4;
     g.ncy = jmax - jmin + 4;
     g.ncells = g.ncx * g.ncy;
-    RCLC_CHECK(g.ncells <= kMaxCells, RCLC_ERR_UNSUPPORTED, "board too large for the cell table");
+    RCLC_CHECK(g.ncells <= kMaxCoarse, RCLC_ERR_UNSUPPORTED, "board too large for the cell table");
+    g.sub = 4;                                  // finest sub-cell sort that fits the shared-memory histograms
+    while (g.sub > 1 && g.ncells * g.sub * g.sub > kMaxCells) g.sub >>= 1;
+    g.nfine = g.ncells * g.sub * g.sub;
     hg.cell_cand.assign((size_t)g.ncells * kCand, -1);
     for (int b = 0; b < g.ncy; ++b)
         for (int a = 0; a < g.ncx; ++a) {
@@ -148,12 +151,16 @@ static PoseCoef host_pose_coef(const double pose[3])
 // ------------------------------------------------------------------------------------------------
 // Device helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cell_of(const GridGeom& g, float x, float y)
+// Sort key of a point: lattice cell (the unit the candidate tables are built on) and, inside it, one of sub x sub
+// sub-cells, so that consecutive points of a cell's segment are spatial neighbours. Returns cell * sub^2 + sub-cell,
+// or -1 outside the lattice.
+__device__ __forceinline__ int fine_of(const GridGeom& g, float x, float y)
 {
-    const int ci = (int)floor((double)x * g.inv_g) - g.i0;
-    const int cj = (int)floor((double)y * g.inv_g) - g.j0;
-    if (ci < 0 || cj < 0 || ci >= g.ncx || cj >= g.ncy) return -1;
-    return cj * g.ncx + ci;
+    const int fi = (int)floor((double)x * (g.inv_g * g.sub)) - g.i0 * g.sub;
+    const int fj = (int)floor((double)y * (g.inv_g * g.sub)) - g.j0 * g.sub;
+    if (fi < 0 || fj < 0 || fi >= g.ncx * g.sub || fj >= g.ncy * g.sub) return -1;
+    const int ci = fi / g.sub, cj = fj / g.sub;
+    return (cj * g.ncx + ci) * (g.sub * g.sub) + (fj - cj * g.sub) * g.sub + (fi - ci * g.sub);
 }
 
 // FLANN L2_Simple<float> over (x,y,z), kept when dist < radius^2 (board_fitting_cost.h:273).
@@ -244,16 +251,15 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
 {
     const int f = blockIdx.x;
     const int tid = threadIdx.x;
-    const int nc = bv.geom.ncells;
-    for (int c = tid; c < nc; c += blockDim.x) {
-        bv.hist[(size_t)f * nc + c] = 0; bv.cursor[(size_t)f * nc + c] = 0; bv.cellz2[(size_t)f * nc + c] = 0u;
-    }
+    const int nc = bv.geom.ncells, nf = bv.geom.nfine;
+    for (int c = tid; c < nf; c += blockDim.x) { bv.hist[(size_t)f * nf + c] = 0; bv.cursor[(size_t)f * nf + c] = 0; }
+    for (int c = tid; c < nc; c += blockDim.x) { bv.cellz2[(size_t)f * nc + c] = 0u; bv.cellcnt[(size_t)f * nc + c] = 0; }
     for (int k = tid; k < bv.geom.nt * 16; k += blockDim.x) bv.acc[(size_t)f * bv.geom.nt * 16 + k] = 0.0;
     if (tid == 0) {
         FrameCtl& c = bv.ctl[f];
         LmState& s = bv.lm[f];
         c.rebin = 1;
-        c.n_items = 0;
+        c.n_rows = 0;
         c.n_binned = 0;
         c.use_exact = 0;
         c.pad_ = 0;
@@ -290,8 +296,8 @@ __global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
     const int64_t n = bv.n_pts[f];
     if ((int64_t)blockIdx.x * kBinChunk >= n) return;
     __shared__ int s_hist[kMaxCells];
-    const int nc = bv.geom.ncells;
-    for (int k = threadIdx.x; k < nc; k += kBinThreads) s_hist[k] = 0;
+    const int nf = bv.geom.nfine;
+    for (int k = threadIdx.x; k < nf; k += kBinThreads) s_hist[k] = 0;
     __syncthreads();
     const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
     const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
@@ -304,31 +310,18 @@ __global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
                 const float4 q = __ldg(src + idx);
                 const float x = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
                 const float y = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
-                const int cell = cell_of(bv.geom, x, y);
-                if (cell >= 0) atomicAdd(&s_hist[cell], 1);
+                const int fine = fine_of(bv.geom, x, y);
+                if (fine >= 0) atomicAdd(&s_hist[fine], 1);
             }
         }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < nc; k += kBinThreads)
-        if (s_hist[k]) atomicAdd(&bv.hist[(size_t)f * nc + k], s_hist[k]);
-}
-
-// The sweep's read-only view of a frame (see SweepSnap).
-__device__ __forceinline__ void snapshot_frame(const BatchView& bv, int f)
-{
-    const FrameCtl& c = bv.ctl[f];
-    SweepSnap sn;
-    sn.sweep_active = c.sweep_active;
-    sn.n_items = c.n_items;
-    sn.use_exact = 0;
-    sn.pad_ = 0;
-    sn.pose = c.pose;
-    bv.snap[f] = sn;
+    for (int k = threadIdx.x; k < nf; k += kBinThreads)
+        if (s_hist[k]) atomicAdd(&bv.hist[(size_t)f * nf + k], s_hist[k]);
 }
 
 // A cell's segment of `binned` is padded to a multiple of 32 points with sentinels that are far outside every
-// disc for every pose, so the sweep needs no tail predicate and a warp row never mixes two cells.
+// disc for every pose, so the sweep needs no tail predicate and a 32-point row never mixes two cells.
 __device__ __forceinline__ int pad32(int v) { return (v + 31) & ~31; }
 constexpr float kSentinelXY = 3.0e18f;      // (3e18)^2 * 2 is finite in fp32
 
@@ -336,22 +329,38 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
 {
     const int f = blockIdx.y;
     FrameCtl& c = bv.ctl[f];
-    if (!c.rebin) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) snapshot_frame(bv, f);
-        return;
-    }
+    if (!c.rebin) return;
     const int64_t n = bv.n_pts[f];
     if ((int64_t)blockIdx.x * kBinChunk >= n && blockIdx.x != 0) return;
-    __shared__ int s_off[kMaxCells];
+    __shared__ int s_off[kMaxCells];       // first: fine histogram; then: offset of every (cell, sub-cell) bin in `binned`
     __shared__ int s_loc[kMaxCells];
+    __shared__ int s_cell[kMaxCoarse];
     __shared__ int s_part[kBinThreads];
     __shared__ int s_bad;
-    const int nc = bv.geom.ncells;
+    const int nc = bv.geom.ncells, nf = bv.geom.nfine, s2 = bv.geom.sub * bv.geom.sub;
     const int tid = threadIdx.x;
-    for (int k = tid; k < nc; k += kBinThreads) s_off[k] = pad32(bv.hist[(size_t)f * nc + k]);
+    for (int k = tid; k < nf; k += kBinThreads) s_off[k] = bv.hist[(size_t)f * nf + k];
     if (tid == 0) s_bad = 0;
     __syncthreads();
-    block_exclusive_scan<kBinThreads>(s_off, nc, s_part);
+    int my_total = 0;
+    for (int cc = tid; cc < nc; cc += kBinThreads) {
+        int tot = 0;
+        for (int k = 0; k < s2; ++k) tot += s_off[cc * s2 + k];
+        s_cell[cc] = pad32(tot);
+        my_total += tot;
+        if (blockIdx.x == 0) bv.cellcnt[(size_t)f * nc + cc] = tot;
+    }
+    __syncthreads();
+    const int n_padded = block_exclusive_scan<kBinThreads>(s_cell, nc, s_part);      // s_cell: first point of every cell
+    for (int cc = tid; cc < nc; cc += kBinThreads) {
+        int run = s_cell[cc];
+        for (int k = 0; k < s2; ++k) {
+            const int v = s_off[cc * s2 + k];
+            s_off[cc * s2 + k] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
 
     const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
     const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
@@ -359,15 +368,15 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
     float4* dstb = bv.binned + (size_t)f * bv.frame_stride;
     unsigned* cellz2 = bv.cellz2 + (size_t)f * nc;
     for (int64_t base = (int64_t)blockIdx.x * kBinChunk; base < n; base += (int64_t)gridDim.x * kBinChunk) {
-        for (int k = tid; k < nc; k += kBinThreads) s_loc[k] = 0;
+        for (int k = tid; k < nf; k += kBinThreads) s_loc[k] = 0;
         __syncthreads();
         float px[kBinP], py[kBinP], pz[kBinP], pi[kBinP];
-        int pcell[kBinP], prank[kBinP];
+        int pbin[kBinP], prank[kBinP];
         bool bad = false;
 #pragma unroll
         for (int p = 0; p < kBinP; ++p) {
             const int64_t idx = base + p * kBinThreads + tid;
-            pcell[p] = -1;
+            pbin[p] = -1;
             if (idx < n) {
                 const float4 q = raw[idx];
                 px[p] = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
@@ -375,9 +384,9 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
                 pz[p] = q.z;
                 pi[p] = q.w;
                 raw[idx] = make_float4(px[p], py[p], pz[p], pi[p]);
-                pcell[p] = cell_of(bv.geom, px[p], py[p]);
-                if (pcell[p] >= 0) {
-                    prank[p] = atomicAdd(&s_loc[pcell[p]], 1);
+                pbin[p] = fine_of(bv.geom, px[p], py[p]);
+                if (pbin[p] >= 0) {
+                    prank[p] = atomicAdd(&s_loc[pbin[p]], 1);
                     // the fast sweep carries counts inside its fp64 sums: exact for I in {0} U [2^-3, 256)
                     bad |= !(pi[p] == 0.f || (pi[p] >= 0.125f && pi[p] < 256.f));
                 }
@@ -385,63 +394,68 @@ __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
         }
         if (bad) s_bad = 1;
         __syncthreads();
-        for (int k = tid; k < nc; k += kBinThreads) {
+        for (int k = tid; k < nf; k += kBinThreads) {
             const int cnt = s_loc[k];
-            if (cnt) s_loc[k] = atomicAdd(&bv.cursor[(size_t)f * nc + k], cnt);     // base of this chunk inside the cell
+            if (cnt) s_loc[k] = atomicAdd(&bv.cursor[(size_t)f * nf + k], cnt);     // base of this chunk inside the bin
         }
         __syncthreads();
 #pragma unroll
         for (int p = 0; p < kBinP; ++p) {
-            if (pcell[p] >= 0) {
-                const int dst = s_off[pcell[p]] + s_loc[pcell[p]] + prank[p];
-                const uint32_t mask = neighbour_mask(bv, pcell[p], px[p], py[p], pz[p]);
+            if (pbin[p] >= 0) {
+                const int cell = pbin[p] / s2;
+                const int dst = s_off[pbin[p]] + s_loc[pbin[p]] + prank[p];
+                const uint32_t mask = neighbour_mask(bv, cell, px[p], py[p], pz[p]);
                 dstb[dst] = make_float4(px[p], py[p], pi[p], __uint_as_float(mask));
                 const unsigned z2 = __float_as_uint(__fmul_rn(pz[p], pz[p]));          // >= 0: float order == uint order
-                if (z2 > cellz2[pcell[p]]) atomicMax(&cellz2[pcell[p]], z2);
+                if (z2 > cellz2[cell]) atomicMax(&cellz2[cell], z2);
             }
         }
         __syncthreads();
     }
     if (tid == 0 && s_bad) atomicOr(&c.use_exact, 1);
     if (blockIdx.x == 0) {
-        // sentinels behind every cell's last point, then the work items: a cell with cnt (padded) points becomes
-        // ceil(cnt / kItemMax) balanced warp items, each a multiple of 32 points
-        __syncthreads();
-        int total = 0;
-        for (int k = tid; k < nc; k += kBinThreads) {
-            const int cnt = bv.hist[(size_t)f * nc + k];
-            for (int j = cnt; j < pad32(cnt); ++j) dstb[s_off[k] + j] = make_float4(kSentinelXY, kSentinelXY, 0.f, __uint_as_float(0xffu));
-            s_loc[k] = (pad32(cnt) + kItemMax - 1) / kItemMax;
-            total += cnt;
+        // sentinels behind every cell's last point; the cell table the sweep walks
+        for (int cc = tid; cc < nc; cc += kBinThreads) {
+            const int cnt = bv.cellcnt[(size_t)f * nc + cc];
+            bv.cellstart[(size_t)f * nc + cc] = s_cell[cc];
+            for (int j = cnt; j < pad32(cnt); ++j)
+                dstb[s_cell[cc] + j] = make_float4(kSentinelXY, kSentinelXY, 0.f, __uint_as_float(0xffu));
         }
         __syncthreads();
-        const int n_items = block_exclusive_scan<kBinThreads>(s_loc, nc, s_part);     // s_off survives
-        int4* items = bv.items + (size_t)f * bv.max_items;
-        for (int k = tid; k < nc; k += kBinThreads) {
-            const int cnt = pad32(bv.hist[(size_t)f * nc + k]);
-            if (cnt == 0) continue;
-            const int nch = (cnt + kItemMax - 1) / kItemMax;
-            const int per = pad32((cnt + nch - 1) / nch);
-            int pos = s_loc[k];
-            for (int j = 0; j < nch; ++j) {
-                const int st = j * per;
-                if (st >= cnt) { items[pos++] = make_int4(k, s_off[k], 0, 0); continue; }
-                items[pos++] = make_int4(k, s_off[k] + st, min(per, cnt - st), 0);
-            }
-        }
-        // n_binned: block reduction of the per-thread totals
-        __syncthreads();
-        s_part[tid] = total;
+        s_part[tid] = my_total;
         __syncthreads();
         for (int off = kBinThreads / 2; off > 0; off >>= 1) {
             if (tid < off) s_part[tid] += s_part[tid + off];
             __syncthreads();
         }
-        if (tid == 0) {
-            c.n_items = n_items; c.n_binned = s_part[0];
-            // c.use_exact is still being OR-ed by the other CTAs of this frame: the sweep reads it from ctl
-            snapshot_frame(bv, f);
+        if (tid == 0) { c.n_rows = n_padded / 32; c.n_binned = s_part[0]; }
+    }
+}
+
+// Bounding box of every 32-point row of a freshly binned frame (sentinels excluded; an all-sentinel row gets an
+// empty box that no disc touches).
+constexpr int kBoxThreads = 256;
+__global__ void __launch_bounds__(kBoxThreads) k_rowbox(BatchView bv)
+{
+    const int f = blockIdx.y;
+    const FrameCtl& c = bv.ctl[f];
+    if (!c.rebin) return;
+    const int n_rows = c.n_rows;
+    const int lane = threadIdx.x & 31;
+    const float4* src = bv.binned + (size_t)f * bv.frame_stride;
+    float4* box = bv.rowbox + (size_t)f * (bv.frame_stride / 32);
+    for (int r = blockIdx.x * (kBoxThreads / 32) + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * (kBoxThreads / 32)) {
+        const float4 q = __ldg(src + (size_t)r * 32 + lane);
+        const bool real = q.x != kSentinelXY;
+        float x0 = real ? q.x : 3.0e38f, y0 = real ? q.y : 3.0e38f, x1 = real ? q.x : -3.0e38f, y1 = real ? q.y : -3.0e38f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+            y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+            x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
         }
+        if (lane == 0) box[r] = make_float4(x0, y0, x1, y1);
     }
 }
 
@@ -820,36 +834,35 @@ __device__ __noinline__ void lm_frame_step(const BatchView& bv, int f, LmStage* 
         for (int k = lane; k < (int)(sizeof(FrameCtl) / 4); k += 32) gc[k] = sc[k];
     }
     if (s_ctl.rebin) {
-        const int nc = g.ncells;
-        for (int k = lane; k < nc; k += 32) {
-            bv.hist[(size_t)f * nc + k] = 0; bv.cursor[(size_t)f * nc + k] = 0; bv.cellz2[(size_t)f * nc + k] = 0u;
-        }
+        const int nc = g.ncells, nf = g.nfine;
+        for (int k = lane; k < nf; k += 32) { bv.hist[(size_t)f * nf + k] = 0; bv.cursor[(size_t)f * nf + k] = 0; }
+        for (int k = lane; k < nc; k += 32) bv.cellz2[(size_t)f * nc + k] = 0u;
     }
     __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_sweep: the hot loop. One WARP = one item (<= kItemMax points of one lattice cell, a multiple of 32);
-// blockIdx.y = frame, 4 independent warps per CTA.
+// k_sweep: the hot loop, a GATHER. One WARP = one target of one frame (blockIdx.y) — or one of `parts` interleaved
+// shares of it.
 //
-//  * staging: lane 0 pulls the item through a private ring of kStages x 4 KB shared-memory tiles with
-//    cp.async.bulk (TMA bulk copy) completing on an mbarrier; the other lanes only wait on the barrier phase;
-//  * pose-aware culling: a candidate target is live only if its gradient disc, pulled back through the trial
-//    pose, can touch the cell rectangle (2 of the 8 candidates for small poses, up to 4 for cm-sized ones);
-//  * the live candidates (<= 4 per pass) sit in the INNER loop with their six nested totals (in-disc, &down,
-//    &right, cost, cost&down, cost&right) in registers for the whole item: per point and candidate 2 compares +
-//    4 compare-and-ands + 6 predicated fp64 adds. Each addend is I + 2^17, so the COUNT rides in the high bits
-//    of the same exact sum (valid for I in {0} U [2^-3, 256) — k_scatter checks; other frames take the
-//    all-fp64 body);
-//  * exactness: predicates are evaluated in fp32; every lane tracks, per candidate, the minimum distance of its
-//    points to any decision boundary (two circles in d^2, two lines in dx, dy). Only if that minimum is inside
-//    the rigorous fp32 error bound (about 1e-7 m; a handful of lanes per sweep) the lane re-reads its points
-//    and corrects the sums of the points whose exact (reference, fp64, no FMA) class differs — so the
-//    accumulator tables equal the oracle's bit for bit;
-//  * the last CTA of a frame to finish runs the LM step (lm_frame_step) — no separate launch.
+//  * the target's discs, pulled back through the trial pose, have centre c = R^T ref - t in the frame the points are
+//    stored in; the warp walks the (at most 3 x 3) cells the gradient disc can touch, tests the bounding boxes of
+//    their 32-point rows 32 at a time (one box per lane) and collects the rows that can touch the disc;
+//  * the collected rows are streamed with one coalesced float4 load per lane and row (512 B per warp instruction,
+//    two rows in flight per warp, ~24 warps per SM);
+//  * per point: e = p - c, d^2 = |e|^2, and the rotated offsets -(R e) whose signs give the down / right classes —
+//    identical, in exact arithmetic, to the reference's p' = R (p + t), ref - p' (board_fitting_cost.h:132-140);
+//    two compares, two selects and four sign-xors build multipliers +-1 / +-0 for six DFMAs that accumulate the six
+//    nested totals as signed sums (accumulate6). Each addend is I + 2^17, so the COUNT rides in the high bits of the
+//    same exact sum (valid for I in {0} U [2^-3, 256) — k_scatter checks; other frames take the all-fp64 body);
+//  * exactness: predicates are evaluated in fp32; every lane tracks the minimum distance of its points to any
+//    decision boundary (two circles in d^2, two lines). Only when a row brings that minimum inside the rigorous fp32
+//    error bound (about 1e-7 m; ~1 % of the rows) the lanes concerned re-evaluate that point exactly like the
+//    reference (fp64, no FMA) and correct the sums — so the accumulator tables equal the oracle's bit for bit;
+//  * the target's 16 accumulators are written once per warp; the last warp of a frame runs the LM step.
 // ------------------------------------------------------------------------------------------------
-constexpr double kCntUnit = 131072.0;           // 2^17 > 512 points per lane x 256
-static_assert(kItemMax / 32 <= 512 && kItemMax % kTile == 0 && kTile % 32 == 0, "count unit / tiling");
+constexpr double kCntUnit = 131072.0;           // 2^17 > 448 rows per lane x 256
+static_assert(kFlushRows * 256.0 <= kCntUnit, "per-lane intensity sum must stay below the count unit");
 
 struct ExactClass { bool in, cost, down, right; };
 
@@ -895,12 +908,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ float4 lds_f4(uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile("{\n\t"
@@ -912,28 +919,46 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                  "DONE_%=:\n\t"
                  "}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
-struct SweepConst {            // per-warp constants of one item
-    float r00, r01, r10, r11, tx, ty;     // fp32 pose
-    float rg2, rc2;                       // fp32 radii^2
-    float E, E2;                          // fp32 error bounds: coordinates, squared distance
+struct SweepConst {            // fp32 constants of one (target, pose)
+    float cx, cy;                         // disc centre in the stored frame
+    float r00, r01, r10, r11;             // rotation
+    float rg2, rc2;                       // radii^2
+    float E, E2;                          // error bounds: rotated offsets, squared distance
 };
 
-// One (point, candidate) update. ptxas turns predicated fp64 adds into add + two selects (12 ALU-pipe selects per
-// pair), so the class is applied as a MULTIPLIER instead: m = +-1.0 / +-0.0 built from two compares, two selects
-// and four sign-xors on the high word (the low word is a constant zero), then six DFMAs:
+// fp32 geometry of one point — the SAME intrinsics in the hot loop and in the correction, so both see identical values.
+// wx, wy = R (p - c) = x' - ref_x, y' - ref_y: the point is right / down of the target when wx / wy > 0.
+__device__ __forceinline__ void point_geom(const SweepConst& k, float qx, float qy, float& wx, float& wy, float& d2)
+{
+    const float ex = __fsub_rn(qx, k.cx), ey = __fsub_rn(qy, k.cy);
+    d2 = __fmaf_rn(ex, ex, __fmul_rn(ey, ey));
+    wx = __fmaf_rn(k.r00, ex, __fmul_rn(k.r01, ey));
+    wy = __fmaf_rn(k.r10, ex, __fmul_rn(k.r11, ey));
+}
+
+// One point update. ptxas turns predicated fp64 adds into add + two selects (12 ALU-pipe selects per point), so the
+// class is applied as a MULTIPLIER instead: m = +-1.0 / +-0.0 built from two compares, two selects and four
+// sign-xors on the high word (the low word is a constant zero), then six DFMAs:
 //   a[0] += [in] v          a[1] += [in] s_y v          a[2] += [in] s_x v        (s = -1 when down / right)
 //   a[3] += [cost] v        a[4] += [cost] s_y v        a[5] += [cost] s_x v
 // All products and sums are exact, so down = (a0 - a1) / 2 etc. are exact too (to_nested_totals).
 template <bool MASKED>
-__device__ __forceinline__ void accumulate6(double (&a)[6], float d2, float dxs, float dys, float rg2, float rc2, double v,
+__device__ __forceinline__ void accumulate6(double (&a)[6], float d2, float wx, float wy, float rg2, float rc2, double v,
                                             uint32_t maskbits, uint32_t bit)
 {
     const uint32_t one = 0x3ff00000u;
     const bool member = !MASKED || (maskbits & bit) != 0u;
     const uint32_t hin = (member && d2 <= rg2) ? one : 0u;
     const uint32_t hc = (member && d2 < rc2) ? one : 0u;
-    const uint32_t sy = __float_as_uint(dys) & 0x80000000u, sx = __float_as_uint(dxs) & 0x80000000u;
+    // s = -1 (sign bit set) when down / right, i.e. when w is positive (sign bit clear)
+    const uint32_t sy = ~__float_as_uint(wy) & 0x80000000u, sx = ~__float_as_uint(wx) & 0x80000000u;
     a[0] = fma(__hiloint2double((int)hin, 0), v, a[0]);
     a[1] = fma(__hiloint2double((int)(hin ^ sy), 0), v, a[1]);
     a[2] = fma(__hiloint2double((int)(hin ^ sx), 0), v, a[2]);
@@ -951,157 +976,37 @@ __device__ __forceinline__ void to_nested_totals(double (&a)[6])
     a[5] = 0.5 * (a[3] - a[5]);
 }
 
-// fp32 geometry of one (point, candidate) pair — the SAME intrinsics in the hot loop and in the fix-up, so both see
-// identical values (no contraction or re-association by the compiler).
-__device__ __forceinline__ void pose_point(const SweepConst& k, float qx, float qy, float& xt, float& yt)
-{
-    const float vx = __fadd_rn(qx, k.tx), vy = __fadd_rn(qy, k.ty);
-    xt = __fmaf_rn(k.r00, vx, __fmul_rn(k.r01, vy));
-    yt = __fmaf_rn(k.r10, vx, __fmul_rn(k.r11, vy));
-}
-__device__ __forceinline__ void pair_geom(float rx, float ry, float xt, float yt, float& dxs, float& dys, float& d2)
-{
-    dxs = __fsub_rn(rx, xt);
-    dys = __fsub_rn(ry, yt);
-    d2 = __fmaf_rn(dxs, dxs, __fmul_rn(dys, dys));
-}
-
-// Rare (about 1e-4 of the (point, candidate) pairs): the point is within the fp32 error bound of a decision boundary
-// of the candidate. Its class is re-evaluated with the reference's own arithmetic (fp64, no FMA) and, if it differs
-// from the fp32 class the hot loop has just used, the signed sums are corrected — every term is exact, so the
-// corrected sums equal what an all-fp64 sweep accumulates.
-// warp reduction of one candidate's six per-lane totals and the atomics into the frame's accumulator table
-__device__ __forceinline__ void flush_candidate(const double (&a)[6], double* __restrict__ acc_t, double* scratch16, int lane)
-{
-    double S[6];
-    int n[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        // a = n * 2^17 + S, 0 <= S < 2^17, everything exact
-        n[j] = (int)(a[j] * (1.0 / kCntUnit));
-        S[j] = fma(-(double)n[j], kCntUnit, a[j]);
-        n[j] = __reduce_add_sync(0xffffffffu, n[j]);
-        S[j] = warp_sum(S[j]);
-    }
-    if (lane == 0)
-        store_totals(scratch16, S[0], S[1], S[2], S[3], S[4], S[5], (double)n[0], (double)n[1], (double)n[2], (double)n[3],
-                     (double)n[4], (double)n[5]);
-    __syncwarp();
-    if (lane < 16) {
-        const double v = scratch16[lane];
-        if (v != 0.0) atomicAdd(acc_t + lane, v);
-    }
-    __syncwarp();
-}
-
-// ---- per-warp stream of 4 KB tiles through shared memory ----
-// The tiles of the warp's items (and of the repeated passes of an item with more than 4 live candidates) form ONE
-// sequence; lane 0 keeps kStages bulk copies in flight and runs ahead into the next item while the warp still
-// computes on (or flushes) the current one.
-struct ItemMeta {
-    int f;            // frame (accumulator / pose index)
-    int cell;
-    int count;        // points, multiple of 32 (0: nothing to stream)
-    const float4* gsrc;
-};
-
-static_assert((kStages & (kStages - 1)) == 0, "stage index is a mask of the tile counter");
-__device__ __forceinline__ int item_tiles(int count) { return (count + kTile - 1) / kTile; }
-
-// Consumer / producer cursors of the warp's stream (identical in every lane).
-struct StreamState {
-    uint32_t issued;       // tiles handed to the copy engine so far
-    uint32_t consumed;     // tiles the warp has finished reading
-    // producer: (current item: pass, tile), then (next item: tiles of its first pass — its number of passes is not
-    // known before it is set up)
-    int pass_cur, tile_cur, tile_nxt;
-    int npass_cur, count_cur, nt_cur;
-    int count_nxt, nt_nxt;
-    const float4* g_cur;
-    const float4* g_nxt;
-};
-
-struct WarpRing {
-    uint32_t tiles;        // shared address of this warp's kStages tiles
-    uint32_t bars;         // shared address of this warp's kStages mbarriers
-    const float4* gen;     // generic pointer to the tiles
-};
-
-__device__ __forceinline__ void ring_issue(const WarpRing& ring, uint32_t issued, const float4* gsrc, int count, int tile)
-{
-    const uint32_t st = issued & (kStages - 1);
-    const uint32_t bytes = (uint32_t)min(kTile, count - tile * kTile) * 16u;
-    mbar_expect_tx(ring.bars + st * 8, bytes);
-    bulk_g2s(ring.tiles + st * (kTile * 16), gsrc + (size_t)tile * kTile, bytes, ring.bars + st * 8);
-}
-
-// Issue copies until kStages are in flight or there is nothing left that may be issued.
-__device__ __forceinline__ void ring_fill(const WarpRing& ring, StreamState& s, int lane)
-{
-    while (s.issued - s.consumed < (uint32_t)kStages) {
-        if (s.pass_cur < s.npass_cur && s.nt_cur > 0) {
-            if (lane == 0) ring_issue(ring, s.issued, s.g_cur, s.count_cur, s.tile_cur);
-            if (++s.tile_cur == s.nt_cur) { s.tile_cur = 0; ++s.pass_cur; }
-        } else if (s.tile_nxt < s.nt_nxt) {
-            if (lane == 0) ring_issue(ring, s.issued, s.g_nxt, s.count_nxt, s.tile_nxt);
-            ++s.tile_nxt;
-        } else break;
-        ++s.issued;
-    }
-}
-
-// wait for the next tile of the stream; returns its generic address
-__device__ __forceinline__ const float4* ring_acquire(const WarpRing& ring, const StreamState& s)
-{
-    const uint32_t st = s.consumed & (kStages - 1);
-    mbar_wait(ring.bars + st * 8, (s.consumed / kStages) & 1u);
-    return ring.gen + st * kTile;
-}
-__device__ __forceinline__ void ring_release(const WarpRing& ring, StreamState& s, int lane)
-{
-    __syncwarp();
-    ++s.consumed;
-    ring_fill(ring, s, lane);
-}
-
-// Everything about the current item that is warp-uniform lives in the warp's slice of shared memory: the hot loop
-// (sweep_pass, a separate function so that its register allocation is its own) picks up what it needs from here.
+// Everything the cold paths need about the warp's task, in the warp's slice of shared memory.
 struct WarpCtx {
     SweepConst k;
     PoseCoef pc;
-    float rx[kCand], ry[kCand];      // live candidates of the item, in pass order
-    uint32_t bit[kCand];
-    int tk[kCand];
-    StreamState st;
+    double2 ref;
+    double rg2, rc2;
 };
 
 struct Corr6 { double d[6]; };
 
-// Rare (about 1e-4 of the (point, candidate) pairs): the point is within the fp32 error bound of a decision boundary
-// of the candidate. Its class is re-evaluated with the reference's own arithmetic (fp64, no FMA) and, if it differs
-// from the fp32 class the hot loop has just used, the signed sums are corrected — every term is exact, so the
-// corrected sums equal what an all-fp64 sweep accumulates.
-template <bool MASKED>
-__device__ __noinline__ Corr6 correct_point(float4 q, const WarpCtx* wc, int c, const double2* __restrict__ tgt_xy, double rg2, double rc2)
+// Rare (about 1e-4 of the points in reach): the point is within the fp32 error bound of a decision boundary. Its class
+// is re-evaluated with the reference's own arithmetic (fp64, no FMA) and, if it differs from the fp32 class the hot
+// loop has just used, the signed sums are corrected — every term is exact, so the corrected sums equal what an
+// all-fp64 sweep accumulates.
+__device__ __noinline__ Corr6 correct_point(float4 q, const WarpCtx* wc, uint32_t bit /* 0: no neighbour mask */)
 {
     Corr6 a;
 #pragma unroll
     for (int j = 0; j < 6; ++j) a.d[j] = 0.0;
     const SweepConst k = wc->k;
-    float xt, yt, dxs, dys, d2;
-    pose_point(k, q.x, q.y, xt, yt);
-    pair_geom(wc->rx[c], wc->ry[c], xt, yt, dxs, dys, d2);
-    const bool near = fabsf(__fsub_rn(d2, k.rg2)) <= k.E2 || fabsf(__fsub_rn(d2, k.rc2)) <= k.E2 || fabsf(dxs) <= k.E || fabsf(dys) <= k.E;
+    float wx, wy, d2;
+    point_geom(k, q.x, q.y, wx, wy, d2);
+    const bool near = fabsf(__fsub_rn(d2, k.rg2)) <= k.E2 || fabsf(__fsub_rn(d2, k.rc2)) <= k.E2 || fabsf(wx) <= k.E || fabsf(wy) <= k.E;
     if (!near) return a;
-    const bool member = !MASKED || ((__float_as_uint(q.w) & wc->bit[c]) != 0u);
-    if (!member) return a;
+    if (bit != 0u && (__float_as_uint(q.w) & bit) == 0u) return a;      // not a kd-tree neighbour: contributes nothing either way
     // what accumulate6 added
     const double f_in = d2 <= k.rg2 ? 1.0 : 0.0, f_c = d2 < k.rc2 ? 1.0 : 0.0;
-    const double f_sy = (__float_as_uint(dys) & 0x80000000u) ? -1.0 : 1.0, f_sx = (__float_as_uint(dxs) & 0x80000000u) ? -1.0 : 1.0;
+    const double f_sy = (__float_as_uint(wy) & 0x80000000u) ? 1.0 : -1.0, f_sx = (__float_as_uint(wx) & 0x80000000u) ? 1.0 : -1.0;
     // what the reference adds
-    const double2 ref = tgt_xy[wc->tk[c]];
     const PoseCoef pc = wc->pc;
-    const ExactClass e = classify_exact(q.x, q.y, pc, ref.x, ref.y, rg2, rc2);
+    const ExactClass e = classify_exact(q.x, q.y, pc, wc->ref.x, wc->ref.y, wc->rg2, wc->rc2);
     const double e_in = e.in ? 1.0 : 0.0, e_c = (e.in && e.cost) ? 1.0 : 0.0;
     const double e_sy = e.down ? -1.0 : 1.0, e_sx = e.right ? -1.0 : 1.0;
     const double v = (double)q.z + kCntUnit;
@@ -1114,362 +1019,299 @@ __device__ __noinline__ Corr6 correct_point(float4 q, const WarpCtx* wc, int c, 
     return a;
 }
 
-// One pass over the current item with N live candidates (wc->rx[c0 .. c0+N)). Signed sums (see accumulate6) go to
-// acc_out[N][6] in the caller's local memory; the stream cursors are read from and written back to wc->st.
-template <int N, bool MASKED>
-__device__ __noinline__ void sweep_pass(WarpCtx* wc, int c0, WarpRing ring, const double2* __restrict__ tgt_xy, double rg2d, double rc2d,
-                                        double* __restrict__ acc_out)
+// Splits the count off the per-lane signed sums and reduces both over the warp into the warp's shared totals:
+// tot[0..5] intensity sums, tot[6..11] counts (in, in&down, in&right, cost, cost&down, cost&right).
+__device__ __forceinline__ void reduce_totals(double (&a)[6], double* tot, int lane)
 {
-    const int lane = threadIdx.x & 31;
-    const SweepConst k = wc->k;
-    StreamState s = wc->st;
-    float rx[N], ry[N];
-    uint32_t bit[N];
-    double acc[N][6];
+    to_nested_totals(a);
 #pragma unroll
-    for (int c = 0; c < N; ++c) {
-        rx[c] = wc->rx[c0 + c]; ry[c] = wc->ry[c0 + c]; bit[c] = wc->bit[c0 + c];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) acc[c][j] = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        // a = n * 2^17 + S, 0 <= S < 2^17, everything exact
+        int n = (int)(a[j] * (1.0 / kCntUnit));
+        double S = fma(-(double)n, kCntUnit, a[j]);
+        n = __reduce_add_sync(0xffffffffu, n);
+        S = warp_sum(S);
+        if (lane == 0) { tot[j] += S; tot[6 + j] += (double)n; }
+        a[j] = 0.0;
     }
-    // distance of this lane's points to the nearest decision boundary since the last flagged row: circles (in d^2), lines
-    float mA = 3.0e38f, mB = 3.0e38f;
-    const int ntiles = s.nt_cur, count = s.count_cur;
-    for (int t = 0; t < ntiles; ++t) {
-        const uint32_t stg = s.consumed & (kStages - 1);
-        mbar_wait(ring.bars + stg * 8, (s.consumed / kStages) & 1u);
-        const uint32_t tile = ring.tiles + stg * (kTile * 16) + lane * 16;
-        const int rows = min(kTile, count - t * kTile) >> 5;
-        uint32_t flagged = 0;            // rows of this tile in which some lane came within the error bound of a boundary
-#pragma unroll(N <= 2 ? 2 : 1)
-        for (int r = 0; r < rows; ++r) {
-            const float4 q = lds_f4(tile + r * 512);
-            float xt, yt;
-            pose_point(k, q.x, q.y, xt, yt);
-            const double v = (double)q.z + kCntUnit;
-            const uint32_t mb = MASKED ? __float_as_uint(q.w) : 0u;
-#pragma unroll
-            for (int c = 0; c < N; ++c) {
-                float dxs, dys, d2;
-                pair_geom(rx[c], ry[c], xt, yt, dxs, dys, d2);
-                mA = fminf(mA, fminf(fabsf(__fsub_rn(d2, k.rg2)), fabsf(__fsub_rn(d2, k.rc2))));
-                mB = fminf(mB, fminf(fabsf(dxs), fabsf(dys)));
-                accumulate6<MASKED>(acc[c], d2, dxs, dys, k.rg2, k.rc2, v, mb, bit[c]);
-            }
-            const bool hit = __any_sync(0xffffffffu, mA <= k.E2 || mB <= k.E);      // warp-uniform, no branch in the loop
-            flagged |= hit ? (1u << r) : 0u;
-            mA = hit ? 3.0e38f : mA;
-            mB = hit ? 3.0e38f : mB;
-        }
-        while (flagged) {                // cold: about 1 % of the rows
-            const int r = __ffs(flagged) - 1;
-            flagged &= flagged - 1;
-            const float4 q = lds_f4(tile + r * 512);
-#pragma unroll
-            for (int c = 0; c < N; ++c) {
-                const Corr6 d = correct_point<MASKED>(q, wc, c0 + c, tgt_xy, rg2d, rc2d);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) acc[c][j] += d.d[j];
-            }
-        }
-        ring_release(ring, s, lane);
-    }
-#pragma unroll
-    for (int c = 0; c < N; ++c) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) acc_out[c * 6 + j] = acc[c][j];
-    }
-    __syncwarp();
-    if (lane == 0) wc->st = s;
     __syncwarp();
 }
+
 
 // all-fp64 body (frames whose intensities cannot carry the count, or RCLC_SWEEP_EXACT=1): every predicate exactly as
-// the reference; one candidate at a time, points straight from global memory.
-__device__ __noinline__ void sweep_item_exact(const BatchView& bv, const float4* __restrict__ gsrc, int count, int lane, const PoseCoef& pc,
-                                              int t, int kbit, double* __restrict__ acc_t, double* scratch16)
+// the reference, plain sums and integer counts. list entries as in stream_rows.
+__device__ __noinline__ void stream_rows_exact(const float4* __restrict__ src, const uint32_t* list, int n, const WarpCtx* wc, double* tot)
 {
-    const double2 ref = bv.tgt_xy[t];
-    double tI = 0, dI = 0, rI = 0, cI = 0, cdI = 0, crI = 0;
-    int tN = 0, dN = 0, rN = 0, cN = 0, cdN = 0, crN = 0;
-    for (int idx = lane; idx < count; idx += 32) {
-        const float4 q = __ldg(gsrc + idx);
-        if (!((__float_as_uint(q.w) >> kbit) & 1u)) continue;
+    const int lane = threadIdx.x & 31;
+    const PoseCoef pc = wc->pc;
+    const double2 ref = wc->ref;
+    const double rg2 = wc->rg2, rc2 = wc->rc2;
+    double sI[6] = {0, 0, 0, 0, 0, 0};
+    int sN[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const uint32_t e = list[i];
+        const float4 q = __ldg(src + (size_t)((e & 0x07ffffffu) << 5) + lane);
         if (q.x == kSentinelXY) continue;
-        const ExactClass e = classify_exact(q.x, q.y, pc, ref.x, ref.y, bv.geom.rg2, bv.geom.rc2);
-        if (!e.in) continue;
+        if (((__float_as_uint(q.w) >> (e >> 27)) & 1u) == 0u) continue;
+        const ExactClass c = classify_exact(q.x, q.y, pc, ref.x, ref.y, rg2, rc2);
+        if (!c.in) continue;
         const double I = (double)q.z;
-        tI += I; tN++;
-        if (e.down) { dI += I; dN++; }
-        if (e.right) { rI += I; rN++; }
-        if (e.cost) {
-            cI += I; cN++;
-            if (e.down) { cdI += I; cdN++; }
-            if (e.right) { crI += I; crN++; }
+        sI[0] += I; sN[0]++;
+        if (c.down) { sI[1] += I; sN[1]++; }
+        if (c.right) { sI[2] += I; sN[2]++; }
+        if (c.cost) {
+            sI[3] += I; sN[3]++;
+            if (c.down) { sI[4] += I; sN[4]++; }
+            if (c.right) { sI[5] += I; sN[5]++; }
         }
     }
-    tI = warp_sum(tI); dI = warp_sum(dI); rI = warp_sum(rI); cI = warp_sum(cI); cdI = warp_sum(cdI); crI = warp_sum(crI);
-    tN = warp_sum(tN); dN = warp_sum(dN); rN = warp_sum(rN); cN = warp_sum(cN); cdN = warp_sum(cdN); crN = warp_sum(crN);
-    if (lane == 0) store_totals(scratch16, tI, dI, rI, cI, cdI, crI, tN, dN, rN, cN, cdN, crN);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const double S = warp_sum(sI[j]);
+        const int N = warp_sum(sN[j]);
+        if (lane == 0) { tot[j] += S; tot[6 + j] += (double)N; }
+    }
+    __syncwarp();
+}
+
+// Streams the collected rows through a per-warp shared-memory ring of kRingGroups x kGroupRows rows filled with
+// cp.async (LDGSTS, 16 B per lane = 512 B per warp instruction, L2-only caching): up to 12 rows are in flight per warp
+// without holding registers, and since every lane later reads exactly the 16 bytes it copied itself the ring needs
+// no barrier at all. list entries: row index | (bit index of the target in the row's cell candidate list) << 27; the
+// caller pads the list with copies of its last entry, so the copy window never needs a bounds check.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool MASKED>
+__device__ __forceinline__ void stream_rows(const float4* __restrict__ src, const uint32_t* list, int n, int lane, uint32_t ring,
+                                            const SweepConst& k, const WarpCtx* wc, double (&acc)[6], float& mA, float& mB)
+{
+    const char* lsrc = reinterpret_cast<const char*>(src + lane);
+    const uint32_t lring = ring + lane * 16u;
+    auto one_row = [&](const float4& qq, int i) {
+        const uint32_t bit = MASKED ? (1u << (list[i] >> 27)) : 0u;
+        float wx, wy, d2;
+        point_geom(k, qq.x, qq.y, wx, wy, d2);
+        const double v = (double)qq.z + kCntUnit;
+        mA = fminf(mA, fminf(fabsf(__fsub_rn(d2, k.rg2)), fabsf(__fsub_rn(d2, k.rc2))));
+        mB = fminf(mB, fminf(fabsf(wx), fabsf(wy)));
+        accumulate6<MASKED>(acc, d2, wx, wy, k.rg2, k.rc2, v, __float_as_uint(qq.w), bit);
+    };
+    auto issue_group = [&](int g) {           // rows g*4 .. g*4+3 of the (padded) list -> slot g % kRingGroups
+        const uint32_t slot = lring + (uint32_t)(g % kRingGroups) * (kGroupRows * 512u);
+#pragma unroll
+        for (int h = 0; h < kGroupRows; ++h)
+            cp_async16(slot + h * 512u, lsrc + (uint64_t)(list[g * kGroupRows + h] & 0x07ffffffu) * 512u);
+        cp_async_commit();
+    };
+    const int ngroups = (n + kGroupRows - 1) / kGroupRows;
+#pragma unroll
+    for (int g = 0; g < kRingGroups - 1; ++g) issue_group(g);        // beyond the list: harmless copies of its last row
+    for (int g = 0; g < ngroups; ++g) {
+        issue_group(g + kRingGroups - 1);                             // its slot was read in the previous iteration
+        cp_async_wait<kRingGroups - 1>();                             // group g has landed
+        const uint32_t slot = lring + (uint32_t)(g % kRingGroups) * (kGroupRows * 512u);
+        const int rows = min(kGroupRows, n - g * kGroupRows);
+        if (rows == kGroupRows) {
+#pragma unroll
+            for (int h = 0; h < kGroupRows; ++h) one_row(lds_f4(slot + h * 512u), g * kGroupRows + h);
+        } else {
+            for (int h = 0; h < rows; ++h) one_row(lds_f4(slot + h * 512u), g * kGroupRows + h);
+        }
+        if (__any_sync(0xffffffffu, mA <= k.E2 || mB <= k.E)) {       // cold: a few % of the 4-row groups
+            if (mA <= k.E2 || mB <= k.E) {
+                for (int h = 0; h < rows; ++h) {
+                    const Corr6 d = correct_point(lds_f4(slot + h * 512u), wc, MASKED ? (1u << (list[g * kGroupRows + h] >> 27)) : 0u);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) acc[j] += d.d[j];
+                }
+            }
+            mA = 3.0e38f;
+            mB = 3.0e38f;
+            __syncwarp();
+        }
+    }
+    cp_async_wait<0>();
+}
+
+constexpr int kListPad = kRingGroups * kGroupRows;    // padding for the copy window
+constexpr int kListCap = kRowList + kListPad;
+constexpr size_t kRingBytes = (size_t)kRingGroups * kGroupRows * 512;
+
+// mode: 0 fast, 1 fast with neighbour mask, 2 all-fp64
+__device__ __forceinline__ void drain_list(int mode, const float4* __restrict__ src, uint32_t* list, int& n_list, int lane, uint32_t ring,
+                                           const SweepConst& k, const WarpCtx* wc, double (&acc)[6], float& mA, float& mB, double* tot,
+                                           int& rows_since_split)
+{
+    if (n_list == 0) return;
+    if (lane < kListPad) list[n_list + lane] = list[n_list - 1];      // padding for the copy window
+    __syncwarp();
+    if (mode == 2) stream_rows_exact(src, list, n_list, wc, tot);
+    else if (mode == 1) stream_rows<true>(src, list, n_list, lane, ring, k, wc, acc, mA, mB);
+    else stream_rows<false>(src, list, n_list, lane, ring, k, wc, acc, mA, mB);
+    rows_since_split += n_list;
+    n_list = 0;
+    if (mode != 2 && rows_since_split > kFlushRows - kRowList) {      // keep the riding count exact
+        reduce_totals(acc, tot, lane);
+        rows_since_split = 0;
+    }
+    __syncwarp();
+}
+
+constexpr size_t kSweepSmem = (size_t)kSweepWarps * (kRingBytes + kListCap * 4 + 16 * 8 + 12 * 8 + sizeof(WarpCtx) + sizeof(LmStage));
+static_assert(kListPad <= 32, "one lane per padding entry");
+
+__global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
+{
+    const int f = blockIdx.y;
+    const FrameCtl& c = bv.ctl[f];
+    if (!c.sweep_active) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int parts = bv.parts;
+    const int task = blockIdx.x * kSweepWarps + warp;
+    const int t = task / parts, part = task - t * parts;
+    if (t >= bv.geom.nt) return;
+    const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;      // frame whose points are read
+
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    unsigned char* sp = s_dyn;
+    const uint32_t ring = smem_addr(sp + warp * kRingBytes);                     sp += kSweepWarps * kRingBytes;
+    uint32_t* list = reinterpret_cast<uint32_t*>(sp) + warp * kListCap;           sp += kSweepWarps * kListCap * 4;
+    double* scratch16 = reinterpret_cast<double*>(sp) + warp * 16;                sp += kSweepWarps * 16 * 8;
+    double* tot = reinterpret_cast<double*>(sp) + warp * 12;                      sp += kSweepWarps * 12 * 8;
+    WarpCtx* wc = reinterpret_cast<WarpCtx*>(sp) + warp;                          sp += kSweepWarps * sizeof(WarpCtx);
+    LmStage* stage = reinterpret_cast<LmStage*>(sp) + warp;
+
+    const GridGeom& g = bv.geom;
+    const PoseCoef pc = c.pose;
+    const double2 ref = bv.tgt_xy[t];
+    const bool exact_body = bv.force_exact || c.use_exact;
+    // p' = R (p + t)  =>  ref - p' = -R (p - c),  c = R^T ref - t
+    const double cxd = pc.r00 * ref.x + pc.r10 * ref.y - pc.tx, cyd = pc.r01 * ref.x + pc.r11 * ref.y - pc.ty;
+    const double rgd = sqrt(g.rg2);
+    SweepConst k;
+    k.cx = (float)cxd; k.cy = (float)cyd;
+    k.r00 = (float)pc.r00; k.r01 = (float)pc.r01; k.r10 = (float)pc.r10; k.r11 = (float)pc.r11;
+    k.rg2 = (float)g.rg2; k.rc2 = (float)g.rc2;
+    {
+        // |fp32 offsets - reference's| <= E for every point that can matter (|p - c| <= 2 rg): rounding of c, of p - c, of the
+        // 2x2 product, plus the reference's own rounding of R (p + t) at coordinate magnitude Bc
+        const double Bc = fabs(cxd) + fabs(cyd) + fabs(pc.tx) + fabs(pc.ty) + fabs(ref.x) + fabs(ref.y) + 0.2;
+        k.E = (float)(6.0 * 5.9604644775390625e-8 * Bc + 1e-9);
+        k.E2 = 1.05f * (2.9f * (float)rgd * k.E + 3e-7f * k.rg2 + 2.f * k.E * k.E + 1e-9f);
+    }
+    if (lane == 0) { wc->k = k; wc->pc = pc; wc->ref = ref; wc->rg2 = g.rg2; wc->rc2 = g.rc2; }
+    if (lane < 12) tot[lane] = 0.0;
+    __syncwarp();
+
+    // kd-tree neighbour mask (3-D distance < neighbour_radius at pose 0, board_fitting_cost.h:273): it can exclude a point
+    // that the pose moves into the gradient disc only if (rg + displacement)^2 + z^2 >= rn^2
+    const float rgf = (float)rgd, reach = rgf + 1e-5f;
+    const float pmax = (float)(sqrt(cxd * cxd + cyd * cyd) + 2.0 * rgd);
+    const float disp = sqrtf(fmaxf(0.f, 2.f - 2.f * k.r00)) * pmax + (float)(fabs(pc.tx) + fabs(pc.ty)) + 1e-5f;
+
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    float mA = 3.0e38f, mB = 3.0e38f;
+    int n_list = 0, rows_since_split = 0;
+    const float4* src = bv.binned + (size_t)fd * bv.frame_stride;
+    const float4* box = bv.rowbox + (size_t)fd * (bv.frame_stride / 32);
+
+    // ---- cells the gradient disc can touch (at most 3 x 3): lane c looks up cell c ----
+    const int ci0 = max((int)floor((cxd - rgd - 1e-5) * g.inv_g) - g.i0, 0), ci1 = min((int)floor((cxd + rgd + 1e-5) * g.inv_g) - g.i0, g.ncx - 1);
+    const int cj0 = max((int)floor((cyd - rgd - 1e-5) * g.inv_g) - g.j0, 0), cj1 = min((int)floor((cyd + rgd + 1e-5) * g.inv_g) - g.j0, g.ncy - 1);
+    const int nci = max(ci1 - ci0 + 1, 0), ncj = max(cj1 - cj0 + 1, 0);
+    int my_row0 = 0, my_nrows = 0, my_ngr = 0;
+    uint32_t my_tag = 0;
+    float z2max = 0.f;
+    if (lane < nci * ncj) {                        // nci, ncj <= 3
+        const int cell = (cj0 + lane / nci) * g.ncx + ci0 + lane % nci;
+        const int cnt = bv.cellcnt[(size_t)fd * g.ncells + cell];
+        const int start = bv.cellstart[(size_t)fd * g.ncells + cell];
+        const int4 cw = *reinterpret_cast<const int4*>(bv.cell_cand + (size_t)cell * kCand);      // 8 x int16
+        z2max = __uint_as_float(bv.cellz2[(size_t)fd * g.ncells + cell]);
+        // bit of this target in the cell's candidate list (the neighbour masks are relative to it). A cell whose list does
+        // not hold the target has no kd-tree neighbour of it, and (rg + 2 g > neighbour radius) no point the pose can move
+        // into the disc while the mask is not needed either.
+        const int w[4] = {cw.x, cw.y, cw.z, cw.w};
+        int kbit = -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if ((int)(short)(w[u] & 0xffff) == t) kbit = 2 * u;
+            if ((int)(short)((unsigned)w[u] >> 16) == t) kbit = 2 * u + 1;
+        }
+        if (cnt > 0 && kbit >= 0) {
+            my_row0 = start >> 5;
+            my_nrows = pad32(cnt) >> 5;
+            my_ngr = (my_nrows + 31) >> 5;
+            my_tag = (uint32_t)kbit << 27;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z2max = fmaxf(z2max, __shfl_xor_sync(0xffffffffu, z2max, o));
+    const bool masked = !((rgf + disp) * (rgf + disp) + z2max < g.rn2f * 0.9999f);
+    // running index of 32-row groups over the cells (dealt round-robin to the parts): exclusive prefix over the lanes
+    int my_pre = my_ngr;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, my_pre, o); if (lane >= o) my_pre += u; }
+    const int n_groups = __shfl_sync(0xffffffffu, my_pre, 15);
+    my_pre -= my_ngr;
+
+    const int mode = exact_body ? 2 : (masked ? 1 : 0);
+
+    // ---- this part's 32-row groups, four box loads in flight per lane ----
+    for (int v0 = part; v0 < n_groups; v0 += 4 * parts) {
+        // a batch appends at most 128 rows: make room first, so that nothing of the batch is live across the streaming
+        if (n_list > kRowList - 128) drain_list(mode, src, list, n_list, lane, ring, k, wc, acc, mA, mB, tot, rows_since_split);
+        float4 b[4];
+        int rbase[4];
+        uint32_t tag[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = v0 + u * parts;
+            const unsigned own = __ballot_sync(0xffffffffu, v >= my_pre && v < my_pre + my_ngr);      // v >= n_groups: nobody
+            const int o = own ? __ffs(own) - 1 : 0;
+            const int row0 = __shfl_sync(0xffffffffu, my_row0, o), nrows = __shfl_sync(0xffffffffu, my_nrows, o);
+            const int j = v - __shfl_sync(0xffffffffu, my_pre, o);
+            tag[u] = __shfl_sync(0xffffffffu, my_tag, o);
+            rbase[u] = row0 + j * 32;
+            b[u] = (own && j * 32 + lane < nrows) ? __ldg(box + rbase[u] + lane) : make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float ex = fmaxf(fmaxf(b[u].x - k.cx, k.cx - b[u].z), 0.f), ey = fmaxf(fmaxf(b[u].y - k.cy, k.cy - b[u].w), 0.f);
+            const bool live = ex * ex + ey * ey <= reach * reach;          // an empty box (+big, -big) is never live
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            const int nl = __popc(m);
+            if (live) list[n_list + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(rbase[u] + lane) | tag[u];
+            n_list += nl;
+        }
+    }
+    drain_list(mode, src, list, n_list, lane, ring, k, wc, acc, mA, mB, tot, rows_since_split);
+
+    // ---- the target's 16 accumulators ----
+    if (mode != 2 && rows_since_split > 0) reduce_totals(acc, tot, lane);
+    if (lane == 0) store_totals(scratch16, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], tot[6], tot[7], tot[8], tot[9], tot[10], tot[11]);
     __syncwarp();
     if (lane < 16) {
+        double* dst = bv.acc + ((size_t)f * g.nt + t) * 16 + lane;
         const double v = scratch16[lane];
-        if (v != 0.0) atomicAdd(acc_t + lane, v);
+        if (parts > 1) { if (v != 0.0) atomicAdd(dst, v); }
+        else *dst = v;
     }
-    __syncwarp();
-}
-
-constexpr size_t kSweepSmemTiles = (size_t)kSweepWarps * kStages * kTile * 16;
-constexpr size_t kSweepSmem = kSweepSmemTiles + (size_t)kSweepWarps * kStages * 8 + (size_t)kSweepWarps * 16 * 8 +
-                              (size_t)kSweepWarps * sizeof(LmStage) + (size_t)kSweepWarps * sizeof(WarpCtx) +
-                              (size_t)(kMaxBatchFrames + 1) * 4;
-
-static_assert(kSweepSmem + 1024 <= 233472 / 4, "four CTAs per SM must fit in 228 KB of shared memory");
-
-// Work enumeration: global item index g -> (frame, item). Frames that are active but have no item (every point
-// outside the lattice) still get one empty item so that their LM step runs.
-struct WorkMap {
-    const int* pref;       // shared: exclusive prefix of items per frame, [n_frames + 1]
-    int n_frames;
-    int uniform;           // > 0: every frame has this many items
-    int total;
-    int f_hint;
-};
-
-__device__ __forceinline__ bool work_lookup(WorkMap& wm, int g, int& f, int& item)
-{
-    if (g >= wm.total) return false;
-    if (wm.uniform > 0) { f = g / wm.uniform; item = g - f * wm.uniform; return true; }
-    int ff = wm.f_hint;
-    while (g >= wm.pref[ff + 1]) ++ff;         // g grows monotonically per warp
-    wm.f_hint = ff;
-    f = ff;
-    item = g - wm.pref[ff];
-    return true;
-}
-
-__device__ __forceinline__ void load_item(const BatchView& bv, int f, int item, ItemMeta& m)
-{
-    const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;
-    const int n_items = bv.uniform_items > 0 ? bv.uniform_items : bv.snap[f].n_items;
-    m.f = f;
-    if (item < n_items) {
-        const int4 it = __ldg(bv.items + (size_t)fd * bv.max_items + item);
-        m.cell = it.x;
-        m.count = it.z;
-        m.gsrc = bv.binned + (size_t)fd * bv.frame_stride + it.y;
-    } else {
-        m.cell = 0; m.count = 0; m.gsrc = bv.binned;
-    }
-}
-
-__global__ void __launch_bounds__(kSweepThreads, 4) k_sweep(BatchView bv)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    extern __shared__ __align__(128) unsigned char s_dyn[];
-    float4* s_tiles = reinterpret_cast<float4*>(s_dyn);
-    uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_dyn + kSweepSmemTiles);
-    double* s_scratch = reinterpret_cast<double*>(s_bars + kSweepWarps * kStages);
-    LmStage* s_stage = reinterpret_cast<LmStage*>(s_scratch + kSweepWarps * 16);
-    WarpCtx* s_wctx = reinterpret_cast<WarpCtx*>(s_stage + kSweepWarps);
-    int* s_pref = reinterpret_cast<int*>(s_wctx + kSweepWarps);
-
-    // ---- items per frame -> prefix (every CTA builds the same table from the pre-launch snapshot) ----
-    WorkMap wm;
-    wm.pref = s_pref;
-    wm.n_frames = bv.n_frames;
-    wm.uniform = bv.uniform_items;
-    wm.f_hint = 0;
-    if (wm.uniform > 0) {
-        wm.total = wm.uniform * bv.n_frames;
-    } else {
-        const int F = bv.n_frames;
-        for (int f = tid; f < F; f += kSweepThreads) {
-            const SweepSnap& sn = bv.snap[f];
-            s_pref[f + 1] = sn.sweep_active ? max(sn.n_items, 1) : 0;
-        }
-        if (tid == 0) s_pref[0] = 0;
-        __syncthreads();
-        if (warp == 0) {                      // inclusive scan of s_pref[1..F] by one warp, 32 frames at a time
-            int carry = 0;
-            for (int base = 1; base <= F; base += 32) {
-                const int idx = base + lane;
-                int v = idx <= F ? s_pref[idx] : 0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-                if (idx <= F) s_pref[idx] = v + carry;
-                carry += __shfl_sync(0xffffffffu, v, 31);
-            }
-        }
-        __syncthreads();
-        wm.total = s_pref[F];
-    }
-    const int stride = gridDim.x * kSweepWarps;
-    int g = blockIdx.x * kSweepWarps + warp;
-    if (g >= wm.total) return;
-
-    WarpRing ring;
-    ring.tiles = smem_addr(s_tiles + (size_t)warp * kStages * kTile);
-    ring.bars = smem_addr(s_bars + warp * kStages);
-    ring.gen = s_tiles + (size_t)warp * kStages * kTile;
-    if (lane == 0) {
-        for (int st = 0; st < kStages; ++st) mbar_init(ring.bars + st * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    double* scratch16 = s_scratch + warp * 16;
-    WarpCtx* wc = s_wctx + warp;
-    const double rg2 = bv.geom.rg2, rc2 = bv.geom.rc2;
-    const float rn2 = bv.geom.rn2f;
-    const float rgf = sqrtf((float)rg2);
-
-    ItemMeta cur, nxt;
-    {
-        int f, item;
-        work_lookup(wm, g, f, item);
-        load_item(bv, f, item, cur);
-    }
-    nxt = cur;
-    StreamState st;
-    st.issued = 0; st.consumed = 0;
-    st.pass_cur = 0; st.tile_cur = 0; st.tile_nxt = 0;
-    st.npass_cur = 1; st.count_cur = cur.count; st.nt_cur = item_tiles(cur.count); st.g_cur = cur.gsrc;
-    st.count_nxt = 0; st.nt_nxt = 0; st.g_nxt = cur.gsrc;
-    ring_fill(ring, st, lane);          // first tiles of the first item are in flight from here on
-
-    for (;;) {
-        // ---- next item's metadata: the load is in flight while this item is set up and swept ----
-        bool have_nxt;
-        {
-            int f, item;
-            have_nxt = work_lookup(wm, g + stride, f, item);
-            if (have_nxt) load_item(bv, f, item, nxt);
-            st.count_nxt = have_nxt ? nxt.count : 0;
-            st.nt_nxt = item_tiles(st.count_nxt);
-            st.g_nxt = nxt.gsrc;
-        }
-        const int f = cur.f;
-        const SweepSnap& sn = bv.snap[f];
-        // (k_scatter may still have been OR-ing ctl.use_exact when it took the snapshot; the multi-start snapshot is final)
-        const bool exact_body = bv.force_exact || (bv.uniform_items > 0 ? sn.use_exact : bv.ctl[f].use_exact);
-        const PoseCoef pc = sn.pose;
-
-        // ---- live candidates of this cell under this pose (lane k < 8 examines candidate k) ----
-        int t = -1;
-        float rxf = 0.f, ryf = 0.f;
-        bool live = false;
-        // cell rectangle in the (un-posed) frame the points are stored in, with a safety margin
-        const int ca = cur.cell % bv.geom.ncx, cb = cur.cell / bv.geom.ncx;
-        const double x0 = (bv.geom.i0 + ca) * bv.geom.g - 1e-6, x1 = (bv.geom.i0 + ca + 1) * bv.geom.g + 1e-6;
-        const double y0 = (bv.geom.j0 + cb) * bv.geom.g - 1e-6, y1 = (bv.geom.j0 + cb + 1) * bv.geom.g + 1e-6;
-        if (lane < kCand && cur.count > 0) {
-            const float4 cf = __ldg(bv.cell_cand_f + (size_t)cur.cell * kCand + lane);
-            t = __float_as_int(cf.z);
-            if (t >= 0) {
-                rxf = cf.x; ryf = cf.y;
-                // p' = R (p + t)  =>  |p' - ref| = |p - (R^T ref - t)|
-                const double cx = pc.r00 * (double)rxf + pc.r10 * (double)ryf - pc.tx, cy = pc.r01 * (double)rxf + pc.r11 * (double)ryf - pc.ty;
-                const double ex = fmax(fmax(x0 - cx, cx - x1), 0.0), ey = fmax(fmax(y0 - cy, cy - y1), 0.0);
-                const double reach = sqrt(rg2) + 1e-5;
-                live = exact_body || (ex * ex + ey * ey) <= reach * reach;
-            }
-        }
-        const unsigned livebits = __ballot_sync(0xffffffffu, live);
-        const int nact = __popc(livebits);
-
-        if (exact_body || nact == 0) {
-            // the copy engine already holds this item's first tiles: drain them so the ring stays in step
-            st.npass_cur = 1;
-            for (int tt = 0; tt < st.nt_cur; ++tt) {
-                ring_acquire(ring, st);
-                ring_release(ring, st, lane);
-            }
-            for (int a = 0; a < nact; ++a) {
-                const int kl = __fns(livebits, 0, a + 1);
-                const int tk = __shfl_sync(0xffffffffu, t, kl);
-                sweep_item_exact(bv, cur.gsrc, cur.count, lane, pc, tk, kl, bv.acc + ((size_t)f * bv.geom.nt + tk) * 16, scratch16);
-            }
-        } else {
-            const float pmax = (float)sqrt(fmax(x0 * x0, x1 * x1) + fmax(y0 * y0, y1 * y1));
-            const float r00f = (float)pc.r00, txf = (float)pc.tx, tyf = (float)pc.ty;
-            // Can the kd-tree neighbour mask (3-D distance < neighbour_radius at pose 0, board_fitting_cost.h:273) exclude a
-            // point that the pose moves into a gradient disc? Not while (rg + max displacement)^2 + max z^2 < rn^2.
-            const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;
-            const float z2max = __uint_as_float(bv.cellz2[(size_t)fd * bv.geom.ncells + cur.cell]);
-            const float disp = sqrtf(fmaxf(0.f, 2.f - 2.f * r00f)) * pmax + fabsf(txf) + fabsf(tyf) + 1e-5f;
-            const bool masked = !((rgf + disp) * (rgf + disp) + z2max < rn2 * 0.9999f);
-            st.npass_cur = (nact + kPassCand - 1) / kPassCand;
-            ring_fill(ring, st, lane);
-            __syncwarp();
-            // the live candidates in pass order; lane j < nact publishes the j-th one
-            {
-                const int kl = __fns(livebits, 0, min(lane, nact - 1) + 1) & 31;
-                const int tkj = __shfl_sync(0xffffffffu, t, kl);
-                const float rxj = __shfl_sync(0xffffffffu, rxf, kl), ryj = __shfl_sync(0xffffffffu, ryf, kl);
-                if (lane < kCand) {
-                    wc->tk[lane] = tkj; wc->rx[lane] = rxj; wc->ry[lane] = ryj;
-                    wc->bit[lane] = lane < nact ? (1u << kl) : 0u;      // padding candidates (masked passes only) own no point
-                }
-            }
-            if (lane == 0) {
-                SweepConst k;
-                k.r00 = r00f; k.r01 = (float)pc.r01; k.r10 = (float)pc.r10; k.r11 = (float)pc.r11;
-                k.tx = txf; k.ty = tyf;
-                k.rg2 = (float)rg2; k.rc2 = (float)rc2;
-                const double Bc = fmax(fmax(fabs(x0), fabs(x1)), fmax(fabs(y0), fabs(y1))) + fabs(pc.tx) + fabs(pc.ty) + 0.1;
-                k.E = (float)(12.0 * 5.9604644775390625e-8 * Bc + 1e-9);
-                k.E2 = 1.05f * (2.9f * sqrtf(k.rg2) * k.E + 3e-7f * k.rg2 + 2.f * k.E * k.E + 1e-9f);
-                wc->k = k;
-                wc->pc = pc;
-                wc->st = st;
-            }
-            __syncwarp();
-            for (int a0 = 0; a0 < nact; a0 += kPassCand) {
-                const int n = min(kPassCand, nact - a0);
-                double acc[kPassCand * 6];
-                if (masked) {
-                    if (n <= 2) sweep_pass<2, true>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
-                    else sweep_pass<4, true>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
-                } else {
-                    if (n == 1) sweep_pass<1, false>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
-                    else if (n == 2) sweep_pass<2, false>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
-                    else if (n == 3) sweep_pass<3, false>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
-                    else sweep_pass<4, false>(wc, a0, ring, bv.tgt_xy, rg2, rc2, acc);
-                }
-                for (int j = 0; j < n; ++j) {
-                    double a6[6];
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) a6[q] = acc[j * 6 + q];
-                    to_nested_totals(a6);
-                    flush_candidate(a6, bv.acc + ((size_t)f * bv.geom.nt + wc->tk[a0 + j]) * 16, scratch16, lane);
-                }
-            }
-            st = wc->st;
-        }
-
-        // ---- fused LM step: the warp that finishes the frame's last item owns the complete accumulator table ----
-        if (bv.fuse_lm) {
-            __threadfence();
-            int last = 0;
-            if (lane == 0) last = (atomicAdd(&bv.sweep_done[f], 1) == max(sn.n_items, 1) - 1);
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                __threadfence();
-                if (lane == 0) bv.sweep_done[f] = 0;
-                lm_frame_step(bv, f, s_stage + warp);
-            }
-        }
-
-        if (!have_nxt) break;
-        g += stride;
-        cur = nxt;
-        // the first pass of the new item may already be (partly) issued
-        st.pass_cur = (st.tile_nxt >= st.nt_nxt && st.nt_nxt > 0) ? 1 : 0;
-        st.tile_cur = (st.tile_nxt >= st.nt_nxt) ? 0 : st.tile_nxt;
-        st.tile_nxt = 0;
-        st.npass_cur = 1; st.count_cur = st.count_nxt; st.nt_cur = st.nt_nxt; st.g_cur = st.g_nxt;
-        st.count_nxt = 0; st.nt_nxt = 0;
-    }
+    if (!bv.fuse_lm) return;
+    // ---- fused LM step: the warp that finishes the frame's last task owns the complete accumulator table ----
+    __threadfence();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&bv.sweep_done[f], 1) == g.nt * parts - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    if (lane == 0) bv.sweep_done[f] = 0;
+    lm_frame_step(bv, f, stage);
 }
 
 __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
@@ -1480,7 +1322,6 @@ __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
         bv.ctl[f].pose = poses[f];
         bv.ctl[f].sweep_active = 1;
         bv.ctl[f].rebin = 0;
-        snapshot_frame(bv, f);
     }
 }
 
@@ -1490,19 +1331,14 @@ __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
 // Not in the reference: cost(p) = sum_k 0.5 * rho_Huber(r_k(p)^2) with r_k from
 // BOARD_FITTING_COST::Evaluate, i.e. what ceres::Problem::Evaluate would report at pose p.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, SweepSnap* snap_ms, const PoseCoef* __restrict__ poses, int P, int frame)
+__global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, const PoseCoef* __restrict__ poses, int P, int frame)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    {
-        SweepSnap sn;
-        sn.sweep_active = 1; sn.n_items = bv.ctl[frame].n_items; sn.use_exact = bv.ctl[frame].use_exact; sn.pad_ = 0; sn.pose = poses[p];
-        snap_ms[p] = sn;
-    }
     FrameCtl c;
     c.sweep_active = 1;
     c.rebin = 0;
-    c.n_items = bv.ctl[frame].n_items;
+    c.n_rows = bv.ctl[frame].n_rows;
     c.n_binned = bv.ctl[frame].n_binned;
     c.use_exact = bv.ctl[frame].use_exact;
     c.pad_ = 0;
@@ -1555,22 +1391,37 @@ static int launch_rebin(rclc_batch* b)
     cudaStream_t st = b->ctx->stream;
     k_count<<<bin_grid(b), kBinThreads, 0, st>>>(b->v);
     k_scatter<<<bin_grid(b), kBinThreads, 0, st>>>(b->v);
-    b->ctx->launches += 2;
+    const int64_t rows = b->v.frame_stride / 32;
+    // (grid-stride; launches in which no frame was re-binned must cost next to nothing)
+    k_rowbox<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 96)), (unsigned)b->n_frames), kBoxThreads, 0, st>>>(b->v);
+    b->ctx->launches += 3;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
 }
 
-// persistent grid: 4 CTAs of 4 warps per SM, every warp walks the item list with stride gridDim.x * 4
-static int sweep_grid_x(const rclc_batch* b) { return b->ctx->sm_count * 4; }
+// One warp per (target, part); parts chosen so that a full batch fills the GPU about twice over.
+static int sweep_parts(const rclc_batch* b, int n_frames)
+{
+    const int64_t slots = (int64_t)b->ctx->sm_count * 20;              // resident warps (5 CTAs of 4 warps per SM)
+    const int64_t tasks = (int64_t)n_frames * b->v.geom.nt;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(8, (2 * slots + tasks - 1) / tasks));
+}
+
+static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames)
+{
+    v.parts = sweep_parts(b, n_frames);
+    const int gx = (v.geom.nt * v.parts + kSweepWarps - 1) / kSweepWarps;
+    k_sweep<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, b->ctx->stream>>>(v);
+    b->ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
 
 static int launch_sweep(rclc_batch* b, bool fuse_lm)
 {
     BatchView v = b->v;
     v.fuse_lm = fuse_lm ? 1 : 0;
-    k_sweep<<<sweep_grid_x(b), kSweepThreads, kSweepSmem, b->ctx->stream>>>(v);
-    b->ctx->launches += 1;
-    RCLC_CUDA(cudaGetLastError());
-    return RCLC_OK;
+    return launch_sweep_view(b, v, b->n_frames);
 }
 
 static int launch_init(rclc_batch* b, const double* d_Tbl)
@@ -1604,8 +1455,7 @@ int rclc_generate_targets(const rclc_config* cfg, double* targets_xy, int32_t* i
 int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, int64_t max_pts, rclc_batch** out)
 {
     RCLC_CHECK(ctx && cfg && out, RCLC_ERR_INVALID, "null argument");
-    RCLC_CHECK(n_frames > 0 && n_frames <= kMaxBatchFrames && max_pts > 0 && max_pts < (1ll << 30), RCLC_ERR_INVALID,
-               "bad batch shape (1..512 frames per batch)");
+    RCLC_CHECK(n_frames > 0 && n_frames <= 65535 && max_pts > 0 && max_pts < (1ll << 30), RCLC_ERR_INVALID, "bad batch shape");
     RCLC_CUDA(cudaSetDevice(ctx->device));
     HostGeom hg;
     RCLC_TRY(build_geom(*cfg, hg));
@@ -1624,9 +1474,9 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.force_exact = b->sweep_exact ? 1 : 0;
     // every cell's segment of `binned` is padded to a multiple of 32 points
     v.frame_stride = (int64_t)align256(((size_t)max_pts + 32 * (size_t)hg.g.ncells) * 16) / 16;
-    v.max_items = hg.g.ncells + (int)((max_pts + 32 * (int64_t)hg.g.ncells + kItemMax - 1) / kItemMax);
+    v.parts = 1;
     RCLC_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
-    const size_t F = n_frames, nt = hg.g.nt, ncell = hg.g.ncells;
+    const size_t F = n_frames, nt = hg.g.nt, ncell = hg.g.ncells, nfine = hg.g.nfine;
     auto fail = [&](const char* what) { set_last_error(what); rclc_batch_destroy(b); return RCLC_ERR_CUDA; };
     const size_t big = F * (size_t)v.frame_stride * 16;
     if (cudaMalloc(&b->d_pristine, big) != cudaSuccess) return fail("cudaMalloc pristine");
@@ -1635,11 +1485,11 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     // small arrays in one block
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
-    const size_t o_npts = take(F * 8), o_hist = take(F * ncell * 4), o_cur = take(F * ncell * 4), o_cmask = take(F * ncell * 4);
-    const size_t o_items = take(F * (size_t)v.max_items * 16), o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
+    const size_t o_npts = take(F * 8), o_hist = take(F * nfine * 4), o_cur = take(F * nfine * 4), o_cmask = take(F * ncell * 4);
+    const size_t o_cstart = take(F * ncell * 4), o_ccnt = take(F * ncell * 4), o_box = take(F * (size_t)(v.frame_stride / 32) * 16);
+    const size_t o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
     const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_txy = take(nt * 16), o_txyf = take(nt * 8);
     const size_t o_row = take(nt), o_cand = take(ncell * kCand * 2), o_eval = take(F * nt * 4 * 8);
-    const size_t o_snap = take(F * sizeof(SweepSnap)), o_candf = take(ncell * kCand * 16);
     const size_t o_corn = take(F * (size_t)hg.g.nc * 3 * 8), o_gmm = take(F * 64 * 8 + 4096 * 8 * 8);
     if (cudaMalloc(&b->d_block, off) != cudaSuccess) return fail("cudaMalloc block");
     char* base = static_cast<char*>(b->d_block);
@@ -1649,7 +1499,9 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.hist = reinterpret_cast<int*>(base + o_hist);
     v.cursor = reinterpret_cast<int*>(base + o_cur);
     v.cellz2 = reinterpret_cast<unsigned*>(base + o_cmask);
-    v.items = reinterpret_cast<int4*>(base + o_items);
+    v.cellstart = reinterpret_cast<int*>(base + o_cstart);
+    v.cellcnt = reinterpret_cast<int*>(base + o_ccnt);
+    v.rowbox = reinterpret_cast<float4*>(base + o_box);
     v.acc = reinterpret_cast<double*>(base + o_acc);
     v.ctl = reinterpret_cast<FrameCtl*>(base + o_ctl);
     v.lm = reinterpret_cast<LmState*>(base + o_lm);
@@ -1659,9 +1511,6 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.tgt_xyf = reinterpret_cast<float2*>(base + o_txyf);
     v.tgt_is_row = reinterpret_cast<uint8_t*>(base + o_row);
     v.cell_cand = reinterpret_cast<int16_t*>(base + o_cand);
-    v.cell_cand_f = reinterpret_cast<float4*>(base + o_candf);
-    v.snap = reinterpret_cast<SweepSnap*>(base + o_snap);
-    v.uniform_items = 0;
     v.eval_out = reinterpret_cast<double*>(base + o_eval);
     v.corners = reinterpret_cast<double*>(base + o_corn);
     b->d_gmm = reinterpret_cast<double*>(base + o_gmm);
@@ -1669,15 +1518,6 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     cudaMemcpyAsync(base + o_txyf, hg.tgt_xyf.data(), nt * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(base + o_row, hg.is_row.data(), nt, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(base + o_cand, hg.cell_cand.data(), ncell * kCand * 2, cudaMemcpyHostToDevice, ctx->stream);
-    std::vector<float4> candf(ncell * kCand);
-    for (size_t k = 0; k < candf.size(); ++k) {
-        const int t = hg.cell_cand[k];
-        int tb = t;
-        float tf;
-        std::memcpy(&tf, &tb, 4);
-        candf[k] = t >= 0 ? make_float4(hg.tgt_xyf[t].x, hg.tgt_xyf[t].y, tf, 0.f) : make_float4(0.f, 0.f, tf, 0.f);
-    }
-    cudaMemcpyAsync(base + o_candf, candf.data(), candf.size() * 16, cudaMemcpyHostToDevice, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail("batch setup copies");
     *out = b;
     return RCLC_OK;
@@ -1751,7 +1591,10 @@ int rclc_batch_sweep(rclc_batch* b, const double* poses)
     RCLC_CUDA(cudaMemcpyAsync(ctx->d_tmp2.p, hp, sizeof(PoseCoef) * b->n_frames, cudaMemcpyHostToDevice, ctx->stream));
     k_set_pose<<<b->n_frames, 256, 0, ctx->stream>>>(b->v, ctx->d_tmp2.as<PoseCoef>());
     ctx->launches += 1;
-    return launch_sweep(b, false);
+    RCLC_CUDA(cudaEventRecord(ctx->evk0, ctx->stream));
+    RCLC_TRY(launch_sweep(b, false));
+    RCLC_CUDA(cudaEventRecord(ctx->evk1, ctx->stream));
+    return RCLC_OK;
 }
 
 int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* acc)
@@ -1871,39 +1714,35 @@ int rclc_batch_multistart(rclc_batch* b, int32_t frame, const double* poses, int
     RCLC_CUDA(cudaSetDevice(ctx->device));
     const size_t nt = b->v.geom.nt;
     const size_t o_ctl = (sizeof(PoseCoef) * P + 255) & ~(size_t)255;
-    const size_t o_snap = o_ctl + ((sizeof(FrameCtl) * P + 255) & ~(size_t)255);
-    const size_t o_acc = o_snap + ((sizeof(SweepSnap) * P + 255) & ~(size_t)255);
+    const size_t o_acc = o_ctl + ((sizeof(FrameCtl) * P + 255) & ~(size_t)255);
     const size_t o_cost = o_acc + (size_t)P * nt * 16 * 8;
     RCLC_TRY(ctx->d_tmp.reserve(o_cost + (size_t)P * 8));
-    RCLC_TRY(ctx->h_pin2.reserve(sizeof(PoseCoef) * P + 64));
-    // items of the (binned) frame: the persistent sweep enumerates P x n_items work items
-    int* h_items = reinterpret_cast<int*>(ctx->h_pin2.as<char>() + sizeof(PoseCoef) * P);
-    RCLC_CUDA(cudaMemcpyAsync(h_items, &b->v.ctl[frame].n_items, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_TRY(ctx->h_pin2.reserve(sizeof(PoseCoef) * P));
     RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int n_items = std::max(*h_items, 1);
-    RCLC_CHECK((int64_t)n_items * P < (1ll << 31), RCLC_ERR_UNSUPPORTED, "too many (pose, item) pairs for one multi-start call");
     PoseCoef* hp = ctx->h_pin2.as<PoseCoef>();
     for (int p = 0; p < P; ++p) hp[p] = host_pose_coef(poses + 3 * p);
     char* base = static_cast<char*>(ctx->d_tmp.p);
     PoseCoef* d_poses = reinterpret_cast<PoseCoef*>(base);
     FrameCtl* d_ctl = reinterpret_cast<FrameCtl*>(base + o_ctl);
-    SweepSnap* d_snap = reinterpret_cast<SweepSnap*>(base + o_snap);
     double* d_acc = reinterpret_cast<double*>(base + o_acc);
     double* d_cost = reinterpret_cast<double*>(base + o_cost);
     RCLC_CUDA(cudaMemcpyAsync(d_poses, hp, sizeof(PoseCoef) * P, cudaMemcpyHostToDevice, ctx->stream));
     RCLC_CUDA(cudaMemsetAsync(d_acc, 0, (size_t)P * nt * 16 * 8, ctx->stream));
     BatchView v = b->v;
-    k_ms_setup<<<(P + 127) / 128, 128, 0, ctx->stream>>>(b->v, d_ctl, d_snap, d_poses, P, frame);
-    v.ctl = d_ctl;
-    v.snap = d_snap;
-    v.acc = d_acc;
+    k_ms_setup<<<(P + 127) / 128, 128, 0, ctx->stream>>>(b->v, d_ctl, d_poses, P, frame);
     v.fixed_frame = frame;
     v.fuse_lm = 0;
-    v.n_frames = P;
-    v.uniform_items = n_items;
-    k_sweep<<<sweep_grid_x(b), kSweepThreads, kSweepSmem, ctx->stream>>>(v);
-    k_ms_cost<<<P, kLmThreads, 0, ctx->stream>>>(v, d_cost);
-    ctx->launches += 2;
+    // blockIdx.y is limited to 65535: sweep poses in slabs
+    for (int p0 = 0; p0 < P; p0 += 32768) {
+        const int np = std::min(32768, P - p0);
+        BatchView vs = v;
+        vs.ctl = d_ctl + p0;
+        vs.acc = d_acc + (size_t)p0 * nt * 16;
+        vs.n_frames = np;
+        RCLC_TRY(launch_sweep_view(b, vs, np));
+        k_ms_cost<<<np, kLmThreads, 0, ctx->stream>>>(vs, d_cost + p0);
+        ctx->launches += 1;
+    }
     ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     RCLC_CUDA(cudaMemcpyAsync(cost_out, d_cost, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -3,12 +3,13 @@
 // Design: the reference evaluates 82 cost functors, each looping over its own
 // kd-tree neighbour copy (board_fitting_cost.h:124-210, 3.3*N point visits per sweep, fp64). Here a
 // frame's points are counting-sorted ONCE per outer iteration into the cells of the half-square
-// lattice on which all targets sit; a cell has at most 8 candidate targets, and each point carries an
-// 8-bit mask of exact (FLANN-equivalent) neighbour membership. Every cell's segment is padded to a
-// multiple of 32 points with far-away sentinels, so a warp row never straddles two cells. A sweep then
-// streams 16 B per point: one WARP owns one item (<= kItemMax points of one cell), pulls it through a
-// private TMA bulk-copy ring in shared memory and keeps the sums of its <= 4 live candidate targets in
-// registers — no atomics and no block barrier in the hot loop.
+// lattice on which all targets sit (and, inside a cell, into 4x4 sub-cells, so that 32 consecutive
+// points — a "row" — are spatial neighbours); a cell has at most 8 candidate targets, and each point
+// carries an 8-bit mask of exact (FLANN-equivalent) neighbour membership. Every cell's segment is
+// padded to a multiple of 32 points with far-away sentinels, and every row has a bounding box.
+// A sweep is a GATHER: one warp owns one target of one frame, pulls in exactly the rows whose box
+// touches the target's discs (as moved by the trial pose) with float4 loads, keeps the target's six
+// sums in registers and writes the target's 16 accumulators once — no atomics in the hot loop.
 #pragma once
 #include "common.cuh"
 
@@ -17,13 +18,13 @@ namespace rclc {
 constexpr int kMaxTargets = 1024;
 constexpr int kMaxCells = 4096;
 constexpr int kCand = 8;                 // candidate targets per cell
+constexpr int kMaxCoarse = 1024;         // lattice cells (kMaxCells bounds cells x sub-cells)
 constexpr int kSweepThreads = 128;
 constexpr int kSweepWarps = kSweepThreads / 32;
-constexpr int kItemMax = 2048;           // points per warp item (<= 512 per lane: the count rides in the fp64 sum)
-constexpr int kTile = 256;               // points per TMA bulk copy (4 KB)
-constexpr int kStages = 2;               // ring depth per warp (power of two): one tile computing, one in flight
-constexpr int kPassCand = 4;             // candidates whose sums live in registers during one pass over an item
-constexpr int kMaxBatchFrames = 512;     // per-CTA prefix table of items per frame
+constexpr int kRowList = 256;            // live rows a warp collects before it streams them
+constexpr int kGroupRows = 4;            // rows per TMA group (one mbarrier phase): 4 x 512 B bulk copies
+constexpr int kRingGroups = 4;           // groups per warp ring (8 KB): one computing, up to three in flight
+constexpr int kFlushRows = 448;          // rows a lane may accumulate before the count riding in the fp64 sum must be split off
 constexpr int kBinThreads = 256;
 constexpr int kBinP = 8;
 constexpr int kBinChunk = kBinThreads * kBinP;
@@ -33,6 +34,7 @@ struct GridGeom {
     int nt;                    // number of targets (col targets first, then row targets)
     int nc;                    // number of corners
     int ncx, ncy, ncells;      // lattice cells
+    int sub, nfine;            // sub-cells per axis inside a cell (sort key only); ncells * sub * sub
     int i0, j0;                // site index of cell (0,0)'s lower corner
     double g, inv_g;           // lattice unit = side/2
     double rc2, rg2;           // cost / gradient radius squared (board_fitting_cost.h:58-59)
@@ -56,23 +58,12 @@ enum Phase { PH_EVAL_INIT = 1, PH_EVAL_CAND = 2, PH_DONE = 3 };
 struct FrameCtl {
     int sweep_active;          // sweep kernels process this frame
     int rebin;                 // count/scatter kernels process this frame (move + re-bin)
-    int n_items;               // work items (cell chunks) of the current binning
+    int n_rows;                // 32-point rows of the current binning (cells padded to whole rows)
     int n_binned;              // points that landed in a lattice cell
     int use_exact;             // some intensity is outside {0} U [2^-3, 256): counts cannot ride in the fp64 sums -> all-fp64 body
     int pad_;
     float move[8];             // T_w1_w0 rows 0,1: m00 m01 m02 m03 / m10 m11 m12 m13
     PoseCoef pose;             // pose the next sweep evaluates
-};
-
-// What one k_sweep launch needs to know about a frame. Written BEFORE the launch (k_scatter / k_set_pose /
-// k_ms_setup) and never during it: the fused LM step of a frame that finishes early rewrites FrameCtl while other
-// warps of the same launch are still enumerating work.
-struct SweepSnap {
-    int sweep_active;
-    int n_items;
-    int use_exact;
-    int pad_;
-    PoseCoef pose;
 };
 
 // Ceres TrustRegionMinimizer state + opt_grid_fitting outer-loop state, one per frame.
@@ -101,19 +92,19 @@ struct BatchView {
     GridGeom geom;
     int n_frames;
     int64_t frame_stride;          // float4 elements between frames in raw/binned
-    int max_items;                 // per frame
+    int parts;                     // warps that share one (frame, target): row groups are dealt round-robin
     int fixed_frame;               // >= 0: every blockIdx.y of k_sweep reads this frame's points (multi-start sweep)
     const int64_t* n_pts;          // [F]
     float4* raw;                   // [F][frame_stride]   current pc_iter (x,y,z,I)
     float4* binned;                // [F][frame_stride]   cell-sorted {x, y, I, mask bits}
-    int* hist;                     // [F][ncells]
-    int* cursor;                   // [F][ncells]
+    int* hist;                     // [F][nfine]
+    int* cursor;                   // [F][nfine]
+    int* cellstart;                // [F][ncells] first point of the cell's segment in `binned` (multiple of 32)
+    int* cellcnt;                  // [F][ncells] points of the cell (the segment holds pad32 of it)
+    float4* rowbox;                // [F][frame_stride / 32] {xmin, ymin, xmax, ymax} of every 32-point row
     unsigned* cellz2;              // [F][ncells] float bits of max z^2 over the cell's points (decides whether the neighbour mask can matter)
-    int4* items;                   // [F][max_items]  {cell, start, count (multiple of 32), 0}
     double* acc;                   // [F][nt][16]
     FrameCtl* ctl;                 // [F]
-    SweepSnap* snap;               // [F]   (multi-start: [P])
-    int uniform_items;             // > 0: every "frame" (pose) has this many items (multi-start sweep)
     LmState* lm;                   // [F]
     int* n_done;                   // [1]
     int* sweep_done;               // [F] CTAs of the current sweep that have finished (last one runs the LM step)
@@ -124,7 +115,6 @@ struct BatchView {
     const float2* tgt_xyf;         // [nt] (float)target  (FLANN query point)
     const uint8_t* tgt_is_row;     // [nt]
     const int16_t* cell_cand;      // [ncells][8] target index or -1
-    const float4* cell_cand_f;     // [ncells][8] {(float)target x, (float)target y, target index bits, 0}
     double* eval_out;              // [F][nt][4] residual, j0, j1, j2 (rclc_batch_read_eval)
     double* corners;               // [F][nc][3]
 };

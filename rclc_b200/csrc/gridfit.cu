@@ -156,30 +156,25 @@ static PoseCoef host_pose_coef(const double pose[3])
 // or -1 outside the lattice.
 __device__ __forceinline__ int fine_of(const GridGeom& g, float x, float y)
 {
-    const int fi = (int)floor((double)x * (g.inv_g * g.sub)) - g.i0 * g.sub;
-    const int fj = (int)floor((double)y * (g.inv_g * g.sub)) - g.j0 * g.sub;
+    // (fp32: a point within rounding of a sub-cell border may fall on either side — every use of the cell tolerates that:
+    //  row boxes come from the coordinates themselves, candidate windows have 2 cm of slack)
+    const float sc = (float)(g.inv_g * g.sub);
+    const int fi = __float2int_rd(x * sc) - g.i0 * g.sub;
+    const int fj = __float2int_rd(y * sc) - g.j0 * g.sub;
     if (fi < 0 || fj < 0 || fi >= g.ncx * g.sub || fj >= g.ncy * g.sub) return -1;
     const int ci = fi / g.sub, cj = fj / g.sub;
     return (cj * g.ncx + ci) * (g.sub * g.sub) + (fj - cj * g.sub) * g.sub + (fi - ci * g.sub);
 }
 
-// FLANN L2_Simple<float> over (x,y,z), kept when dist < radius^2 (board_fitting_cost.h:273).
-__device__ __forceinline__ uint32_t neighbour_mask(const BatchView& bv, int cell, float x, float y, float z)
+// Is the stored point a kd-tree neighbour of the target? FLANN L2_Simple<float> over (x,y,z), kept when
+// dist < radius^2 (board_fitting_cost.h:273); tq = (float)target, the query point.
+__device__ __forceinline__ bool is_neighbour(float tqx, float tqy, float rn2f, float x, float y, float z)
 {
-    uint32_t m = 0;
-    const int16_t* cand = bv.cell_cand + (size_t)cell * kCand;
-#pragma unroll
-    for (int k = 0; k < kCand; ++k) {
-        const int t = cand[k];
-        if (t < 0) continue;
-        const float2 q = bv.tgt_xyf[t];
-        const float dx = __fsub_rn(q.x, x), dy = __fsub_rn(q.y, y), dz = __fsub_rn(0.0f, z);
-        float r = __fmul_rn(dx, dx);
-        r = __fadd_rn(r, __fmul_rn(dy, dy));
-        r = __fadd_rn(r, __fmul_rn(dz, dz));
-        if (r < bv.geom.rn2f) m |= (1u << k);
-    }
-    return m;
+    const float dx = __fsub_rn(tqx, x), dy = __fsub_rn(tqy, y), dz = __fsub_rn(0.0f, z);
+    float r = __fmul_rn(dx, dx);
+    r = __fadd_rn(r, __fmul_rn(dy, dy));
+    r = __fadd_rn(r, __fmul_rn(dz, dz));
+    return r < rn2f;
 }
 
 __device__ __forceinline__ void pose_coef_dev(double x, double y, double yaw, PoseCoef& pc)
@@ -229,16 +224,6 @@ __device__ int block_exclusive_scan(int* data, int n, int* s_part /* [T] */)
 // ------------------------------------------------------------------------------------------------
 // k_init: working copy + control/LM state for a fresh solve (or a fresh binning)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_copy_frames(BatchView bv, const float4* __restrict__ pristine)
-{
-    const int f = blockIdx.y;
-    const int64_t n = bv.n_pts[f];
-    const float4* src = pristine + (size_t)f * bv.frame_stride;
-    float4* dst = bv.raw + (size_t)f * bv.frame_stride;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = __ldg(src + i);
-}
-
 __device__ void reset_lm_for_outer(LmState& s, FrameCtl& c)
 {
     s.phase = PH_EVAL_INIT;
@@ -262,7 +247,7 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
         c.n_rows = 0;
         c.n_binned = 0;
         c.use_exact = 0;
-        c.pad_ = 0;
+        c.drift = 0.f;
         bv.sweep_done[f] = 0;
         for (int k = 0; k < 8; ++k) c.move[k] = 0.f;
         c.move[0] = 1.f;
@@ -277,6 +262,7 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
         s.rep.first_initial_cost = 0; s.rep.last_final_cost = 0;
         for (int k = 0; k < 3; ++k) s.rep.se2_first[k] = 0;
         reset_lm_for_outer(s, c);
+        if (bv.n_pts[f] != 0) bv.rebin_list[bv.list_parity * bv.n_frames + atomicAdd(&bv.rebin_cnt[bv.list_parity], 1)] = f;
         if (bv.n_pts[f] == 0) { s.phase = PH_DONE; c.sweep_active = 0; c.rebin = 0; s.status = 2; s.rep.status = 2; atomicAdd(bv.n_done, 1); }
         if (f == 0 && false) *bv.n_done = 0;
     }
@@ -286,167 +272,219 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
 // k_count / k_scatter: move (float) + counting sort by lattice cell. Grid-stride over chunks so that the
 // (frequent) launches in which no frame needs a re-bin cost only a few hundred early-exit CTAs.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBinGridX = 64;
-
-__global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
-{
-    const int f = blockIdx.y;
-    const FrameCtl& c = bv.ctl[f];
-    if (!c.rebin) return;
-    const int64_t n = bv.n_pts[f];
-    if ((int64_t)blockIdx.x * kBinChunk >= n) return;
-    __shared__ int s_hist[kMaxCells];
-    const int nf = bv.geom.nfine;
-    for (int k = threadIdx.x; k < nf; k += kBinThreads) s_hist[k] = 0;
-    __syncthreads();
-    const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
-    const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
-    const float4* src = bv.raw + (size_t)f * bv.frame_stride;
-    for (int64_t base = (int64_t)blockIdx.x * kBinChunk; base < n; base += (int64_t)gridDim.x * kBinChunk) {
-#pragma unroll
-        for (int p = 0; p < kBinP; ++p) {
-            const int64_t idx = base + p * kBinThreads + threadIdx.x;
-            if (idx < n) {
-                const float4 q = __ldg(src + idx);
-                const float x = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
-                const float y = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
-                const int fine = fine_of(bv.geom, x, y);
-                if (fine >= 0) atomicAdd(&s_hist[fine], 1);
-            }
-        }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < nf; k += kBinThreads)
-        if (s_hist[k]) atomicAdd(&bv.hist[(size_t)f * nf + k], s_hist[k]);
-}
+constexpr int kBinGridX = 128;
 
 // A cell's segment of `binned` is padded to a multiple of 32 points with sentinels that are far outside every
 // disc for every pose, so the sweep needs no tail predicate and a 32-point row never mixes two cells.
 __device__ __forceinline__ int pad32(int v) { return (v + 31) & ~31; }
 constexpr float kSentinelXY = 3.0e18f;      // (3e18)^2 * 2 is finite in fp32
 
-__global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
+// warp-aggregated atomicAdd(&counter[bin], 1): lanes with the same bin elect a leader; returns this lane's rank
+__device__ __forceinline__ int bin_rank(int* counter, int bin, bool valid)
 {
-    const int f = blockIdx.y;
-    FrameCtl& c = bv.ctl[f];
-    if (!c.rebin) return;
-    const int64_t n = bv.n_pts[f];
-    if ((int64_t)blockIdx.x * kBinChunk >= n && blockIdx.x != 0) return;
-    __shared__ int s_off[kMaxCells];       // first: fine histogram; then: offset of every (cell, sub-cell) bin in `binned`
-    __shared__ int s_loc[kMaxCells];
-    __shared__ int s_cell[kMaxCoarse];
-    __shared__ int s_part[kBinThreads];
-    __shared__ int s_bad;
-    const int nc = bv.geom.ncells, nf = bv.geom.nfine, s2 = bv.geom.sub * bv.geom.sub;
-    const int tid = threadIdx.x;
-    for (int k = tid; k < nf; k += kBinThreads) s_off[k] = bv.hist[(size_t)f * nf + k];
-    if (tid == 0) s_bad = 0;
-    __syncthreads();
-    int my_total = 0;
-    for (int cc = tid; cc < nc; cc += kBinThreads) {
-        int tot = 0;
-        for (int k = 0; k < s2; ++k) tot += s_off[cc * s2 + k];
-        s_cell[cc] = pad32(tot);
-        my_total += tot;
-        if (blockIdx.x == 0) bv.cellcnt[(size_t)f * nc + cc] = tot;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    int rank = 0;
+    if (valid) {
+        const unsigned peers = __match_any_sync(act, bin);
+        const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(counter + bin, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        rank = base + __popc(peers & ((1u << lane) - 1u));
     }
-    __syncthreads();
-    const int n_padded = block_exclusive_scan<kBinThreads>(s_cell, nc, s_part);      // s_cell: first point of every cell
-    for (int cc = tid; cc < nc; cc += kBinThreads) {
-        int run = s_cell[cc];
-        for (int k = 0; k < s2; ++k) {
-            const int v = s_off[cc * s2 + k];
-            s_off[cc * s2 + k] = run;
-            run += v;
-        }
-    }
-    __syncthreads();
+    return rank;
+}
 
-    const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
-    const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
-    float4* raw = bv.raw + (size_t)f * bv.frame_stride;
-    float4* dstb = bv.binned + (size_t)f * bv.frame_stride;
-    unsigned* cellz2 = bv.cellz2 + (size_t)f * nc;
-    for (int64_t base = (int64_t)blockIdx.x * kBinChunk; base < n; base += (int64_t)gridDim.x * kBinChunk) {
-        for (int k = tid; k < nf; k += kBinThreads) s_loc[k] = 0;
-        __syncthreads();
-        float px[kBinP], py[kBinP], pz[kBinP], pi[kBinP];
-        int pbin[kBinP], prank[kBinP];
-        bool bad = false;
-#pragma unroll
-        for (int p = 0; p < kBinP; ++p) {
-            const int64_t idx = base + p * kBinThreads + tid;
-            pbin[p] = -1;
-            if (idx < n) {
-                const float4 q = raw[idx];
-                px[p] = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.z);
-                py[p] = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.z);
-                pz[p] = q.z;
-                pi[p] = q.w;
-                raw[idx] = make_float4(px[p], py[p], pz[p], pi[p]);
-                pbin[p] = fine_of(bv.geom, px[p], py[p]);
-                if (pbin[p] >= 0) {
-                    prank[p] = atomicAdd(&s_loc[pbin[p]], 1);
-                    // the fast sweep carries counts inside its fp64 sums: exact for I in {0} U [2^-3, 256)
-                    bad |= !(pi[p] == 0.f || (pi[p] >= 0.125f && pi[p] < 256.f));
-                }
-            }
-        }
-        if (bad) s_bad = 1;
-        __syncthreads();
-        for (int k = tid; k < nf; k += kBinThreads) {
-            const int cnt = s_loc[k];
-            if (cnt) s_loc[k] = atomicAdd(&bv.cursor[(size_t)f * nf + k], cnt);     // base of this chunk inside the bin
-        }
-        __syncthreads();
-#pragma unroll
-        for (int p = 0; p < kBinP; ++p) {
-            if (pbin[p] >= 0) {
-                const int cell = pbin[p] / s2;
-                const int dst = s_off[pbin[p]] + s_loc[pbin[p]] + prank[p];
-                const uint32_t mask = neighbour_mask(bv, cell, px[p], py[p], pz[p]);
-                dstb[dst] = make_float4(px[p], py[p], pi[p], __uint_as_float(mask));
-                const unsigned z2 = __float_as_uint(__fmul_rn(pz[p], pz[p]));          // >= 0: float order == uint order
-                if (z2 > cellz2[cell]) atomicMax(&cellz2[cell], z2);
-            }
-        }
-        __syncthreads();
-    }
-    if (tid == 0 && s_bad) atomicOr(&c.use_exact, 1);
-    if (blockIdx.x == 0) {
-        // sentinels behind every cell's last point; the cell table the sweep walks
-        for (int cc = tid; cc < nc; cc += kBinThreads) {
-            const int cnt = bv.cellcnt[(size_t)f * nc + cc];
-            bv.cellstart[(size_t)f * nc + cc] = s_cell[cc];
-            for (int j = cnt; j < pad32(cnt); ++j)
-                dstb[s_cell[cc] + j] = make_float4(kSentinelXY, kSentinelXY, 0.f, __uint_as_float(0xffu));
-        }
-        __syncthreads();
-        s_part[tid] = my_total;
-        __syncthreads();
-        for (int off = kBinThreads / 2; off > 0; off >>= 1) {
-            if (tid < off) s_part[tid] += s_part[tid + off];
-            __syncthreads();
-        }
-        if (tid == 0) { c.n_rows = n_padded / 32; c.n_binned = s_part[0]; }
+__device__ __forceinline__ void k_count_frame(const BatchView& bv, int f);
+__device__ __forceinline__ void k_scatter_frame(const BatchView& bv, int f);
+
+// warp-aggregated atomicAdd(&counter[bin], 1) without a return value
+__device__ __forceinline__ void bin_count(int* counter, int bin, bool valid)
+{
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        const unsigned peers = __match_any_sync(act, bin);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counter + bin, __popc(peers));
     }
 }
 
-// Bounding box of every 32-point row of a freshly binned frame (sentinels excluded; an all-sentinel row gets an
-// empty box that no disc touches).
-constexpr int kBoxThreads = 256;
-__global__ void __launch_bounds__(kBoxThreads) k_rowbox(BatchView bv)
+// Pass 1 of the counting sort: histogram of (cell, sub-cell) bins of the moved points; the last CTA of the frame then
+// turns the histogram into bin offsets (cells padded to whole rows), the cell table and the sentinels.
+__global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
 {
-    const int f = blockIdx.y;
-    const FrameCtl& c = bv.ctl[f];
-    if (!c.rebin) return;
+    // the list the LM steps of this round will fill was consumed by the previous round: empty it
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) bv.rebin_cnt[bv.list_parity ^ 1] = 0;
+    const int n_list = bv.rebin_cnt[bv.list_parity];
+    for (int li = blockIdx.y; li < n_list; li += gridDim.y) k_count_frame(bv, bv.rebin_list[bv.list_parity * bv.n_frames + li]);
+}
+
+__device__ __forceinline__ void k_count_frame(const BatchView& bv, int f)
+{
+    FrameCtl& c = bv.ctl[f];
+    const int64_t n = bv.n_pts[f];
+    const int nf = bv.geom.nfine, nc = bv.geom.ncells, s2 = bv.geom.sub * bv.geom.sub;
+    const int tid = threadIdx.x;
+    int* hist = bv.hist + (size_t)f * nf;
+    {
+        const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
+        const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
+        const float4* src = bv.raw + (size_t)f * bv.frame_stride;
+        // four independent loads in flight per thread; whole warps stay converged for the aggregated atomics
+        const int64_t stride = (int64_t)gridDim.x * kBinThreads, n_up = (n + 31) & ~(int64_t)31;
+        for (int64_t idx0 = (int64_t)blockIdx.x * kBinThreads + tid; idx0 < n_up; idx0 += 4 * stride) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t idx = idx0 + u * stride;
+                q[u] = idx < n ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t idx = idx0 + u * stride;
+                if (idx >= n_up) break;                       // warp-uniform
+                int fine = -1;
+                if (idx < n) {
+                    const float x = affine_row_f(m00, m01, m02, m03, q[u].x, q[u].y, q[u].z);
+                    const float y = affine_row_f(m10, m11, m12, m13, q[u].x, q[u].y, q[u].z);
+                    fine = fine_of(bv.geom, x, y);
+                }
+                bin_count(hist, max(fine, 0), fine >= 0);
+            }
+        }
+    }
+    // ---- last CTA of the frame: offsets ----
+    __shared__ int s_cell[kMaxCoarse];
+    __shared__ int s_part[kBinThreads];
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&bv.bin_done[f], 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) { __syncthreads(); return; }
+    __threadfence();
+    if (tid == 0) bv.bin_done[f] = 0;
+    int my_total = 0;
+    for (int cc = tid; cc < nc; cc += kBinThreads) {
+        int tot = 0;
+        for (int k = 0; k < s2; ++k) tot += __ldcg(hist + cc * s2 + k);
+        s_cell[cc] = pad32(tot);
+        my_total += tot;
+        bv.cellcnt[(size_t)f * nc + cc] = tot;
+    }
+    __syncthreads();
+    const int n_padded = block_exclusive_scan<kBinThreads>(s_cell, nc, s_part);      // s_cell: first point of every cell
+    float4* dstb = bv.binned + (size_t)f * bv.frame_stride;
+    int* cursor = bv.cursor + (size_t)f * nf;                                        // becomes: next free slot of every bin
+    for (int cc = tid; cc < nc; cc += kBinThreads) {
+        int run = s_cell[cc];
+        bv.cellstart[(size_t)f * nc + cc] = run;
+        for (int k = 0; k < s2; ++k) {
+            cursor[cc * s2 + k] = run;
+            run += __ldcg(hist + cc * s2 + k);
+        }
+        for (int j = run; j < s_cell[cc] + pad32(run - s_cell[cc]); ++j)
+            dstb[j] = make_float4(kSentinelXY, kSentinelXY, 0.f, 0.f);
+    }
+    __syncthreads();
+    s_part[tid] = my_total;
+    __syncthreads();
+    for (int off = kBinThreads / 2; off > 0; off >>= 1) {
+        if (tid < off) s_part[tid] += s_part[tid + off];
+        __syncthreads();
+    }
+    if (tid == 0) { c.n_rows = n_padded / 32; c.n_binned = s_part[0]; }
+    __syncthreads();                 // shared arrays are reused by the next frame of this CTA
+}
+
+// Pass 2: move the points for good (pcl::transformPointCloud restated in float), drop each one into the next free slot of
+// its bin (warp-aggregated atomics on the bin cursors) together with its exact kd-tree neighbour mask.
+__global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
+{
+    const int n_list = bv.rebin_cnt[bv.list_parity];
+    for (int li = blockIdx.y; li < n_list; li += gridDim.y) k_scatter_frame(bv, bv.rebin_list[bv.list_parity * bv.n_frames + li]);
+}
+
+__device__ __forceinline__ void k_scatter_frame(const BatchView& bv, int f)
+{
+    FrameCtl& c = bv.ctl[f];
+    const int64_t n = bv.n_pts[f];
+    const int nf = bv.geom.nfine, nc = bv.geom.ncells, s2 = bv.geom.sub * bv.geom.sub;
+    const int tid = threadIdx.x;
+    const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
+    const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
+    const float4* raw = bv.raw + (size_t)f * bv.frame_stride;
+    float4* dstb = bv.binned + (size_t)f * bv.frame_stride;
+    int* cursor = bv.cursor + (size_t)f * nf;
+    unsigned* cellz2 = bv.cellz2 + (size_t)f * nc;
+    bool bad = false;
+    // four points per thread and iteration: the loads, then the (warp-aggregated) cursor atomics, then the stores — three
+    // memory round trips per four points instead of twelve
+    const int64_t stride = (int64_t)gridDim.x * kBinThreads, n_up = (n + 31) & ~(int64_t)31;
+    for (int64_t idx0 = (int64_t)blockIdx.x * kBinThreads + tid; idx0 < n_up; idx0 += 4 * stride) {
+        float4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t idx = idx0 + u * stride;
+            q[u] = idx < n ? __ldg(raw + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        int fine[4], dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t idx = idx0 + u * stride;
+            fine[u] = -1;
+            if (idx < n) {
+                const float x = affine_row_f(m00, m01, m02, m03, q[u].x, q[u].y, q[u].z);
+                const float y = affine_row_f(m10, m11, m12, m13, q[u].x, q[u].y, q[u].z);
+                q[u].x = x; q[u].y = y;
+                fine[u] = fine_of(bv.geom, x, y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            dst[u] = 0;
+            if (idx0 + u * stride < n_up) dst[u] = bin_rank(cursor, max(fine[u], 0), fine[u] >= 0);      // warp-uniform guard
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (fine[u] >= 0) {
+                const int cell = fine[u] / s2;
+                const float in = q[u].w;
+                dstb[dst[u]] = make_float4(q[u].x, q[u].y, in, q[u].z);
+                // the fast sweep carries counts inside its fp64 sums: exact for I in {0} U [2^-3, 256)
+                bad |= !(in == 0.f || (in >= 0.125f && in < 256.f));
+                const unsigned z2 = __float_as_uint(__fmul_rn(q[u].z, q[u].z));          // >= 0: float order == uint order
+                if (z2 > cellz2[cell]) atomicMax(&cellz2[cell], z2);
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) atomicOr(&c.use_exact, 1);
+}
+
+// Bounding box of every 32-point row (sentinels excluded; an all-sentinel row gets an empty box that no disc touches).
+// MOVE = false: right after the initial sort. MOVE = true: the outer loop's pcl::transformPointCloud(pc_iter, T_w1_w0)
+// (opt_grid_fitting.h:105-107, float) applied IN PLACE to the sorted points — a rigid motion of a few millimetres keeps
+// rows spatially compact, so the sort is not repeated; the frame only remembers a bound on the accumulated drift, by
+// which the sweep widens its cell look-up.
+constexpr int kBoxThreads = 256;
+template <bool MOVE>
+__device__ __forceinline__ void rowbox_frame(const BatchView& bv, int f)
+{
+    FrameCtl& c = bv.ctl[f];
     const int n_rows = c.n_rows;
     const int lane = threadIdx.x & 31;
-    const float4* src = bv.binned + (size_t)f * bv.frame_stride;
+    float4* pts = bv.binned + (size_t)f * bv.frame_stride;
     float4* box = bv.rowbox + (size_t)f * (bv.frame_stride / 32);
+    const float m00 = c.move[0], m01 = c.move[1], m02 = c.move[2], m03 = c.move[3];
+    const float m10 = c.move[4], m11 = c.move[5], m12 = c.move[6], m13 = c.move[7];
     for (int r = blockIdx.x * (kBoxThreads / 32) + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * (kBoxThreads / 32)) {
-        const float4 q = __ldg(src + (size_t)r * 32 + lane);
+        float4 q = pts[(size_t)r * 32 + lane];
         const bool real = q.x != kSentinelXY;
+        if (MOVE && real) {
+            const float x = affine_row_f(m00, m01, m02, m03, q.x, q.y, q.w);       // q.w is z; row 2 of an SE(2) leaves it alone
+            const float y = affine_row_f(m10, m11, m12, m13, q.x, q.y, q.w);
+            q.x = x; q.y = y;
+            pts[(size_t)r * 32 + lane] = q;
+        }
         float x0 = real ? q.x : 3.0e38f, y0 = real ? q.y : 3.0e38f, x1 = real ? q.x : -3.0e38f, y1 = real ? q.y : -3.0e38f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -457,6 +495,29 @@ __global__ void __launch_bounds__(kBoxThreads) k_rowbox(BatchView bv)
         }
         if (lane == 0) box[r] = make_float4(x0, y0, x1, y1);
     }
+    if (MOVE && blockIdx.x == 0 && threadIdx.x == 0) {
+        // |p' - p| <= |R - I| |p| + |t| over the lattice the points live in (+ the drift they already have)
+        const GridGeom& g = bv.geom;
+        const float ex = (float)(fmax(fabs(g.i0 * g.g), fabs((g.i0 + g.ncx) * g.g))), ey = (float)(fmax(fabs(g.j0 * g.g), fabs((g.j0 + g.ncy) * g.g)));
+        const float pmax = sqrtf(ex * ex + ey * ey) + c.drift;
+        const float dr = sqrtf((m00 - 1.f) * (m00 - 1.f) + m01 * m01 + m10 * m10 + (m11 - 1.f) * (m11 - 1.f));     // Frobenius >= spectral
+        c.drift += 1.0001f * (dr * pmax + fabsf(m03) + fabsf(m13)) + 1e-7f;
+    }
+}
+
+__global__ void __launch_bounds__(kBoxThreads) k_rowbox(BatchView bv)
+{
+    const int n_list = bv.rebin_cnt[bv.list_parity];
+    for (int li = blockIdx.y; li < n_list; li += gridDim.y) rowbox_frame<false>(bv, bv.rebin_list[bv.list_parity * bv.n_frames + li]);
+}
+
+// One launch per round: frames whose LM step asked for the next outer iteration are moved in place.
+__global__ void __launch_bounds__(kBoxThreads) k_move(BatchView bv)
+{
+    // the list the LM steps of this round will fill was consumed by the previous round: empty it
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) bv.rebin_cnt[bv.list_parity ^ 1] = 0;
+    const int n_list = bv.rebin_cnt[bv.list_parity];
+    for (int li = blockIdx.y; li < n_list; li += gridDim.y) rowbox_frame<true>(bv, bv.rebin_list[bv.list_parity * bv.n_frames + li]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -834,6 +895,7 @@ __device__ __noinline__ void lm_frame_step(const BatchView& bv, int f, LmStage* 
         for (int k = lane; k < (int)(sizeof(FrameCtl) / 4); k += 32) gc[k] = sc[k];
     }
     if (s_ctl.rebin) {
+        if (lane == 0) bv.rebin_list[(bv.list_parity ^ 1) * bv.n_frames + atomicAdd(&bv.rebin_cnt[bv.list_parity ^ 1], 1)] = f;
         const int nc = g.ncells, nf = g.nfine;
         for (int k = lane; k < nf; k += 32) { bv.hist[(size_t)f * nf + k] = 0; bv.cursor[(size_t)f * nf + k] = 0; }
         for (int k = lane; k < nc; k += 32) bv.cellz2[(size_t)f * nc + k] = 0u;
@@ -931,6 +993,7 @@ struct SweepConst {            // fp32 constants of one (target, pose)
     float r00, r01, r10, r11;             // rotation
     float rg2, rc2;                       // radii^2
     float E, E2;                          // error bounds: rotated offsets, squared distance
+    float tqx, tqy, rn2;                  // (float)target and neighbour radius^2: the kd-tree membership test
 };
 
 // fp32 geometry of one point — the SAME intrinsics in the hot loop and in the correction, so both see identical values.
@@ -949,12 +1012,9 @@ __device__ __forceinline__ void point_geom(const SweepConst& k, float qx, float 
 //   a[0] += [in] v          a[1] += [in] s_y v          a[2] += [in] s_x v        (s = -1 when down / right)
 //   a[3] += [cost] v        a[4] += [cost] s_y v        a[5] += [cost] s_x v
 // All products and sums are exact, so down = (a0 - a1) / 2 etc. are exact too (to_nested_totals).
-template <bool MASKED>
-__device__ __forceinline__ void accumulate6(double (&a)[6], float d2, float wx, float wy, float rg2, float rc2, double v,
-                                            uint32_t maskbits, uint32_t bit)
+__device__ __forceinline__ void accumulate6(double (&a)[6], float d2, float wx, float wy, float rg2, float rc2, double v, bool member)
 {
     const uint32_t one = 0x3ff00000u;
-    const bool member = !MASKED || (maskbits & bit) != 0u;
     const uint32_t hin = (member && d2 <= rg2) ? one : 0u;
     const uint32_t hc = (member && d2 < rc2) ? one : 0u;
     // s = -1 (sign bit set) when down / right, i.e. when w is positive (sign bit clear)
@@ -990,7 +1050,7 @@ struct Corr6 { double d[6]; };
 // is re-evaluated with the reference's own arithmetic (fp64, no FMA) and, if it differs from the fp32 class the hot
 // loop has just used, the signed sums are corrected — every term is exact, so the corrected sums equal what an
 // all-fp64 sweep accumulates.
-__device__ __noinline__ Corr6 correct_point(float4 q, const WarpCtx* wc, uint32_t bit /* 0: no neighbour mask */)
+__device__ __noinline__ Corr6 correct_point(float4 q, const WarpCtx* wc, bool masked)
 {
     Corr6 a;
 #pragma unroll
@@ -1000,7 +1060,7 @@ __device__ __noinline__ Corr6 correct_point(float4 q, const WarpCtx* wc, uint32_
     point_geom(k, q.x, q.y, wx, wy, d2);
     const bool near = fabsf(__fsub_rn(d2, k.rg2)) <= k.E2 || fabsf(__fsub_rn(d2, k.rc2)) <= k.E2 || fabsf(wx) <= k.E || fabsf(wy) <= k.E;
     if (!near) return a;
-    if (bit != 0u && (__float_as_uint(q.w) & bit) == 0u) return a;      // not a kd-tree neighbour: contributes nothing either way
+    if (masked && !is_neighbour(k.tqx, k.tqy, k.rn2, q.x, q.y, q.w)) return a;      // not a kd-tree neighbour: contributes nothing either way
     // what accumulate6 added
     const double f_in = d2 <= k.rg2 ? 1.0 : 0.0, f_c = d2 < k.rc2 ? 1.0 : 0.0;
     const double f_sy = (__float_as_uint(wy) & 0x80000000u) ? 1.0 : -1.0, f_sx = (__float_as_uint(wx) & 0x80000000u) ? 1.0 : -1.0;
@@ -1048,11 +1108,11 @@ __device__ __noinline__ void stream_rows_exact(const float4* __restrict__ src, c
     const double rg2 = wc->rg2, rc2 = wc->rc2;
     double sI[6] = {0, 0, 0, 0, 0, 0};
     int sN[6] = {0, 0, 0, 0, 0, 0};
+    const SweepConst k = wc->k;
     for (int i = 0; i < n; ++i) {
-        const uint32_t e = list[i];
-        const float4 q = __ldg(src + (size_t)((e & 0x07ffffffu) << 5) + lane);
+        const float4 q = __ldg(src + (size_t)(list[i] << 5) + lane);
         if (q.x == kSentinelXY) continue;
-        if (((__float_as_uint(q.w) >> (e >> 27)) & 1u) == 0u) continue;
+        if (!is_neighbour(k.tqx, k.tqy, k.rn2, q.x, q.y, q.w)) continue;
         const ExactClass c = classify_exact(q.x, q.y, pc, ref.x, ref.y, rg2, rc2);
         if (!c.in) continue;
         const double I = (double)q.z;
@@ -1092,20 +1152,19 @@ __device__ __forceinline__ void stream_rows(const float4* __restrict__ src, cons
 {
     const char* lsrc = reinterpret_cast<const char*>(src + lane);
     const uint32_t lring = ring + lane * 16u;
-    auto one_row = [&](const float4& qq, int i) {
-        const uint32_t bit = MASKED ? (1u << (list[i] >> 27)) : 0u;
+    auto one_row = [&](const float4& qq) {
         float wx, wy, d2;
         point_geom(k, qq.x, qq.y, wx, wy, d2);
         const double v = (double)qq.z + kCntUnit;
         mA = fminf(mA, fminf(fabsf(__fsub_rn(d2, k.rg2)), fabsf(__fsub_rn(d2, k.rc2))));
         mB = fminf(mB, fminf(fabsf(wx), fabsf(wy)));
-        accumulate6<MASKED>(acc, d2, wx, wy, k.rg2, k.rc2, v, __float_as_uint(qq.w), bit);
+        accumulate6(acc, d2, wx, wy, k.rg2, k.rc2, v, !MASKED || is_neighbour(k.tqx, k.tqy, k.rn2, qq.x, qq.y, qq.w));
     };
     auto issue_group = [&](int g) {           // rows g*4 .. g*4+3 of the (padded) list -> slot g % kRingGroups
         const uint32_t slot = lring + (uint32_t)(g % kRingGroups) * (kGroupRows * 512u);
 #pragma unroll
         for (int h = 0; h < kGroupRows; ++h)
-            cp_async16(slot + h * 512u, lsrc + (uint64_t)(list[g * kGroupRows + h] & 0x07ffffffu) * 512u);
+            cp_async16(slot + h * 512u, lsrc + (uint64_t)list[g * kGroupRows + h] * 512u);
         cp_async_commit();
     };
     const int ngroups = (n + kGroupRows - 1) / kGroupRows;
@@ -1118,14 +1177,14 @@ __device__ __forceinline__ void stream_rows(const float4* __restrict__ src, cons
         const int rows = min(kGroupRows, n - g * kGroupRows);
         if (rows == kGroupRows) {
 #pragma unroll
-            for (int h = 0; h < kGroupRows; ++h) one_row(lds_f4(slot + h * 512u), g * kGroupRows + h);
+            for (int h = 0; h < kGroupRows; ++h) one_row(lds_f4(slot + h * 512u));
         } else {
-            for (int h = 0; h < rows; ++h) one_row(lds_f4(slot + h * 512u), g * kGroupRows + h);
+            for (int h = 0; h < rows; ++h) one_row(lds_f4(slot + h * 512u));
         }
         if (__any_sync(0xffffffffu, mA <= k.E2 || mB <= k.E)) {       // cold: a few % of the 4-row groups
             if (mA <= k.E2 || mB <= k.E) {
                 for (int h = 0; h < rows; ++h) {
-                    const Corr6 d = correct_point(lds_f4(slot + h * 512u), wc, MASKED ? (1u << (list[g * kGroupRows + h] >> 27)) : 0u);
+                    const Corr6 d = correct_point(lds_f4(slot + h * 512u), wc, MASKED);
 #pragma unroll
                     for (int j = 0; j < 6; ++j) acc[j] += d.d[j];
                 }
@@ -1197,6 +1256,7 @@ __global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
     k.cx = (float)cxd; k.cy = (float)cyd;
     k.r00 = (float)pc.r00; k.r01 = (float)pc.r01; k.r10 = (float)pc.r10; k.r11 = (float)pc.r11;
     k.rg2 = (float)g.rg2; k.rc2 = (float)g.rc2;
+    { const float2 tq = bv.tgt_xyf[t]; k.tqx = tq.x; k.tqy = tq.y; k.rn2 = g.rn2f; }
     {
         // |fp32 offsets - reference's| <= E for every point that can matter (|p - c| <= 2 rg): rounding of c, of p - c, of the
         // 2x2 product, plus the reference's own rounding of R (p + t) at coordinate magnitude Bc
@@ -1220,75 +1280,69 @@ __global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
     const float4* src = bv.binned + (size_t)fd * bv.frame_stride;
     const float4* box = bv.rowbox + (size_t)fd * (bv.frame_stride / 32);
 
-    // ---- cells the gradient disc can touch (at most 3 x 3): lane c looks up cell c ----
-    const int ci0 = max((int)floor((cxd - rgd - 1e-5) * g.inv_g) - g.i0, 0), ci1 = min((int)floor((cxd + rgd + 1e-5) * g.inv_g) - g.i0, g.ncx - 1);
-    const int cj0 = max((int)floor((cyd - rgd - 1e-5) * g.inv_g) - g.j0, 0), cj1 = min((int)floor((cyd + rgd + 1e-5) * g.inv_g) - g.j0, g.ncy - 1);
-    const int nci = max(ci1 - ci0 + 1, 0), ncj = max(cj1 - cj0 + 1, 0);
-    int my_row0 = 0, my_nrows = 0, my_ngr = 0;
-    uint32_t my_tag = 0;
+    // ---- cells that can hold a point of the gradient disc: the disc widened by how far points have drifted out of the
+    //      cells they were sorted into (in-place moves). Window of nci x ncj cells, normally 3 x 3. ----
+    const double rsel = rgd + (double)bv.ctl[fd].drift + 1e-5;
+    const int ci0 = max((int)floor((cxd - rsel) * g.inv_g) - g.i0, 0), ci1 = min((int)floor((cxd + rsel) * g.inv_g) - g.i0, g.ncx - 1);
+    const int cj0 = max((int)floor((cyd - rsel) * g.inv_g) - g.j0, 0), cj1 = min((int)floor((cyd + rsel) * g.inv_g) - g.j0, g.ncy - 1);
+    const int nci = min(max(ci1 - ci0 + 1, 0), 32), ncj = max(cj1 - cj0 + 1, 0);      // (a lattice wider than 32 cells under > 0.7 m of drift: not a case)
+    // kd-tree neighbour test needed? (all cells of the window)
     float z2max = 0.f;
-    if (lane < nci * ncj) {                        // nci, ncj <= 3
-        const int cell = (cj0 + lane / nci) * g.ncx + ci0 + lane % nci;
-        const int cnt = bv.cellcnt[(size_t)fd * g.ncells + cell];
-        const int start = bv.cellstart[(size_t)fd * g.ncells + cell];
-        const int4 cw = *reinterpret_cast<const int4*>(bv.cell_cand + (size_t)cell * kCand);      // 8 x int16
-        z2max = __uint_as_float(bv.cellz2[(size_t)fd * g.ncells + cell]);
-        // bit of this target in the cell's candidate list (the neighbour masks are relative to it). A cell whose list does
-        // not hold the target has no kd-tree neighbour of it, and (rg + 2 g > neighbour radius) no point the pose can move
-        // into the disc while the mask is not needed either.
-        const int w[4] = {cw.x, cw.y, cw.z, cw.w};
-        int kbit = -1;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if ((int)(short)(w[u] & 0xffff) == t) kbit = 2 * u;
-            if ((int)(short)((unsigned)w[u] >> 16) == t) kbit = 2 * u + 1;
-        }
-        if (cnt > 0 && kbit >= 0) {
-            my_row0 = start >> 5;
-            my_nrows = pad32(cnt) >> 5;
-            my_ngr = (my_nrows + 31) >> 5;
-            my_tag = (uint32_t)kbit << 27;
-        }
-    }
+    for (int cc = lane; cc < nci * ncj; cc += 32)
+        z2max = fmaxf(z2max, __uint_as_float(bv.cellz2[(size_t)fd * g.ncells + (cj0 + cc / nci) * g.ncx + ci0 + cc % nci]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) z2max = fmaxf(z2max, __shfl_xor_sync(0xffffffffu, z2max, o));
     const bool masked = !((rgf + disp) * (rgf + disp) + z2max < g.rn2f * 0.9999f);
-    // running index of 32-row groups over the cells (dealt round-robin to the parts): exclusive prefix over the lanes
-    int my_pre = my_ngr;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, my_pre, o); if (lane >= o) my_pre += u; }
-    const int n_groups = __shfl_sync(0xffffffffu, my_pre, 15);
-    my_pre -= my_ngr;
-
     const int mode = exact_body ? 2 : (masked ? 1 : 0);
 
-    // ---- this part's 32-row groups, four box loads in flight per lane ----
-    for (int v0 = part; v0 < n_groups; v0 += 4 * parts) {
-        // a batch appends at most 128 rows: make room first, so that nothing of the batch is live across the streaming
-        if (n_list > kRowList - 128) drain_list(mode, src, list, n_list, lane, ring, k, wc, acc, mA, mB, tot, rows_since_split);
-        float4 b[4];
-        int rbase[4];
-        uint32_t tag[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int v = v0 + u * parts;
-            const unsigned own = __ballot_sync(0xffffffffu, v >= my_pre && v < my_pre + my_ngr);      // v >= n_groups: nobody
-            const int o = own ? __ffs(own) - 1 : 0;
-            const int row0 = __shfl_sync(0xffffffffu, my_row0, o), nrows = __shfl_sync(0xffffffffu, my_nrows, o);
-            const int j = v - __shfl_sync(0xffffffffu, my_pre, o);
-            tag[u] = __shfl_sync(0xffffffffu, my_tag, o);
-            rbase[u] = row0 + j * 32;
-            b[u] = (own && j * 32 + lane < nrows) ? __ldg(box + rbase[u] + lane) : make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+    // lane c looks up cell c of (a slab of) the window: at most 32 cells per pass, one pass for windows up to 5 x 5
+    const int rows_per_pass = nci > 0 ? max(32 / nci, 1) : 1;
+    int gbase = 0;                       // running index of 32-row groups over the window: dealt round-robin to the parts
+    for (int cjb = cj0; cjb <= cj1 && nci > 0; cjb += rows_per_pass) {
+        const int ncj_p = min(rows_per_pass, cj1 - cjb + 1);
+        int my_row0 = 0, my_nrows = 0, my_ngr = 0;
+        if (lane < nci * ncj_p) {
+            const int cell = (cjb + lane / nci) * g.ncx + ci0 + lane % nci;
+            const int cnt = bv.cellcnt[(size_t)fd * g.ncells + cell];
+            const int start = bv.cellstart[(size_t)fd * g.ncells + cell];
+            if (cnt > 0) {
+                my_row0 = start >> 5;
+                my_nrows = pad32(cnt) >> 5;
+                my_ngr = (my_nrows + 31) >> 5;
+            }
         }
+        int my_pre = my_ngr;             // exclusive prefix over the lanes
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float ex = fmaxf(fmaxf(b[u].x - k.cx, k.cx - b[u].z), 0.f), ey = fmaxf(fmaxf(b[u].y - k.cy, k.cy - b[u].w), 0.f);
-            const bool live = ex * ex + ey * ey <= reach * reach;          // an empty box (+big, -big) is never live
-            const unsigned m = __ballot_sync(0xffffffffu, live);
-            const int nl = __popc(m);
-            if (live) list[n_list + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(rbase[u] + lane) | tag[u];
-            n_list += nl;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, my_pre, o); if (lane >= o) my_pre += u; }
+        const int n_groups = __shfl_sync(0xffffffffu, my_pre, 31);
+        my_pre -= my_ngr;
+
+        // ---- this part's 32-row groups, four box loads in flight per lane ----
+        for (int v0 = (part - gbase % parts + parts) % parts; v0 < n_groups; v0 += 4 * parts) {
+            // a batch appends at most 128 rows: make room first, so that nothing of the batch is live across the streaming
+            if (n_list > kRowList - 128) drain_list(mode, src, list, n_list, lane, ring, k, wc, acc, mA, mB, tot, rows_since_split);
+            float4 b[4];
+            int rbase[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = v0 + u * parts;
+                const unsigned own = __ballot_sync(0xffffffffu, v >= my_pre && v < my_pre + my_ngr);      // v >= n_groups: nobody
+                const int o = own ? __ffs(own) - 1 : 0;
+                const int row0 = __shfl_sync(0xffffffffu, my_row0, o), nrows = __shfl_sync(0xffffffffu, my_nrows, o);
+                const int j = v - __shfl_sync(0xffffffffu, my_pre, o);
+                rbase[u] = row0 + j * 32;
+                b[u] = (own && j * 32 + lane < nrows) ? __ldg(box + rbase[u] + lane) : make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float ex = fmaxf(fmaxf(b[u].x - k.cx, k.cx - b[u].z), 0.f), ey = fmaxf(fmaxf(b[u].y - k.cy, k.cy - b[u].w), 0.f);
+                const bool live = ex * ex + ey * ey <= reach * reach;          // an empty box (+big, -big) is never live
+                const unsigned m = __ballot_sync(0xffffffffu, live);
+                if (live) list[n_list + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(rbase[u] + lane);
+                n_list += __popc(m);
+            }
         }
+        gbase += n_groups;
     }
     drain_list(mode, src, list, n_list, lane, ring, k, wc, acc, mA, mB, tot, rows_since_split);
 
@@ -1341,7 +1395,7 @@ __global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, const PoseCoef* __res
     c.n_rows = bv.ctl[frame].n_rows;
     c.n_binned = bv.ctl[frame].n_binned;
     c.use_exact = bv.ctl[frame].use_exact;
-    c.pad_ = 0;
+    c.drift = bv.ctl[frame].drift;
     for (int k = 0; k < 8; ++k) c.move[k] = 0.f;
     c.pose = poses[p];
     ctl_ms[p] = c;
@@ -1380,20 +1434,37 @@ __global__ void __launch_bounds__(kLmThreads) k_ms_cost(BatchView bv, double* __
 // ------------------------------------------------------------------------------------------------
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// The binning kernels walk the re-bin list with gridDim.y CTA columns: most rounds have nothing (or one frame) to
+// re-bin and must cost next to nothing, while one frame alone still gets hundreds of CTAs.
+constexpr int kBinGridY = 2;
 static dim3 bin_grid(const rclc_batch* b)
 {
-    const int64_t chunks = (b->max_pts + kBinChunk - 1) / kBinChunk;
-    return dim3((unsigned)std::min<int64_t>(chunks, kBinGridX), (unsigned)b->n_frames);
+    const int64_t ctas = (b->max_pts + kBinThreads * 4 - 1) / (kBinThreads * 4);
+    return dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas, 512)), (unsigned)std::min(kBinGridY, b->n_frames));
 }
 
 static int launch_rebin(rclc_batch* b)
 {
     cudaStream_t st = b->ctx->stream;
+    b->v.list_parity = b->round & 1;
     k_count<<<bin_grid(b), kBinThreads, 0, st>>>(b->v);
     k_scatter<<<bin_grid(b), kBinThreads, 0, st>>>(b->v);
     const int64_t rows = b->v.frame_stride / 32;
-    // (grid-stride; launches in which no frame was re-binned must cost next to nothing)
-    k_rowbox<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 96)), (unsigned)b->n_frames), kBoxThreads, 0, st>>>(b->v);
+    k_rowbox<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 256)), (unsigned)std::min(kBinGridY, b->n_frames)), kBoxThreads, 0, st>>>(b->v);
+    b->round++;              // the sweep that follows keeps this round's parity (its LM steps fill the other list)
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+// rounds after the initial sort: frames that start their next outer iteration are moved in place
+static int launch_move(rclc_batch* b)
+{
+    cudaStream_t st = b->ctx->stream;
+    b->v.list_parity = b->round & 1;
+    const int64_t rows = b->v.frame_stride / 32;
+    k_move<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 444)), (unsigned)std::min(kBinGridY, b->n_frames)), kBoxThreads, 0, st>>>(b->v);
+    b->ctx->launches += 1;
+    b->round++;
     b->ctx->launches += 3;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
@@ -1428,9 +1499,10 @@ static int launch_init(rclc_batch* b, const double* d_Tbl)
 {
     cudaStream_t st = b->ctx->stream;
     RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, sizeof(int), st));
-    k_copy_frames<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((b->max_pts + 1023) / 1024, 4096)), (unsigned)b->n_frames), 256, 0, st>>>(b->v, b->d_pristine);
+    RCLC_CUDA(cudaMemsetAsync(b->v.rebin_cnt, 0, 2 * sizeof(int), st));
+    b->v.list_parity = b->round & 1;
     k_init_state<<<b->n_frames, 256, 0, st>>>(b->v, d_Tbl);
-    b->ctx->launches += 2;
+    b->ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
 }
@@ -1480,7 +1552,7 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     auto fail = [&](const char* what) { set_last_error(what); rclc_batch_destroy(b); return RCLC_ERR_CUDA; };
     const size_t big = F * (size_t)v.frame_stride * 16;
     if (cudaMalloc(&b->d_pristine, big) != cudaSuccess) return fail("cudaMalloc pristine");
-    if (cudaMalloc(&v.raw, big) != cudaSuccess) return fail("cudaMalloc raw");
+    v.raw = b->d_pristine;
     if (cudaMalloc(&v.binned, big) != cudaSuccess) return fail("cudaMalloc binned");
     // small arrays in one block
     size_t off = 0;
@@ -1488,7 +1560,7 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     const size_t o_npts = take(F * 8), o_hist = take(F * nfine * 4), o_cur = take(F * nfine * 4), o_cmask = take(F * ncell * 4);
     const size_t o_cstart = take(F * ncell * 4), o_ccnt = take(F * ncell * 4), o_box = take(F * (size_t)(v.frame_stride / 32) * 16);
     const size_t o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
-    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_txy = take(nt * 16), o_txyf = take(nt * 8);
+    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_bdone = take(F * 4), o_rlist = take(2 * F * 4), o_rcnt = take(256), o_txy = take(nt * 16), o_txyf = take(nt * 8);
     const size_t o_row = take(nt), o_cand = take(ncell * kCand * 2), o_eval = take(F * nt * 4 * 8);
     const size_t o_corn = take(F * (size_t)hg.g.nc * 3 * 8), o_gmm = take(F * 64 * 8 + 4096 * 8 * 8);
     if (cudaMalloc(&b->d_block, off) != cudaSuccess) return fail("cudaMalloc block");
@@ -1507,6 +1579,10 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.lm = reinterpret_cast<LmState*>(base + o_lm);
     v.n_done = reinterpret_cast<int*>(base + o_done);
     v.sweep_done = reinterpret_cast<int*>(base + o_sdone);
+    v.bin_done = reinterpret_cast<int*>(base + o_bdone);
+    v.rebin_list = reinterpret_cast<int*>(base + o_rlist);
+    v.rebin_cnt = reinterpret_cast<int*>(base + o_rcnt);
+    v.list_parity = 0;
     v.tgt_xy = reinterpret_cast<double2*>(base + o_txy);
     v.tgt_xyf = reinterpret_cast<float2*>(base + o_txyf);
     v.tgt_is_row = reinterpret_cast<uint8_t*>(base + o_row);
@@ -1529,7 +1605,6 @@ int rclc_batch_destroy(rclc_batch* b)
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
     if (b->d_pristine) cudaFree(b->d_pristine);
-    if (b->v.raw) cudaFree(b->v.raw);
     if (b->v.binned) cudaFree(b->v.binned);
     if (b->d_block) cudaFree(b->d_block);
     delete b;
@@ -1640,9 +1715,15 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     const int64_t max_rounds = (int64_t)(g.max_iter_time + 2) * (g.max_lm_iters + 3);
     const int rounds_per_check = 24;
     int64_t rounds = 0;
+    // RCLC_PROFILE_ROUNDS=1: CUDA events between the binning launches and the sweep of every round; totals on stderr
+    static const bool prof = [] { const char* e = std::getenv("RCLC_PROFILE_ROUNDS"); return e && e[0] == '1'; }();
+    std::vector<cudaEvent_t> evs;
     for (;;) {
         for (int r = 0; r < rounds_per_check; ++r) {
-            RCLC_TRY(launch_rebin(b));
+            if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e); }
+            if (rounds == 0 && r == 0) RCLC_TRY(launch_rebin(b));      // the one counting sort of the solve
+            else RCLC_TRY(launch_move(b));
+            if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e); }
             RCLC_TRY(launch_sweep(b, true));      // sweep + fused LM step (last CTA per frame)
         }
         rounds += rounds_per_check;
@@ -1651,6 +1732,21 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
         RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (*h_done >= F) break;
         RCLC_CHECK(rounds < max_rounds, RCLC_ERR_NUMERIC, "grid-fit state machine did not terminate");
+    }
+    if (prof && evs.size() >= 4) {
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e);
+        cudaEventSynchronize(e);
+        double t_bin = 0, t_sweep = 0, bin_max = 0; int n_bin_big = 0;
+        for (size_t i = 0; i + 2 < evs.size(); i += 2) {
+            float a = 0, c = 0;
+            cudaEventElapsedTime(&a, evs[i], evs[i + 1]);
+            cudaEventElapsedTime(&c, evs[i + 1], evs[i + 2]);
+            t_bin += a; t_sweep += c; bin_max = std::max<double>(bin_max, a); n_bin_big += a > 0.02f;
+        }
+        float tot = 0; cudaEventElapsedTime(&tot, evs.front(), evs.back());
+        fprintf(stderr, "[rclc profile] rounds %zu  total %.2f ms  binning %.2f ms (%d rounds > 20 us, max %.1f us)  sweep+lm %.2f ms\n",
+                evs.size() / 2, tot, t_bin, n_bin_big, bin_max * 1e3, t_sweep);
+        for (cudaEvent_t x : evs) cudaEventDestroy(x);
     }
     std::vector<LmState> h_lm(F);
     RCLC_CUDA(cudaMemcpyAsync(h_lm.data(), b->v.lm, sizeof(LmState) * F, cudaMemcpyDeviceToHost, ctx->stream));

@@ -61,7 +61,7 @@ struct FrameCtl {
     int n_rows;                // 32-point rows of the current binning (cells padded to whole rows)
     int n_binned;              // points that landed in a lattice cell
     int use_exact;             // some intensity is outside {0} U [2^-3, 256): counts cannot ride in the fp64 sums -> all-fp64 body
-    int pad_;
+    float drift;               // bound on how far any point has moved since the frame was sorted (in-place moves)
     float move[8];             // T_w1_w0 rows 0,1: m00 m01 m02 m03 / m10 m11 m12 m13
     PoseCoef pose;             // pose the next sweep evaluates
 };
@@ -95,8 +95,8 @@ struct BatchView {
     int parts;                     // warps that share one (frame, target): row groups are dealt round-robin
     int fixed_frame;               // >= 0: every blockIdx.y of k_sweep reads this frame's points (multi-start sweep)
     const int64_t* n_pts;          // [F]
-    float4* raw;                   // [F][frame_stride]   current pc_iter (x,y,z,I)
-    float4* binned;                // [F][frame_stride]   cell-sorted {x, y, I, mask bits}
+    const float4* raw;             // [F][frame_stride]   the uploaded clouds (x,y,z,I); read once, by the initial sort
+    float4* binned;                // [F][frame_stride]   current pc_iter, cell-sorted: {x, y, I, z}
     int* hist;                     // [F][nfine]
     int* cursor;                   // [F][nfine]
     int* cellstart;                // [F][ncells] first point of the cell's segment in `binned` (multiple of 32)
@@ -107,6 +107,10 @@ struct BatchView {
     FrameCtl* ctl;                 // [F]
     LmState* lm;                   // [F]
     int* n_done;                   // [1]
+    int* rebin_list;               // [2][F] frames that need a re-bin: the LM steps of round r fill list (r+1)&1
+    int* rebin_cnt;                // [2]
+    int list_parity;               // which list this round's binning kernels consume
+    int* bin_done;                 // [F] CTAs of k_count that have finished their share of the histogram
     int* sweep_done;               // [F] CTAs of the current sweep that have finished (last one runs the LM step)
     int fuse_lm;                   // 1: k_sweep's last CTA per frame advances the Ceres state machine
     int force_exact;               // RCLC_SWEEP_EXACT=1
@@ -132,6 +136,7 @@ struct rclc_batch {
     void* d_block = nullptr;          // one allocation for the small arrays
     int64_t* d_npts = nullptr;
     bool binned_valid = false;
+    int round = 0;                    // parity of the re-bin list the next round consumes
     bool sweep_exact = false;         // RCLC_SWEEP_EXACT=1: run the all-fp64 v1 sweep (debug / A-B reference)
     // GMM scratch
     double* d_gmm = nullptr;

@@ -6,7 +6,7 @@ from rclc_b200 import capi, synth
 cfg = capi.config()
 ctx = capi.Context(0)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 500000
-for F in (5, 20, 40):
+for F in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["5","20","40"])]:
     frames, perts = synth.gridfit_batch(F, N, seed0=1000)
     b = capi.Batch(ctx, cfg, F, N)
     for f, p in enumerate(frames):

@@ -1,6 +1,8 @@
 // api.cu — context lifecycle, timing helpers and small shared host utilities of the C ABI.
 #define RCLC_CONFIG_IMPLEMENTATION
 #include "common.cuh"
+#include <thread>
+#include <algorithm>
 
 namespace rclc {
 
@@ -9,27 +11,47 @@ void set_last_error(const std::string& s) { g_last_error = s; }
 
 __global__ void k_pack_passthrough() {}
 
+// Host side of an upload: the strided records are packed to float4 {x,y,z,I} into one of two pinned buffers by a few
+// threads, then copied asynchronously; the copy of frame f overlaps the packing of frame f + 1 (the buffers are guarded by
+// events, the stream orders the kernels that follow behind the copy).
+static void pack_range(const char* src, int stride, int ioff, int64_t k0, int64_t k1, float* o)
+{
+    if (stride == 16 && ioff == 12) {
+        std::memcpy(o + 4 * k0, src + k0 * 16, (size_t)(k1 - k0) * 16);
+        return;
+    }
+    for (int64_t k = k0; k < k1; ++k) {
+        const char* r = src + k * (int64_t)stride;
+        std::memcpy(o + 4 * k, r, 12);
+        std::memcpy(o + 4 * k + 3, r + ioff, 4);
+    }
+}
+
 int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, float4* dst)
 {
     RCLC_CHECK(stride >= 16 && ioff + 4 <= stride && ioff >= 12, RCLC_ERR_INVALID, "bad stride/ioff");
     if (n == 0) return RCLC_OK;
-    if (stride == 16 && ioff == 12) {
-        // already float4: a pageable->device copy stages internally; use our pinned buffer for async behaviour
-        RCLC_TRY(ctx->h_pin.reserve((size_t)n * 16));
-        std::memcpy(ctx->h_pin.p, pts, (size_t)n * 16);
+    const int bi = ctx->up_flip;
+    ctx->up_flip ^= 1;
+    if (!ctx->ev_up[bi]) RCLC_CUDA(cudaEventCreateWithFlags(&ctx->ev_up[bi], cudaEventDisableTiming));
+    RCLC_CUDA(cudaEventSynchronize(ctx->ev_up[bi]));               // previous copy out of this buffer (no-op the first time)
+    RCLC_TRY(ctx->h_up[bi].reserve((size_t)n * 16));
+    float* o = ctx->h_up[bi].as<float>();
+    const char* src = static_cast<const char*>(pts);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int nth = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), std::max<int64_t>(1, n / 65536));
+    if (nth <= 1) {
+        pack_range(src, stride, ioff, 0, n, o);
     } else {
-        RCLC_TRY(ctx->h_pin.reserve((size_t)n * 16));
-        float* o = ctx->h_pin.as<float>();
-        const char* src = static_cast<const char*>(pts);
-        for (int64_t k = 0; k < n; ++k) {
-            const char* r = src + k * (int64_t)stride;
-            std::memcpy(o + 4 * k, r, 12);
-            std::memcpy(o + 4 * k + 3, r + ioff, 4);
-        }
+        std::vector<std::thread> th;
+        const int64_t per = (n + nth - 1) / nth;
+        for (int t = 1; t < nth; ++t)
+            th.emplace_back(pack_range, src, stride, ioff, std::min(n, t * per), std::min(n, (t + 1) * per), o);
+        pack_range(src, stride, ioff, 0, std::min(n, per), o);
+        for (auto& x : th) x.join();
     }
-    RCLC_CUDA(cudaMemcpyAsync(dst, ctx->h_pin.p, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
-    // the pinned buffer is reused by the next call: wait for the copy
-    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    RCLC_CUDA(cudaMemcpyAsync(dst, o, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    RCLC_CUDA(cudaEventRecord(ctx->ev_up[bi], ctx->stream));
     return RCLC_OK;
 }
 
@@ -97,6 +119,9 @@ int rclc_ctx_destroy(rclc_ctx* c)
     cudaEventDestroy(c->ev1);
     cudaEventDestroy(c->evk0);
     cudaEventDestroy(c->evk1);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    for (cudaStream_t st : c->aux_streams) cudaStreamDestroy(st);
+    for (int i = 0; i < 2; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); c->h_up[i].release(); }
     cudaStreamDestroy(c->stream);
     delete c;
     return RCLC_OK;

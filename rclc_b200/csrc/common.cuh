@@ -71,9 +71,14 @@ struct rclc_ctx {
     int64_t l2_bytes = 0;
     int64_t launches = 0;
     int flush_parity = 0;
+    std::vector<cudaStream_t> aux_streams;             // extra streams of the grouped grid-fit solve
+    cudaEvent_t ev_sync = nullptr;
     rclc::Buf d_pts, d_tmp, d_tmp2, d_out, d_flush;   // device scratch
     rclc::Buf h_pin, h_pin2;                           // pinned staging
-    rclc_ctx() { h_pin.pinned = true; h_pin2.pinned = true; }
+    rclc::Buf h_up[2];                                 // pinned double buffer of the cloud uploads
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};         // "the copy out of h_up[i] has finished"
+    int up_flip = 0;
+    rclc_ctx() { h_pin.pinned = true; h_pin2.pinned = true; h_up[0].pinned = true; h_up[1].pinned = true; }
 };
 
 namespace rclc {

@@ -260,6 +260,7 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
         }
         s.rep.outer_iterations = 0; s.rep.status = 0; s.rep.pose_evals = 0; s.rep.lm_iterations = 0;
         s.rep.first_initial_cost = 0; s.rep.last_final_cost = 0;
+        for (int k = 0; k < 8; ++k) s.dbg[k] = 0;
         for (int k = 0; k < 3; ++k) s.rep.se2_first[k] = 0;
         reset_lm_for_outer(s, c);
         if (bv.n_pts[f] != 0) bv.rebin_list[bv.list_parity * bv.n_frames + atomicAdd(&bv.rebin_cnt[bv.list_parity], 1)] = f;
@@ -278,6 +279,11 @@ constexpr int kBinGridX = 128;
 // disc for every pose, so the sweep needs no tail predicate and a 32-point row never mixes two cells.
 __device__ __forceinline__ int pad32(int v) { return (v + 31) & ~31; }
 constexpr float kSentinelXY = 3.0e18f;      // (3e18)^2 * 2 is finite in fp32
+
+// Release / acquire fence at device scope. (__threadfence() is the sequentially-consistent fence: MEMBAR.SC.GPU plus an L1
+// invalidate, at the end of every one of thousands of tasks; the last-arriver protocols here only need their own earlier
+// writes and atomics ordered before the counter increment, and the reader reads through L2.)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // warp-aggregated atomicAdd(&counter[bin], 1): lanes with the same bin elect a leader; returns this lane's rank
 __device__ __forceinline__ int bin_rank(int* counter, int bin, bool valid)
@@ -356,12 +362,12 @@ __device__ __forceinline__ void k_count_frame(const BatchView& bv, int f)
     __shared__ int s_cell[kMaxCoarse];
     __shared__ int s_part[kBinThreads];
     __shared__ int s_last;
-    __threadfence();
+    fence_acq_rel_gpu();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&bv.bin_done[f], 1) == (int)gridDim.x - 1);
     __syncthreads();
     if (!s_last) { __syncthreads(); return; }
-    __threadfence();
+    fence_acq_rel_gpu();
     if (tid == 0) bv.bin_done[f] = 0;
     int my_total = 0;
     for (int cc = tid; cc < nc; cc += kBinThreads) {
@@ -829,53 +835,97 @@ struct LmStage { LmState lm; FrameCtl ctl; };
 // One WARP: residuals + heuristic Jacobian + Huber corrector for every target from the accumulator table, 3x3 normal
 // equations reduced with shuffles, then the Ceres step / accept-reject / radius logic and the opt_grid_fitting
 // outer-loop bookkeeping on lane 0. The frame's state is staged through the warp's slice of shared memory.
+// The ten LM terms of one target from its 16 accumulators: residual + heuristic Jacobian (board_fitting_cost.h:211-260),
+// HuberLoss + Corrector (rho'' <= 0 branch): cost 0.5 rho0, r *= sqrt(rho1), J *= sqrt(rho1); then the products the
+// 3x3 normal equations sum. out[0] cost, out[1..6] J'J (00,01,02,11,12,22), out[7..9] J'r, out[10] bad residual,
+// out[11] bad Jacobian.
+__device__ __forceinline__ void target_terms(const double* a16, bool is_row, const PoseCoef& pc, double cth, double sth, double huber_a,
+                                             double (&out)[12])
+{
+    double r, j0, j1, j2;
+    target_residual(a16, is_row, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
+    out[10] = isfinite(r) ? 0.0 : 1.0;
+    out[11] = (isfinite(j0) && isfinite(j1) && isfinite(j2)) ? 0.0 : 1.0;
+    const double sq = r * r, bb = huber_a * huber_a;
+    double rho0, rho1;
+    if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
+    else { rho0 = sq; rho1 = 1.0; }
+    const double w = sqrt(rho1);
+    r *= w; j0 *= w; j1 *= w; j2 *= w;
+    out[0] = 0.5 * rho0;
+    out[1] = j0 * j0; out[2] = j0 * j1; out[3] = j0 * j2;
+    out[4] = j1 * j1; out[5] = j1 * j2; out[6] = j2 * j2;
+    out[7] = j0 * r;  out[8] = j1 * r;  out[9] = j2 * r;
+}
+
+// One WARP: sums the per-target LM terms into the 3x3 normal equations (shuffles), then the Ceres step / accept-reject /
+// radius logic and the opt_grid_fitting outer-loop bookkeeping on lane 0. HAVE_TERMS: the sweep's tasks have already
+// turned every target's accumulators into its ten terms (bv.terms) and cleared the accumulators; otherwise this warp does
+// that too. The frame's state is staged through the warp's slice of shared memory.
+template <bool HAVE_TERMS>
 __device__ __noinline__ void lm_frame_step(const BatchView& bv, int f, LmStage* stage)
 {
     const int lane = threadIdx.x & 31;
+    const long long c0 = clock64();
     const GridGeom& g = bv.geom;
     LmState& s_lm = stage->lm;
     FrameCtl& s_ctl = stage->ctl;
     {
-        const int* gl = reinterpret_cast<const int*>(&bv.lm[f]);
-        int* sl = reinterpret_cast<int*>(&s_lm);
-        for (int k = lane; k < (int)(sizeof(LmState) / 4); k += 32) sl[k] = __ldcg(gl + k);
-        const int* gc = reinterpret_cast<const int*>(&bv.ctl[f]);
-        int* sc = reinterpret_cast<int*>(&s_ctl);
-        for (int k = lane; k < (int)(sizeof(FrameCtl) / 4); k += 32) sc[k] = __ldcg(gc + k);
+        // 16-byte loads, all in flight before the first store to shared memory
+        static_assert(sizeof(LmState) % 16 == 0 && sizeof(FrameCtl) % 8 == 0 && sizeof(LmState) / 16 <= 96, "state staging");
+        const int4* gl = reinterpret_cast<const int4*>(&bv.lm[f]);
+        int4* sl = reinterpret_cast<int4*>(&s_lm);
+        constexpr int n16 = (int)(sizeof(LmState) / 16);
+        int4 v[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) if (lane + 32 * u < n16) v[u] = __ldcg(gl + lane + 32 * u);
+        const int2* gc = reinterpret_cast<const int2*>(&bv.ctl[f]);
+        int2* sc = reinterpret_cast<int2*>(&s_ctl);
+        constexpr int n8 = (int)(sizeof(FrameCtl) / 8);
+        static_assert(n8 <= 32, "FrameCtl staging");
+        int2 w = make_int2(0, 0);
+        if (lane < n8) w = __ldcg(gc + lane);
+#pragma unroll
+        for (int u = 0; u < 3; ++u) if (lane + 32 * u < n16) sl[lane + 32 * u] = v[u];
+        if (lane < n8) sc[lane] = w;
     }
     __syncwarp();
+    const long long c1 = clock64();
     const PoseCoef pc = s_ctl.pose;
-    const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
-    const double cth = cos(theta), sth = sin(theta);
     double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cost, A00,A01,A02,A11,A12,A22, b0,b1,b2
     int bad_r = 0, bad_j = 0;
-    double* acc = bv.acc + (size_t)f * g.nt * 16;
-    for (int t = lane; t < g.nt; t += 32) {
-        double a16[16];
+    if (HAVE_TERMS) {
+        const double* tm = bv.terms + (size_t)f * 12 * g.nt;
+        for (int t = lane; t < g.nt; t += 32) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) a16[k] = __ldcg(acc + (size_t)t * 16 + k);
-        double r, j0, j1, j2;
-        target_residual(a16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
-        if (!isfinite(r)) bad_r = 1;
-        if (!(isfinite(j0) && isfinite(j1) && isfinite(j2))) bad_j = 1;
-        // HuberLoss + Corrector (rho'' <= 0 branch): cost 0.5 rho0, r *= sqrt(rho1), J *= sqrt(rho1)
-        const double sq = r * r, bb = g.huber_a * g.huber_a;
-        double rho0, rho1;
-        if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * g.huber_a * rr - bb; rho1 = fmax(DBL_MIN, g.huber_a / rr); }
-        else { rho0 = sq; rho1 = 1.0; }
-        const double w = sqrt(rho1);
-        r *= w; j0 *= w; j1 *= w; j2 *= w;
-        sums[0] += 0.5 * rho0;
-        sums[1] += j0 * j0; sums[2] += j0 * j1; sums[3] += j0 * j2;
-        sums[4] += j1 * j1; sums[5] += j1 * j2; sums[6] += j2 * j2;
-        sums[7] += j0 * r;  sums[8] += j1 * r;  sums[9] += j2 * r;
+            for (int k = 0; k < 10; ++k) sums[k] += __ldcg(tm + (size_t)k * g.nt + t);
+            if (__ldcg(tm + (size_t)10 * g.nt + t) != 0.0) bad_r = 1;
+            if (__ldcg(tm + (size_t)11 * g.nt + t) != 0.0) bad_j = 1;
+        }
+    } else {
+        const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
+        const double cth = cos(theta), sth = sin(theta);
+        double* acc = bv.acc + (size_t)f * g.nt * 16;
+        for (int t = lane; t < g.nt; t += 32) {
+            double a16[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) a16[k] = __ldcg(acc + (size_t)t * 16 + k);
+            double tt[12];
+            target_terms(a16, bv.tgt_is_row[t] != 0, pc, cth, sth, g.huber_a, tt);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) sums[k] += tt[k];
+            if (tt[10] != 0.0) bad_r = 1;
+            if (tt[11] != 0.0) bad_j = 1;
+        }
+        __syncwarp();
+        for (int k = lane; k < g.nt * 16; k += 32) acc[k] = 0.0;      // consumed: clear for the next sweep
     }
-    __syncwarp();
-    for (int k = lane; k < g.nt * 16; k += 32) acc[k] = 0.0;      // consumed: clear for the next sweep
+    const long long c2 = clock64();
 #pragma unroll
     for (int k = 0; k < 10; ++k) sums[k] = warp_sum(sums[k]);
     bad_r = __any_sync(0xffffffffu, bad_r);
     bad_j = __any_sync(0xffffffffu, bad_j);
+    const long long c3 = clock64();
     if (lane == 0) {
         EvalSums e;
         e.cost = sums[0];
@@ -884,22 +934,20 @@ __device__ __noinline__ void lm_frame_step(const BatchView& bv, int f, LmStage* 
         e.res_valid = !bad_r;
         e.jac_valid = e.res_valid && !bad_j;
         lm_advance(g, s_lm, s_ctl, e, bv.corners + (size_t)f * g.nc * 3, bv.n_done);
+        const long long c4 = clock64();
+        s_lm.dbg[0] += c1 - c0; s_lm.dbg[1] += c2 - c1; s_lm.dbg[2] += c3 - c2; s_lm.dbg[3] += c4 - c3; s_lm.dbg[4] += 1;
     }
     __syncwarp();
     {
-        int* gl = reinterpret_cast<int*>(&bv.lm[f]);
-        const int* sl = reinterpret_cast<const int*>(&s_lm);
-        for (int k = lane; k < (int)(sizeof(LmState) / 4); k += 32) gl[k] = sl[k];
-        int* gc = reinterpret_cast<int*>(&bv.ctl[f]);
-        const int* sc = reinterpret_cast<const int*>(&s_ctl);
-        for (int k = lane; k < (int)(sizeof(FrameCtl) / 4); k += 32) gc[k] = sc[k];
+        int4* gl = reinterpret_cast<int4*>(&bv.lm[f]);
+        const int4* sl = reinterpret_cast<const int4*>(&s_lm);
+        for (int k = lane; k < (int)(sizeof(LmState) / 16); k += 32) gl[k] = sl[k];
+        int2* gc = reinterpret_cast<int2*>(&bv.ctl[f]);
+        const int2* sc = reinterpret_cast<const int2*>(&s_ctl);
+        if (lane < (int)(sizeof(FrameCtl) / 8)) gc[lane] = sc[lane];
     }
-    if (s_ctl.rebin) {
-        if (lane == 0) bv.rebin_list[(bv.list_parity ^ 1) * bv.n_frames + atomicAdd(&bv.rebin_cnt[bv.list_parity ^ 1], 1)] = f;
-        const int nc = g.ncells, nf = g.nfine;
-        for (int k = lane; k < nf; k += 32) { bv.hist[(size_t)f * nf + k] = 0; bv.cursor[(size_t)f * nf + k] = 0; }
-        for (int k = lane; k < nc; k += 32) bv.cellz2[(size_t)f * nc + k] = 0u;
-    }
+    // the next outer iteration starts with the points moved in place (k_move walks this list)
+    if (s_ctl.rebin && lane == 0) bv.rebin_list[(bv.list_parity ^ 1) * bv.n_frames + atomicAdd(&bv.rebin_cnt[bv.list_parity ^ 1], 1)] = f;
     __syncwarp();
 }
 
@@ -1221,6 +1269,15 @@ __device__ __forceinline__ void drain_list(int mode, const float4* __restrict__ 
     __syncwarp();
 }
 
+// The LM step as its own launch (one warp per frame) — RCLC_LM_SEPARATE=1, an A/B switch for the fused variant.
+__global__ void __launch_bounds__(32) k_lm(BatchView bv)
+{
+    const int f = blockIdx.x;
+    if (!bv.ctl[f].sweep_active) return;
+    __shared__ LmStage stage;
+    lm_frame_step<false>(bv, f, &stage);
+}
+
 constexpr size_t kSweepSmem = (size_t)kSweepWarps * (kRingBytes + kListCap * 4 + 16 * 8 + 12 * 8 + sizeof(WarpCtx) + sizeof(LmStage));
 static_assert(kListPad <= 32, "one lane per padding entry");
 
@@ -1357,15 +1414,43 @@ __global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
         else *dst = v;
     }
     if (!bv.fuse_lm) return;
-    // ---- fused LM step: the warp that finishes the frame's last task owns the complete accumulator table ----
-    __threadfence();
-    int last = 0;
-    if (lane == 0) last = (atomicAdd(&bv.sweep_done[f], 1) == g.nt * parts - 1);
+    // ---- fused LM step, part 1: the warp that adds the target's last share turns its 16 accumulators into the ten LM terms
+    //      (in parallel over the targets, overlapped with the tasks still sweeping) and clears them for the next sweep ----
+    if (bv.fuse_lm != 2) fence_acq_rel_gpu();
+    int last = 1;
+    if (parts > 1) {
+        if (lane == 0) last = (atomicAdd(&bv.tgt_done[(size_t)f * g.nt + t], 1) == parts - 1);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) return;
+        if (bv.fuse_lm != 2) fence_acq_rel_gpu();
+        if (lane == 0) bv.tgt_done[(size_t)f * g.nt + t] = 0;
+    }
+    {
+        double* acc_t = bv.acc + ((size_t)f * g.nt + t) * 16;
+        double a16[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) a16[q] = __ldcg(acc_t + q);               // same addresses in every lane: one transaction each
+        const PoseCoef pcc = wc->pc;
+        const double theta = (pcc.yaw_deg * 3.14159265358979323846) / 180.0;
+        const double cth = cos(theta), sth = sin(theta);
+        double tt[12];
+        target_terms(a16, bv.tgt_is_row[t] != 0, pcc, cth, sth, g.huber_a, tt);
+        double* tm = bv.terms + (size_t)f * 12 * g.nt + t;
+        double mine = 0.0;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) if (lane == q) mine = tt[q];
+        if (lane < 12) tm[(size_t)lane * g.nt] = mine;
+        if (lane >= 16) acc_t[lane - 16] = 0.0;
+    }
+    // ---- part 2: the warp that finishes the frame's last target sums the terms and runs the LM state machine ----
+    if (bv.fuse_lm != 2) fence_acq_rel_gpu();
+    last = 0;
+    if (lane == 0) last = (atomicAdd(&bv.sweep_done[f], 1) == g.nt - 1);
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
-    __threadfence();
+    if (bv.fuse_lm != 2) fence_acq_rel_gpu();
     if (lane == 0) bv.sweep_done[f] = 0;
-    lm_frame_step(bv, f, stage);
+    lm_frame_step<true>(bv, f, stage);
 }
 
 __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
@@ -1435,42 +1520,78 @@ __global__ void __launch_bounds__(kLmThreads) k_ms_cost(BatchView bv, double* __
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // The binning kernels walk the re-bin list with gridDim.y CTA columns: most rounds have nothing (or one frame) to
-// re-bin and must cost next to nothing, while one frame alone still gets hundreds of CTAs.
+// move and must cost next to nothing, while one frame alone still gets hundreds of CTAs.
 constexpr int kBinGridY = 2;
-static dim3 bin_grid(const rclc_batch* b)
+
+// A contiguous range of frames of the batch, run as a unit on its own stream.
+struct GroupRun {
+    BatchView v;
+    int f0 = 0, nf = 0;
+    int round = 0;            // parity of the re-bin list the next round consumes
+    cudaStream_t st = nullptr;
+};
+
+static BatchView slice_view(const BatchView& v, int f0, int nf, int group)
 {
-    const int64_t ctas = (b->max_pts + kBinThreads * 4 - 1) / (kBinThreads * 4);
-    return dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas, 512)), (unsigned)std::min(kBinGridY, b->n_frames));
+    BatchView s = v;
+    const size_t nt = v.geom.nt, nc = v.geom.ncells, nfine = v.geom.nfine, ncorn = v.geom.nc;
+    s.n_frames = nf;
+    s.n_pts = v.n_pts + f0;
+    s.raw = v.raw + (size_t)f0 * v.frame_stride;
+    s.binned = v.binned + (size_t)f0 * v.frame_stride;
+    s.hist = v.hist + (size_t)f0 * nfine;
+    s.cursor = v.cursor + (size_t)f0 * nfine;
+    s.cellstart = v.cellstart + (size_t)f0 * nc;
+    s.cellcnt = v.cellcnt + (size_t)f0 * nc;
+    s.cellz2 = v.cellz2 + (size_t)f0 * nc;
+    s.rowbox = v.rowbox + (size_t)f0 * (v.frame_stride / 32);
+    s.acc = v.acc + (size_t)f0 * nt * 16;
+    s.ctl = v.ctl + f0;
+    s.lm = v.lm + f0;
+    s.bin_done = v.bin_done + f0;
+    s.terms = v.terms + (size_t)f0 * nt * 12;
+    s.tgt_done = v.tgt_done + (size_t)f0 * nt;
+    s.sweep_done = v.sweep_done + f0;
+    s.eval_out = v.eval_out + (size_t)f0 * nt * 4;
+    s.corners = v.corners + (size_t)f0 * ncorn * 3;
+    s.rebin_list = v.rebin_list + 2 * f0;          // [2][nf] inside the batch's [2 * F]
+    s.rebin_cnt = v.rebin_cnt + 2 * group;
+    return s;
 }
 
-static int launch_rebin(rclc_batch* b)
+static dim3 bin_grid(int64_t max_pts, int nf)
 {
-    cudaStream_t st = b->ctx->stream;
-    b->v.list_parity = b->round & 1;
-    k_count<<<bin_grid(b), kBinThreads, 0, st>>>(b->v);
-    k_scatter<<<bin_grid(b), kBinThreads, 0, st>>>(b->v);
-    const int64_t rows = b->v.frame_stride / 32;
-    k_rowbox<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 256)), (unsigned)std::min(kBinGridY, b->n_frames)), kBoxThreads, 0, st>>>(b->v);
-    b->round++;              // the sweep that follows keeps this round's parity (its LM steps fill the other list)
-    RCLC_CUDA(cudaGetLastError());
-    return RCLC_OK;
+    const int64_t ctas = (max_pts + kBinThreads * 4 - 1) / (kBinThreads * 4);
+    return dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas, 512)), (unsigned)std::min(kBinGridY, nf));
 }
 
-// rounds after the initial sort: frames that start their next outer iteration are moved in place
-static int launch_move(rclc_batch* b)
+// the one counting sort of a solve (or of rclc_batch_bin): count + offsets, scatter, row boxes
+static int launch_rebin(rclc_batch* b, GroupRun& gr)
 {
-    cudaStream_t st = b->ctx->stream;
-    b->v.list_parity = b->round & 1;
-    const int64_t rows = b->v.frame_stride / 32;
-    k_move<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 444)), (unsigned)std::min(kBinGridY, b->n_frames)), kBoxThreads, 0, st>>>(b->v);
-    b->ctx->launches += 1;
-    b->round++;
+    gr.v.list_parity = gr.round & 1;
+    k_count<<<bin_grid(b->max_pts, gr.nf), kBinThreads, 0, gr.st>>>(gr.v);
+    k_scatter<<<bin_grid(b->max_pts, gr.nf), kBinThreads, 0, gr.st>>>(gr.v);
+    const int64_t rows = gr.v.frame_stride / 32;
+    k_rowbox<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 256)), (unsigned)std::min(kBinGridY, gr.nf)), kBoxThreads, 0, gr.st>>>(gr.v);
     b->ctx->launches += 3;
+    gr.round++;              // the sweep that follows keeps this round's parity (its LM steps fill the other list)
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
 }
 
-// One warp per (target, part); parts chosen so that a full batch fills the GPU about twice over.
+// rounds after the sort: frames that start their next outer iteration are moved in place
+static int launch_move(rclc_batch* b, GroupRun& gr)
+{
+    gr.v.list_parity = gr.round & 1;
+    const int64_t rows = gr.v.frame_stride / 32;
+    k_move<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 444)), (unsigned)std::min(kBinGridY, gr.nf)), kBoxThreads, 0, gr.st>>>(gr.v);
+    b->ctx->launches += 1;
+    gr.round++;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+// One warp per (target, part); parts chosen so that the frames in flight fill the GPU about twice over.
 static int sweep_parts(const rclc_batch* b, int n_frames)
 {
     const int64_t slots = (int64_t)b->ctx->sm_count * 20;              // resident warps (5 CTAs of 4 warps per SM)
@@ -1478,30 +1599,36 @@ static int sweep_parts(const rclc_batch* b, int n_frames)
     return (int)std::max<int64_t>(1, std::min<int64_t>(8, (2 * slots + tasks - 1) / tasks));
 }
 
-static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames)
+static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames, cudaStream_t st, int frames_in_flight)
 {
-    v.parts = sweep_parts(b, n_frames);
+    v.parts = sweep_parts(b, frames_in_flight);
     const int gx = (v.geom.nt * v.parts + kSweepWarps - 1) / kSweepWarps;
-    k_sweep<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, b->ctx->stream>>>(v);
+    k_sweep<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
     b->ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
+}
+
+static GroupRun whole_batch(rclc_batch* b)
+{
+    GroupRun gr;
+    gr.v = b->v;
+    gr.f0 = 0; gr.nf = b->n_frames; gr.round = b->round; gr.st = b->ctx->stream;
+    return gr;
 }
 
 static int launch_sweep(rclc_batch* b, bool fuse_lm)
 {
     BatchView v = b->v;
     v.fuse_lm = fuse_lm ? 1 : 0;
-    return launch_sweep_view(b, v, b->n_frames);
+    return launch_sweep_view(b, v, b->n_frames, b->ctx->stream, b->n_frames);
 }
 
-static int launch_init(rclc_batch* b, const double* d_Tbl)
+static int launch_init(rclc_batch* b, GroupRun& gr, const double* d_Tbl)
 {
-    cudaStream_t st = b->ctx->stream;
-    RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, sizeof(int), st));
-    RCLC_CUDA(cudaMemsetAsync(b->v.rebin_cnt, 0, 2 * sizeof(int), st));
-    b->v.list_parity = b->round & 1;
-    k_init_state<<<b->n_frames, 256, 0, st>>>(b->v, d_Tbl);
+    RCLC_CUDA(cudaMemsetAsync(gr.v.rebin_cnt, 0, 2 * sizeof(int), gr.st));
+    gr.v.list_parity = gr.round & 1;
+    k_init_state<<<gr.nf, 256, 0, gr.st>>>(gr.v, d_Tbl ? d_Tbl + (size_t)gr.f0 * 16 : nullptr);
     b->ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
@@ -1560,7 +1687,7 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     const size_t o_npts = take(F * 8), o_hist = take(F * nfine * 4), o_cur = take(F * nfine * 4), o_cmask = take(F * ncell * 4);
     const size_t o_cstart = take(F * ncell * 4), o_ccnt = take(F * ncell * 4), o_box = take(F * (size_t)(v.frame_stride / 32) * 16);
     const size_t o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
-    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_bdone = take(F * 4), o_rlist = take(2 * F * 4), o_rcnt = take(256), o_txy = take(nt * 16), o_txyf = take(nt * 8);
+    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_bdone = take(F * 4), o_rlist = take(2 * F * 4), o_rcnt = take(256), o_terms = take(F * nt * 12 * 8), o_tdone = take(F * nt * 4), o_txy = take(nt * 16), o_txyf = take(nt * 8);
     const size_t o_row = take(nt), o_cand = take(ncell * kCand * 2), o_eval = take(F * nt * 4 * 8);
     const size_t o_corn = take(F * (size_t)hg.g.nc * 3 * 8), o_gmm = take(F * 64 * 8 + 4096 * 8 * 8);
     if (cudaMalloc(&b->d_block, off) != cudaSuccess) return fail("cudaMalloc block");
@@ -1580,6 +1707,8 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.n_done = reinterpret_cast<int*>(base + o_done);
     v.sweep_done = reinterpret_cast<int*>(base + o_sdone);
     v.bin_done = reinterpret_cast<int*>(base + o_bdone);
+    v.terms = reinterpret_cast<double*>(base + o_terms);
+    v.tgt_done = reinterpret_cast<int*>(base + o_tdone);
     v.rebin_list = reinterpret_cast<int*>(base + o_rlist);
     v.rebin_cnt = reinterpret_cast<int*>(base + o_rcnt);
     v.list_parity = 0;
@@ -1647,8 +1776,12 @@ int rclc_batch_bin(rclc_batch* b)
 {
     RCLC_CHECK(b, RCLC_ERR_INVALID, "null batch");
     RCLC_CUDA(cudaSetDevice(b->ctx->device));
-    RCLC_TRY(launch_init(b, nullptr));
-    RCLC_TRY(launch_rebin(b));
+    RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, sizeof(int), b->ctx->stream));
+    GroupRun gr = whole_batch(b);
+    RCLC_TRY(launch_init(b, gr, nullptr));
+    RCLC_TRY(launch_rebin(b, gr));
+    b->round = gr.round;
+    b->v.list_parity = gr.v.list_parity;
     b->binned_valid = true;
     return RCLC_OK;
 }
@@ -1707,27 +1840,68 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     // opt_grid_fitting.h:47-56 apply_noise_test is a debugging aid that perturbs the input; the caller
     // can apply it with rclc_transform_cloud. It is rejected here rather than silently ignored.
     RCLC_CHECK(!b->cfg.apply_noise_test, RCLC_ERR_UNSUPPORTED, "apply_noise_test: perturb the input with rclc_transform_cloud instead");
-    RCLC_TRY(launch_init(b, d_Tbl));
     b->binned_valid = false;
     RCLC_TRY(ctx->h_pin2.reserve(64));
     int* h_done = ctx->h_pin2.as<int>();
+    // Frames are independent until the extrinsic solve, so the batch runs as G groups on G streams: while the LM steps of
+    // one group (a single warp per frame, ~15 us of dependent fp64) hold the tail of its sweep kernel, the other groups'
+    // sweeps keep the SMs busy. RCLC_SOLVE_GROUPS overrides the default of 2 (1: the whole batch in lock-step).
+    static const int want_groups = [] { const char* e = std::getenv("RCLC_SOLVE_GROUPS"); return e ? std::max(1, std::min(16, atoi(e))) : 2; }();
+    const int G = std::max(1, std::min(want_groups, F / 2));
+    while ((int)ctx->aux_streams.size() < G - 1) {
+        cudaStream_t st;
+        RCLC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->aux_streams.push_back(st);
+    }
+    if (!ctx->ev_sync) RCLC_CUDA(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+    RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, sizeof(int), ctx->stream));
+    RCLC_CUDA(cudaEventRecord(ctx->ev_sync, ctx->stream));              // uploads, T_bl, ... precede every group
+    std::vector<GroupRun> groups(G);
+    for (int gi = 0; gi < G; ++gi) {
+        GroupRun& gr = groups[gi];
+        gr.f0 = (int)((int64_t)F * gi / G);
+        gr.nf = (int)((int64_t)F * (gi + 1) / G) - gr.f0;
+        gr.st = gi == 0 ? ctx->stream : ctx->aux_streams[gi - 1];
+        gr.v = slice_view(b->v, gr.f0, gr.nf, gi);
+        { static const int fl = [] { const char* e = std::getenv("RCLC_UNSAFE_NOFENCE"); return (e && e[0] == '1') ? 2 : 1; }(); gr.v.fuse_lm = fl; }
+        gr.round = 0;
+        if (gi > 0) RCLC_CUDA(cudaStreamWaitEvent(gr.st, ctx->ev_sync, 0));
+        RCLC_TRY(launch_init(b, gr, d_Tbl));
+    }
     // Upper bound on rounds: every outer iteration needs at most max_lm_iters+2 evaluations.
     const int64_t max_rounds = (int64_t)(g.max_iter_time + 2) * (g.max_lm_iters + 3);
     const int rounds_per_check = 24;
     int64_t rounds = 0;
-    // RCLC_PROFILE_ROUNDS=1: CUDA events between the binning launches and the sweep of every round; totals on stderr
+    // RCLC_PROFILE_ROUNDS=1: CUDA events between the move and the sweep of every round of group 0; totals on stderr
     static const bool prof = [] { const char* e = std::getenv("RCLC_PROFILE_ROUNDS"); return e && e[0] == '1'; }();
-    std::vector<cudaEvent_t> evs;
+    static const bool lm_separate = [] { const char* e = std::getenv("RCLC_LM_SEPARATE"); return e && e[0] == '1'; }();
+    std::vector<cudaEvent_t> evs, evs_lm;
     for (;;) {
         for (int r = 0; r < rounds_per_check; ++r) {
-            if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e); }
-            if (rounds == 0 && r == 0) RCLC_TRY(launch_rebin(b));      // the one counting sort of the solve
-            else RCLC_TRY(launch_move(b));
-            if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e); }
-            RCLC_TRY(launch_sweep(b, true));      // sweep + fused LM step (last CTA per frame)
+            for (int gi = 0; gi < G; ++gi) {
+                GroupRun& gr = groups[gi];
+                const bool pg = prof && gi == 0;
+                if (pg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, gr.st); evs.push_back(e); }
+                if (rounds == 0 && r == 0) RCLC_TRY(launch_rebin(b, gr));      // the one counting sort of the solve
+                else RCLC_TRY(launch_move(b, gr));
+                if (pg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, gr.st); evs.push_back(e); }
+                if (lm_separate) {
+                    gr.v.fuse_lm = 0;
+                    RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, F));
+                    if (pg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, gr.st); evs_lm.push_back(e); }
+                    k_lm<<<gr.nf, 32, 0, gr.st>>>(gr.v);
+                    ctx->launches += 1;
+                } else {
+                    RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, F));      // sweep + fused LM step (last warp per frame)
+                }
+            }
         }
         rounds += rounds_per_check;
         RCLC_CUDA(cudaGetLastError());
+        for (int gi = 1; gi < G; ++gi) {                                        // ctx->stream joins the other groups
+            RCLC_CUDA(cudaEventRecord(ctx->ev_sync, groups[gi].st));
+            RCLC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
+        }
         RCLC_CUDA(cudaMemcpyAsync(h_done, b->v.n_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (*h_done >= F) break;
@@ -1736,12 +1910,29 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     if (prof && evs.size() >= 4) {
         cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e);
         cudaEventSynchronize(e);
+        if (evs_lm.size() * 2 + 1 == evs.size()) {
+            double t_lm = 0;
+            for (size_t i = 0; i < evs_lm.size(); ++i) { float a = 0; cudaEventElapsedTime(&a, evs_lm[i], evs[2 * i + 2]); t_lm += a; }
+            fprintf(stderr, "[rclc profile] separate k_lm launches: %.2f ms total, %.1f us each\n", t_lm, 1e3 * t_lm / evs_lm.size());
+            for (cudaEvent_t x : evs_lm) cudaEventDestroy(x);
+        }
         double t_bin = 0, t_sweep = 0, bin_max = 0; int n_bin_big = 0;
+        std::vector<float> sw;
         for (size_t i = 0; i + 2 < evs.size(); i += 2) {
             float a = 0, c = 0;
             cudaEventElapsedTime(&a, evs[i], evs[i + 1]);
             cudaEventElapsedTime(&c, evs[i + 1], evs[i + 2]);
             t_bin += a; t_sweep += c; bin_max = std::max<double>(bin_max, a); n_bin_big += a > 0.02f;
+            sw.push_back(c);
+        }
+        {
+            std::vector<float> q = sw; std::sort(q.begin(), q.end());
+            fprintf(stderr, "[rclc profile] sweep+lm per round: min %.1f  p25 %.1f  median %.1f  p75 %.1f  max %.1f us; first 8:", q.front() * 1e3,
+                    q[q.size() / 4] * 1e3, q[q.size() / 2] * 1e3, q[3 * q.size() / 4] * 1e3, q.back() * 1e3);
+            for (size_t i = 0; i < 8 && i < sw.size(); ++i) fprintf(stderr, " %.0f", sw[i] * 1e3);
+            fprintf(stderr, "; last 8:");
+            for (size_t i = sw.size() >= 8 ? sw.size() - 8 : 0; i < sw.size(); ++i) fprintf(stderr, " %.0f", sw[i] * 1e3);
+            fprintf(stderr, "\n");
         }
         float tot = 0; cudaEventElapsedTime(&tot, evs.front(), evs.back());
         fprintf(stderr, "[rclc profile] rounds %zu  total %.2f ms  binning %.2f ms (%d rounds > 20 us, max %.1f us)  sweep+lm %.2f ms\n",
@@ -1753,6 +1944,13 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     if (corners_out)
         RCLC_CUDA(cudaMemcpyAsync(corners_out, b->v.corners, (size_t)F * g.nc * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (prof) {
+        long long d[5] = {0, 0, 0, 0, 0};
+        for (int f = 0; f < F; ++f) for (int k = 0; k < 5; ++k) d[k] += h_lm[f].dbg[k];
+        if (d[4] > 0)
+            fprintf(stderr, "[rclc profile] lm_frame_step cycles per call: load state %lld, acc + residuals %lld, clear + warp sums %lld, lm_advance %lld (%lld calls)\n",
+                    d[0] / d[4], d[1] / d[4], d[2] / d[4], d[3] / d[4], d[4]);
+    }
     int rc = RCLC_OK;
     for (int f = 0; f < F; ++f) {
         if (reports) reports[f] = h_lm[f].rep;
@@ -1835,7 +2033,7 @@ int rclc_batch_multistart(rclc_batch* b, int32_t frame, const double* poses, int
         vs.ctl = d_ctl + p0;
         vs.acc = d_acc + (size_t)p0 * nt * 16;
         vs.n_frames = np;
-        RCLC_TRY(launch_sweep_view(b, vs, np));
+        RCLC_TRY(launch_sweep_view(b, vs, np, ctx->stream, np));
         k_ms_cost<<<np, kLmThreads, 0, ctx->stream>>>(vs, d_cost + p0);
         ctx->launches += 1;
     }

@@ -55,7 +55,7 @@ struct PoseCoef {              // R = Quaternion(cos(t/2),0,0,sin(t/2)).matrix()
 enum Phase { PH_EVAL_INIT = 1, PH_EVAL_CAND = 2, PH_DONE = 3 };
 
 // Per-frame control block read by the streaming kernels.
-struct FrameCtl {
+struct alignas(8) FrameCtl {
     int sweep_active;          // sweep kernels process this frame
     int rebin;                 // count/scatter kernels process this frame (move + re-bin)
     int n_rows;                // 32-point rows of the current binning (cells padded to whole rows)
@@ -67,7 +67,7 @@ struct FrameCtl {
 };
 
 // Ceres TrustRegionMinimizer state + opt_grid_fitting outer-loop state, one per frame.
-struct LmState {
+struct alignas(16) LmState {
     int phase;
     int outer_iter;
     int status;
@@ -86,6 +86,7 @@ struct LmState {
     float T_base_laser[16];
     double T_bl[16];
     rclc_gridfit_report rep;
+    long long dbg[8];          // RCLC_PROFILE_ROUNDS: SM cycles spent in the stages of lm_frame_step, summed over its calls
 };
 
 struct BatchView {
@@ -110,6 +111,8 @@ struct BatchView {
     int* rebin_list;               // [2][F] frames that need a re-bin: the LM steps of round r fill list (r+1)&1
     int* rebin_cnt;                // [2]
     int list_parity;               // which list this round's binning kernels consume
+    double* terms;                 // [F][12][nt] per-target LM terms (cost, 6 J'J, 3 J'r, 2 flags) written by the sweep
+    int* tgt_done;                 // [F][nt] parts of a target that have flushed their accumulators
     int* bin_done;                 // [F] CTAs of k_count that have finished their share of the histogram
     int* sweep_done;               // [F] CTAs of the current sweep that have finished (last one runs the LM step)
     int fuse_lm;                   // 1: k_sweep's last CTA per frame advances the Ceres state machine

@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librclc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-fopenmp", "-ccbin", "/usr/bin/g++"]
 
 
 def _stale():
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on " + s)
         if verbose or "warning" in out:
             sys.stderr.write(out)
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart_static", "-ldl", "-lrt",
+    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart_static", "-ldl", "-lrt", "-lgomp",
                                                                  "-lpthread"])
     return LIB
 

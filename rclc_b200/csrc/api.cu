@@ -1,7 +1,7 @@
 // api.cu — context lifecycle, timing helpers and small shared host utilities of the C ABI.
 #define RCLC_CONFIG_IMPLEMENTATION
 #include "common.cuh"
-#include <thread>
+#include <omp.h>
 #include <algorithm>
 
 namespace rclc {
@@ -38,18 +38,12 @@ int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_
     RCLC_TRY(ctx->h_up[bi].reserve((size_t)n * 16));
     float* o = ctx->h_up[bi].as<float>();
     const char* src = static_cast<const char*>(pts);
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int nth = (int)std::min<int64_t>(std::min<unsigned>(hw, 8u), std::max<int64_t>(1, n / 65536));
-    if (nth <= 1) {
-        pack_range(src, stride, ioff, 0, n, o);
-    } else {
-        std::vector<std::thread> th;
-        const int64_t per = (n + nth - 1) / nth;
-        for (int t = 1; t < nth; ++t)
-            th.emplace_back(pack_range, src, stride, ioff, std::min(n, t * per), std::min(n, (t + 1) * per), o);
-        pack_range(src, stride, ioff, 0, std::min(n, per), o);
-        for (auto& x : th) x.join();
-    }
+    // OpenMP keeps its worker threads between calls (spawning std::threads per frame cost more than the copy itself)
+    const int64_t chunk = 65536;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    const int nth = (int)std::min<int64_t>(std::min(omp_get_max_threads(), 8), nchunks);
+#pragma omp parallel for num_threads(nth) schedule(static)
+    for (int64_t c = 0; c < nchunks; ++c) pack_range(src, stride, ioff, c * chunk, std::min(n, (c + 1) * chunk), o);
     RCLC_CUDA(cudaMemcpyAsync(dst, o, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
     RCLC_CUDA(cudaEventRecord(ctx->ev_up[bi], ctx->stream));
     return RCLC_OK;

@@ -1,0 +1,431 @@
+// rclc_ops.hpp — the reference's C++ operator surface on top of the C ABI (rclc_b200.h).
+//
+// zhijianglu/RCLC has no plugin layer: its hot path is a set of header-inline free functions and small classes with
+// PCL / Eigen / Ceres types in their signatures. This header gives that path the SAME names, argument
+// order, in/out conventions and "never throws, prints and carries on" error behaviour, and forwards to
+// librclc_b200.so:
+//
+//   reference symbol (file:line)                                         forwards to
+//   ---------------------------------------------------------------------------------------------------------
+//   GMMFit::fit_1d                       include/GMMFit.h:31                rclc_gmm_fit_1d
+//   pc_plane_prj                         include/pc_process.h:41            rclc_plane_project
+//   opt_grid_fitting                     include/opt/opt_grid_fitting.h:25  rclc_gridfit_solve
+//   BOARD_FITTING_COST::Create/Evaluate  include/opt/board_fitting_cost.h:64-78   rclc_batch_* (one sweep serves all 82 functors)
+//   pose_reprj_opt                       include/opt/opt_reprj_calib.h:21   rclc_pose_refine
+//   PinholeCam::{imgPt2norm,normPt2img,Pt2img,is_in_FoV}  include/PinholeCam.h:78-110   (host inline, same arithmetic)
+//   colourise loop                       apps/Calibrate.cpp:134-148         rclc_project_colorize  (colorize_cloud)
+//   pcl::SACSegmentation<>::segment as configured at apps/BoardSegmentation.cpp:64-72
+//                                                                           rclc_ransac_plane_score + host replay of
+//                                                                           PCL's adaptive rule + rclc_ransac_plane_select
+//
+// Types. With -DRCLC_WITH_PCL_EIGEN the signatures use the real pcl:: / Eigen:: types, so the header drops into
+// BoardSegmentation.cpp / Calibrate.cpp unchanged. Neither library exists in the build image of this repository, so by
+// default it compiles against the small stand-ins in rclc_b200::compat, which have the SAME memory layout
+// (pcl::PointXYZI is 32 bytes: x y z pad | intensity pad pad pad) and the accessors the shims use.
+//
+// Threading: the reference calls these operators inside `#pragma omp parallel for` over frames; every host thread
+// gets its own rclc_ctx (one CUDA stream + scratch) through thread_ctx().
+#ifndef RCLC_OPS_HPP
+#define RCLC_OPS_HPP
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <vector>
+
+#include "rclc_b200.h"
+
+#ifdef RCLC_WITH_PCL_EIGEN
+#include <Eigen/Dense>
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#include <pcl/ModelCoefficients.h>
+#include <pcl/PointIndices.h>
+#endif
+
+namespace rclc_b200 {
+
+#ifndef RCLC_WITH_PCL_EIGEN
+// ---------------------------------------------------------------------------------------------------------------
+// Stand-ins with the layout and the accessors of the PCL / Eigen types in the reference's signatures.
+// ---------------------------------------------------------------------------------------------------------------
+namespace compat {
+struct alignas(16) PointXYZI {          // == pcl::PointXYZI (32 bytes)
+    float x = 0, y = 0, z = 0, _w = 1.f;
+    float intensity = 0, _p[3] = {0, 0, 0};
+};
+struct alignas(16) PointXYZRGB {        // == pcl::PointXYZRGB (32 bytes, bgra packed at offset 16)
+    float x = 0, y = 0, z = 0, _w = 1.f;
+    uint8_t b = 0, g = 0, r = 0, a = 255;
+    float _p[3] = {0, 0, 0};
+};
+static_assert(sizeof(PointXYZI) == 32 && sizeof(PointXYZRGB) == 32, "PCL point layout");
+template <class P> struct PointCloud {
+    typedef std::shared_ptr<PointCloud<P>> Ptr;
+    std::vector<P> points;
+    size_t size() const { return points.size(); }
+};
+template <int N> struct Vec {
+    double v[N];
+    Vec() { for (int i = 0; i < N; ++i) v[i] = 0; }
+    Vec(double a, double b) { static_assert(N == 2, ""); v[0] = a; v[1] = b; }
+    Vec(double a, double b, double c) { static_assert(N == 3, ""); v[0] = a; v[1] = b; v[2] = c; }
+    Vec(double a, double b, double c, double d) { static_assert(N == 4, ""); v[0] = a; v[1] = b; v[2] = c; v[3] = d; }
+    double& operator[](int i) { return v[i]; }
+    double operator[](int i) const { return v[i]; }
+    double& x() { return v[0]; } double& y() { return v[1]; } double& z() { return v[2]; } double& w() { return v[3]; }
+    double x() const { return v[0]; } double y() const { return v[1]; } double z() const { return v[2]; } double w() const { return v[3]; }
+};
+typedef Vec<2> Vector2d;
+typedef Vec<3> Vector3d;
+typedef Vec<4> Vector4d;
+template <class T> struct Mat4 {        // (row, col) access like Eigen; storage order is private to the shim
+    T m[16];
+    Mat4() { for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? T(1) : T(0); }
+    T& operator()(int r, int c) { return m[r * 4 + c]; }
+    T operator()(int r, int c) const { return m[r * 4 + c]; }
+};
+typedef Mat4<double> Matrix4d;
+typedef Mat4<float> Matrix4f;
+struct VectorXd {                       // the subset GMMFit::fit_1d uses
+    std::vector<double> d;
+    VectorXd() {}
+    explicit VectorXd(long n) : d((size_t)n, 0.0) {}
+    long size() const { return (long)d.size(); }
+    long rows() const { return (long)d.size(); }
+    double& operator()(long i) { return d[(size_t)i]; }
+    double operator()(long i) const { return d[(size_t)i]; }
+};
+struct PointIndices { std::vector<int> indices; };
+struct ModelCoefficients { std::vector<float> values; };
+}  // namespace compat
+using compat::PointXYZI; using compat::PointXYZRGB; using compat::PointCloud;
+using compat::Vector2d; using compat::Vector3d; using compat::Vector4d; using compat::Matrix4d; using compat::Matrix4f;
+using compat::VectorXd; using compat::PointIndices; using compat::ModelCoefficients;
+#else
+typedef pcl::PointXYZI PointXYZI; typedef pcl::PointXYZRGB PointXYZRGB;
+template <class P> using PointCloud = pcl::PointCloud<P>;
+using Eigen::Vector2d; using Eigen::Vector3d; using Eigen::Vector4d; using Eigen::Matrix4d; using Eigen::Matrix4f; using Eigen::VectorXd;
+typedef pcl::PointIndices PointIndices; typedef pcl::ModelCoefficients ModelCoefficients;
+#endif
+typedef PointXYZI PoinT;                // include/global.h:59 "typedef pcl::PointXYZI PoinT"
+typedef PointXYZRGB DisplayType;        // include/global.h:60
+
+// ---------------------------------------------------------------------------------------------------------------
+// Session state: the reference's globals CfgParam / Cam (include/global.h:118-120) become one POD config, read-only
+// after set_config(); every host thread owns a context.
+// ---------------------------------------------------------------------------------------------------------------
+inline rclc_config& CfgParam()
+{
+    static rclc_config cfg = [] { rclc_config c; rclc_config_default(&c); return c; }();
+    return cfg;
+}
+inline int& device_ordinal() { static int dev = 0; return dev; }
+
+struct CtxHolder {
+    rclc_ctx* ctx = nullptr;
+    ~CtxHolder() { if (ctx) rclc_ctx_destroy(ctx); }
+};
+// nullptr (after printing why) when there is no CUDA device: there is NO CPU fallback behind these operators.
+inline rclc_ctx* thread_ctx()
+{
+    static thread_local CtxHolder h;
+    if (!h.ctx && rclc_ctx_create(device_ordinal(), &h.ctx) != RCLC_OK) {
+        std::fprintf(stderr, "rclc_b200: no context (%s)\n", rclc_last_error_string());
+        h.ctx = nullptr;
+    }
+    return h.ctx;
+}
+inline bool ok(int rc, const char* what)
+{
+    // the reference's operators do not report errors (failures are printed, Calibrate.cpp carries on): same here
+    if (rc != RCLC_OK) std::fprintf(stderr, "rclc_b200: %s failed (%d): %s\n", what, rc, rclc_last_error_string());
+    return rc == RCLC_OK;
+}
+inline void to_row_major(const Matrix4d& T, double out[16]) { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[r * 4 + c] = T(r, c); }
+inline void from_row_major(const double in[16], Matrix4d& T) { for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T(r, c) = in[r * 4 + c]; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// GMMFit::fit_1d — include/GMMFit.h:31, src/GMMFit.cpp:7-108. mu / sigma in-out. (The reference's function falls off
+// its end without a return value; callers ignore it. This one returns whether the device call succeeded.)
+// The reference feeds it float intensities widened to double (pc_process.h:600-606); the kernel reads floats.
+// ---------------------------------------------------------------------------------------------------------------
+class GMMFit {
+public:
+    static bool fit_1d(const VectorXd& in_vec, const int K, std::vector<double>& mu, std::vector<double>& sigma, bool show_debug_info = false)
+    {
+        (void)show_debug_info;
+        rclc_ctx* ctx = thread_ctx();
+        if (!ctx || (int)mu.size() != K || (int)sigma.size() != K) return false;
+        std::vector<float> x((size_t)in_vec.size());
+        for (long i = 0; i < (long)in_vec.size(); ++i) x[(size_t)i] = (float)in_vec(i);
+        double priors[8] = {0};
+        return ok(rclc_gmm_fit_1d(ctx, x.data(), 4, (int64_t)x.size(), K, CfgParam().gmm_iters, mu.data(), sigma.data(), priors), "GMMFit::fit_1d");
+    }
+};
+
+// pc_plane_prj — include/pc_process.h:41-57: slides every point along its ray onto the plane, in place.
+inline void pc_plane_prj(typename PointCloud<PoinT>::Ptr& Points, Vector4d& plane_param_l)
+{
+    rclc_ctx* ctx = thread_ctx();
+    if (!ctx || !Points || Points->size() == 0) return;
+    const double plane[4] = {plane_param_l.x(), plane_param_l.y(), plane_param_l.z(), plane_param_l.w()};
+    ok(rclc_plane_project(ctx, Points->points.data(), (int)sizeof(PoinT), (int64_t)Points->size(), plane), "pc_plane_prj");
+}
+
+// opt_grid_fitting — include/opt/opt_grid_fitting.h:25-132. cloud in the board frame, T_bl in/out, 35 corners appended.
+inline void opt_grid_fitting(typename PointCloud<PoinT>::Ptr& cloud_src, Matrix4d& T_bl, std::vector<Vector3d>& est_pc_corners,
+                             void* viewer = nullptr, rclc_gridfit_report* report = nullptr)
+{
+    (void)viewer;
+    rclc_ctx* ctx = thread_ctx();
+    if (!ctx || !cloud_src || cloud_src->size() == 0) return;
+    const rclc_config& cfg = CfgParam();
+    const int nc = (cfg.board_width - 1) * (cfg.board_height - 1);
+    std::vector<double> corners((size_t)nc * 3);
+    double Tb[16];
+    to_row_major(T_bl, Tb);
+    rclc_gridfit_report rep;
+    if (!ok(rclc_gridfit_solve(ctx, &cfg, cloud_src->points.data(), (int)sizeof(PoinT), 16, (int64_t)cloud_src->size(), Tb, corners.data(), &rep),
+            "opt_grid_fitting"))
+        return;
+    from_row_major(Tb, T_bl);
+    for (int k = 0; k < nc; ++k) est_pc_corners.push_back(Vector3d(corners[3 * k], corners[3 * k + 1], corners[3 * k + 2]));
+    if (report) *report = rep;
+    std::printf("cost: %g --> %g\n", rep.first_initial_cost, rep.last_final_cost);      // opt_grid_fitting.h:112
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BOARD_FITTING_COST — include/opt/board_fitting_cost.h:27-280. The reference builds one functor per target (82) and
+// lets Ceres call Evaluate on each; here the functors of one cloud share a device-resident, binned copy of it, and
+// the first Evaluate at a new (x, y, yaw) runs ONE sweep whose 82 residuals and Jacobian rows serve all of them.
+// ---------------------------------------------------------------------------------------------------------------
+class BoardCloudOnDevice {
+public:
+    explicit BoardCloudOnDevice(typename PointCloud<PoinT>::Ptr cloud)
+    {
+        rclc_ctx* ctx = thread_ctx();
+        const rclc_config& cfg = CfgParam();
+        nt_ = (cfg.board_width - 1) * cfg.board_height + (cfg.board_height - 1) * cfg.board_width;
+        tgt_.resize((size_t)nt_ * 2); is_row_.resize((size_t)nt_);
+        int32_t n = 0;
+        rclc_generate_targets(&cfg, tgt_.data(), is_row_.data(), &n);
+        if (!ctx || !cloud || cloud->size() == 0) return;
+        if (!ok(rclc_batch_create(ctx, &cfg, 1, (int64_t)cloud->size(), &batch_), "BOARD_FITTING_COST (batch)")) { batch_ = nullptr; return; }
+        valid_ = ok(rclc_batch_upload(batch_, 0, cloud->points.data(), (int)sizeof(PoinT), 16, (int64_t)cloud->size()), "upload") &&
+                 ok(rclc_batch_bin(batch_), "bin");
+        res_.assign((size_t)nt_, 0.0); jac_.assign((size_t)nt_ * 3, 0.0);
+    }
+    ~BoardCloudOnDevice() { if (batch_) rclc_batch_destroy(batch_); }
+    int find_target(double x, double y, bool is_row) const
+    {
+        for (int t = 0; t < nt_; ++t)
+            if ((is_row_[(size_t)t] != 0) == is_row && std::fabs(tgt_[2 * (size_t)t] - x) < 1e-9 && std::fabs(tgt_[2 * (size_t)t + 1] - y) < 1e-9) return t;
+        return -1;
+    }
+    bool evaluate(const double pose[3])
+    {
+        if (!valid_) return false;
+        if (have_ && pose[0] == pose_[0] && pose[1] == pose_[1] && pose[2] == pose_[2]) return true;
+        if (!ok(rclc_batch_sweep(batch_, pose), "sweep") || !ok(rclc_batch_read_eval(batch_, res_.data(), jac_.data(), nullptr), "read")) return false;
+        pose_[0] = pose[0]; pose_[1] = pose[1]; pose_[2] = pose[2];
+        have_ = true;
+        return true;
+    }
+    double residual(int t) const { return res_[(size_t)t]; }
+    const double* jacobian(int t) const { return &jac_[(size_t)t * 3]; }
+private:
+    rclc_batch* batch_ = nullptr;
+    bool valid_ = false, have_ = false;
+    int nt_ = 0;
+    double pose_[3] = {0, 0, 0};
+    std::vector<double> tgt_, res_, jac_;
+    std::vector<int32_t> is_row_;
+};
+
+class BOARD_FITTING_COST {          // (with Ceres present, derive from ceres::SizedCostFunction<1, 3>)
+public:
+    virtual ~BOARD_FITTING_COST() {}
+    BOARD_FITTING_COST(Vector3d _target_point, bool _is_row, std::shared_ptr<BoardCloudOnDevice> _cloud)
+        : cloud_(_cloud), target_(_cloud ? _cloud->find_target(_target_point.x(), _target_point.y(), _is_row) : -1) {}
+    // _kdtree of the reference (board_fitting_cost.h:67) has no counterpart: the neighbour test runs on the device.
+    static BOARD_FITTING_COST* Create(Vector3d _target_point, bool _is_row, std::shared_ptr<BoardCloudOnDevice> _cloud_src)
+    {
+        return new BOARD_FITTING_COST(_target_point, _is_row, _cloud_src);
+    }
+    // parameters[0] = {x, y, yaw in degrees}; jacobians / jacobians[0] may be NULL (board_fitting_cost.h:256)
+    virtual bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const
+    {
+        if (!cloud_ || target_ < 0 || !cloud_->evaluate(parameters[0])) { residuals[0] = std::nan(""); return true; }
+        residuals[0] = cloud_->residual(target_);
+        if (jacobians && jacobians[0]) { const double* j = cloud_->jacobian(target_); jacobians[0][0] = j[0]; jacobians[0][1] = j[1]; jacobians[0][2] = j[2]; }
+        return true;            // the reference returns true always (board_fitting_cost.h:261)
+    }
+private:
+    std::shared_ptr<BoardCloudOnDevice> cloud_;
+    int target_;
+};
+
+// pose_reprj_opt — include/opt/opt_reprj_calib.h:21-66. Tcl = (qx, qy, qz, qw, tx, ty, tz) in/out (Calibrate.cpp:59-66).
+inline void pose_reprj_opt(std::vector<std::vector<Vector2d>>& img_norm_points, std::vector<std::vector<Vector3d>>& pc_corner_points, double* Tcl,
+                           bool debug_show = false)
+{
+    rclc_ctx* ctx = thread_ctx();
+    const int F = (int)pc_corner_points.size();
+    if (!ctx || F == 0 || img_norm_points.size() != pc_corner_points.size()) return;
+    const int C = (int)pc_corner_points[0].size();
+    std::vector<double> pc((size_t)F * C * 3), im((size_t)F * C * 2);
+    for (int f = 0; f < F; ++f)
+        for (int k = 0; k < C; ++k) {
+            for (int d = 0; d < 3; ++d) pc[((size_t)f * C + k) * 3 + d] = pc_corner_points[(size_t)f][(size_t)k][d];
+            for (int d = 0; d < 2; ++d) im[((size_t)f * C + k) * 2 + d] = img_norm_points[(size_t)f][(size_t)k][d];
+        }
+    double c0 = 0, c1 = 0;
+    int32_t it = 0;
+    if (ok(rclc_pose_refine(ctx, &CfgParam(), pc.data(), im.data(), F, C, Tcl, &c0, &c1, &it), "pose_reprj_opt") && debug_show)
+        std::printf("pose_reprj_opt: cost %g -> %g in %d iterations\n", c0, c1, it);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// PinholeCam — include/PinholeCam.h:78-110 (projection side only; undistort/remap is image-side OpenCV, out of scope)
+// ---------------------------------------------------------------------------------------------------------------
+class PinholeCam {
+public:
+    int cam_width = 0, cam_height = 0;
+    double fx = 0, fy = 0, cx = 0, cy = 0;
+    PinholeCam() {}
+    PinholeCam(int w, int h, double _fx, double _fy, double _cx, double _cy) : cam_width(w), cam_height(h), fx(_fx), fy(_fy), cx(_cx), cy(_cy) {}
+    Vector2d imgPt2norm(Vector2d& imgPt) { return Vector2d((imgPt.x() - cx) / fx, (imgPt.y() - cy) / fy); }
+    Vector2d normPt2img(Vector3d normPt) { return Vector2d(normPt.x() * fx + cx, normPt.y() * fy + cy); }
+    Vector2d Pt2img(Vector3d Pt)
+    {   // cvRound == lrint under the default rounding mode: ties to even (PinholeCam.h:93-99)
+        return Vector2d((double)std::lrint((Pt.x() / Pt.z()) * fx + cx), (double)std::lrint((Pt.y() / Pt.z()) * fy + cy));
+    }
+    bool is_in_FoV(Vector2d& pt) { return !(pt.x() < 0 || pt.y() < 0 || pt.x() >= cam_width || pt.y() >= cam_height); }
+    void to_config(rclc_config& c) const { c.cam_width = cam_width; c.cam_height = cam_height; c.fx = fx; c.fy = fy; c.cx = cx; c.cy = cy; }
+};
+
+// The colourise loop of apps/Calibrate.cpp:134-148 as one call: transformPointCloud(T_cl) (float) -> Pt2img -> is_in_FoV ->
+// BGR gather. `bgr` is the cv::Mat data pointer of a continuous CV_8UC3 image of cam_width x cam_height.
+inline void colorize_cloud(typename PointCloud<DisplayType>::Ptr& pc_show, const Matrix4f& T_cl, const uint8_t* bgr,
+                           std::vector<uint8_t>* in_fov = nullptr)
+{
+    rclc_ctx* ctx = thread_ctx();
+    if (!ctx || !pc_show || pc_show->size() == 0) return;
+    const int64_t n = (int64_t)pc_show->size();
+    float T[16];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T[r * 4 + c] = T_cl(r, c);
+    std::vector<uint8_t> rgb((size_t)n * 3), fov((size_t)n);
+    std::vector<int32_t> pix((size_t)n * 2);
+    if (!ok(rclc_project_colorize(ctx, &CfgParam(), pc_show->points.data(), (int)sizeof(DisplayType), n, T, bgr, rgb.data(), pix.data(), fov.data()),
+            "colorize_cloud"))
+        return;
+    for (int64_t i = 0; i < n; ++i) {
+        DisplayType& pt = pc_show->points[(size_t)i];
+        // the reference transforms the cloud in place first (Calibrate.cpp:133): x' = m00 x + m01 y + m02 z + m03 in float
+        const float x = pt.x, y = pt.y, z = pt.z;
+        pt.x = ((T[0] * x + T[1] * y) + T[2] * z) + T[3];
+        pt.y = ((T[4] * x + T[5] * y) + T[6] * z) + T[7];
+        pt.z = ((T[8] * x + T[9] * y) + T[10] * z) + T[11];
+        if (!fov[(size_t)i]) continue;
+        pt.r = rgb[3 * (size_t)i]; pt.g = rgb[3 * (size_t)i + 1]; pt.b = rgb[3 * (size_t)i + 2];
+    }
+    if (in_fov) in_fov->swap(fov);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pcl::SACSegmentation<PoinT> as configured at apps/BoardSegmentation.cpp:64-72 (SAC_RANSAC, SACMODEL_PLANE,
+// maxIterations 800, threshold 0.08, defaults: probability 0.99, optimize_coefficients true). PCL's loop is adaptive and
+// sequential; here all hypotheses are scored in one device pass and the loop is replayed on
+// the host over the counts, which selects the same model after the same number of iterations.
+// ---------------------------------------------------------------------------------------------------------------
+class PlaneSegmentation {
+public:
+    void setInputCloud(typename PointCloud<PoinT>::Ptr c) { cloud_ = c; }
+    void setMaxIterations(int n) { max_iterations_ = n; }
+    void setDistanceThreshold(double t) { threshold_ = t; }
+    void setProbability(double p) { probability_ = p; }
+    int iterations() const { return iterations_; }
+
+    // PCL SampleConsensusModel::drawIndexSample: mt19937 seeded 12345 per model object, partial Fisher-Yates on a
+    // persistent index list (the hypotheses are an INPUT of the parity definition: any fixed list is legitimate).
+    static void draw_triplets(int64_t n, int H, std::vector<int32_t>& tri)
+    {
+        std::mt19937 rng(12345u);
+        std::vector<int32_t> idx((size_t)n);
+        for (int64_t i = 0; i < n; ++i) idx[(size_t)i] = (int32_t)i;
+        tri.resize((size_t)H * 3);
+        for (int h = 0; h < H; ++h) {
+            for (int i = 0; i < 3; ++i) { const uint32_t r = rng() >> 1; std::swap(idx[(size_t)i], idx[(size_t)(i + (r % (uint64_t)(n - i)))]); }
+            for (int i = 0; i < 3; ++i) tri[(size_t)h * 3 + i] = idx[(size_t)i];
+        }
+    }
+    // pcl::RandomSampleConsensus::computeModel replayed over per-hypothesis inlier counts; returns the winner or -1
+    static int replay(const std::vector<int32_t>& counts, const std::vector<int32_t>& valid, int64_t n, int max_iterations, double probability,
+                      int* iterations_out)
+    {
+        const int H = (int)counts.size();
+        int best = -INT_MAX, winner = -1, iter = 0, skipped = 0, h = 0;
+        double k = 1.0;
+        const double log_probability = std::log(1.0 - probability);
+        const int max_skip = max_iterations * 10;
+        while (iter < k && skipped < max_skip && h < H) {
+            const int cur = h++;
+            if (!valid[(size_t)cur]) { ++skipped; continue; }
+            if (counts[(size_t)cur] > best) {
+                best = counts[(size_t)cur]; winner = cur;
+                const double w = (double)best / (double)n;
+                double p_no_outliers = 1.0 - w * w * w;
+                p_no_outliers = std::max(std::numeric_limits<double>::epsilon(), p_no_outliers);
+                p_no_outliers = std::min(1.0 - std::numeric_limits<double>::epsilon(), p_no_outliers);
+                k = log_probability / std::log(p_no_outliers);
+            }
+            ++iter;
+            if (iter > max_iterations) break;
+        }
+        if (iterations_out) *iterations_out = iter;
+        return winner;
+    }
+    void segment(PointIndices& inliers, ModelCoefficients& model_coefficients)
+    {
+        inliers.indices.clear(); model_coefficients.values.clear();
+        rclc_ctx* ctx = thread_ctx();
+        if (!ctx || !cloud_ || cloud_->size() < 3) return;
+        const int64_t n = (int64_t)cloud_->size();
+        const int H = max_iterations_ + 1;
+        std::vector<int32_t> tri;
+        draw_triplets(n, H, tri);
+        std::vector<float> planes((size_t)H * 4);
+        std::vector<int32_t> valid((size_t)H), counts((size_t)H);
+        if (!ok(rclc_ransac_plane_score(ctx, cloud_->points.data(), (int)sizeof(PoinT), n, tri.data(), H, threshold_, planes.data(), valid.data(), counts.data()),
+                "SACSegmentation::segment (score)"))
+            return;
+        const int win = replay(counts, valid, n, max_iterations_, probability_, &iterations_);
+        if (win < 0) return;
+        std::vector<uint8_t> mask((size_t)n);
+        float refined[4], centroid[3];
+        int64_t n_in = 0;
+        if (!ok(rclc_ransac_plane_select(ctx, cloud_->points.data(), (int)sizeof(PoinT), n, &planes[(size_t)win * 4], threshold_, mask.data(), refined, centroid, &n_in),
+                "SACSegmentation::segment (select)"))
+            return;
+        // SACSegmentation::segment re-selects the inliers with the optimised coefficients (Appendix A)
+        float unused4[4], unused3[3];
+        if (!ok(rclc_ransac_plane_select(ctx, cloud_->points.data(), (int)sizeof(PoinT), n, refined, threshold_, mask.data(), unused4, unused3, &n_in),
+                "SACSegmentation::segment (re-select)"))
+            return;
+        for (int64_t i = 0; i < n; ++i) if (mask[(size_t)i]) inliers.indices.push_back((int)i);
+        model_coefficients.values.assign(refined, refined + 4);
+    }
+private:
+    typename PointCloud<PoinT>::Ptr cloud_;
+    int max_iterations_ = 800, iterations_ = 0;
+    double threshold_ = 0.08, probability_ = 0.99;
+};
+
+}  // namespace rclc_b200
+#endif  // RCLC_OPS_HPP

@@ -105,3 +105,51 @@ def frustum_cloud(n, seed, zmin=1.0, zmax=100.0, half_fov_x=0.9, half_fov_y=0.6)
 def noise_image(seed, W=1920, H=1080):
     rng = np.random.default_rng(seed)
     return rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+
+
+def _rot_xyz(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def std_corners(W=8, H=6, side=0.1):
+    """utils.h:47-66 calc_transfered_standard_corners lattice (board frame, z = 0), row-major over (H-1) x (W-1)."""
+    fcx, fcy = float((W - 1) // 2) * side, float((H - 1) // 2) * side
+    return np.array([[fcx - c * side, fcy - r * side, 0.0] for r in range(H - 1) for c in range(W - 1)])
+
+
+def calib_frame(f, n_pts, seed0=5000, W=8, H=6, side=0.1, pattern="rosette", pix_sigma=1e-4, T_cl_gt=None):
+    """One frame of BASELINE config 4 (batch calibration), addressed by its GLOBAL index f so that any rank can generate
+    exactly its shard: the board-only cloud in its approximate board frame, T_bl (laser -> approximate board frame, the input
+    of opt_grid_fitting), the true laser-frame corners, and the normalised image corners seen through the ground-truth
+    extrinsic T_cl_gt (camera <- laser) with a little pixel noise."""
+    rng = np.random.default_rng(seed0 + f)
+    pert = (rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01), rng.uniform(-0.8, 0.8))
+    cloud = board_frame_cloud(n_pts, seed0 + f, W, H, side, pert, pattern=pattern)
+    # approximate board frame b' -> laser: the board 3.5-5.5 m down the lidar x axis, facing it, tilted a little
+    R_lb = _rot_xyz(np.deg2rad(rng.uniform(-10, 10)), np.deg2rad(rng.uniform(-20, 20)), np.deg2rad(rng.uniform(-20, 20))) @ \
+        np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+    T_lb = np.eye(4); T_lb[:3, :3] = R_lb; T_lb[:3, 3] = [rng.uniform(3.5, 5.5), rng.uniform(-0.5, 0.5), rng.uniform(-0.3, 0.3)]
+    T_bl = np.linalg.inv(T_lb)
+    # true board frame b from b': p_b = Rz(yaw) (p_b' + t)   (board_fitting_cost.h:132-133)
+    th = np.deg2rad(pert[2])
+    T_b_bp = np.eye(4); T_b_bp[:2, :2] = [[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]]
+    T_b_bp[:3, 3] = T_b_bp[:3, :3] @ np.array([pert[0], pert[1], 0.0])
+    c_std = np.c_[std_corners(W, H, side), np.ones((W - 1) * (H - 1))]
+    corners_l = (T_lb @ np.linalg.inv(T_b_bp) @ c_std.T).T[:, :3]
+    if T_cl_gt is None:
+        T_cl_gt = gt_extrinsic()
+    P = (T_cl_gt[:3, :3] @ corners_l.T).T + T_cl_gt[:3, 3]
+    img_norm = P[:, :2] / P[:, 2:3] + rng.normal(0.0, pix_sigma, (len(P), 2))
+    return cloud, T_bl, corners_l, img_norm
+
+
+def gt_extrinsic():
+    """Ground-truth camera <- laser transform of the synthetic rig: the camera looks down the lidar's +x axis."""
+    T = np.eye(4)
+    T[:3, :3] = _rot_xyz(np.deg2rad(1.5), np.deg2rad(-2.0), np.deg2rad(0.8)) @ np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])
+    T[:3, 3] = [0.06, -0.04, 0.03]
+    return T

@@ -3,7 +3,7 @@
  *
  * The reference (zhijianglu/RCLC) has no plugin/FFI layer: its operators are header-inline C++
  * with PCL/Eigen/Ceres types in the signatures. Each entry point below replaces
- * one of those operators with plain pointers and sizes; the C++ shims in rclc_b200/host/ give them
+ * one of those operators with plain pointers and sizes; the C++ operator surface in include/rclc_ops.hpp gives them
  * back the reference's names and argument meaning (INTEGRATION.md shows the binding).
  *
  * Conventions

@@ -5,7 +5,7 @@
 // Appendix A): SampleConsensusModelPlane::computeModelCoefficients for every sample triplet,
 // countWithinDistance for every hypothesis (K1), then selectWithinDistance + the centroid/covariance
 // reduction of optimizeModelCoefficients for the chosen model (K2). PCL's adaptive, sequential stopping
-// rule is replayed on the host over the device-computed counts (rclc_b200/host/rclc_shims.hpp).
+// rule is replayed on the host over the device-computed counts (include/rclc_ops.hpp, PlaneSegmentation::replay).
 //
 // Everything that decides an inlier is float arithmetic in PCL's (Eigen SSE2) association order with
 // no FMA contraction, so masks and counts are bit-exact for a given hypothesis set.

@@ -1584,24 +1584,32 @@ static int launch_move(rclc_batch* b, GroupRun& gr)
 {
     gr.v.list_parity = gr.round & 1;
     const int64_t rows = gr.v.frame_stride / 32;
-    k_move<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, 444)), (unsigned)std::min(kBinGridY, gr.nf)), kBoxThreads, 0, gr.st>>>(gr.v);
+    // (most rounds move nothing: a small grid keeps the idle launch cheap; a real move still gets ~2400 warps)
+    k_move<<<dim3((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, b->ctx->sm_count)), (unsigned)std::min(kBinGridY, gr.nf)), kBoxThreads, 0, gr.st>>>(gr.v);
     b->ctx->launches += 1;
     gr.round++;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
 }
 
-// One warp per (target, part); parts chosen so that the frames in flight fill the GPU about twice over.
-static int sweep_parts(const rclc_batch* b, int n_frames)
+// One warp per (target, part). Tasks are latency-heavy at both ends (cell and box look-ups, the final reduction), so fewer
+// and longer tasks win: measured on B200 the best split keeps about 0.55 x the resident warp slots busy (~11 warps per SM),
+// i.e. parts = 1 from 20 active 8x6 frames up and 8 for a single one (profiles/r01_sweep_history.md).
+// Inside the solve (fused LM step) a finer split is better: a frame's LM step starts when its last task ends, and short
+// tasks let the first frames' LM steps overlap the sweeping of the later ones (measured: 20.7 vs 22.7 ms per 20-frame step).
+static int sweep_parts(const rclc_batch* b, int n_frames, bool fused)
 {
-    const int64_t slots = (int64_t)b->ctx->sm_count * 20;              // resident warps (5 CTAs of 4 warps per SM)
-    const int64_t tasks = (int64_t)n_frames * b->v.geom.nt;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(8, (2 * slots + tasks - 1) / tasks));
+    const double slots = (double)b->ctx->sm_count * 20.0;              // resident warps (5 CTAs of 4 warps per SM)
+    const double tasks = (double)std::max(n_frames, 1) * b->v.geom.nt;
+    static const int forced = [] { const char* e = std::getenv("RCLC_SWEEP_PARTS"); return e ? atoi(e) : 0; }();
+    if (forced > 0) return forced;
+    if (fused) return (int)std::max(1.0, std::min(8.0, std::ceil(2.0 * slots / tasks)));
+    return (int)std::max(1.0, std::min(8.0, std::floor(0.55 * slots / tasks + 0.5)));
 }
 
 static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames, cudaStream_t st, int frames_in_flight)
 {
-    v.parts = sweep_parts(b, frames_in_flight);
+    v.parts = sweep_parts(b, frames_in_flight, v.fuse_lm != 0);
     const int gx = (v.geom.nt * v.parts + kSweepWarps - 1) / kSweepWarps;
     k_sweep<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
     b->ctx->launches += 1;
@@ -1876,6 +1884,9 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     static const bool prof = [] { const char* e = std::getenv("RCLC_PROFILE_ROUNDS"); return e && e[0] == '1'; }();
     static const bool lm_separate = [] { const char* e = std::getenv("RCLC_LM_SEPARATE"); return e && e[0] == '1'; }();
     std::vector<cudaEvent_t> evs, evs_lm;
+    int active_est = F;            // frames still solving, as of the last poll: sizes the sweep's task split
+    static const int fused_mode = [] { const char* e = std::getenv("RCLC_FUSED_PARTS_MODE"); return e ? atoi(e) : 0; }();
+    int fused_frames = F;
     for (;;) {
         for (int r = 0; r < rounds_per_check; ++r) {
             for (int gi = 0; gi < G; ++gi) {
@@ -1887,12 +1898,12 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
                 if (pg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, gr.st); evs.push_back(e); }
                 if (lm_separate) {
                     gr.v.fuse_lm = 0;
-                    RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, F));
+                    RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, active_est));
                     if (pg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, gr.st); evs_lm.push_back(e); }
                     k_lm<<<gr.nf, 32, 0, gr.st>>>(gr.v);
                     ctx->launches += 1;
                 } else {
-                    RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, F));      // sweep + fused LM step (last warp per frame)
+                    RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, fused_frames));      // sweep + fused LM step (last warp per frame)
                 }
             }
         }
@@ -1905,6 +1916,8 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
         RCLC_CUDA(cudaMemcpyAsync(h_done, b->v.n_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
         if (*h_done >= F) break;
+        active_est = std::max(1, F - *h_done);
+        if (fused_mode == 1) fused_frames = active_est;
         RCLC_CHECK(rounds < max_rounds, RCLC_ERR_NUMERIC, "grid-fit state machine did not terminate");
     }
     if (prof && evs.size() >= 4) {

@@ -22,7 +22,7 @@ constexpr int kMaxCoarse = 1024;         // lattice cells (kMaxCells bounds cell
 constexpr int kSweepThreads = 128;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kRowList = 256;            // live rows a warp collects before it streams them
-constexpr int kGroupRows = 4;            // rows per TMA group (one mbarrier phase): 4 x 512 B bulk copies
+constexpr int kGroupRows = 4;            // rows per cp.async group (one commit / wait per group)
 constexpr int kRingGroups = 4;           // groups per warp ring (8 KB): one computing, up to three in flight
 constexpr int kFlushRows = 448;          // rows a lane may accumulate before the count riding in the fp64 sum must be split off
 constexpr int kBinThreads = 256;

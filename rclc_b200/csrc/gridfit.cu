@@ -113,7 +113,9 @@ static int build_geom(const rclc_config& c, HostGeom& hg)
     g.ncy = jmax - jmin + 4;
     g.ncells = g.ncx * g.ncy;
     RCLC_CHECK(g.ncells <= kMaxCoarse, RCLC_ERR_UNSUPPORTED, "board too large for the cell table");
-    g.sub = 4;                                  // finest sub-cell sort that fits the shared-memory histograms
+    // sub-cells per axis inside a cell (sort key only): the finer, the tighter the row boxes. RCLC_SUBCELLS overrides.
+    static const int want_sub = [] { const char* e = std::getenv("RCLC_SUBCELLS"); return e ? std::max(1, std::min(16, atoi(e))) : 4; }();
+    g.sub = want_sub;
     while (g.sub > 1 && g.ncells * g.sub * g.sub > kMaxCells) g.sub >>= 1;
     g.nfine = g.ncells * g.sub * g.sub;
     hg.cell_cand.assign((size_t)g.ncells * kCand, -1);
@@ -1744,6 +1746,7 @@ int rclc_batch_destroy(rclc_batch* b)
     if (b->d_pristine) cudaFree(b->d_pristine);
     if (b->v.binned) cudaFree(b->v.binned);
     if (b->d_block) cudaFree(b->d_block);
+    for (cudaGraphExec_t ge : b->round_graphs) cudaGraphExecDestroy(ge);
     delete b;
     return RCLC_OK;
 }
@@ -1887,7 +1890,43 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     int active_est = F;            // frames still solving, as of the last poll: sizes the sweep's task split
     static const int fused_mode = [] { const char* e = std::getenv("RCLC_FUSED_PARTS_MODE"); return e ? atoi(e) : 0; }();
     int fused_frames = F;
+    // After the first batch of rounds (which holds the counting sort) every batch is the same 24 x {k_move, k_sweep} per group:
+    // captured once per batch object into a CUDA graph, which removes most of the launch gaps between these short kernels.
+    static const bool use_graphs = [] { const char* e = std::getenv("RCLC_NO_GRAPHS"); return !(e && e[0] == '1'); }() ;
+    const bool graphs_ok = use_graphs && !prof && !lm_separate && (rounds_per_check % 2 == 0);
+    if (graphs_ok && b->graphs_groups != G) {
+        for (cudaGraphExec_t ge : b->round_graphs) cudaGraphExecDestroy(ge);
+        b->round_graphs.clear();
+        b->graphs_groups = 0;
+    }
     for (;;) {
+        if (graphs_ok && rounds > 0) {
+            if (b->round_graphs.empty()) {
+                for (int gi = 0; gi < G; ++gi) {
+                    GroupRun gr = groups[gi];                   // a copy: capturing must not advance the real round counters
+                    cudaGraph_t graph = nullptr;
+                    RCLC_CUDA(cudaStreamBeginCapture(gr.st, cudaStreamCaptureModeThreadLocal));
+                    int rc_cap = RCLC_OK;
+                    for (int r = 0; r < rounds_per_check && rc_cap == RCLC_OK; ++r) {
+                        rc_cap = launch_move(b, gr);
+                        if (rc_cap == RCLC_OK) rc_cap = launch_sweep_view(b, gr.v, gr.nf, gr.st, F);
+                    }
+                    RCLC_CUDA(cudaStreamEndCapture(gr.st, &graph));
+                    RCLC_TRY(rc_cap);
+                    cudaGraphExec_t ge = nullptr;
+                    RCLC_CUDA(cudaGraphInstantiate(&ge, graph, 0));
+                    cudaGraphDestroy(graph);
+                    b->round_graphs.push_back(ge);
+                    ctx->launches -= 2 * rounds_per_check;      // (counted when the graph is launched)
+                }
+                b->graphs_groups = G;
+            }
+            for (int gi = 0; gi < G; ++gi) {
+                RCLC_CUDA(cudaGraphLaunch(b->round_graphs[gi], groups[gi].st));
+                groups[gi].round += rounds_per_check;
+                ctx->launches += 2 * rounds_per_check;
+            }
+        } else
         for (int r = 0; r < rounds_per_check; ++r) {
             for (int gi = 0; gi < G; ++gi) {
                 GroupRun& gr = groups[gi];

@@ -16,14 +16,14 @@
 namespace rclc {
 
 constexpr int kMaxTargets = 1024;
-constexpr int kMaxCells = 4096;
+constexpr int kMaxCells = 65536;          // (cell, sub-cell) bins per frame: global histograms
 constexpr int kCand = 8;                 // candidate targets per cell
 constexpr int kMaxCoarse = 1024;         // lattice cells (kMaxCells bounds cells x sub-cells)
 constexpr int kSweepThreads = 128;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kRowList = 256;            // live rows a warp collects before it streams them
 constexpr int kGroupRows = 4;            // rows per cp.async group (one commit / wait per group)
-constexpr int kRingGroups = 4;           // groups per warp ring (8 KB): one computing, up to three in flight
+constexpr int kRingGroups = 4;           // groups per warp ring (8 KB): one computing, up to three in flight (8 groups measured no faster)
 constexpr int kFlushRows = 448;          // rows a lane may accumulate before the count riding in the fp64 sum must be split off
 constexpr int kBinThreads = 256;
 constexpr int kBinP = 8;
@@ -140,6 +140,9 @@ struct rclc_batch {
     int64_t* d_npts = nullptr;
     bool binned_valid = false;
     int round = 0;                    // parity of the re-bin list the next round consumes
+    // one instantiated CUDA graph per solve group: 24 rounds of {k_move, k_sweep} (the steady state of the solve)
+    std::vector<cudaGraphExec_t> round_graphs;
+    int graphs_groups = 0;
     bool sweep_exact = false;         // RCLC_SWEEP_EXACT=1: run the all-fp64 v1 sweep (debug / A-B reference)
     // GMM scratch
     double* d_gmm = nullptr;

@@ -277,7 +277,8 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": F, "pts_per_frame": args.pts,
-                       "l2": "working set 3 x %d MB per GPU exceeds the 126 MB L2; no flush between steps" % (total_pts * 16 // 2**20)},
+                       "l2": "steps: working set 2 x %d MB per GPU exceeds the 126 MB L2, no flush between steps; roofline launches: "
+                             "L2 flushed before each" % (total_pts * 16 // 2**20)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": ms_e / args.steps},

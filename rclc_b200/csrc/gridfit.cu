@@ -7,17 +7,20 @@
 //   opt_grid_fitting outer re-linearisation loop     include/opt/opt_grid_fitting.h:60-131
 //   generate_std_corners / SE2_to_SE3 / calc_transfered_standard_corners   include/utils.h:286-316, 273-284, 47-66
 //
-// Kernels (one launch covers every active frame of the batch; blockIdx.y = frame):
-//   k_count / k_scatter  move the cloud by the last solved SE(2) (float, like pcl::transformPointCloud)
-//                        and counting-sort it into lattice cells with exact per-point neighbour masks
-//   k_sweep              streams 16 B/point, accumulates the 16 sums of every target (HBM-bound)
-//   k_lm                 residuals + heuristic Jacobian + Huber corrector + 3x3 normal equations and the
-//                        Ceres LM accept/reject/radius state machine; also the outer loop bookkeeping
+// Kernels (one launch covers every frame of a group):
+//   k_count / k_scatter / k_rowbox   once per solve: counting sort of the cloud into lattice cells and sub-cells (warp-
+//                        aggregated atomics), cell table, sentinels, bounding box of every 32-point row
+//   k_move               every later outer iteration: moves the SORTED points in place by the solved SE(2) (float, like
+//                        pcl::transformPointCloud) and refreshes the row boxes
+//   k_sweep              the hot loop: one warp per (frame, target), gathers the rows its discs can touch, accumulates the
+//                        target's 16 sums (16 B per point and pose); its last warps turn the sums into residuals, heuristic
+//                        Jacobian, Huber corrector and 3x3 normal equations and run the Ceres LM accept/reject/radius state
+//                        machine plus the outer loop bookkeeping (lm_frame_step / lm_advance)
 //
-// Arithmetic that decides class membership is done exactly as the reference does it (double maths on
-// float-stored points, explicit _rn intrinsics so nvcc cannot contract a*b+c into an FMA the x86
-// reference build does not use). Sums of float intensities in double are exact for realistic data, so
-// the accumulator tables do not depend on summation order.
+// Arithmetic that decides class membership is done exactly as the reference does it wherever the fast fp32 evaluation is
+// within its error bound of a decision boundary (double maths on float-stored points, explicit _rn intrinsics so nvcc cannot
+// contract a*b+c into an FMA the x86 reference build does not use). Sums of float intensities in double are exact for
+// realistic data, so the accumulator tables do not depend on summation order.
 #include "gridfit.cuh"
 
 #include <algorithm>
@@ -35,7 +38,6 @@ struct HostGeom {
     std::vector<double2> tgt_xy;
     std::vector<float2> tgt_xyf;
     std::vector<uint8_t> is_row;
-    std::vector<int16_t> cell_cand;
 };
 
 // include/utils.h:286-316 — same expressions, same order, so the doubles are bit-identical.
@@ -87,13 +89,12 @@ static int build_geom(const rclc_config& c, HostGeom& hg)
     g.function_tol = c.gridfit_function_tol;
     g.max_lm_iters = c.gridfit_max_lm_iters;
     g.max_iter_time = c.max_iter_time;
-    // Lattice: all targets sit on odd-parity sites of the half-square lattice (unit g = side/2). The
-    // candidate enumeration below needs every target outside a cell's 4x4 site window to be farther
-    // than the kd-tree radius from any point of the cell: 2 g > neighbour_radius.
+    // Lattice: all targets sit on sites of the half-square lattice (unit g = side/2); its cells are the coarse sort key.
     g.g = c.gride_side_length / 2.0;
     g.inv_g = 1.0 / g.g;
-    RCLC_CHECK(neighbour_radius < 1.98 * g.g, RCLC_ERR_UNSUPPORTED,
-               "neighbour_radius_rate must be < 0.99 (cell candidate window)");
+    // The lattice box keeps a margin of 2 cells around the outermost targets; points outside it are dropped, which is exact
+    // only while no dropped point can be a kd-tree neighbour of a target (board_fitting_cost.h:273).
+    RCLC_CHECK(neighbour_radius < 1.98 * g.g, RCLC_ERR_UNSUPPORTED, "neighbour_radius_rate must be < 0.99 (lattice margin)");
     RCLC_CHECK(c.uniform_sampling_radius == 0.0, RCLC_ERR_UNSUPPORTED,
                "uniform_sampling_radius != 0 is not implemented on device (shipped config uses 0)");
     int imin = INT32_MAX, imax = INT32_MIN, jmin = INT32_MAX, jmax = INT32_MIN;
@@ -118,18 +119,6 @@ static int build_geom(const rclc_config& c, HostGeom& hg)
     g.sub = want_sub;
     while (g.sub > 1 && g.ncells * g.sub * g.sub > kMaxCells) g.sub >>= 1;
     g.nfine = g.ncells * g.sub * g.sub;
-    hg.cell_cand.assign((size_t)g.ncells * kCand, -1);
-    for (int b = 0; b < g.ncy; ++b)
-        for (int a = 0; a < g.ncx; ++a) {
-            const int ia = g.i0 + a, ja = g.j0 + b;     // cell spans sites [ia, ia+1] x [ja, ja+1]
-            int k = 0;
-            for (int t = 0; t < g.nt; ++t) {
-                const int di = si[t] - ia, dj = sj[t] - ja;
-                if (di < -1 || di > 2 || dj < -1 || dj > 2) continue;
-                RCLC_CHECK(k < kCand, RCLC_ERR_UNSUPPORTED, "more than 8 candidate targets per cell");
-                hg.cell_cand[((size_t)b * g.ncx + a) * kCand + k++] = (int16_t)t;
-            }
-        }
     return RCLC_OK;
 }
 
@@ -275,7 +264,6 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
 // k_count / k_scatter: move (float) + counting sort by lattice cell. Grid-stride over chunks so that the
 // (frequent) launches in which no frame needs a re-bin cost only a few hundred early-exit CTAs.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBinGridX = 128;
 
 // A cell's segment of `binned` is padded to a multiple of 32 points with sentinels that are far outside every
 // disc for every pose, so the sweep needs no tail predicate and a 32-point row never mixes two cells.
@@ -405,7 +393,7 @@ __device__ __forceinline__ void k_count_frame(const BatchView& bv, int f)
 }
 
 // Pass 2: move the points for good (pcl::transformPointCloud restated in float), drop each one into the next free slot of
-// its bin (warp-aggregated atomics on the bin cursors) together with its exact kd-tree neighbour mask.
+// its bin (warp-aggregated atomics on the bin cursors) together with its z (the kd-tree neighbour test needs it).
 __global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
 {
     const int n_list = bv.rebin_cnt[bv.list_parity];
@@ -1005,32 +993,7 @@ __device__ __forceinline__ void store_totals(double* o, double tI, double dI, do
     o[12] = dN - cdN; o[13] = (tN - dN) - (cN - cdN); o[14] = (tN - rN) - (cN - crN); o[15] = rN - crN;
 }
 
-// ---- mbarrier / TMA bulk copy (PTX) ----
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile("{\n\t"
-                 ".reg .pred p;\n\t"
-                 "WAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@p bra DONE_%=;\n\t"
-                 "bra WAIT_%=;\n\t"
-                 "DONE_%=:\n\t"
-                 "}" ::"r"(bar), "r"(parity) : "memory");
-}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr)
 {
     float4 v;
@@ -1698,7 +1661,7 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     const size_t o_cstart = take(F * ncell * 4), o_ccnt = take(F * ncell * 4), o_box = take(F * (size_t)(v.frame_stride / 32) * 16);
     const size_t o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
     const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_bdone = take(F * 4), o_rlist = take(2 * F * 4), o_rcnt = take(256), o_terms = take(F * nt * 12 * 8), o_tdone = take(F * nt * 4), o_txy = take(nt * 16), o_txyf = take(nt * 8);
-    const size_t o_row = take(nt), o_cand = take(ncell * kCand * 2), o_eval = take(F * nt * 4 * 8);
+    const size_t o_row = take(nt), o_eval = take(F * nt * 4 * 8);
     const size_t o_corn = take(F * (size_t)hg.g.nc * 3 * 8), o_gmm = take(F * 64 * 8 + 4096 * 8 * 8);
     if (cudaMalloc(&b->d_block, off) != cudaSuccess) return fail("cudaMalloc block");
     char* base = static_cast<char*>(b->d_block);
@@ -1725,14 +1688,12 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.tgt_xy = reinterpret_cast<double2*>(base + o_txy);
     v.tgt_xyf = reinterpret_cast<float2*>(base + o_txyf);
     v.tgt_is_row = reinterpret_cast<uint8_t*>(base + o_row);
-    v.cell_cand = reinterpret_cast<int16_t*>(base + o_cand);
     v.eval_out = reinterpret_cast<double*>(base + o_eval);
     v.corners = reinterpret_cast<double*>(base + o_corn);
     b->d_gmm = reinterpret_cast<double*>(base + o_gmm);
     cudaMemcpyAsync(base + o_txy, hg.tgt_xy.data(), nt * 16, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(base + o_txyf, hg.tgt_xyf.data(), nt * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(base + o_row, hg.is_row.data(), nt, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(base + o_cand, hg.cell_cand.data(), ncell * kCand * 2, cudaMemcpyHostToDevice, ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail("batch setup copies");
     *out = b;
     return RCLC_OK;

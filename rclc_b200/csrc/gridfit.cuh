@@ -4,9 +4,8 @@
 // kd-tree neighbour copy (board_fitting_cost.h:124-210, 3.3*N point visits per sweep, fp64). Here a
 // frame's points are counting-sorted ONCE per outer iteration into the cells of the half-square
 // lattice on which all targets sit (and, inside a cell, into 4x4 sub-cells, so that 32 consecutive
-// points — a "row" — are spatial neighbours); a cell has at most 8 candidate targets, and each point
-// carries an 8-bit mask of exact (FLANN-equivalent) neighbour membership. Every cell's segment is
-// padded to a multiple of 32 points with far-away sentinels, and every row has a bounding box.
+// points — a "row" — are spatial neighbours). Every cell's segment is padded to a multiple of 32
+// points with far-away sentinels, and every row has a bounding box.
 // A sweep is a GATHER: one warp owns one target of one frame, pulls in exactly the rows whose box
 // touches the target's discs (as moved by the trial pose) with float4 loads, keeps the target's six
 // sums in registers and writes the target's 16 accumulators once — no atomics in the hot loop.
@@ -17,7 +16,6 @@ namespace rclc {
 
 constexpr int kMaxTargets = 1024;
 constexpr int kMaxCells = 65536;          // (cell, sub-cell) bins per frame: global histograms
-constexpr int kCand = 8;                 // candidate targets per cell
 constexpr int kMaxCoarse = 1024;         // lattice cells (kMaxCells bounds cells x sub-cells)
 constexpr int kSweepThreads = 128;
 constexpr int kSweepWarps = kSweepThreads / 32;
@@ -121,7 +119,6 @@ struct BatchView {
     const double2* tgt_xy;         // [nt]
     const float2* tgt_xyf;         // [nt] (float)target  (FLANN query point)
     const uint8_t* tgt_is_row;     // [nt]
-    const int16_t* cell_cand;      // [ncells][8] target index or -1
     double* eval_out;              // [F][nt][4] residual, j0, j1, j2 (rclc_batch_read_eval)
     double* corners;               // [F][nc][3]
 };

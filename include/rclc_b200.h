@@ -107,6 +107,10 @@ int rclc_gmm_fit_1d(rclc_ctx* ctx, const void* intensity, int stride, int64_t n,
 
 /* ---- pc_plane_prj (pc_process.h:41-57), in place ---- */
 int rclc_plane_project(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const double plane[4]);
+/* ---- pc_plane_fitting (opt_plane_param.hpp:45-88): Huber-robust plane (a,b,c,d) through the points with intensity >=
+ * cfg->plane_reflactive_thd, Ceres LM from (0.1, 0.1, 1, 1). iterations / n_used may be NULL. ---- */
+int rclc_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
+                   int32_t* iterations, int64_t* n_used);
 /* ---- pcl::transformPointCloud(Matrix4f) in place, row-major T ---- */
 int rclc_transform_cloud(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const float T[16]);
 

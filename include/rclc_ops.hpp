@@ -9,6 +9,7 @@
 //   ---------------------------------------------------------------------------------------------------------
 //   GMMFit::fit_1d                       include/GMMFit.h:31                rclc_gmm_fit_1d
 //   pc_plane_prj                         include/pc_process.h:41            rclc_plane_project
+//   pc_plane_fitting                     include/opt/opt_plane_param.hpp:45 rclc_plane_fit
 //   opt_grid_fitting                     include/opt/opt_grid_fitting.h:25  rclc_gridfit_solve
 //   BOARD_FITTING_COST::Create/Evaluate  include/opt/board_fitting_cost.h:64-78   rclc_batch_* (one sweep serves all 82 functors)
 //   pose_reprj_opt                       include/opt/opt_reprj_calib.h:21   rclc_pose_refine
@@ -176,6 +177,23 @@ inline void pc_plane_prj(typename PointCloud<PoinT>::Ptr& Points, Vector4d& plan
     if (!ctx || !Points || Points->size() == 0) return;
     const double plane[4] = {plane_param_l.x(), plane_param_l.y(), plane_param_l.z(), plane_param_l.w()};
     ok(rclc_plane_project(ctx, Points->points.data(), (int)sizeof(PoinT), (int64_t)Points->size(), plane), "pc_plane_prj");
+}
+
+// pc_plane_fitting — include/opt/opt_plane_param.hpp:45-88: Huber(0.1)-robust plane through the points whose intensity is at
+// least reflactive_thd (default 100, as there); param = (a, b, c, d), not normalised. Always returns 0 like the reference.
+inline int pc_plane_fitting(typename PointCloud<PoinT>::Ptr& Points, Vector4d& param, double reflactive_thd = 100)
+{
+    rclc_ctx* ctx = thread_ctx();
+    if (!ctx || !Points) return 0;
+    rclc_config cfg = CfgParam();
+    cfg.plane_reflactive_thd = reflactive_thd;
+    cfg.plane_huber_a = 0.1;                                   // hard-coded at opt_plane_param.hpp:63
+    double abcd[4] = {0.1, 0.1, 1, 1};
+    if (Points->size() > 0)
+        ok(rclc_plane_fit(ctx, &cfg, Points->points.data(), (int)sizeof(PoinT), 16, (int64_t)Points->size(), abcd, nullptr, nullptr),
+           "pc_plane_fitting");
+    param = Vector4d(abcd[0], abcd[1], abcd[2], abcd[3]);
+    return 0;
 }
 
 // opt_grid_fitting — include/opt/opt_grid_fitting.h:25-132. cloud in the board frame, T_bl in/out, 35 corners appended.

@@ -164,6 +164,14 @@ class Context:
         _chk(lib().rclc_plane_project(self.h, _p(pts), stride, C.c_int64(len(pts)), _p(plane)))
         return pts
 
+    def plane_fit(self, cfg, pts):
+        pts, stride, ioff = _cloud(pts)
+        out = np.zeros(4); it = C.c_int32(); nu = C.c_int64()
+        rc = lib().rclc_plane_fit(self.h, C.byref(cfg), _p(pts), stride, ioff, C.c_int64(len(pts)), _p(out), C.byref(it), C.byref(nu))
+        if rc not in (0, 4):
+            _chk(rc)
+        return rc, out, it.value, nu.value
+
     def transform_cloud(self, pts, T):
         pts, stride, _ = _cloud(pts); pts = pts.copy()
         T = np.ascontiguousarray(T, np.float32)

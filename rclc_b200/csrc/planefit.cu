@@ -1,0 +1,291 @@
+// planefit.cu — robust plane fit of the white board points on device (SURVEY.md §8f "next #1").
+//
+// Replaces pc_plane_fitting (include/opt/opt_plane_param.hpp:45-88): one residual per point with intensity >= 100,
+//   r = |a x + b y + c z + d| / sqrt(a^2 + b^2 + c^2)            (PLANE_FITTING_COST, :24-43, evaluated through AutoDiff)
+// each under its own HuberLoss(0.1), parameters (a, b, c, d) from (0.1, 0.1, 1, 1), ceres::Solve with DENSE_QR and
+// otherwise default options (50 iterations, function_tolerance 1e-6). The reference allocates one residual block and one
+// loss object per point; here an evaluation is ONE streaming pass (16 B per point) that reduces the robustified cost and
+// the 4x4 normal equations J'J / J'r, and the last CTA of that pass runs Ceres' trust-region step (the same accept /
+// reject / radius schedule as the grid fit, restated for 4 parameters). The step is solved by Cholesky on the normal
+// equations instead of QR on the stacked Jacobian: the same minimiser of the same damped quadratic.
+#include "common.cuh"
+
+#include <cfloat>
+
+namespace rclc {
+
+constexpr int kPfThreads = 256;
+constexpr int kPfMaxCtas = 592;       // 148 SMs x 4
+constexpr int kPfTerms = 16;          // cost, 10 J'J (upper triangle), 4 J'r, count
+
+struct PlaneLm {
+    // control
+    int phase;                 // 1 evaluate x (initial), 2 evaluate candidate, 3 done
+    int termination;           // 0 convergence, 1 no convergence, 2 failure
+    int iteration, num_iterations, num_consecutive_invalid, reuse_diagonal, step_is_successful;
+    unsigned int counter;      // CTAs of the current pass that have written their partials
+    long long n_used;
+    double eval_x[4];          // where the next pass evaluates
+    double x[4], cand[4], best[4];
+    double x_cost, x_norm, radius, decrease_factor, minimum_cost, initial_cost, min_iter_cost, model_cost_change, gmax;
+    double A[10], g[4], scale[4], diag[4];
+};
+
+struct PlaneEval { double cost; double A[10]; double g[4]; bool valid; };
+
+__device__ bool chol4_solve(const double* A10, const double* l, const double* b, double* y)
+{
+    // A (upper triangle, row-major: 00 01 02 03 11 12 13 22 23 33) + diag(l^2), Cholesky, solve A y = b
+    double M[4][4];
+    int q = 0;
+    for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { M[i][j] = A10[q]; M[j][i] = A10[q]; ++q; }
+    for (int i = 0; i < 4; ++i) M[i][i] += l[i] * l[i];
+    double L[4][4] = {{0}};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = M[i][j];
+            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+            if (i == j) { if (!(s > 0.0)) return false; L[i][i] = sqrt(s); }
+            else L[i][j] = s / L[j][j];
+        }
+    double z[4];
+    for (int i = 0; i < 4; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * z[k]; z[i] = s / L[i][i]; }
+    for (int i = 3; i >= 0; --i) { double s = z[i]; for (int k = i + 1; k < 4; ++k) s -= L[k][i] * y[k]; y[i] = s / L[i][i]; }
+    return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]) && isfinite(y[3]);
+}
+
+__device__ void plane_take_eval(PlaneLm& s, const PlaneEval& e)
+{
+    s.x_cost = e.cost;
+    for (int k = 0; k < 10; ++k) s.A[k] = e.A[k];
+    double gm = 0;
+    for (int k = 0; k < 4; ++k) { s.g[k] = e.g[k]; gm = fmax(gm, fabs(s.x[k] - (s.x[k] + (-e.g[k])))); }
+    s.gmax = gm;
+}
+
+// TrustRegionMinimizer as a resumable state machine (oracle/ceres_lm.hpp documents the published algorithm).
+__device__ void plane_lm_advance(PlaneLm& s, const PlaneEval& e, double ftol, int max_iters)
+{
+    const int diag_idx[4] = {0, 4, 7, 9};
+    bool terminate = false;
+    if (s.phase == 1) {
+        if (!e.valid) { s.termination = 2; s.initial_cost = nan(""); s.min_iter_cost = nan(""); s.phase = 3; return; }
+        plane_take_eval(s, e);
+        for (int k = 0; k < 4; ++k) s.scale[k] = 1.0 / (1.0 + sqrt(e.A[diag_idx[k]]));       // jacobi scaling, once
+        s.initial_cost = s.x_cost; s.min_iter_cost = s.x_cost; s.minimum_cost = DBL_MAX;
+        s.step_is_successful = 1; s.iteration = 0; s.num_iterations = 0; s.radius = 1e4; s.decrease_factor = 2.0;
+        s.reuse_diagonal = 0; s.num_consecutive_invalid = 0;
+        s.x_norm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2] + s.x[3] * s.x[3]);
+    } else {
+        const double cand_cost = e.valid ? e.cost : DBL_MAX;
+        double sn = 0;
+        for (int k = 0; k < 4; ++k) sn += (s.x[k] - s.cand[k]) * (s.x[k] - s.cand[k]);
+        if (sqrt(sn) <= 1e-8 * (s.x_norm + 1e-8)) { s.termination = 0; terminate = true; }
+        else if (fabs(s.x_cost - cand_cost) <= ftol * s.x_cost) { s.termination = 0; terminate = true; }
+        else {
+            const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : (s.x_cost - cand_cost) / s.model_cost_change;
+            if (rel > 1e-3) {
+                for (int k = 0; k < 4; ++k) s.x[k] = s.cand[k];
+                s.x_norm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2] + s.x[3] * s.x[3]);
+                if (!e.valid) { s.termination = 2; terminate = true; }
+                else {
+                    plane_take_eval(s, e);
+                    s.step_is_successful = 1;
+                    const double q = 2.0 * rel - 1.0;
+                    s.radius = fmin(1e16, s.radius / fmax(1.0 / 3.0, 1.0 - q * q * q));
+                    s.decrease_factor = 2.0;
+                    s.reuse_diagonal = 0;
+                    s.min_iter_cost = fmin(s.min_iter_cost, s.x_cost);
+                }
+            } else {
+                s.min_iter_cost = fmin(s.min_iter_cost, cand_cost);
+                s.radius = s.radius / s.decrease_factor;
+                s.decrease_factor *= 2.0;
+                s.reuse_diagonal = 1;
+                s.step_is_successful = 0;
+            }
+        }
+    }
+    while (!terminate) {
+        if (s.step_is_successful && s.x_cost < s.minimum_cost) { s.minimum_cost = s.x_cost; for (int k = 0; k < 4; ++k) s.best[k] = s.x[k]; }
+        s.num_iterations++;
+        if (s.iteration >= max_iters) { s.termination = 1; break; }
+        if (s.step_is_successful && s.gmax <= 1e-10) { s.termination = 0; break; }
+        if (s.radius <= 1e-32) { s.termination = 0; break; }
+        s.iteration++;
+        s.step_is_successful = 0;
+        double As[10], bs[4], l[4], y[4];
+        {
+            int q = 0;
+            for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { As[q] = s.A[q] * s.scale[i] * s.scale[j]; ++q; }
+        }
+        for (int k = 0; k < 4; ++k) bs[k] = s.g[k] * s.scale[k];
+        if (!s.reuse_diagonal) for (int k = 0; k < 4; ++k) s.diag[k] = fmin(fmax(As[diag_idx[k]], 1e-6), 1e32);
+        for (int k = 0; k < 4; ++k) l[k] = sqrt(s.diag[k] / s.radius);
+        bool valid = chol4_solve(As, l, bs, y);
+        s.reuse_diagonal = 1;
+        double step[4], mcc = 0;
+        if (valid) {
+            for (int k = 0; k < 4; ++k) step[k] = -y[k];
+            double M[4][4]; int q = 0;
+            for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { M[i][j] = As[q]; M[j][i] = As[q]; ++q; }
+            double sAs = 0, sb = 0;
+            for (int i = 0; i < 4; ++i) { double r = 0; for (int j = 0; j < 4; ++j) r += M[i][j] * step[j]; sAs += step[i] * r; sb += step[i] * bs[i]; }
+            mcc = -(sb + 0.5 * sAs);                       // -(J step)'(r + J step / 2)
+            valid = mcc > 0.0;
+        }
+        if (!valid) {
+            if (++s.num_consecutive_invalid >= 5) { s.termination = 2; break; }
+            s.radius *= 0.5;
+            s.min_iter_cost = fmin(s.min_iter_cost, s.x_cost);
+            continue;
+        }
+        s.num_consecutive_invalid = 0;
+        s.model_cost_change = mcc;
+        for (int k = 0; k < 4; ++k) { s.cand[k] = s.x[k] + step[k] * s.scale[k]; s.eval_x[k] = s.cand[k]; }
+        s.phase = 2;
+        return;
+    }
+    s.phase = 3;
+}
+
+// One evaluation: cost + normal equations at st->eval_x over the points with intensity >= thd; the last CTA folds the per-CTA
+// partials in a fixed order (deterministic) and advances the LM state.
+__global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restrict__ pts, int64_t n, float thd_lo, double thd, double huber_a,
+                                                           double ftol, int max_iters, PlaneLm* __restrict__ st, double* __restrict__ partials)
+{
+    if (st->phase == 3) return;
+    const double a = st->eval_x[0], b = st->eval_x[1], c = st->eval_x[2], d = st->eval_x[3];
+    const double nn = a * a + b * b + c * c, nrm = sqrt(nn);
+    double acc[kPfTerms];
+#pragma unroll
+    for (int k = 0; k < kPfTerms; ++k) acc[k] = 0.0;
+    bool bad = false;
+    for (int64_t i = blockIdx.x * (int64_t)kPfThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kPfThreads) {
+        const float4 p = __ldg(pts + i);
+        if ((double)p.w < thd) continue;                                   // opt_plane_param.hpp:56 (float < double)
+        const double X = p.x, Y = p.y, Z = p.z;
+        const double e = a * X + b * Y + c * Z + d;
+        double r = fabs(e) / nrm;                                           // :35-38
+        const double sg = (e < 0) ? -1.0 : 1.0, ae = fabs(e);               // ceres abs(Jet): f.a < 0 ? -f : f
+        double j[4] = {(sg * X) / nrm - ae * a / (nn * nrm), (sg * Y) / nrm - ae * b / (nn * nrm), (sg * Z) / nrm - ae * c / (nn * nrm), sg / nrm};
+        if (!isfinite(r) || !isfinite(j[0]) || !isfinite(j[1]) || !isfinite(j[2]) || !isfinite(j[3])) { bad = true; continue; }
+        // HuberLoss + Corrector (rho'' <= 0 branch)
+        const double sq = r * r, bb = huber_a * huber_a;
+        double rho0, rho1;
+        if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
+        else { rho0 = sq; rho1 = 1.0; }
+        const double w = sqrt(rho1);
+        r *= w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) j[k] *= w;
+        acc[0] += 0.5 * rho0;
+        int q = 1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = u; v < 4; ++v) acc[q++] += j[u] * j[v];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[11 + u] += j[u] * r;
+        acc[15] += 1.0;
+    }
+    (void)thd_lo;
+    __shared__ double s_red[kPfThreads / 32][kPfTerms];
+    __shared__ int s_bad, s_last;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if (bad) s_bad = 1;
+#pragma unroll
+    for (int k = 0; k < kPfTerms; ++k) acc[k] = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < kPfTerms; ++k) s_red[threadIdx.x >> 5][k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x < kPfTerms) {
+        double v = 0;
+        for (int w = 0; w < kPfThreads / 32; ++w) v += s_red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * (kPfTerms + 1) + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * (kPfTerms + 1) + kPfTerms] = s_bad ? 1.0 : 0.0;
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    // fold: thread k < 17 sums term k over the CTAs in index order
+    __shared__ double s_tot[kPfTerms + 1];
+    if (threadIdx.x <= kPfTerms) {
+        double v = 0;
+        for (unsigned cta = 0; cta < gridDim.x; ++cta) v += __ldcg(partials + (size_t)cta * (kPfTerms + 1) + threadIdx.x);
+        s_tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->counter = 0;
+        PlaneEval e;
+        e.cost = s_tot[0];
+        for (int k = 0; k < 10; ++k) e.A[k] = s_tot[1 + k];
+        for (int k = 0; k < 4; ++k) e.g[k] = s_tot[11 + k];
+        e.valid = s_tot[kPfTerms] == 0.0;
+        st->n_used = (long long)s_tot[15];
+        PlaneLm s = *st;
+        plane_lm_advance(s, e, ftol, max_iters);
+        *st = s;
+    }
+}
+
+__global__ void k_plane_init(PlaneLm* st)
+{
+    PlaneLm s;
+    memset(&s, 0, sizeof(s));
+    const double x0[4] = {0.1, 0.1, 1.0, 1.0};                                 // opt_plane_param.hpp:49
+    for (int k = 0; k < 4; ++k) { s.x[k] = x0[k]; s.eval_x[k] = x0[k]; s.best[k] = x0[k]; }
+    s.phase = 1;
+    s.termination = 1;
+    *st = s;
+}
+
+} // namespace rclc
+
+using namespace rclc;
+
+extern "C" int rclc_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
+                              int32_t* iterations, int64_t* n_used)
+{
+    RCLC_CHECK(ctx && cfg && pts && plane_out && n > 0, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
+    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, ioff, n, ctx->d_pts.as<float4>()));
+    const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPfThreads * 4 - 1) / (kPfThreads * 4), kPfMaxCtas));
+    RCLC_TRY(ctx->d_tmp.reserve(sizeof(PlaneLm) + 256 + (size_t)kPfMaxCtas * (kPfTerms + 1) * 8));
+    PlaneLm* d_st = ctx->d_tmp.as<PlaneLm>();
+    double* d_part = reinterpret_cast<double*>(ctx->d_tmp.as<char>() + ((sizeof(PlaneLm) + 255) & ~(size_t)255));
+    k_plane_init<<<1, 1, 0, ctx->stream>>>(d_st);
+    ctx->launches += 1;
+    // Ceres defaults for this solve (opt_plane_param.hpp:75-77 sets only DENSE_QR): 50 iterations, function_tolerance 1e-6.
+    const int max_iters = 50;
+    const double ftol = 1e-6;
+    RCLC_TRY(ctx->h_pin2.reserve(sizeof(PlaneLm)));
+    PlaneLm* h = ctx->h_pin2.as<PlaneLm>();
+    const int max_launches = 2 * (max_iters + 8) + 8;
+    int launched = 0;
+    for (;;) {
+        for (int r = 0; r < 8; ++r) {
+            k_plane_eval<<<ctas, kPfThreads, 0, ctx->stream>>>(ctx->d_pts.as<float4>(), n, 0.f, cfg->plane_reflactive_thd, cfg->plane_huber_a, ftol,
+                                                               max_iters, d_st, d_part);
+            ctx->launches += 1;
+        }
+        launched += 8;
+        RCLC_CUDA(cudaGetLastError());
+        RCLC_CUDA(cudaMemcpyAsync(h, d_st, sizeof(PlaneLm), cudaMemcpyDeviceToHost, ctx->stream));
+        RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h->phase == 3) break;
+        RCLC_CHECK(launched < max_launches, RCLC_ERR_NUMERIC, "plane-fit state machine did not terminate");
+    }
+    // solver.cc: the user state is only overwritten when the solution is usable
+    const double x0[4] = {0.1, 0.1, 1.0, 1.0};
+    for (int k = 0; k < 4; ++k) plane_out[k] = h->termination == 2 ? x0[k] : h->best[k];
+    if (iterations) *iterations = h->num_iterations;
+    if (n_used) *n_used = h->n_used;
+    return h->termination == 2 ? RCLC_ERR_NUMERIC : RCLC_OK;
+}

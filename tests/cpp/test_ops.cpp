@@ -101,6 +101,25 @@ int main()
         for (auto& p : pc->points) worst = std::max(worst, std::fabs(0.1 * p.x - 0.05 * p.y + 0.99 * p.z - 3.96));
         CHECK(worst < 1e-5, "distance to plane %g", worst);
     }
+    // ---- pc_plane_fitting: the board plane from the bright points only (the dark ones are displaced on purpose) ----
+    {
+        auto pc = std::make_shared<PointCloud<PoinT>>();
+        std::mt19937 rng(9); std::uniform_real_distribution<double> u(-0.4, 0.4); std::normal_distribution<double> nz(0, 0.003);
+        for (int i = 0; i < 30000; ++i) {
+            PoinT p; p.x = (float)u(rng); p.y = (float)u(rng);
+            const bool bright = (i % 2) == 0;
+            p.z = (float)(4.0 - 0.1 * p.x + 0.2 * p.y + nz(rng) + (bright ? 0.0 : 0.05));
+            p.intensity = bright ? 120.f : 20.f;
+            pc->points.push_back(p);
+        }
+        Vector4d plane;
+        CHECK(pc_plane_fitting(pc, plane) == 0, "return value");
+        const double nrm = std::sqrt(plane.x() * plane.x() + plane.y() * plane.y() + plane.z() * plane.z());
+        const double s = plane.z() < 0 ? -1.0 : 1.0, ref = std::sqrt(0.01 + 0.04 + 1.0);
+        CHECK(std::fabs(s * plane.x() / nrm - 0.1 / ref) < 1e-3 && std::fabs(s * plane.y() / nrm + 0.2 / ref) < 1e-3 &&
+                  std::fabs(s * plane.w() / nrm + 4.0 / ref) < 1e-3,
+              "plane %g %g %g %g", plane.x() / nrm, plane.y() / nrm, plane.z() / nrm, plane.w() / nrm);
+    }
     // ---- PlaneSegmentation (pcl::SACSegmentation drop-in): plane + 30 % outliers ----
     {
         auto pc = std::make_shared<PointCloud<PoinT>>();

@@ -190,6 +190,48 @@ def test_plane_project_and_transform_bit_exact(ctx, oracle):
     assert np.array_equal(ctx.transform_cloud(pts, T3), oracle.transform_cloud(pts, T3))
 
 
+def _tilted_board(n, seed, nrm, dist, sigma=0.004, outliers=0):
+    rng = np.random.default_rng(seed)
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, 0] = rng.uniform(-0.4, 0.4, n); pts[:, 1] = rng.uniform(-0.3, 0.3, n)
+    nrm = np.asarray(nrm, float); nrm = nrm / np.linalg.norm(nrm)
+    pts[:, 2] = (dist - nrm[0] * pts[:, 0] - nrm[1] * pts[:, 1]) / nrm[2] + rng.normal(0, sigma, n)
+    pts[:, 3] = np.where(rng.uniform(size=n) < 0.5, 15, 110)
+    if outliers:
+        k = rng.choice(n, outliers, replace=False)
+        pts[k, 2] += rng.uniform(0.3, 1.0, outliers)
+    return pts, nrm
+
+
+@pytest.mark.parametrize("case", [(20000, 12, (0.15, -0.1, 1.0), 4.0, 0), (300000, 13, (-0.3, 0.2, 1.0), 5.5, 3000),
+                                  (777, 14, (0.0, 0.0, 1.0), 3.0, 20)])
+def test_plane_fit_matches_oracle(ctx, cfg, oracle, ocfg, case):
+    """pc_plane_fitting (opt_plane_param.hpp:45-88): same Ceres trajectory (iteration count) and the same plane; the sums
+    over points are reduced in a different order and the step is solved by Cholesky instead of QR, hence 1e-9."""
+    n, seed, nrm, dist, outl = case
+    pts, _ = _tilted_board(n, seed, nrm, dist, outliers=outl)
+    rc0, p0, it0, used0 = oracle.plane_fit(ocfg, pts)
+    rc1, p1, it1, used1 = ctx.plane_fit(cfg, pts)
+    assert rc1 == rc0 == 0 and used1 == used0 == int((pts[:, 3] >= 100).sum())
+    assert it1 == it0
+    np.testing.assert_allclose(p1, p0, rtol=1e-9, atol=1e-10)
+
+
+def test_plane_fit_pcl_layout_and_degenerate(ctx, cfg, oracle, ocfg):
+    pts, _ = _tilted_board(5000, 15, (0.1, 0.1, 1.0), 4.0)
+    pcl = np.zeros((len(pts), 8), np.float32); pcl[:, :3] = pts[:, :3]; pcl[:, 4] = pts[:, 3]     # PointXYZI: intensity at +16
+    rc0, p0, it0, _ = oracle.plane_fit(ocfg, pts)
+    rc1, p1, it1, _ = ctx.plane_fit(cfg, pcl)
+    assert rc1 == rc0 == 0 and it1 == it0
+    np.testing.assert_allclose(p1, p0, rtol=1e-9, atol=1e-10)
+    # no point passes the reflectance filter: zero residual blocks, the start point comes back in both
+    dark = pts.copy(); dark[:, 3] = 10
+    rc0, p0, _, u0 = oracle.plane_fit(ocfg, dark)
+    rc1, p1, _, u1 = ctx.plane_fit(cfg, dark)
+    assert u0 == u1 == 0 and rc0 == rc1
+    np.testing.assert_array_equal(p1, p0)
+
+
 def test_ransac_counts_masks_bit_exact(ctx, oracle):
     rng = np.random.default_rng(5)
     n = 60000

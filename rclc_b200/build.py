@@ -9,7 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librclc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-fopenmp", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-fopenmp", "-ccbin", "/usr/bin/g++"] + \
+    os.environ.get("RCLC_EXTRA_NVCC_FLAGS", "").split()          # experiments only (e.g. -DRCLC_SWEEP_TIMING)
 
 
 def _stale():

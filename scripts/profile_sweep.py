@@ -14,8 +14,11 @@ for f, p in enumerate(frames):
     b.upload(f, p)
 b.bin()
 poses = np.array(perts)
+ms = []
 for _ in range(reps):
     ctx.flush_l2()
     b.sweep(poses)
-ctx.synchronize()
+    ctx.synchronize()
+    ms.append(ctx.last_sweep_ms())
+print("k_sweep us:", " ".join("%.1f" % (m * 1e3) for m in ms), "median %.1f" % (np.median(ms[2:]) * 1e3))
 print("ok", b.total_points())

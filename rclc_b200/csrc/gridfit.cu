@@ -1249,14 +1249,21 @@ static_assert(kListPad <= 32, "one lane per padding entry");
 __global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
 {
     const int f = blockIdx.y;
-    const FrameCtl& c = bv.ctl[f];
-    if (!c.sweep_active) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int parts = bv.parts;
     const int task = blockIdx.x * kSweepWarps + warp;
     const int t = task / parts, part = task - t * parts;
     if (t >= bv.geom.nt) return;
     const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;      // frame whose points are read
+    // everything the task needs from global memory, requested before the first use
+    const FrameCtl& c = bv.ctl[f];
+    const int active = c.sweep_active;
+    const PoseCoef pc = c.pose;
+    const int use_exact = c.use_exact;
+    const float drift = bv.ctl[fd].drift;
+    const double2 ref = bv.tgt_xy[t];
+    const float2 tq = bv.tgt_xyf[t];
+    if (!active) return;
 
     extern __shared__ __align__(128) unsigned char s_dyn[];
     unsigned char* sp = s_dyn;
@@ -1268,9 +1275,7 @@ __global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
     LmStage* stage = reinterpret_cast<LmStage*>(sp) + warp;
 
     const GridGeom& g = bv.geom;
-    const PoseCoef pc = c.pose;
-    const double2 ref = bv.tgt_xy[t];
-    const bool exact_body = bv.force_exact || c.use_exact;
+    const bool exact_body = bv.force_exact || use_exact;
     // p' = R (p + t)  =>  ref - p' = -R (p - c),  c = R^T ref - t
     const double cxd = pc.r00 * ref.x + pc.r10 * ref.y - pc.tx, cyd = pc.r01 * ref.x + pc.r11 * ref.y - pc.ty;
     const double rgd = sqrt(g.rg2);
@@ -1278,7 +1283,7 @@ __global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
     k.cx = (float)cxd; k.cy = (float)cyd;
     k.r00 = (float)pc.r00; k.r01 = (float)pc.r01; k.r10 = (float)pc.r10; k.r11 = (float)pc.r11;
     k.rg2 = (float)g.rg2; k.rc2 = (float)g.rc2;
-    { const float2 tq = bv.tgt_xyf[t]; k.tqx = tq.x; k.tqy = tq.y; k.rn2 = g.rn2f; }
+    k.tqx = tq.x; k.tqy = tq.y; k.rn2 = g.rn2f;
     {
         // |fp32 offsets - reference's| <= E for every point that can matter (|p - c| <= 2 rg): rounding of c, of p - c, of the
         // 2x2 product, plus the reference's own rounding of R (p + t) at coordinate magnitude Bc
@@ -1304,18 +1309,15 @@ __global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
 
     // ---- cells that can hold a point of the gradient disc: the disc widened by how far points have drifted out of the
     //      cells they were sorted into (in-place moves). Window of nci x ncj cells, normally 3 x 3. ----
-    const double rsel = rgd + (double)bv.ctl[fd].drift + 1e-5;
+    const double rsel = rgd + (double)drift + 1e-5;
     const int ci0 = max((int)floor((cxd - rsel) * g.inv_g) - g.i0, 0), ci1 = min((int)floor((cxd + rsel) * g.inv_g) - g.i0, g.ncx - 1);
     const int cj0 = max((int)floor((cyd - rsel) * g.inv_g) - g.j0, 0), cj1 = min((int)floor((cyd + rsel) * g.inv_g) - g.j0, g.ncy - 1);
     const int nci = min(max(ci1 - ci0 + 1, 0), 32), ncj = max(cj1 - cj0 + 1, 0);      // (a lattice wider than 32 cells under > 0.7 m of drift: not a case)
-    // kd-tree neighbour test needed? (all cells of the window)
+    // kd-tree neighbour test needed? (max z^2 over all cells of the window; reduced once the first cell look-ups are on their way)
     float z2max = 0.f;
     for (int cc = lane; cc < nci * ncj; cc += 32)
         z2max = fmaxf(z2max, __uint_as_float(bv.cellz2[(size_t)fd * g.ncells + (cj0 + cc / nci) * g.ncx + ci0 + cc % nci]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) z2max = fmaxf(z2max, __shfl_xor_sync(0xffffffffu, z2max, o));
-    const bool masked = !((rgf + disp) * (rgf + disp) + z2max < g.rn2f * 0.9999f);
-    const int mode = exact_body ? 2 : (masked ? 1 : 0);
+    int mode = -1;                       // 0 fast, 1 fast with neighbour mask, 2 all-fp64: decided below, once the first cell look-ups are on their way
 
     // lane c looks up cell c of (a slab of) the window: at most 32 cells per pass, one pass for windows up to 5 x 5
     const int rows_per_pass = nci > 0 ? max(32 / nci, 1) : 1;
@@ -1333,11 +1335,30 @@ __global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
                 my_ngr = (my_nrows + 31) >> 5;
             }
         }
-        int my_pre = my_ngr;             // exclusive prefix over the lanes
+        if (mode < 0) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, my_pre, o); if (lane >= o) my_pre += u; }
-        const int n_groups = __shfl_sync(0xffffffffu, my_pre, 31);
-        my_pre -= my_ngr;
+            for (int o = 16; o > 0; o >>= 1) z2max = fmaxf(z2max, __shfl_xor_sync(0xffffffffu, z2max, o));
+            const bool masked = !((rgf + disp) * (rgf + disp) + z2max < g.rn2f * 0.9999f);
+            mode = exact_body ? 2 : (masked ? 1 : 0);
+        }
+        // the window's boxes on their way into L2 (16 B per row): the batches below then wait for L2, not for DRAM
+        for (int i = 0; i * 8 < my_nrows; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(box + my_row0 + i * 8));
+        // Order of the cells = the four parity classes of (ci, cj), one after the other. A cell is wanted by the two targets
+        // on its corners (and grazed by a few more); every one of them reaches it in the same quarter of its own walk, so the
+        // second reader finds the rows in L2 instead of DRAM (measured: DRAM reads 239 -> 166 MB per sweep, L2 hit rate 16 -> 36 %).
+        const int slot = (lane < nci * ncj_p) ? (((ci0 + lane % nci) & 1) | (((cjb + lane / nci) & 1) << 1)) : 4;
+        // exclusive prefix of my_ngr in that order: one scan over four 16-bit fields (a cell has far fewer than 2047 groups)
+        unsigned long long inc = (slot < 4) ? (unsigned long long)my_ngr << (16 * slot) : 0ull;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        const unsigned long long all = __shfl_sync(0xffffffffu, inc, 31);
+        int my_pre = (slot < 4) ? (int)((inc >> (16 * slot)) & 0xffffu) - my_ngr : 0, n_groups = 0;
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+            const int tot_sl = (int)((all >> (16 * sl)) & 0xffffu);
+            if (sl < slot && slot < 4) my_pre += tot_sl;
+            n_groups += tot_sl;
+        }
 
         // ---- this part's 32-row groups, four box loads in flight per lane ----
         for (int v0 = (part - gbase % parts + parts) % parts; v0 < n_groups; v0 += 4 * parts) {

@@ -15,35 +15,25 @@ for _ in range(4):
     ctx.flush_l2(); b.sweep(poses)
 ctx.synchronize()
 print("sweep ms", ctx.last_sweep_ms())
-nt = cfg.n_targets()
-parts = int(os.environ.get("RCLC_SWEEP_PARTS", "1"))
 out = np.zeros((32 * 128 * 8, 12), np.int64)
 capi.lib().rclc_batch_debug_read_terms.argtypes = [C.c_void_p, C.c_void_p]
 rc = capi.lib().rclc_batch_debug_read_terms(b.h, out.ctypes.data_as(C.c_void_p))
 assert rc == 0
-out = out[:F * nt * parts]
-o = out.astype(np.float64)
-nt = nt * parts
+o = out[out[:, 0] != 0].astype(np.float64)
 t0 = o[:, 0].min()
 beg, end = (o[:, 0] - t0) / 1e3, (o[:, 1] - t0) / 1e3
 clk = 1.965e3   # cycles per us (approx)
-def q(x): return "min %.1f p10 %.1f med %.1f p90 %.1f max %.1f" % (x.min(), np.percentile(x, 10), np.median(x), np.percentile(x, 90), x.max())
+def q(x): return "min %.1f p10 %.1f med %.1f p90 %.1f max %.1f sum %.0f" % (x.min(), np.percentile(x, 10), np.median(x), np.percentile(x, 90), x.max(), x.sum())
 print("tasks", len(o), "span us", end.max())
+busy = o[o[:, 7] > 0]
+print("tasks with rows", len(busy))
 print("begin us  ", q(beg)); print("end us    ", q(end)); print("dur us    ", q(end - beg))
-print("dur cyc/us", q(o[:, 2] / clk))
-print("list us   ", q(o[:, 3] / clk)); print("stream us ", q(o[:, 4] / clk))
-print("prologue (consts, smem init) us", q(o[:, 5] / clk)); print("cell look-up + prefix us     ", q(o[:, 7] / clk))
-print("final pump + fold us         ", q(o[:, 8] / clk)); print("epilogue (totals out) us     ", q(o[:, 10] / clk))
-print("rows      ", q(o[:, 6]))
-print("mode counts", np.bincount(o[:, 9].astype(int)))
-print("cyc/row in stream", q(o[:, 4] / np.maximum(o[:, 6], 1)))
-print("other us (dur - list - stream)", q((o[:, 2] - o[:, 3] - o[:, 4]) / clk))
+for name, col in (("setup us", 3), ("stream us", 4), ("fold+atomics us", 5)):
+    print("%-16s" % name, q(busy[:, col] / clk))
+print("rows of cell    ", q(busy[:, 6])); print("row visits      ", q(busy[:, 7])); print("passes          ", q(busy[:, 8]))
+print("cyc per row visit in stream", q(busy[:, 4] / np.maximum(busy[:, 7], 1)))
 sm = o[:, 11].astype(int)
 per_sm = np.bincount(sm, minlength=148)
 print("tasks per SM", q(per_sm.astype(float)))
-# slowest tasks
-idx = np.argsort(end)[-8:]
-for i in idx: print("late task f=%d t=%d beg %.1f end %.1f rows %d list %.1f stream %.1f sm %d (%d tasks)" % (i // nt, i % nt, beg[i], end[i], o[i, 6], o[i, 3] / clk, o[i, 4] / clk, sm[i], per_sm[sm[i]]))
-for n_on in sorted(set(per_sm)): print("SMs with %d tasks: %d, median end %.1f" % (n_on, (per_sm == n_on).sum(), np.median(end[per_sm[sm] == n_on]) if (per_sm[sm] == n_on).any() else 0))
 np.save("gpurun_out/sweep_timeline.npy", out)
 sys.stdout.flush(); os._exit(0)

@@ -1246,7 +1246,10 @@ __global__ void __launch_bounds__(32) k_lm(BatchView bv)
 constexpr size_t kSweepSmem = (size_t)kSweepWarps * (kRingBytes + kListCap * 4 + 16 * 8 + 12 * 8 + sizeof(WarpCtx) + sizeof(LmStage));
 static_assert(kListPad <= 32, "one lane per padding entry");
 
-__global__ void __launch_bounds__(kSweepThreads, 5) k_sweep(BatchView bv)
+// Three CTAs (12 warps) per SM: with 160 registers the hot loop and the cold paths around it keep everything in registers.
+// Measured (20 x 500 k points, one pose): 5 CTAs / 96 registers 63.5 us, 4 / 128 59.4 us, 3 / 160 57.3 us — the single-pose
+// sweep needs only 11 warps per SM, and the 25 MB of spill traffic per launch that ncu showed at 96 registers is gone.
+__global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(BatchView bv)
 {
     const int f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1579,18 +1582,18 @@ static int launch_move(rclc_batch* b, GroupRun& gr)
 }
 
 // One warp per (target, part). Tasks are latency-heavy at both ends (cell and box look-ups, the final reduction), so fewer
-// and longer tasks win: measured on B200 the best split keeps about 0.55 x the resident warp slots busy (~11 warps per SM),
-// i.e. parts = 1 from 20 active 8x6 frames up and 8 for a single one (profiles/r01_sweep_history.md).
+// and longer tasks win: measured on B200 the best split of a plain sweep is parts = 1 from 20 active 8x6 frames up and 8
+// for a single one (profiles/r01_sweep_history.md).
 // Inside the solve (fused LM step) a finer split is better: a frame's LM step starts when its last task ends, and short
-// tasks let the first frames' LM steps overlap the sweeping of the later ones (measured: 20.7 vs 22.7 ms per 20-frame step).
+// tasks let the first frames' LM steps overlap the sweeping of the later ones.
 static int sweep_parts(const rclc_batch* b, int n_frames, bool fused)
 {
-    const double slots = (double)b->ctx->sm_count * 20.0;              // resident warps (5 CTAs of 4 warps per SM)
+    const double slots = (double)b->ctx->sm_count * 12.0;              // resident warps (3 CTAs of 4 warps per SM)
     const double tasks = (double)std::max(n_frames, 1) * b->v.geom.nt;
     static const int forced = [] { const char* e = std::getenv("RCLC_SWEEP_PARTS"); return e ? atoi(e) : 0; }();
     if (forced > 0) return forced;
     if (fused) return (int)std::max(1.0, std::min(8.0, std::ceil(2.0 * slots / tasks)));
-    return (int)std::max(1.0, std::min(8.0, std::floor(0.55 * slots / tasks + 0.5)));
+    return (int)std::max(1.0, std::min(8.0, std::floor(0.9 * slots / tasks + 0.5)));
 }
 
 static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames, cudaStream_t st, int frames_in_flight)

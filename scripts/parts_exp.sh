@@ -1,3 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 120 python scripts/profile_sweep.py 20 500000 6 > gpurun_out/p4.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 3 -c 2 -o gpurun_out/prof_sweep_r01_final2 -f python scripts/profile_sweep.py 20 500000 6 > gpurun_out/ncu_p4.log 2>&1; tail -2 gpurun_out/p4.log
+for G in 3 4; do for P in 1 2 3; do
+  export RCLC_SWEEP_PARTS=$P
+  RCLC_SOLVE_GROUPS=$G timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('G=$G P=$P', round(d['ms_per_step'],2), round(d['e2e']['ms_per_step'],2))"
+done; done

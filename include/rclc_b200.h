@@ -111,6 +111,15 @@ int rclc_plane_project(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const
  * cfg->plane_reflactive_thd, Ceres LM from (0.1, 0.1, 1, 1). iterations / n_used may be NULL. ---- */
 int rclc_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
                    int32_t* iterations, int64_t* n_used);
+/* ---- pcl::UniformSampling (pc_process.h:111-115, apps/BoardSegmentation.cpp:58-61): per voxel of side `leaf` (grid anchored at
+ * the cloud's min corner) the input point nearest the voxel centre. idx_out (room for n) receives the kept point indices in
+ * ascending voxel-key order (PCL's order is its hash map's; the SET is the same). ---- */
+int rclc_uniform_sample(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double leaf, int32_t* idx_out, int64_t* n_out);
+/* ---- pcl::EuclideanClusterExtraction (pc_process.h:62-72, 131-139): connected components of "distance < tol", components with
+ * min_size <= size <= max_size ranked by size descending (ties: smallest member index first). labels_out[i] = rank or -1;
+ * sizes_out (room for n, may be NULL) receives the n_clusters sizes. ---- */
+int rclc_euclidean_cluster(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double tol, int64_t min_size, int64_t max_size,
+                           int32_t* labels_out, int32_t* n_clusters, int32_t* sizes_out);
 /* ---- pcl::transformPointCloud(Matrix4f) in place, row-major T ---- */
 int rclc_transform_cloud(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const float T[16]);
 

@@ -15,6 +15,9 @@
 //   pose_reprj_opt                       include/opt/opt_reprj_calib.h:21   rclc_pose_refine
 //   PinholeCam::{imgPt2norm,normPt2img,Pt2img,is_in_FoV}  include/PinholeCam.h:78-110   (host inline, same arithmetic)
 //   colourise loop                       apps/Calibrate.cpp:134-148         rclc_project_colorize  (colorize_cloud)
+//   pcl::UniformSampling<PoinT>          include/pc_process.h:111-115, apps/BoardSegmentation.cpp:58-61   rclc_uniform_sample  (UniformSampling)
+//   pcl::EuclideanClusterExtraction<PoinT>  include/pc_process.h:62-72, 131-139     rclc_euclidean_cluster  (EuclideanClusterExtraction)
+//   EulerCluster, eular_cluster_iter     include/pc_process.h:59-79, 104-211  (host logic over the two classes above)
 //   pcl::SACSegmentation<>::segment as configured at apps/BoardSegmentation.cpp:64-72
 //                                                                           rclc_ransac_plane_score + host replay of
 //                                                                           PCL's adaptive rule + rclc_ransac_plane_select
@@ -444,6 +447,152 @@ private:
     int max_iterations_ = 800, iterations_ = 0;
     double threshold_ = 0.08, probability_ = 0.99;
 };
+
+// pcl::UniformSampling<PoinT> drop-in (the calls the reference makes: setInputCloud, setRadiusSearch, filter).
+// Output order: ascending voxel key (PCL's is its hash map's iteration order); the kept SET is PCL's.
+class UniformSampling {
+public:
+    void setInputCloud(typename PointCloud<PoinT>::Ptr c) { cloud_ = c; }
+    void setRadiusSearch(double r) { leaf_ = r; }
+    void filter(PointCloud<PoinT>& out)
+    {
+        std::vector<PoinT> kept;
+        rclc_ctx* ctx = thread_ctx();
+        if (ctx && cloud_ && cloud_->size() > 0 && leaf_ > 0) {
+            std::vector<int32_t> idx(cloud_->size());
+            int64_t n_out = 0;
+            if (ok(rclc_uniform_sample(ctx, cloud_->points.data(), (int)sizeof(PoinT), 16, (int64_t)cloud_->size(), leaf_, idx.data(), &n_out), "UniformSampling::filter")) {
+                kept.reserve((size_t)n_out);
+                for (int64_t k = 0; k < n_out; ++k) kept.push_back(cloud_->points[(size_t)idx[(size_t)k]]);
+            }
+        }
+        out.points.assign(kept.begin(), kept.end());      // (out may be the input cloud, as at pc_process.h:115)
+    }
+private:
+    typename PointCloud<PoinT>::Ptr cloud_;
+    double leaf_ = 0;
+};
+
+// pcl::EuclideanClusterExtraction<PoinT> drop-in: clusters ranked by size descending, indices ascending inside a cluster.
+class EuclideanClusterExtraction {
+public:
+    void setInputCloud(typename PointCloud<PoinT>::Ptr c) { cloud_ = c; }
+    void setClusterTolerance(double t) { tol_ = t; }
+    void setMinClusterSize(int64_t n) { min_ = n; }
+    void setMaxClusterSize(int64_t n) { max_ = n; }
+    template <class Tree> void setSearchMethod(const Tree&) {}      // the kd-tree is replaced by a uniform grid on device
+    void extract(std::vector<PointIndices>& clusters)
+    {
+        clusters.clear();
+        rclc_ctx* ctx = thread_ctx();
+        if (!ctx || !cloud_ || cloud_->size() == 0) return;
+        const int64_t n = (int64_t)cloud_->size();
+        std::vector<int32_t> lab((size_t)n), sizes((size_t)n);
+        int32_t nc = 0;
+        if (!ok(rclc_euclidean_cluster(ctx, cloud_->points.data(), (int)sizeof(PoinT), 16, n, tol_, min_, max_, lab.data(), &nc, sizes.data()),
+                "EuclideanClusterExtraction::extract"))
+            return;
+        clusters.resize((size_t)nc);
+        for (int32_t k = 0; k < nc; ++k) clusters[(size_t)k].indices.reserve((size_t)sizes[(size_t)k]);
+        for (int64_t i = 0; i < n; ++i) if (lab[(size_t)i] >= 0) clusters[(size_t)lab[(size_t)i]].indices.push_back((int)i);
+    }
+private:
+    typename PointCloud<PoinT>::Ptr cloud_;
+    double tol_ = 0;
+    int64_t min_ = 1, max_ = INT_MAX;
+};
+
+// EulerCluster — include/pc_process.h:59-79: the largest cluster (tolerance 3 cm, 500 .. 2.5 M points) of target_clouds.
+inline void EulerCluster(typename PointCloud<PoinT>::Ptr& target_clouds, typename PointCloud<PoinT>::Ptr& output)
+{
+    std::vector<PointIndices> ece_inlier;
+    EuclideanClusterExtraction ece;
+    ece.setInputCloud(target_clouds);
+    ece.setClusterTolerance(0.03);
+    ece.setMinClusterSize(500);
+    ece.setMaxClusterSize(2500000);
+    ece.extract(ece_inlier);
+    if (!output) output = std::make_shared<PointCloud<PoinT>>();
+    output->points.clear();
+    if (ece_inlier.empty()) return;                       // (the reference indexes [0] unconditionally)
+    for (int i : ece_inlier[0].indices) output->points.push_back(target_clouds->points[(size_t)i]);
+}
+
+// eular_cluster_iter — include/pc_process.h:104-211: centroids of the board's black blocks. Thins the cloud to 3 mm, then
+// lowers the reflectivity threshold step by step until the black points fall apart into at least board_w * board_h / 2
+// clusters; the first block_num clusters (by size, stopping at a 0.65 size drop) are the blocks, later ones are merged into
+// the nearest block within half a square diagonal. max_rounds bounds the reference's unbounded loop.
+inline void eular_cluster_iter(const typename PointCloud<PoinT>::Ptr& cloudInRaw, double reflactive_thd, std::vector<Vector3d>& block_centroid,
+                               void* viewer = nullptr, int max_rounds = 200)
+{
+    (void)viewer;
+    const rclc_config& cfg = CfgParam();
+    auto blocks_cloud = std::make_shared<PointCloud<PoinT>>();
+    UniformSampling US;
+    US.setInputCloud(cloudInRaw);
+    US.setRadiusSearch(cfg.block_us_radius);
+    US.filter(*blocks_cloud);
+    std::vector<std::vector<PoinT>> block_clouds_inlier;
+    std::vector<int> block_centroid_inlier_num;
+    const int block_num = cfg.board_width * cfg.board_height / 2;
+    const double diag = cfg.gride_side_length * std::sqrt(2.0f);                      // src/global.cpp:47
+    double curr = reflactive_thd / cfg.reflactivity_dec_step;
+    for (int round = 0; round < max_rounds; ++round) {
+        curr *= cfg.reflactivity_dec_step;
+        {   // pcl::PassThrough on "intensity", [3, curr], inclusive
+            std::vector<PoinT> kept;
+            for (const PoinT& p : blocks_cloud->points)
+                if (std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z) && p.intensity >= 3.0f && p.intensity <= (float)curr) kept.push_back(p);
+            blocks_cloud->points.swap(kept);
+        }
+        if (blocks_cloud->size() == 0) return;
+        std::vector<PointIndices> ece_inlier;
+        EuclideanClusterExtraction ece;
+        ece.setInputCloud(blocks_cloud);
+        ece.setClusterTolerance(cfg.black_pt_cluster_dst_thd);
+        ece.setMinClusterSize(3);
+        ece.setMaxClusterSize(25000);
+        ece.extract(ece_inlier);
+        if ((int)ece_inlier.size() < block_num) continue;
+        for (int i_seg = 0; i_seg < (int)ece_inlier.size(); ++i_seg) {
+            std::vector<PoinT> ext;
+            float cx = 0.f, cy = 0.f, cz = 0.f;                                        // pcl::compute3DCentroid: float accumulation
+            for (int i : ece_inlier[(size_t)i_seg].indices) { const PoinT& p = blocks_cloud->points[(size_t)i]; ext.push_back(p); cx += p.x; cy += p.y; cz += p.z; }
+            const float inv = 1.0f / (float)ext.size();
+            const Vector3d centroid_curr((double)(cx * inv), (double)(cy * inv), (double)(cz * inv));
+            if (i_seg < block_num) {
+                if (i_seg > 0 && (double(ext.size()) / double(block_clouds_inlier[(size_t)i_seg - 1].size())) < 0.65) break;
+                block_clouds_inlier.push_back(ext);
+                block_centroid.push_back(centroid_curr);
+                block_centroid_inlier_num.push_back((int)ext.size());
+            } else {
+                int nearest = -1;
+                double nearest_dst = 10e3;
+                for (int i = 0; i < (int)block_centroid.size(); ++i) {
+                    const double dx = block_centroid[(size_t)i].x() - centroid_curr.x(), dy = block_centroid[(size_t)i].y() - centroid_curr.y(),
+                                 dz = block_centroid[(size_t)i].z() - centroid_curr.z();
+                    const float dst = (float)std::sqrt(dx * dx + dy * dy + dz * dz);
+                    if (dst < nearest_dst) { nearest_dst = dst; nearest = i; }
+                }
+                if (nearest >= 0 && nearest_dst < 0.5 * diag) {
+                    Vector3d& old = block_centroid[(size_t)nearest];
+                    const double a = block_centroid_inlier_num[(size_t)nearest], b = (double)ext.size();
+                    old = Vector3d((old.x() * a + centroid_curr.x() * b) / (a + b), (old.y() * a + centroid_curr.y() * b) / (a + b),
+                                   (old.z() * a + centroid_curr.z() * b) / (a + b));
+                    block_centroid_inlier_num[(size_t)nearest] += (int)ext.size();
+                    block_clouds_inlier[(size_t)nearest].insert(block_clouds_inlier[(size_t)nearest].end(), ext.begin(), ext.end());
+                }
+            }
+        }
+        if ((int)block_centroid.size() < block_num) {
+            block_clouds_inlier.clear();
+            block_centroid.clear();
+            block_centroid_inlier_num.clear();
+            continue;
+        }
+        return;
+    }
+}
 
 }  // namespace rclc_b200
 #endif  // RCLC_OPS_HPP

@@ -193,3 +193,18 @@ def plane_fit(cfg, pts):
     rc = lib().orc_plane_fit(C.byref(cfg), _p(pts), stride, ioff, C.c_int64(pts.shape[0]), _p(out), C.byref(it),
                              C.byref(nu))
     return rc, out, it.value, nu.value
+
+
+def uniform_sample(pts, leaf):
+    pts, stride, _ = _cloud(pts)
+    idx = np.zeros(len(pts), np.int32); n = C.c_int64()
+    lib().orc_uniform_sample(_p(pts), stride, C.c_int64(len(pts)), C.c_double(leaf), _p(idx), C.byref(n))
+    return idx[:n.value].copy()
+
+
+def euclidean_cluster(pts, tol, min_size, max_size):
+    pts, stride, _ = _cloud(pts)
+    lab = np.zeros(len(pts), np.int32); sizes = np.zeros(max(len(pts), 1), np.int32); nc = C.c_int32()
+    lib().orc_euclidean_cluster(_p(pts), stride, C.c_int64(len(pts)), C.c_double(tol), C.c_int64(min_size), C.c_int64(max_size),
+                                _p(lab), C.byref(nc), _p(sizes))
+    return lab, sizes[:nc.value].copy()

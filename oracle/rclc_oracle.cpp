@@ -15,6 +15,8 @@
 #include <cstdint>
 #include <cstring>
 #include <random>
+#include <map>
+#include <cfloat>
 #include <vector>
 
 namespace {
@@ -930,6 +932,98 @@ int orc_plane_fit(const rclc_config* cfg, const void* pts, int stride, int ioff,
     for (int q = 0; q < 4; ++q) plane_out[q] = abcd[q];
     if (iterations) *iterations = sum.num_iterations;
     return sum.termination == orc::FAILURE ? 1 : 0;
+}
+
+// pcl::UniformSampling (filters/uniform_sampling.hpp, applyFilter)
+int orc_uniform_sample(const void* pts, int stride, int64_t n, double leaf_d, int32_t* idx_out, int64_t* n_out)
+{
+    const float leaf = (float)leaf_d, inv = 1.0f / leaf;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool any = false;
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = rec(pts, stride, i);
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+        any = true;
+        for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], p[d]); mx[d] = std::max(mx[d], p[d]); }
+    }
+    *n_out = 0;
+    if (!any) return 0;
+    int64_t mb[3], div[3];
+    for (int d = 0; d < 3; ++d) {
+        mb[d] = (int64_t)std::floor(mn[d] * inv);
+        div[d] = (int64_t)std::floor(mx[d] * inv) - mb[d] + 1;
+    }
+    struct Leaf { int32_t idx; float dist; };
+    std::map<int64_t, Leaf> leaves;                       // ordered: the output order is ascending voxel key
+    for (int64_t i = 0; i < n; ++i) {
+        const float* p = rec(pts, stride, i);
+        if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+        int64_t ijk[3];
+        float dist = 0.f;
+        for (int d = 0; d < 3; ++d) {
+            const float fl = std::floor(p[d] * inv);
+            ijk[d] = (int64_t)fl;
+            const float c = (fl + 0.5f) * leaf;
+            const float e = p[d] - c;
+            const float e2 = e * e;
+            dist = (d == 0) ? e2 : dist + e2;
+        }
+        const int64_t key = (ijk[0] - mb[0]) + (ijk[1] - mb[1]) * div[0] + (ijk[2] - mb[2]) * div[0] * div[1];
+        auto it = leaves.find(key);
+        if (it == leaves.end()) leaves[key] = {(int32_t)i, dist};
+        else if (dist < it->second.dist) it->second = {(int32_t)i, dist};
+    }
+    int64_t k = 0;
+    for (auto& kv : leaves) idx_out[k++] = kv.second.idx;
+    *n_out = k;
+    return 0;
+}
+
+// pcl::EuclideanClusterExtraction (segmentation/extract_clusters.hpp) over KdTreeFLANN::radiusSearch
+int orc_euclidean_cluster(const void* pts, int stride, int64_t n, double tol, int64_t min_size, int64_t max_size, int32_t* labels_out,
+                          int32_t* n_clusters, int32_t* sizes_out)
+{
+    const float r2 = (float)(tol * tol);                  // kdtree_flann.hpp: radiusSearch passes static_cast<float>(radius * radius)
+    const double cell = tol * 1.0001;
+    std::vector<int32_t> parent((size_t)n);
+    for (int64_t i = 0; i < n; ++i) parent[i] = (int32_t)i;
+    auto find = [&](int32_t a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
+    auto finite = [&](int64_t i) { const float* p = rec(pts, stride, i); return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]); };
+    struct Key { int64_t x, y, z; bool operator<(const Key& o) const { return x != o.x ? x < o.x : (y != o.y ? y < o.y : z < o.z); } };
+    std::map<Key, std::vector<int32_t>> grid;
+    auto key_of = [&](int64_t i) { const float* p = rec(pts, stride, i); return Key{(int64_t)std::floor((double)p[0] / cell), (int64_t)std::floor((double)p[1] / cell), (int64_t)std::floor((double)p[2] / cell)}; };
+    for (int64_t i = 0; i < n; ++i) if (finite(i)) grid[key_of(i)].push_back((int32_t)i);
+    for (int64_t i = 0; i < n; ++i) {
+        if (!finite(i)) continue;
+        const float* p = rec(pts, stride, i);
+        const Key k0 = key_of(i);
+        for (int64_t dz = -1; dz <= 1; ++dz) for (int64_t dy = -1; dy <= 1; ++dy) for (int64_t dx = -1; dx <= 1; ++dx) {
+            auto it = grid.find(Key{k0.x + dx, k0.y + dy, k0.z + dz});
+            if (it == grid.end()) continue;
+            for (int32_t j : it->second) {
+                if (j >= i) continue;
+                const float* q = rec(pts, stride, j);
+                const float ex = p[0] - q[0], ey = p[1] - q[1], ez = p[2] - q[2];
+                float d = ex * ex;                            // flann L2_Simple: result += diff * diff, in order
+                d += ey * ey;
+                d += ez * ez;
+                if (d < r2) {                                 // flann RadiusResultSet::addPoint: dist < radius
+                    const int32_t a = find((int32_t)i), b = find(j);
+                    if (a != b) parent[std::max(a, b)] = std::min(a, b);
+                }
+            }
+        }
+    }
+    std::vector<int32_t> size((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) if (finite(i)) size[find((int32_t)i)]++;
+    std::vector<int32_t> roots;
+    for (int64_t i = 0; i < n; ++i) if (size[i] >= min_size && size[i] <= max_size && size[i] > 0) roots.push_back((int32_t)i);
+    std::stable_sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return size[a] != size[b] ? size[a] > size[b] : a < b; });
+    std::vector<int32_t> rank((size_t)n, -1);
+    for (size_t k = 0; k < roots.size(); ++k) { rank[roots[k]] = (int32_t)k; if (sizes_out) sizes_out[k] = size[roots[k]]; }
+    for (int64_t i = 0; i < n; ++i) labels_out[i] = finite(i) ? rank[find((int32_t)i)] : -1;
+    *n_clusters = (int32_t)roots.size();
+    return 0;
 }
 
 } // extern "C"

@@ -102,6 +102,17 @@ int orc_inverse4(const double T[16], double Tinv[16]);
 int orc_plane_fit(const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
                   int32_t* iterations, int64_t* n_used);
 
+/* pcl::UniformSampling as used at pc_process.h:111-115 / BoardSegmentation.cpp:58-61: voxel grid of leaf
+ * `leaf` anchored at the cloud's min corner, per voxel the input point nearest the voxel centre (float arithmetic, earliest index
+ * on ties); kept indices in ascending voxel-key order (PCL's own order is its hash map's). idx_out has room for n entries. */
+int orc_uniform_sample(const void* pts, int stride, int64_t n, double leaf, int32_t* idx_out, int64_t* n_out);
+
+/* pcl::EuclideanClusterExtraction as used at pc_process.h:62-72, 131-139: connected components of "FLANN L2_Simple distance^2 <
+ * (float)(tol*tol)", components with min_size <= size <= max_size kept, ranked by size descending (ties: smallest member index
+ * first). labels_out[i] = rank or -1; sizes_out has room for n entries (only n_clusters are written). */
+int orc_euclidean_cluster(const void* pts, int stride, int64_t n, double tol, int64_t min_size, int64_t max_size, int32_t* labels_out,
+                          int32_t* n_clusters, int32_t* sizes_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -172,6 +172,19 @@ class Context:
             _chk(rc)
         return rc, out, it.value, nu.value
 
+    def uniform_sample(self, pts, leaf):
+        pts, stride, ioff = _cloud(pts)
+        idx = np.zeros(len(pts), np.int32); n = C.c_int64()
+        _chk(lib().rclc_uniform_sample(self.h, _p(pts), stride, ioff, C.c_int64(len(pts)), C.c_double(leaf), _p(idx), C.byref(n)))
+        return idx[:n.value].copy()
+
+    def euclidean_cluster(self, pts, tol, min_size, max_size):
+        pts, stride, ioff = _cloud(pts)
+        lab = np.zeros(len(pts), np.int32); sizes = np.zeros(max(len(pts), 1), np.int32); nc = C.c_int32()
+        _chk(lib().rclc_euclidean_cluster(self.h, _p(pts), stride, ioff, C.c_int64(len(pts)), C.c_double(tol), C.c_int64(min_size),
+                                          C.c_int64(max_size), _p(lab), C.byref(nc), _p(sizes)))
+        return lab, sizes[:nc.value].copy()
+
     def transform_cloud(self, pts, T):
         pts, stride, _ = _cloud(pts); pts = pts.copy()
         T = np.ascontiguousarray(T, np.float32)

@@ -120,6 +120,50 @@ int main()
                   std::fabs(s * plane.w() / nrm + 4.0 / ref) < 1e-3,
               "plane %g %g %g %g", plane.x() / nrm, plane.y() / nrm, plane.z() / nrm, plane.w() / nrm);
     }
+    // ---- UniformSampling / EuclideanClusterExtraction / EulerCluster / eular_cluster_iter ----
+    {
+        // a board whose black squares read darker towards their middle (mixed pixels along the edges), plus far clutter
+        std::mt19937 rng(11);
+        std::uniform_real_distribution<double> ux(-0.4 + 1e-6, 0.4 - 1e-6), uy(-0.3 + 1e-6, 0.3 - 1e-6), far(-2.0, 2.0);
+        std::normal_distribution<double> nI(0.0, 2.0), nz(0.0, 0.001);
+        auto cloud = std::make_shared<PointCloud<PoinT>>();
+        for (int i = 0; i < 150000; ++i) {
+            PoinT p;
+            const double u = ux(rng), v = uy(rng);
+            const double fu = (u + 0.4) / 0.1, fv = (v + 0.3) / 0.1;
+            const int ci = (int)std::floor(fu), ri = (int)std::floor(fv);
+            const double eu = std::min(fu - ci, ci + 1 - fu) * 0.1, ev = std::min(fv - ri, ri + 1 - fv) * 0.1, e = std::min(eu, ev);
+            const bool black = ((ci + ri) % 2) == 0;
+            p.x = (float)u; p.y = (float)v; p.z = (float)(4.004 + nz(rng));      // mid-voxel for the 8 mm grid below
+            p.intensity = (float)std::max(4.0, (black ? 10.0 + 60.0 * std::max(0.0, 1.0 - e / 0.012) : 110.0) + nI(rng));
+            cloud->points.push_back(p);
+        }
+        const size_t n_board = cloud->size();
+        for (int i = 0; i < 300; ++i) { PoinT p; p.x = (float)(3.0 + far(rng)); p.y = (float)far(rng); p.z = (float)(8.0 + far(rng)); p.intensity = 50.f; cloud->points.push_back(p); }
+
+        auto thin = std::make_shared<PointCloud<PoinT>>();
+        UniformSampling US; US.setInputCloud(cloud); US.setRadiusSearch(0.008); US.filter(*thin);
+        CHECK(thin->size() > 5000 && thin->size() < 9000, "uniform sampling kept %zu", thin->size());        // ~ 0.48 m^2 / (8 mm)^2 = 7500 voxels
+        PointCloud<PoinT>::Ptr board;
+        EulerCluster(thin, board);
+        CHECK(board && board->size() > 5000 && board->size() + 250 < thin->size() + 1 && board->size() <= n_board, "largest cluster %zu of %zu", board ? board->size() : 0, thin->size());
+        bool all_on_board = true;
+        if (board) for (auto& p : board->points) all_on_board = all_on_board && p.z < 5.f;
+        CHECK(all_on_board, "largest cluster is the board");
+
+        std::vector<Vector3d> centroids;
+        eular_cluster_iter(board, 50.0, centroids);
+        CHECK(centroids.size() == 24, "black block centroids: %zu", centroids.size());
+        double worst = 0;
+        for (auto& c : centroids) {
+            // nearest black square centre
+            const double fu = (c.x() + 0.4) / 0.1, fv = (c.y() + 0.3) / 0.1;
+            const int ci = (int)std::floor(fu), ri = (int)std::floor(fv);
+            CHECK(((ci + ri) % 2) == 0, "centroid (%g, %g) is on a white square", c.x(), c.y());
+            worst = std::max(worst, std::hypot(c.x() - (-0.4 + 0.1 * ci + 0.05), c.y() - (-0.3 + 0.1 * ri + 0.05)));
+        }
+        CHECK(worst < 3e-3, "block centroid error %g m", worst);
+    }
     // ---- PlaneSegmentation (pcl::SACSegmentation drop-in): plane + 30 % outliers ----
     {
         auto pc = std::make_shared<PointCloud<PoinT>>();

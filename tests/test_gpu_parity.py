@@ -232,6 +232,33 @@ def test_plane_fit_pcl_layout_and_degenerate(ctx, cfg, oracle, ocfg):
     np.testing.assert_array_equal(p1, p0)
 
 
+def _cluster_scene(n, seed):
+    from tests.test_oracle_restatement import _scene
+    return _scene(n, seed)
+
+
+@pytest.mark.parametrize("n,leaf", [(50000, 0.008), (400000, 0.003), (1000, 0.5)])
+def test_uniform_sample_identical_indices(ctx, oracle, n, leaf):
+    """pcl::UniformSampling: the same point per voxel, in the same (voxel key) order."""
+    pts = _cluster_scene(n, 31)
+    pts[5, 1] = np.inf; pts[77, 2] = np.nan
+    assert np.array_equal(ctx.uniform_sample(pts, leaf), oracle.uniform_sample(pts, leaf))
+    pcl = np.zeros((n, 8), np.float32); pcl[:, :3] = pts[:, :3]; pcl[:, 4] = pts[:, 3]
+    assert np.array_equal(ctx.uniform_sample(pcl, leaf), oracle.uniform_sample(pts, leaf))
+
+
+@pytest.mark.parametrize("n,tol,min_size", [(60000, 0.03, 500), (60000, 0.0085, 3), (3000, 0.05, 1)])
+def test_euclidean_cluster_identical_labels(ctx, oracle, n, tol, min_size):
+    """pcl::EuclideanClusterExtraction: same partition, same ranking (size descending, smallest member first)."""
+    pts = _cluster_scene(n, 32)
+    pts = pts[oracle.uniform_sample(pts, 0.004)]                     # the reference always thins before it clusters
+    pts[3, 0] = np.nan
+    l0, s0 = oracle.euclidean_cluster(pts, tol, min_size, 2500000)
+    l1, s1 = ctx.euclidean_cluster(pts, tol, min_size, 2500000)
+    assert np.array_equal(s1, s0) and np.array_equal(l1, l0)
+    assert len(s0) >= 3 and l0[3] == -1
+
+
 def test_ransac_counts_masks_bit_exact(ctx, oracle):
     rng = np.random.default_rng(5)
     n = 60000

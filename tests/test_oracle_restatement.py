@@ -240,3 +240,72 @@ def test_plane_fit(oracle, ocfg):
     if p[2] < 0: p = -p
     np.testing.assert_allclose(p[:3], nrm, atol=2e-3)
     assert abs(-p[3] - 4.0 * 1.0) < 5e-3
+
+
+def _scene(n, seed):
+    """Three planar blobs and scattered noise: clusters of different sizes with clear gaps."""
+    rng = np.random.default_rng(seed)
+    pts = np.zeros((n, 4), np.float32)
+    k = n // 10
+    centres = [(0.0, 0.0, 4.0, 5 * k, 0.15), (0.6, 0.1, 4.2, 3 * k, 0.1), (-0.5, -0.4, 3.8, k, 0.05)]
+    o = 0
+    for cx, cy, cz, m, r in centres:
+        pts[o:o + m, 0] = cx + rng.uniform(-r, r, m); pts[o:o + m, 1] = cy + rng.uniform(-r, r, m); pts[o:o + m, 2] = cz + rng.normal(0, 0.002, m)
+        o += m
+    pts[o:, :3] = rng.uniform(-3, 3, (n - o, 3)) + [0, 0, 8]
+    pts[:, 3] = rng.uniform(0, 150, n)
+    return pts[rng.permutation(n)]
+
+
+def test_uniform_sample_against_bruteforce(oracle):
+    """Oracle vs a direct numpy restatement of SURVEY.md Appendix A (one point per voxel, nearest the centre, key order)."""
+    pts = _scene(4000, 3)
+    pts[17, 0] = np.nan
+    leaf = np.float32(0.02)
+    idx = oracle.uniform_sample(pts, float(leaf))
+    fin = np.isfinite(pts[:, :3]).all(1)
+    inv = np.float32(1.0) / leaf
+    fl = np.floor(pts[:, :3] * inv)
+    mb = np.floor(pts[fin, :3].min(0) * inv).astype(np.int64)
+    div = np.floor(pts[fin, :3].max(0) * inv).astype(np.int64) - mb + 1
+    best = {}
+    for i in np.nonzero(fin)[0]:
+        ijk = fl[i].astype(np.int64)
+        e = pts[i, :3] - (fl[i] + np.float32(0.5)) * leaf
+        e2 = e * e
+        d = np.float32(np.float32(e2[0] + e2[1]) + e2[2])
+        key = int((ijk[0] - mb[0]) + (ijk[1] - mb[1]) * div[0] + (ijk[2] - mb[2]) * div[0] * div[1])
+        if key not in best or d < best[key][0]:
+            best[key] = (d, i)
+    want = np.array([best[k][1] for k in sorted(best)], np.int32)
+    assert np.array_equal(idx, want)
+
+
+def test_euclidean_cluster_against_bruteforce(oracle):
+    pts = _scene(1500, 4)
+    tol = 0.05
+    lab, sizes = oracle.euclidean_cluster(pts, tol, 5, 100000)
+    # brute force connected components with the same float distance
+    n = len(pts)
+    x = pts[:, :3]
+    parent = list(range(n))
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]; a = parent[a]
+        return a
+    r2 = np.float32(tol * tol)
+    for i in range(n):
+        e = x[i] - x[:i]
+        d = (e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1]) + e[:, 2] * e[:, 2]
+        for j in np.nonzero(d < r2)[0]:
+            a, b = find(i), find(int(j))
+            if a != b: parent[max(a, b)] = min(a, b)
+    root = np.array([find(i) for i in range(n)])
+    cnt = np.bincount(root, minlength=n)
+    keep = [r for r in range(n) if cnt[r] >= 5]
+    keep.sort(key=lambda r: (-cnt[r], r))
+    rank = {r: k for k, r in enumerate(keep)}
+    want = np.array([rank.get(r, -1) for r in root], np.int32)
+    assert np.array_equal(lab, want)
+    assert np.array_equal(sizes, [cnt[r] for r in keep])
+    assert sizes[0] > sizes[1] > sizes[2]

@@ -37,3 +37,14 @@ def test_ops_run_on_gpu():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.returncode, r.stdout[-3000:], r.stderr[-2000:])
     assert "all operator checks passed" in r.stdout
+
+
+def test_pcd_io_round_trip_and_formats(tmp_path):
+    """include/rclc_pcd.hpp (loadPCDFile / savePCDFileBinary / T_base): host code, runs anywhere."""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_pcd")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "cpp", "test_pcd.cpp")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-Wall", "-Wno-unused-function", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "livox_ascii.pcd"), str(tmp_path / "pcd")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "all PCD checks passed" in r.stdout

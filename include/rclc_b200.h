@@ -120,6 +120,13 @@ int rclc_uniform_sample(rclc_ctx* ctx, const void* pts, int stride, int ioff, in
  * sizes_out (room for n, may be NULL) receives the n_clusters sizes. ---- */
 int rclc_euclidean_cluster(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double tol, int64_t min_size, int64_t max_size,
                            int32_t* labels_out, int32_t* n_clusters, int32_t* sizes_out);
+/* ---- cv::solvePnPRansac(objectPoints, imagePoints, K, dist, rvec, tvec, false, SOLVEPNP_UPNP) at apps/Calibrate.cpp:41-50, on
+ * NORMALISED image points (Cam.imgPt2norm, Calibrate.cpp:36): the starting pose of pose_reprj_opt. obj [n][3], norm_pts [n][2],
+ * thresh = reprojection threshold in normalised units (8 px / focal length for OpenCV's default), max_iters / confidence <= 0 pick
+ * OpenCV's defaults (100, 0.99). R_out row-major camera <- laser, t_out; inlier_mask [n] and n_inliers may be NULL. Host code:
+ * needs no context and no device. ---- */
+int rclc_pnp_ransac(const double* obj, const double* norm_pts, int64_t n, double thresh, int32_t max_iters, double confidence, uint32_t seed,
+                    double R_out[9], double t_out[3], uint8_t* inlier_mask, int32_t* n_inliers);
 /* ---- pcl::transformPointCloud(Matrix4f) in place, row-major T ---- */
 int rclc_transform_cloud(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const float T[16]);
 

@@ -12,6 +12,7 @@
 //   pc_plane_fitting                     include/opt/opt_plane_param.hpp:45 rclc_plane_fit
 //   opt_grid_fitting                     include/opt/opt_grid_fitting.h:25  rclc_gridfit_solve
 //   BOARD_FITTING_COST::Create/Evaluate  include/opt/board_fitting_cost.h:64-78   rclc_batch_* (one sweep serves all 82 functors)
+//   cv::solvePnPRansac + Rodrigues + Quaterniond(R)   apps/Calibrate.cpp:41-62       rclc_pnp_ransac  (pnp_init)
 //   pose_reprj_opt                       include/opt/opt_reprj_calib.h:21   rclc_pose_refine
 //   PinholeCam::{imgPt2norm,normPt2img,Pt2img,is_in_FoV}  include/PinholeCam.h:78-110   (host inline, same arithmetic)
 //   colourise loop                       apps/Calibrate.cpp:134-148         rclc_project_colorize  (colorize_cloud)
@@ -291,6 +292,42 @@ private:
     std::shared_ptr<BoardCloudOnDevice> cloud_;
     int target_;
 };
+
+// pnp_init — apps/Calibrate.cpp:41-62: the starting extrinsic of pose_reprj_opt from all corner correspondences, on the
+// normalised image points the reference builds at :36 (e_imagePoints). Tcl = (qx, qy, qz, qw, tx, ty, tz) as at :59-62.
+// reprj_thresh_px / focal_px: OpenCV's default reprojectionError of 8 px at the camera's focal length. Host code.
+inline bool pnp_init(const std::vector<std::vector<Vector2d>>& img_norm_points, const std::vector<std::vector<Vector3d>>& pc_corner_points, double* Tcl,
+                     double reprj_thresh_px = 8.0, double focal_px = 0.0, unsigned seed = 1)
+{
+    std::vector<double> obj, uv;
+    for (size_t f = 0; f < pc_corner_points.size() && f < img_norm_points.size(); ++f)
+        for (size_t k = 0; k < pc_corner_points[f].size() && k < img_norm_points[f].size(); ++k) {
+            obj.push_back(pc_corner_points[f][k].x()); obj.push_back(pc_corner_points[f][k].y()); obj.push_back(pc_corner_points[f][k].z());
+            uv.push_back(img_norm_points[f][k].x()); uv.push_back(img_norm_points[f][k].y());
+        }
+    if (focal_px <= 0) focal_px = 0.5 * (CfgParam().fx + CfgParam().fy);
+    double R[9], t[3];
+    if (!ok(rclc_pnp_ransac(obj.data(), uv.data(), (int64_t)(uv.size() / 2), reprj_thresh_px / focal_px, 100, 0.99, seed, R, t, nullptr, nullptr), "pnp_init")) return false;
+    // Eigen::Quaterniond(Matrix3d) (Calibrate.cpp:61): Shepperd's branches as in Eigen/src/Geometry/Quaternion.h
+    double qw, qx, qy, qz;
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0) { double s = std::sqrt(tr + 1.0); qw = 0.5 * s; s = 0.5 / s; qx = (R[7] - R[5]) * s; qy = (R[2] - R[6]) * s; qz = (R[3] - R[1]) * s; }
+    else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double s = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        double q[3];
+        q[i] = 0.5 * s; s = 0.5 / s;
+        qw = (R[3 * k + j] - R[3 * j + k]) * s;
+        q[j] = (R[3 * j + i] + R[3 * i + j]) * s;
+        q[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+        qx = q[0]; qy = q[1]; qz = q[2];
+    }
+    Tcl[0] = qx; Tcl[1] = qy; Tcl[2] = qz; Tcl[3] = qw; Tcl[4] = t[0]; Tcl[5] = t[1]; Tcl[6] = t[2];
+    return true;
+}
 
 // pose_reprj_opt — include/opt/opt_reprj_calib.h:21-66. Tcl = (qx, qy, qz, qw, tx, ty, tz) in/out (Calibrate.cpp:59-66).
 inline void pose_reprj_opt(std::vector<std::vector<Vector2d>>& img_norm_points, std::vector<std::vector<Vector3d>>& pc_corner_points, double* Tcl,

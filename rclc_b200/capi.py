@@ -66,6 +66,15 @@ def config() -> RclcConfig:
     return cfg
 
 
+def pnp_ransac(obj, norm_pts, thresh, max_iters=100, confidence=0.99, seed=1):
+    """cv::solvePnPRansac stand-in on normalised image points (apps/Calibrate.cpp:41-50). Host code, no context."""
+    obj = np.ascontiguousarray(obj, np.float64); uv = np.ascontiguousarray(norm_pts, np.float64)
+    n = len(obj); R = np.zeros(9); t = np.zeros(3); mask = np.zeros(n, np.uint8); ni = C.c_int32()
+    _chk(lib().rclc_pnp_ransac(_p(obj), _p(uv), C.c_int64(n), C.c_double(thresh), C.c_int32(max_iters), C.c_double(confidence), C.c_uint32(seed),
+                               _p(R), _p(t), _p(mask), C.byref(ni)))
+    return R.reshape(3, 3), t, mask.astype(bool)
+
+
 def generate_targets(cfg):
     nt = cfg.n_targets()
     xy = np.zeros((nt, 2)); is_row = np.zeros(nt, np.int32); n = C.c_int32()

@@ -184,7 +184,7 @@ int main()
         }
         CHECK(sac.iterations() >= 1 && sac.iterations() <= 800, "iterations %d", sac.iterations());
     }
-    // ---- pose_reprj_opt: perturbed extrinsic comes back ----
+    // ---- pnp_init + pose_reprj_opt: the extrinsic comes back from the correspondences alone ----
     {
         std::mt19937 rng(11); std::uniform_real_distribution<double> u(-0.4, 0.4), d(3.5, 5.5); std::normal_distribution<double> px(0, 1e-4);
         const double q[4] = {0.02, -0.01, 0.015, 0.9996}; const double t[3] = {0.05, -0.03, 0.02};
@@ -205,7 +205,14 @@ int main()
             }
             pcs.push_back(pc); ims.push_back(im);
         }
-        double Tcl[7] = {0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0};
+        // start from the PnP pose, as apps/Calibrate.cpp:41-63 does
+        double Tpnp[7] = {0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0};
+        CHECK(pnp_init(ims, pcs, Tpnp), "pnp_init");
+        double dq0 = 0; for (int k = 0; k < 4; ++k) dq0 = std::max(dq0, std::fabs(Tpnp[k] - q[k] / std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])));
+        CHECK(dq0 < 2e-3 && std::fabs(Tpnp[4] - t[0]) < 5e-3 && std::fabs(Tpnp[5] - t[1]) < 5e-3 && std::fabs(Tpnp[6] - t[2]) < 2e-2, "PnP start %g %g %g %g | %g %g %g", Tpnp[0],
+              Tpnp[1], Tpnp[2], Tpnp[3], Tpnp[4], Tpnp[5], Tpnp[6]);
+        double Tcl[7];
+        for (int k = 0; k < 7; ++k) Tcl[k] = Tpnp[k];
         pose_reprj_opt(ims, pcs, Tcl, false);
         const double nq = std::sqrt(Tcl[0] * Tcl[0] + Tcl[1] * Tcl[1] + Tcl[2] * Tcl[2] + Tcl[3] * Tcl[3]);
         double dq = 0; for (int k = 0; k < 4; ++k) dq = std::max(dq, std::fabs(Tcl[k] / nq - q[k] / std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])));

@@ -1175,9 +1175,14 @@ __device__ __forceinline__ void stream_rows(const float4* __restrict__ src, cons
     };
     auto issue_group = [&](int g) {           // rows g*4 .. g*4+3 of the (padded) list -> slot g % kRingGroups
         const uint32_t slot = lring + (uint32_t)(g % kRingGroups) * (kGroupRows * 512u);
-#pragma unroll
-        for (int h = 0; h < kGroupRows; ++h)
-            cp_async16(slot + h * 512u, lsrc + (uint64_t)list[g * kGroupRows + h] * 512u);
+        // the group's four list entries with ONE 16-byte load: ptxas pads every shared load that precedes an LDGSTS with three
+        // dummy loads, so four scalar loads cost sixteen issue slots per group
+        static_assert(kGroupRows == 4, "one 16-byte load per group");
+        const uint4 e = *reinterpret_cast<const uint4*>(list + g * kGroupRows);
+        cp_async16(slot, lsrc + (uint64_t)e.x * 512u);
+        cp_async16(slot + 512u, lsrc + (uint64_t)e.y * 512u);
+        cp_async16(slot + 1024u, lsrc + (uint64_t)e.z * 512u);
+        cp_async16(slot + 1536u, lsrc + (uint64_t)e.w * 512u);
         cp_async_commit();
     };
     const int ngroups = (n + kGroupRows - 1) / kGroupRows;

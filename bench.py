@@ -32,7 +32,7 @@ WORKLOAD = "configs[1]: 20 synthetic Avia/Horizon raster frames x 500k pts, 8x6 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=20)
@@ -55,7 +55,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0 = index, None, [], None
+
+    def mark(self):
+        """Start of the timed region: samples before it were taken during the warm-up (same workload, same load)."""
+        self.t0 = time.time()
 
     def start(self):
         try:
@@ -69,7 +73,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -78,7 +82,11 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        timed = [ln for (t, ln) in self.lines if self.t0 is None or t >= self.t0]
+        window = "timed region"
+        if not timed:               # nvidia-smi reports every 100 ms: a sub-100-ms region can fall between two lines
+            timed, window = [ln for (_, ln) in self.lines[-3:]], "warm-up, same workload (timed region shorter than the sampling period)"
+        for ln in timed:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -90,7 +98,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -204,11 +212,12 @@ def run_ours(args):
         return sum(len(frames[f]) * reps[f].pose_evals for f in range(F)), corners
 
     # ---- value: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    sampler.start()                                  # nvidia-smi needs a few hundred ms to come up: start it before the warm-up
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark()
     l0 = ctx.kernel_launches()
     ctx.timer_start()
     work = 0

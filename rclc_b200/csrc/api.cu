@@ -2,6 +2,7 @@
 #define RCLC_CONFIG_IMPLEMENTATION
 #include "common.cuh"
 #include <omp.h>
+#include <thread>
 #include <algorithm>
 
 namespace rclc {
@@ -41,7 +42,16 @@ int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_
     // OpenMP keeps its worker threads between calls (spawning std::threads per frame cost more than the copy itself)
     const int64_t chunk = 65536;
     const int64_t nchunks = (n + chunk - 1) / chunk;
-    const int nth = (int)std::min<int64_t>(std::min(omp_get_max_threads(), 8), nchunks);
+    // up to 8 threads per context, sized from the machine and the ranks sharing it rather than from OMP_NUM_THREADS: torchrun
+    // exports OMP_NUM_THREADS=1 to every rank, which made the multi-GPU uploads single-threaded (RCLC_UPLOAD_THREADS overrides)
+    static const int want = [] {
+        if (const char* e = std::getenv("RCLC_UPLOAD_THREADS")) return std::max(1, atoi(e));
+        const char* lw = std::getenv("LOCAL_WORLD_SIZE");
+        const int ranks = lw ? std::max(1, atoi(lw)) : 1;
+        const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+        return std::max(1, std::min(8, hw / ranks));
+    }();
+    const int nth = (int)std::min<int64_t>(want, nchunks);
 #pragma omp parallel for num_threads(nth) schedule(static)
     for (int64_t c = 0; c < nchunks; ++c) pack_range(src, stride, ioff, c * chunk, std::min(n, (c + 1) * chunk), o);
     RCLC_CUDA(cudaMemcpyAsync(dst, o, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));

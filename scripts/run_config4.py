@@ -45,14 +45,16 @@ def main():
     # initial guess: ground truth perturbed by ~1 degree / 2 cm (the reference starts from solvePnPRansac, Calibrate.cpp:43-51)
     dR = synth._rot_xyz(0.012, -0.015, 0.01)
     q0 = rot_to_quat_xyzw(dR @ T_gt[:3, :3]); Tcl0 = np.r_[q0, T_gt[:3, 3] + [0.02, -0.015, 0.01]]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ctx.timer_start()
-    Tcl, corners_all, reports, (c0, c1, it) = multi.calibrate_sharded(ctx, cfg, frames, img, a.frames, rank, world, Tcl0,
-                                                                      device=torch.device("cuda", local), T_bl_local=T_bl)
-    ms = ctx.timer_stop_ms()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    ms_runs = []
+    for _ in range(2):                   # the first call pays the allocations (device, pinned) and the CUDA-graph capture
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        Tcl, corners_all, reports, (c0, c1, it) = multi.calibrate_sharded(ctx, cfg, frames, img, a.frames, rank, world, Tcl0,
+                                                                          device=torch.device("cuda", local), T_bl_local=T_bl)
+        ms_runs.append(ctx.timer_stop_ms())
+    t = torch.tensor(ms_runs, dtype=torch.float64, device="cuda")
     same = torch.tensor(Tcl, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -67,7 +69,7 @@ def main():
         ang = 2 * np.arcsin(min(1.0, np.linalg.norm(q * np.sign(q[3]) - q_gt * np.sign(q_gt[3])) / 2))
         corner_err = float(np.abs(corners_all[mine] - np.stack([s[2] for s in scene])).max()) if scene else None
         print(json.dumps({"config": "configs[3]: batch calibration, frames sharded round-robin, one all-gather of corners",
-                          "frames": a.frames, "pts_per_frame": a.pts, "n_gpus": world, "ms": float(t.item()),
+                          "frames": a.frames, "pts_per_frame": a.pts, "n_gpus": world, "ms_first_call": float(t[0].item()), "ms": float(t[1].item()),
                           "rot_err_rad_vs_gt": float(ang), "trans_err_m_vs_gt": float(np.abs(Tcl[4:] - T_gt[:3, 3]).max()),
                           "max_corner_err_m_rank0": corner_err, "pose_cost": [c0, c1], "pose_iterations": it,
                           "all_ranks_identical": identical}), flush=True)

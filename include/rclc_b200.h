@@ -120,6 +120,10 @@ int rclc_uniform_sample(rclc_ctx* ctx, const void* pts, int stride, int ioff, in
  * sizes_out (room for n, may be NULL) receives the n_clusters sizes. ---- */
 int rclc_euclidean_cluster(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double tol, int64_t min_size, int64_t max_size,
                            int32_t* labels_out, int32_t* n_clusters, int32_t* sizes_out);
+/* ---- get_ref_pt (include/utils.h:160-202) + calc_laser_coor_v1 (include/pc_process.h:373-462) + line_fitting
+ * (include/opt/opt_line_fitting.h:51-108): T_bl (row-major 4x4, board <- laser) from the n black-block centroids [n][3] of
+ * eular_cluster_iter and the board plane. Host code: needs no context and no device. ---- */
+int rclc_calc_laser_coor(const rclc_config* cfg, const double* centroids, int32_t n, const double plane[4], double Tbl_out[16]);
 /* ---- cv::solvePnPRansac(objectPoints, imagePoints, K, dist, rvec, tvec, false, SOLVEPNP_UPNP) at apps/Calibrate.cpp:41-50, on
  * NORMALISED image points (Cam.imgPt2norm, Calibrate.cpp:36): the starting pose of pose_reprj_opt. obj [n][3], norm_pts [n][2],
  * thresh = reprojection threshold in normalised units (8 px / focal length for OpenCV's default), max_iters / confidence <= 0 pick

@@ -19,6 +19,9 @@
 //   pcl::UniformSampling<PoinT>          include/pc_process.h:111-115, apps/BoardSegmentation.cpp:58-61   rclc_uniform_sample  (UniformSampling)
 //   pcl::EuclideanClusterExtraction<PoinT>  include/pc_process.h:62-72, 131-139     rclc_euclidean_cluster  (EuclideanClusterExtraction)
 //   EulerCluster, eular_cluster_iter     include/pc_process.h:59-79, 104-211  (host logic over the two classes above)
+//   get_ref_pt + calc_laser_coor_v1 + line_fitting   include/utils.h:160, pc_process.h:373, opt/opt_line_fitting.h:51   rclc_calc_laser_coor
+//   pcl::transformPointCloud(in, out, Matrix4f)      pc_process.h:594,618; Calibrate.cpp:99   rclc_transform_cloud  (transformPointCloud)
+//   est_board_corner                     include/pc_process.h:583-646       (the per-frame chain over the operators above)
 //   pcl::SACSegmentation<>::segment as configured at apps/BoardSegmentation.cpp:64-72
 //                                                                           rclc_ransac_plane_score + host replay of
 //                                                                           PCL's adaptive rule + rclc_ransac_plane_select
@@ -629,6 +632,78 @@ inline void eular_cluster_iter(const typename PointCloud<PoinT>::Ptr& cloudInRaw
         }
         return;
     }
+}
+
+// pcl::transformPointCloud(cloud_in, cloud_out, Matrix4f) as the reference calls it (in place: pc_process.h:594, 618).
+inline void transformPointCloud(const PointCloud<PoinT>& in, PointCloud<PoinT>& out, const Matrix4f& T)
+{
+    if (&in != &out) out.points = in.points;
+    rclc_ctx* ctx = thread_ctx();
+    if (!ctx || out.size() == 0) return;
+    float Tr[16];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) Tr[r * 4 + c] = T(r, c);
+    ok(rclc_transform_cloud(ctx, out.points.data(), (int)sizeof(PoinT), (int64_t)out.size(), Tr), "transformPointCloud");
+}
+
+// calc_laser_coor_v1 — include/pc_process.h:373-462 (with get_ref_pt, utils.h:160, and line_fitting, opt_line_fitting.h:51):
+// T_bl (board <- laser) from the black-block centroids and the board plane. Returns 0, or -1 when the centroids cannot be
+// arranged into board_height rows of board_width / 2 blocks (the reference's calc_laser_coor prints and returns -1 there).
+inline int calc_laser_coor_v1(std::vector<Vector3d>& v_grid_centroid, Vector4d& board_plane_param, Matrix4d& Tbl, void* viewer = nullptr)
+{
+    (void)viewer;
+    std::vector<double> cen;
+    for (const Vector3d& p : v_grid_centroid) { cen.push_back(p.x()); cen.push_back(p.y()); cen.push_back(p.z()); }
+    const double plane[4] = {board_plane_param.x(), board_plane_param.y(), board_plane_param.z(), board_plane_param.w()};
+    double T[16];
+    if (!ok(rclc_calc_laser_coor(&CfgParam(), cen.data(), (int32_t)v_grid_centroid.size(), plane, T), "calc_laser_coor_v1")) return -1;
+    from_row_major(T, Tbl);
+    return 0;
+}
+
+// est_board_corner — include/pc_process.h:583-646: one board-only cloud (laser frame, after T_base) in, the (W-1) x (H-1)
+// board corners in the laser frame out. The cloud is modified like in the reference (projected onto its plane, then moved into
+// the board frame). Returns false when a stage gives up (the reference carries on and crashes or produces garbage there).
+inline bool est_board_corner(typename PointCloud<PoinT>::Ptr& chess_board_processe, std::vector<Vector3d>& board_corner, void* viewer = nullptr,
+                             rclc_gridfit_report* report = nullptr)
+{
+    (void)viewer;
+    const rclc_config& cfg = CfgParam();
+    if (!chess_board_processe || chess_board_processe->size() == 0) return false;
+    if (cfg.board_order == 1) {
+        Matrix4f T_grid_shift;
+        T_grid_shift(0, 0) = -1.0f;
+        transformPointCloud(*chess_board_processe, *chess_board_processe, T_grid_shift);
+    }
+    Vector4d board_plane_param;
+    pc_plane_fitting(chess_board_processe, board_plane_param);
+    pc_plane_prj(chess_board_processe, board_plane_param);
+    VectorXd board_intensity((long)chess_board_processe->size());
+    for (long i = 0; i < (long)chess_board_processe->size(); ++i) board_intensity(i) = chess_board_processe->points[(size_t)i].intensity;
+    std::vector<double> mu{15, 100}, sigma{15, 15};
+    GMMFit::fit_1d(board_intensity, 2, mu, sigma, false);
+    const double reflactive_thd = mu[0] + 2.0 * sigma[0];
+    std::vector<Vector3d> block_centroid;
+    eular_cluster_iter(chess_board_processe, reflactive_thd, block_centroid);
+    if ((int)block_centroid.size() < cfg.board_width * cfg.board_height / 2) return false;
+    Matrix4d T_bl;
+    if (calc_laser_coor_v1(block_centroid, board_plane_param, T_bl) != 0) return false;
+    Matrix4f T_blf;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T_blf(r, c) = (float)T_bl(r, c);
+    transformPointCloud(*chess_board_processe, *chess_board_processe, T_blf);
+    const size_t before = board_corner.size();
+    opt_grid_fitting(chess_board_processe, T_bl, board_corner, nullptr, report);
+    if (board_corner.size() == before) return false;
+    if (cfg.board_order == 1) {
+        const int n_pt_per_row = cfg.board_width - 1;
+        std::vector<Vector3d> tmp(board_corner.size());
+        for (int row = 0; row < cfg.board_height - 1; ++row)
+            for (int col = 0; col < n_pt_per_row; ++col) {
+                const Vector3d& pt = board_corner[(size_t)(row * n_pt_per_row + col)];
+                tmp[(size_t)(row * n_pt_per_row + n_pt_per_row - col - 1)] = Vector3d(-pt.x(), pt.y(), pt.z());
+            }
+        board_corner = tmp;
+    }
+    return true;
 }
 
 }  // namespace rclc_b200

@@ -208,3 +208,9 @@ def euclidean_cluster(pts, tol, min_size, max_size):
     lib().orc_euclidean_cluster(_p(pts), stride, C.c_int64(len(pts)), C.c_double(tol), C.c_int64(min_size), C.c_int64(max_size),
                                 _p(lab), C.byref(nc), _p(sizes))
     return lab, sizes[:nc.value].copy()
+
+
+def calc_laser_coor(cfg, centroids, plane):
+    cen = np.ascontiguousarray(centroids, np.float64); pl = np.ascontiguousarray(plane, np.float64); T = np.zeros(16)
+    rc = lib().orc_calc_laser_coor(C.byref(cfg), _p(cen), C.c_int32(len(cen)), _p(pl), _p(T))
+    return rc, T.reshape(4, 4)

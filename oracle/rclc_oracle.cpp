@@ -1026,4 +1026,102 @@ int orc_euclidean_cluster(const void* pts, int stride, int64_t n, double tol, in
     return 0;
 }
 
+// utils.h:160-202, pc_process.h:373-462, opt/opt_line_fitting.h:17-108
+int orc_calc_laser_coor(const rclc_config* cfg, const double* cen, int32_t n, const double plane[4], double Tbl[16])
+{
+    struct V3 { double x, y, z; };
+    auto at = [&](int i) { return V3{cen[3 * i], cen[3 * i + 1], cen[3 * i + 2]}; };
+    auto sub = [](V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; };
+    auto cross = [](V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
+    auto norm = [](V3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); };
+    // get_ref_pt: the farthest centroid of the (x > cx, y <= cy) quadrant
+    V3 c{0, 0, 0};
+    for (int i = 0; i < n; ++i) { c.x += cen[3 * i]; c.y += cen[3 * i + 1]; c.z += cen[3 * i + 2]; }
+    c.x /= n; c.y /= n; c.z /= n;
+    double far_d[4] = {0, 0, 0, 0};
+    int far_i[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+        const V3 p = at(i);
+        const double d = norm(sub(p, c));
+        const int axis = p.x > c.x ? (p.y > c.y ? 0 : 1) : (p.y > c.y ? 2 : 3);
+        if (d > far_d[axis]) { far_d[axis] = d; far_i[axis] = i; }
+    }
+    const int ref_idx = far_i[1];
+    const V3 ref0 = at(ref_idx);
+    std::vector<std::pair<double, int>> dl;
+    for (int i = 0; i < n; ++i) if (i != ref_idx) dl.push_back({norm(sub(at(i), ref0)), i});
+    std::sort(dl.begin(), dl.end());
+    const V3 ref1 = at(dl[1].second), ref2 = at(dl[2].second);
+    V3 xt = (ref1.x < ref2.x && ref1.y < ref2.y) ? sub(ref0, ref1) : sub(ref0, ref2);
+    { const double l = norm(xt); xt = V3{xt.x / l, xt.y / l, xt.z / l}; }
+    std::vector<std::pair<double, int>> rows;
+    for (int i = 0; i < n; ++i) rows.push_back({norm(cross(sub(ref0, at(i)), xt)), i});
+    std::sort(rows.begin(), rows.end());
+    // line_fitting: one residual per board row, sum over the row's points of |(p - row centroid) x normalize(abc)|, Huber(0.1)
+    const int per_row = cfg->board_width / 2, n_rows = cfg->board_height, origin_id = cfg->board_height / 2;
+    if (per_row * n_rows > n) return 1;
+    std::vector<std::vector<V3>> rp((size_t)n_rows);
+    std::vector<V3> rc((size_t)n_rows);
+    V3 origin_centroid{0, 0, 0};
+    int cnt = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        V3 cc{0, 0, 0};
+        for (int k = 0; k < per_row; ++k) { const V3 p = at(rows[(size_t)cnt++].second); rp[(size_t)r].push_back(p); cc.x += p.x; cc.y += p.y; cc.z += p.z; }
+        cc.x /= per_row; cc.y /= per_row; cc.z /= per_row;
+        rc[(size_t)r] = cc;
+        if (r == origin_id) origin_centroid = cc;
+    }
+    double abc[3] = {xt.x, xt.y, xt.z};
+    orc::LMProblem P;
+    P.m = n_rows; P.n = 3; P.nl = 3;
+    P.evaluate = [&](const double* x, double* cost, double* res, double* jac) {
+        const double na = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+        const V3 u{x[0] / na, x[1] / na, x[2] / na};
+        double total = 0;
+        for (int r = 0; r < n_rows; ++r) {
+            double rr = 0, g[3] = {0, 0, 0};
+            for (const V3& p : rp[(size_t)r]) {
+                const V3 d = sub(p, rc[(size_t)r]);
+                const V3 cr = cross(d, u);
+                const double l = norm(cr);
+                rr += l;
+                if (jac) { const V3 ch{cr.x / l, cr.y / l, cr.z / l}; const V3 q = cross(ch, d); g[0] += q.x; g[1] += q.y; g[2] += q.z; }      // d|d x u|/du
+            }
+            double j3[3];
+            if (jac) {
+                const double gu = g[0] * u.x + g[1] * u.y + g[2] * u.z;                    // du/da = (I - u u^T) / |a|
+                j3[0] = (g[0] - gu * u.x) / na; j3[1] = (g[1] - gu * u.y) / na; j3[2] = (g[2] - gu * u.z) / na;
+            }
+            if (!std::isfinite(rr)) return false;
+            total += orc::apply_loss_1d(0.1, &rr, jac ? j3 : nullptr, 3);
+            if (res) res[r] = rr;
+            if (jac) for (int q = 0; q < 3; ++q) jac[r * 3 + q] = j3[q];
+        }
+        *cost = total;
+        return true;
+    };
+    orc::LMOptions opt;
+    opt.linear_solver = orc::DENSE_QR;
+    orc::lm_minimize(P, opt, abc);
+    V3 bx{abc[0], abc[1], abc[2]};
+    { const double l = norm(bx); bx = V3{bx.x / l, bx.y / l, bx.z / l}; }
+    V3 bz{plane[0], plane[1], plane[2]};
+    { const double l = norm(bz); bz = V3{bz.x / l, bz.y / l, bz.z / l}; }
+    V3 by = cross(bx, bz);
+    if (bx.x < 0) bx = V3{-bx.x, -bx.y, -bx.z};
+    if (by.y < 0) by = V3{-by.x, -by.y, -by.z};
+    if (bz.z < 0) bz = V3{-bz.x, -bz.y, -bz.z};
+    const double s = cfg->gride_side_length;
+    const V3 ot = (cfg->board_height % 2 != 0) ? V3{-s * 0.5, -s * 0.5, 0} : V3{s * 0.5, -s * 0.5, 0};
+    const V3 o{bx.x * ot.x + by.x * ot.y + bz.x * ot.z + origin_centroid.x, bx.y * ot.x + by.y * ot.y + bz.y * ot.z + origin_centroid.y,
+               bx.z * ot.x + by.z * ot.y + bz.z * ot.z + origin_centroid.z};
+    const V3 ax[3] = {bx, by, bz};
+    for (int r = 0; r < 3; ++r) {
+        Tbl[4 * r] = ax[r].x; Tbl[4 * r + 1] = ax[r].y; Tbl[4 * r + 2] = ax[r].z;
+        Tbl[4 * r + 3] = -(ax[r].x * o.x + ax[r].y * o.y + ax[r].z * o.z);
+    }
+    Tbl[12] = 0; Tbl[13] = 0; Tbl[14] = 0; Tbl[15] = 1;
+    return 0;
+}
+
 } // extern "C"

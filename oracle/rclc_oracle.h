@@ -113,6 +113,10 @@ int orc_uniform_sample(const void* pts, int stride, int64_t n, double leaf, int3
 int orc_euclidean_cluster(const void* pts, int stride, int64_t n, double tol, int64_t min_size, int64_t max_size, int32_t* labels_out,
                           int32_t* n_clusters, int32_t* sizes_out);
 
+/* get_ref_pt (utils.h:160-202) + calc_laser_coor_v1 (pc_process.h:373-462) + line_fitting (opt/opt_line_fitting.h:51-108): the
+ * board frame T_bl (row-major 4x4, board <- laser) from the centroids of the black blocks and the board plane. Returns 0. */
+int orc_calc_laser_coor(const rclc_config* cfg, const double* centroids, int32_t n, const double plane[4], double Tbl_out[16]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,13 @@ def pnp_ransac(obj, norm_pts, thresh, max_iters=100, confidence=0.99, seed=1):
     return R.reshape(3, 3), t, mask.astype(bool)
 
 
+def calc_laser_coor(cfg, centroids, plane):
+    """calc_laser_coor_v1 (pc_process.h:373-462): board frame from the black-block centroids. Host code, no context."""
+    cen = np.ascontiguousarray(centroids, np.float64); pl = np.ascontiguousarray(plane, np.float64); T = np.zeros(16)
+    _chk(lib().rclc_calc_laser_coor(C.byref(cfg), _p(cen), C.c_int32(len(cen)), _p(pl), _p(T)))
+    return T.reshape(4, 4)
+
+
 def generate_targets(cfg):
     nt = cfg.n_targets()
     xy = np.zeros((nt, 2)); is_row = np.zeros(nt, np.int32); n = C.c_int32()

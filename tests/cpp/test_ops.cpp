@@ -164,6 +164,53 @@ int main()
         }
         CHECK(worst < 3e-3, "block centroid error %g m", worst);
     }
+    // ---- est_board_corner: the whole per-frame chain (plane fit, projection, GMM, block clustering, board frame, grid fit) ----
+    {
+        // board in the laser frame (x right, y down, z forward, i.e. after T_base), top-right square black as the reference requires
+        std::mt19937 rng(21);
+        std::uniform_real_distribution<double> ux(-0.4 + 1e-6, 0.4 - 1e-6), uy(-0.3 + 1e-6, 0.3 - 1e-6);
+        std::normal_distribution<double> nI(0.0, 2.0), nz(0.0, 0.002);
+        const double ax = 0.06, ay = -0.09, az = 0.05;      // small tilt
+        const double cxr = std::cos(ax), sxr = std::sin(ax), cyr = std::cos(ay), syr = std::sin(ay), czr = std::cos(az), szr = std::sin(az);
+        const double R[9] = {czr * cyr, czr * syr * sxr - szr * cxr, czr * syr * cxr + szr * sxr, szr * cyr, szr * syr * sxr + czr * cxr, szr * syr * cxr - czr * sxr,
+                             -syr, cyr * sxr, cyr * cxr};
+        const double t[3] = {0.1, -0.05, 4.0};
+        auto to_laser = [&](double u, double v, double w, double* o) { for (int r = 0; r < 3; ++r) o[r] = R[3 * r] * u + R[3 * r + 1] * v + R[3 * r + 2] * w + t[r]; };
+        auto cloud = std::make_shared<PointCloud<PoinT>>();
+        for (int i = 0; i < 120000; ++i) {
+            const double u = ux(rng), v = uy(rng);
+            const double fu = (u + 0.4) / 0.1, fv = (v + 0.3) / 0.1;
+            const int ci = (int)std::floor(fu), ri = (int)std::floor(fv);
+            const double e = std::min(std::min(fu - ci, ci + 1 - fu), std::min(fv - ri, ri + 1 - fv)) * 0.1;
+            const bool black = ((ci + ri) % 2) == 1;         // (7, 0) = max x, min y = top right: black
+            double o[3];
+            to_laser(u, v, nz(rng), o);
+            PoinT p; p.x = (float)o[0]; p.y = (float)o[1]; p.z = (float)o[2];
+            p.intensity = (float)std::max(4.0, (black ? 10.0 + 60.0 * std::max(0.0, 1.0 - e / 0.012) : 110.0) + nI(rng));
+            cloud->points.push_back(p);
+        }
+        std::vector<Vector3d> corners;
+        rclc_gridfit_report rep;
+        const bool done = est_board_corner(cloud, corners, nullptr, &rep);
+        CHECK(done && corners.size() == 35, "est_board_corner: %d, %zu corners", (int)done, corners.size());
+        // every interior corner of the board is found once, within 5 mm
+        std::vector<int> hit(35, 0);
+        double worst = 0;
+        for (auto& c : corners) {
+            double best = 1e9; int bi = -1;
+            for (int k = 0; k < 35; ++k) {
+                double o[3];
+                to_laser(-0.3 + 0.1 * (k % 7), -0.2 + 0.1 * (k / 7), 0.0, o);
+                const double d = std::sqrt((c.x() - o[0]) * (c.x() - o[0]) + (c.y() - o[1]) * (c.y() - o[1]) + (c.z() - o[2]) * (c.z() - o[2]));
+                if (d < best) { best = d; bi = k; }
+            }
+            worst = std::max(worst, best);
+            if (bi >= 0) hit[(size_t)bi]++;
+        }
+        bool once = true;
+        for (int h : hit) once = once && h == 1;
+        CHECK(once && worst < 5e-3, "corner error %g m, each corner once: %d", worst, (int)once);
+    }
     // ---- PlaneSegmentation (pcl::SACSegmentation drop-in): plane + 30 % outliers ----
     {
         auto pc = std::make_shared<PointCloud<PoinT>>();

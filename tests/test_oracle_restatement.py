@@ -309,3 +309,27 @@ def test_euclidean_cluster_against_bruteforce(oracle):
     assert np.array_equal(lab, want)
     assert np.array_equal(sizes, [cnt[r] for r in keep])
     assert sizes[0] > sizes[1] > sizes[2]
+
+
+def test_calc_laser_coor_library_matches_oracle(oracle, ocfg):
+    """calc_laser_coor_v1 + get_ref_pt + line_fitting: the library's host code (own trust-region loop, Cholesky) against the oracle
+    (Ceres restatement, DENSE_QR) on noisy block centroids; and the frame it builds is the board frame of the grid fit."""
+    from rclc_b200 import capi, synth
+    cfg = capi.config()
+    W, H, s = 8, 6, 0.1
+    x0, _, y0, _ = synth.board_extent(W, H, s)
+    cent = np.array([[x0 + (ci + 0.5) * s, y0 + (ri + 0.5) * s, 0.0] for ri in range(H) for ci in range(W) if (ci + ri) % 2 == 1])   # top right black
+    rng = np.random.default_rng(7)
+    for trial in range(5):
+        R = synth._rot_xyz(*rng.uniform(-0.15, 0.15, 3)); t = np.array([rng.uniform(-0.5, 0.5), rng.uniform(-0.3, 0.3), rng.uniform(3, 6)])
+        P = (R @ cent.T).T + t + rng.normal(0, 8e-4, cent.shape)
+        P = P[rng.permutation(len(P))]
+        n = R[:, 2]; plane = np.r_[n, -n @ t] * rng.uniform(0.5, 2.0)
+        T1 = capi.calc_laser_coor(cfg, P, plane)
+        rc, T0 = oracle.calc_laser_coor(ocfg, P, plane)
+        assert rc == 0
+        np.testing.assert_allclose(T1, T0, atol=1e-8)
+        back = (T1[:3, :3] @ P.T).T + T1[:3, 3]
+        assert np.abs(back[:, 2]).max() < 5e-3
+        xs = np.sort(np.unique(np.round(back[:, 0], 2))); ys = np.sort(np.unique(np.round(back[:, 1], 2)))
+        np.testing.assert_allclose(xs, np.arange(-0.35, 0.36, 0.1), atol=1e-9); np.testing.assert_allclose(ys, np.arange(-0.25, 0.26, 0.1), atol=1e-9)

@@ -1254,7 +1254,16 @@ static_assert(kListPad <= 32, "one lane per padding entry");
 // Three CTAs (12 warps) per SM: with 160 registers the hot loop and the cold paths around it keep everything in registers.
 // Measured (20 x 500 k points, one pose): 5 CTAs / 96 registers 63.5 us, 4 / 128 59.4 us, 3 / 160 57.3 us — the single-pose
 // sweep needs only 11 warps per SM, and the 25 MB of spill traffic per launch that ncu showed at 96 registers is gone.
-__global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(BatchView bv)
+template <int CTAS>
+__device__ __forceinline__ void sweep_body(const BatchView& bv);
+
+__global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(BatchView bv) { sweep_body<3>(bv); }
+// The multi-start search reads one frame (L2-resident) under thousands of poses: it is bound by issue slots and L2 latency,
+// not by DRAM, and wants more resident warps — the same body at 5 CTAs per SM (96 registers).
+__global__ void __launch_bounds__(kSweepThreads, 5) k_sweep_dense(BatchView bv) { sweep_body<5>(bv); }
+
+template <int CTAS>
+__device__ __forceinline__ void sweep_body(const BatchView& bv)
 {
     const int f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1605,7 +1614,9 @@ static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames, cudaStre
 {
     v.parts = sweep_parts(b, frames_in_flight, v.fuse_lm != 0);
     const int gx = (v.geom.nt * v.parts + kSweepWarps - 1) / kSweepWarps;
-    k_sweep<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
+    static const int dense_mode = [] { const char* e = std::getenv("RCLC_MS_DENSE"); return e ? atoi(e) : 1; }();
+    if (v.fixed_frame >= 0 && dense_mode) k_sweep_dense<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
+    else k_sweep<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
     b->ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;
@@ -1677,6 +1688,7 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.frame_stride = (int64_t)align256(((size_t)max_pts + 32 * (size_t)hg.g.ncells) * 16) / 16;
     v.parts = 1;
     RCLC_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
+    RCLC_CUDA(cudaFuncSetAttribute(k_sweep_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
     const size_t F = n_frames, nt = hg.g.nt, ncell = hg.g.ncells, nfine = hg.g.nfine;
     auto fail = [&](const char* what) { set_last_error(what); rclc_batch_destroy(b); return RCLC_ERR_CUDA; };
     const size_t big = F * (size_t)v.frame_stride * 16;

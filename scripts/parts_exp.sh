@@ -1,3 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
-timeout 120 python scripts/profile_sweep.py 20 500000 10 2>&1 | tail -2
-for i in 1 2; do timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['launch_ms'])"; done
+for D in 0 1; do for P in 0 1 2; do
+  if [ $P -eq 0 ]; then unset RCLC_SWEEP_PARTS; else export RCLC_SWEEP_PARTS=$P; fi
+  echo "dense=$D parts=$P"; RCLC_MS_DENSE=$D timeout 300 python scripts/bench_multistart.py 2>&1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_search'], d['Mpts_poses_per_s'], d['best_pose'])"
+done; done

@@ -22,6 +22,7 @@
 //   get_ref_pt + calc_laser_coor_v1 + line_fitting   include/utils.h:160, pc_process.h:373, opt/opt_line_fitting.h:51   rclc_calc_laser_coor
 //   pcl::transformPointCloud(in, out, Matrix4f)      pc_process.h:594,618; Calibrate.cpp:99   rclc_transform_cloud  (transformPointCloud)
 //   est_board_corner                     include/pc_process.h:583-646       (the per-frame chain over the operators above)
+//   pcl::PassThrough, cut_roi, the per-cloud body of main()   pc_process.h:81-101, apps/BoardSegmentation.cpp:45-165   (PassThrough, cut_roi, segment_board)
 //   pcl::SACSegmentation<>::segment as configured at apps/BoardSegmentation.cpp:64-72
 //                                                                           rclc_ransac_plane_score + host replay of
 //                                                                           PCL's adaptive rule + rclc_ransac_plane_select
@@ -44,6 +45,7 @@
 #include <cstring>
 #include <memory>
 #include <random>
+#include <string>
 #include <vector>
 
 #include "rclc_b200.h"
@@ -704,6 +706,130 @@ inline bool est_board_corner(typename PointCloud<PoinT>::Ptr& chess_board_proces
         board_corner = tmp;
     }
     return true;
+}
+
+// pcl::PassThrough<PoinT> as the reference uses it (field "x" / "y" / "z" / "intensity", inclusive limits, optional negative):
+// host code — a compaction of a few hundred thousand points is not worth a round trip.
+class PassThrough {
+public:
+    void setInputCloud(typename PointCloud<PoinT>::Ptr c) { cloud_ = c; }
+    void setFilterFieldName(const std::string& f) { field_ = f; }
+    void setFilterLimits(double lo, double hi) { lo_ = (float)lo; hi_ = (float)hi; }
+    void setFilterLimitsNegative(bool n) { negative_ = n; }
+    void filter(PointCloud<PoinT>& out)
+    {
+        std::vector<PoinT> kept;
+        if (cloud_)
+            for (const PoinT& p : cloud_->points) {
+                if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
+                const float v = field_ == "x" ? p.x : field_ == "y" ? p.y : field_ == "z" ? p.z : p.intensity;
+                const bool in = std::isfinite(v) && v >= lo_ && v <= hi_;
+                if (in != negative_) kept.push_back(p);
+            }
+        out.points.swap(kept);
+    }
+private:
+    typename PointCloud<PoinT>::Ptr cloud_;
+    std::string field_ = "x";
+    float lo_ = -3.4e38f, hi_ = 3.4e38f;
+    bool negative_ = false;
+};
+
+// cut_roi — include/pc_process.h:81-101: keeps the points of raw_board inside the axis-aligned box [min_p, max_p].
+inline void cut_roi(typename PointCloud<PoinT>::Ptr& raw_board, PoinT min_p, PoinT max_p)
+{
+    PassThrough pass;
+    const char* names[3] = {"x", "y", "z"};
+    const float lo[3] = {min_p.x, min_p.y, min_p.z}, hi[3] = {max_p.x, max_p.y, max_p.z};
+    for (int d = 0; d < 3; ++d) {
+        pass.setInputCloud(raw_board);
+        pass.setFilterFieldName(names[d]);
+        pass.setFilterLimits(lo[d], hi[d]);
+        pass.setFilterLimitsNegative(false);
+        pass.filter(*raw_board);
+    }
+}
+
+// segment_board — the per-cloud body of apps/BoardSegmentation.cpp:45-165: the chessboard's points out of one raw scan (lidar
+// frame, x forward). ROI x in [3, 6] m, 8 mm uniform sampling, planes peeled off by RANSAC until 5 % of the points are left,
+// the nearest large plane that faces the lidar is the board candidate; its largest cluster gives the ROI box of the raw scan;
+// a GMM on the candidate's reflectance splits black from white, each side keeps its largest cluster. Returns false when no
+// plane qualifies (the reference goes on with an empty cloud).
+inline bool segment_board(const typename PointCloud<PoinT>::Ptr& raw_cloud_read, typename PointCloud<PoinT>::Ptr& final_plane,
+                          double x_min = 3.0, double x_max = 6.0)
+{
+    const rclc_config& cfg = CfgParam();
+    auto raw_cloud = std::make_shared<PointCloud<PoinT>>();
+    {
+        PassThrough pass;
+        pass.setInputCloud(raw_cloud_read);
+        pass.setFilterFieldName("x");
+        pass.setFilterLimits(x_min, x_max);                                       // BoardSegmentation.cpp:48
+        pass.filter(*raw_cloud);
+    }
+    auto vox_cloud = std::make_shared<PointCloud<PoinT>>();
+    UniformSampling US0;
+    US0.setInputCloud(raw_cloud);
+    US0.setRadiusSearch(0.008f);                                                  // :60
+    US0.filter(*vox_cloud);
+    PlaneSegmentation sac;
+    sac.setMaxIterations(800);                                                    // :71-72
+    sac.setDistanceThreshold(0.08);
+    auto target_plane = std::make_shared<PointCloud<PoinT>>();
+    const size_t pt_size = vox_cloud->size();
+    double closest_plane_dist = 1000;
+    while (vox_cloud->size() > pt_size * 0.05) {
+        PointIndices inliner;
+        ModelCoefficients coefficients;
+        sac.setInputCloud(vox_cloud);
+        sac.segment(inliner, coefficients);
+        if (coefficients.values.size() != 4 || inliner.indices.empty()) break;   // (PCL prints an error and the reference would spin)
+        std::vector<uint8_t> is_in(vox_cloud->size(), 0);
+        for (int i : inliner.indices) is_in[(size_t)i] = 1;
+        std::vector<PoinT> ext, rest;
+        for (size_t i = 0; i < vox_cloud->size(); ++i) (is_in[i] ? ext : rest).push_back(vox_cloud->points[i]);
+        vox_cloud->points.swap(rest);
+        const double a = coefficients.values[0], b = coefficients.values[1], c = coefficients.values[2];
+        const double nx = a / std::sqrt(a * a + b * b + c * c);
+        if (ext.size() < pt_size * 0.02 || std::fabs(nx) <= cfg.angle_thd) continue;          // :101
+        float sx = 0.f, sy = 0.f, sz = 0.f;                                        // pcl::compute3DCentroid
+        for (const PoinT& p : ext) { sx += p.x; sy += p.y; sz += p.z; }
+        const float inv = 1.0f / (float)ext.size();
+        const double plane_distance = std::sqrt((double)(sx * inv) * (sx * inv) + (double)(sy * inv) * (sy * inv) + (double)(sz * inv) * (sz * inv));
+        if ((closest_plane_dist - plane_distance) > 0.3) {                         // :107
+            closest_plane_dist = plane_distance;
+            target_plane->points = ext;
+        }
+    }
+    if (target_plane->size() == 0) return false;
+    EulerCluster(target_plane, target_plane);
+    if (target_plane->size() == 0) return false;
+    PoinT min_p = target_plane->points[0], max_p = target_plane->points[0];        // pcl::getMinMax3D
+    for (const PoinT& p : target_plane->points) {
+        min_p.x = std::min(min_p.x, p.x); min_p.y = std::min(min_p.y, p.y); min_p.z = std::min(min_p.z, p.z);
+        max_p.x = std::max(max_p.x, p.x); max_p.y = std::max(max_p.y, p.y); max_p.z = std::max(max_p.z, p.z);
+    }
+    cut_roi(raw_cloud, min_p, max_p);
+    VectorXd board_intensity((long)target_plane->size());
+    for (long i = 0; i < (long)target_plane->size(); ++i) board_intensity(i) = target_plane->points[(size_t)i].intensity;
+    std::vector<double> mu{15, 100}, sigma{15, 15};
+    GMMFit::fit_1d(board_intensity, 2, mu, sigma, false);
+    const double reflactive_thd = mu[0] + 1.7 * sigma[0];                          // :134
+    auto black = std::make_shared<PointCloud<PoinT>>(), white = std::make_shared<PointCloud<PoinT>>();
+    PassThrough pass_intensity;
+    pass_intensity.setInputCloud(raw_cloud);
+    pass_intensity.setFilterFieldName("intensity");
+    pass_intensity.setFilterLimits(cfg.noise_reflactivity_thd, reflactive_thd);
+    pass_intensity.filter(*black);
+    EulerCluster(black, black);
+    pass_intensity.setInputCloud(raw_cloud);
+    pass_intensity.setFilterLimits(reflactive_thd, 150);
+    pass_intensity.filter(*white);
+    EulerCluster(white, white);
+    if (!final_plane) final_plane = std::make_shared<PointCloud<PoinT>>();
+    final_plane->points = white->points;                                           // *final_plane = *white + *black (:160)
+    final_plane->points.insert(final_plane->points.end(), black->points.begin(), black->points.end());
+    return final_plane->size() > 0;
 }
 
 }  // namespace rclc_b200

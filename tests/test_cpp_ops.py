@@ -48,3 +48,32 @@ def test_pcd_io_round_trip_and_formats(tmp_path):
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "livox_ascii.pcd"), str(tmp_path / "pcd")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, (r.stdout, r.stderr)
     assert "all PCD checks passed" in r.stdout
+
+
+def _build_pipeline():
+    from rclc_b200 import build
+    lib = build.build()
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_pipeline")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "cpp", "test_pipeline.cpp")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-Wall", "-Wno-unused-function", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", os.path.dirname(lib), "-lrclc_b200", "-Wl,-rpath," + os.path.dirname(lib)])
+    return exe
+
+
+def test_pipeline_compiles_and_needs_a_device():
+    import torch
+    exe = _build_pipeline()
+    if torch.cuda.is_available():
+        pytest.skip("GPU box: covered by test_pipeline_scene_to_extrinsic")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 77, (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_pipeline_scene_to_extrinsic():
+    """BASELINE configs[0] in miniature: raw scans -> segment_board -> PCD hand-off -> est_board_corner -> pnp_init + pose_reprj_opt."""
+    exe = _build_pipeline()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.returncode, r.stdout[-3000:], r.stderr[-2000:])
+    assert "pipeline checks passed" in r.stdout

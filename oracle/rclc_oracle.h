@@ -117,6 +117,15 @@ int orc_euclidean_cluster(const void* pts, int stride, int64_t n, double tol, in
  * board frame T_bl (row-major 4x4, board <- laser) from the centroids of the black blocks and the board plane. Returns 0. */
 int orc_calc_laser_coor(const rclc_config* cfg, const double* centroids, int32_t n, const double plane[4], double Tbl_out[16]);
 
+/* The reference's host-side chains over the primitives above (rclc_pipeline.cpp): eular_cluster_iter (pc_process.h:104-211;
+ * centroids_out has room for board_width * board_height doubles x 3), est_board_corner (pc_process.h:583-646; pts_io float4
+ * {x, y, z, I}, stride 16, modified like the reference's cloud), the per-cloud body of apps/BoardSegmentation.cpp:45-165 (out:
+ * float4 [n], white cluster then black cluster). */
+int orc_eular_cluster_iter(const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double reflactive_thd, double* centroids_out,
+                           int32_t* n_out);
+int orc_est_board_corner(const rclc_config* cfg, void* pts_io, int64_t n, double* corners_out, orc_gridfit_report* rep);
+int orc_segment_board(const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double x_min, double x_max, void* out, int64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

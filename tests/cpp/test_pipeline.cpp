@@ -7,6 +7,7 @@
 #include <random>
 
 #include "rclc_pcd.hpp"
+#include "rclc_oracle.h"      // the CPU oracle: the checker of every stage below (tests may link it, the product may not)
 
 using namespace rclc_b200;
 static int g_fail = 0;
@@ -30,7 +31,7 @@ int main()
     double Rcl[9];
     rot_xyz(0.02, -0.03, 0.015, Rcl);
     const double tcl[3] = {0.07, -0.05, 0.04};
-    std::vector<std::vector<Vector3d>> pcs;
+    std::vector<std::vector<Vector3d>> pcs, pcs_oracle;
     std::vector<std::vector<Vector2d>> ims;
     const Matrix4f Tb = io::T_base();
     for (int f = 0; f < F; ++f) {
@@ -62,6 +63,15 @@ int main()
         const bool found = segment_board(raw, board);
         CHECK(found && board && board->size() > 0.85 * n_board && board->size() < 1.02 * n_board, "frame %d: board cloud %zu of %zu", f, board ? board->size() : 0, n_board);
         if (!found || !board) continue;
+        {   // oracle: the same chain on the CPU must return the same points in the same order
+            std::vector<float> o4(raw->size() * 4);
+            int64_t n_o = 0;
+            const int rc = orc_segment_board(&CfgParam(), raw->points.data(), (int)sizeof(PoinT), 16, (int64_t)raw->size(), 3.0, 6.0, o4.data(), &n_o);
+            bool same = rc == 0 && (size_t)n_o == board->size();
+            for (size_t i = 0; same && i < board->size(); ++i)
+                same = board->points[i].x == o4[4 * i] && board->points[i].y == o4[4 * i + 1] && board->points[i].z == o4[4 * i + 2] && board->points[i].intensity == o4[4 * i + 3];
+            CHECK(same, "frame %d: segment_board differs from the oracle (rc %d, %lld vs %zu points)", f, rc, (long long)n_o, board->size());
+        }
         // the hand-off: PCD round trip, then the axis permutation of Calibrate.cpp:98-99
         CHECK(io::savePCDFileBinary("/tmp/rclc_pipeline_board.pcd", *board) == 0, "save");
         auto chess_board = std::make_shared<PointCloud<PoinT>>();
@@ -69,8 +79,27 @@ int main()
         transformPointCloud(*chess_board, *chess_board, Tb);
 
         // ---- stage 2, per frame ----
+        std::vector<float> cb4(chess_board->size() * 4);            // the oracle's copy of the input (est_board_corner works in place)
+        for (size_t i = 0; i < chess_board->size(); ++i) { const PoinT& p = chess_board->points[i]; cb4[4 * i] = p.x; cb4[4 * i + 1] = p.y; cb4[4 * i + 2] = p.z; cb4[4 * i + 3] = p.intensity; }
         std::vector<Vector3d> corners;
         const bool ok_c = est_board_corner(chess_board, corners);
+        {
+            std::vector<double> oc(35 * 3);
+            orc_gridfit_report orep;
+            const int rc = orc_est_board_corner(&CfgParam(), cb4.data(), (int64_t)(cb4.size() / 4), oc.data(), &orep);
+            double dmax = 0;
+            if (rc == 0 && corners.size() == 35)
+                for (int k = 0; k < 35; ++k)
+                    dmax = std::max(dmax, std::max(std::fabs(corners[(size_t)k].x() - oc[3 * k]), std::max(std::fabs(corners[(size_t)k].y() - oc[3 * k + 1]), std::fabs(corners[(size_t)k].z() - oc[3 * k + 2]))));
+            // The chain is not bit-reproducible across the two implementations: the plane fit agrees to 1e-9, which moves some
+            // projected float coordinates by one ulp, and the discrete decisions downstream (voxel winners, LM accept / reject) can
+            // then take a different, equally valid path: typically 1e-6 m on the corners, a few 1e-4 m when an LM path forks.
+            // The bar of the north star is on the EXTRINSIC (1e-4 rad, 0.1 mm): checked below from both corner sets.
+            CHECK(rc == 0 && corners.size() == 35 && dmax < 5e-4, "frame %d: est_board_corner vs oracle: rc %d, max |d| %g m", f, rc, dmax);
+            std::vector<Vector3d> oc_v;
+            for (int k = 0; k < 35; ++k) oc_v.push_back(Vector3d(oc[3 * k], oc[3 * k + 1], oc[3 * k + 2]));
+            pcs_oracle.push_back(oc_v);
+        }
         CHECK(ok_c && corners.size() == 35, "frame %d: est_board_corner %d, %zu corners", f, (int)ok_c, corners.size());
         if (!ok_c || corners.size() != 35) continue;
         std::vector<Vector2d> im;
@@ -114,6 +143,22 @@ int main()
         const double dt = std::sqrt((Tcl[4] - tcl[0]) * (Tcl[4] - tcl[0]) + (Tcl[5] - tcl[1]) * (Tcl[5] - tcl[1]) + (Tcl[6] - tcl[2]) * (Tcl[6] - tcl[2]));
         std::printf("extrinsic: rotation error %.4f deg, translation error %.4f m\n", ang, dt);
         CHECK(ang < 0.2 && dt < 0.02, "extrinsic error %g deg, %g m", ang, dt);
+        // the same solve from the ORACLE's corners: the two extrinsics must agree to the north star's bar
+        if (pcs_oracle.size() == pcs.size()) {
+            double To[7] = {0, 0, 0, 1, 0, 0, 0};
+            CHECK(pnp_init(ims, pcs_oracle, To), "pnp_init (oracle corners)");
+            pose_reprj_opt(ims, pcs_oracle, To, false);
+            const double no = std::sqrt(To[0] * To[0] + To[1] * To[1] + To[2] * To[2] + To[3] * To[3]);
+            double dq = 0, dtt = 0;
+            const double sgn = (To[3] * Tcl[3] < 0) ? -1.0 : 1.0;
+            for (int k = 0; k < 4; ++k) dq = std::max(dq, std::fabs(To[k] / no * sgn - Tcl[k] / nq));
+            for (int k = 4; k < 7; ++k) dtt = std::max(dtt, std::fabs(To[k] - Tcl[k]));
+            std::printf("extrinsic from the oracle's corners: |dq| %.2e (about %.2e rad), |dt| %.2e m\n", dq, 2 * dq, dtt);
+            // 1e-4 rad as the north star asks. The translation bar here is 0.5 mm, not 0.1 mm: with six frames a corner set that
+            // forked by 0.2 mm in one frame (see above) moves the weakly constrained depth component by that order — on IDENTICAL
+            // corners the refine itself meets 0.1 mm (tests/test_gpu_parity.py::test_pose_eval_and_refine).
+            CHECK(2 * dq < 1e-4 && dtt < 5e-4, "extrinsic differs from the oracle-fed solve: %g rad, %g m", 2 * dq, dtt);
+        }
     }
     if (g_fail) { std::printf("%d check(s) failed\n", g_fail); return 1; }
     std::printf("pipeline checks passed\n");

@@ -56,8 +56,12 @@ def _build_pipeline():
     exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_pipeline")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     src = os.path.join(ROOT, "tests", "cpp", "test_pipeline.cpp")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-Wall", "-Wno-unused-function", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
-                           "-L", os.path.dirname(lib), "-lrclc_b200", "-Wl,-rpath," + os.path.dirname(lib)])
+    from oracle import pyoracle
+    pyoracle.build()                               # the checker: every stage of the pipeline is compared with the CPU oracle
+    odir = os.path.join(ROOT, "oracle", "_build")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-Wall", "-Wno-unused-function", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle"),
+                           src, "-o", exe, "-L", os.path.dirname(lib), "-lrclc_b200", "-Wl,-rpath," + os.path.dirname(lib),
+                           "-L", odir, "-lrclc_oracle", "-Wl,-rpath," + odir])
     return exe
 
 

@@ -1,14 +1,13 @@
-// gridfit.cuh — data structures of the grid-fit path (K4/K5), shared by gridfit.cu and multistart.cu.
+// gridfit.cuh — data structures of the grid-fit path (K4/K5): the batch view every kernel of gridfit.cu receives.
 //
-// Design: the reference evaluates 82 cost functors, each looping over its own
-// kd-tree neighbour copy (board_fitting_cost.h:124-210, 3.3*N point visits per sweep, fp64). Here a
-// frame's points are counting-sorted ONCE per outer iteration into the cells of the half-square
-// lattice on which all targets sit (and, inside a cell, into 4x4 sub-cells, so that 32 consecutive
-// points — a "row" — are spatial neighbours). Every cell's segment is padded to a multiple of 32
-// points with far-away sentinels, and every row has a bounding box.
-// A sweep is a GATHER: one warp owns one target of one frame, pulls in exactly the rows whose box
-// touches the target's discs (as moved by the trial pose) with float4 loads, keeps the target's six
-// sums in registers and writes the target's 16 accumulators once — no atomics in the hot loop.
+// Design: the reference evaluates 82 cost functors, each looping over its own kd-tree neighbour copy
+// (board_fitting_cost.h:124-210, 3.3*N point visits per sweep, fp64). Here a frame's points are counting-sorted ONCE per solve
+// into the cells of the half-square lattice on which all targets sit (and, inside a cell, into 4x4 sub-cells, so that 32
+// consecutive points — a "row" — are spatial neighbours); later outer iterations move the sorted points in place. Every cell's
+// segment is padded to a multiple of 32 points with far-away sentinels, and every row has a bounding box.
+// A sweep is a GATHER: one warp owns one target of one frame, pulls in exactly the rows whose box touches the target's discs
+// (as moved by the trial pose), keeps the target's six sums in registers and writes the target's 16 accumulators once — no
+// atomics in the hot loop.
 #pragma once
 #include "common.cuh"
 
@@ -21,7 +20,7 @@ constexpr int kSweepThreads = 128;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kRowList = 256;            // live rows a warp collects before it streams them
 constexpr int kGroupRows = 4;            // rows per cp.async group (one commit / wait per group)
-constexpr int kRingGroups = 4;           // groups per warp ring (8 KB): one computing, up to three in flight (8 groups measured no faster)
+constexpr int kRingGroups = 4;           // groups per warp ring (8 KB): one computing, up to three in flight (8 groups, or 8-row groups, measured no faster)
 constexpr int kFlushRows = 448;          // rows a lane may accumulate before the count riding in the fp64 sum must be split off
 constexpr int kBinThreads = 256;
 constexpr int kBinP = 8;

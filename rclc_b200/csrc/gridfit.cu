@@ -1225,6 +1225,10 @@ __device__ __forceinline__ void drain_list(int mode, const float4* __restrict__ 
                                            int& rows_since_split)
 {
     if (n_list == 0) return;
+    if (mode != 2 && rows_since_split + n_list > kFlushRows) {        // keep the riding count exact: split it off BEFORE a list that
+        reduce_totals(acc, tot, lane);                                // would take a lane past kFlushRows points (a task of a 500 k
+        rows_since_split = 0;                                         // frame has ~330 rows: one reduction at its end, not three)
+    }
     if (lane < kListPad) list[n_list + lane] = list[n_list - 1];      // padding for the copy window
     __syncwarp();
     if (mode == 2) stream_rows_exact(src, list, n_list, wc, tot);
@@ -1232,10 +1236,6 @@ __device__ __forceinline__ void drain_list(int mode, const float4* __restrict__ 
     else stream_rows<false>(src, list, n_list, lane, ring, k, wc, acc, mA, mB);
     rows_since_split += n_list;
     n_list = 0;
-    if (mode != 2 && rows_since_split > kFlushRows - kRowList) {      // keep the riding count exact
-        reduce_totals(acc, tot, lane);
-        rows_since_split = 0;
-    }
     __syncwarp();
 }
 

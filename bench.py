@@ -191,6 +191,10 @@ def run_ours(args):
     cfg = capi.config()
     ctx = capi.Context(local)
     frames, perts = make_frames(args.frames, args.pts, rank)
+    # the step's inputs live in page-locked host memory (the bench contract's "pinned host memory"): the library's upload then
+    # needs no staging copy, the H2D DMA reads the records in place
+    pinned = [torch.from_numpy(p).pin_memory() for p in frames]
+    frames = [t.numpy() for t in pinned]
     F = len(frames)
     batch = capi.Batch(ctx, cfg, F, max(len(p) for p in frames))
     for f, p in enumerate(frames):
@@ -206,7 +210,7 @@ def run_ours(args):
 
     def step_e2e():
         for f, p in enumerate(frames):
-            batch.upload(f, p)                       # host -> pinned -> device, every step
+            batch.upload(f, p)                       # pinned host -> device, every step
         batch.gmm_fit()
         corners, reps = batch.gridfit_solve()        # device -> host: corners + reports
         return sum(len(frames[f]) * reps[f].pose_evals for f in range(F)), corners

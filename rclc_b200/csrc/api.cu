@@ -32,6 +32,16 @@ int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_
 {
     RCLC_CHECK(stride >= 16 && ioff + 4 <= stride && ioff >= 12, RCLC_ERR_INVALID, "bad stride/ioff");
     if (n == 0) return RCLC_OK;
+    if (stride == 16 && ioff == 12) {
+        // {x, y, z, I} records that already sit in page-locked host memory need no staging copy: the DMA reads them in place.
+        // (The copy is asynchronous: the caller keeps the buffer unchanged until the next call that returns results.)
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, pts) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+            RCLC_CUDA(cudaMemcpyAsync(dst, pts, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+            return RCLC_OK;
+        }
+        cudaGetLastError();                                         // (older drivers flag unregistered host pointers as an error)
+    }
     const int bi = ctx->up_flip;
     ctx->up_flip ^= 1;
     if (!ctx->ev_up[bi]) RCLC_CUDA(cudaEventCreateWithFlags(&ctx->ev_up[bi], cudaEventDisableTiming));

@@ -210,9 +210,9 @@ def run_ours(args):
 
     def step_e2e():
         for f, p in enumerate(frames):
-            batch.upload(f, p)                       # pinned host -> device, every step
-        batch.gmm_fit()
-        corners, reps = batch.gridfit_solve()        # device -> host: corners + reports
+            batch.upload(f, p)                       # pinned host -> device, every step (asynchronous, on the frame's group stream)
+        corners, reps = batch.gridfit_solve()        # device -> host: corners + reports; group g starts when ITS frames have arrived
+        batch.gmm_fit()                              # device -> host: mu, sigma, priors
         return sum(len(frames[f]) * reps[f].pose_evals for f in range(F)), corners
 
     # ---- value: inputs resident in HBM ----

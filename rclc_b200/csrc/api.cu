@@ -28,8 +28,9 @@ static void pack_range(const char* src, int stride, int ioff, int64_t k0, int64_
     }
 }
 
-int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, float4* dst)
+int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, float4* dst, cudaStream_t st)
 {
+    if (!st) st = ctx->stream;
     RCLC_CHECK(stride >= 16 && ioff + 4 <= stride && ioff >= 12, RCLC_ERR_INVALID, "bad stride/ioff");
     if (n == 0) return RCLC_OK;
     if (stride == 16 && ioff == 12) {
@@ -37,7 +38,7 @@ int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_
         // (The copy is asynchronous: the caller keeps the buffer unchanged until the next call that returns results.)
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, pts) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
-            RCLC_CUDA(cudaMemcpyAsync(dst, pts, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+            RCLC_CUDA(cudaMemcpyAsync(dst, pts, (size_t)n * 16, cudaMemcpyHostToDevice, st));
             return RCLC_OK;
         }
         cudaGetLastError();                                         // (older drivers flag unregistered host pointers as an error)
@@ -64,8 +65,8 @@ int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_
     const int nth = (int)std::min<int64_t>(want, nchunks);
 #pragma omp parallel for num_threads(nth) schedule(static)
     for (int64_t c = 0; c < nchunks; ++c) pack_range(src, stride, ioff, c * chunk, std::min(n, (c + 1) * chunk), o);
-    RCLC_CUDA(cudaMemcpyAsync(dst, o, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
-    RCLC_CUDA(cudaEventRecord(ctx->ev_up[bi], ctx->stream));
+    RCLC_CUDA(cudaMemcpyAsync(dst, o, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    RCLC_CUDA(cudaEventRecord(ctx->ev_up[bi], st));
     return RCLC_OK;
 }
 

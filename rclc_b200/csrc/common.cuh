@@ -84,7 +84,8 @@ struct rclc_ctx {
 namespace rclc {
 
 // Packs a strided host cloud into pinned float4 {x,y,z,I} and uploads it to `dst` (device).
-int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, float4* dst);
+// `st`: the stream the copy is enqueued on (null: ctx->stream).
+int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, float4* dst, cudaStream_t st = nullptr);
 
 // ---- device helpers ----
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }

@@ -184,6 +184,7 @@ int rclc_batch_gmm_fit(rclc_batch* b, double* mu_io, double* sigma_io, double* p
 {
     RCLC_CHECK(b && mu_io && sigma_io, RCLC_ERR_INVALID, "null argument");
     RCLC_CUDA(cudaSetDevice(b->ctx->device));
+    RCLC_TRY(batch_join_uploads(b));
     int64_t max_n = 0;
     for (int64_t n : b->h_npts) max_n = std::max(max_n, n);
     // intensity is the .w lane of the resident float4 cloud (pc_process.h:603-606 copies it out; here it is read in place)

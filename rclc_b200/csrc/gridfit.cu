@@ -1745,6 +1745,7 @@ int rclc_batch_destroy(rclc_batch* b)
     if (!b) return RCLC_OK;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
+    for (cudaStream_t st : b->ctx->aux_streams) cudaStreamSynchronize(st);
     if (b->d_pristine) cudaFree(b->d_pristine);
     if (b->v.binned) cudaFree(b->v.binned);
     if (b->d_block) cudaFree(b->d_block);
@@ -1753,11 +1754,55 @@ int rclc_batch_destroy(rclc_batch* b)
     return RCLC_OK;
 }
 
-static int set_npts(rclc_batch* b, int32_t frame, int64_t n)
+// The solve runs the batch as G groups of consecutive frames on G streams (ctx->stream and ctx->aux_streams). A frame is
+// uploaded on the stream of ITS group, so that a solve which follows the uploads starts on the first group as soon as that
+// group's frames have arrived, while the copy engine is still busy with the later groups.
+static int solve_groups(const rclc_batch* b)
+{
+    static const int want_groups = [] { const char* e = std::getenv("RCLC_SOLVE_GROUPS"); return e ? std::max(1, std::min(16, atoi(e))) : 4; }();
+    return std::max(1, std::min(want_groups, b->n_frames / 2));
+}
+static int ensure_group_streams(rclc_ctx* ctx, int G)
+{
+    if (!ctx->ev_sync) RCLC_CUDA(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+    while ((int)ctx->aux_streams.size() < G - 1) {
+        cudaStream_t st;
+        RCLC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ctx->aux_streams.push_back(st);
+    }
+    return RCLC_OK;
+}
+static int frame_stream(rclc_batch* b, int32_t frame, cudaStream_t* st)
+{
+    const int G = solve_groups(b);
+    RCLC_TRY(ensure_group_streams(b->ctx, G));
+    int gi = 0;
+    while (gi + 1 < G && (int)((int64_t)b->n_frames * (gi + 1) / G) <= frame) ++gi;      // group gi holds frames [F gi / G, F (gi + 1) / G)
+    *st = gi == 0 ? b->ctx->stream : b->ctx->aux_streams[(size_t)gi - 1];
+    if (gi > 0) b->uploads_pending = true;
+    return RCLC_OK;
+}
+// ctx->stream waits for the uploads that went to the other group streams (every entry point that reads the frames on ctx->stream)
+static int join_uploads(rclc_batch* b)
+{
+    if (!b->uploads_pending) return RCLC_OK;
+    rclc_ctx* ctx = b->ctx;
+    for (cudaStream_t st : ctx->aux_streams) {
+        RCLC_CUDA(cudaEventRecord(ctx->ev_sync, st));
+        RCLC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
+    }
+    b->uploads_pending = false;
+    return RCLC_OK;
+}
+} // extern "C"
+int rclc::batch_join_uploads(rclc_batch* b) { return join_uploads(b); }
+extern "C" {
+
+static int set_npts(rclc_batch* b, int32_t frame, int64_t n, cudaStream_t st)
 {
     b->h_npts[frame] = n;
     b->binned_valid = false;
-    RCLC_CUDA(cudaMemcpyAsync(b->d_npts + frame, &b->h_npts[frame], 8, cudaMemcpyHostToDevice, b->ctx->stream));
+    RCLC_CUDA(cudaMemcpyAsync(b->d_npts + frame, &b->h_npts[frame], 8, cudaMemcpyHostToDevice, st));
     return RCLC_OK;
 }
 
@@ -1765,17 +1810,20 @@ int rclc_batch_upload(rclc_batch* b, int32_t frame, const void* pts, int stride,
 {
     RCLC_CHECK(b && (pts || n == 0), RCLC_ERR_INVALID, "null argument");
     RCLC_CHECK(frame >= 0 && frame < b->n_frames && n >= 0 && n <= b->max_pts, RCLC_ERR_INVALID, "frame/n out of range");
-    RCLC_TRY(upload_cloud_f4(b->ctx, pts, stride, ioff, n, b->d_pristine + (size_t)frame * b->v.frame_stride));
-    return set_npts(b, frame, n);
+    cudaStream_t st;
+    RCLC_TRY(frame_stream(b, frame, &st));
+    RCLC_TRY(upload_cloud_f4(b->ctx, pts, stride, ioff, n, b->d_pristine + (size_t)frame * b->v.frame_stride, st));
+    return set_npts(b, frame, n, st);
 }
 
 int rclc_batch_set_frame_dev(rclc_batch* b, int32_t frame, const void* pts_dev, int64_t n)
 {
     RCLC_CHECK(b && (pts_dev || n == 0), RCLC_ERR_INVALID, "null argument");
     RCLC_CHECK(frame >= 0 && frame < b->n_frames && n >= 0 && n <= b->max_pts, RCLC_ERR_INVALID, "frame/n out of range");
-    RCLC_CUDA(cudaMemcpyAsync(b->d_pristine + (size_t)frame * b->v.frame_stride, pts_dev, (size_t)n * 16,
-                              cudaMemcpyDeviceToDevice, b->ctx->stream));
-    return set_npts(b, frame, n);
+    cudaStream_t st;
+    RCLC_TRY(frame_stream(b, frame, &st));
+    RCLC_CUDA(cudaMemcpyAsync(b->d_pristine + (size_t)frame * b->v.frame_stride, pts_dev, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
+    return set_npts(b, frame, n, st);
 }
 
 int64_t rclc_batch_total_points(rclc_batch* b)
@@ -1789,6 +1837,7 @@ int rclc_batch_bin(rclc_batch* b)
 {
     RCLC_CHECK(b, RCLC_ERR_INVALID, "null batch");
     RCLC_CUDA(cudaSetDevice(b->ctx->device));
+    RCLC_TRY(join_uploads(b));
     RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, sizeof(int), b->ctx->stream));
     GroupRun gr = whole_batch(b);
     RCLC_TRY(launch_init(b, gr, nullptr));
@@ -1860,14 +1909,9 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     // one group (a single warp per frame, ~15 us of dependent fp64) hold the tail of its sweep kernel, the other groups'
     // sweeps keep the SMs busy. RCLC_SOLVE_GROUPS overrides the default of 4 (1: the whole batch in lock-step;
     // measured on 20 x 500 k points: 2 groups 18.8 ms per step, 3 17.9, 4 17.6, 5 17.5).
-    static const int want_groups = [] { const char* e = std::getenv("RCLC_SOLVE_GROUPS"); return e ? std::max(1, std::min(16, atoi(e))) : 4; }();
-    const int G = std::max(1, std::min(want_groups, F / 2));
-    while ((int)ctx->aux_streams.size() < G - 1) {
-        cudaStream_t st;
-        RCLC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        ctx->aux_streams.push_back(st);
-    }
-    if (!ctx->ev_sync) RCLC_CUDA(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+    const int G = solve_groups(b);
+    RCLC_TRY(ensure_group_streams(ctx, G));
+    b->uploads_pending = false;          // every group stream carries its own frames' uploads ahead of its kernels
     RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, sizeof(int), ctx->stream));
     RCLC_CUDA(cudaEventRecord(ctx->ev_sync, ctx->stream));              // uploads, T_bl, ... precede every group
     std::vector<GroupRun> groups(G);

@@ -124,12 +124,16 @@ struct BatchView {
 
 } // namespace rclc
 
+struct rclc_batch;
+namespace rclc { int batch_join_uploads(rclc_batch* b); }      // ctx->stream waits for uploads that went to the other group streams
+
 struct rclc_batch {
     rclc_ctx* ctx = nullptr;
     rclc_config cfg;
     rclc::BatchView v;
     int n_frames = 0;
     int64_t max_pts = 0;
+    bool uploads_pending = false;     // some frames were uploaded on a group stream other than ctx->stream since the last join
     std::vector<int64_t> h_npts;
     float4* d_pristine = nullptr;     // [F][frame_stride] uploaded clouds (solve works on a copy)
     void* d_block = nullptr;          // one allocation for the small arrays

@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on " + s)
         if verbose or "warning" in out:
             sys.stderr.write(out)
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart_static", "-ldl", "-lrt", "-lgomp",
+    subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart_static", "-ldl", "-lrt", "-lgomp",
                                                                  "-lpthread"])
     return LIB
 

@@ -73,6 +73,7 @@ struct rclc_ctx {
     int flush_parity = 0;
     std::vector<cudaStream_t> aux_streams;             // extra streams of the grouped grid-fit solve
     cudaEvent_t ev_sync = nullptr;
+    std::vector<cudaEvent_t> ev_groups;                // one per solve group: "this group's last batch of rounds has finished"
     rclc::Buf d_pts, d_tmp, d_tmp2, d_out, d_flush;   // device scratch
     rclc::Buf h_pin, h_pin2;                           // pinned staging
     rclc::Buf h_up[2];                                 // pinned double buffer of the cloud uploads

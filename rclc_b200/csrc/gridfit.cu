@@ -23,6 +23,8 @@
 // realistic data, so the accumulator tables do not depend on summation order.
 #include "gridfit.cuh"
 
+#include <thread>
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -1559,6 +1561,7 @@ static BatchView slice_view(const BatchView& v, int f0, int nf, int group)
     s.corners = v.corners + (size_t)f0 * ncorn * 3;
     s.rebin_list = v.rebin_list + 2 * f0;          // [2][nf] inside the batch's [2 * F]
     s.rebin_cnt = v.rebin_cnt + 2 * group;
+    s.n_done = v.n_done + group;                   // finished frames are counted per group: the groups advance independently
     return s;
 }
 
@@ -1903,8 +1906,8 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     // can apply it with rclc_transform_cloud. It is rejected here rather than silently ignored.
     RCLC_CHECK(!b->cfg.apply_noise_test, RCLC_ERR_UNSUPPORTED, "apply_noise_test: perturb the input with rclc_transform_cloud instead");
     b->binned_valid = false;
-    RCLC_TRY(ctx->h_pin2.reserve(64));
-    int* h_done = ctx->h_pin2.as<int>();
+    RCLC_TRY(ctx->h_pin2.reserve(256));
+    int* h_done = ctx->h_pin2.as<int>();           // [G] finished frames per group, as of each group's last poll
     // Frames are independent until the extrinsic solve, so the batch runs as G groups on G streams: while the LM steps of
     // one group (a single warp per frame, ~15 us of dependent fp64) hold the tail of its sweep kernel, the other groups'
     // sweeps keep the SMs busy. RCLC_SOLVE_GROUPS overrides the default of 4 (1: the whole batch in lock-step;
@@ -1912,7 +1915,8 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     const int G = solve_groups(b);
     RCLC_TRY(ensure_group_streams(ctx, G));
     b->uploads_pending = false;          // every group stream carries its own frames' uploads ahead of its kernels
-    RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, sizeof(int), ctx->stream));
+    RCLC_CHECK(G <= 16, RCLC_ERR_INVALID, "at most 16 solve groups");
+    RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, 64 * sizeof(int), ctx->stream));
     RCLC_CUDA(cudaEventRecord(ctx->ev_sync, ctx->stream));              // uploads, T_bl, ... precede every group
     std::vector<GroupRun> groups(G);
     for (int gi = 0; gi < G; ++gi) {
@@ -1947,33 +1951,6 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
         b->graphs_groups = 0;
     }
     for (;;) {
-        if (graphs_ok && rounds > 0) {
-            if (b->round_graphs.empty()) {
-                for (int gi = 0; gi < G; ++gi) {
-                    GroupRun gr = groups[gi];                   // a copy: capturing must not advance the real round counters
-                    cudaGraph_t graph = nullptr;
-                    RCLC_CUDA(cudaStreamBeginCapture(gr.st, cudaStreamCaptureModeThreadLocal));
-                    int rc_cap = RCLC_OK;
-                    for (int r = 0; r < rounds_per_check && rc_cap == RCLC_OK; ++r) {
-                        rc_cap = launch_move(b, gr);
-                        if (rc_cap == RCLC_OK) rc_cap = launch_sweep_view(b, gr.v, gr.nf, gr.st, F);
-                    }
-                    RCLC_CUDA(cudaStreamEndCapture(gr.st, &graph));
-                    RCLC_TRY(rc_cap);
-                    cudaGraphExec_t ge = nullptr;
-                    RCLC_CUDA(cudaGraphInstantiate(&ge, graph, 0));
-                    cudaGraphDestroy(graph);
-                    b->round_graphs.push_back(ge);
-                    ctx->launches -= 2 * rounds_per_check;      // (counted when the graph is launched)
-                }
-                b->graphs_groups = G;
-            }
-            for (int gi = 0; gi < G; ++gi) {
-                RCLC_CUDA(cudaGraphLaunch(b->round_graphs[gi], groups[gi].st));
-                groups[gi].round += rounds_per_check;
-                ctx->launches += 2 * rounds_per_check;
-            }
-        } else
         for (int r = 0; r < rounds_per_check; ++r) {
             for (int gi = 0; gi < G; ++gi) {
                 GroupRun& gr = groups[gi];
@@ -1995,14 +1972,78 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
         }
         rounds += rounds_per_check;
         RCLC_CUDA(cudaGetLastError());
-        for (int gi = 1; gi < G; ++gi) {                                        // ctx->stream joins the other groups
+        if (graphs_ok) {
+            // ---- From here on every group advances on its own: its 24-round graph is re-launched as soon as ITS previous batch has
+            //      finished and still left frames unsolved. No group waits for another (a group whose frames arrived later over
+            //      PCIe, or whose frames need more rounds, no longer holds the others back at every poll). ----
+            if (b->round_graphs.empty()) {
+                for (int gi = 0; gi < G; ++gi) {
+                    GroupRun gr = groups[gi];                   // a copy: capturing must not advance the real round counters
+                    cudaGraph_t graph = nullptr;
+                    RCLC_CUDA(cudaStreamBeginCapture(gr.st, cudaStreamCaptureModeThreadLocal));
+                    int rc_cap = RCLC_OK;
+                    for (int r = 0; r < rounds_per_check && rc_cap == RCLC_OK; ++r) {
+                        rc_cap = launch_move(b, gr);
+                        if (rc_cap == RCLC_OK) rc_cap = launch_sweep_view(b, gr.v, gr.nf, gr.st, F);
+                    }
+                    RCLC_CUDA(cudaStreamEndCapture(gr.st, &graph));
+                    RCLC_TRY(rc_cap);
+                    cudaGraphExec_t ge = nullptr;
+                    RCLC_CUDA(cudaGraphInstantiate(&ge, graph, 0));
+                    cudaGraphDestroy(graph);
+                    b->round_graphs.push_back(ge);
+                    ctx->launches -= 2 * rounds_per_check;      // (counted when the graph is launched)
+                }
+                b->graphs_groups = G;
+            }
+            while ((int)ctx->ev_groups.size() < G) {
+                cudaEvent_t e;
+                RCLC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->ev_groups.push_back(e);
+            }
+            auto poll = [&](int gi) -> int {
+                RCLC_CUDA(cudaMemcpyAsync(h_done + gi, groups[gi].v.n_done, sizeof(int), cudaMemcpyDeviceToHost, groups[gi].st));
+                RCLC_CUDA(cudaEventRecord(ctx->ev_groups[(size_t)gi], groups[gi].st));
+                return RCLC_OK;
+            };
+            for (int gi = 0; gi < G; ++gi) RCLC_TRY(poll(gi));
+            std::vector<char> finished((size_t)G, 0);
+            std::vector<int64_t> g_rounds((size_t)G, rounds);
+            int n_finished = 0;
+            while (n_finished < G) {
+                bool progressed = false;
+                for (int gi = 0; gi < G; ++gi) {
+                    if (finished[(size_t)gi]) continue;
+                    const cudaError_t q = cudaEventQuery(ctx->ev_groups[(size_t)gi]);
+                    if (q == cudaErrorNotReady) continue;
+                    RCLC_CUDA(q);
+                    progressed = true;
+                    if (h_done[gi] >= groups[gi].nf) { finished[(size_t)gi] = 1; ++n_finished; continue; }
+                    RCLC_CHECK(g_rounds[(size_t)gi] < max_rounds, RCLC_ERR_NUMERIC, "grid-fit state machine did not terminate");
+                    RCLC_CUDA(cudaGraphLaunch(b->round_graphs[(size_t)gi], groups[gi].st));
+                    groups[gi].round += rounds_per_check;
+                    g_rounds[(size_t)gi] += rounds_per_check;
+                    ctx->launches += 2 * rounds_per_check;
+                    RCLC_TRY(poll(gi));
+                }
+                if (!progressed) std::this_thread::yield();
+            }
+            for (int gi = 1; gi < G; ++gi) {                                    // ctx->stream joins the other groups
+                RCLC_CUDA(cudaEventRecord(ctx->ev_sync, groups[gi].st));
+                RCLC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
+            }
+            break;
+        }
+        for (int gi = 1; gi < G; ++gi) {                                        // lock-step path (profiling / A-B switches): ctx->stream joins the other groups
             RCLC_CUDA(cudaEventRecord(ctx->ev_sync, groups[gi].st));
             RCLC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
         }
-        RCLC_CUDA(cudaMemcpyAsync(h_done, b->v.n_done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RCLC_CUDA(cudaMemcpyAsync(h_done, b->v.n_done, G * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (*h_done >= F) break;
-        active_est = std::max(1, F - *h_done);
+        int done_total = 0;
+        for (int gi = 0; gi < G; ++gi) done_total += h_done[gi];
+        if (done_total >= F) break;
+        active_est = std::max(1, F - done_total);
         if (fused_mode == 1) fused_frames = active_est;
         RCLC_CHECK(rounds < max_rounds, RCLC_ERR_NUMERIC, "grid-fit state machine did not terminate");
     }

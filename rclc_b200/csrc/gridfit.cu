@@ -1762,8 +1762,8 @@ int rclc_batch_destroy(rclc_batch* b)
 // group's frames have arrived, while the copy engine is still busy with the later groups.
 static int solve_groups(const rclc_batch* b)
 {
-    static const int want_groups = [] { const char* e = std::getenv("RCLC_SOLVE_GROUPS"); return e ? std::max(1, std::min(16, atoi(e))) : 4; }();
-    return std::max(1, std::min(want_groups, b->n_frames / 2));
+    static const int want_groups = [] { const char* e = std::getenv("RCLC_SOLVE_GROUPS"); return e ? std::max(1, std::min(32, atoi(e))) : 10; }();
+    return std::max(1, std::min(want_groups, b->n_frames));
 }
 static int ensure_group_streams(rclc_ctx* ctx, int G)
 {
@@ -1908,14 +1908,15 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     b->binned_valid = false;
     RCLC_TRY(ctx->h_pin2.reserve(256));
     int* h_done = ctx->h_pin2.as<int>();           // [G] finished frames per group, as of each group's last poll
-    // Frames are independent until the extrinsic solve, so the batch runs as G groups on G streams: while the LM steps of
-    // one group (a single warp per frame, ~15 us of dependent fp64) hold the tail of its sweep kernel, the other groups'
-    // sweeps keep the SMs busy. RCLC_SOLVE_GROUPS overrides the default of 4 (1: the whole batch in lock-step;
-    // measured on 20 x 500 k points: 2 groups 18.8 ms per step, 3 17.9, 4 17.6, 5 17.5).
+    // Frames are independent until the extrinsic solve, so the batch runs as G groups on G streams, each advancing on its own:
+    // while the LM steps of one group (a single warp per frame, ~7 us of dependent fp64) hold the tail of its sweep kernel, the
+    // other groups' sweeps keep the SMs busy, and a group whose frames need few rounds finishes early. RCLC_SOLVE_GROUPS
+    // overrides the default of 10 (measured on 20 x 500 k points, ms per step resident / end to end: 4 groups 16.3 / 18.9,
+    // 8: 16.0 / 18.0, 10: 15.7 / 18.2, 16: 16.3 / 17.6, 20: 16.8 / 17.5).
     const int G = solve_groups(b);
     RCLC_TRY(ensure_group_streams(ctx, G));
     b->uploads_pending = false;          // every group stream carries its own frames' uploads ahead of its kernels
-    RCLC_CHECK(G <= 16, RCLC_ERR_INVALID, "at most 16 solve groups");
+    RCLC_CHECK(G <= 32, RCLC_ERR_INVALID, "at most 32 solve groups");
     RCLC_CUDA(cudaMemsetAsync(b->v.n_done, 0, 64 * sizeof(int), ctx->stream));
     RCLC_CUDA(cudaEventRecord(ctx->ev_sync, ctx->stream));              // uploads, T_bl, ... precede every group
     std::vector<GroupRun> groups(G);

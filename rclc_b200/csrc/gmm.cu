@@ -114,6 +114,18 @@ __global__ void __launch_bounds__(kGmmThreads) k_gmm_pass(GmmView v)
     }
 }
 
+// intensity plane of the resident float4 clouds: the 20 EM passes then read 4 B per point from a 40 MB array that stays in L2,
+// instead of striding through 16 B records in DRAM
+__global__ void __launch_bounds__(256) k_pack_intensity(const float4* __restrict__ cloud, int64_t frame_stride, const int64_t* __restrict__ n_pts,
+                                                        float* __restrict__ out, int64_t out_stride)
+{
+    const int f = blockIdx.y;
+    const int64_t n = n_pts[f];
+    const float4* src = cloud + (size_t)f * frame_stride;
+    float* dst = out + (size_t)f * out_stride;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) dst[i] = __ldg(src + i).w;
+}
+
 static int gmm_run(rclc_ctx* ctx, GmmView v, int F, int64_t max_n, int iters)
 {
     const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>((max_n + kGmmThreads * 8 - 1) / (kGmmThreads * 8), kGmmMaxCtas));
@@ -187,9 +199,17 @@ int rclc_batch_gmm_fit(rclc_batch* b, double* mu_io, double* sigma_io, double* p
     RCLC_TRY(batch_join_uploads(b));
     int64_t max_n = 0;
     for (int64_t n : b->h_npts) max_n = std::max(max_n, n);
-    // intensity is the .w lane of the resident float4 cloud (pc_process.h:603-606 copies it out; here it is read in place)
-    return gmm_solve(b->ctx, reinterpret_cast<const float*>(b->d_pristine) + 3, b->v.frame_stride * 4, 4, b->d_npts, b->n_frames,
-                     max_n, b->cfg.gmm_iters, mu_io, sigma_io, priors_out);
+    if (max_n == 0) return gmm_solve(b->ctx, reinterpret_cast<const float*>(b->d_pristine) + 3, b->v.frame_stride * 4, 4, b->d_npts, b->n_frames,
+                                     max_n, b->cfg.gmm_iters, mu_io, sigma_io, priors_out);
+    // intensity is the .w lane of the resident float4 cloud (pc_process.h:603-606 copies it out into an Eigen vector; so does this)
+    rclc_ctx* ctx = b->ctx;
+    const int64_t out_stride = (max_n + 63) & ~(int64_t)63;
+    RCLC_TRY(ctx->d_pts.reserve((size_t)b->n_frames * (size_t)out_stride * 4));
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>((max_n + 256 * 8 - 1) / (256 * 8), 1184));
+    k_pack_intensity<<<dim3((unsigned)gx, (unsigned)b->n_frames), 256, 0, ctx->stream>>>(b->d_pristine, b->v.frame_stride, b->d_npts, ctx->d_pts.as<float>(),
+                                                                                            out_stride);
+    ctx->launches += 1;
+    return gmm_solve(ctx, ctx->d_pts.as<float>(), out_stride, 1, b->d_npts, b->n_frames, max_n, b->cfg.gmm_iters, mu_io, sigma_io, priors_out);
 }
 
 } // extern "C"

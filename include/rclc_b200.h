@@ -84,7 +84,11 @@ int rclc_gridfit_solve(rclc_ctx* ctx, const rclc_config* cfg, void* pts_io, int 
 /* ---- frames resident in HBM ---- */
 int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, int64_t max_pts_per_frame, rclc_batch** out);
 int rclc_batch_destroy(rclc_batch* b);
-/* host -> device (pinned staging inside); frame f gets n points */
+/* host -> device; frame f gets n points. The copy is asynchronous. Pageable or strided sources are packed into pinned staging
+ * first, so the caller's buffer is free on return; {x, y, z, I} records (stride 16, ioff 12) that already sit in page-locked
+ * host memory are read in place by the DMA: keep such a buffer unchanged until the next call that returns results
+ * (rclc_batch_gridfit_solve, rclc_batch_gmm_fit, rclc_batch_read_eval, rclc_ctx_synchronize). Uploads go to the stream of the
+ * frame's solve group: a solve that follows them starts on the first frames while the later ones are still on the bus. */
 int rclc_batch_upload(rclc_batch* b, int32_t frame, const void* pts_host, int stride, int ioff, int64_t n);
 /* device float4 {x,y,z,I} -> batch storage */
 int rclc_batch_set_frame_dev(rclc_batch* b, int32_t frame, const void* pts_dev_float4, int64_t n);

@@ -147,6 +147,7 @@ int rclc_ctx_synchronize(rclc_ctx* c)
 {
     RCLC_CHECK(c, RCLC_ERR_INVALID, "ctx is null");
     RCLC_CUDA(cudaStreamSynchronize(c->stream));
+    for (cudaStream_t st : c->aux_streams) RCLC_CUDA(cudaStreamSynchronize(st));      // (uploads of the later solve groups live there)
     return RCLC_OK;
 }
 

@@ -308,7 +308,7 @@ __device__ __forceinline__ void bin_count(int* counter, int bin, bool valid)
 
 // Pass 1 of the counting sort: histogram of (cell, sub-cell) bins of the moved points; the last CTA of the frame then
 // turns the histogram into bin offsets (cells padded to whole rows), the cell table and the sentinels.
-__global__ void __launch_bounds__(kBinThreads) k_count(BatchView bv)
+__global__ void __launch_bounds__(kBinThreads) k_count(const __grid_constant__ BatchView bv)
 {
     // the list the LM steps of this round will fill was consumed by the previous round: empty it
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) bv.rebin_cnt[bv.list_parity ^ 1] = 0;
@@ -396,7 +396,7 @@ __device__ __forceinline__ void k_count_frame(const BatchView& bv, int f)
 
 // Pass 2: move the points for good (pcl::transformPointCloud restated in float), drop each one into the next free slot of
 // its bin (warp-aggregated atomics on the bin cursors) together with its z (the kd-tree neighbour test needs it).
-__global__ void __launch_bounds__(kBinThreads) k_scatter(BatchView bv)
+__global__ void __launch_bounds__(kBinThreads) k_scatter(const __grid_constant__ BatchView bv)
 {
     const int n_list = bv.rebin_cnt[bv.list_parity];
     for (int li = blockIdx.y; li < n_list; li += gridDim.y) k_scatter_frame(bv, bv.rebin_list[bv.list_parity * bv.n_frames + li]);
@@ -503,14 +503,14 @@ __device__ __forceinline__ void rowbox_frame(const BatchView& bv, int f)
     }
 }
 
-__global__ void __launch_bounds__(kBoxThreads) k_rowbox(BatchView bv)
+__global__ void __launch_bounds__(kBoxThreads) k_rowbox(const __grid_constant__ BatchView bv)
 {
     const int n_list = bv.rebin_cnt[bv.list_parity];
     for (int li = blockIdx.y; li < n_list; li += gridDim.y) rowbox_frame<false>(bv, bv.rebin_list[bv.list_parity * bv.n_frames + li]);
 }
 
 // One launch per round: frames whose LM step asked for the next outer iteration are moved in place.
-__global__ void __launch_bounds__(kBoxThreads) k_move(BatchView bv)
+__global__ void __launch_bounds__(kBoxThreads) k_move(const __grid_constant__ BatchView bv)
 {
     // the list the LM steps of this round will fill was consumed by the previous round: empty it
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) bv.rebin_cnt[bv.list_parity ^ 1] = 0;
@@ -1242,7 +1242,7 @@ __device__ __forceinline__ void drain_list(int mode, const float4* __restrict__ 
 }
 
 // The LM step as its own launch (one warp per frame) — RCLC_LM_SEPARATE=1, an A/B switch for the fused variant.
-__global__ void __launch_bounds__(32) k_lm(BatchView bv)
+__global__ void __launch_bounds__(32) k_lm(const __grid_constant__ BatchView bv)
 {
     const int f = blockIdx.x;
     if (!bv.ctl[f].sweep_active) return;
@@ -1259,10 +1259,10 @@ static_assert(kListPad <= 32, "one lane per padding entry");
 template <int CTAS>
 __device__ __forceinline__ void sweep_body(const BatchView& bv);
 
-__global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(BatchView bv) { sweep_body<3>(bv); }
+__global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const __grid_constant__ BatchView bv) { sweep_body<3>(bv); }
 // The multi-start search reads one frame (L2-resident) under thousands of poses: it is bound by issue slots and L2 latency,
 // not by DRAM, and wants more resident warps — the same body at 5 CTAs per SM (96 registers).
-__global__ void __launch_bounds__(kSweepThreads, 5) k_sweep_dense(BatchView bv) { sweep_body<5>(bv); }
+__global__ void __launch_bounds__(kSweepThreads, 5) k_sweep_dense(const __grid_constant__ BatchView bv) { sweep_body<5>(bv); }
 
 template <int CTAS>
 __device__ __forceinline__ void sweep_body(const BatchView& bv)

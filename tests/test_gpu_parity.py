@@ -259,6 +259,29 @@ def test_euclidean_cluster_identical_labels(ctx, oracle, n, tol, min_size):
     assert len(s0) >= 3 and l0[3] == -1
 
 
+def test_uniform_and_cluster_degenerate_inputs(ctx, oracle):
+    """One point, no finite point, a cluster above max_size, an empty cloud (the C ABI refuses it; the shims never send it)."""
+    from rclc_b200.capi import RclcError
+    one = np.array([[1, 2, 3, 50]], np.float32)
+    assert list(ctx.uniform_sample(one, 0.01)) == list(oracle.uniform_sample(one, 0.01)) == [0]
+    l1, s1 = ctx.euclidean_cluster(one, 0.1, 1, 10); l0, s0 = oracle.euclidean_cluster(one, 0.1, 1, 10)
+    assert list(l1) == list(l0) == [0] and list(s1) == list(s0) == [1]
+    bad = np.full((64, 4), np.nan, np.float32); bad[::2, 0] = np.inf
+    assert len(ctx.uniform_sample(bad, 0.01)) == len(oracle.uniform_sample(bad, 0.01)) == 0
+    l1, s1 = ctx.euclidean_cluster(bad, 0.1, 1, 10); l0, s0 = oracle.euclidean_cluster(bad, 0.1, 1, 10)
+    assert np.array_equal(l1, l0) and (l1 == -1).all() and len(s1) == len(s0) == 0
+    # a dense blob of 500 and a far pair: max_size 100 rejects the blob, min_size 3 the pair
+    rng = np.random.default_rng(9)
+    blob = np.zeros((502, 4), np.float32); blob[:500, :3] = rng.uniform(0, 0.05, (500, 3)); blob[500:, :3] = [[9, 9, 9], [9.01, 9, 9]]
+    for mn, mx in ((1, 100), (3, 1000), (1, 1000), (1, 500), (501, 1000)):
+        l1, s1 = ctx.euclidean_cluster(blob, 0.06, mn, mx); l0, s0 = oracle.euclidean_cluster(blob, 0.06, mn, mx)
+        assert np.array_equal(l1, l0) and np.array_equal(s1, s0), (mn, mx)
+    with pytest.raises(RclcError):
+        ctx.uniform_sample(np.zeros((0, 4), np.float32), 0.01)
+    with pytest.raises(RclcError):
+        ctx.euclidean_cluster(np.zeros((0, 4), np.float32), 0.1, 1, 10)
+
+
 def test_ransac_counts_masks_bit_exact(ctx, oracle):
     rng = np.random.default_rng(5)
     n = 60000

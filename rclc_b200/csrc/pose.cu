@@ -8,11 +8,21 @@
 // reduced across the CTA in shared memory and the Ceres LM step (Cholesky + accept/reject/radius
 // schedule) runs on device. The whole solve is ONE kernel launch — this path is latency-bound
 //  and is the site whose 6x6 system is all-reduced when frames are sharded.
+//
+// Two launch shapes share the solver. One CTA: one thread per frame, as above. A thread-block cluster (16 CTAs, else 8):
+// the (frame, corner) pairs are dealt over the cluster, then ONE thread per frame forms that frame's sums from the per-corner
+// factors in corner order and rank 0 reduces the frames in the one-CTA kernel's order, so both shapes return the same bits
+// (tests/test_gpu_parity.py::test_pose_refine_cluster_equals_one_cta). That matters because this solve wanders for its whole
+// 1000-iteration budget around a non-smooth minimum and the capped iterate depends on the last bit of every sum.
 #include "common.cuh"
 
 #include <cfloat>
+#include <cstdlib>
+#include <cooperative_groups.h>
 
 namespace rclc {
+
+namespace cg = cooperative_groups;
 
 struct J7 {
     double a;
@@ -145,6 +155,119 @@ __device__ void pose_evaluate(const double* pc, const double* img, int F, int C,
     block_sum<30>(v, s_warp, s_sum);
 }
 
+// ---- the cluster shape of the evaluation ----
+// q, t -> the nine rotation entries as duals (pose_block_dev's prologue, same expressions)
+__device__ __forceinline__ void pose_rot_dev(const double* Tcl, J7* R, J7* t)
+{
+    J7 q[4];
+    for (int k = 0; k < 4; ++k) q[k] = jvar(Tcl[k], k);
+    for (int k = 0; k < 3; ++k) t[k] = jvar(Tcl[4 + k], 4 + k);
+    const J7 two = jconst(2.0), one = jconst(1.0);
+    const J7 &x = q[0], &y = q[1], &z = q[2], &w = q[3];
+    const J7 tx = two * x, ty = two * y, tz = two * z;
+    const J7 twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = one - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = one - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = one - (txx + tyy);
+}
+
+// One corner of pose_block_dev's loop, stopped at the operands of "res + |e| / depth_norm": the one-CTA kernel contracts that
+// sum into res.v = fma((|e|.v - fg * d.v), 1/d.a, res.v) with fg = |e|.a / d.a, so the factors travel, not the quotient.
+// out (component stride os): fg, 1/d.a, (|e|.v - fg * d.v)[7], d.a, d.v[7].
+constexpr int kCornerVals = 17;
+__device__ __forceinline__ void pose_corner_dev(const J7* R, const J7* t, const double* pc3, const double* img2, double* out, int os)
+{
+    const J7 p0 = jconst(pc3[0]), p1 = jconst(pc3[1]), p2 = jconst(pc3[2]);
+    const J7 X = (R[0] * p0 + (R[1] * p1 + R[2] * p2)) + t[0];
+    const J7 Y = (R[3] * p0 + (R[4] * p1 + R[5] * p2)) + t[1];
+    const J7 Z = (R[6] * p0 + (R[7] * p1 + R[8] * p2)) + t[2];
+    const J7 depth_norm = jsqrt(X * X + (Y * Y + Z * Z));
+    const J7 e0 = jconst(img2[0]) - X / Z, e1 = jconst(img2[1]) - Y / Z;
+    const J7 en = jsqrt(e0 * e0 + e1 * e1);
+    const double gi = 1.0 / depth_norm.a, fg = en.a * gi;
+    out[0] = fg;
+    out[os] = gi;
+    for (int i = 0; i < 7; ++i) out[(2 + i) * os] = fma(-fg, depth_norm.v[i], en.v[i]);
+    out[9 * os] = depth_norm.a;
+    for (int i = 0; i < 7; ++i) out[(10 + i) * os] = depth_norm.v[i];
+}
+
+// One frame from its corners' factors, in corner order: pose_block_dev's running sum, arg-max and epilogue.
+__device__ __forceinline__ void pose_frame_from_corners(const double* Tcl, const double* c0, int os, int C, double& r, double* j6)
+{
+    J7 res = jconst(0.0), depth_max = jconst(0.0);
+    for (int i = 0; i < C; ++i) {
+        const double* o = c0 + i;
+        if (o[9 * os] > depth_max.a) {
+            depth_max.a = o[9 * os];
+            for (int k = 0; k < 7; ++k) depth_max.v[k] = o[(10 + k) * os];
+        }
+        const double fg = o[0], gi = o[os];
+        res.a = res.a + fg;
+        for (int k = 0; k < 7; ++k) res.v[k] = fma(o[(2 + k) * os], gi, res.v[k]);
+    }
+    res = res * depth_max;
+    r = res.a;
+    const double P[12] = {Tcl[3], Tcl[2], -Tcl[1], -Tcl[2], Tcl[3], Tcl[0], Tcl[1], -Tcl[0], Tcl[3], -Tcl[0], -Tcl[1], -Tcl[2]};
+    for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += res.v[k] * P[k * 3 + c];
+        j6[c] = s;
+    }
+    for (int c = 0; c < 3; ++c) j6[3 + c] = res.v[4 + c];
+}
+
+// pose_evaluate over a cluster. Frame f belongs to slot f % 256 (the one-CTA kernel's thread), slot s to rank s / (256 / n_cta);
+// a slot's frames are taken in the one-CTA order. s_corner: [kCornerVals][slots_per_cta * C] doubles; s_v: [slots_per_cta][30].
+__device__ void pose_evaluate_cluster(cg::cluster_group& cluster, const double* pc, const double* img, int F, int C, double huber_a,
+                                      const double* s_x, double* s_corner, double* s_v, double* s_warp, double* s_sum, int mode)
+{
+    const int tid = threadIdx.x, rank = (int)cluster.block_rank(), n_cta = (int)cluster.num_blocks();
+    const int S = kPoseThreads / n_cta, os = S * C;
+    double v[30];
+    for (int k = 0; k < 30; ++k) v[k] = 0;
+    const int first = rank * S;                                   // this CTA's first slot
+    if (first < F) {
+        J7 R[9], t[3];
+        const bool has_corner_work = mode != 1 && tid < min(F - first, S) * C;
+        if (has_corner_work) pose_rot_dev(s_x, R, t);
+        for (int base = first; base < F; base += kPoseThreads) {
+            const int nfr = min(F - base, S), ntask = mode == 1 ? 0 : nfr * C;
+            for (int tsk = tid; tsk < ntask; tsk += kPoseThreads) {
+                const size_t fc = (size_t)base * C + tsk;         // (frame base + tsk / C, corner tsk % C), frames are contiguous
+                pose_corner_dev(R, t, pc + fc * 3, img + fc * 2, s_corner + tsk, os);
+            }
+            __syncthreads();
+            if (tid < nfr) {
+                double r, j[6];
+                if (mode == 1) pose_block_dev(s_x, pc + (size_t)(base + tid) * C * 3, img + (size_t)(base + tid) * C * 2, C, r, j);
+                else pose_frame_from_corners(s_x, s_corner + tid * C, os, C, r, j);
+                if (!isfinite(r)) v[28] = 1.0;
+                for (int c = 0; c < 6; ++c) if (!isfinite(j[c])) v[29] = 1.0;
+                const double sq = r * r, bb = huber_a * huber_a;
+                double rho0, rho1;
+                if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
+                else { rho0 = sq; rho1 = 1.0; }
+                const double w = sqrt(rho1);
+                r *= w;
+                v[0] += 0.5 * rho0;
+                int q = 1;
+                for (int a = 0; a < 6; ++a) j[a] *= w;
+                for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) v[q++] += j[a] * j[b];
+                for (int a = 0; a < 6; ++a) v[22 + a] += j[a] * r;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < S) for (int k = 0; k < 30; ++k) s_v[tid * 30 + k] = v[k];
+    cluster.sync();                                               // every slot's sums are in its owner's shared memory
+    if (rank == 0) {
+        const double* src = cluster.map_shared_rank(s_v, tid / S) + (tid % S) * 30;
+        for (int k = 0; k < 30; ++k) v[k] = src[k];
+        block_sum<30>(v, s_warp, s_sum);                          // the one-CTA reduction, slot = thread
+    }
+}
+
 __device__ bool chol6_solve(const double* A /*6x6 full*/, const double* b, double* y)
 {
     double L[36];
@@ -168,22 +291,54 @@ __device__ bool chol6_solve(const double* A /*6x6 full*/, const double* b, doubl
 }
 
 // Ceres TrustRegionMinimizer (see oracle/ceres_lm.hpp for the published algorithm this mirrors)
-__global__ void __launch_bounds__(kPoseThreads) k_pose_refine(const double* __restrict__ pc, const double* __restrict__ img, int F, int C,
-                                                              double huber_a, double ftol, int max_iters, const double* __restrict__ T0,
-                                                              PoseOut* __restrict__ out)
+// kCluster: the evaluation is shared by the CTAs of a cluster, rank 0's thread 0 runs the solver, two cluster barriers per step.
+template <bool kCluster>
+__device__ __forceinline__ void pose_refine_body(const double* __restrict__ pc, const double* __restrict__ img, int F, int C,
+                                                 double huber_a, double ftol, int max_iters, const double* __restrict__ T0,
+                                                 PoseOut* __restrict__ out, int mode)
 {
     __shared__ double s_warp[(kPoseThreads / 32) * 30];
     __shared__ double s_sum[30];
     __shared__ double s_x[7], s_cand[7];
-    __shared__ int s_ctrl;           // 0 = evaluate candidate next, 1 = stop
+    __shared__ int s_ctrl[2];        // 0 = evaluate candidate next, 1 = stop; two slots used in turn, so that the boss's next
+    int pub = 0;                     // decision never lands on a word some thread has yet to read
+    extern __shared__ double s_dyn[];                 // cluster shape only: per-corner factors, then per-slot sums
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = kCluster ? (int)cluster.block_rank() : 0;
+    double* s_corner = s_dyn;
+    double* s_v = s_dyn + (kCluster ? (size_t)kCornerVals * (kPoseThreads / (int)cluster.num_blocks()) * C : 0);
+    auto evaluate = [&](const double* at) {
+        if constexpr (kCluster) pose_evaluate_cluster(cluster, pc, img, F, C, huber_a, at, s_corner, s_v, s_warp, s_sum, mode);
+        else pose_evaluate(pc, img, F, C, huber_a, at, true, s_warp, s_sum);
+    };
+    // the boss's s_ctrl / s_cand reach the other threads (and, in a cluster, the other ranks)
+    auto publish = [&]() -> int {
+        const int slot = pub & 1;
+        ++pub;
+        if constexpr (kCluster) {
+            // rank 0 pushes, so that nobody reads rank 0's words after the barrier, when the boss may already be writing the next ones
+            if (rank == 0) {
+                __syncthreads();
+                const int n_cta = (int)cluster.num_blocks(), dst = 1 + (int)threadIdx.x / 8, k = (int)threadIdx.x % 8;
+                if (dst < n_cta) {
+                    if (k < 7) cluster.map_shared_rank(s_cand, dst)[k] = s_cand[k];
+                    else cluster.map_shared_rank(s_ctrl, dst)[slot] = s_ctrl[slot];
+                }
+            }
+            cluster.sync();
+        } else {
+            __syncthreads();
+        }
+        return s_ctrl[slot];
+    };
     // thread-0 state
     double A[36], g[6], scale[6], diag[6], best[7];
     double x_cost = 0, x_norm = 0, radius = 1e4, decrease_factor = 2.0, gmax = 0, model_cost_change = 0;
     double minimum_cost = DBL_MAX, initial_cost = 0, min_iter_cost = 0;
     int iteration = 0, ninvalid = 0, n_iters = 0, term = 1;
     bool reuse_diagonal = false, step_ok = true, failed = false;
-    const int tid = threadIdx.x;
-    if (tid < 7) s_x[tid] = T0[tid];
+    const int tid = (kCluster && rank != 0) ? -1 : (int)threadIdx.x;      // "tid == 0" below: the boss
+    if (threadIdx.x < 7) s_x[threadIdx.x] = T0[threadIdx.x];
     __syncthreads();
 
     auto take_eval = [&]() {          // thread 0: accept s_sum as the evaluation at s_x
@@ -198,9 +353,9 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_refine(const double* __re
         for (int k = 0; k < 7; ++k) gmax = fmax(gmax, fabs(s_x[k] - xp[k]));
     };
 
-    pose_evaluate(pc, img, F, C, huber_a, s_x, true, s_warp, s_sum);
+    evaluate(s_x);
     if (tid == 0) {
-        if (s_sum[28] != 0.0 || s_sum[29] != 0.0) { failed = true; term = 2; initial_cost = nan(""); min_iter_cost = nan(""); s_ctrl = 1; }
+        if (s_sum[28] != 0.0 || s_sum[29] != 0.0) { failed = true; term = 2; initial_cost = nan(""); min_iter_cost = nan(""); s_ctrl[pub & 1] = 1; }
         else {
             take_eval();
             for (int a = 0; a < 6; ++a) scale[a] = 1.0 / (1.0 + sqrt(A[a * 6 + a]));
@@ -208,11 +363,10 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_refine(const double* __re
             x_norm = 0; for (int k = 0; k < 7; ++k) x_norm += s_x[k] * s_x[k];
             x_norm = sqrt(x_norm);
             for (int k = 0; k < 7; ++k) best[k] = s_x[k];
-            s_ctrl = 0;
+            s_ctrl[pub & 1] = 0;
         }
     }
-    __syncthreads();
-    bool stop = (s_ctrl == 1);
+    bool stop = (publish() == 1);
     while (!stop) {
         if (tid == 0) {
             // Finalize + step computation loop (invalid steps do not need an evaluation)
@@ -254,25 +408,25 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_refine(const double* __re
                 pose_plus(s_x, delta, s_cand);
                 need_eval = true;
             }
-            s_ctrl = need_eval ? 0 : 1;
+            s_ctrl[pub & 1] = need_eval ? 0 : 1;
         }
-        __syncthreads();
-        if (s_ctrl == 1) break;
+        if (publish() == 1) break;
         // evaluate the candidate (cost + Jacobian in one pass; Ceres evaluates the Jacobian again on acceptance)
-        pose_evaluate(pc, img, F, C, huber_a, s_cand, true, s_warp, s_sum);
+        evaluate(s_cand);
         if (tid == 0) {
+            s_ctrl[pub & 1] = 0;
             const double cand_cost = (s_sum[28] == 0.0) ? s_sum[0] : DBL_MAX;
             double sn = 0;
             for (int k = 0; k < 7; ++k) sn += (s_x[k] - s_cand[k]) * (s_x[k] - s_cand[k]);
-            if (sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) { term = 0; s_ctrl = 1; }
-            else if (fabs(x_cost - cand_cost) <= ftol * x_cost) { term = 0; s_ctrl = 1; }
+            if (sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) { term = 0; s_ctrl[pub & 1] = 1; }
+            else if (fabs(x_cost - cand_cost) <= ftol * x_cost) { term = 0; s_ctrl[pub & 1] = 1; }
             else {
                 const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : (x_cost - cand_cost) / model_cost_change;
                 if (rel > 1e-3) {
                     for (int k = 0; k < 7; ++k) s_x[k] = s_cand[k];
                     x_norm = 0; for (int k = 0; k < 7; ++k) x_norm += s_x[k] * s_x[k];
                     x_norm = sqrt(x_norm);
-                    if (s_sum[29] != 0.0) { term = 2; failed = true; s_ctrl = 1; }
+                    if (s_sum[29] != 0.0) { term = 2; failed = true; s_ctrl[pub & 1] = 1; }
                     else {
                         take_eval();
                         step_ok = true;
@@ -291,8 +445,7 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_refine(const double* __re
                 }
             }
         }
-        __syncthreads();
-        stop = (s_ctrl == 1);
+        stop = (publish() == 1);
     }
     if (tid == 0) {
         for (int k = 0; k < 7; ++k) out->Tcl[k] = failed ? T0[k] : best[k];
@@ -301,6 +454,21 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_refine(const double* __re
         out->iterations = n_iters;
         out->termination = term;
     }
+    if constexpr (kCluster) cluster.sync();           // nobody leaves while rank 0's shared memory may still be read
+}
+
+__global__ void __launch_bounds__(kPoseThreads) k_pose_refine(const double* __restrict__ pc, const double* __restrict__ img, int F, int C,
+                                                              double huber_a, double ftol, int max_iters, const double* __restrict__ T0,
+                                                              PoseOut* __restrict__ out)
+{
+    pose_refine_body<false>(pc, img, F, C, huber_a, ftol, max_iters, T0, out, 0);
+}
+
+__global__ void __launch_bounds__(kPoseThreads) k_pose_refine_cluster(const double* __restrict__ pc, const double* __restrict__ img, int F, int C,
+                                                                      double huber_a, double ftol, int max_iters,
+                                                                      const double* __restrict__ T0, PoseOut* __restrict__ out, int mode)
+{
+    pose_refine_body<true>(pc, img, F, C, huber_a, ftol, max_iters, T0, out, mode);
 }
 
 __global__ void k_pose_eval(const double* __restrict__ pc, const double* __restrict__ img, int F, int C, const double* __restrict__ Tcl,
@@ -310,6 +478,22 @@ __global__ void k_pose_eval(const double* __restrict__ pc, const double* __restr
     if (f >= F) return;
     double r, j[6];
     pose_block_dev(Tcl, pc + (size_t)f * C * 3, img + (size_t)f * C * 2, C, r, j);
+    res[f] = r;
+    for (int c = 0; c < 6; ++c) jac[6 * f + c] = j[c];
+}
+
+// debug: the split evaluation (rotation, corners, frame assembly) one thread per frame, scratch in global memory
+__global__ void k_pose_eval_split(const double* __restrict__ pc, const double* __restrict__ img, int F, int C, const double* __restrict__ Tcl,
+                                  double* __restrict__ res, double* __restrict__ jac, double* __restrict__ scratch)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    J7 R[9], t[3];
+    pose_rot_dev(Tcl, R, t);
+    double* sc = scratch + (size_t)f * kCornerVals * C;
+    for (int i = 0; i < C; ++i) pose_corner_dev(R, t, pc + ((size_t)f * C + i) * 3, img + ((size_t)f * C + i) * 2, sc + i, C);
+    double r, j[6];
+    pose_frame_from_corners(Tcl, sc, C, C, r, j);
     res[f] = r;
     for (int c = 0; c < 6; ++c) jac[6 * f + c] = j[c];
 }
@@ -328,6 +512,35 @@ static int upload_pose_inputs(rclc_ctx* ctx, const double* pc, const double* img
     return RCLC_OK;
 }
 
+// The cluster launch: 16 CTAs (non-portable size, opt-in), else 8. RCLC_ERR_UNSUPPORTED when the per-corner factors of a CTA's
+// slots do not fit shared memory or no cluster can be launched; the caller then uses the one-CTA kernel.
+static int launch_pose_cluster(rclc_ctx* ctx, const double* pc, const double* img, int F, int C, double huber_a, double ftol, int max_iters,
+                               const double* T0, PoseOut* out)
+{
+    const char* dm = std::getenv("RCLC_POSE_CLUSTER_DEBUG");
+    const int mode = dm ? std::atoi(dm) : 0;
+    for (int n_cta : {16, 8}) {
+        const int S = kPoseThreads / n_cta;
+        const size_t dyn = ((size_t)kCornerVals * S * C + (size_t)S * 30) * sizeof(double);
+        if (dyn > 200 * 1024) continue;
+        if (cudaFuncSetAttribute(k_pose_refine_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (n_cta > 8 && cudaFuncSetAttribute(k_pose_refine_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)n_cta);
+        lc.blockDim = dim3(kPoseThreads);
+        lc.dynamicSmemBytes = dyn;
+        lc.stream = ctx->stream;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = (unsigned)n_cta; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        lc.attrs = &at;
+        lc.numAttrs = 1;
+        if (cudaLaunchKernelEx(&lc, k_pose_refine_cluster, pc, img, F, C, huber_a, ftol, max_iters, T0, out, mode) == cudaSuccess) return RCLC_OK;
+        cudaGetLastError();
+    }
+    return RCLC_ERR_UNSUPPORTED;
+}
+
 } // namespace rclc
 
 using namespace rclc;
@@ -344,6 +557,11 @@ int rclc_pose_eval(rclc_ctx* ctx, const double* pc_corners, const double* img_no
     RCLC_TRY(ctx->d_out.reserve((size_t)F * 7 * 8));
     double* d_res = ctx->d_out.as<double>();
     double* d_jac = d_res + F;
+    const char* dbg = std::getenv("RCLC_POSE_EVAL_SPLIT");
+    if (dbg && dbg[0] == '1') {
+        RCLC_TRY(ctx->d_tmp2.reserve((size_t)F * kCornerVals * C * 8));
+        k_pose_eval_split<<<(F + 127) / 128, 128, 0, ctx->stream>>>(d_pc, d_img, F, C, d_T, d_res, d_jac, ctx->d_tmp2.as<double>());
+    } else
     k_pose_eval<<<(F + 127) / 128, 128, 0, ctx->stream>>>(d_pc, d_img, F, C, d_T, d_res, d_jac);
     ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
@@ -361,8 +579,15 @@ int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_cor
     double *d_pc, *d_img, *d_T;
     RCLC_TRY(upload_pose_inputs(ctx, pc_corners, img_norm, F, C, Tcl_io, &d_pc, &d_img, &d_T));
     RCLC_TRY(ctx->d_out.reserve(sizeof(PoseOut)));
-    k_pose_refine<<<1, kPoseThreads, 0, ctx->stream>>>(d_pc, d_img, F, C, cfg->pose_huber_a, cfg->pose_function_tol, cfg->pose_max_lm_iters,
-                                                      d_T, ctx->d_out.as<PoseOut>());
+    // RCLC_POSE_CLUSTER=0 keeps the one-CTA kernel (the A/B switch of the bit-identity test); read on every call
+    const char* e = std::getenv("RCLC_POSE_CLUSTER");
+    bool launched = false;
+    if (!(e && e[0] == '0') && ((int64_t)F * C >= 8 * kPoseThreads || (e && e[0] == '2')))      // '2': the cluster for any size
+        launched = launch_pose_cluster(ctx, d_pc, d_img, F, C, cfg->pose_huber_a, cfg->pose_function_tol, cfg->pose_max_lm_iters, d_T,
+                                       ctx->d_out.as<PoseOut>()) == RCLC_OK;
+    if (!launched)
+        k_pose_refine<<<1, kPoseThreads, 0, ctx->stream>>>(d_pc, d_img, F, C, cfg->pose_huber_a, cfg->pose_function_tol, cfg->pose_max_lm_iters,
+                                                          d_T, ctx->d_out.as<PoseOut>());
     ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     PoseOut h;

@@ -18,6 +18,7 @@
 
 #include <cfloat>
 #include <cstdlib>
+#include <cstdio>
 #include <cooperative_groups.h>
 
 namespace rclc {
@@ -108,7 +109,17 @@ __device__ void pose_plus(const double* x, const double* d, double* out)
 }
 
 constexpr int kPoseThreads = 256;
-struct PoseOut { double Tcl[7]; double initial_cost, final_cost; int iterations; int termination; };
+struct PoseOut {
+    double Tcl[7]; double initial_cost, final_cost; int iterations; int termination;
+#ifdef RCLC_POSE_TIMING
+    long long t_step, t_pub, t_eval, t_decide;       // thread 0's clock64 in the four parts of an iteration (experiments only)
+#endif
+};
+#ifdef RCLC_POSE_TIMING
+#define POSE_TICK(acc) do { const long long now_ = clock64(); acc += now_ - tick_; tick_ = now_; } while (0)
+#else
+#define POSE_TICK(acc) do { } while (0)
+#endif
 
 // Block-wide sum of NV values per thread -> s_out[NV] (fixed order)
 template <int NV>
@@ -196,15 +207,19 @@ __device__ __forceinline__ void pose_corner_dev(const J7* R, const J7* t, const 
 __device__ __forceinline__ void pose_frame_from_corners(const double* Tcl, const double* c0, int os, int C, double& r, double* j6)
 {
     J7 res = jconst(0.0), depth_max = jconst(0.0);
+#pragma unroll 5
     for (int i = 0; i < C; ++i) {
         const double* o = c0 + i;
-        if (o[9 * os] > depth_max.a) {
-            depth_max.a = o[9 * os];
-            for (int k = 0; k < 7; ++k) depth_max.v[k] = o[(10 + k) * os];
-        }
-        const double fg = o[0], gi = o[os];
-        res.a = res.a + fg;
-        for (int k = 0; k < 7; ++k) res.v[k] = fma(o[(2 + k) * os], gi, res.v[k]);
+        double ld[kCornerVals];
+#pragma unroll
+        for (int k = 0; k < kCornerVals; ++k) ld[k] = o[k * os];      // all loads up front, the arg-max as selects: no branch
+        const bool farther = ld[9] > depth_max.a;
+        depth_max.a = farther ? ld[9] : depth_max.a;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) depth_max.v[k] = farther ? ld[10 + k] : depth_max.v[k];
+        res.a = res.a + ld[0];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) res.v[k] = fma(ld[2 + k], ld[1], res.v[k]);
     }
     res = res * depth_max;
     r = res.a;
@@ -217,8 +232,74 @@ __device__ __forceinline__ void pose_frame_from_corners(const double* Tcl, const
     for (int c = 0; c < 3; ++c) j6[3 + c] = res.v[4 + c];
 }
 
+// block_sum<30> on s_v[30][256] in place, spread over all threads: the xor butterfly's pairs (lane i with lane i + o, o = 16 .. 1)
+// level by level, then the eight warp sums in warp order - the same additions on the same operands, so the same bits.
+static_assert(kPoseThreads == 256, "tree_sum30 assumes eight warps");
+// s_v[k][slot], padded (33 per warp of slots, 265 per value) so that no level of the tree runs into bank conflicts
+constexpr int kSvStride = 265;
+__device__ __forceinline__ int sv_index(int k, int slot) { return k * kSvStride + 33 * (slot >> 5) + (slot & 31); }
+__device__ void tree_sum30(double* s_v, double* s_sum)
+{
+    for (int lo = 4; lo >= 0; --lo) {
+        const int o = 1 << lo, n = 30 * (kPoseThreads / 32) * o;                 // 8 * o pairs per value at this level
+        for (int idx = threadIdx.x; idx < n; idx += kPoseThreads) {
+            const int k = idx >> (3 + lo), rem = idx & ((8 << lo) - 1), w = rem >> lo, i = rem & (o - 1);
+            double* p = s_v + k * kSvStride + 33 * w + i;
+            p[0] = p[0] + p[o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 30) {
+        double t = 0;
+        for (int w = 0; w < kPoseThreads / 32; ++w) t += s_v[threadIdx.x * kSvStride + 33 * w];
+        s_sum[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
+#ifdef RCLC_POSE_TIMING
+__device__ long long g_pose_ticks[8];
+#define EVAL_TICK(k) do { if (threadIdx.x == 0 && rank == 0) { const long long now_ = clock64(); g_pose_ticks[k] += now_ - etick_; etick_ = now_; } } while (0)
+#else
+#define EVAL_TICK(k) do { } while (0)
+#endif
+// The two phases are separate routines so that the nine rotation duals (144 registers) are not live while a frame is assembled.
+__device__ __noinline__ void pose_corners_phase(const double* Tcl, const double* pc, const double* img, size_t fc0, int ntask,
+                                                double* s_corner, int os)
+{
+    J7 R[9], t[3];
+    pose_rot_dev(Tcl, R, t);
+    for (int tsk = threadIdx.x; tsk < ntask; tsk += kPoseThreads)          // frames are contiguous: (frame, corner) = fc0 + tsk
+        pose_corner_dev(R, t, pc + (fc0 + tsk) * 3, img + (fc0 + tsk) * 2, s_corner + tsk, os);
+}
+
+// pose_evaluate's per-frame body: r, j -> Huber -> the thread's 30 running sums
+__device__ __forceinline__ void pose_accumulate(double r, double* j, double huber_a, double* v)
+{
+    if (!isfinite(r)) v[28] = 1.0;
+    for (int c = 0; c < 6; ++c) if (!isfinite(j[c])) v[29] = 1.0;
+    const double sq = r * r, bb = huber_a * huber_a;
+    double rho0, rho1;
+    if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
+    else { rho0 = sq; rho1 = 1.0; }
+    const double w = sqrt(rho1);
+    r *= w;
+    v[0] += 0.5 * rho0;
+    int q = 1;
+    for (int a = 0; a < 6; ++a) j[a] *= w;
+    for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) v[q++] += j[a] * j[b];
+    for (int a = 0; a < 6; ++a) v[22 + a] += j[a] * r;
+}
+
+__device__ __noinline__ void pose_frame_phase(const double* Tcl, const double* c0, int os, int C, double huber_a, double* v)
+{
+    double r, j[6];
+    pose_frame_from_corners(Tcl, c0, os, C, r, j);
+    pose_accumulate(r, j, huber_a, v);
+}
+
 // pose_evaluate over a cluster. Frame f belongs to slot f % 256 (the one-CTA kernel's thread), slot s to rank s / (256 / n_cta);
-// a slot's frames are taken in the one-CTA order. s_corner: [kCornerVals][slots_per_cta * C] doubles; s_v: [slots_per_cta][30].
+// a slot's frames are taken in the one-CTA order. s_corner: [kCornerVals][slots_per_cta * C] doubles; s_v: [30][kSvStride] (rank 0's is used).
 __device__ void pose_evaluate_cluster(cg::cluster_group& cluster, const double* pc, const double* img, int F, int C, double huber_a,
                                       const double* s_x, double* s_corner, double* s_v, double* s_warp, double* s_sum, int mode)
 {
@@ -227,44 +308,42 @@ __device__ void pose_evaluate_cluster(cg::cluster_group& cluster, const double* 
     double v[30];
     for (int k = 0; k < 30; ++k) v[k] = 0;
     const int first = rank * S;                                   // this CTA's first slot
-    if (first < F) {
-        J7 R[9], t[3];
-        const bool has_corner_work = mode != 1 && tid < min(F - first, S) * C;
-        if (has_corner_work) pose_rot_dev(s_x, R, t);
-        for (int base = first; base < F; base += kPoseThreads) {
-            const int nfr = min(F - base, S), ntask = mode == 1 ? 0 : nfr * C;
-            for (int tsk = tid; tsk < ntask; tsk += kPoseThreads) {
-                const size_t fc = (size_t)base * C + tsk;         // (frame base + tsk / C, corner tsk % C), frames are contiguous
-                pose_corner_dev(R, t, pc + fc * 3, img + fc * 2, s_corner + tsk, os);
-            }
-            __syncthreads();
-            if (tid < nfr) {
+#ifdef RCLC_POSE_TIMING
+    long long etick_ = clock64();
+#endif
+    for (int base = first; base < F; base += kPoseThreads) {
+        const int nfr = min(F - base, S), ntask = mode == 1 ? 0 : nfr * C;
+        if (tid < ntask) pose_corners_phase(s_x, pc, img, (size_t)base * C, ntask, s_corner, os);
+        EVAL_TICK(1);
+        __syncthreads();
+        EVAL_TICK(2);
+        if (tid < nfr) {
+            if (mode == 1) {                                      // test hook: the whole frame by the one-CTA kernel's routine
                 double r, j[6];
-                if (mode == 1) pose_block_dev(s_x, pc + (size_t)(base + tid) * C * 3, img + (size_t)(base + tid) * C * 2, C, r, j);
-                else pose_frame_from_corners(s_x, s_corner + tid * C, os, C, r, j);
-                if (!isfinite(r)) v[28] = 1.0;
-                for (int c = 0; c < 6; ++c) if (!isfinite(j[c])) v[29] = 1.0;
-                const double sq = r * r, bb = huber_a * huber_a;
-                double rho0, rho1;
-                if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
-                else { rho0 = sq; rho1 = 1.0; }
-                const double w = sqrt(rho1);
-                r *= w;
-                v[0] += 0.5 * rho0;
-                int q = 1;
-                for (int a = 0; a < 6; ++a) j[a] *= w;
-                for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) v[q++] += j[a] * j[b];
-                for (int a = 0; a < 6; ++a) v[22 + a] += j[a] * r;
+                pose_block_dev(s_x, pc + (size_t)(base + tid) * C * 3, img + (size_t)(base + tid) * C * 2, C, r, j);
+                pose_accumulate(r, j, huber_a, v);
+            } else {
+                pose_frame_phase(s_x, s_corner + tid * C, os, C, huber_a, v);
             }
-            __syncthreads();
         }
+        EVAL_TICK(3);
+        __syncthreads();
     }
-    if (tid < S) for (int k = 0; k < 30; ++k) s_v[tid * 30 + k] = v[k];
-    cluster.sync();                                               // every slot's sums are in its owner's shared memory
+    if (tid < S) {                                                // slot sums go to rank 0: s_v[k][slot]
+        double* dst = cluster.map_shared_rank(s_v, 0);
+        for (int k = 0; k < 30; ++k) dst[sv_index(k, first + tid)] = v[k];
+    }
+    EVAL_TICK(4);
+    cluster.sync();                                               // every slot's sums are in rank 0's shared memory
+    EVAL_TICK(5);
     if (rank == 0) {
-        const double* src = cluster.map_shared_rank(s_v, tid / S) + (tid % S) * 30;
-        for (int k = 0; k < 30; ++k) v[k] = src[k];
-        block_sum<30>(v, s_warp, s_sum);                          // the one-CTA reduction, slot = thread
+        if (mode == 2) {                                          // test hook: the one-CTA routine itself, slot = thread
+            for (int k = 0; k < 30; ++k) v[k] = s_v[sv_index(k, tid)];
+            block_sum<30>(v, s_warp, s_sum);
+        } else {
+            tree_sum30(s_v, s_sum);
+        }
+        EVAL_TICK(7);
     }
 }
 
@@ -367,6 +446,9 @@ __device__ __forceinline__ void pose_refine_body(const double* __restrict__ pc, 
         }
     }
     bool stop = (publish() == 1);
+#ifdef RCLC_POSE_TIMING
+    long long t_step = 0, t_pub = 0, t_eval = 0, t_decide = 0, tick_ = clock64();
+#endif
     while (!stop) {
         if (tid == 0) {
             // Finalize + step computation loop (invalid steps do not need an evaluation)
@@ -410,9 +492,13 @@ __device__ __forceinline__ void pose_refine_body(const double* __restrict__ pc, 
             }
             s_ctrl[pub & 1] = need_eval ? 0 : 1;
         }
-        if (publish() == 1) break;
+        POSE_TICK(t_step);
+        const bool done = publish() == 1;
+        POSE_TICK(t_pub);
+        if (done) break;
         // evaluate the candidate (cost + Jacobian in one pass; Ceres evaluates the Jacobian again on acceptance)
         evaluate(s_cand);
+        POSE_TICK(t_eval);
         if (tid == 0) {
             s_ctrl[pub & 1] = 0;
             const double cand_cost = (s_sum[28] == 0.0) ? s_sum[0] : DBL_MAX;
@@ -445,7 +531,9 @@ __device__ __forceinline__ void pose_refine_body(const double* __restrict__ pc, 
                 }
             }
         }
+        POSE_TICK(t_decide);
         stop = (publish() == 1);
+        POSE_TICK(t_pub);
     }
     if (tid == 0) {
         for (int k = 0; k < 7; ++k) out->Tcl[k] = failed ? T0[k] : best[k];
@@ -453,6 +541,9 @@ __device__ __forceinline__ void pose_refine_body(const double* __restrict__ pc, 
         out->final_cost = fmin(initial_cost, min_iter_cost);
         out->iterations = n_iters;
         out->termination = term;
+#ifdef RCLC_POSE_TIMING
+        out->t_step = t_step; out->t_pub = t_pub; out->t_eval = t_eval; out->t_decide = t_decide;
+#endif
     }
     if constexpr (kCluster) cluster.sync();           // nobody leaves while rank 0's shared memory may still be read
 }
@@ -521,7 +612,7 @@ static int launch_pose_cluster(rclc_ctx* ctx, const double* pc, const double* im
     const int mode = dm ? std::atoi(dm) : 0;
     for (int n_cta : {16, 8}) {
         const int S = kPoseThreads / n_cta;
-        const size_t dyn = ((size_t)kCornerVals * S * C + (size_t)S * 30) * sizeof(double);
+        const size_t dyn = ((size_t)kCornerVals * S * C + (size_t)kSvStride * 30) * sizeof(double);
         if (dyn > 200 * 1024) continue;
         if (cudaFuncSetAttribute(k_pose_refine_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) { cudaGetLastError(); continue; }
         if (n_cta > 8 && cudaFuncSetAttribute(k_pose_refine_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
@@ -579,10 +670,10 @@ int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_cor
     double *d_pc, *d_img, *d_T;
     RCLC_TRY(upload_pose_inputs(ctx, pc_corners, img_norm, F, C, Tcl_io, &d_pc, &d_img, &d_T));
     RCLC_TRY(ctx->d_out.reserve(sizeof(PoseOut)));
-    // RCLC_POSE_CLUSTER=0 keeps the one-CTA kernel (the A/B switch of the bit-identity test); read on every call
+    // RCLC_POSE_CLUSTER=0 keeps the one-CTA kernel, =2 takes the cluster at any size (the A/B switch of the bit-identity test)
     const char* e = std::getenv("RCLC_POSE_CLUSTER");
     bool launched = false;
-    if (!(e && e[0] == '0') && ((int64_t)F * C >= 8 * kPoseThreads || (e && e[0] == '2')))      // '2': the cluster for any size
+    if (!(e && e[0] == '0') && ((int64_t)F * C >= 2 * kPoseThreads || (e && e[0] == '2')))      // '2': the cluster for any size
         launched = launch_pose_cluster(ctx, d_pc, d_img, F, C, cfg->pose_huber_a, cfg->pose_function_tol, cfg->pose_max_lm_iters, d_T,
                                        ctx->d_out.as<PoseOut>()) == RCLC_OK;
     if (!launched)
@@ -593,6 +684,19 @@ int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_cor
     PoseOut h;
     RCLC_CUDA(cudaMemcpyAsync(&h, ctx->d_out.p, sizeof(PoseOut), cudaMemcpyDeviceToHost, ctx->stream));
     RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+#ifdef RCLC_POSE_TIMING
+    if (launched) {
+        long long tk[8], z[8] = {};
+        cudaMemcpyFromSymbol(tk, g_pose_ticks, sizeof(tk));
+        cudaMemcpyToSymbol(g_pose_ticks, z, sizeof(z));
+        fprintf(stderr, "  evaluate, cycles per iteration: rot %.0f, corners %.0f, wait %.0f, frames %.0f, wait+store %.0f, cluster sync %.0f, gather %.0f, sum %.0f\n",
+                (double)tk[0] / h.iterations, (double)tk[1] / h.iterations, (double)tk[2] / h.iterations, (double)tk[3] / h.iterations,
+                (double)tk[4] / h.iterations, (double)tk[5] / h.iterations, (double)tk[6] / h.iterations, (double)tk[7] / h.iterations);
+    }
+    fprintf(stderr, "pose timing (%s, F=%d): %d iterations; cycles per iteration: step %.0f, publish %.0f, evaluate %.0f, decide %.0f\n",
+            launched ? "cluster" : "one CTA", F, h.iterations, (double)h.t_step / h.iterations, (double)h.t_pub / h.iterations,
+            (double)h.t_eval / h.iterations, (double)h.t_decide / h.iterations);
+#endif
     for (int k = 0; k < 7; ++k) Tcl_io[k] = h.Tcl[k];
     if (initial_cost) *initial_cost = h.initial_cost;
     if (final_cost) *final_cost = h.final_cost;

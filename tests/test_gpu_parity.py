@@ -356,22 +356,23 @@ def test_pose_refine_cluster_frame_split_is_exact(ctx, cfg, oracle, F, seed, mon
     pc, img, T0, _ = _pose_problem(oracle, F, seed=seed)
     monkeypatch.setenv("RCLC_POSE_CLUSTER", "2")
     out = []
-    for dbg in ("0", "1"):
+    for dbg in ("0", "1", "2"):      # 1: whole-frame evaluation by one thread; 2: the one-CTA kernel's block reduction on rank 0
         monkeypatch.setenv("RCLC_POSE_CLUSTER_DEBUG", dbg)
         rc, T, c0, c1, it = ctx.pose_refine(cfg, pc, img, T0)
         out.append((rc, T.tobytes(), c0, c1, it))
-    assert out[0] == out[1]
+    assert out[0] == out[1] == out[2]
     r0, j0 = ctx.pose_eval(pc, img, T0)
     monkeypatch.setenv("RCLC_POSE_EVAL_SPLIT", "1")
     r1, j1 = ctx.pose_eval(pc, img, T0)
     assert r0.tobytes() == r1.tobytes() and j0.tobytes() == j1.tobytes()
 
 
-@pytest.mark.parametrize("F,seed", [(64, 3), (256, 9), (300, 4), (700, 5)])
-def test_pose_refine_cluster_vs_one_cta(ctx, cfg, oracle, ocfg, F, seed, monkeypatch):
-    """Cluster shape (the default from 2048 corner observations up) against the one-CTA kernel and the oracle: same initial cost
-    to the bit (same per-frame values, same reduction order), extrinsic within the bar. The solver code is compiled once per
-    shape, so the step arithmetic may round differently and the iteration counts differ - see test_pose_eval_and_refine."""
+@pytest.mark.parametrize("F,seed", [(5, 9), (20, 9), (64, 3), (256, 9), (300, 4), (700, 5)])
+def test_pose_refine_cluster_equals_one_cta(ctx, cfg, oracle, ocfg, F, seed, monkeypatch):
+    """The cluster shape (the default from 512 corner observations up) keeps each frame's arithmetic and the frames' reduction
+    order, and thread 0's solver code is the same text: in this build the two shapes return the same bits - extrinsic, costs,
+    iteration count - which is what one wants of a solve whose capped iterate depends on the last bit of every sum. Sizes the
+    other pose test does not cover are also held to the bar against the oracle."""
     import time
     pc, img, T0, _ = _pose_problem(oracle, F, seed=seed)
     out = {}
@@ -379,16 +380,16 @@ def test_pose_refine_cluster_vs_one_cta(ctx, cfg, oracle, ocfg, F, seed, monkeyp
         monkeypatch.setenv("RCLC_POSE_CLUSTER", mode)
         ctx.pose_refine(cfg, pc, img, T0)
         t0 = time.perf_counter()
-        out[mode] = ctx.pose_refine(cfg, pc, img, T0)
+        rc, T, c0, c1, it = ctx.pose_refine(cfg, pc, img, T0)
         out[mode + "ms"] = (time.perf_counter() - t0) * 1e3
-    (rc0, Ta, c0a, c1a, ita), (rc1, Tb, c0b, c1b, itb) = out["0"], out["2"]
-    print(f"pose refine F={F}: one CTA {out['0ms']:.2f} ms / {ita} iterations, cluster {out['2ms']:.2f} ms / {itb} iterations")
-    rco, To, c0o, c1o, ito = oracle.pose_refine(ocfg, pc, img, T0)
-    assert rc0 == rc1 == rco == 0 and c0a == c0b
-    for T in (Ta, To):
-        assert np.abs(Tb[4:] - T[4:]).max() < 1e-4
-        assert 2 * np.linalg.norm(Tb[:4] * np.sign(Tb[3]) - T[:4] * np.sign(T[3])) < 1e-4
-    np.testing.assert_allclose(c1b, c1a, rtol=1e-6)
+        out[mode] = (rc, T.tobytes(), c0, c1, it)
+    print(f"pose refine F={F}: one CTA {out['0ms']:.2f} ms, cluster {out['2ms']:.2f} ms, {out['0'][4]} iterations")
+    assert out["0"] == out["2"]
+    if F in (64, 300, 700):
+        rco, To, c0o, c1o, ito = oracle.pose_refine(ocfg, pc, img, T0)
+        assert rc == rco == 0
+        assert np.abs(T[4:] - To[4:]).max() < 1e-4
+        assert 2 * np.linalg.norm(T[:4] * np.sign(T[3]) - To[:4] * np.sign(To[3])) < 1e-4
 
 
 def test_project_colorize_exact(ctx, cfg, oracle, ocfg):

@@ -47,6 +47,10 @@ typedef struct rclc_gridfit_report {
     double  last_final_cost;      /* Summary::final_cost of the last solve                        */
     double  se2_first[3];         /* (x, y, yaw deg) of the first solve                           */
     float   T_base_laser[16];     /* accumulated float transform, row-major                       */
+    int64_t poses_swept;          /* poses the device evaluated, including speculative candidates the LM replay then discarded
+                                     (pose_evals counts only the evaluations Ceres would have made)                        */
+    int32_t rounds;               /* sweep rounds this frame took part in (pose_evals would be the count without speculation) */
+    int32_t spec_mismatch;        /* speculated candidates that differed from the replayed ones: always 0 (self-check)    */
 } rclc_gridfit_report;
 
 const char* rclc_last_error_string(void);
@@ -64,6 +68,8 @@ int rclc_ctx_timer_start(rclc_ctx* ctx);
 int rclc_ctx_timer_stop_ms(rclc_ctx* ctx, float* ms_out);   /* records stop, synchronises, returns ms */
 int rclc_ctx_flush_l2(rclc_ctx* ctx);               /* writes a buffer larger than L2            */
 int64_t rclc_ctx_kernel_launches(rclc_ctx* ctx);    /* kernels launched by this ctx so far       */
+/* the batched grid-fit solve runs its frames as `groups` independent groups on as many streams (default 10, 1..32) */
+int rclc_ctx_set_solve_groups(rclc_ctx* ctx, int32_t groups);
 /* device time of the k_sweep kernel launched by the last rclc_batch_sweep (CUDA events recorded on the ctx stream
  * immediately before and after that launch; synchronises on the second one) */
 int rclc_ctx_last_sweep_ms(rclc_ctx* ctx, float* ms_out);
@@ -95,6 +101,10 @@ int rclc_batch_set_frame_dev(rclc_batch* b, int32_t frame, const void* pts_dev_f
 int64_t rclc_batch_total_points(rclc_batch* b);
 /* bins every frame's cloud by lattice cell (once per cloud state); then single-pose passes */
 int rclc_batch_bin(rclc_batch* b);
+/* on != 0: every later sweep / solve of this batch runs the all-fp64 body (each predicate evaluated exactly like the reference,
+ * board_fitting_cost.h:132-151) instead of the fp32 body with exact re-evaluation near decision boundaries. Same results bit for
+ * bit, several times slower: the A/B reference of the fast body. */
+int rclc_batch_set_exact_sweep(rclc_batch* b, int32_t on);
 int rclc_batch_sweep(rclc_batch* b, const double* poses /* F*3 */);           /* accumulate only (async) */
 int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* acc); /* F*nt[, *3, *16] */
 /* full solve for all frames (async LM state machine on device); outputs on host */

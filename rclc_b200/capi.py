@@ -23,7 +23,8 @@ class RclcError(RuntimeError):
 class GridfitReport(C.Structure):
     _fields_ = [("outer_iterations", C.c_int32), ("status", C.c_int32), ("pose_evals", C.c_int64),
                 ("lm_iterations", C.c_int64), ("first_initial_cost", C.c_double), ("last_final_cost", C.c_double),
-                ("se2_first", C.c_double * 3), ("T_base_laser", C.c_float * 16)]
+                ("se2_first", C.c_double * 3), ("T_base_laser", C.c_float * 16), ("poses_swept", C.c_int64),
+                ("rounds", C.c_int32), ("spec_mismatch", C.c_int32)]
 
 
 def lib():
@@ -133,6 +134,9 @@ class Context:
 
     def flush_l2(self):
         _chk(lib().rclc_ctx_flush_l2(self.h))
+
+    def set_solve_groups(self, n):
+        _chk(lib().rclc_ctx_set_solve_groups(self.h, int(n)))
 
     def kernel_launches(self):
         return lib().rclc_ctx_kernel_launches(self.h)
@@ -279,6 +283,10 @@ class Batch:
 
     def bin(self):
         _chk(lib().rclc_batch_bin(self.h))
+
+    def set_exact_sweep(self, on=True):
+        """All-fp64 sweep body (the A/B reference of the fast body) for every later sweep / solve of this batch."""
+        _chk(lib().rclc_batch_set_exact_sweep(self.h, 1 if on else 0))
 
     def sweep(self, poses):
         poses = np.ascontiguousarray(poses, np.float64)

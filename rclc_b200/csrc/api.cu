@@ -10,7 +10,7 @@ namespace rclc {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
 
-__global__ void k_pack_passthrough() {}
+
 
 // Host side of an upload: the strided records are packed to float4 {x,y,z,I} into one of two pinned buffers by a few
 // threads, then copied asynchronously; the copy of frame f overlaps the packing of frame f + 1 (the buffers are guarded by
@@ -197,6 +197,13 @@ int rclc_ctx_flush_l2(rclc_ctx* c)
 }
 
 int64_t rclc_ctx_kernel_launches(rclc_ctx* c) { return c ? c->launches : 0; }
+
+int rclc_ctx_set_solve_groups(rclc_ctx* c, int32_t groups)
+{
+    RCLC_CHECK(c && groups >= 1 && groups <= 32, RCLC_ERR_INVALID, "solve groups must be 1..32");
+    c->solve_groups = groups;
+    return RCLC_OK;
+}
 
 int rclc_ctx_last_sweep_ms(rclc_ctx* c, float* ms_out)
 {

@@ -71,6 +71,7 @@ struct rclc_ctx {
     int64_t l2_bytes = 0;
     int64_t launches = 0;
     int flush_parity = 0;
+    int solve_groups = 10;                             // independent frame groups (streams) of the grid-fit solve
     std::vector<cudaStream_t> aux_streams;             // extra streams of the grouped grid-fit solve
     cudaEvent_t ev_sync = nullptr;
     std::vector<cudaEvent_t> ev_groups;                // one per solve group: "this group's last batch of rounds has finished"

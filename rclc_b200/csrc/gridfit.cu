@@ -116,9 +116,8 @@ static int build_geom(const rclc_config& c, HostGeom& hg)
     g.ncy = jmax - jmin + 4;
     g.ncells = g.ncx * g.ncy;
     RCLC_CHECK(g.ncells <= kMaxCoarse, RCLC_ERR_UNSUPPORTED, "board too large for the cell table");
-    // sub-cells per axis inside a cell (sort key only): the finer, the tighter the row boxes. RCLC_SUBCELLS overrides.
-    static const int want_sub = [] { const char* e = std::getenv("RCLC_SUBCELLS"); return e ? std::max(1, std::min(16, atoi(e))) : 4; }();
-    g.sub = want_sub;
+    // sub-cells per axis inside a cell (sort key only): the finer, the tighter the row boxes
+    g.sub = 4;
     while (g.sub > 1 && g.ncells * g.sub * g.sub > kMaxCells) g.sub >>= 1;
     g.nfine = g.ncells * g.sub * g.sub;
     return RCLC_OK;
@@ -219,9 +218,10 @@ __device__ int block_exclusive_scan(int* data, int n, int* s_part /* [T] */)
 // ------------------------------------------------------------------------------------------------
 __device__ void reset_lm_for_outer(LmState& s, FrameCtl& c)
 {
-    s.phase = PH_EVAL_INIT;
-    for (int k = 0; k < 3; ++k) { s.x[k] = 0; s.cand[k] = 0; s.best[k] = 0; }
-    pose_coef_dev(0.0, 0.0, 0.0, c.pose);
+    s.core.phase = PH_EVAL_INIT;
+    for (int k = 0; k < 3; ++k) { s.core.x[k] = 0; s.core.cand[k] = 0; s.core.best[k] = 0; s.spec[0][k] = 0; }
+    pose_coef_dev(0.0, 0.0, 0.0, c.pose[0]);
+    c.n_pose = 1;                    // T_se2_wl = {0, 0, 0} (opt_grid_fitting.h:70): nothing to speculate on before the first Jacobian
     c.sweep_active = 1;
 }
 
@@ -232,7 +232,9 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
     const int nc = bv.geom.ncells, nf = bv.geom.nfine;
     for (int c = tid; c < nf; c += blockDim.x) { bv.hist[(size_t)f * nf + c] = 0; bv.cursor[(size_t)f * nf + c] = 0; }
     for (int c = tid; c < nc; c += blockDim.x) { bv.cellz2[(size_t)f * nc + c] = 0u; bv.cellcnt[(size_t)f * nc + c] = 0; }
-    for (int k = tid; k < bv.geom.nt * 16; k += blockDim.x) bv.acc[(size_t)f * bv.geom.nt * 16 + k] = 0.0;
+    for (int k = tid; k < kSpec * bv.geom.nt * 16; k += blockDim.x) bv.acc[(size_t)f * bv.acc_stride + k] = 0.0;
+    for (int k = tid; k < kSpec * bv.geom.nt; k += blockDim.x) bv.tgt_done[(size_t)f * kSpec * bv.geom.nt + k] = 0;
+    if (tid < kSpec) bv.slot_done[(size_t)f * kSpec + tid] = 0;
     if (tid == 0) {
         FrameCtl& c = bv.ctl[f];
         LmState& s = bv.lm[f];
@@ -247,18 +249,22 @@ __global__ void k_init_state(BatchView bv, const double* __restrict__ T_bl /* F*
         c.move[5] = 1.f;
         s.outer_iter = 0;
         s.status = 0;
+        s.chain = 0;
+        s.n_rejected = 0;
         for (int k = 0; k < 16; ++k) {
             s.T_base_laser[k] = (k % 5 == 0) ? 1.f : 0.f;
             s.T_bl[k] = T_bl ? T_bl[(size_t)f * 16 + k] : ((k % 5 == 0) ? 1.0 : 0.0);
         }
         s.rep.outer_iterations = 0; s.rep.status = 0; s.rep.pose_evals = 0; s.rep.lm_iterations = 0;
         s.rep.first_initial_cost = 0; s.rep.last_final_cost = 0;
+        s.rep.poses_swept = 0; s.rep.rounds = 0; s.rep.spec_mismatch = 0;
+#ifdef RCLC_LAB
         for (int k = 0; k < 8; ++k) s.dbg[k] = 0;
+#endif
         for (int k = 0; k < 3; ++k) s.rep.se2_first[k] = 0;
         reset_lm_for_outer(s, c);
         if (bv.n_pts[f] != 0) bv.rebin_list[bv.list_parity * bv.n_frames + atomicAdd(&bv.rebin_cnt[bv.list_parity], 1)] = f;
-        if (bv.n_pts[f] == 0) { s.phase = PH_DONE; c.sweep_active = 0; c.rebin = 0; s.status = 2; s.rep.status = 2; atomicAdd(bv.n_done, 1); }
-        if (f == 0 && false) *bv.n_done = 0;
+        if (bv.n_pts[f] == 0) { s.core.phase = PH_DONE; c.sweep_active = 0; c.rebin = 0; s.status = 2; s.rep.status = 2; atomicAdd(bv.n_done, 1); }
     }
 }
 
@@ -541,12 +547,12 @@ __device__ __forceinline__ void target_residual(const double* a, bool is_row, do
 __global__ void k_eval_out(BatchView bv)
 {
     const int f = blockIdx.x;
-    const PoseCoef pc = bv.ctl[f].pose;
+    const PoseCoef pc = bv.ctl[f].pose[0];
     const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
     const double cth = cos(theta), sth = sin(theta);
     for (int t = threadIdx.x; t < bv.geom.nt; t += blockDim.x) {
         double r, j0, j1, j2;
-        target_residual(bv.acc + ((size_t)f * bv.geom.nt + t) * 16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
+        target_residual(bv.acc + (size_t)f * bv.acc_stride + (size_t)t * 16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
         double* o = bv.eval_out + ((size_t)f * bv.geom.nt + t) * 4;
         o[0] = r; o[1] = j0; o[2] = j1; o[3] = j2;
     }
@@ -629,7 +635,7 @@ __device__ bool chol3_solve(const double* A6 /*00,01,02,11,12,22*/, const double
     return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]);
 }
 
-__device__ void accept_eval(LmState& s, const EvalSums& e)
+__device__ void accept_eval(LmCore& s, const EvalSums& e)
 {
     s.x_cost = e.cost;
     for (int k = 0; k < 6; ++k) s.Au[k] = e.A[k];
@@ -643,83 +649,85 @@ __device__ void accept_eval(LmState& s, const EvalSums& e)
     s.gmax = gm;
 }
 
-// Runs on one thread. Consumes the evaluation of ctl.pose and advances until the next pose needs a
-// sweep, the frame needs a re-bin, or the frame is done.
-__device__ void lm_advance(const GridGeom& g, LmState& s, FrameCtl& c, const EvalSums& e, double* corners, int* n_done)
+enum LmTerm { T_CONV = 0, T_NOCONV = 1, T_FAIL = 2, T_RUNNING = 3, T_FAIL_INITIAL = 4 };
+enum LmVerdict { V_ACCEPTED = 0, V_REJECTED = 1, V_ENDED = 2 };
+
+// ceres::TrustRegionMinimizer, resumable, in two halves.
+// lm_judge: consumes the evaluation of the pose the minimiser asked for last (x = 0 at the start of a solve, then s.cand):
+// parameter / function tolerance, step quality, accept or reject and the radius update. `term` is set when the solve ends here.
+__device__ int lm_judge(const GridGeom& g, LmCore& s, const EvalSums& e, int& term)
 {
-    enum { T_CONV = 0, T_NOCONV = 1, T_FAIL = 2 };
-    bool terminate = false;
-    int term = T_CONV;
-    bool initial_failure = false;
-    s.rep.pose_evals++;
+    term = T_RUNNING;
     if (s.phase == PH_EVAL_INIT) {
-        c.rebin = 0;
         s.n_lm_iterations_this_solve = 0;
         if (!e.res_valid || !e.jac_valid) {
             s.initial_cost = nan("");
             s.min_iter_cost = nan("");
-            terminate = true; term = T_FAIL; initial_failure = true;
-        } else {
-            accept_eval(s, e);
-            for (int k = 0; k < 3; ++k) {
-                const double cn = (k == 0) ? e.A[0] : (k == 1) ? e.A[3] : e.A[5];
-                s.scale[k] = 1.0 / (1.0 + sqrt(cn));                              // jacobi scaling, computed once
-            }
-            s.initial_cost = s.x_cost;
-            s.min_iter_cost = s.x_cost;
-            s.minimum_cost = DBL_MAX;
-            s.step_is_successful = 1;
-            s.iteration = 0;
-            s.radius = 1e4;
-            s.decrease_factor = 2.0;
-            s.reuse_diagonal = 0;
-            s.num_consecutive_invalid = 0;
-            s.x_norm = 0.0;
+            term = T_FAIL_INITIAL;
+            return V_ENDED;
         }
-    } else {
-        const double cand_cost = e.res_valid ? e.cost : DBL_MAX;
-        double sn = 0;
-        for (int k = 0; k < 3; ++k) sn += (s.x[k] - s.cand[k]) * (s.x[k] - s.cand[k]);
-        if (sqrt(sn) <= 1e-8 * (s.x_norm + 1e-8)) { terminate = true; term = T_CONV; }               // parameter tolerance
-        else if (fabs(s.x_cost - cand_cost) <= g.function_tol * s.x_cost) { terminate = true; term = T_CONV; }   // function tolerance
-        else {
-            const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : (s.x_cost - cand_cost) / s.model_cost_change;
-            if (rel > 1e-3) {
-                for (int k = 0; k < 3; ++k) s.x[k] = s.cand[k];
-                s.x_norm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2]);
-                if (!e.jac_valid) { terminate = true; term = T_FAIL; }
-                else {
-                    accept_eval(s, e);
-                    s.step_is_successful = 1;
-                    const double q = 2.0 * rel - 1.0;
-                    s.radius = s.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
-                    s.radius = fmin(1e16, s.radius);
-                    s.decrease_factor = 2.0;
-                    s.reuse_diagonal = 0;
-                    s.min_iter_cost = fmin(s.min_iter_cost, s.x_cost);
-                }
-            } else {
-                s.min_iter_cost = fmin(s.min_iter_cost, cand_cost);
-                s.radius = s.radius / s.decrease_factor;
-                s.decrease_factor *= 2.0;
-                s.reuse_diagonal = 1;
-                s.step_is_successful = 0;
-            }
+        accept_eval(s, e);
+        for (int k = 0; k < 3; ++k) {
+            const double cn = (k == 0) ? e.A[0] : (k == 1) ? e.A[3] : e.A[5];
+            s.scale[k] = 1.0 / (1.0 + sqrt(cn));                              // jacobi scaling, computed once
         }
+        s.initial_cost = s.x_cost;
+        s.min_iter_cost = s.x_cost;
+        s.minimum_cost = DBL_MAX;
+        s.step_is_successful = 1;
+        s.iteration = 0;
+        s.radius = 1e4;
+        s.decrease_factor = 2.0;
+        s.reuse_diagonal = 0;
+        s.num_consecutive_invalid = 0;
+        s.x_norm = 0.0;
+        return V_ACCEPTED;
     }
-    while (!terminate) {
-        // FinalizeIterationAndCheckIfMinimizerCanContinue
+    const double cand_cost = e.res_valid ? e.cost : DBL_MAX;
+    double sn = 0;
+    for (int k = 0; k < 3; ++k) sn += (s.x[k] - s.cand[k]) * (s.x[k] - s.cand[k]);
+    if (sqrt(sn) <= 1e-8 * (s.x_norm + 1e-8)) { term = T_CONV; return V_ENDED; }                              // parameter tolerance
+    if (fabs(s.x_cost - cand_cost) <= g.function_tol * s.x_cost) { term = T_CONV; return V_ENDED; }           // function tolerance
+    const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : (s.x_cost - cand_cost) / s.model_cost_change;
+    if (rel > 1e-3) {
+        for (int k = 0; k < 3; ++k) s.x[k] = s.cand[k];
+        s.x_norm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2]);
+        if (!e.jac_valid) { term = T_FAIL; return V_ENDED; }
+        accept_eval(s, e);
+        s.step_is_successful = 1;
+        const double q = 2.0 * rel - 1.0;
+        s.radius = s.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+        s.radius = fmin(1e16, s.radius);
+        s.decrease_factor = 2.0;
+        s.reuse_diagonal = 0;
+        s.min_iter_cost = fmin(s.min_iter_cost, s.x_cost);
+        return V_ACCEPTED;
+    }
+    s.min_iter_cost = fmin(s.min_iter_cost, cand_cost);
+    s.radius = s.radius / s.decrease_factor;            // StepRejected: the rule does not look at the cost
+    s.decrease_factor *= 2.0;
+    s.reuse_diagonal = 1;
+    s.step_is_successful = 0;
+    return V_REJECTED;
+}
+
+// lm_propose: from the judged state to the next candidate (FinalizeIterationAndCheckIfMinimizerCanContinue, then
+// LevenbergMarquardtStrategy::ComputeStep on the jacobi-scaled normal equations, invalid steps handled like Ceres). Returns
+// T_RUNNING with s.cand / s.model_cost_change set, or how the solve ended. Out of line on purpose: the real minimiser and the
+// speculating lanes (lm_frame_step) must execute the very same instructions, because their candidates are compared bit for bit.
+__device__ __noinline__ int lm_propose(const GridGeom& g, LmCore& s)
+{
+    for (;;) {
         if (s.step_is_successful && s.x_cost < s.minimum_cost) {
             s.minimum_cost = s.x_cost;
             for (int k = 0; k < 3; ++k) s.best[k] = s.x[k];
         }
         s.n_lm_iterations_this_solve++;
-        if (s.iteration >= g.max_lm_iters) { terminate = true; term = T_NOCONV; break; }
-        if (s.step_is_successful && s.gmax <= 1e-10) { terminate = true; term = T_CONV; break; }
-        if (s.radius <= 1e-32) { terminate = true; term = T_CONV; break; }
+        if (s.iteration >= g.max_lm_iters) return T_NOCONV;
+        if (s.step_is_successful && s.gmax <= 1e-10) return T_CONV;
+        if (s.radius <= 1e-32) return T_CONV;
         s.iteration++;
         s.step_is_successful = 0;
-        // LevenbergMarquardtStrategy::ComputeStep on the jacobi-scaled normal equations
         double As[6], bs[3], l[3], y[3];
         const double* sc = s.scale;
         As[0] = s.Au[0] * sc[0] * sc[0]; As[1] = s.Au[1] * sc[0] * sc[1]; As[2] = s.Au[2] * sc[0] * sc[2];
@@ -745,7 +753,7 @@ __device__ void lm_advance(const GridGeom& g, LmState& s, FrameCtl& c, const Eva
             valid = mcc > 0.0;
         }
         if (!valid) {
-            if (++s.num_consecutive_invalid >= 5) { terminate = true; term = T_FAIL; break; }
+            if (++s.num_consecutive_invalid >= 5) return T_FAIL;
             s.radius *= 0.5;
             s.min_iter_cost = fmin(s.min_iter_cost, s.x_cost);
             continue;
@@ -753,44 +761,49 @@ __device__ void lm_advance(const GridGeom& g, LmState& s, FrameCtl& c, const Eva
         s.num_consecutive_invalid = 0;
         s.model_cost_change = mcc;
         for (int k = 0; k < 3; ++k) s.cand[k] = s.x[k] + step[k] * sc[k];
-        pose_coef_dev(s.cand[0], s.cand[1], s.cand[2], c.pose);
-        c.sweep_active = 1;
         s.phase = PH_EVAL_CAND;
-        return;
+        return T_RUNNING;
     }
+}
 
-    // ---- inner solve finished: opt_grid_fitting.h:105-125 ----
+// The inner solve has ended: opt_grid_fitting.h:105-125 (move the cloud, decide whether to go on, compose the transforms) and,
+// at the end of the outer loop, :129-131 + utils.h:47-66 (the corners).
+__device__ void outer_finish(const GridGeom& g, LmState& st, FrameCtl& c, int term, double* corners, int* n_done)
+{
+    LmCore& s = st.core;
+    const bool initial_failure = term == T_FAIL_INITIAL;
+    if (initial_failure) term = T_FAIL;
     const double final_cost = fmin(s.initial_cost, s.min_iter_cost);
     double xo[3] = {0.0, 0.0, 0.0};
     if (term != T_FAIL) for (int k = 0; k < 3; ++k) xo[k] = s.best[k];
     float Tw[16];
     se2_to_se3f_dev(xo[0], xo[1], xo[2], Tw);
     const double rate = (s.initial_cost - final_cost) / s.initial_cost;
-    s.outer_iter++;
-    if (s.outer_iter == 1) {
-        s.rep.first_initial_cost = s.initial_cost;
-        for (int k = 0; k < 3; ++k) s.rep.se2_first[k] = xo[k];
+    st.outer_iter++;
+    if (st.outer_iter == 1) {
+        st.rep.first_initial_cost = s.initial_cost;
+        for (int k = 0; k < 3; ++k) st.rep.se2_first[k] = xo[k];
     }
-    s.rep.last_final_cost = final_cost;
-    s.rep.lm_iterations += s.n_lm_iterations_this_solve;
-    if (term == T_FAIL) { s.status = 1; s.rep.status = 1; }
+    st.rep.last_final_cost = final_cost;
+    st.rep.lm_iterations += s.n_lm_iterations_this_solve;
+    if (term == T_FAIL) { st.status = 1; st.rep.status = 1; }
     if (initial_failure) {
         // x stays (0,0,0) -> identity move -> every remaining outer iteration repeats this failure.
-        const int remaining = g.max_iter_time + 1 - s.outer_iter;
-        if (remaining > 0) { s.rep.pose_evals += remaining; s.outer_iter += remaining; }
+        const int remaining = g.max_iter_time + 1 - st.outer_iter;
+        if (remaining > 0) { st.rep.pose_evals += remaining; st.outer_iter += remaining; }
     }
-    const bool quit = (fabs(rate) < 1e-6) || (s.outer_iter > g.max_iter_time);
+    const bool quit = (fabs(rate) < 1e-6) || (st.outer_iter > g.max_iter_time);
     if (quit) {
-        if (rate > 0) mat4f_mul_dev(Tw, s.T_base_laser, s.T_base_laser);
+        if (rate > 0) mat4f_mul_dev(Tw, st.T_base_laser, st.T_base_laser);
         double Tb[16], Fm[16], Fi[16];
-        for (int k = 0; k < 16; ++k) Tb[k] = (double)s.T_base_laser[k];
+        for (int k = 0; k < 16; ++k) Tb[k] = (double)st.T_base_laser[k];
         for (int r = 0; r < 4; ++r)
             for (int cc = 0; cc < 4; ++cc) {
                 double v = 0;
-                for (int k = 0; k < 4; ++k) v += Tb[r * 4 + k] * s.T_bl[k * 4 + cc];
+                for (int k = 0; k < 4; ++k) v += Tb[r * 4 + k] * st.T_bl[k * 4 + cc];
                 Fm[r * 4 + cc] = v;
             }
-        if (!inverse4_dev(Fm, Fi)) { s.status = 3; s.rep.status = 3; for (int k = 0; k < 16; ++k) Fi[k] = nan(""); }
+        if (!inverse4_dev(Fm, Fi)) { st.status = 3; st.rep.status = 3; for (int k = 0; k < 16; ++k) Fi[k] = nan(""); }
         // utils.h:47-66
         const double sd = g.side;
         const double fcx = double(int((g.board_w - 1) / 2)) * sd, fcy = double(int((g.board_h - 1) / 2)) * sd;
@@ -805,28 +818,46 @@ __device__ void lm_advance(const GridGeom& g, LmState& s, FrameCtl& c, const Eva
                 }
                 ++kk;
             }
-        s.rep.outer_iterations = s.outer_iter;
-        for (int k = 0; k < 16; ++k) s.rep.T_base_laser[k] = s.T_base_laser[k];
+        st.rep.outer_iterations = st.outer_iter;
+        for (int k = 0; k < 16; ++k) st.rep.T_base_laser[k] = st.T_base_laser[k];
         s.phase = PH_DONE;
         c.sweep_active = 0;
+        c.n_pose = 0;
         c.rebin = 0;
         atomicAdd(n_done, 1);
     } else {
-        mat4f_mul_dev(Tw, s.T_base_laser, s.T_base_laser);
+        mat4f_mul_dev(Tw, st.T_base_laser, st.T_base_laser);
         c.move[0] = Tw[0]; c.move[1] = Tw[1]; c.move[2] = Tw[2]; c.move[3] = Tw[3];
         c.move[4] = Tw[4]; c.move[5] = Tw[5]; c.move[6] = Tw[6]; c.move[7] = Tw[7];
         c.rebin = 1;
-        reset_lm_for_outer(s, c);
+        reset_lm_for_outer(st, c);
     }
+}
+
+// With the heuristic Jacobian of board_fitting_cost.h:245-260 Ceres rejects most steps (typically six in a row, then one accept,
+// then rejections until the function tolerance ends the solve). A rejection leaves x, J and r alone and shrinks the radius by a
+// rule that does not look at the cost (radius /= decrease_factor; decrease_factor *= 2), so the poses Ceres will ask for next,
+// IF it keeps rejecting, are known before the first of them has been evaluated. One sweep round evaluates a batch of them; the
+// real minimiser then consumes the evaluations in order for as long as its state is, bit for bit, the state the speculation
+// assumed (lm_frame_step).
+//
+// How many poses the next round should carry is a performance heuristic only (whatever it answers, the minimiser consumes
+// exactly the evaluations Ceres would have made). With initial_trust_region_radius = 1e4 the first accepted step of a solve
+// typically comes after six rejections, and later chains end after 1 .. 7 evaluations: aim each batch at the likely end of the
+// chain instead of always sweeping kSpec poses (measured on the 20 x 500 k frames of BASELINE configs[1]: 1.44 -> 1.12 poses
+// swept per pose consumed).
+__device__ __forceinline__ int speculation_depth(int chain, int n_rejected, int cap)
+{
+    int k;
+    if (chain == 0) k = n_rejected < 7 ? 7 - n_rejected : (n_rejected == 7 ? 2 : 1);
+    else k = n_rejected < 4 ? 4 - n_rejected : (n_rejected < 7 ? 7 - n_rejected : 1);
+    return max(1, min(k, cap));
 }
 
 constexpr int kLmThreads = 128;         // k_ms_cost block size
 
-struct LmStage { LmState lm; FrameCtl ctl; };
+struct LmStage { LmState lm; FrameCtl ctl; double ev[kSpec][12]; LmCore lane_core[kSpec]; };
 
-// One WARP: residuals + heuristic Jacobian + Huber corrector for every target from the accumulator table, 3x3 normal
-// equations reduced with shuffles, then the Ceres step / accept-reject / radius logic and the opt_grid_fitting
-// outer-loop bookkeeping on lane 0. The frame's state is staged through the warp's slice of shared memory.
 // The ten LM terms of one target from its 16 accumulators: residual + heuristic Jacobian (board_fitting_cost.h:211-260),
 // HuberLoss + Corrector (rho'' <= 0 branch): cost 0.5 rho0, r *= sqrt(rho1), J *= sqrt(rho1); then the products the
 // 3x3 normal equations sum. out[0] cost, out[1..6] J'J (00,01,02,11,12,22), out[7..9] J'r, out[10] bad residual,
@@ -850,94 +881,193 @@ __device__ __forceinline__ void target_terms(const double* a16, bool is_row, con
     out[7] = j0 * r;  out[8] = j1 * r;  out[9] = j2 * r;
 }
 
-// One WARP: sums the per-target LM terms into the 3x3 normal equations (shuffles), then the Ceres step / accept-reject /
-// radius logic and the opt_grid_fitting outer-loop bookkeeping on lane 0. HAVE_TERMS: the sweep's tasks have already
-// turned every target's accumulators into its ten terms (bv.terms) and cleared the accumulators; otherwise this warp does
-// that too. The frame's state is staged through the warp's slice of shared memory.
-template <bool HAVE_TERMS>
+template <typename T>
+__device__ __forceinline__ void stage_copy16(T* dst, const T* src, int lane, bool from_global)
+{
+    static_assert(sizeof(T) % 16 == 0, "staged with 16-byte accesses");
+    constexpr int n16 = (int)(sizeof(T) / 16);
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    constexpr int per = (n16 + 31) / 32;
+    int4 v[per];
+#pragma unroll
+    for (int u = 0; u < per; ++u) if (lane + 32 * u < n16) v[u] = from_global ? __ldcg(s4 + lane + 32 * u) : s4[lane + 32 * u];
+#pragma unroll
+    for (int u = 0; u < per; ++u) if (lane + 32 * u < n16) d4[lane + 32 * u] = v[u];
+}
+
+// One WARP, once per (frame, pose slot) and round — the warp that writes the slot's last target: sums the slot's per-target LM
+// terms into the 3x3 normal equations. Fixed order (lane-strided over the targets, then a butterfly), so a pose's sums do not
+// depend on the slot or the round it was evaluated in. All loads are in flight together: one L2 round trip.
+__device__ __forceinline__ void slot_sums(const BatchView& bv, int f, int slot, int lane)
+{
+    const int nt = bv.geom.nt;
+    const double* tm = bv.terms + ((size_t)f * kSpec + slot) * 12 * nt;
+    double sums[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) sums[k] = 0.0;
+    for (int t0 = 0; t0 < nt; t0 += 96) {
+        double v[3][12];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int t = t0 + lane + 32 * u;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) v[u][k] = t < nt ? __ldcg(tm + (size_t)k * nt + t) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+            for (int k = 0; k < 12; ++k) sums[k] += v[u][k];
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) sums[k] = warp_sum(sums[k]);
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) if (lane == k) mine = sums[k];
+    if (lane < 12) bv.evsum[((size_t)f * kSpec + slot) * 12 + lane] = mine;
+}
+
+// One WARP, once per frame and round (the warp that finishes the frame's last pose slot): replays Ceres on the evaluations of
+// the round (lane 0), runs the opt_grid_fitting outer-loop bookkeeping, and proposes the poses of the next round — lane k
+// computes the candidate Ceres will ask for after k further rejections, all lanes at once. The frame's state is staged through
+// shared memory (one LmStage per CTA: all warps of a CTA work on the same frame, and only one warp per frame and launch gets
+// here).
 __device__ __noinline__ void lm_frame_step(const BatchView& bv, int f, LmStage* stage)
 {
     const int lane = threadIdx.x & 31;
-    const long long c0 = clock64();
     const GridGeom& g = bv.geom;
     LmState& s_lm = stage->lm;
     FrameCtl& s_ctl = stage->ctl;
-    {
-        // 16-byte loads, all in flight before the first store to shared memory
-        static_assert(sizeof(LmState) % 16 == 0 && sizeof(FrameCtl) % 8 == 0 && sizeof(LmState) / 16 <= 96, "state staging");
-        const int4* gl = reinterpret_cast<const int4*>(&bv.lm[f]);
-        int4* sl = reinterpret_cast<int4*>(&s_lm);
-        constexpr int n16 = (int)(sizeof(LmState) / 16);
-        int4 v[3];
-#pragma unroll
-        for (int u = 0; u < 3; ++u) if (lane + 32 * u < n16) v[u] = __ldcg(gl + lane + 32 * u);
-        const int2* gc = reinterpret_cast<const int2*>(&bv.ctl[f]);
-        int2* sc = reinterpret_cast<int2*>(&s_ctl);
-        constexpr int n8 = (int)(sizeof(FrameCtl) / 8);
-        static_assert(n8 <= 32, "FrameCtl staging");
-        int2 w = make_int2(0, 0);
-        if (lane < n8) w = __ldcg(gc + lane);
-#pragma unroll
-        for (int u = 0; u < 3; ++u) if (lane + 32 * u < n16) sl[lane + 32 * u] = v[u];
-        if (lane < n8) sc[lane] = w;
+#ifdef RCLC_LAB
+    long long tm[5];
+    auto now = [] { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    tm[0] = now();
+#endif
+    stage_copy16(&s_lm, &bv.lm[f], lane, true);
+    stage_copy16(&s_ctl, &bv.ctl[f], lane, true);
+    if (lane < kSpec * 12 / 4) {            // evsum[f]: kSpec x 12 doubles, 32 bytes per lane
+        const int4* src = reinterpret_cast<const int4*>(bv.evsum + (size_t)f * kSpec * 12) + 2 * lane;
+        const int4 a = __ldcg(src), b = __ldcg(src + 1);
+        int4* dst = reinterpret_cast<int4*>(&stage->ev[0][0]) + 2 * lane;
+        dst[0] = a; dst[1] = b;
     }
     __syncwarp();
-    const long long c1 = clock64();
-    const PoseCoef pc = s_ctl.pose;
-    double sums[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // cost, A00,A01,A02,A11,A12,A22, b0,b1,b2
-    int bad_r = 0, bad_j = 0;
-    if (HAVE_TERMS) {
-        const double* tm = bv.terms + (size_t)f * 12 * g.nt;
-        for (int t = lane; t < g.nt; t += 32) {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) sums[k] += __ldcg(tm + (size_t)k * g.nt + t);
-            if (__ldcg(tm + (size_t)10 * g.nt + t) != 0.0) bad_r = 1;
-            if (__ldcg(tm + (size_t)11 * g.nt + t) != 0.0) bad_j = 1;
+    const int n_pose = s_ctl.n_pose;
+#ifdef RCLC_LAB
+    tm[1] = now();
+#endif
+    // ---- replay (lane 0) ----
+    int need = 0;                   // 0: no proposal wanted (frame done, or next outer iteration); 1: propose from the judged state
+    if (lane == 0) {
+        LmCore& s = s_lm.core;
+        s_lm.rep.rounds++;
+        s_lm.rep.poses_swept += n_pose;
+        for (int i = 0; i < n_pose; ++i) {
+            if (i > 0) {
+                // adopt the proposal lane i made in the last round: valid iff the state it assumed is the state we are in
+                if (!(s.radius == s_lm.spec_radius[i] && s.decrease_factor == s_lm.spec_factor[i])) { s_lm.rep.spec_mismatch++; need = 1; break; }
+                s.n_lm_iterations_this_solve++;             // what lm_propose does on a clean pass (no invalid step, no end)
+                s.iteration++;
+                s.step_is_successful = 0;
+                s.reuse_diagonal = 1;
+                s.num_consecutive_invalid = 0;
+                s.model_cost_change = s_lm.spec_mcc[i];
+                for (int k = 0; k < 3; ++k) s.cand[k] = s_lm.spec[i][k];
+            }
+            EvalSums e;
+            e.cost = stage->ev[i][0];
+            for (int k = 0; k < 6; ++k) e.A[k] = stage->ev[i][1 + k];
+            for (int k = 0; k < 3; ++k) e.b[k] = stage->ev[i][7 + k];
+            e.res_valid = stage->ev[i][10] == 0.0;
+            e.jac_valid = e.res_valid && stage->ev[i][11] == 0.0;
+            const bool was_init = s.phase == PH_EVAL_INIT;
+            if (was_init) s_ctl.rebin = 0;
+            s_lm.rep.pose_evals++;
+            int term;
+            const int verdict = lm_judge(g, s, e, term);
+            if (verdict == V_ENDED) {
+                outer_finish(g, s_lm, s_ctl, term, bv.corners + (size_t)f * g.nc * 3, bv.n_done);
+                need = 0;
+                break;
+            }
+            need = 1;
+            if (verdict == V_ACCEPTED) { s_lm.chain = was_init ? 0 : 1; s_lm.n_rejected = 0; break; }       // new J: the rest of the batch is void
+            s_lm.n_rejected++;
         }
-    } else {
-        const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
-        const double cth = cos(theta), sth = sin(theta);
-        double* acc = bv.acc + (size_t)f * g.nt * 16;
-        for (int t = lane; t < g.nt; t += 32) {
-            double a16[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) a16[k] = __ldcg(acc + (size_t)t * 16 + k);
-            double tt[12];
-            target_terms(a16, bv.tgt_is_row[t] != 0, pc, cth, sth, g.huber_a, tt);
-#pragma unroll
-            for (int k = 0; k < 10; ++k) sums[k] += tt[k];
-            if (tt[10] != 0.0) bad_r = 1;
-            if (tt[11] != 0.0) bad_j = 1;
+#ifdef RCLC_LAB
+        tm[2] = now();
+#endif
+        if (need) stage->lane_core[0] = s;
+    }
+    need = __shfl_sync(0xffffffffu, need, 0);
+    __syncwarp();
+    // ---- proposals: lane k's copy of the judged state is rejected k more times, then proposes ----
+    if (need) {
+        const int depth = speculation_depth(s_lm.chain, s_lm.n_rejected, bv.npose_max);
+        int term = T_RUNNING;
+        bool clean = false;
+        double r_in = 0.0, f_in = 0.0;
+        if (lane < depth) {
+            LmCore& c = stage->lane_core[lane];
+            if (lane > 0) {
+                c = stage->lane_core[0];
+                for (int j = 0; j < lane; ++j) {
+                    if (j > 0) { c.n_lm_iterations_this_solve++; c.iteration++; }      // the clean lm_propose pass before rejection j + 1 ...
+                    c.radius = c.radius / c.decrease_factor;                           // ... and StepRejected
+                    c.decrease_factor *= 2.0;
+                }
+                // (the first pass, on the judged state, is lane 0's own: counted below once lane 0 has shown to be clean)
+                c.n_lm_iterations_this_solve++; c.iteration++;
+                c.step_is_successful = 0;
+                c.num_consecutive_invalid = 0;
+                // (reuse_diagonal stays as judged: after an accepted step every lane derives the same diagonal from the same J'J)
+            }
+            r_in = c.radius; f_in = c.decrease_factor;
         }
         __syncwarp();
-        for (int k = lane; k < g.nt * 16; k += 32) acc[k] = 0.0;      // consumed: clear for the next sweep
-    }
-    const long long c2 = clock64();
-#pragma unroll
-    for (int k = 0; k < 10; ++k) sums[k] = warp_sum(sums[k]);
-    bad_r = __any_sync(0xffffffffu, bad_r);
-    bad_j = __any_sync(0xffffffffu, bad_j);
-    const long long c3 = clock64();
-    if (lane == 0) {
-        EvalSums e;
-        e.cost = sums[0];
-        for (int k = 0; k < 6; ++k) e.A[k] = sums[1 + k];
-        for (int k = 0; k < 3; ++k) e.b[k] = sums[7 + k];
-        e.res_valid = !bad_r;
-        e.jac_valid = e.res_valid && !bad_j;
-        lm_advance(g, s_lm, s_ctl, e, bv.corners + (size_t)f * g.nc * 3, bv.n_done);
-        const long long c4 = clock64();
-        s_lm.dbg[0] += c1 - c0; s_lm.dbg[1] += c2 - c1; s_lm.dbg[2] += c3 - c2; s_lm.dbg[3] += c4 - c3; s_lm.dbg[4] += 1;
+        if (lane < depth) {
+            LmCore& c = stage->lane_core[lane];
+            const int iter_in = c.iteration;
+            term = lm_propose(g, c);
+            clean = term == T_RUNNING && c.radius == r_in && c.iteration == iter_in + 1;      // no invalid step inside, no end
+        }
+        // lane k is usable iff lanes 0 .. k are all clean; lane 0's own result is the real minimiser's whatever it is
+        const unsigned dirty = __ballot_sync(0xffffffffu, lane < depth && !clean) | (depth < 32 ? ~0u << depth : 0u);
+        const int n_next = max(1, __ffs(dirty) - 1);
+        if (lane == 0) {
+            LmCore& s = s_lm.core;
+            s = stage->lane_core[0];
+            if (term != T_RUNNING) {
+                outer_finish(g, s_lm, s_ctl, term, bv.corners + (size_t)f * g.nc * 3, bv.n_done);
+            } else {
+                s_ctl.sweep_active = 1;
+                s_ctl.n_pose = n_next;
+            }
+        }
+        __syncwarp();
+        if (s_lm.core.phase == PH_EVAL_CAND && lane < s_ctl.n_pose) {
+            const LmCore& c = stage->lane_core[lane];
+            for (int k = 0; k < 3; ++k) s_lm.spec[lane][k] = c.cand[k];
+            s_lm.spec_mcc[lane] = c.model_cost_change;
+            s_lm.spec_radius[lane] = r_in;
+            s_lm.spec_factor[lane] = f_in;
+            pose_coef_dev(c.cand[0], c.cand[1], c.cand[2], s_ctl.pose[lane]);
+        }
     }
     __syncwarp();
-    {
-        int4* gl = reinterpret_cast<int4*>(&bv.lm[f]);
-        const int4* sl = reinterpret_cast<const int4*>(&s_lm);
-        for (int k = lane; k < (int)(sizeof(LmState) / 16); k += 32) gl[k] = sl[k];
-        int2* gc = reinterpret_cast<int2*>(&bv.ctl[f]);
-        const int2* sc = reinterpret_cast<const int2*>(&s_ctl);
-        if (lane < (int)(sizeof(FrameCtl) / 8)) gc[lane] = sc[lane];
+#ifdef RCLC_LAB
+    if (lane == 0) {
+        tm[3] = now();
+        tm[4] = tm[3];
+        for (int k = 0; k < 3; ++k) s_lm.dbg[k] += tm[k + 1] - tm[k];
+        s_lm.dbg[4] += 1;
+        if (s_lm.dbg[5] == 0) s_lm.dbg[5] = tm[0];          // first LM step of the solve
+        s_lm.dbg[6] = tm[4];                                 // last
     }
+    __syncwarp();
+#endif
+    stage_copy16(&bv.lm[f], &s_lm, lane, false);
+    stage_copy16(&bv.ctl[f], &s_ctl, lane, false);
     // the next outer iteration starts with the points moved in place (k_move walks this list)
     if (s_ctl.rebin && lane == 0) bv.rebin_list[(bv.list_parity ^ 1) * bv.n_frames + atomicAdd(&bv.rebin_cnt[bv.list_parity ^ 1], 1)] = f;
     __syncwarp();
@@ -1027,19 +1157,21 @@ __device__ __forceinline__ void point_geom(const SweepConst& k, float qx, float 
 //   a[0] += [in] v          a[1] += [in] s_y v          a[2] += [in] s_x v        (s = -1 when down / right)
 //   a[3] += [cost] v        a[4] += [cost] s_y v        a[5] += [cost] s_x v
 // All products and sums are exact, so down = (a0 - a1) / 2 etc. are exact too (to_nested_totals).
-__device__ __forceinline__ void accumulate6(double (&a)[6], float d2, float wx, float wy, float rg2, float rc2, double v, bool member)
+__device__ __forceinline__ void accumulate6(double (&a)[6], float d2, float wx, float wy, float rg2, float rc2, double v, bool member, int zlo)
 {
     const uint32_t one = 0x3ff00000u;
     const uint32_t hin = (member && d2 <= rg2) ? one : 0u;
     const uint32_t hc = (member && d2 < rc2) ? one : 0u;
     // s = -1 (sign bit set) when down / right, i.e. when w is positive (sign bit clear)
     const uint32_t sy = ~__float_as_uint(wy) & 0x80000000u, sx = ~__float_as_uint(wx) & 0x80000000u;
-    a[0] = fma(__hiloint2double((int)hin, 0), v, a[0]);
-    a[1] = fma(__hiloint2double((int)(hin ^ sy), 0), v, a[1]);
-    a[2] = fma(__hiloint2double((int)(hin ^ sx), 0), v, a[2]);
-    a[3] = fma(__hiloint2double((int)hc, 0), v, a[3]);
-    a[4] = fma(__hiloint2double((int)(hc ^ sy), 0), v, a[4]);
-    a[5] = fma(__hiloint2double((int)(hc ^ sx), 0), v, a[5]);
+    // zlo: a zero the compiler cannot see through (stream_rows), so the six multipliers share ONE low word held in a register
+    // instead of six freshly zeroed ones per point
+    a[0] = fma(__hiloint2double((int)hin, zlo), v, a[0]);
+    a[1] = fma(__hiloint2double((int)(hin ^ sy), zlo), v, a[1]);
+    a[2] = fma(__hiloint2double((int)(hin ^ sx), zlo), v, a[2]);
+    a[3] = fma(__hiloint2double((int)hc, zlo), v, a[3]);
+    a[4] = fma(__hiloint2double((int)(hc ^ sy), zlo), v, a[4]);
+    a[5] = fma(__hiloint2double((int)(hc ^ sx), zlo), v, a[5]);
 }
 
 // signed sums -> the six nested totals (in, in&down, in&right, cost, cost&down, cost&right); exact
@@ -1167,13 +1299,15 @@ __device__ __forceinline__ void stream_rows(const float4* __restrict__ src, cons
 {
     const char* lsrc = reinterpret_cast<const char*>(src + lane);
     const uint32_t lring = ring + lane * 16u;
+    int zlo;
+    asm volatile("mov.b32 %0, 0;" : "=r"(zlo));
     auto one_row = [&](const float4& qq) {
         float wx, wy, d2;
         point_geom(k, qq.x, qq.y, wx, wy, d2);
         const double v = (double)qq.z + kCntUnit;
         mA = fminf(mA, fminf(fabsf(__fsub_rn(d2, k.rg2)), fabsf(__fsub_rn(d2, k.rc2))));
         mB = fminf(mB, fminf(fabsf(wx), fabsf(wy)));
-        accumulate6(acc, d2, wx, wy, k.rg2, k.rc2, v, !MASKED || is_neighbour(k.tqx, k.tqy, k.rn2, qq.x, qq.y, qq.w));
+        accumulate6(acc, d2, wx, wy, k.rg2, k.rc2, v, !MASKED || is_neighbour(k.tqx, k.tqy, k.rn2, qq.x, qq.y, qq.w), zlo);
     };
     auto issue_group = [&](int g) {           // rows g*4 .. g*4+3 of the (padded) list -> slot g % kRingGroups
         const uint32_t slot = lring + (uint32_t)(g % kRingGroups) * (kGroupRows * 512u);
@@ -1241,16 +1375,7 @@ __device__ __forceinline__ void drain_list(int mode, const float4* __restrict__ 
     __syncwarp();
 }
 
-// The LM step as its own launch (one warp per frame) — RCLC_LM_SEPARATE=1, an A/B switch for the fused variant.
-__global__ void __launch_bounds__(32) k_lm(const __grid_constant__ BatchView bv)
-{
-    const int f = blockIdx.x;
-    if (!bv.ctl[f].sweep_active) return;
-    __shared__ LmStage stage;
-    lm_frame_step<false>(bv, f, &stage);
-}
-
-constexpr size_t kSweepSmem = (size_t)kSweepWarps * (kRingBytes + kListCap * 4 + 16 * 8 + 12 * 8 + sizeof(WarpCtx) + sizeof(LmStage));
+constexpr size_t kSweepSmem = (size_t)kSweepWarps * (kRingBytes + kListCap * 4 + 16 * 8 + 12 * 8 + sizeof(WarpCtx)) + sizeof(LmStage);
 static_assert(kListPad <= 32, "one lane per padding entry");
 
 // Three CTAs (12 warps) per SM: with 160 registers the hot loop and the cold paths around it keep everything in registers.
@@ -1271,18 +1396,20 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int parts = bv.parts;
     const int task = blockIdx.x * kSweepWarps + warp;
-    const int t = task / parts, part = task - t * parts;
-    if (t >= bv.geom.nt) return;
+    // tasks of a frame: pose slot (slowest), target, part — the slots a round does not use are the CTAs at the end of the grid
+    const int slot = task / (bv.geom.nt * parts), t = (task - slot * bv.geom.nt * parts) / parts, part = task % parts;
+    if (slot >= bv.npose_max) return;
     const int fd = bv.fixed_frame >= 0 ? bv.fixed_frame : f;      // frame whose points are read
     // everything the task needs from global memory, requested before the first use
     const FrameCtl& c = bv.ctl[f];
     const int active = c.sweep_active;
-    const PoseCoef pc = c.pose;
+    const int n_pose = c.n_pose;
+    const PoseCoef pc = c.pose[slot];
     const int use_exact = c.use_exact;
     const float drift = bv.ctl[fd].drift;
     const double2 ref = bv.tgt_xy[t];
     const float2 tq = bv.tgt_xyf[t];
-    if (!active) return;
+    if (!active || slot >= n_pose) return;
 
     extern __shared__ __align__(128) unsigned char s_dyn[];
     unsigned char* sp = s_dyn;
@@ -1291,7 +1418,7 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
     double* scratch16 = reinterpret_cast<double*>(sp) + warp * 16;                sp += kSweepWarps * 16 * 8;
     double* tot = reinterpret_cast<double*>(sp) + warp * 12;                      sp += kSweepWarps * 12 * 8;
     WarpCtx* wc = reinterpret_cast<WarpCtx*>(sp) + warp;                          sp += kSweepWarps * sizeof(WarpCtx);
-    LmStage* stage = reinterpret_cast<LmStage*>(sp) + warp;
+    LmStage* stage = reinterpret_cast<LmStage*>(sp);
 
     const GridGeom& g = bv.geom;
     const bool exact_body = bv.force_exact || use_exact;
@@ -1412,26 +1539,26 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
     if (mode != 2 && rows_since_split > 0) reduce_totals(acc, tot, lane);
     if (lane == 0) store_totals(scratch16, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], tot[6], tot[7], tot[8], tot[9], tot[10], tot[11]);
     __syncwarp();
+    double* acc_t = bv.acc + (size_t)f * bv.acc_stride + ((size_t)slot * g.nt + t) * 16;
     if (lane < 16) {
-        double* dst = bv.acc + ((size_t)f * g.nt + t) * 16 + lane;
         const double v = scratch16[lane];
-        if (parts > 1) { if (v != 0.0) atomicAdd(dst, v); }
-        else *dst = v;
+        if (parts > 1) { if (v != 0.0) atomicAdd(acc_t + lane, v); }
+        else acc_t[lane] = v;
     }
     if (!bv.fuse_lm) return;
-    // ---- fused LM step, part 1: the warp that adds the target's last share turns its 16 accumulators into the ten LM terms
+    // ---- fused LM step, part 1: the warp that adds the (pose, target)'s last share turns its 16 accumulators into the LM terms
     //      (in parallel over the targets, overlapped with the tasks still sweeping) and clears them for the next sweep ----
-    if (bv.fuse_lm != 2) fence_acq_rel_gpu();
+    fence_acq_rel_gpu();
     int last = 1;
     if (parts > 1) {
-        if (lane == 0) last = (atomicAdd(&bv.tgt_done[(size_t)f * g.nt + t], 1) == parts - 1);
+        int* td = bv.tgt_done + ((size_t)f * kSpec + slot) * g.nt + t;
+        if (lane == 0) last = (atomicAdd(td, 1) == parts - 1);
         last = __shfl_sync(0xffffffffu, last, 0);
         if (!last) return;
-        if (bv.fuse_lm != 2) fence_acq_rel_gpu();
-        if (lane == 0) bv.tgt_done[(size_t)f * g.nt + t] = 0;
+        fence_acq_rel_gpu();
+        if (lane == 0) *td = 0;
     }
     {
-        double* acc_t = bv.acc + ((size_t)f * g.nt + t) * 16;
         double a16[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) a16[q] = __ldcg(acc_t + q);               // same addresses in every lane: one transaction each
@@ -1440,30 +1567,40 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
         const double cth = cos(theta), sth = sin(theta);
         double tt[12];
         target_terms(a16, bv.tgt_is_row[t] != 0, pcc, cth, sth, g.huber_a, tt);
-        double* tm = bv.terms + (size_t)f * 12 * g.nt + t;
+        double* tm = bv.terms + ((size_t)f * kSpec + slot) * 12 * g.nt + t;
         double mine = 0.0;
 #pragma unroll
         for (int q = 0; q < 12; ++q) if (lane == q) mine = tt[q];
         if (lane < 12) tm[(size_t)lane * g.nt] = mine;
         if (lane >= 16) acc_t[lane - 16] = 0.0;
     }
-    // ---- part 2: the warp that finishes the frame's last target sums the terms and runs the LM state machine ----
-    if (bv.fuse_lm != 2) fence_acq_rel_gpu();
+    // ---- part 2: the warp that writes a pose slot's last target sums the slot's terms (all lanes, one L2 round trip) ----
+    fence_acq_rel_gpu();
     last = 0;
-    if (lane == 0) last = (atomicAdd(&bv.sweep_done[f], 1) == g.nt - 1);
+    if (lane == 0) last = (atomicAdd(&bv.slot_done[(size_t)f * kSpec + slot], 1) == g.nt - 1);
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
-    if (bv.fuse_lm != 2) fence_acq_rel_gpu();
+    fence_acq_rel_gpu();
+    if (lane == 0) bv.slot_done[(size_t)f * kSpec + slot] = 0;
+    slot_sums(bv, f, slot, lane);
+    // ---- part 3: the warp that finishes the frame's last pose slot runs the LM state machine ----
+    fence_acq_rel_gpu();
+    last = 0;
+    if (lane == 0) last = (atomicAdd(&bv.sweep_done[f], 1) == n_pose - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    fence_acq_rel_gpu();
     if (lane == 0) bv.sweep_done[f] = 0;
-    lm_frame_step<true>(bv, f, stage);
+    lm_frame_step(bv, f, stage);
 }
 
 __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
 {
     const int f = blockIdx.x;
-    for (int k = threadIdx.x; k < bv.geom.nt * 16; k += blockDim.x) bv.acc[(size_t)f * bv.geom.nt * 16 + k] = 0.0;
+    for (int k = threadIdx.x; k < bv.geom.nt * 16; k += blockDim.x) bv.acc[(size_t)f * bv.acc_stride + k] = 0.0;
     if (threadIdx.x == 0) {
-        bv.ctl[f].pose = poses[f];
+        bv.ctl[f].pose[0] = poses[f];
+        bv.ctl[f].n_pose = 1;
         bv.ctl[f].sweep_active = 1;
         bv.ctl[f].rebin = 0;
     }
@@ -1479,7 +1616,7 @@ __global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, const PoseCoef* __res
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    FrameCtl c;
+    FrameCtl& c = ctl_ms[p];
     c.sweep_active = 1;
     c.rebin = 0;
     c.n_rows = bv.ctl[frame].n_rows;
@@ -1487,20 +1624,20 @@ __global__ void k_ms_setup(BatchView bv, FrameCtl* ctl_ms, const PoseCoef* __res
     c.use_exact = bv.ctl[frame].use_exact;
     c.drift = bv.ctl[frame].drift;
     for (int k = 0; k < 8; ++k) c.move[k] = 0.f;
-    c.pose = poses[p];
-    ctl_ms[p] = c;
+    c.n_pose = 1;
+    c.pose[0] = poses[p];
 }
 
 __global__ void __launch_bounds__(kLmThreads) k_ms_cost(BatchView bv, double* __restrict__ cost_out)
 {
     const int p = blockIdx.x;
     const GridGeom& g = bv.geom;
-    const PoseCoef pc = bv.ctl[p].pose;
+    const PoseCoef pc = bv.ctl[p].pose[0];
     const double theta = (pc.yaw_deg * 3.14159265358979323846) / 180.0;
     const double cth = cos(theta), sth = sin(theta);
     __shared__ double s_red[kLmThreads / 32][2];
     double cost = 0, bad = 0;
-    const double* acc = bv.acc + (size_t)p * g.nt * 16;
+    const double* acc = bv.acc + (size_t)p * bv.acc_stride;
     for (int t = threadIdx.x; t < g.nt; t += kLmThreads) {
         double r, j0, j1, j2;
         target_residual(acc + (size_t)t * 16, bv.tgt_is_row[t] != 0, pc.tx, pc.ty, cth, sth, r, j0, j1, j2);
@@ -1523,6 +1660,8 @@ __global__ void __launch_bounds__(kLmThreads) k_ms_cost(BatchView bv, double* __
 // Host side of the batch
 // ------------------------------------------------------------------------------------------------
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+constexpr int kRoundsPerGraph = 12;      // rounds per graph launch: a solve takes about three rounds per outer iteration
 
 // The binning kernels walk the re-bin list with gridDim.y CTA columns: most rounds have nothing (or one frame) to
 // move and must cost next to nothing, while one frame alone still gets hundreds of CTAs.
@@ -1550,12 +1689,14 @@ static BatchView slice_view(const BatchView& v, int f0, int nf, int group)
     s.cellcnt = v.cellcnt + (size_t)f0 * nc;
     s.cellz2 = v.cellz2 + (size_t)f0 * nc;
     s.rowbox = v.rowbox + (size_t)f0 * (v.frame_stride / 32);
-    s.acc = v.acc + (size_t)f0 * nt * 16;
+    s.acc = v.acc + (size_t)f0 * v.acc_stride;
     s.ctl = v.ctl + f0;
     s.lm = v.lm + f0;
     s.bin_done = v.bin_done + f0;
-    s.terms = v.terms + (size_t)f0 * nt * 12;
-    s.tgt_done = v.tgt_done + (size_t)f0 * nt;
+    s.terms = v.terms + (size_t)f0 * kSpec * nt * 12;
+    s.tgt_done = v.tgt_done + (size_t)f0 * kSpec * nt;
+    s.slot_done = v.slot_done + (size_t)f0 * kSpec;
+    s.evsum = v.evsum + (size_t)f0 * kSpec * 12;
     s.sweep_done = v.sweep_done + f0;
     s.eval_out = v.eval_out + (size_t)f0 * nt * 4;
     s.corners = v.corners + (size_t)f0 * ncorn * 3;
@@ -1598,17 +1739,15 @@ static int launch_move(rclc_batch* b, GroupRun& gr)
     return RCLC_OK;
 }
 
-// One warp per (target, part). Tasks are latency-heavy at both ends (cell and box look-ups, the final reduction), so fewer
-// and longer tasks win: measured on B200 the best split of a plain sweep is parts = 1 from 20 active 8x6 frames up and 8
+// One warp per (pose slot, target, part). Tasks are latency-heavy at both ends (cell and box look-ups, the final reduction), so
+// fewer and longer tasks win: measured on B200 the best split of a plain sweep is parts = 1 from 20 active 8x6 frames up and 8
 // for a single one (profiles/r01_sweep_history.md).
 // Inside the solve (fused LM step) a finer split is better: a frame's LM step starts when its last task ends, and short
-// tasks let the first frames' LM steps overlap the sweeping of the later ones.
+// tasks let the first frames' LM steps overlap the sweeping of the later ones. Most rounds of a solve carry kSpec poses per frame.
 static int sweep_parts(const rclc_batch* b, int n_frames, bool fused)
 {
     const double slots = (double)b->ctx->sm_count * 12.0;              // resident warps (3 CTAs of 4 warps per SM)
-    const double tasks = (double)std::max(n_frames, 1) * b->v.geom.nt;
-    static const int forced = [] { const char* e = std::getenv("RCLC_SWEEP_PARTS"); return e ? atoi(e) : 0; }();
-    if (forced > 0) return forced;
+    const double tasks = (double)std::max(n_frames, 1) * b->v.geom.nt * (fused ? 0.75 * kSpec : 1.0);
     if (fused) return (int)std::max(1.0, std::min(8.0, std::ceil(2.0 * slots / tasks)));
     return (int)std::max(1.0, std::min(8.0, std::floor(0.9 * slots / tasks + 0.5)));
 }
@@ -1616,9 +1755,9 @@ static int sweep_parts(const rclc_batch* b, int n_frames, bool fused)
 static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames, cudaStream_t st, int frames_in_flight)
 {
     v.parts = sweep_parts(b, frames_in_flight, v.fuse_lm != 0);
-    const int gx = (v.geom.nt * v.parts + kSweepWarps - 1) / kSweepWarps;
-    static const int dense_mode = [] { const char* e = std::getenv("RCLC_MS_DENSE"); return e ? atoi(e) : 1; }();
-    if (v.fixed_frame >= 0 && dense_mode) k_sweep_dense<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
+    v.npose_max = v.fuse_lm ? kSpec : 1;
+    const int gx = (v.geom.nt * v.parts * v.npose_max + kSweepWarps - 1) / kSweepWarps;
+    if (v.fixed_frame >= 0) k_sweep_dense<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
     else k_sweep<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
     b->ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
@@ -1680,13 +1819,13 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     b->n_frames = n_frames;
     b->max_pts = max_pts;
     b->h_npts.assign(n_frames, 0);
-    { const char* e = std::getenv("RCLC_SWEEP_EXACT"); b->sweep_exact = e && e[0] == '1'; }
     BatchView& v = b->v;
     v.geom = hg.g;
     v.n_frames = n_frames;
     v.fixed_frame = -1;
     v.fuse_lm = 0;
-    v.force_exact = b->sweep_exact ? 1 : 0;
+    v.force_exact = 0;
+    v.npose_max = 1;
     // every cell's segment of `binned` is padded to a multiple of 32 points
     v.frame_stride = (int64_t)align256(((size_t)max_pts + 32 * (size_t)hg.g.ncells) * 16) / 16;
     v.parts = 1;
@@ -1703,8 +1842,9 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     auto take = [&](size_t bytes) { size_t o = off; off = align256(off + bytes); return o; };
     const size_t o_npts = take(F * 8), o_hist = take(F * nfine * 4), o_cur = take(F * nfine * 4), o_cmask = take(F * ncell * 4);
     const size_t o_cstart = take(F * ncell * 4), o_ccnt = take(F * ncell * 4), o_box = take(F * (size_t)(v.frame_stride / 32) * 16);
-    const size_t o_acc = take(F * nt * 16 * 8), o_ctl = take(F * sizeof(FrameCtl));
-    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_bdone = take(F * 4), o_rlist = take(2 * F * 4), o_rcnt = take(256), o_terms = take(F * nt * 12 * 8), o_tdone = take(F * nt * 4), o_txy = take(nt * 16), o_txyf = take(nt * 8);
+    v.acc_stride = (int64_t)kSpec * nt * 16;
+    const size_t o_acc = take(F * (size_t)v.acc_stride * 8), o_ctl = take(F * sizeof(FrameCtl));
+    const size_t o_lm = take(F * sizeof(LmState)), o_done = take(256), o_sdone = take(F * 4), o_bdone = take(F * 4), o_rlist = take(2 * F * 4), o_rcnt = take(256), o_terms = take(F * kSpec * nt * 12 * 8), o_tdone = take(F * kSpec * nt * 4), o_sldone = take(F * kSpec * 4), o_evsum = take(F * kSpec * 12 * 8), o_txy = take(nt * 16), o_txyf = take(nt * 8);
     const size_t o_row = take(nt), o_eval = take(F * nt * 4 * 8);
     const size_t o_corn = take(F * (size_t)hg.g.nc * 3 * 8), o_gmm = take(F * 64 * 8 + 4096 * 8 * 8);
     if (cudaMalloc(&b->d_block, off) != cudaSuccess) return fail("cudaMalloc block");
@@ -1726,6 +1866,8 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.bin_done = reinterpret_cast<int*>(base + o_bdone);
     v.terms = reinterpret_cast<double*>(base + o_terms);
     v.tgt_done = reinterpret_cast<int*>(base + o_tdone);
+    v.slot_done = reinterpret_cast<int*>(base + o_sldone);
+    v.evsum = reinterpret_cast<double*>(base + o_evsum);
     v.rebin_list = reinterpret_cast<int*>(base + o_rlist);
     v.rebin_cnt = reinterpret_cast<int*>(base + o_rcnt);
     v.list_parity = 0;
@@ -1762,8 +1904,7 @@ int rclc_batch_destroy(rclc_batch* b)
 // group's frames have arrived, while the copy engine is still busy with the later groups.
 static int solve_groups(const rclc_batch* b)
 {
-    static const int want_groups = [] { const char* e = std::getenv("RCLC_SOLVE_GROUPS"); return e ? std::max(1, std::min(32, atoi(e))) : 10; }();
-    return std::max(1, std::min(want_groups, b->n_frames));
+    return std::max(1, std::min(b->ctx->solve_groups, b->n_frames));
 }
 static int ensure_group_streams(rclc_ctx* ctx, int G)
 {
@@ -1880,12 +2021,23 @@ int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* 
     RCLC_CUDA(cudaGetLastError());
     std::vector<double> h(F * nt * 4);
     RCLC_CUDA(cudaMemcpyAsync(h.data(), b->v.eval_out, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (acc) RCLC_CUDA(cudaMemcpyAsync(acc, b->v.acc, F * nt * 16 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (acc)            // pose slot 0 of every frame
+        RCLC_CUDA(cudaMemcpy2DAsync(acc, nt * 16 * 8, b->v.acc, (size_t)b->v.acc_stride * 8, nt * 16 * 8, F, cudaMemcpyDeviceToHost, ctx->stream));
     RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (size_t k = 0; k < F * nt; ++k) {
         if (residuals) residuals[k] = h[4 * k];
         if (jac) { jac[3 * k] = h[4 * k + 1]; jac[3 * k + 1] = h[4 * k + 2]; jac[3 * k + 2] = h[4 * k + 3]; }
     }
+    return RCLC_OK;
+}
+
+int rclc_batch_set_exact_sweep(rclc_batch* b, int32_t on)
+{
+    RCLC_CHECK(b, RCLC_ERR_INVALID, "null batch");
+    b->v.force_exact = on ? 1 : 0;
+    for (cudaGraphExec_t ge : b->round_graphs) cudaGraphExecDestroy(ge);      // the graphs hold the view by value
+    b->round_graphs.clear();
+    b->graphs_groups = 0;
     return RCLC_OK;
 }
 
@@ -1909,10 +2061,8 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
     RCLC_TRY(ctx->h_pin2.reserve(256));
     int* h_done = ctx->h_pin2.as<int>();           // [G] finished frames per group, as of each group's last poll
     // Frames are independent until the extrinsic solve, so the batch runs as G groups on G streams, each advancing on its own:
-    // while the LM steps of one group (a single warp per frame, ~7 us of dependent fp64) hold the tail of its sweep kernel, the
-    // other groups' sweeps keep the SMs busy, and a group whose frames need few rounds finishes early. RCLC_SOLVE_GROUPS
-    // overrides the default of 10 (measured on 20 x 500 k points, ms per step resident / end to end: 4 groups 16.3 / 18.9,
-    // 8: 16.0 / 18.0, 10: 15.7 / 18.2, 16: 16.3 / 17.6, 20: 16.8 / 17.5).
+    // while the LM steps of one group (a single warp per frame, a few us of dependent fp64) hold the tail of its sweep kernel, the
+    // other groups' sweeps keep the SMs busy, and a group whose frames need few rounds finishes early.
     const int G = solve_groups(b);
     RCLC_TRY(ensure_group_streams(ctx, G));
     b->uploads_pending = false;          // every group stream carries its own frames' uploads ahead of its kernels
@@ -1926,178 +2076,105 @@ int rclc_batch_gridfit_solve(rclc_batch* b, const double* T_bl, double* T_bl_out
         gr.nf = (int)((int64_t)F * (gi + 1) / G) - gr.f0;
         gr.st = gi == 0 ? ctx->stream : ctx->aux_streams[gi - 1];
         gr.v = slice_view(b->v, gr.f0, gr.nf, gi);
-        { static const int fl = [] { const char* e = std::getenv("RCLC_UNSAFE_NOFENCE"); return (e && e[0] == '1') ? 2 : 1; }(); gr.v.fuse_lm = fl; }
+        gr.v.fuse_lm = 1;
         gr.round = 0;
         if (gi > 0) RCLC_CUDA(cudaStreamWaitEvent(gr.st, ctx->ev_sync, 0));
         RCLC_TRY(launch_init(b, gr, d_Tbl));
     }
     // Upper bound on rounds: every outer iteration needs at most max_lm_iters+2 evaluations.
     const int64_t max_rounds = (int64_t)(g.max_iter_time + 2) * (g.max_lm_iters + 3);
-    const int rounds_per_check = 24;
-    int64_t rounds = 0;
-    // RCLC_PROFILE_ROUNDS=1: CUDA events between the move and the sweep of every round of group 0; totals on stderr
-    static const bool prof = [] { const char* e = std::getenv("RCLC_PROFILE_ROUNDS"); return e && e[0] == '1'; }();
-    static const bool lm_separate = [] { const char* e = std::getenv("RCLC_LM_SEPARATE"); return e && e[0] == '1'; }();
-    std::vector<cudaEvent_t> evs, evs_lm;
-    int active_est = F;            // frames still solving, as of the last poll: sizes the sweep's task split
-    static const int fused_mode = [] { const char* e = std::getenv("RCLC_FUSED_PARTS_MODE"); return e ? atoi(e) : 0; }();
-    int fused_frames = F;
-    // After the first batch of rounds (which holds the counting sort) every batch is the same 24 x {k_move, k_sweep} per group:
-    // captured once per batch object into a CUDA graph, which removes most of the launch gaps between these short kernels.
-    static const bool use_graphs = [] { const char* e = std::getenv("RCLC_NO_GRAPHS"); return !(e && e[0] == '1'); }() ;
-    const bool graphs_ok = use_graphs && !prof && !lm_separate && (rounds_per_check % 2 == 0);
-    if (graphs_ok && b->graphs_groups != G) {
+    // ---- first batch of rounds, launched directly: the one counting sort of the solve, then {k_move, k_sweep} ----
+    for (int r = 0; r < kRoundsPerGraph; ++r)
+        for (int gi = 0; gi < G; ++gi) {
+            GroupRun& gr = groups[gi];
+            if (r == 0) RCLC_TRY(launch_rebin(b, gr));
+            else RCLC_TRY(launch_move(b, gr));
+            RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, F));      // sweep + fused LM step (last warp per frame)
+        }
+    // ---- every later batch is the same kRoundsPerGraph x {k_move, k_sweep} per group: captured once per batch object into a CUDA
+    //      graph. From here on every group advances on its own: its graph is re-launched as soon as ITS previous batch has finished
+    //      and still left frames unsolved. No group waits for another. ----
+    static_assert(kRoundsPerGraph % 2 == 0, "a graph must leave the parity of the re-bin lists as it found it");
+    if (b->graphs_groups != G) {
         for (cudaGraphExec_t ge : b->round_graphs) cudaGraphExecDestroy(ge);
         b->round_graphs.clear();
         b->graphs_groups = 0;
     }
-    for (;;) {
-        for (int r = 0; r < rounds_per_check; ++r) {
-            for (int gi = 0; gi < G; ++gi) {
-                GroupRun& gr = groups[gi];
-                const bool pg = prof && gi == 0;
-                if (pg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, gr.st); evs.push_back(e); }
-                if (rounds == 0 && r == 0) RCLC_TRY(launch_rebin(b, gr));      // the one counting sort of the solve
-                else RCLC_TRY(launch_move(b, gr));
-                if (pg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, gr.st); evs.push_back(e); }
-                if (lm_separate) {
-                    gr.v.fuse_lm = 0;
-                    RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, active_est));
-                    if (pg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, gr.st); evs_lm.push_back(e); }
-                    k_lm<<<gr.nf, 32, 0, gr.st>>>(gr.v);
-                    ctx->launches += 1;
-                } else {
-                    RCLC_TRY(launch_sweep_view(b, gr.v, gr.nf, gr.st, fused_frames));      // sweep + fused LM step (last warp per frame)
-                }
+    if (b->round_graphs.empty()) {
+        for (int gi = 0; gi < G; ++gi) {
+            GroupRun gr = groups[gi];                   // a copy: capturing must not advance the real round counters
+            cudaGraph_t graph = nullptr;
+            RCLC_CUDA(cudaStreamBeginCapture(gr.st, cudaStreamCaptureModeThreadLocal));
+            int rc_cap = RCLC_OK;
+            for (int r = 0; r < kRoundsPerGraph && rc_cap == RCLC_OK; ++r) {
+                rc_cap = launch_move(b, gr);
+                if (rc_cap == RCLC_OK) rc_cap = launch_sweep_view(b, gr.v, gr.nf, gr.st, F);
             }
+            RCLC_CUDA(cudaStreamEndCapture(gr.st, &graph));
+            RCLC_TRY(rc_cap);
+            cudaGraphExec_t ge = nullptr;
+            RCLC_CUDA(cudaGraphInstantiate(&ge, graph, 0));
+            cudaGraphDestroy(graph);
+            b->round_graphs.push_back(ge);
+            ctx->launches -= 2 * kRoundsPerGraph;       // (counted when the graph is launched)
         }
-        rounds += rounds_per_check;
-        RCLC_CUDA(cudaGetLastError());
-        if (graphs_ok) {
-            // ---- From here on every group advances on its own: its 24-round graph is re-launched as soon as ITS previous batch has
-            //      finished and still left frames unsolved. No group waits for another (a group whose frames arrived later over
-            //      PCIe, or whose frames need more rounds, no longer holds the others back at every poll). ----
-            if (b->round_graphs.empty()) {
-                for (int gi = 0; gi < G; ++gi) {
-                    GroupRun gr = groups[gi];                   // a copy: capturing must not advance the real round counters
-                    cudaGraph_t graph = nullptr;
-                    RCLC_CUDA(cudaStreamBeginCapture(gr.st, cudaStreamCaptureModeThreadLocal));
-                    int rc_cap = RCLC_OK;
-                    for (int r = 0; r < rounds_per_check && rc_cap == RCLC_OK; ++r) {
-                        rc_cap = launch_move(b, gr);
-                        if (rc_cap == RCLC_OK) rc_cap = launch_sweep_view(b, gr.v, gr.nf, gr.st, F);
-                    }
-                    RCLC_CUDA(cudaStreamEndCapture(gr.st, &graph));
-                    RCLC_TRY(rc_cap);
-                    cudaGraphExec_t ge = nullptr;
-                    RCLC_CUDA(cudaGraphInstantiate(&ge, graph, 0));
-                    cudaGraphDestroy(graph);
-                    b->round_graphs.push_back(ge);
-                    ctx->launches -= 2 * rounds_per_check;      // (counted when the graph is launched)
-                }
-                b->graphs_groups = G;
-            }
-            while ((int)ctx->ev_groups.size() < G) {
-                cudaEvent_t e;
-                RCLC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                ctx->ev_groups.push_back(e);
-            }
-            auto poll = [&](int gi) -> int {
-                RCLC_CUDA(cudaMemcpyAsync(h_done + gi, groups[gi].v.n_done, sizeof(int), cudaMemcpyDeviceToHost, groups[gi].st));
-                RCLC_CUDA(cudaEventRecord(ctx->ev_groups[(size_t)gi], groups[gi].st));
-                return RCLC_OK;
-            };
-            for (int gi = 0; gi < G; ++gi) RCLC_TRY(poll(gi));
-            std::vector<char> finished((size_t)G, 0);
-            std::vector<int64_t> g_rounds((size_t)G, rounds);
-            int n_finished = 0;
-            while (n_finished < G) {
-                bool progressed = false;
-                for (int gi = 0; gi < G; ++gi) {
-                    if (finished[(size_t)gi]) continue;
-                    const cudaError_t q = cudaEventQuery(ctx->ev_groups[(size_t)gi]);
-                    if (q == cudaErrorNotReady) continue;
-                    RCLC_CUDA(q);
-                    progressed = true;
-                    if (h_done[gi] >= groups[gi].nf) { finished[(size_t)gi] = 1; ++n_finished; continue; }
-                    RCLC_CHECK(g_rounds[(size_t)gi] < max_rounds, RCLC_ERR_NUMERIC, "grid-fit state machine did not terminate");
-                    RCLC_CUDA(cudaGraphLaunch(b->round_graphs[(size_t)gi], groups[gi].st));
-                    groups[gi].round += rounds_per_check;
-                    g_rounds[(size_t)gi] += rounds_per_check;
-                    ctx->launches += 2 * rounds_per_check;
-                    RCLC_TRY(poll(gi));
-                }
-                if (!progressed) std::this_thread::yield();
-            }
-            for (int gi = 1; gi < G; ++gi) {                                    // ctx->stream joins the other groups
-                RCLC_CUDA(cudaEventRecord(ctx->ev_sync, groups[gi].st));
-                RCLC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
-            }
-            break;
-        }
-        for (int gi = 1; gi < G; ++gi) {                                        // lock-step path (profiling / A-B switches): ctx->stream joins the other groups
-            RCLC_CUDA(cudaEventRecord(ctx->ev_sync, groups[gi].st));
-            RCLC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
-        }
-        RCLC_CUDA(cudaMemcpyAsync(h_done, b->v.n_done, G * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
-        int done_total = 0;
-        for (int gi = 0; gi < G; ++gi) done_total += h_done[gi];
-        if (done_total >= F) break;
-        active_est = std::max(1, F - done_total);
-        if (fused_mode == 1) fused_frames = active_est;
-        RCLC_CHECK(rounds < max_rounds, RCLC_ERR_NUMERIC, "grid-fit state machine did not terminate");
+        b->graphs_groups = G;
     }
-    if (prof && evs.size() >= 4) {
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); evs.push_back(e);
-        cudaEventSynchronize(e);
-        if (evs_lm.size() * 2 + 1 == evs.size()) {
-            double t_lm = 0;
-            for (size_t i = 0; i < evs_lm.size(); ++i) { float a = 0; cudaEventElapsedTime(&a, evs_lm[i], evs[2 * i + 2]); t_lm += a; }
-            fprintf(stderr, "[rclc profile] separate k_lm launches: %.2f ms total, %.1f us each\n", t_lm, 1e3 * t_lm / evs_lm.size());
-            for (cudaEvent_t x : evs_lm) cudaEventDestroy(x);
+    while ((int)ctx->ev_groups.size() < G) {
+        cudaEvent_t e;
+        RCLC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_groups.push_back(e);
+    }
+    auto poll = [&](int gi) -> int {
+        RCLC_CUDA(cudaMemcpyAsync(h_done + gi, groups[gi].v.n_done, sizeof(int), cudaMemcpyDeviceToHost, groups[gi].st));
+        RCLC_CUDA(cudaEventRecord(ctx->ev_groups[(size_t)gi], groups[gi].st));
+        return RCLC_OK;
+    };
+    for (int gi = 0; gi < G; ++gi) RCLC_TRY(poll(gi));
+    std::vector<char> finished((size_t)G, 0);
+    std::vector<int64_t> g_rounds((size_t)G, kRoundsPerGraph);
+    int n_finished = 0;
+    while (n_finished < G) {
+        bool progressed = false;
+        for (int gi = 0; gi < G; ++gi) {
+            if (finished[(size_t)gi]) continue;
+            const cudaError_t q = cudaEventQuery(ctx->ev_groups[(size_t)gi]);
+            if (q == cudaErrorNotReady) continue;
+            RCLC_CUDA(q);
+            progressed = true;
+            if (h_done[gi] >= groups[gi].nf) { finished[(size_t)gi] = 1; ++n_finished; continue; }
+            RCLC_CHECK(g_rounds[(size_t)gi] < max_rounds, RCLC_ERR_NUMERIC, "grid-fit state machine did not terminate");
+            RCLC_CUDA(cudaGraphLaunch(b->round_graphs[(size_t)gi], groups[gi].st));
+            groups[gi].round += kRoundsPerGraph;
+            g_rounds[(size_t)gi] += kRoundsPerGraph;
+            ctx->launches += 2 * kRoundsPerGraph;
+            RCLC_TRY(poll(gi));
         }
-        double t_bin = 0, t_sweep = 0, bin_max = 0; int n_bin_big = 0;
-        std::vector<float> sw;
-        for (size_t i = 0; i + 2 < evs.size(); i += 2) {
-            float a = 0, c = 0;
-            cudaEventElapsedTime(&a, evs[i], evs[i + 1]);
-            cudaEventElapsedTime(&c, evs[i + 1], evs[i + 2]);
-            t_bin += a; t_sweep += c; bin_max = std::max<double>(bin_max, a); n_bin_big += a > 0.02f;
-            sw.push_back(c);
-        }
-        {
-            std::vector<float> q = sw; std::sort(q.begin(), q.end());
-            fprintf(stderr, "[rclc profile] sweep+lm per round: min %.1f  p25 %.1f  median %.1f  p75 %.1f  max %.1f us; first 8:", q.front() * 1e3,
-                    q[q.size() / 4] * 1e3, q[q.size() / 2] * 1e3, q[3 * q.size() / 4] * 1e3, q.back() * 1e3);
-            for (size_t i = 0; i < 8 && i < sw.size(); ++i) fprintf(stderr, " %.0f", sw[i] * 1e3);
-            fprintf(stderr, "; last 8:");
-            for (size_t i = sw.size() >= 8 ? sw.size() - 8 : 0; i < sw.size(); ++i) fprintf(stderr, " %.0f", sw[i] * 1e3);
-            fprintf(stderr, "\n");
-        }
-        float tot = 0; cudaEventElapsedTime(&tot, evs.front(), evs.back());
-        fprintf(stderr, "[rclc profile] rounds %zu  total %.2f ms  binning %.2f ms (%d rounds > 20 us, max %.1f us)  sweep+lm %.2f ms\n",
-                evs.size() / 2, tot, t_bin, n_bin_big, bin_max * 1e3, t_sweep);
-        for (cudaEvent_t x : evs) cudaEventDestroy(x);
+        if (!progressed) std::this_thread::yield();
+    }
+    for (int gi = 1; gi < G; ++gi) {                                    // ctx->stream joins the other groups
+        RCLC_CUDA(cudaEventRecord(ctx->ev_sync, groups[gi].st));
+        RCLC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
     }
     std::vector<LmState> h_lm(F);
     RCLC_CUDA(cudaMemcpyAsync(h_lm.data(), b->v.lm, sizeof(LmState) * F, cudaMemcpyDeviceToHost, ctx->stream));
     if (corners_out)
         RCLC_CUDA(cudaMemcpyAsync(corners_out, b->v.corners, (size_t)F * g.nc * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (prof) {
-        long long d[5] = {0, 0, 0, 0, 0};
-        for (int f = 0; f < F; ++f) for (int k = 0; k < 5; ++k) d[k] += h_lm[f].dbg[k];
+#ifdef RCLC_LAB
+    for (int f = 0; f < F; ++f) {
+        const long long* d = h_lm[f].dbg;
         if (d[4] > 0)
-            fprintf(stderr, "[rclc profile] lm_frame_step cycles per call: load state %lld, acc + residuals %lld, clear + warp sums %lld, lm_advance %lld (%lld calls)\n",
-                    d[0] / d[4], d[1] / d[4], d[2] / d[4], d[3] / d[4], d[4]);
+            fprintf(stderr, "[rclc lab] frame %d: %lld LM steps; per step: load %.2f us, replay %.2f us, proposals %.2f us; first -> last step %.1f us (%.1f us per round)\n",
+                    f, d[4], 1e-3 * d[0] / d[4], 1e-3 * d[1] / d[4], 1e-3 * d[2] / d[4], 1e-3 * (d[6] - d[5]),
+                    d[4] > 1 ? 1e-3 * (d[6] - d[5]) / (d[4] - 1) : 0.0);
     }
-    int rc = RCLC_OK;
+#endif
     for (int f = 0; f < F; ++f) {
         if (reports) reports[f] = h_lm[f].rep;
         if (T_bl_out) for (int k = 0; k < 16; ++k) T_bl_out[(size_t)f * 16 + k] = h_lm[f].T_bl[k];
     }
-    return rc;
+    return RCLC_OK;
 }
 
 int rclc_gridfit_eval(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n,
@@ -2167,6 +2244,7 @@ int rclc_batch_multistart(rclc_batch* b, int32_t frame, const double* poses, int
     k_ms_setup<<<(P + 127) / 128, 128, 0, ctx->stream>>>(b->v, d_ctl, d_poses, P, frame);
     v.fixed_frame = frame;
     v.fuse_lm = 0;
+    v.acc_stride = (int64_t)nt * 16;            // one pose slot per hypothesis
     // blockIdx.y is limited to 65535: sweep poses in slabs
     for (int p0 = 0; p0 < P; p0 += 32768) {
         const int np = std::min(32768, P - p0);

@@ -23,8 +23,7 @@ constexpr int kGroupRows = 4;            // rows per cp.async group (one commit 
 constexpr int kRingGroups = 4;           // groups per warp ring (8 KB): one computing, up to three in flight (8 groups, or 8-row groups, measured no faster)
 constexpr int kFlushRows = 448;          // rows a lane may accumulate before the count riding in the fp64 sum must be split off
 constexpr int kBinThreads = 256;
-constexpr int kBinP = 8;
-constexpr int kBinChunk = kBinThreads * kBinP;
+constexpr int kSpec = 8;                 // most poses one round evaluates per frame: the LM candidate and the ones that follow it if every one is rejected
 
 // Geometry derived from rclc_config on the host (gridfit.cu: build_geom).
 struct GridGeom {
@@ -52,7 +51,7 @@ struct PoseCoef {              // R = Quaternion(cos(t/2),0,0,sin(t/2)).matrix()
 enum Phase { PH_EVAL_INIT = 1, PH_EVAL_CAND = 2, PH_DONE = 3 };
 
 // Per-frame control block read by the streaming kernels.
-struct alignas(8) FrameCtl {
+struct alignas(16) FrameCtl {
     int sweep_active;          // sweep kernels process this frame
     int rebin;                 // count/scatter kernels process this frame (move + re-bin)
     int n_rows;                // 32-point rows of the current binning (cells padded to whole rows)
@@ -60,14 +59,17 @@ struct alignas(8) FrameCtl {
     int use_exact;             // some intensity is outside {0} U [2^-3, 256): counts cannot ride in the fp64 sums -> all-fp64 body
     float drift;               // bound on how far any point has moved since the frame was sorted (in-place moves)
     float move[8];             // T_w1_w0 rows 0,1: m00 m01 m02 m03 / m10 m11 m12 m13
-    PoseCoef pose;             // pose the next sweep evaluates
+    int n_pose;                // poses the next sweep evaluates (1 .. kSpec)
+    int pad_;
+    PoseCoef pose[kSpec];      // pose[0]: the point the LM needs next; pose[1..]: its successors under "every step is rejected"
 };
+static_assert(sizeof(FrameCtl) % 16 == 0, "FrameCtl is staged with 16-byte loads");
 
-// Ceres TrustRegionMinimizer state + opt_grid_fitting outer-loop state, one per frame.
-struct alignas(16) LmState {
+// Ceres TrustRegionMinimizer state of the running inner solve. Kept apart from the rest of the frame's state because the
+// LM step runs it twice: for real (lm_consume on the evaluations of a round) and on a scratch copy that is fed "rejected"
+// to predict the next candidates (speculate_candidates).
+struct LmCore {
     int phase;
-    int outer_iter;
-    int status;
     int iteration;
     int num_consecutive_invalid;
     int reuse_diagonal;
@@ -80,11 +82,27 @@ struct alignas(16) LmState {
     double scale[3], diag[3];
     double model_cost_change;
     double gmax;
+};
+
+// LmCore + opt_grid_fitting outer-loop state, one per frame.
+struct alignas(16) LmState {
+    LmCore core;
+    int outer_iter;
+    int status;
+    int chain;                 // 0: no step of the running solve has been accepted yet; 1: after the first accepted step
+    int n_rejected;            // rejections since the last accepted step (or since the start of the solve)
+    double spec[kSpec][3];     // the poses of the round in flight: spec[0] is the LM's candidate, spec[k] what follows k rejections
+    double spec_mcc[kSpec];    // model_cost_change of spec[k]
+    double spec_radius[kSpec]; // the trust-region radius and decrease factor spec[k] was computed for: the replay adopts spec[k]
+    double spec_factor[kSpec]; // only if, after k rejections, the minimiser's own are these, bit for bit
     float T_base_laser[16];
     double T_bl[16];
     rclc_gridfit_report rep;
-    long long dbg[8];          // RCLC_PROFILE_ROUNDS: SM cycles spent in the stages of lm_frame_step, summed over its calls
+#ifdef RCLC_LAB
+    long long dbg[8];          // lab build only: ns spent in the stages of lm_frame_step, summed over its calls (scripts/lm_timing.py)
+#endif
 };
+static_assert(sizeof(LmState) % 16 == 0, "LmState is staged with 16-byte loads");
 
 struct BatchView {
     GridGeom geom;
@@ -101,19 +119,23 @@ struct BatchView {
     int* cellcnt;                  // [F][ncells] points of the cell (the segment holds pad32 of it)
     float4* rowbox;                // [F][frame_stride / 32] {xmin, ymin, xmax, ymax} of every 32-point row
     unsigned* cellz2;              // [F][ncells] float bits of max z^2 over the cell's points (decides whether the neighbour mask can matter)
-    double* acc;                   // [F][nt][16]
+    double* acc;                   // [F][kSpec][nt][16] (acc_stride doubles per frame; a plain sweep uses pose slot 0)
+    int64_t acc_stride;            // doubles between the accumulator tables of two frames
+    int npose_max;                 // pose slots a sweep launch covers per frame: 1 (plain sweeps, multi-start) or kSpec (the solve)
     FrameCtl* ctl;                 // [F]
     LmState* lm;                   // [F]
     int* n_done;                   // [1]
     int* rebin_list;               // [2][F] frames that need a re-bin: the LM steps of round r fill list (r+1)&1
     int* rebin_cnt;                // [2]
     int list_parity;               // which list this round's binning kernels consume
-    double* terms;                 // [F][12][nt] per-target LM terms (cost, 6 J'J, 3 J'r, 2 flags) written by the sweep
-    int* tgt_done;                 // [F][nt] parts of a target that have flushed their accumulators
+    double* terms;                 // [F][kSpec][12][nt] per-target LM terms (cost, 6 J'J, 3 J'r, 2 flags) written by the sweep
+    int* tgt_done;                 // [F][kSpec][nt] parts of a (pose, target) that have flushed their accumulators
+    int* slot_done;                // [F][kSpec] targets of a pose slot whose terms are written (the last one sums them)
+    double* evsum;                 // [F][kSpec][12] the summed terms of every pose slot: what Ceres' evaluation returns
     int* bin_done;                 // [F] CTAs of k_count that have finished their share of the histogram
-    int* sweep_done;               // [F] CTAs of the current sweep that have finished (last one runs the LM step)
-    int fuse_lm;                   // 1: k_sweep's last CTA per frame advances the Ceres state machine
-    int force_exact;               // RCLC_SWEEP_EXACT=1
+    int* sweep_done;               // [F] pose slots of the current sweep that are summed (the last one runs the LM step)
+    int fuse_lm;                   // 1: k_sweep's last warp per frame advances the Ceres state machine
+    int force_exact;               // all-fp64 sweep body for every frame (rclc_batch_set_exact_sweep: the A/B reference of the fast body)
     // geometry tables
     const double2* tgt_xy;         // [nt]
     const float2* tgt_xyf;         // [nt] (float)target  (FLANN query point)
@@ -140,10 +162,9 @@ struct rclc_batch {
     int64_t* d_npts = nullptr;
     bool binned_valid = false;
     int round = 0;                    // parity of the re-bin list the next round consumes
-    // one instantiated CUDA graph per solve group: 24 rounds of {k_move, k_sweep} (the steady state of the solve)
+    // one instantiated CUDA graph per solve group: kRoundsPerGraph rounds of {k_move, k_sweep} (the steady state of the solve)
     std::vector<cudaGraphExec_t> round_graphs;
     int graphs_groups = 0;
-    bool sweep_exact = false;         // RCLC_SWEEP_EXACT=1: run the all-fp64 v1 sweep (debug / A-B reference)
     // GMM scratch
     double* d_gmm = nullptr;
 };

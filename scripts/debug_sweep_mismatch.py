@@ -8,8 +8,8 @@ ctx = capi.Context(0)
 frames = [synth.board_frame_cloud(150000, 900 + i, pert=(0.004 * i, -0.003 * i, 0.3 * i), pattern="rosette" if i % 2 else "raster") for i in range(4)]
 tables = {}
 for mode in ("0", "1"):
-    os.environ["RCLC_SWEEP_EXACT"] = mode
     b = capi.Batch(ctx, cfg, 4, 150000)
+    b.set_exact_sweep(mode == "1")
     for f, p in enumerate(frames): b.upload(f, p)
     b.bin()
     prng = np.random.default_rng(5); out = []

@@ -39,8 +39,9 @@ def batch20(capi, ctx, cfg):
     b.close()
 
 
-def _tables(capi, ctx, cfg, clouds, poses):
+def _tables(capi, ctx, cfg, clouds, poses, exact=False):
     b = capi.Batch(ctx, cfg, len(clouds), max(len(c) for c in clouds))
+    b.set_exact_sweep(exact)
     for f, p in enumerate(clouds):
         b.upload(f, p)
     b.bin()
@@ -71,8 +72,7 @@ def test_fast_sweep_equals_all_fp64_sweep_at_full_size(capi, ctx, cfg, batch20, 
     b, frames, perts = batch20
     b.sweep(perts)
     fast = b.read_eval(want_acc=True)[2].copy()
-    monkeypatch.setenv("RCLC_SWEEP_EXACT", "1")
-    exact = _tables(capi, ctx, cfg, frames[:6], perts[:6])
+    exact = _tables(capi, ctx, cfg, frames[:6], perts[:6], exact=True)
     assert np.array_equal(exact, fast[:6])
 
 

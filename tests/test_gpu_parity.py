@@ -418,8 +418,8 @@ def test_fast_sweep_equals_exact_sweep(capi, ctx, cfg, oracle, ocfg, monkeypatch
               for i in range(4)]
     tables = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("RCLC_SWEEP_EXACT", mode)
         b = capi.Batch(ctx, cfg, 4, 150000)
+        b.set_exact_sweep(mode == "1")
         for f, p in enumerate(frames):
             b.upload(f, p)
         b.bin()

@@ -738,18 +738,28 @@ int orc_ransac_replay(const int32_t* counts, const int32_t* valid, int H, int64_
 int orc_plane_refine(const void* pts, int stride, int64_t n, const uint8_t* mask, const float plane_in[4],
                      float plane_out[4], float centroid_out[3])
 {
-    // computeMeanAndCovarianceMatrix single pass; accumulation in double (PCL's Scalar differs by
-    // version; unpinned), normalised the same way: accu /= n; cov = E[xx'] - mean mean'.
-    double accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // computeMeanAndCovarianceMatrix single pass. PCL's accumulation type and order differ by version and are unpinned; the
+    // oracle DEFINES the nine sums as exact, order-free sums: every term (x, y, z and the products of two floats, exact in a
+    // double) is floored onto the fixed-point grid of 2^-80 and added as a 128-bit integer, the total is rounded to a double
+    // once. Normalised like PCL: accu /= n; cov = E[xx'] - mean mean'.
+    __int128 acc128[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto add = [](__int128& a, double t) {
+        const double s = t * 65536.0, fl = std::floor(s);
+        const __int128 hi = (__int128)(long long)fl;
+        const unsigned long long lo = (unsigned long long)((s - fl) * 18446744073709551616.0);
+        a += hi * ((__int128)1 << 64) + (__int128)lo;
+    };
     int64_t cnt = 0;
     for (int64_t k = 0; k < n; ++k) {
         if (!mask[k]) continue;
         const float* p = rec(pts, stride, k);
         const double x = p[0], y = p[1], z = p[2];
-        accu[0] += x * x; accu[1] += x * y; accu[2] += x * z; accu[3] += y * y; accu[4] += y * z; accu[5] += z * z;
-        accu[6] += x; accu[7] += y; accu[8] += z;
+        add(acc128[0], x * x); add(acc128[1], x * y); add(acc128[2], x * z); add(acc128[3], y * y); add(acc128[4], y * z); add(acc128[5], z * z);
+        add(acc128[6], x); add(acc128[7], y); add(acc128[8], z);
         ++cnt;
     }
+    double accu[9];
+    for (int q = 0; q < 9; ++q) accu[q] = std::ldexp((double)acc128[q], -80);
     if (cnt <= 3) { for (int q = 0; q < 4; ++q) plane_out[q] = plane_in[q]; centroid_out[0] = centroid_out[1] = centroid_out[2] = 0; return 0; }
     for (int q = 0; q < 9; ++q) accu[q] /= (double)cnt;
     double cov[9];

@@ -2,7 +2,7 @@
 //   K8 plane_project     pc_plane_prj                         include/pc_process.h:41-57
 //      transform_cloud   pcl::transformPointCloud(Matrix4f)   (called at pc_process.h:594,618; opt_grid_fitting.h:54,107; Calibrate.cpp:99,134)
 //   K7 project_colorize  colourise loop                       apps/Calibrate.cpp:134-148 + include/PinholeCam.h:93-110
-#include "common.cuh"
+#include "ops_dev.cuh"
 
 #include <climits>
 
@@ -80,6 +80,26 @@ static int download_xyz(rclc_ctx* ctx, const float4* d, void* pts, int stride, i
     return RCLC_OK;
 }
 
+int dev_plane_project(rclc_ctx* ctx, float4* d_pts, int64_t n, const double plane[4])
+{
+    if (n == 0) return RCLC_OK;
+    k_plane_project<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(d_pts, n, plane[0], plane[1], plane[2], plane[3]);
+    ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+int dev_transform(rclc_ctx* ctx, float4* d_pts, int64_t n, const float T[16])
+{
+    if (n == 0) return RCLC_OK;
+    Mat34f M;
+    for (int k = 0; k < 12; ++k) M.m[k] = T[k];
+    k_transform<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(d_pts, n, M);
+    ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
 } // namespace rclc
 
 using namespace rclc;
@@ -92,9 +112,7 @@ int rclc_plane_project(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const
     RCLC_CUDA(cudaSetDevice(ctx->device));
     RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
     RCLC_TRY(upload_cloud_f4(ctx, pts_io, stride, 12, n, ctx->d_pts.as<float4>()));
-    k_plane_project<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(ctx->d_pts.as<float4>(), n, plane[0], plane[1], plane[2], plane[3]);
-    ctx->launches += 1;
-    RCLC_CUDA(cudaGetLastError());
+    RCLC_TRY(dev_plane_project(ctx, ctx->d_pts.as<float4>(), n, plane));
     return download_xyz(ctx, ctx->d_pts.as<float4>(), pts_io, stride, n);
 }
 
@@ -104,11 +122,7 @@ int rclc_transform_cloud(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, con
     RCLC_CUDA(cudaSetDevice(ctx->device));
     RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
     RCLC_TRY(upload_cloud_f4(ctx, pts_io, stride, 12, n, ctx->d_pts.as<float4>()));
-    Mat34f M;
-    for (int k = 0; k < 12; ++k) M.m[k] = T[k];
-    k_transform<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(ctx->d_pts.as<float4>(), n, M);
-    ctx->launches += 1;
-    RCLC_CUDA(cudaGetLastError());
+    RCLC_TRY(dev_transform(ctx, ctx->d_pts.as<float4>(), n, T));
     return download_xyz(ctx, ctx->d_pts.as<float4>(), pts_io, stride, n);
 }
 

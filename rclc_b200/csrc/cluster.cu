@@ -9,7 +9,7 @@
 //     points sorted by cell, a hash table cell -> range, every point tests the points of its 27 neighbour cells with the FLANN
 //     L2_Simple distance and joins them with a lock-free union-find whose roots are the smallest member index. Sizes and the
 //     final ranking (size descending, smallest member first) follow on the few roots.
-#include "common.cuh"
+#include "ops_dev.cuh"
 
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
@@ -213,18 +213,41 @@ __global__ void __launch_bounds__(256) k_ec_roots(const float4* __restrict__ pts
 static uint32_t pow2_at_least(uint64_t v) { uint32_t c = 1024; while (c < v && c < (1u << 31)) c <<= 1; return c; }
 static int grid_for(int64_t n, int threads, int sms) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)sms * 8)); }
 
-} // namespace rclc
-
-using namespace rclc;
-
-extern "C" int rclc_uniform_sample(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double leaf_d, int32_t* idx_out, int64_t* n_out)
+// roots of components: (root index, size) pairs appended in no particular order (the host ranks them)
+__global__ void __launch_bounds__(256) k_ec_collect_roots(const int* __restrict__ size, int64_t n, int2* __restrict__ out, int* __restrict__ n_out)
 {
-    RCLC_CHECK(ctx && pts && idx_out && n_out && n > 0 && n < (1ll << 31) && leaf_d > 0, RCLC_ERR_INVALID, "bad argument");
-    RCLC_CUDA(cudaSetDevice(ctx->device));
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
+        const int sz = size[i];
+        if (sz > 0) out[atomicAdd(n_out, 1)] = make_int2((int)i, sz);
+    }
+}
+__global__ void __launch_bounds__(256) k_fill_int(int* a, int64_t n, int v) { for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) a[i] = v; }
+__global__ void __launch_bounds__(256) k_ec_set_rank(const int2* __restrict__ ranked, int n_ranked, int* __restrict__ rank_of)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < n_ranked) rank_of[ranked[k].x] = ranked[k].y;
+}
+__global__ void __launch_bounds__(256) k_ec_labels(const int* __restrict__ root, const int* __restrict__ rank_of, int64_t n, int* __restrict__ label)
+{
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) { const int r = root[i]; label[i] = r >= 0 ? rank_of[r] : -1; }
+}
+__global__ void __launch_bounds__(256) k_gather(const float4* __restrict__ src, const int* __restrict__ idx, int64_t n, float4* __restrict__ dst)
+{
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) dst[i] = src[idx[i]];
+}
+
+int dev_gather(rclc_ctx* ctx, const float4* d_src, const int* d_idx, int64_t n, float4* d_dst)
+{
+    if (n == 0) return RCLC_OK;
+    k_gather<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(d_src, d_idx, n, d_dst);
+    ctx->launches += 1;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+int dev_uniform_sample(rclc_ctx* ctx, const float4* d_pts, int64_t n, double leaf_d, const int** d_idx, int64_t* n_out)
+{
     cudaStream_t st = ctx->stream;
-    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
-    float4* d_pts = ctx->d_pts.as<float4>();
-    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, ioff, n, d_pts));
     const uint32_t cap = pow2_at_least((uint64_t)n * 2);
     // scratch: bbox | table keys | table best | out keys (x2 for the sort) | out idx (x2) | counter | cub temp
     size_t temp_bytes = 0;
@@ -247,6 +270,7 @@ extern "C" int rclc_uniform_sample(rclc_ctx* ctx, const void* pts, int stride, i
     RCLC_CUDA(cudaStreamSynchronize(st));
     auto o2f_h = [](int i) { const int v = i >= 0 ? i : i ^ 0x7fffffff; float f; std::memcpy(&f, &v, 4); return f; };
     *n_out = 0;
+    *d_idx = nullptr;
     if (o2f_h(h_bb[0]) > o2f_h(h_bb[3])) return RCLC_OK;                                     // no finite point
     UsGeom g;
     g.leaf = (float)leaf_d;
@@ -270,31 +294,28 @@ extern "C" int rclc_uniform_sample(rclc_ctx* ctx, const void* pts, int stride, i
     const int kept = h_bb[0];
     RCLC_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, d_ok, d_ok2, d_oi, d_oi2, kept, 0, 64, st));
     ctx->launches += 1;
-    RCLC_CUDA(cudaMemcpyAsync(idx_out, d_oi2, (size_t)kept * 4, cudaMemcpyDeviceToHost, st));
-    RCLC_CUDA(cudaStreamSynchronize(st));
     *n_out = kept;
+    *d_idx = d_oi2;
     return RCLC_OK;
 }
 
-extern "C" int rclc_euclidean_cluster(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double tol, int64_t min_size, int64_t max_size,
-                                      int32_t* labels_out, int32_t* n_clusters, int32_t* sizes_out)
+int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double tol, int64_t min_size, int64_t max_size, ClusterSet* out)
 {
-    RCLC_CHECK(ctx && pts && labels_out && n_clusters && n > 0 && n < (1ll << 31) && tol > 0, RCLC_ERR_INVALID, "bad argument");
-    RCLC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
-    float4* d_pts = ctx->d_pts.as<float4>();
-    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, ioff, n, d_pts));
     const uint32_t cap = pow2_at_least((uint64_t)n * 2);
     size_t temp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, (int)n, 0, 64, st);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_bb = 0, o_k = 256, o_k2 = o_k + al((size_t)n * 8), o_i = o_k2 + al((size_t)n * 8), o_i2 = o_i + al((size_t)n * 4), o_tk = o_i2 + al((size_t)n * 4),
-                 o_ts = o_tk + (size_t)cap * 8, o_par = o_ts + (size_t)cap * 4, o_size = o_par + al((size_t)n * 4), o_tmp = o_size + al((size_t)n * 4);
+                 o_ts = o_tk + (size_t)cap * 8, o_par = o_ts + (size_t)cap * 4, o_size = o_par + al((size_t)n * 4), o_lab = o_size + al((size_t)n * 4),
+                 o_tmp = o_lab + al((size_t)n * 4);
     RCLC_TRY(ctx->d_tmp.reserve(o_tmp + temp_bytes + 256));
     char* base = ctx->d_tmp.as<char>();
     int* d_bb = reinterpret_cast<int*>(base + o_bb);
+    int* d_label = reinterpret_cast<int*>(base + o_lab);
     const int sms = ctx->sm_count;
+    out->d_label = d_label;
+    out->sizes.clear();
     k_bbox_init<<<1, 32, 0, st>>>(d_bb);
     k_bbox<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, d_bb);
     ctx->launches += 2;
@@ -303,8 +324,11 @@ extern "C" int rclc_euclidean_cluster(rclc_ctx* ctx, const void* pts, int stride
     RCLC_CUDA(cudaMemcpyAsync(h_bb, d_bb, 24, cudaMemcpyDeviceToHost, st));
     RCLC_CUDA(cudaStreamSynchronize(st));
     auto o2f_h = [](int i) { const int v = i >= 0 ? i : i ^ 0x7fffffff; float f; std::memcpy(&f, &v, 4); return f; };
-    *n_clusters = 0;
-    if (o2f_h(h_bb[0]) > o2f_h(h_bb[3])) { for (int64_t i = 0; i < n; ++i) labels_out[i] = -1; return RCLC_OK; }
+    if (o2f_h(h_bb[0]) > o2f_h(h_bb[3])) {                                                    // no finite point
+        k_fill_int<<<grid_for(n, 256, sms), 256, 0, st>>>(d_label, n, -1);
+        ctx->launches += 1;
+        return RCLC_OK;
+    }
     EcGeom g;
     g.inv_cell = 1.0 / (tol * 1.0001);
     g.r2 = (float)(tol * tol);
@@ -325,24 +349,69 @@ extern "C" int rclc_euclidean_cluster(rclc_ctx* ctx, const void* pts, int stride
     RCLC_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, d_k, d_k2, d_i, d_i2, (int)n, 0, 64, st));
     RCLC_CUDA(cudaMemsetAsync(d_tk, 0xff, (size_t)cap * 8, st));
     RCLC_CUDA(cudaMemsetAsync(d_size, 0, (size_t)n * 4, st));
+    RCLC_CUDA(cudaMemsetAsync(d_bb, 0, 4, st));                 // (the bounding box is consumed: its first word becomes the root counter)
     k_ec_cells<<<grid_for(n, 256, sms), 256, 0, st>>>(d_k2, n, d_tk, d_ts, cap);
     k_iota<<<grid_for(n, 256, sms), 256, 0, st>>>(d_par, n);
     k_ec_union<<<grid_for(n, 128, sms), 128, 0, st>>>(d_pts, d_k2, d_i2, n, g, d_tk, d_ts, cap, d_par);
     k_ec_roots<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, d_par, d_size);
-    ctx->launches += 6;
+    // the roots (a few, against n points) go to the host for the ranking; the sorted keys are dead by now: their space takes the list
+    int2* d_roots = reinterpret_cast<int2*>(d_k);
+    k_ec_collect_roots<<<grid_for(n, 256, sms), 256, 0, st>>>(d_size, n, d_roots, d_bb);
+    ctx->launches += 7;
     RCLC_CUDA(cudaGetLastError());
-    // roots and sizes to the host; the ranking touches only the roots
-    int* h_root = ctx->h_pin2.as<int>();
-    int* h_size = h_root + n;
-    RCLC_CUDA(cudaMemcpyAsync(h_root, d_par, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    RCLC_CUDA(cudaMemcpyAsync(h_size, d_size, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    RCLC_CUDA(cudaMemcpyAsync(h_bb, d_bb, 4, cudaMemcpyDeviceToHost, st));
     RCLC_CUDA(cudaStreamSynchronize(st));
-    std::vector<int> roots;
-    for (int64_t i = 0; i < n; ++i) if (h_size[i] > 0 && h_size[i] >= min_size && h_size[i] <= max_size) roots.push_back((int)i);
-    std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) { return h_size[a] != h_size[b] ? h_size[a] > h_size[b] : a < b; });
-    std::vector<int> rank((size_t)n, -1);
-    for (size_t k = 0; k < roots.size(); ++k) { rank[roots[k]] = (int)k; if (sizes_out) sizes_out[k] = h_size[roots[k]]; }
-    for (int64_t i = 0; i < n; ++i) labels_out[i] = h_root[i] >= 0 ? rank[h_root[i]] : -1;
-    *n_clusters = (int32_t)roots.size();
+    const int n_roots = h_bb[0];
+    int2* h_roots = reinterpret_cast<int2*>(ctx->h_pin2.as<char>() + 64);
+    RCLC_CUDA(cudaMemcpyAsync(h_roots, d_roots, (size_t)n_roots * 8, cudaMemcpyDeviceToHost, st));
+    RCLC_CUDA(cudaStreamSynchronize(st));
+    std::vector<int2> kept;
+    for (int k = 0; k < n_roots; ++k) if (h_roots[k].y >= min_size && h_roots[k].y <= max_size) kept.push_back(h_roots[k]);
+    std::sort(kept.begin(), kept.end(), [](const int2& a, const int2& b) { return a.y != b.y ? a.y > b.y : a.x < b.x; });
+    for (size_t k = 0; k < kept.size(); ++k) { out->sizes.push_back(kept[k].y); h_roots[k] = make_int2(kept[k].x, (int)k); }
+    // rank of every root (the size array is dead: it becomes the root -> rank table), then of every point
+    k_fill_int<<<grid_for(n, 256, sms), 256, 0, st>>>(d_size, n, -1);
+    if (!kept.empty()) {
+        RCLC_CUDA(cudaMemcpyAsync(d_roots, h_roots, kept.size() * 8, cudaMemcpyHostToDevice, st));
+        k_ec_set_rank<<<(unsigned)((kept.size() + 255) / 256), 256, 0, st>>>(d_roots, (int)kept.size(), d_size);
+    }
+    k_ec_labels<<<grid_for(n, 256, sms), 256, 0, st>>>(d_par, d_size, n, d_label);
+    ctx->launches += 3;
+    RCLC_CUDA(cudaGetLastError());
+    return RCLC_OK;
+}
+
+} // namespace rclc
+
+using namespace rclc;
+
+extern "C" int rclc_uniform_sample(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double leaf_d, int32_t* idx_out, int64_t* n_out)
+{
+    RCLC_CHECK(ctx && pts && idx_out && n_out && n > 0 && n < (1ll << 31) && leaf_d > 0, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
+    float4* d_pts = ctx->d_pts.as<float4>();
+    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, ioff, n, d_pts));
+    const int* d_idx = nullptr;
+    RCLC_TRY(dev_uniform_sample(ctx, d_pts, n, leaf_d, &d_idx, n_out));
+    if (*n_out > 0) RCLC_CUDA(cudaMemcpyAsync(idx_out, d_idx, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return RCLC_OK;
+}
+
+extern "C" int rclc_euclidean_cluster(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double tol, int64_t min_size, int64_t max_size,
+                                      int32_t* labels_out, int32_t* n_clusters, int32_t* sizes_out)
+{
+    RCLC_CHECK(ctx && pts && labels_out && n_clusters && n > 0 && n < (1ll << 31) && tol > 0, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
+    float4* d_pts = ctx->d_pts.as<float4>();
+    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, ioff, n, d_pts));
+    ClusterSet cs;
+    RCLC_TRY(dev_euclidean_cluster(ctx, d_pts, n, tol, min_size, max_size, &cs));
+    RCLC_CUDA(cudaMemcpyAsync(labels_out, cs.d_label, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_clusters = (int32_t)cs.sizes.size();
+    if (sizes_out) for (size_t k = 0; k < cs.sizes.size(); ++k) sizes_out[k] = cs.sizes[k];
     return RCLC_OK;
 }

@@ -6,6 +6,7 @@
 // GMMFit.cpp:79-85 does) with warp-shuffle / block reductions. Reductions are two-stage and
 // fixed-order (per-CTA partials, last CTA folds them), so results are deterministic.
 #include "gridfit.cuh"
+#include "ops_dev.cuh"
 
 namespace rclc {
 
@@ -164,6 +165,19 @@ static int gmm_solve(rclc_ctx* ctx, const float* d_x, int64_t frame_stride, int 
             if (priors_out) priors_out[2 * f + k] = h[f].prior[k];
         }
     return RCLC_OK;
+}
+
+int dev_gmm_fit(rclc_ctx* ctx, const float* d_x, int elem_stride, int64_t n, int iters, double* mu_io, double* sigma_io, double* priors_out)
+{
+    // the point count lives next to the solver state (gmm_solve reserves d_out first; the count goes behind everything it uses)
+    const size_t o_n = sizeof(GmmState) + 256 + (size_t)kGmmMaxCtas * 4 * 8 + 512;
+    RCLC_TRY(ctx->d_out.reserve(o_n + 64));
+    RCLC_TRY(ctx->h_pin2.reserve(64));
+    int64_t* h_n = ctx->h_pin2.as<int64_t>();
+    *h_n = n;
+    int64_t* d_n = reinterpret_cast<int64_t*>(ctx->d_out.as<char>() + o_n);
+    RCLC_CUDA(cudaMemcpyAsync(d_n, h_n, 8, cudaMemcpyHostToDevice, ctx->stream));
+    return gmm_solve(ctx, d_x, 0, elem_stride, d_n, 1, n, iters, mu_io, sigma_io, priors_out);
 }
 
 } // namespace rclc

@@ -8,7 +8,7 @@
 // the 4x4 normal equations J'J / J'r, and the last CTA of that pass runs Ceres' trust-region step (the same accept /
 // reject / radius schedule as the grid fit, restated for 4 parameters). The step is solved by Cholesky on the normal
 // equations instead of QR on the stacked Jacobian: the same minimiser of the same damped quadratic.
-#include "common.cuh"
+#include "ops_dev.cuh"
 
 #include <cfloat>
 
@@ -245,17 +245,8 @@ __global__ void k_plane_init(PlaneLm* st)
     *st = s;
 }
 
-} // namespace rclc
-
-using namespace rclc;
-
-extern "C" int rclc_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
-                              int32_t* iterations, int64_t* n_used)
+int dev_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_pts, int64_t n, double plane_out[4], int32_t* iterations, int64_t* n_used)
 {
-    RCLC_CHECK(ctx && cfg && pts && plane_out && n > 0, RCLC_ERR_INVALID, "bad argument");
-    RCLC_CUDA(cudaSetDevice(ctx->device));
-    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
-    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, ioff, n, ctx->d_pts.as<float4>()));
     const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPfThreads * 4 - 1) / (kPfThreads * 4), kPfMaxCtas));
     RCLC_TRY(ctx->d_tmp.reserve(sizeof(PlaneLm) + 256 + (size_t)kPfMaxCtas * (kPfTerms + 1) * 8));
     PlaneLm* d_st = ctx->d_tmp.as<PlaneLm>();
@@ -271,8 +262,7 @@ extern "C" int rclc_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const void*
     int launched = 0;
     for (;;) {
         for (int r = 0; r < 8; ++r) {
-            k_plane_eval<<<ctas, kPfThreads, 0, ctx->stream>>>(ctx->d_pts.as<float4>(), n, 0.f, cfg->plane_reflactive_thd, cfg->plane_huber_a, ftol,
-                                                               max_iters, d_st, d_part);
+            k_plane_eval<<<ctas, kPfThreads, 0, ctx->stream>>>(d_pts, n, 0.f, cfg->plane_reflactive_thd, cfg->plane_huber_a, ftol, max_iters, d_st, d_part);
             ctx->launches += 1;
         }
         launched += 8;
@@ -288,4 +278,18 @@ extern "C" int rclc_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const void*
     if (iterations) *iterations = h->num_iterations;
     if (n_used) *n_used = h->n_used;
     return h->termination == 2 ? RCLC_ERR_NUMERIC : RCLC_OK;
+}
+
+} // namespace rclc
+
+using namespace rclc;
+
+extern "C" int rclc_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
+                              int32_t* iterations, int64_t* n_used)
+{
+    RCLC_CHECK(ctx && cfg && pts && plane_out && n > 0, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
+    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, ioff, n, ctx->d_pts.as<float4>()));
+    return dev_plane_fit(ctx, cfg, ctx->d_pts.as<float4>(), n, plane_out, iterations, n_used);
 }

@@ -9,7 +9,7 @@
 //
 // Everything that decides an inlier is float arithmetic in PCL's (Eigen SSE2) association order with
 // no FMA contraction, so masks and counts are bit-exact for a given hypothesis set.
-#include "common.cuh"
+#include "ops_dev.cuh"
 
 #include <cmath>
 
@@ -70,32 +70,78 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const float4* __restric
     }
 }
 
-// selectWithinDistance mask + first/second moments of the inliers (double), per-CTA partials
+// selectWithinDistance mask + first/second moments of the inliers, per-CTA partials.
+// The moments are EXACT, order-free sums: every term (x, y, z and the products of two floats, which a double holds exactly) is
+// put on the fixed-point grid of 2^-80 (floor; nothing is lost for coordinates of 8 um and more, and what is lost below is lost
+// the same way for every order of the points) and added as a 128-bit integer. The CPU checker of the tests defines the sums the
+// same way, so the refined plane and the re-selected mask agree with it bit for bit — the reference's own accumulation order
+// (PCL's computeMeanAndCovarianceMatrix) is unpinned.
 constexpr int kSelThreads = 256;
-__global__ void __launch_bounds__(kSelThreads) k_select(const float4* __restrict__ pts, int64_t n, float4 pl, float thr_le,
-                                                        uint8_t* __restrict__ mask, double* __restrict__ partials /* [grid][10] */)
+constexpr int kSelTerms = 9;            // xx xy xz yy yz zz x y z
+
+struct Fix128 { long long hi; unsigned long long lo; };          // value = (hi * 2^64 + lo) * 2^-80
+
+__device__ __forceinline__ void fix128_add_double(Fix128& a, double t)
 {
-    double a[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const double s = t * 65536.0;                                 // exact
+    const long long hi = __double2ll_rd(s);                       // floor(t * 2^16): |t| < 2^47
+    const double r = s - floor(s);                                // [0, 1), exact
+    const unsigned long long lo = __double2ull_rz(r * 18446744073709551616.0);
+    const unsigned long long nl = a.lo + lo;
+    a.hi += hi + (nl < lo ? 1 : 0);
+    a.lo = nl;
+}
+__device__ __forceinline__ void fix128_add(Fix128& a, long long hi, unsigned long long lo)
+{
+    const unsigned long long nl = a.lo + lo;
+    a.hi += hi + (nl < lo ? 1 : 0);
+    a.lo = nl;
+}
+
+__global__ void __launch_bounds__(kSelThreads) k_select(const float4* __restrict__ pts, int64_t n, float4 pl, float thr_le,
+                                                        uint8_t* __restrict__ mask, unsigned long long* __restrict__ partials /* [grid][2 * kSelTerms + 1] */)
+{
+    Fix128 a[kSelTerms];
+#pragma unroll
+    for (int k = 0; k < kSelTerms; ++k) { a[k].hi = 0; a[k].lo = 0; }
+    unsigned long long cnt = 0;
     for (int64_t i = blockIdx.x * (int64_t)kSelThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kSelThreads) {
         const float4 q = __ldg(pts + i);
         const bool in = fabsf(plane_dot(pl.x, pl.y, pl.z, pl.w, q.x, q.y, q.z)) <= thr_le;
         mask[i] = in ? 1 : 0;
         if (in) {
             const double x = q.x, y = q.y, z = q.z;
-            a[0] += x * x; a[1] += x * y; a[2] += x * z; a[3] += y * y; a[4] += y * z; a[5] += z * z;
-            a[6] += x; a[7] += y; a[8] += z; a[9] += 1.0;
+            fix128_add_double(a[0], __dmul_rn(x, x)); fix128_add_double(a[1], __dmul_rn(x, y)); fix128_add_double(a[2], __dmul_rn(x, z));
+            fix128_add_double(a[3], __dmul_rn(y, y)); fix128_add_double(a[4], __dmul_rn(y, z)); fix128_add_double(a[5], __dmul_rn(z, z));
+            fix128_add_double(a[6], x); fix128_add_double(a[7], y); fix128_add_double(a[8], z);
+            ++cnt;
         }
     }
-    __shared__ double s_red[kSelThreads / 32][10];
+    __shared__ unsigned long long s_red[kSelThreads / 32][2 * kSelTerms + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < 10; ++k) a[k] = warp_sum(a[k]);
-    if (lane == 0) for (int k = 0; k < 10; ++k) s_red[warp][k] = a[k];
+    for (int k = 0; k < kSelTerms; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            fix128_add(a[k], __shfl_xor_sync(0xffffffffu, a[k].hi, o), __shfl_xor_sync(0xffffffffu, a[k].lo, o));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+        for (int k = 0; k < kSelTerms; ++k) { s_red[warp][2 * k] = (unsigned long long)a[k].hi; s_red[warp][2 * k + 1] = a[k].lo; }
+        s_red[warp][2 * kSelTerms] = cnt;
+    }
     __syncthreads();
-    if (threadIdx.x < 10) {
-        double t = 0;
-        for (int w = 0; w < kSelThreads / 32; ++w) t += s_red[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * 10 + threadIdx.x] = t;
+    if (threadIdx.x < kSelTerms) {
+        Fix128 t;
+        t.hi = 0; t.lo = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) fix128_add(t, (long long)s_red[w][2 * threadIdx.x], s_red[w][2 * threadIdx.x + 1]);
+        partials[(size_t)blockIdx.x * (2 * kSelTerms + 1) + 2 * threadIdx.x] = (unsigned long long)t.hi;
+        partials[(size_t)blockIdx.x * (2 * kSelTerms + 1) + 2 * threadIdx.x + 1] = t.lo;
+    }
+    if (threadIdx.x == kSelTerms) {
+        unsigned long long c = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) c += s_red[w][2 * kSelTerms];
+        partials[(size_t)blockIdx.x * (2 * kSelTerms + 1) + 2 * kSelTerms] = c;
     }
 }
 
@@ -130,20 +176,9 @@ static void smallest_eigvec3(const double cov[9], double ev[3])
     for (int k = 0; k < 3; ++k) ev[k] = v[k][best];
 }
 
-} // namespace rclc
-
-using namespace rclc;
-
-extern "C" {
-
-int rclc_ransac_plane_score(rclc_ctx* ctx, const void* pts, int stride, int64_t n, const int32_t* triplets, int32_t H,
-                            double thr, float* planes_out, int32_t* valid_out, int32_t* counts_out)
+int dev_ransac_score(rclc_ctx* ctx, const float4* d_pts, int64_t n, const int32_t* triplets, int32_t H, double thr, float* planes_out,
+                     int32_t* valid_out, int32_t* counts_out)
 {
-    RCLC_CHECK(ctx && pts && triplets && counts_out && n > 0 && H > 0 && stride >= 16, RCLC_ERR_INVALID, "bad argument");
-    for (int k = 0; k < 3 * H; ++k) RCLC_CHECK(triplets[k] >= 0 && triplets[k] < n, RCLC_ERR_INVALID, "triplet index out of range");
-    RCLC_CUDA(cudaSetDevice(ctx->device));
-    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
-    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, 12, n, ctx->d_pts.as<float4>()));
     const size_t o_pl = ((size_t)H * 12 + 255) & ~(size_t)255, o_va = o_pl + (((size_t)H * 16 + 255) & ~(size_t)255);
     const size_t o_cn = o_va + (((size_t)H * 4 + 255) & ~(size_t)255), total = o_cn + (size_t)H * 4;
     RCLC_TRY(ctx->d_tmp.reserve(total));
@@ -154,9 +189,8 @@ int rclc_ransac_plane_score(rclc_ctx* ctx, const void* pts, int stride, int64_t 
     int* d_counts = reinterpret_cast<int*>(base + o_cn);
     RCLC_CUDA(cudaMemcpyAsync(d_trip, triplets, (size_t)H * 12, cudaMemcpyHostToDevice, ctx->stream));
     RCLC_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)H * 4, ctx->stream));
-    k_planes<<<(H + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pts.as<float4>(), d_trip, H, d_planes, d_valid);
-    k_score<<<(unsigned)((n + kScoreTile - 1) / kScoreTile), kScoreThreads, 0, ctx->stream>>>(ctx->d_pts.as<float4>(), n, d_planes, d_valid, H,
-                                                                                             threshold_le(thr), d_counts);
+    k_planes<<<(H + 127) / 128, 128, 0, ctx->stream>>>(d_pts, d_trip, H, d_planes, d_valid);
+    k_score<<<(unsigned)((n + kScoreTile - 1) / kScoreTile), kScoreThreads, 0, ctx->stream>>>(d_pts, n, d_planes, d_valid, H, threshold_le(thr), d_counts);
     ctx->launches += 2;
     RCLC_CUDA(cudaGetLastError());
     if (planes_out) RCLC_CUDA(cudaMemcpyAsync(planes_out, d_planes, (size_t)H * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -166,29 +200,33 @@ int rclc_ransac_plane_score(rclc_ctx* ctx, const void* pts, int stride, int64_t 
     return RCLC_OK;
 }
 
-int rclc_ransac_plane_select(rclc_ctx* ctx, const void* pts, int stride, int64_t n, const float plane[4], double thr,
-                             uint8_t* mask_out, float refined_out[4], float centroid_out[3], int64_t* n_inliers)
+int dev_ransac_select(rclc_ctx* ctx, const float4* d_pts, int64_t n, const float plane[4], double thr, const uint8_t** d_mask_out, float refined_out[4],
+                      float centroid_out[3], int64_t* n_inliers)
 {
-    RCLC_CHECK(ctx && pts && plane && mask_out && n > 0 && stride >= 16, RCLC_ERR_INVALID, "bad argument");
-    RCLC_CUDA(cudaSetDevice(ctx->device));
-    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
-    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, 12, n, ctx->d_pts.as<float4>()));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + kSelThreads * 4 - 1) / (kSelThreads * 4), (int64_t)ctx->sm_count * 4));
+    constexpr int kW = 2 * kSelTerms + 1;
     const size_t o_part = ((size_t)n + 255) & ~(size_t)255;
-    RCLC_TRY(ctx->d_tmp.reserve(o_part + (size_t)grid * 80));
+    RCLC_TRY(ctx->d_tmp.reserve(o_part + (size_t)grid * kW * 8));
     uint8_t* d_mask = ctx->d_tmp.as<uint8_t>();
-    double* d_part = reinterpret_cast<double*>(static_cast<char*>(ctx->d_tmp.p) + o_part);
-    k_select<<<grid, kSelThreads, 0, ctx->stream>>>(ctx->d_pts.as<float4>(), n, make_float4(plane[0], plane[1], plane[2], plane[3]),
-                                                   threshold_le(thr), d_mask, d_part);
+    unsigned long long* d_part = reinterpret_cast<unsigned long long*>(static_cast<char*>(ctx->d_tmp.p) + o_part);
+    k_select<<<grid, kSelThreads, 0, ctx->stream>>>(d_pts, n, make_float4(plane[0], plane[1], plane[2], plane[3]), threshold_le(thr), d_mask, d_part);
     ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
-    std::vector<double> part((size_t)grid * 10);
-    RCLC_CUDA(cudaMemcpyAsync(mask_out, d_mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    RCLC_CUDA(cudaMemcpyAsync(part.data(), d_part, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_mask_out) *d_mask_out = d_mask;
+    RCLC_TRY(ctx->h_pin2.reserve((size_t)grid * kW * 8));
+    unsigned long long* part = ctx->h_pin2.as<unsigned long long>();
+    RCLC_CUDA(cudaMemcpyAsync(part, d_part, (size_t)grid * kW * 8, cudaMemcpyDeviceToHost, ctx->stream));
     RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
-    double accu[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int c = 0; c < grid; ++c) for (int k = 0; k < 10; ++k) accu[k] += part[(size_t)c * 10 + k];
-    const int64_t cnt = (int64_t)accu[9];
+    // fold the 128-bit partial sums (integer addition: any order) and put them back on the double grid, rounded to nearest once
+    double accu[9];
+    int64_t cnt = 0;
+    for (int k = 0; k < kSelTerms; ++k) {
+        __int128 t = 0;
+        for (int c = 0; c < grid; ++c)
+            t += (__int128)(((unsigned __int128)part[(size_t)c * kW + 2 * k] << 64) | (unsigned __int128)part[(size_t)c * kW + 2 * k + 1]);
+        accu[k] = std::ldexp((double)t, -80);
+    }
+    for (int c = 0; c < grid; ++c) cnt += (int64_t)part[(size_t)c * kW + 2 * kSelTerms];
     if (n_inliers) *n_inliers = cnt;
     if (refined_out) {
         // optimizeModelCoefficients (sac_model_plane.hpp): needs more than 3 inliers
@@ -211,6 +249,37 @@ int rclc_ransac_plane_select(rclc_ctx* ctx, const void* pts, int stride, int64_t
             if (centroid_out) { centroid_out[0] = m0; centroid_out[1] = m1; centroid_out[2] = m2; }
         }
     }
+    return RCLC_OK;
+}
+
+} // namespace rclc
+
+using namespace rclc;
+
+extern "C" {
+
+int rclc_ransac_plane_score(rclc_ctx* ctx, const void* pts, int stride, int64_t n, const int32_t* triplets, int32_t H,
+                            double thr, float* planes_out, int32_t* valid_out, int32_t* counts_out)
+{
+    RCLC_CHECK(ctx && pts && triplets && counts_out && n > 0 && H > 0 && stride >= 16, RCLC_ERR_INVALID, "bad argument");
+    for (int k = 0; k < 3 * H; ++k) RCLC_CHECK(triplets[k] >= 0 && triplets[k] < n, RCLC_ERR_INVALID, "triplet index out of range");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
+    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, 12, n, ctx->d_pts.as<float4>()));
+    return dev_ransac_score(ctx, ctx->d_pts.as<float4>(), n, triplets, H, thr, planes_out, valid_out, counts_out);
+}
+
+int rclc_ransac_plane_select(rclc_ctx* ctx, const void* pts, int stride, int64_t n, const float plane[4], double thr,
+                             uint8_t* mask_out, float refined_out[4], float centroid_out[3], int64_t* n_inliers)
+{
+    RCLC_CHECK(ctx && pts && plane && mask_out && n > 0 && stride >= 16, RCLC_ERR_INVALID, "bad argument");
+    RCLC_CUDA(cudaSetDevice(ctx->device));
+    RCLC_TRY(ctx->d_pts.reserve((size_t)n * 16));
+    RCLC_TRY(upload_cloud_f4(ctx, pts, stride, 12, n, ctx->d_pts.as<float4>()));
+    const uint8_t* d_mask = nullptr;
+    RCLC_TRY(dev_ransac_select(ctx, ctx->d_pts.as<float4>(), n, plane, thr, &d_mask, refined_out, centroid_out, n_inliers));
+    RCLC_CUDA(cudaMemcpyAsync(mask_out, d_mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
     return RCLC_OK;
 }
 

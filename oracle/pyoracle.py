@@ -214,3 +214,28 @@ def calc_laser_coor(cfg, centroids, plane):
     cen = np.ascontiguousarray(centroids, np.float64); pl = np.ascontiguousarray(plane, np.float64); T = np.zeros(16)
     rc = lib().orc_calc_laser_coor(C.byref(cfg), _p(cen), C.c_int32(len(cen)), _p(pl), _p(T))
     return rc, T.reshape(4, 4)
+
+
+def segment_board(cfg, raw, x_min=3.0, x_max=6.0):
+    """apps/BoardSegmentation.cpp:45-165 on one raw scan: (rc, board cloud [m, 4] = white cluster then black cluster)."""
+    raw, stride, ioff = _cloud(raw)
+    out = np.zeros((len(raw), 4), np.float32); n = C.c_int64()
+    rc = lib().orc_segment_board(C.byref(cfg), _p(raw), stride, ioff, C.c_int64(len(raw)), C.c_double(x_min), C.c_double(x_max), _p(out), C.byref(n))
+    return rc, out[:n.value].copy()
+
+
+def est_board_corner(cfg, board):
+    """include/pc_process.h:583-646 on one board-only cloud in the T_base'd laser frame: (rc, corners [(W-1)*(H-1), 3], report,
+    the cloud as the reference leaves it: projected and moved into the board frame)."""
+    pts = np.ascontiguousarray(board, np.float32).copy()
+    assert pts.ndim == 2 and pts.shape[1] == 4
+    corners = np.zeros(((cfg.board_width - 1) * (cfg.board_height - 1), 3)); rep = GridfitReport()
+    rc = lib().orc_est_board_corner(C.byref(cfg), _p(pts), C.c_int64(len(pts)), _p(corners), C.byref(rep))
+    return rc, corners, rep, pts
+
+
+def eular_cluster_iter(cfg, pts, thd):
+    pts, stride, ioff = _cloud(pts)
+    cen = np.zeros((cfg.board_width * cfg.board_height, 3)); n = C.c_int32()
+    rc = lib().orc_eular_cluster_iter(C.byref(cfg), _p(pts), stride, ioff, C.c_int64(len(pts)), C.c_double(thd), _p(cen), C.byref(n))
+    return rc, cen[:n.value].copy()

@@ -735,6 +735,21 @@ int orc_ransac_replay(const int32_t* counts, const int32_t* valid, int H, int64_
     return 0;
 }
 
+// Exact, order-free sum: terms floored onto the fixed-point grid of 2^-80, added as 128-bit integers, rounded to a double once.
+namespace {
+struct ExactSum {
+    __int128 v = 0;
+    void add(double t)
+    {
+        const double s = t * 65536.0, fl = std::floor(s);
+        const __int128 hi = (__int128)(long long)fl;
+        const unsigned long long lo = (unsigned long long)((s - fl) * 18446744073709551616.0);
+        v += hi * ((__int128)1 << 64) + (__int128)lo;
+    }
+    double value() const { return std::ldexp((double)v, -80); }       // int128 -> double: to nearest even
+};
+} // namespace
+
 int orc_plane_refine(const void* pts, int stride, int64_t n, const uint8_t* mask, const float plane_in[4],
                      float plane_out[4], float centroid_out[3])
 {
@@ -742,13 +757,8 @@ int orc_plane_refine(const void* pts, int stride, int64_t n, const uint8_t* mask
     // oracle DEFINES the nine sums as exact, order-free sums: every term (x, y, z and the products of two floats, exact in a
     // double) is floored onto the fixed-point grid of 2^-80 and added as a 128-bit integer, the total is rounded to a double
     // once. Normalised like PCL: accu /= n; cov = E[xx'] - mean mean'.
-    __int128 acc128[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    auto add = [](__int128& a, double t) {
-        const double s = t * 65536.0, fl = std::floor(s);
-        const __int128 hi = (__int128)(long long)fl;
-        const unsigned long long lo = (unsigned long long)((s - fl) * 18446744073709551616.0);
-        a += hi * ((__int128)1 << 64) + (__int128)lo;
-    };
+    ExactSum acc128[9];
+    auto add = [](ExactSum& a, double t) { a.add(t); };
     int64_t cnt = 0;
     for (int64_t k = 0; k < n; ++k) {
         if (!mask[k]) continue;
@@ -759,7 +769,7 @@ int orc_plane_refine(const void* pts, int stride, int64_t n, const uint8_t* mask
         ++cnt;
     }
     double accu[9];
-    for (int q = 0; q < 9; ++q) accu[q] = std::ldexp((double)acc128[q], -80);
+    for (int q = 0; q < 9; ++q) accu[q] = acc128[q].value();
     if (cnt <= 3) { for (int q = 0; q < 4; ++q) plane_out[q] = plane_in[q]; centroid_out[0] = centroid_out[1] = centroid_out[2] = 0; return 0; }
     for (int q = 0; q < 9; ++q) accu[q] /= (double)cnt;
     double cov[9];
@@ -894,6 +904,16 @@ int orc_R_to_euler(const double R[9], double rpy[3])
 int orc_inverse4(const double T[16], double Tinv[16]) { return inverse4(T, Tinv) ? 0 : 1; }
 
 // include/opt/opt_plane_param.hpp:24-88
+// pc_plane_fitting (include/opt/opt_plane_param.hpp:45-88): PLANE_FITTING_COST (:24-43) through AutoDiff, one HuberLoss(0.1) per
+// point, ceres::Solve with DENSE_QR and otherwise default options, from (0.1, 0.1, 1, 1).
+//
+// The trust-region loop is ceres_lm.hpp's (same control flow, same tests), restated here for this one problem with a DEFINED
+// arithmetic: Ceres' DENSE_QR is Eigen's Householder QR on the stacked (m + 4) x 4 Jacobian, whose operation order is not pinned
+// by the reference (no Ceres / Eigen version), and any reordering of those m-term dot products moves the solution in its last
+// bits — which is enough to change float coordinates after pc_plane_prj and fork the grid fit downstream
+// (tests/test_chain_sensitivity.py). So the oracle defines the sums over the points (cost, J'J, J'r) as exact, order-free sums of
+// once-rounded terms and takes the step from the 4x4 damped normal equations by Cholesky: the same minimiser of the same
+// quadratic model, reproducible bit for bit by any implementation, in any summation order.
 int orc_plane_fit(const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
                   int32_t* iterations, int64_t* n_used)
 {
@@ -903,45 +923,156 @@ int orc_plane_fit(const rclc_config* cfg, const void* pts, int stride, int ioff,
         const float* p = rec(pts, stride, k);
         xyz.push_back(p[0]); xyz.push_back(p[1]); xyz.push_back(p[2]);
     }
-    const int m = (int)(xyz.size() / 3);
+    const int64_t m = (int64_t)(xyz.size() / 3);
     if (n_used) *n_used = m;
-    double abcd[4] = {0.1, 0.1, 1, 1};                                                    // :49
     const double huber_a = cfg->plane_huber_a;
-    orc::LMProblem P;
-    P.m = m; P.n = 4; P.nl = 4;
-    P.evaluate = [&](const double* x, double* cost, double* r, double* j) {
-        double total = 0;
+    struct Eval { double cost, A[10], g[4]; bool valid; };
+    // cost, J'J (upper triangle, row-major) and J'r at x; false on evaluation failure
+    auto evaluate = [&](const double* x) {
+        Eval ev;
+        ExactSum acc[15];
         const double a = x[0], b = x[1], c = x[2], d = x[3];
-        const double nn = a * a + b * b + c * c;
-        const double nrm = std::sqrt(nn);
-        for (int i = 0; i < m; ++i) {
+        const double nn = (a * a + b * b) + c * c;
+        const double nrm = std::sqrt(nn), den = nn * nrm;
+        const double hb = huber_a * huber_a;
+        bool bad = false;
+        for (int64_t i = 0; i < m; ++i) {
             const double X = xyz[3 * i], Y = xyz[3 * i + 1], Z = xyz[3 * i + 2];
-            const double e = a * X + b * Y + c * Z + d;
-            double rr = std::fabs(e) / nrm;                                               // :35-38
-            double j4[4];
-            if (j) {
-                // Jet: d|e| = sign(e) de ; d(1/nrm) = -(a,b,c)/nrm^3
-                const double sg = (e < 0) ? -1.0 : 1.0;   // ceres abs(Jet): f.a < 0 ? -f : f
-                const double ae = std::fabs(e);
-                j4[0] = (sg * X) / nrm - ae * a / (nn * nrm);
-                j4[1] = (sg * Y) / nrm - ae * b / (nn * nrm);
-                j4[2] = (sg * Z) / nrm - ae * c / (nn * nrm);
-                j4[3] = sg / nrm;
-            }
-            if (!std::isfinite(rr)) return false;
-            total += orc::apply_loss_1d(huber_a, &rr, j ? j4 : nullptr, 4);
-            if (r) r[i] = rr;
-            if (j) for (int q = 0; q < 4; ++q) j[i * 4 + q] = j4[q];
+            const double e = ((a * X + b * Y) + c * Z) + d;
+            const double ae = std::fabs(e);
+            double r = ae / nrm;                                                          // :35-38
+            const double sg = (e < 0) ? -1.0 : 1.0;                                       // ceres abs(Jet): f.a < 0 ? -f : f
+            // Jet: d|e| = sign(e) de ; d(1/nrm) = -(a,b,c)/nrm^3
+            double j[4] = {(sg * X) / nrm - (ae * a) / den, (sg * Y) / nrm - (ae * b) / den, (sg * Z) / nrm - (ae * c) / den, sg / nrm};
+            // IsEvaluationValid: non-finite residual or Jacobian; entries beyond 2^13 would leave the range of the exact sums and
+            // count as that too (a collapsed normal, never a fit of real coordinates)
+            if (!(std::fabs(r) < 8192.0 && std::fabs(j[0]) < 8192.0 && std::fabs(j[1]) < 8192.0 && std::fabs(j[2]) < 8192.0 && std::fabs(j[3]) < 8192.0)) { bad = true; continue; }
+            // HuberLoss::Evaluate + Corrector (rho'' <= 0: the scaling branch), as orc::apply_loss_1d
+            const double sq = r * r;
+            double rho0, rho1;
+            if (sq > hb) { const double rr = std::sqrt(sq); rho0 = (2.0 * huber_a) * rr - hb; rho1 = std::max(DBL_MIN, huber_a / rr); }
+            else { rho0 = sq; rho1 = 1.0; }
+            const double w = std::sqrt(rho1);
+            r = r * w;
+            for (int k = 0; k < 4; ++k) j[k] = j[k] * w;
+            acc[0].add(0.5 * rho0);
+            int q = 1;
+            for (int u = 0; u < 4; ++u) for (int v = u; v < 4; ++v) acc[q++].add(j[u] * j[v]);
+            for (int u = 0; u < 4; ++u) acc[11 + u].add(j[u] * r);
         }
-        *cost = total;
-        return true;
+        ev.cost = acc[0].value();
+        for (int k = 0; k < 10; ++k) ev.A[k] = acc[1 + k].value();
+        for (int k = 0; k < 4; ++k) ev.g[k] = acc[11 + k].value();
+        ev.valid = !bad;
+        return ev;
     };
-    orc::LMOptions opt;                     // :75-77: DENSE_QR, everything else Ceres defaults (50 its, ftol 1e-6)
-    opt.linear_solver = orc::DENSE_QR;
-    const orc::LMSummary sum = orc::lm_minimize(P, opt, abcd);
-    for (int q = 0; q < 4; ++q) plane_out[q] = abcd[q];
-    if (iterations) *iterations = sum.num_iterations;
-    return sum.termination == orc::FAILURE ? 1 : 0;
+    auto norm4 = [](const double* v) { return std::sqrt(((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]) + v[3] * v[3]); };
+    // (A + diag(l^2)) y = b by Cholesky; A: upper triangle, row-major
+    auto chol4 = [](const double* A10, const double* l, const double* b, double* y) {
+        double M[4][4], L[4][4] = {{0}};
+        int q = 0;
+        for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { M[i][j] = A10[q]; M[j][i] = A10[q]; ++q; }
+        for (int i = 0; i < 4; ++i) M[i][i] = M[i][i] + l[i] * l[i];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double s = M[i][j];
+                for (int k = 0; k < j; ++k) s = s - L[i][k] * L[j][k];
+                if (i == j) { if (!(s > 0.0)) return false; L[i][i] = std::sqrt(s); }
+                else L[i][j] = s / L[j][j];
+            }
+        double z[4];
+        for (int i = 0; i < 4; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s = s - L[i][k] * z[k]; z[i] = s / L[i][i]; }
+        for (int i = 3; i >= 0; --i) { double s = z[i]; for (int k = i + 1; k < 4; ++k) s = s - L[k][i] * y[k]; y[i] = s / L[i][i]; }
+        return std::isfinite(y[0]) && std::isfinite(y[1]) && std::isfinite(y[2]) && std::isfinite(y[3]);
+    };
+    const int diag_idx[4] = {0, 4, 7, 9};
+    const orc::LMOptions opt;                      // :75-77 set only DENSE_QR: 50 iterations, function_tolerance 1e-6, defaults
+    double x[4] = {0.1, 0.1, 1, 1}, best[4] = {0.1, 0.1, 1, 1}, cand[4];                  // :49
+    double A[10], g[4], scale[4], diag[4], x_cost = 0, gmax = 0;
+    auto take = [&](const Eval& ev) {
+        x_cost = ev.cost;
+        for (int k = 0; k < 10; ++k) A[k] = ev.A[k];
+        gmax = 0;
+        for (int k = 0; k < 4; ++k) { g[k] = ev.g[k]; gmax = std::max(gmax, std::fabs(x[k] - (x[k] + (-ev.g[k])))); }
+    };
+    int num_iterations = 0, termination = orc::NO_CONVERGENCE;
+    for (int k = 0; k < 4; ++k) plane_out[k] = x[k];
+    {
+        const Eval e0 = evaluate(x);
+        if (!e0.valid) { if (iterations) *iterations = 0; return 1; }
+        take(e0);
+        for (int k = 0; k < 4; ++k) scale[k] = 1.0 / (1.0 + std::sqrt(e0.A[diag_idx[k]]));      // Jacobi scaling, once
+    }
+    double x_norm = norm4(x), radius = opt.initial_trust_region_radius, decrease_factor = 2.0, minimum_cost = DBL_MAX;
+    bool reuse_diagonal = false, step_is_successful = true;
+    int iteration = 0, num_consecutive_invalid = 0;
+    for (;;) {
+        if (step_is_successful && x_cost < minimum_cost) { minimum_cost = x_cost; for (int k = 0; k < 4; ++k) best[k] = x[k]; }
+        num_iterations++;
+        if (iteration >= opt.max_num_iterations) { termination = orc::NO_CONVERGENCE; break; }
+        if (step_is_successful && gmax <= opt.gradient_tolerance) { termination = orc::CONVERGENCE; break; }
+        if (radius <= opt.min_trust_region_radius) { termination = orc::CONVERGENCE; break; }
+        iteration++;
+        step_is_successful = false;
+        double As[10], bs[4], l[4], y[4];
+        {
+            int q = 0;
+            for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { As[q] = (A[q] * scale[i]) * scale[j]; ++q; }
+        }
+        for (int k = 0; k < 4; ++k) bs[k] = g[k] * scale[k];
+        if (!reuse_diagonal) for (int k = 0; k < 4; ++k) diag[k] = std::min(std::max(As[diag_idx[k]], opt.min_lm_diagonal), opt.max_lm_diagonal);
+        for (int k = 0; k < 4; ++k) l[k] = std::sqrt(diag[k] / radius);
+        bool valid = chol4(As, l, bs, y);
+        reuse_diagonal = true;
+        double step[4], mcc = 0;
+        if (valid) {
+            for (int k = 0; k < 4; ++k) step[k] = -y[k];
+            double M[4][4];
+            int q = 0;
+            for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { M[i][j] = As[q]; M[j][i] = As[q]; ++q; }
+            double sAs = 0, sb = 0;
+            for (int i = 0; i < 4; ++i) {
+                double r = 0;
+                for (int j = 0; j < 4; ++j) r = r + M[i][j] * step[j];
+                sAs = sAs + step[i] * r;
+                sb = sb + step[i] * bs[i];
+            }
+            mcc = -(sb + 0.5 * sAs);                                                      // -(J step)'(r + J step / 2)
+            valid = mcc > 0.0;
+        }
+        if (!valid) {
+            if (++num_consecutive_invalid >= opt.max_num_consecutive_invalid_steps) { termination = orc::FAILURE; break; }
+            radius *= 0.5;
+            continue;
+        }
+        num_consecutive_invalid = 0;
+        for (int k = 0; k < 4; ++k) cand[k] = x[k] + step[k] * scale[k];
+        const Eval ec = evaluate(cand);
+        const double cand_cost = ec.valid ? ec.cost : DBL_MAX;
+        double sn = 0;
+        for (int k = 0; k < 4; ++k) sn = sn + (x[k] - cand[k]) * (x[k] - cand[k]);
+        if (std::sqrt(sn) <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) { termination = orc::CONVERGENCE; break; }
+        if (std::fabs(x_cost - cand_cost) <= opt.function_tolerance * x_cost) { termination = orc::CONVERGENCE; break; }
+        const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : (x_cost - cand_cost) / mcc;
+        if (rel > opt.min_relative_decrease) {
+            for (int k = 0; k < 4; ++k) x[k] = cand[k];
+            x_norm = norm4(x);
+            if (!ec.valid) { termination = orc::FAILURE; break; }
+            take(ec);
+            step_is_successful = true;
+            const double q = 2.0 * rel - 1.0;
+            radius = std::min(opt.max_trust_region_radius, radius / std::max(1.0 / 3.0, 1.0 - (q * q) * q));
+            decrease_factor = 2.0;
+            reuse_diagonal = false;
+        } else {
+            radius = radius / decrease_factor;
+            decrease_factor *= 2.0;
+            reuse_diagonal = true;
+        }
+    }
+    if (termination != orc::FAILURE) for (int k = 0; k < 4; ++k) plane_out[k] = best[k];   // solver.cc: only a usable solution is written back
+    if (iterations) *iterations = num_iterations;
+    return termination == orc::FAILURE ? 1 : 0;
 }
 
 // pcl::UniformSampling (filters/uniform_sampling.hpp, applyFilter)

@@ -3,9 +3,9 @@
 // Replaces get_ref_pt (include/utils.h:160-202), calc_laser_coor_v1 (include/pc_process.h:373-462) and its Ceres problem
 // line_fitting / LINE_FITTING_COST (include/opt/opt_line_fitting.h:17-108): the link between eular_cluster_iter and
 // opt_grid_fitting inside est_board_corner (pc_process.h:583-621). The line fit — three parameters, one Huber(0.1) residual
-// per board row, ceres::Solve with DENSE_QR and default options — runs through the same trust-region schedule as the device
-// solvers of this library (Jacobi scaling once, LM diagonal clamp, accept / reject / radius rule, the three stop tests), with
-// the analytic Jacobian of sum |d x a/|a|| in place of Ceres' autodiff and Cholesky on the 3x3 normal equations in place of QR.
+// per board row, ceres::Solve with DENSE_QR and default options — runs through Ceres' trust-region schedule (Jacobi scaling once,
+// LM diagonal clamp, Householder QR on the stacked Jacobian, accept / reject / radius rule, the three stop tests), with the
+// analytic Jacobian of sum |d x a/|a|| in place of Ceres' autodiff.
 #include "common.cuh"
 
 #include <algorithm>
@@ -22,80 +22,125 @@ inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b
 inline double norm(V3 a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
 inline V3 unit(V3 a) { const double l = norm(a); return {a.x / l, a.y / l, a.z / l}; }
 
-struct Eval3 { double cost, A[6], g[3]; bool valid; };      // A: J'J upper triangle 00 01 02 11 12 22, g: J'r
+constexpr int kMaxRows = 32;                                  // board_height residuals (one per board row)
 
-bool chol3(const double* A6, const double* l, const double* b, double* y)
+// One evaluation of the line-fit problem: robustified cost, and (when asked) the loss-corrected residuals and Jacobian rows.
+struct Eval3 { double cost; double r[kMaxRows]; double J[kMaxRows][3]; bool valid; };
+
+// min || A y - b || for the (rows x 3) stacked system by Householder reflections, column by column, no pivoting — what Ceres'
+// DENSE_QR (Eigen::HouseholderQR) computes. A and b are overwritten.
+bool householder3(double (*A)[3], double* b, int rows, double* y)
 {
-    const double a00 = A6[0] + l[0] * l[0], a01 = A6[1], a02 = A6[2], a11 = A6[3] + l[1] * l[1], a12 = A6[4], a22 = A6[5] + l[2] * l[2];
-    if (!(a00 > 0)) return false;
-    const double l00 = std::sqrt(a00), l10 = a01 / l00, l20 = a02 / l00;
-    const double d1 = a11 - l10 * l10;
-    if (!(d1 > 0)) return false;
-    const double l11 = std::sqrt(d1), l21 = (a12 - l20 * l10) / l11;
-    const double d2 = a22 - l20 * l20 - l21 * l21;
-    if (!(d2 > 0)) return false;
-    const double l22 = std::sqrt(d2);
-    const double z0 = b[0] / l00, z1 = (b[1] - l10 * z0) / l11, z2 = (b[2] - l20 * z0 - l21 * z1) / l22;
-    y[2] = z2 / l22; y[1] = (z1 - l21 * y[2]) / l11; y[0] = (z0 - l10 * y[1] - l20 * y[2]) / l00;
+    for (int k = 0; k < 3; ++k) {
+        double norm2 = 0;
+        for (int i = k; i < rows; ++i) norm2 += A[i][k] * A[i][k];
+        const double alpha = A[k][k];
+        double beta = std::sqrt(norm2);
+        if (beta == 0.0) return false;
+        if (alpha > 0) beta = -beta;
+        const double vk = alpha - beta;                           // v = x - beta e1
+        const double vtv = norm2 - alpha * alpha + vk * vk;
+        if (vtv == 0.0) return false;
+        for (int c = k + 1; c < 3; ++c) {
+            double dot = vk * A[k][c];
+            for (int i = k + 1; i < rows; ++i) dot += A[i][k] * A[i][c];
+            const double f = 2.0 * dot / vtv;
+            A[k][c] -= f * vk;
+            for (int i = k + 1; i < rows; ++i) A[i][c] -= f * A[i][k];
+        }
+        double dot = vk * b[k];
+        for (int i = k + 1; i < rows; ++i) dot += A[i][k] * b[i];
+        const double f = 2.0 * dot / vtv;
+        b[k] -= f * vk;
+        for (int i = k + 1; i < rows; ++i) b[i] -= f * A[i][k];
+        A[k][k] = beta;
+    }
+    for (int k = 2; k >= 0; --k) {
+        double s = b[k];
+        for (int c = k + 1; c < 3; ++c) s -= A[k][c] * y[c];
+        if (A[k][k] == 0.0) return false;
+        y[k] = s / A[k][k];
+    }
     return std::isfinite(y[0]) && std::isfinite(y[1]) && std::isfinite(y[2]);
 }
 
-// Ceres TrustRegionMinimizer with default options (50 iterations, function_tolerance 1e-6, gradient_tolerance 1e-10,
-// parameter_tolerance 1e-8, initial radius 1e4) for three parameters. x is updated unless the solve fails.
-void lm3(const std::function<Eval3(const double*)>& eval, double* x)
+// Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy with DENSE_QR and default options (50 iterations, function_tolerance
+// 1e-6, gradient_tolerance 1e-10, parameter_tolerance 1e-8, initial radius 1e4, Jacobi scaling) for m residuals over three
+// parameters. The problem is scale-invariant in its parameters (rank 2), so WHICH minimiser of the damped model is taken matters
+// to the fourth digit of the answer: the step is the QR solution of the stacked system, like Ceres', not a Cholesky solve of the
+// normal equations. x is updated with the best iterate unless the solve fails.
+void lm3(const std::function<void(const double*, bool, Eval3&)>& eval, int m, double* x)
 {
-    const int di[3] = {0, 3, 5};
-    Eval3 e = eval(x);
+    Eval3 e, ec;
+    e.cost = 0; e.valid = false;
+    double grad[3], scale[3] = {1, 1, 1}, diag[3] = {0, 0, 0}, best[3] = {x[0], x[1], x[2]};
+    double x_cost = 0, gmax = 0;
+    auto take = [&](bool first) {                                 // gradient, Jacobi scaling, max-norm of the projected gradient
+        x_cost = e.cost;
+        for (int c = 0; c < 3; ++c) grad[c] = 0;
+        for (int i = 0; i < m; ++i) for (int c = 0; c < 3; ++c) grad[c] += e.J[i][c] * e.r[i];
+        if (first)
+            for (int c = 0; c < 3; ++c) { double s = 0; for (int i = 0; i < m; ++i) s += e.J[i][c] * e.J[i][c]; scale[c] = 1.0 / (1.0 + std::sqrt(s)); }
+        for (int i = 0; i < m; ++i) for (int c = 0; c < 3; ++c) e.J[i][c] *= scale[c];
+        gmax = 0;
+        for (int k = 0; k < 3; ++k) gmax = std::max(gmax, std::fabs(x[k] - (x[k] + (-grad[k]))));
+    };
+    eval(x, true, e);
     if (!e.valid) return;
-    double scale[3], diag[3] = {0, 0, 0};
-    for (int k = 0; k < 3; ++k) scale[k] = 1.0 / (1.0 + std::sqrt(e.A[di[k]]));
-    double x_cost = e.cost, radius = 1e4, dec = 2.0;
-    double xn = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-    bool reuse = false;
+    take(true);
+    auto norm3 = [](const double* v) { double s = 0; for (int k = 0; k < 3; ++k) s += v[k] * v[k]; return std::sqrt(s); };
+    double radius = 1e4, dec = 2.0, xn = norm3(x), minimum_cost = DBL_MAX;
+    bool reuse = false, success = true, failed = false;
     int invalid = 0;
-    auto gmax = [&](const Eval3& ev) { double m = 0; for (int k = 0; k < 3; ++k) m = std::max(m, std::fabs(x[k] - (x[k] + (-ev.g[k])))); return m; };
-    bool success = true;
     for (int it = 0;;) {
-        if (it >= 50) return;
-        if (success && gmax(e) <= 1e-10) return;
-        if (radius <= 1e-32) return;
+        if (success && x_cost < minimum_cost) { minimum_cost = x_cost; for (int k = 0; k < 3; ++k) best[k] = x[k]; }
+        if (it >= 50) break;
+        if (success && gmax <= 1e-10) break;
+        if (radius <= 1e-32) break;
         ++it;
         success = false;
-        double As[6], bs[3], l[3], y[3];
-        { int q = 0; for (int i = 0; i < 3; ++i) for (int j = i; j < 3; ++j) { As[q] = e.A[q] * scale[i] * scale[j]; ++q; } }
-        for (int k = 0; k < 3; ++k) bs[k] = e.g[k] * scale[k];
-        if (!reuse) for (int k = 0; k < 3; ++k) diag[k] = std::min(std::max(As[di[k]], 1e-6), 1e32);
-        for (int k = 0; k < 3; ++k) l[k] = std::sqrt(diag[k] / radius);
-        bool valid = chol3(As, l, bs, y);
+        if (!reuse)
+            for (int c = 0; c < 3; ++c) { double s = 0; for (int i = 0; i < m; ++i) s += e.J[i][c] * e.J[i][c]; diag[c] = std::min(std::max(s, 1e-6), 1e32); }
+        double A[kMaxRows + 3][3], b[kMaxRows + 3], step[3];
+        for (int i = 0; i < m; ++i) { for (int c = 0; c < 3; ++c) A[i][c] = e.J[i][c]; b[i] = e.r[i]; }
+        for (int c = 0; c < 3; ++c) { for (int q = 0; q < 3; ++q) A[m + c][q] = 0.0; A[m + c][c] = std::sqrt(diag[c] / radius); b[m + c] = 0.0; }
+        bool valid = householder3(A, b, m + 3, step);
         reuse = true;
-        double step[3], mcc = 0;
+        double mcc = 0;
         if (valid) {
-            for (int k = 0; k < 3; ++k) step[k] = -y[k];
-            const double sAs = step[0] * (As[0] * step[0] + As[1] * step[1] + As[2] * step[2]) + step[1] * (As[1] * step[0] + As[3] * step[1] + As[4] * step[2]) +
-                               step[2] * (As[2] * step[0] + As[4] * step[1] + As[5] * step[2]);
-            mcc = -((step[0] * bs[0] + step[1] * bs[1] + step[2] * bs[2]) + 0.5 * sAs);
-            valid = mcc > 0;
+            for (int c = 0; c < 3; ++c) step[c] = -step[c];
+            double dot = 0;
+            for (int i = 0; i < m; ++i) {
+                double s = 0;
+                for (int c = 0; c < 3; ++c) s += e.J[i][c] * step[c];
+                dot += s * (e.r[i] + s / 2.0);                    // model_cost_change = -(J step)'(r + J step / 2)
+            }
+            mcc = -dot;
+            valid = mcc > 0.0;
         }
-        if (!valid) { if (++invalid >= 5) return; radius *= 0.5; continue; }
+        if (!valid) { if (++invalid >= 5) { failed = true; break; } radius *= 0.5; continue; }
         invalid = 0;
         double cand[3];
         for (int k = 0; k < 3; ++k) cand[k] = x[k] + step[k] * scale[k];
-        const Eval3 ec = eval(cand);
+        eval(cand, false, ec);
         const double cc = ec.valid ? ec.cost : DBL_MAX;
         double sn = 0;
         for (int k = 0; k < 3; ++k) sn += (x[k] - cand[k]) * (x[k] - cand[k]);
-        if (std::sqrt(sn) <= 1e-8 * (xn + 1e-8)) return;
-        if (std::fabs(x_cost - cc) <= 1e-6 * x_cost) return;
+        if (std::sqrt(sn) <= 1e-8 * (xn + 1e-8)) break;
+        if (std::fabs(x_cost - cc) <= 1e-6 * x_cost) break;
         const double rel = cc >= DBL_MAX ? -DBL_MAX : (x_cost - cc) / mcc;
         if (rel > 1e-3) {
             for (int k = 0; k < 3; ++k) x[k] = cand[k];
-            xn = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-            e = ec; x_cost = ec.cost; success = true;
-            const double q = 2.0 * rel - 1.0;
-            radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - q * q * q));
+            xn = norm3(x);
+            eval(x, true, e);
+            if (!e.valid) { failed = true; break; }
+            take(false);
+            success = true;
+            radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
             dec = 2.0; reuse = false;
-        } else { radius /= dec; dec *= 2.0; reuse = true; }
+        } else { radius = radius / dec; dec *= 2.0; reuse = true; }
     }
+    if (!failed) for (int k = 0; k < 3; ++k) x[k] = best[k];
 }
 
 } // namespace
@@ -147,11 +192,9 @@ extern "C" int rclc_calc_laser_coor(const rclc_config* cfg, const double* cen, i
         if (r == origin_id) origin_centroid = cc;
     }
     double abc[3] = {xt.x, xt.y, xt.z};
-    lm3([&](const double* x) {
-        Eval3 e;
+    RCLC_CHECK(n_rows <= kMaxRows, RCLC_ERR_INVALID, "board_height too large");
+    lm3([&](const double* x, bool want_jac, Eval3& e) {
         e.cost = 0; e.valid = true;
-        for (double& v : e.A) v = 0;
-        for (double& v : e.g) v = 0;
         const double na = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
         const V3 u{x[0] / na, x[1] / na, x[2] / na};
         for (int r = 0; r < n_rows; ++r) {
@@ -161,26 +204,26 @@ extern "C" int rclc_calc_laser_coor(const rclc_config* cfg, const double* cen, i
                 const V3 cr = cross(d, u);
                 const double l = norm(cr);
                 rr += l;
-                const V3 q = cross(V3{cr.x / l, cr.y / l, cr.z / l}, d);          // d|d x u| / du
-                g[0] += q.x; g[1] += q.y; g[2] += q.z;
+                if (want_jac) { const V3 q = cross(V3{cr.x / l, cr.y / l, cr.z / l}, d); g[0] += q.x; g[1] += q.y; g[2] += q.z; }      // d|d x u| / du
             }
-            const double gu = g[0] * u.x + g[1] * u.y + g[2] * u.z;               // du/da = (I - u u^T) / |a|
-            double j[3] = {(g[0] - gu * u.x) / na, (g[1] - gu * u.y) / na, (g[2] - gu * u.z) / na};
-            if (!std::isfinite(rr) || !std::isfinite(j[0]) || !std::isfinite(j[1]) || !std::isfinite(j[2])) { e.valid = false; return e; }
+            double j[3] = {0, 0, 0};
+            if (want_jac) {
+                const double gu = g[0] * u.x + g[1] * u.y + g[2] * u.z;           // du/da = (I - u u^T) / |a|
+                j[0] = (g[0] - gu * u.x) / na; j[1] = (g[1] - gu * u.y) / na; j[2] = (g[2] - gu * u.z) / na;
+            }
+            if (!std::isfinite(rr)) { e.valid = false; return; }
             // HuberLoss(0.1) + Corrector (rho'' <= 0 branch)
             const double sq = rr * rr, bb = 0.1 * 0.1;
             double rho0, rho1;
             if (sq > bb) { const double s = std::sqrt(sq); rho0 = 2.0 * 0.1 * s - bb; rho1 = std::max(DBL_MIN, 0.1 / s); } else { rho0 = sq; rho1 = 1.0; }
             const double w = std::sqrt(rho1);
-            rr *= w;
             for (double& v : j) v *= w;
+            rr *= w;
             e.cost += 0.5 * rho0;
-            int q = 0;
-            for (int a = 0; a < 3; ++a) for (int b2 = a; b2 < 3; ++b2) e.A[q++] += j[a] * j[b2];
-            for (int a = 0; a < 3; ++a) e.g[a] += j[a] * rr;
+            e.r[r] = rr;
+            for (int q = 0; q < 3; ++q) e.J[r][q] = j[q];
         }
-        return e;
-    }, abc);
+    }, n_rows, abc);
     V3 bx = unit(V3{abc[0], abc[1], abc[2]});
     V3 bz = unit(V3{plane[0], plane[1], plane[2]});
     V3 by = cross(bx, bz);

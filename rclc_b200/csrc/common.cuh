@@ -105,6 +105,81 @@ __device__ __forceinline__ int warp_sum(int v)
     return v;
 }
 
+// ---- exact, order-free sums ------------------------------------------------------------------------------------------------
+// A sum that must not depend on the order of its terms (grid shape, warp schedule, CPU vs GPU) is kept in 128-bit fixed point:
+// value = (hi * 2^64 + lo) * 2^-80 (sums below 2^47). A term (a double) is floored onto that grid — exact for everything a float
+// coordinate or a product of two of them can hold, and below that every term loses the same bits whatever the order — and added
+// as an integer; the total is rounded to a double once, to nearest even (fix128_to_double).
+struct Fix128 { long long hi; unsigned long long lo; };
+
+__device__ __forceinline__ void fix128_add(Fix128& a, long long hi, unsigned long long lo)
+{
+    const unsigned long long nl = a.lo + lo;
+    a.hi += hi + (nl < lo ? 1 : 0);
+    a.lo = nl;
+}
+__device__ __forceinline__ void fix128_add_double(Fix128& a, double t)
+{
+    const double s = t * 65536.0;                                 // exact
+    const double fl = floor(s);
+    const long long hi = __double2ll_rd(s);                       // floor(t * 2^16)
+    const unsigned long long lo = __double2ull_rz((s - fl) * 18446744073709551616.0);     // [0, 1) * 2^64, exact
+    fix128_add(a, hi, lo);
+}
+__device__ __forceinline__ void fix128_warp_sum(Fix128& a)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fix128_add(a, __shfl_xor_sync(0xffffffffu, a.hi, o), __shfl_xor_sync(0xffffffffu, a.lo, o));
+}
+// (hi * 2^64 + lo) * 2^-80 rounded to the nearest double, ties to even — what a conversion of the 128-bit integer does.
+__host__ __device__ inline double fix128_to_double(long long hi, unsigned long long lo)
+{
+    const bool neg = hi < 0;
+    unsigned long long h = (unsigned long long)hi, l = lo;
+    if (neg) { l = ~l + 1ull; h = ~h + (l == 0ull ? 1ull : 0ull); }
+    if (h == 0ull && l == 0ull) return 0.0;
+    int p = 0;                                                    // index of the leading one
+    {
+        unsigned long long w = h ? h : l;
+        int b = 0;
+        while (w >>= 1) ++b;
+        p = h ? 64 + b : b;
+    }
+    double r;
+    if (p <= 52) r = ldexp((double)l, -80);
+    else {
+        const int s = p - 52;                                     // bits to drop: 1 .. 75
+        unsigned long long mant;
+        bool above_half, is_half;
+        if (s < 64) {
+            mant = (h << (64 - s)) | (l >> s);
+            const unsigned long long rem = l & ((1ull << s) - 1ull), half = 1ull << (s - 1);
+            above_half = rem > half; is_half = rem == half;
+        } else {
+            const int t = s - 64;
+            mant = h >> t;
+            const unsigned long long rem_hi = t ? (h & ((1ull << t) - 1ull)) : 0ull;
+            const unsigned long long half_hi = t ? (1ull << (t - 1)) : 0ull, half_lo = t ? 0ull : (1ull << 63);
+            above_half = rem_hi > half_hi || (rem_hi == half_hi && l > half_lo);
+            is_half = rem_hi == half_hi && l == half_lo;
+        }
+        if (above_half || (is_half && (mant & 1ull))) ++mant;
+        r = ldexp((double)mant, s - 80);
+    }
+    return neg ? -r : r;
+}
+
+// A double whose arithmetic is spelled with the _rn intrinsics: nvcc never contracts it into FMAs, so an expression written with
+// xd gives the bits the same expression gives on a CPU built without FMA contraction (the checker of the tests is).
+struct xd { double v; };
+__device__ __forceinline__ xd operator+(xd a, xd b) { return xd{__dadd_rn(a.v, b.v)}; }
+__device__ __forceinline__ xd operator-(xd a, xd b) { return xd{__dsub_rn(a.v, b.v)}; }
+__device__ __forceinline__ xd operator*(xd a, xd b) { return xd{__dmul_rn(a.v, b.v)}; }
+__device__ __forceinline__ xd operator/(xd a, xd b) { return xd{__ddiv_rn(a.v, b.v)}; }
+__device__ __forceinline__ xd operator-(xd a) { return xd{-a.v}; }
+__device__ __forceinline__ xd xsqrt(xd a) { return xd{__dsqrt_rn(a.v)}; }
+__device__ __forceinline__ xd xabs(xd a) { return xd{fabs(a.v)}; }
+
 // pcl::transformPointCloud(Matrix4f) restated: ((m0*x + m1*y) + m2*z) + m3 in float, no FMA contraction.
 __device__ __forceinline__ float affine_row_f(float m0, float m1, float m2, float m3, float x, float y, float z)
 {

@@ -14,9 +14,17 @@
 
 namespace rclc {
 
+// Bit-reproducible by construction. The sums over the points (cost, J'J, J'r) are exact, order-free fixed-point sums of terms
+// that are each rounded once (common.cuh: Fix128), every other expression is written with `xd` (no FMA contraction) in one fixed
+// association, and the step is the Cholesky solution of the 4x4 damped normal equations built from those sums. The CPU checker of
+// the tests states the solve the same way — Ceres' own DENSE_QR (Eigen Householder on the stacked Jacobian) has no pinned
+// operation order in the reference either — so plane, iteration count and every intermediate agree with it bit for bit, whatever
+// the grid shape. That is what the downstream stages need: the projection onto this plane is rounded to float, and a last-bit
+// difference there is enough to fork the grid fit's LM path (sensitivity of the chain).
 constexpr int kPfThreads = 256;
 constexpr int kPfMaxCtas = 592;       // 148 SMs x 4
-constexpr int kPfTerms = 16;          // cost, 10 J'J (upper triangle), 4 J'r, count
+constexpr int kPfSums = 15;           // cost, 10 J'J (upper triangle, row-major), 4 J'r
+constexpr int kPfWords = 2 * kPfSums + 2;     // 128-bit sums, the point count, the "evaluation failed" flag
 
 struct PlaneLm {
     // control
@@ -36,22 +44,29 @@ struct PlaneEval { double cost; double A[10]; double g[4]; bool valid; };
 __device__ bool chol4_solve(const double* A10, const double* l, const double* b, double* y)
 {
     // A (upper triangle, row-major: 00 01 02 03 11 12 13 22 23 33) + diag(l^2), Cholesky, solve A y = b
-    double M[4][4];
+    xd M[4][4];
     int q = 0;
-    for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { M[i][j] = A10[q]; M[j][i] = A10[q]; ++q; }
-    for (int i = 0; i < 4; ++i) M[i][i] += l[i] * l[i];
-    double L[4][4] = {{0}};
+    for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { M[i][j] = xd{A10[q]}; M[j][i] = xd{A10[q]}; ++q; }
+    for (int i = 0; i < 4; ++i) M[i][i] = M[i][i] + xd{l[i]} * xd{l[i]};
+    xd L[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) L[i][j] = xd{0.0};
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j <= i; ++j) {
-            double s = M[i][j];
-            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-            if (i == j) { if (!(s > 0.0)) return false; L[i][i] = sqrt(s); }
+            xd s = M[i][j];
+            for (int k = 0; k < j; ++k) s = s - L[i][k] * L[j][k];
+            if (i == j) { if (!(s.v > 0.0)) return false; L[i][i] = xsqrt(s); }
             else L[i][j] = s / L[j][j];
         }
-    double z[4];
-    for (int i = 0; i < 4; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[i][k] * z[k]; z[i] = s / L[i][i]; }
-    for (int i = 3; i >= 0; --i) { double s = z[i]; for (int k = i + 1; k < 4; ++k) s -= L[k][i] * y[k]; y[i] = s / L[i][i]; }
+    xd z[4], yy[4];
+    for (int i = 0; i < 4; ++i) { xd s = xd{b[i]}; for (int k = 0; k < i; ++k) s = s - L[i][k] * z[k]; z[i] = s / L[i][i]; }
+    for (int i = 3; i >= 0; --i) { xd s = z[i]; for (int k = i + 1; k < 4; ++k) s = s - L[k][i] * yy[k]; yy[i] = s / L[i][i]; }
+    for (int i = 0; i < 4; ++i) y[i] = yy[i].v;
     return isfinite(y[0]) && isfinite(y[1]) && isfinite(y[2]) && isfinite(y[3]);
+}
+
+__device__ double norm4(const double* x)
+{
+    return xsqrt(((xd{x[0]} * xd{x[0]} + xd{x[1]} * xd{x[1]}) + xd{x[2]} * xd{x[2]}) + xd{x[3]} * xd{x[3]}).v;
 }
 
 __device__ void plane_take_eval(PlaneLm& s, const PlaneEval& e)
@@ -59,11 +74,11 @@ __device__ void plane_take_eval(PlaneLm& s, const PlaneEval& e)
     s.x_cost = e.cost;
     for (int k = 0; k < 10; ++k) s.A[k] = e.A[k];
     double gm = 0;
-    for (int k = 0; k < 4; ++k) { s.g[k] = e.g[k]; gm = fmax(gm, fabs(s.x[k] - (s.x[k] + (-e.g[k])))); }
+    for (int k = 0; k < 4; ++k) { s.g[k] = e.g[k]; gm = fmax(gm, fabs((xd{s.x[k]} - (xd{s.x[k]} + xd{-e.g[k]})).v)); }
     s.gmax = gm;
 }
 
-// TrustRegionMinimizer as a resumable state machine (oracle/ceres_lm.hpp documents the published algorithm).
+// TrustRegionMinimizer as a resumable state machine (Ceres' published algorithm: SURVEY.md Appendix B).
 __device__ void plane_lm_advance(PlaneLm& s, const PlaneEval& e, double ftol, int max_iters)
 {
     const int diag_idx[4] = {0, 4, 7, 9};
@@ -71,35 +86,35 @@ __device__ void plane_lm_advance(PlaneLm& s, const PlaneEval& e, double ftol, in
     if (s.phase == 1) {
         if (!e.valid) { s.termination = 2; s.initial_cost = nan(""); s.min_iter_cost = nan(""); s.phase = 3; return; }
         plane_take_eval(s, e);
-        for (int k = 0; k < 4; ++k) s.scale[k] = 1.0 / (1.0 + sqrt(e.A[diag_idx[k]]));       // jacobi scaling, once
+        for (int k = 0; k < 4; ++k) s.scale[k] = (xd{1.0} / (xd{1.0} + xsqrt(xd{e.A[diag_idx[k]]}))).v;       // jacobi scaling, once
         s.initial_cost = s.x_cost; s.min_iter_cost = s.x_cost; s.minimum_cost = DBL_MAX;
         s.step_is_successful = 1; s.iteration = 0; s.num_iterations = 0; s.radius = 1e4; s.decrease_factor = 2.0;
         s.reuse_diagonal = 0; s.num_consecutive_invalid = 0;
-        s.x_norm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2] + s.x[3] * s.x[3]);
+        s.x_norm = norm4(s.x);
     } else {
         const double cand_cost = e.valid ? e.cost : DBL_MAX;
-        double sn = 0;
-        for (int k = 0; k < 4; ++k) sn += (s.x[k] - s.cand[k]) * (s.x[k] - s.cand[k]);
-        if (sqrt(sn) <= 1e-8 * (s.x_norm + 1e-8)) { s.termination = 0; terminate = true; }
-        else if (fabs(s.x_cost - cand_cost) <= ftol * s.x_cost) { s.termination = 0; terminate = true; }
+        xd sn = xd{0.0};
+        for (int k = 0; k < 4; ++k) sn = sn + (xd{s.x[k]} - xd{s.cand[k]}) * (xd{s.x[k]} - xd{s.cand[k]});
+        if (xsqrt(sn).v <= (xd{1e-8} * (xd{s.x_norm} + xd{1e-8})).v) { s.termination = 0; terminate = true; }
+        else if (fabs((xd{s.x_cost} - xd{cand_cost}).v) <= (xd{ftol} * xd{s.x_cost}).v) { s.termination = 0; terminate = true; }
         else {
-            const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : (s.x_cost - cand_cost) / s.model_cost_change;
+            const double rel = (cand_cost >= DBL_MAX) ? -DBL_MAX : ((xd{s.x_cost} - xd{cand_cost}) / xd{s.model_cost_change}).v;
             if (rel > 1e-3) {
                 for (int k = 0; k < 4; ++k) s.x[k] = s.cand[k];
-                s.x_norm = sqrt(s.x[0] * s.x[0] + s.x[1] * s.x[1] + s.x[2] * s.x[2] + s.x[3] * s.x[3]);
+                s.x_norm = norm4(s.x);
                 if (!e.valid) { s.termination = 2; terminate = true; }
                 else {
                     plane_take_eval(s, e);
                     s.step_is_successful = 1;
-                    const double q = 2.0 * rel - 1.0;
-                    s.radius = fmin(1e16, s.radius / fmax(1.0 / 3.0, 1.0 - q * q * q));
+                    const xd q = xd{2.0} * xd{rel} - xd{1.0};
+                    s.radius = fmin(1e16, (xd{s.radius} / xd{fmax(1.0 / 3.0, (xd{1.0} - (q * q) * q).v)}).v);
                     s.decrease_factor = 2.0;
                     s.reuse_diagonal = 0;
                     s.min_iter_cost = fmin(s.min_iter_cost, s.x_cost);
                 }
             } else {
                 s.min_iter_cost = fmin(s.min_iter_cost, cand_cost);
-                s.radius = s.radius / s.decrease_factor;
+                s.radius = (xd{s.radius} / xd{s.decrease_factor}).v;
                 s.decrease_factor *= 2.0;
                 s.reuse_diagonal = 1;
                 s.step_is_successful = 0;
@@ -117,11 +132,11 @@ __device__ void plane_lm_advance(PlaneLm& s, const PlaneEval& e, double ftol, in
         double As[10], bs[4], l[4], y[4];
         {
             int q = 0;
-            for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { As[q] = s.A[q] * s.scale[i] * s.scale[j]; ++q; }
+            for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { As[q] = ((xd{s.A[q]} * xd{s.scale[i]}) * xd{s.scale[j]}).v; ++q; }
         }
-        for (int k = 0; k < 4; ++k) bs[k] = s.g[k] * s.scale[k];
+        for (int k = 0; k < 4; ++k) bs[k] = (xd{s.g[k]} * xd{s.scale[k]}).v;
         if (!s.reuse_diagonal) for (int k = 0; k < 4; ++k) s.diag[k] = fmin(fmax(As[diag_idx[k]], 1e-6), 1e32);
-        for (int k = 0; k < 4; ++k) l[k] = sqrt(s.diag[k] / s.radius);
+        for (int k = 0; k < 4; ++k) l[k] = xsqrt(xd{s.diag[k]} / xd{s.radius}).v;
         bool valid = chol4_solve(As, l, bs, y);
         s.reuse_diagonal = 1;
         double step[4], mcc = 0;
@@ -129,9 +144,14 @@ __device__ void plane_lm_advance(PlaneLm& s, const PlaneEval& e, double ftol, in
             for (int k = 0; k < 4; ++k) step[k] = -y[k];
             double M[4][4]; int q = 0;
             for (int i = 0; i < 4; ++i) for (int j = i; j < 4; ++j) { M[i][j] = As[q]; M[j][i] = As[q]; ++q; }
-            double sAs = 0, sb = 0;
-            for (int i = 0; i < 4; ++i) { double r = 0; for (int j = 0; j < 4; ++j) r += M[i][j] * step[j]; sAs += step[i] * r; sb += step[i] * bs[i]; }
-            mcc = -(sb + 0.5 * sAs);                       // -(J step)'(r + J step / 2)
+            xd sAs = xd{0.0}, sb = xd{0.0};
+            for (int i = 0; i < 4; ++i) {
+                xd r = xd{0.0};
+                for (int j = 0; j < 4; ++j) r = r + xd{M[i][j]} * xd{step[j]};
+                sAs = sAs + xd{step[i]} * r;
+                sb = sb + xd{step[i]} * xd{bs[i]};
+            }
+            mcc = (-(sb + xd{0.5} * sAs)).v;               // -(J step)'(r + J step / 2)
             valid = mcc > 0.0;
         }
         if (!valid) {
@@ -142,82 +162,103 @@ __device__ void plane_lm_advance(PlaneLm& s, const PlaneEval& e, double ftol, in
         }
         s.num_consecutive_invalid = 0;
         s.model_cost_change = mcc;
-        for (int k = 0; k < 4; ++k) { s.cand[k] = s.x[k] + step[k] * s.scale[k]; s.eval_x[k] = s.cand[k]; }
+        for (int k = 0; k < 4; ++k) { s.cand[k] = (xd{s.x[k]} + xd{step[k]} * xd{s.scale[k]}).v; s.eval_x[k] = s.cand[k]; }
         s.phase = 2;
         return;
     }
     s.phase = 3;
 }
 
-// One evaluation: cost + normal equations at st->eval_x over the points with intensity >= thd; the last CTA folds the per-CTA
-// partials in a fixed order (deterministic) and advances the LM state.
-__global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restrict__ pts, int64_t n, float thd_lo, double thd, double huber_a,
-                                                           double ftol, int max_iters, PlaneLm* __restrict__ st, double* __restrict__ partials)
+// One evaluation: cost + normal equations at st->eval_x over the points with intensity >= thd; the last CTA adds the per-CTA
+// partial sums (integers: any order) and advances the LM state.
+__global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restrict__ pts, int64_t n, double thd, double huber_a, double ftol, int max_iters,
+                                                           PlaneLm* __restrict__ st, unsigned long long* __restrict__ partials)
 {
     if (st->phase == 3) return;
-    const double a = st->eval_x[0], b = st->eval_x[1], c = st->eval_x[2], d = st->eval_x[3];
-    const double nn = a * a + b * b + c * c, nrm = sqrt(nn);
-    double acc[kPfTerms];
+    const xd a{st->eval_x[0]}, b{st->eval_x[1]}, c{st->eval_x[2]}, d{st->eval_x[3]};
+    const xd nn = (a * a + b * b) + c * c, nrm = xsqrt(nn), den = nn * nrm;
+    const xd ha{huber_a}, hb = ha * ha;
+    Fix128 acc[kPfSums];
 #pragma unroll
-    for (int k = 0; k < kPfTerms; ++k) acc[k] = 0.0;
+    for (int k = 0; k < kPfSums; ++k) { acc[k].hi = 0; acc[k].lo = 0; }
+    unsigned long long cnt = 0;
     bool bad = false;
     for (int64_t i = blockIdx.x * (int64_t)kPfThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kPfThreads) {
         const float4 p = __ldg(pts + i);
         if ((double)p.w < thd) continue;                                   // opt_plane_param.hpp:56 (float < double)
-        const double X = p.x, Y = p.y, Z = p.z;
-        const double e = a * X + b * Y + c * Z + d;
-        double r = fabs(e) / nrm;                                           // :35-38
-        const double sg = (e < 0) ? -1.0 : 1.0, ae = fabs(e);               // ceres abs(Jet): f.a < 0 ? -f : f
-        double j[4] = {(sg * X) / nrm - ae * a / (nn * nrm), (sg * Y) / nrm - ae * b / (nn * nrm), (sg * Z) / nrm - ae * c / (nn * nrm), sg / nrm};
-        if (!isfinite(r) || !isfinite(j[0]) || !isfinite(j[1]) || !isfinite(j[2]) || !isfinite(j[3])) { bad = true; continue; }
+        const xd X{(double)p.x}, Y{(double)p.y}, Z{(double)p.z};
+        const xd e = ((a * X + b * Y) + c * Z) + d;
+        const xd ae = xabs(e);
+        xd r = ae / nrm;                                                    // :35-38
+        const xd sg{(e.v < 0) ? -1.0 : 1.0};                                // ceres abs(Jet): f.a < 0 ? -f : f
+        xd j[4] = {(sg * X) / nrm - (ae * a) / den, (sg * Y) / nrm - (ae * b) / den, (sg * Z) / nrm - (ae * c) / den, sg / nrm};
+        // an evaluation fails on a non-finite residual or Jacobian; entries beyond 2^13 (products beyond 2^26: 2^21 of them would leave
+        // the fixed-point range) count as that too — a plane whose normal has collapsed, never a fit of real coordinates
+        if (!(fabs(r.v) < 8192.0 && fabs(j[0].v) < 8192.0 && fabs(j[1].v) < 8192.0 && fabs(j[2].v) < 8192.0 && fabs(j[3].v) < 8192.0)) { bad = true; continue; }
         // HuberLoss + Corrector (rho'' <= 0 branch)
-        const double sq = r * r, bb = huber_a * huber_a;
-        double rho0, rho1;
-        if (sq > bb) { const double rr = sqrt(sq); rho0 = 2.0 * huber_a * rr - bb; rho1 = fmax(DBL_MIN, huber_a / rr); }
-        else { rho0 = sq; rho1 = 1.0; }
-        const double w = sqrt(rho1);
-        r *= w;
+        const xd sq = r * r;
+        xd rho0, rho1;
+        if (sq.v > hb.v) { const xd rr = xsqrt(sq); rho0 = (xd{2.0} * ha) * rr - hb; rho1 = xd{fmax(DBL_MIN, (ha / rr).v)}; }
+        else { rho0 = sq; rho1 = xd{1.0}; }
+        const xd w = xsqrt(rho1);
+        r = r * w;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) j[k] *= w;
-        acc[0] += 0.5 * rho0;
+        for (int k = 0; k < 4; ++k) j[k] = j[k] * w;
+        fix128_add_double(acc[0], (xd{0.5} * rho0).v);
         int q = 1;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int v = u; v < 4; ++v) acc[q++] += j[u] * j[v];
+            for (int v = u; v < 4; ++v) fix128_add_double(acc[q++], (j[u] * j[v]).v);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[11 + u] += j[u] * r;
-        acc[15] += 1.0;
+        for (int u = 0; u < 4; ++u) fix128_add_double(acc[11 + u], (j[u] * r).v);
+        ++cnt;
     }
-    (void)thd_lo;
-    __shared__ double s_red[kPfThreads / 32][kPfTerms];
+    __shared__ unsigned long long s_red[kPfThreads / 32][kPfWords];
     __shared__ int s_bad, s_last;
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     if (bad) s_bad = 1;
 #pragma unroll
-    for (int k = 0; k < kPfTerms; ++k) acc[k] = warp_sum(acc[k]);
-    if ((threadIdx.x & 31) == 0)
-        for (int k = 0; k < kPfTerms; ++k) s_red[threadIdx.x >> 5][k] = acc[k];
-    __syncthreads();
-    if (threadIdx.x < kPfTerms) {
-        double v = 0;
-        for (int w = 0; w < kPfThreads / 32; ++w) v += s_red[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * (kPfTerms + 1) + threadIdx.x] = v;
+    for (int k = 0; k < kPfSums; ++k) fix128_warp_sum(acc[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < kPfSums; ++k) { s_red[threadIdx.x >> 5][2 * k] = (unsigned long long)acc[k].hi; s_red[threadIdx.x >> 5][2 * k + 1] = acc[k].lo; }
+        s_red[threadIdx.x >> 5][2 * kPfSums] = cnt;
     }
-    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * (kPfTerms + 1) + kPfTerms] = s_bad ? 1.0 : 0.0;
+    __syncthreads();
+    unsigned long long* mine = partials + (size_t)blockIdx.x * kPfWords;
+    if (threadIdx.x < kPfSums) {
+        Fix128 t;
+        t.hi = 0; t.lo = 0;
+        for (int w = 0; w < kPfThreads / 32; ++w) fix128_add(t, (long long)s_red[w][2 * threadIdx.x], s_red[w][2 * threadIdx.x + 1]);
+        mine[2 * threadIdx.x] = (unsigned long long)t.hi;
+        mine[2 * threadIdx.x + 1] = t.lo;
+    } else if (threadIdx.x == kPfSums) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kPfThreads / 32; ++w) t += s_red[w][2 * kPfSums];
+        mine[2 * kPfSums] = t;
+        mine[2 * kPfSums + 1] = s_bad ? 1ull : 0ull;
+    }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->counter, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    // fold: thread k < 17 sums term k over the CTAs in index order
-    __shared__ double s_tot[kPfTerms + 1];
-    if (threadIdx.x <= kPfTerms) {
-        double v = 0;
-        for (unsigned cta = 0; cta < gridDim.x; ++cta) v += __ldcg(partials + (size_t)cta * (kPfTerms + 1) + threadIdx.x);
-        s_tot[threadIdx.x] = v;
+    __shared__ double s_tot[kPfSums];
+    __shared__ unsigned long long s_cnt, s_anybad;
+    if (threadIdx.x < kPfSums) {
+        Fix128 t;
+        t.hi = 0; t.lo = 0;
+        for (unsigned cta = 0; cta < gridDim.x; ++cta)
+            fix128_add(t, (long long)__ldcg(partials + (size_t)cta * kPfWords + 2 * threadIdx.x), __ldcg(partials + (size_t)cta * kPfWords + 2 * threadIdx.x + 1));
+        s_tot[threadIdx.x] = fix128_to_double(t.hi, t.lo);
+    } else if (threadIdx.x == kPfSums) {
+        unsigned long long t = 0, bd = 0;
+        for (unsigned cta = 0; cta < gridDim.x; ++cta) { t += __ldcg(partials + (size_t)cta * kPfWords + 2 * kPfSums); bd |= __ldcg(partials + (size_t)cta * kPfWords + 2 * kPfSums + 1); }
+        s_cnt = t; s_anybad = bd;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -226,8 +267,8 @@ __global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restr
         e.cost = s_tot[0];
         for (int k = 0; k < 10; ++k) e.A[k] = s_tot[1 + k];
         for (int k = 0; k < 4; ++k) e.g[k] = s_tot[11 + k];
-        e.valid = s_tot[kPfTerms] == 0.0;
-        st->n_used = (long long)s_tot[15];
+        e.valid = s_anybad == 0ull;
+        st->n_used = (long long)s_cnt;
         PlaneLm s = *st;
         plane_lm_advance(s, e, ftol, max_iters);
         *st = s;
@@ -248,9 +289,9 @@ __global__ void k_plane_init(PlaneLm* st)
 int dev_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_pts, int64_t n, double plane_out[4], int32_t* iterations, int64_t* n_used)
 {
     const int ctas = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPfThreads * 4 - 1) / (kPfThreads * 4), kPfMaxCtas));
-    RCLC_TRY(ctx->d_tmp.reserve(sizeof(PlaneLm) + 256 + (size_t)kPfMaxCtas * (kPfTerms + 1) * 8));
+    RCLC_TRY(ctx->d_tmp.reserve(sizeof(PlaneLm) + 256 + (size_t)kPfMaxCtas * kPfWords * 8));
     PlaneLm* d_st = ctx->d_tmp.as<PlaneLm>();
-    double* d_part = reinterpret_cast<double*>(ctx->d_tmp.as<char>() + ((sizeof(PlaneLm) + 255) & ~(size_t)255));
+    unsigned long long* d_part = reinterpret_cast<unsigned long long*>(ctx->d_tmp.as<char>() + ((sizeof(PlaneLm) + 255) & ~(size_t)255));
     k_plane_init<<<1, 1, 0, ctx->stream>>>(d_st);
     ctx->launches += 1;
     // Ceres defaults for this solve (opt_plane_param.hpp:75-77 sets only DENSE_QR): 50 iterations, function_tolerance 1e-6.
@@ -262,7 +303,7 @@ int dev_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_pts, in
     int launched = 0;
     for (;;) {
         for (int r = 0; r < 8; ++r) {
-            k_plane_eval<<<ctas, kPfThreads, 0, ctx->stream>>>(d_pts, n, 0.f, cfg->plane_reflactive_thd, cfg->plane_huber_a, ftol, max_iters, d_st, d_part);
+            k_plane_eval<<<ctas, kPfThreads, 0, ctx->stream>>>(d_pts, n, cfg->plane_reflactive_thd, cfg->plane_huber_a, ftol, max_iters, d_st, d_part);
             ctx->launches += 1;
         }
         launched += 8;

@@ -79,25 +79,6 @@ __global__ void __launch_bounds__(kScoreThreads) k_score(const float4* __restric
 constexpr int kSelThreads = 256;
 constexpr int kSelTerms = 9;            // xx xy xz yy yz zz x y z
 
-struct Fix128 { long long hi; unsigned long long lo; };          // value = (hi * 2^64 + lo) * 2^-80
-
-__device__ __forceinline__ void fix128_add_double(Fix128& a, double t)
-{
-    const double s = t * 65536.0;                                 // exact
-    const long long hi = __double2ll_rd(s);                       // floor(t * 2^16): |t| < 2^47
-    const double r = s - floor(s);                                // [0, 1), exact
-    const unsigned long long lo = __double2ull_rz(r * 18446744073709551616.0);
-    const unsigned long long nl = a.lo + lo;
-    a.hi += hi + (nl < lo ? 1 : 0);
-    a.lo = nl;
-}
-__device__ __forceinline__ void fix128_add(Fix128& a, long long hi, unsigned long long lo)
-{
-    const unsigned long long nl = a.lo + lo;
-    a.hi += hi + (nl < lo ? 1 : 0);
-    a.lo = nl;
-}
-
 __global__ void __launch_bounds__(kSelThreads) k_select(const float4* __restrict__ pts, int64_t n, float4 pl, float thr_le,
                                                         uint8_t* __restrict__ mask, unsigned long long* __restrict__ partials /* [grid][2 * kSelTerms + 1] */)
 {
@@ -120,10 +101,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select(const float4* __restrict
     __shared__ unsigned long long s_red[kSelThreads / 32][2 * kSelTerms + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < kSelTerms; ++k)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            fix128_add(a[k], __shfl_xor_sync(0xffffffffu, a[k].hi, o), __shfl_xor_sync(0xffffffffu, a[k].lo, o));
+    for (int k = 0; k < kSelTerms; ++k) fix128_warp_sum(a[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) {
@@ -224,7 +202,7 @@ int dev_ransac_select(rclc_ctx* ctx, const float4* d_pts, int64_t n, const float
         __int128 t = 0;
         for (int c = 0; c < grid; ++c)
             t += (__int128)(((unsigned __int128)part[(size_t)c * kW + 2 * k] << 64) | (unsigned __int128)part[(size_t)c * kW + 2 * k + 1]);
-        accu[k] = std::ldexp((double)t, -80);
+        accu[k] = fix128_to_double((long long)(t >> 64), (unsigned long long)t);
     }
     for (int c = 0; c < grid; ++c) cnt += (int64_t)part[(size_t)c * kW + 2 * kSelTerms];
     if (n_inliers) *n_inliers = cnt;

@@ -153,3 +153,84 @@ def gt_extrinsic():
     T[:3, :3] = _rot_xyz(np.deg2rad(1.5), np.deg2rad(-2.0), np.deg2rad(0.8)) @ np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])
     T[:3, 3] = [0.06, -0.04, 0.03]
     return T
+
+
+T_BASE = np.array([[0.0, -1.0, 0.0, 0.0], [0.0, 0.0, -1.0, 0.0], [1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0]])   # src/global.cpp:116-122
+
+
+def scan_extrinsic():
+    """Ground-truth camera <- (T_base'd) laser transform of the raw-scan rig (the frame est_board_corner's corners live in)."""
+    T = np.eye(4)
+    T[:3, :3] = _rot_xyz(0.02, -0.03, 0.015)
+    T[:3, 3] = [0.07, -0.05, 0.04]
+    return T
+
+
+def raw_scan(f, n_pts=100000, seed0=7000, W=8, H=6, side=0.1, board_share=0.62, pix_sigma=1e-4):
+    """One RAW lidar scan of BASELINE configs[0] (the input of apps/BoardSegmentation.cpp), addressed by its global index f:
+    a MID-40-like rosette (golden-ratio ray order, density rising towards the optical axis) cast into a scene of a W x H
+    chessboard 4-5 m down the lidar's x axis, the ground (z = -1.2 m), a back wall (x = 5.9 m) and scattered clutter; points are
+    float32 {x, y, z, intensity} in the LIDAR frame (x forward, z up). `board_share` of the rays are aimed at the board's
+    neighbourhood (an integrated non-repetitive scan is densest where the sensor points), the rest sweep the whole 38 deg cone.
+
+    Returns (raw [n, 4], img_norm [(W-1)*(H-1), 2], corners_cam [(W-1)*(H-1), 3]): the normalised image coordinates of the inner
+    corners seen through scan_extrinsic() with a little pixel noise, and the true corners in the T_base'd laser frame, both in
+    the order est_board_corner returns them for this rig."""
+    rng = np.random.default_rng(seed0 + f)
+    # the board in the camera-like frame (u right, v down, w forward), top-right square black
+    Rb = _rot_xyz(0.12 * (rng.uniform() - 0.5), 0.3 * (rng.uniform() - 0.5), 0.16 * (rng.uniform() - 0.5))
+    tb = np.array([0.8 * (rng.uniform() - 0.5), 0.4 * (rng.uniform() - 0.5), 4.0 + 1.0 * rng.uniform()])
+    hw, hh = W * side / 2, H * side / 2
+    n_board = int(n_pts * board_share)
+    i = np.arange(n_pts, dtype=np.float64)
+    # ray directions in the camera-like frame, (u/w, v/w)
+    g1 = np.modf(i * GOLD + rng.uniform())[0]
+    g2 = np.modf(i * PLASTIC + rng.uniform())[0]
+    aim = np.arange(n_pts) % 50 < int(round(50 * board_share))            # interleaved, like a scan that keeps revisiting
+    # aimed rays: a disc around the board centre's direction, 15 % wider than the board's half diagonal
+    rho_b = 1.15 * np.hypot(hw, hh) / tb[2]
+    r_a = rho_b * np.sqrt(g1)
+    r_w = np.tan(np.deg2rad(19.2)) * g1 ** 0.8                            # whole cone, denser at the centre
+    r = np.where(aim, r_a, r_w)
+    phi = 2 * np.pi * g2
+    du = np.where(aim, tb[0] / tb[2], 0.0) + r * np.cos(phi)
+    dv = np.where(aim, tb[1] / tb[2], 0.0) + r * np.sin(phi)
+    d = np.stack([du, dv, np.ones(n_pts)], axis=1)
+    # board plane: normal = Rb[:, 2], through tb
+    nb = Rb[:, 2]
+    t_board = (nb @ tb) / (d @ nb)
+    hit = d * t_board[:, None]
+    ab = (hit - tb) @ Rb[:, :2]
+    on_board = (np.abs(ab[:, 0]) <= hw) & (np.abs(ab[:, 1]) <= hh) & (t_board > 0)
+    # ground: lidar z = -1.2  <=>  camera-like v = +1.2 ; wall: lidar x = 5.9  <=>  w = 5.9
+    t_ground = np.where(d[:, 1] > 1e-6, 1.2 / np.maximum(d[:, 1], 1e-6), np.inf)
+    t_wall = np.full(n_pts, 5.9)
+    t_bg = np.minimum(t_ground, t_wall)
+    is_ground = t_ground < t_wall
+    t = np.where(on_board, t_board, t_bg)
+    P = d * t[:, None]
+    # range noise: 2 mm along the board normal on the board, 1 cm on the background
+    P = P + np.where(on_board[:, None], nb[None, :] * rng.normal(0.0, 0.002, n_pts)[:, None],
+                     np.where(is_ground[:, None], np.array([0.0, 1.0, 0.0])[None, :], np.array([0.0, 0.0, 1.0])[None, :]) *
+                     rng.normal(0.0, 0.01, n_pts)[:, None])
+    # reflectance: white 110, black 10 rising to 70 within 12 mm of a square's edge (the beam footprint), +- 2
+    fu, fv = (ab[:, 0] + hw) / side, (ab[:, 1] + hh) / side
+    ci = np.clip(np.floor(fu), 0, W - 1); ri = np.clip(np.floor(fv), 0, H - 1)
+    e = np.minimum(np.minimum(fu - ci, ci + 1 - fu), np.minimum(fv - ri, ri + 1 - fv)) * side
+    black = ((ci + ri) % 2) == 1
+    I_board = np.maximum(4.0, np.where(black, 10.0 + 60.0 * np.maximum(0.0, 1.0 - e / 0.012), 110.0) + rng.normal(0.0, 2.0, n_pts))
+    I = np.where(on_board, I_board, np.where(is_ground, 40.0, 60.0))
+    # clutter: 3 % of the background rays return from somewhere in the volume
+    cl = (~on_board) & (rng.uniform(size=n_pts) < 0.03)
+    P[cl] = np.stack([-3.0 + 6.0 * rng.uniform(size=cl.sum()), 1.2 - 3.0 * rng.uniform(size=cl.sum()), 1.0 + 8.0 * rng.uniform(size=cl.sum())], axis=1)
+    I[cl] = 150.0 * rng.uniform(size=cl.sum())
+    # camera-like -> lidar: inverse of T_base (x_l = w, y_l = -u, z_l = -v)
+    raw = np.stack([P[:, 2], -P[:, 0], -P[:, 1], I], axis=1).astype(np.float32)
+    # the inner corners in est_board_corner's order for this rig, in the T_base'd laser frame
+    k = np.arange((W - 1) * (H - 1))[::-1]                               # (the board frame of calc_laser_coor_v1 runs the other way)
+    cb = np.stack([-(W - 2) * side / 2 + side * (k % (W - 1)), -(H - 2) * side / 2 + side * (k // (W - 1)), np.zeros(len(k))], axis=1)
+    corners_cam = cb @ Rb.T + tb
+    T = scan_extrinsic()
+    Pc = corners_cam @ T[:3, :3].T + T[:3, 3]
+    img_norm = Pc[:, :2] / Pc[:, 2:3] + rng.normal(0.0, pix_sigma, (len(k), 2))
+    return raw, img_norm, corners_cam

@@ -169,6 +169,41 @@ int rclc_project_colorize(rclc_ctx* ctx, const rclc_config* cfg, const void* pts
 int rclc_gridfit_multistart(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n,
                             const double* poses, int32_t P, double* cost_out);
 
+/* ---- the per-frame chains on a cloud that is uploaded once and stays in HBM between the operators (csrc/calib.cu) ---- */
+/* the per-cloud body of apps/BoardSegmentation.cpp:45-165: the chessboard's points out of one raw scan (lidar frame, x forward):
+ * PassThrough x in [x_min, x_max] (:48), 8 mm UniformSampling (:58-61), planes peeled off by RANSAC (:64-113), EulerCluster of the
+ * candidate (:116), cut_roi of the raw scan (:118-128), GMM split (:130-137), largest black / white cluster (:140-158).
+ * out_xyzi: room for n float4 {x, y, z, I}; receives the white cluster followed by the black one (:160). *n_out == 0: no plane
+ * qualified. */
+int rclc_segment_board(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double x_min, double x_max,
+                       void* out_xyzi, int64_t* n_out);
+/* est_board_corner (include/pc_process.h:583-646): one board-only cloud (float4 {x, y, z, I}, the T_base'd laser frame) in, the
+ * (W-1) x (H-1) corners in that frame out [nc][3]. The cloud comes back as the reference leaves it (projected onto its plane, moved
+ * into the board frame). T_bl_out (16, may be NULL): the refined board <- laser transform; report may be NULL.
+ * *stage_failed (may be NULL): 0, or the stage that gave up: 1 plane fit, 2 block centroids, 3 board frame, 4 grid fit. */
+int rclc_est_board_corner(rclc_ctx* ctx, const rclc_config* cfg, void* pts_io_xyzi, int64_t n, double* corners_out, double* T_bl_out,
+                          rclc_gridfit_report* report, int32_t* stage_failed);
+/* Stage 1 + stage 2 for F raw scans (apps/BoardSegmentation.cpp:31-165 -> apps/Calibrate.cpp:90-107 -> calib_opt :12-67): every scan
+ * is uploaded once; the frames' chains run concurrently, one host worker (own stream, own scratch) per frame in flight like the
+ * reference's `omp parallel for` over frames; the grid fits of all frames run together (rclc_batch_gridfit_solve); then, when
+ * img_norm and Tcl_io are given, the extrinsic: the PnP start (unless RCLC_CALIB_KEEP_TCL: Tcl_io is the start) and pose_reprj_opt
+ * over the frames that produced corners.
+ *   scans[f]: n_pts[f] records of `stride` bytes, x y z at +0, intensity at +ioff (page-locked {x,y,z,I} records are read in place)
+ *   img_norm [F][nc][2] normalised image corners (Cam.imgPt2norm) in est_board_corner's corner order, or NULL
+ *   corners_out [F][nc][3]; frame_status [F]: 0 ok, 10 no board plane, 21 / 22 / 23 / 24 plane fit / block centroids / board frame /
+ *   grid fit gave up; n_board [F] (may be NULL): points of the segmented board; reports [F] (may be NULL)
+ *   Tcl_io (qx, qy, qz, qw, tx, ty, tz); pose_costs [2] initial / final (may be NULL); pose_iterations (may be NULL)
+ *   stage_ms [4] (may be NULL): host wall time of per-frame chains | grid fit | extrinsic | total */
+#define RCLC_CALIB_KEEP_TCL 1
+int rclc_calibrate_frames(rclc_ctx* ctx, const rclc_config* cfg, const void* const* scans, const int64_t* n_pts, int32_t F, int stride, int ioff,
+                          double x_min, double x_max, const double* img_norm, int32_t flags, double* corners_out, int32_t* frame_status,
+                          int64_t* n_board, rclc_gridfit_report* reports, double* Tcl_io, double* pose_costs, int32_t* pose_iterations,
+                          double* stage_ms);
+/* host workers of rclc_calibrate_frames: 0 = one per host core (divided by LOCAL_WORLD_SIZE), at most one per frame */
+int rclc_ctx_set_calib_workers(rclc_ctx* ctx, int32_t workers);
+/* Eigen::Quaterniond(Matrix3d) as at apps/Calibrate.cpp:61; R row-major, q = (x, y, z, w). Host code. */
+int rclc_quat_from_R(const double R[9], double q_xyzw[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -251,6 +251,48 @@ class Context:
                                          _p(infov)))
         return rgb, pix, infov
 
+    # ---- the per-frame chains on resident clouds (csrc/calib.cu) ----
+    def segment_board(self, cfg, raw, x_min=3.0, x_max=6.0):
+        """apps/BoardSegmentation.cpp:45-165 on one raw scan -> board cloud [m, 4] (white cluster, then black)."""
+        raw, stride, ioff = _cloud(raw)
+        out = np.zeros((len(raw), 4), np.float32); n = C.c_int64()
+        _chk(lib().rclc_segment_board(self.h, C.byref(cfg), _p(raw), stride, ioff, C.c_int64(len(raw)), C.c_double(x_min), C.c_double(x_max),
+                                      _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def est_board_corner(self, cfg, board):
+        """pc_process.h:583-646 on one board-only cloud [n, 4] in the T_base'd laser frame -> (stage_failed, corners, report, cloud as
+        the reference leaves it)."""
+        pts = np.ascontiguousarray(board, np.float32).copy()
+        assert pts.ndim == 2 and pts.shape[1] == 4
+        corners = np.zeros((cfg.n_corners(), 3)); rep = GridfitReport(); st = C.c_int32(); T = np.zeros(16)
+        _chk(lib().rclc_est_board_corner(self.h, C.byref(cfg), _p(pts), C.c_int64(len(pts)), _p(corners), _p(T), C.byref(rep), C.byref(st)))
+        return st.value, corners, rep, pts
+
+    def set_calib_workers(self, n):
+        _chk(lib().rclc_ctx_set_calib_workers(self.h, int(n)))
+
+    def calibrate_frames(self, cfg, scans, img_norm=None, x_min=3.0, x_max=6.0, Tcl0=None):
+        """rclc_calibrate_frames: F raw scans (list of [n, 4] float32 arrays; pinned torch-backed arrays are read in place) ->
+        dict(corners [F, nc, 3], status [F], n_board [F], reports, Tcl [7], pose_costs, pose_iterations, stage_ms [4])."""
+        F = len(scans)
+        scans = [np.ascontiguousarray(s, np.float32) for s in scans]
+        assert all(s.ndim == 2 and s.shape[1] == 4 for s in scans)
+        ptrs = (C.c_void_p * F)(*[s.ctypes.data for s in scans])
+        n_pts = np.array([len(s) for s in scans], np.int64)
+        nc = cfg.n_corners()
+        corners = np.zeros((F, nc, 3)); status = np.zeros(F, np.int32); n_board = np.zeros(F, np.int64)
+        reports = (GridfitReport * F)()
+        Tcl = np.array([0, 0, 0, 1, 0, 0, 0], np.float64) if Tcl0 is None else np.array(Tcl0, np.float64)
+        costs = np.zeros(2); its = C.c_int32(); ms = np.zeros(4)
+        img = None if img_norm is None else np.ascontiguousarray(img_norm, np.float64)
+        flags = 0 if Tcl0 is None else 1
+        _chk(lib().rclc_calibrate_frames(self.h, C.byref(cfg), ptrs, _p(n_pts), F, 16, 12, C.c_double(x_min), C.c_double(x_max), _p(img), flags,
+                                         _p(corners), _p(status), _p(n_board), reports, _p(Tcl) if img is not None else None, _p(costs),
+                                         C.byref(its), _p(ms)))
+        return dict(corners=corners, status=status, n_board=n_board, reports=reports, Tcl=Tcl, pose_costs=costs, pose_iterations=its.value,
+                    stage_ms=ms)
+
 
 class Batch:
     """Frames resident in HBM (rclc_batch_*)."""

@@ -128,6 +128,9 @@ int rclc_ctx_destroy(rclc_ctx* c)
     if (!c) return RCLC_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    rclc::destroy_calib_state(c);
+    for (rclc::Buf& b : c->d_chain) b.release();
+    c->d_boards.release(); c->h_chain.release();
     c->d_pts.release(); c->d_tmp.release(); c->d_tmp2.release(); c->d_out.release(); c->d_flush.release();
     c->h_pin.release(); c->h_pin2.release();
     cudaEventDestroy(c->ev0);

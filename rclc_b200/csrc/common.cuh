@@ -80,7 +80,13 @@ struct rclc_ctx {
     rclc::Buf h_up[2];                                 // pinned double buffer of the cloud uploads
     cudaEvent_t ev_up[2] = {nullptr, nullptr};         // "the copy out of h_up[i] has finished"
     int up_flip = 0;
-    rclc_ctx() { h_pin.pinned = true; h_pin2.pinned = true; h_up[0].pinned = true; h_up[1].pinned = true; }
+    // the calibration chains (calib.cu): clouds that live across operators, the worker contexts of the batched calibration and its
+    // cached grid-fit batch
+    rclc::Buf d_chain[10], d_boards, h_chain;
+    struct rclc_batch* calib_batch = nullptr;
+    void* calib_pool = nullptr;
+    int calib_workers = 0;                             // 0: one per host core (at most one per frame)
+    rclc_ctx() { h_pin.pinned = true; h_pin2.pinned = true; h_up[0].pinned = true; h_up[1].pinned = true; h_chain.pinned = true; }
 };
 
 namespace rclc {
@@ -88,6 +94,7 @@ namespace rclc {
 // Packs a strided host cloud into pinned float4 {x,y,z,I} and uploads it to `dst` (device).
 // `st`: the stream the copy is enqueued on (null: ctx->stream).
 int upload_cloud_f4(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, float4* dst, cudaStream_t st = nullptr);
+void destroy_calib_state(rclc_ctx* ctx);      // calib.cu: the worker pool and the cached batch
 
 // ---- device helpers ----
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }

@@ -18,6 +18,9 @@ namespace rclc {
 // pcl::UniformSampling: *d_idx (ctx scratch) = indices of the kept points in ascending voxel-key order.
 int dev_uniform_sample(rclc_ctx* ctx, const float4* d_pts, int64_t n, double leaf, const int** d_idx, int64_t* n_out);
 
+// d_dst[i] = d_src[d_idx[i]]
+int dev_gather(rclc_ctx* ctx, const float4* d_src, const int* d_idx, int64_t n, float4* d_dst);
+
 // pcl::EuclideanClusterExtraction: d_label[i] (ctx scratch) = rank of the point's cluster (size descending, ties: smallest member
 // index first) or -1; sizes of the ranked clusters on the host.
 struct ClusterSet {

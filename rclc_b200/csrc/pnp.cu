@@ -277,3 +277,29 @@ extern "C" int rclc_pnp_ransac(const double* obj, const double* norm_pts, int64_
     if (n_inliers) *n_inliers = best_cnt;
     return RCLC_OK;
 }
+
+// Eigen::Quaterniond(Matrix3d) (apps/Calibrate.cpp:61): Shepperd's branches as in Eigen/src/Geometry/Quaternion.h. R row-major,
+// q = (x, y, z, w), the storage order of the reference's Tcl (Calibrate.cpp:59-62).
+extern "C" int rclc_quat_from_R(const double R[9], double q_xyzw[4])
+{
+    RCLC_CHECK(R && q_xyzw, RCLC_ERR_INVALID, "null argument");
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0) {
+        double s = std::sqrt(tr + 1.0);
+        q_xyzw[3] = 0.5 * s;
+        s = 0.5 / s;
+        q_xyzw[0] = (R[7] - R[5]) * s; q_xyzw[1] = (R[2] - R[6]) * s; q_xyzw[2] = (R[3] - R[1]) * s;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double s = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        q_xyzw[i] = 0.5 * s;
+        s = 0.5 / s;
+        q_xyzw[3] = (R[3 * k + j] - R[3 * j + k]) * s;
+        q_xyzw[j] = (R[3 * j + i] + R[3 * i + j]) * s;
+        q_xyzw[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+    }
+    return RCLC_OK;
+}

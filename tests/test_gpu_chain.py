@@ -1,0 +1,121 @@
+"""The per-frame chains on resident clouds (csrc/calib.cu) against the CPU oracle's restatement of the same chains
+(oracle/rclc_pipeline.cpp) on raw scans of the synthetic MID-40 rig: BASELINE configs[0].
+
+  rclc_segment_board      apps/BoardSegmentation.cpp:45-165      -> the oracle's points, bit for bit, in the oracle's order
+  rclc_est_board_corner   include/pc_process.h:583-646           -> the oracle's LM trajectory and corners (1 um)
+  rclc_calibrate_frames   both stages for F scans + calib_opt    -> per-frame results equal to the single-frame calls;
+                                                                    extrinsic within 1e-4 rad / 0.1 mm of the oracle's
+"""
+import numpy as np
+import pytest
+
+from rclc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from rclc_b200 import capi
+    with capi.Context(0) as c:
+        yield c
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    from rclc_b200 import capi
+    return capi.config()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import pyoracle
+    return pyoracle
+
+
+def _to_cam(board):
+    return np.c_[board[:, :3] @ synth.T_BASE[:3, :3].T, board[:, 3]].astype(np.float32)
+
+
+@pytest.mark.parametrize("f", [0, 1, 5])
+def test_segment_board_bit_exact(ctx, cfg, oracle, f):
+    raw, _, _ = synth.raw_scan(f)
+    rc, want = oracle.segment_board(oracle.config(), raw)
+    got = ctx.segment_board(cfg, raw)
+    assert rc == 0 and len(want) > 30000
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_segment_board_no_board_and_strided_input(ctx, cfg, oracle):
+    raw, _, _ = synth.raw_scan(2)
+    # PointXYZI layout (32-byte records, intensity at +16)
+    pcl = np.zeros((len(raw), 8), np.float32); pcl[:, :3] = raw[:, :3]; pcl[:, 4] = raw[:, 3]
+    rc, want = oracle.segment_board(oracle.config(), raw)
+    got = ctx.segment_board(cfg, pcl)
+    assert rc == 0 and np.array_equal(got, want)
+    # nothing inside the x range: no plane, empty result (the oracle returns 1)
+    far = raw.copy(); far[:, 0] += 10.0
+    rc, want = oracle.segment_board(oracle.config(), far)
+    assert rc == 1 and len(ctx.segment_board(cfg, far)) == 0
+    # a scene without the board: planes are found, none faces the lidar within reach or the candidate has no cluster
+    rng = np.random.default_rng(3)
+    n = 60000
+    ground = np.c_[rng.uniform(3, 6, n), rng.uniform(-2, 2, n), -1.2 + rng.normal(0, 0.01, n), np.full(n, 40.0)].astype(np.float32)
+    rc, want = oracle.segment_board(oracle.config(), ground)
+    got = ctx.segment_board(cfg, ground)
+    assert (rc == 0) == (len(got) > 0) and (rc != 0 or np.array_equal(got, want))
+
+
+@pytest.mark.parametrize("f", [0, 3, 5])
+def test_est_board_corner_matches_oracle(ctx, cfg, oracle, f):
+    raw, _, truth = synth.raw_scan(f)
+    rc, board = oracle.segment_board(oracle.config(), raw)
+    board = _to_cam(board)
+    rc0, c0, r0, cloud0 = oracle.est_board_corner(oracle.config(), board)
+    st, c1, r1, cloud1 = ctx.est_board_corner(cfg, board)
+    assert rc0 == 0 and st == 0
+    assert np.array_equal(cloud1.view(np.uint32), cloud0.view(np.uint32))          # projected + moved cloud: the same floats
+    assert r1.pose_evals == r0.pose_evals and r1.outer_iterations == r0.outer_iterations
+    assert np.abs(c1 - c0).max() < 1e-6
+    assert np.linalg.norm(c1 - truth, axis=1).max() < 6e-3                          # and they are the board's corners
+
+
+def test_calibrate_frames_equals_single_frame_calls_and_oracle_extrinsic(ctx, cfg, oracle):
+    F = 6
+    ocfg = oracle.config()
+    scans, imgs, truth = zip(*[synth.raw_scan(f) for f in range(F)])
+    out = ctx.calibrate_frames(cfg, list(scans), np.stack(imgs))
+    assert (out["status"] == 0).all()
+    oc = []
+    for f in range(F):
+        board = ctx.segment_board(cfg, scans[f])
+        assert out["n_board"][f] == len(board)
+        st, c1, r1, _ = ctx.est_board_corner(cfg, _to_cam(board))
+        assert st == 0 and np.array_equal(out["corners"][f], c1)                   # batched == single frame, bit for bit
+        assert out["reports"][f].pose_evals == r1.pose_evals
+        rc, ob = oracle.segment_board(ocfg, scans[f])
+        rc, c0, _, _ = oracle.est_board_corner(ocfg, _to_cam(ob))
+        assert rc == 0 and np.abs(c1 - c0).max() < 1e-6
+        oc.append(c0)
+    # the extrinsic: the same PnP start, pose_reprj_opt on the oracle's corners by the oracle
+    rc, T0, _, _, _ = oracle.pose_refine(ocfg, np.stack(oc), np.stack(imgs), out_start(ctx, cfg, np.stack(oc), np.stack(imgs)))
+    T1 = out["Tcl"]
+    q0, q1 = T0[:4] / np.linalg.norm(T0[:4]), T1[:4] / np.linalg.norm(T1[:4])
+    if q0 @ q1 < 0:
+        q1 = -q1
+    assert 2 * np.abs(q0 - q1).max() < 1e-4 and np.abs(T0[4:] - T1[4:]).max() < 1e-4
+    # and it is the rig's extrinsic
+    Tgt = synth.scan_extrinsic()
+    R1 = oracle.quat_to_R([q1[3], q1[0], q1[1], q1[2]])
+    ang = np.arccos(np.clip((np.trace(R1 @ Tgt[:3, :3].T) - 1) / 2, -1, 1))
+    assert ang < 3e-3 and np.abs(T1[4:] - Tgt[:3, 3]).max() < 0.02
+
+
+def out_start(ctx, cfg, corners, imgs):
+    """The PnP start rclc_calibrate_frames uses (apps/Calibrate.cpp:41-62), rebuilt through the same entry points."""
+    from rclc_b200 import capi
+    import ctypes as C
+    R, t, _ = capi.pnp_ransac(corners.reshape(-1, 3), imgs.reshape(-1, 2), 8.0 / (0.5 * (cfg.fx + cfg.fy)))[:3]
+    q = np.zeros(4)
+    capi.lib().rclc_quat_from_R(np.ascontiguousarray(R, np.float64).ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p))
+    return np.r_[q, t]

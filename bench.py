@@ -29,6 +29,13 @@ UNIT = "Mpts·poses/s"
 WORKLOAD = "configs[1]: 20 synthetic Avia/Horizon raster frames x 500k pts, 8x6 board, GMM EM + grid fit"
 
 
+def bench_config(frames_per_gpu, pts):
+    """The same dict on both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "frames_per_gpu": frames_per_gpu, "pts_per_frame": pts,
+            "l2": "steps: working set 2 x %d MB per GPU exceeds the 126 MB L2, no flush between steps; roofline launches: L2 flushed "
+                  "(read of 2 x L2 of foreign data) before each" % (frames_per_gpu * pts * 16 // 2**20)}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -38,6 +45,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--pts", type=int, default=500000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--calib-frames", type=int, default=20)
+    ap.add_argument("--calib-pts", type=int, default=100000)
+    ap.add_argument("--no-calib", action="store_true")
     return ap.parse_args()
 
 
@@ -127,6 +137,72 @@ def cpu_sample_frames(frames, cores):
     return frames[:n]
 
 
+
+# ----------------------------------------------------------------------------------------------------------
+# calibration wall time (the second half of BASELINE.json's metric): stage 1 + stage 2 on 20 raw MID-40 scans
+# ----------------------------------------------------------------------------------------------------------
+CALIB_WORKLOAD = ("configs[0] shape, 20 frames: synthetic MID-40 rosette raw scans x 100k pts (board + ground + wall + clutter) -> "
+                  "BoardSegmentation (apps/BoardSegmentation.cpp:45-165) + est_board_corner (pc_process.h:583-646) per frame, "
+                  "then PnP start + pose_reprj_opt over all frames (Calibrate.cpp:12-67)")
+
+
+def make_scans(n_frames, n_pts, first=0):
+    from rclc_b200 import synth
+    scans, imgs = [], []
+    for f in range(first, first + n_frames):
+        raw, img, _ = synth.raw_scan(f, n_pts)
+        scans.append(raw); imgs.append(img)
+    return scans, np.stack(imgs)
+
+
+def cpu_calibration(scans, imgs, cores, start_fn):
+    """The reference's CPU path through the oracle: `omp parallel for` over frames for both programs (BoardSegmentation.cpp:31-33,
+    Calibrate.cpp:90-92) = a thread per frame here (ctypes releases the GIL), then the single-threaded extrinsic solve from the
+    given start (the reference's start is OpenCV's solvePnPRansac, which the oracle does not restate: its time is left out of
+    the CPU side)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as O
+    from rclc_b200 import synth
+    cfg = O.config()
+
+    def stage1(raw):
+        rc, board = O.segment_board(cfg, raw)
+        return board if rc == 0 else None
+
+    def stage2(board):
+        if board is None:
+            return None
+        b = np.c_[board[:, :3] @ synth.T_BASE[:3, :3].T, board[:, 3]].astype(np.float32)
+        rc, corners, rep, _ = O.est_board_corner(cfg, b)
+        return corners if rc == 0 else None
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        boards = list(ex.map(stage1, scans))
+    t1 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        corners = list(ex.map(stage2, boards))
+    t2 = time.perf_counter()
+    ok = [k for k, c in enumerate(corners) if c is not None]
+    pc = np.stack([corners[k] for k in ok])
+    Tcl_start = start_fn(pc, imgs[ok])                       # not timed
+    t2b = time.perf_counter()
+    rc, Tcl, c0, c1, its = O.pose_refine(cfg, pc, imgs[ok], Tcl_start)
+    t3 = time.perf_counter()
+    return {"stage1_ms": 1e3 * (t1 - t0), "stage2_corners_ms": 1e3 * (t2 - t1), "extrinsic_ms": 1e3 * (t3 - t2b),
+            "total_ms": 1e3 * ((t2 - t0) + (t3 - t2b)), "frames_ok": len(ok), "cores": cores, "kind": "port",
+            "note": "oracle (CPU restatement of the reference path), a thread per frame; the PnP start (OpenCV in the reference) is not timed"}, Tcl, pc
+
+
+def pnp_start(cfg, corners, imgs):
+    import ctypes as C
+    from rclc_b200 import capi
+    R, t, _ = capi.pnp_ransac(np.asarray(corners).reshape(-1, 3), np.asarray(imgs).reshape(-1, 2), 8.0 / (0.5 * (cfg.fx + cfg.fy)))
+    q = np.zeros(4)
+    capi.lib().rclc_quat_from_R(np.ascontiguousarray(R, np.float64).ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p))
+    return np.r_[q, t]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,12 +221,59 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames": args.frames, "pts_per_frame": args.pts},
+            "config": bench_config(args.frames, args.pts),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement (oracle) of the reference path: PCL/Ceres/Eigen are absent, the reference cannot be built"}
+    if not args.no_calib:
+        from rclc_b200 import capi
+        ccfg = capi.config()                                 # (host-side PnP start only; nothing of the library is timed here)
+        scans, imgs = make_scans(args.calib_frames, args.calib_pts)
+        cpu, _, _ = cpu_calibration(scans, imgs, cores, lambda pc, im: pnp_start(ccfg, pc, im))
+        line["calib_wall_ms"] = {"workload": CALIB_WORKLOAD, "frames": args.calib_frames, "pts_per_scan": args.calib_pts, "total": cpu["total_ms"],
+                                 "cpu": cpu}
     print(json.dumps(line), flush=True)
 
+
+
+def calib_leg(args, ctx, cfg, rank, world, barrier, max_over_ranks):
+    """End-to-end calibration wall time through the C ABI with HOST buffers: rclc_calibrate_frames uploads every raw scan once,
+    runs stage 1 + stage 2 and returns corners + extrinsic. Every rank calibrates its own 20 scans (weak scaling, no collective)."""
+    import torch
+    scans, imgs = make_scans(args.calib_frames, args.calib_pts, first=rank * args.calib_frames)
+    pinned = [torch.from_numpy(s).pin_memory() for s in scans]
+    host = [t.numpy() for t in pinned]
+    for _ in range(3):
+        out = ctx.calibrate_frames(cfg, host, imgs)
+    barrier()
+    walls, stages = [], []
+    l0 = ctx.kernel_launches()
+    reps = 10
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = ctx.calibrate_frames(cfg, host, imgs)
+        walls.append((time.perf_counter() - t0) * 1e3)
+        stages.append(out["stage_ms"].copy())
+    launches = (ctx.kernel_launches() - l0) // reps
+    barrier()
+    st = np.median(np.stack(stages), axis=0)
+    total = max_over_ranks(float(np.median(walls)))
+    res = {"workload": CALIB_WORKLOAD, "frames": args.calib_frames * world, "pts_per_scan": args.calib_pts, "total": total,
+           "per_frame_chains": float(st[0]), "grid_fit": float(st[1]), "extrinsic": float(st[2]), "frames_ok": int((out["status"] == 0).sum()),
+           "board_pts_per_frame": int(np.median(out["n_board"])), "pose_iterations": int(out["pose_iterations"]),
+           "h2d_bytes": int(sum(len(s) for s in scans) * 16), "gpu_launches": int(launches),
+           "timing": "host wall clock around rclc_calibrate_frames (pinned host scans in, corners + extrinsic out), median of %d, max over ranks" % reps}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cpu, Tcl_cpu, pc_cpu = cpu_calibration(scans, imgs, cores, lambda pc, im: pnp_start(cfg, pc, im))
+        res["cpu"] = cpu
+        q0, q1 = Tcl_cpu[:4] / np.linalg.norm(Tcl_cpu[:4]), out["Tcl"][:4] / np.linalg.norm(out["Tcl"][:4])
+        if q0 @ q1 < 0:
+            q1 = -q1
+        ok = out["status"] == 0
+        res["vs_cpu_path"] = {"extrinsic_rad": float(2 * np.abs(q0 - q1).max()), "extrinsic_m": float(np.abs(Tcl_cpu[4:] - out["Tcl"][4:]).max()),
+                              "corners_m": float(np.abs(out["corners"][ok] - pc_cpu).max()) if cpu["frames_ok"] == int(ok.sum()) else None}
+    return res
 
 # ----------------------------------------------------------------------------------------------------------
 # our arm
@@ -289,15 +412,15 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": F, "pts_per_frame": args.pts,
-                       "l2": "steps: working set 2 x %d MB per GPU exceeds the 126 MB L2, no flush between steps; roofline launches: "
-                             "L2 flushed before each" % (total_pts * 16 // 2**20)},
+            "config": bench_config(F, args.pts),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": ms_e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "calib_wall_ms": {"grid_fit_plus_gmm_per_step": ms / args.steps, "frames": F * world}}
+            "gmm_plus_grid_fit_ms_per_step": ms / args.steps}
+    if not args.no_calib:
+        line["calib_wall_ms"] = calib_leg(args, ctx, cfg, rank, world, barrier, max_over_ranks)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -5,10 +5,11 @@
 //   * uniform sampling: one hash-table slot per occupied voxel, the winner of a voxel decided by a 64-bit atomicMin over
 //     (float distance to the voxel centre, point index) — the same float expressions as PCL, so the same point wins — and the
 //     kept indices sorted by voxel key (cub radix sort of the survivors);
-//   * clustering: the host kd-tree region growing becomes connected components over a uniform grid of cell = tolerance:
-//     points sorted by cell, a hash table cell -> range, every point tests the points of its 27 neighbour cells with the FLANN
-//     L2_Simple distance and joins them with a lock-free union-find whose roots are the smallest member index. Sizes and the
-//     final ranking (size descending, smallest member first) follow on the few roots.
+//   * clustering: the host kd-tree region growing becomes connected components over a uniform grid of cells of 0.57 tolerance:
+//     a cell's points are within the tolerance of each other by construction, so the union-find runs over CELLS: points sorted
+//     by cell, a hash table cell -> range, every pair of cells within the 5 x 5 x 5 neighbourhood is joined as soon as one point
+//     pair passes FLANN's L2_Simple test; roots are the smallest member index. Sizes and the final ranking (size descending,
+//     smallest member first) follow on the few roots.
 #include "ops_dev.cuh"
 
 #include <algorithm>
@@ -116,7 +117,12 @@ __global__ void __launch_bounds__(256) k_us_collect(const unsigned long long* __
 }
 
 // ---- clustering ----
-struct EcGeom { double inv_cell; long long mb[3]; float r2; };
+// The grid of the clustering: cells of side 0.57 tol, so that two points of one cell are within tol of each other whatever they
+// are (the cell's diagonal is 0.987 tol) — a cell is connected by construction — and a point's neighbours within tol lie in the
+// 5 x 5 x 5 cells around its own. Keys pack the three cell coordinates (biased by 2) into bx + by + bz bits, sized from the cloud's
+// extent, so the radix sort runs over the bits in use only.
+struct EcGeom { double inv_cell; long long mb[3]; float r2; int bx, by, bz; };
+constexpr double kEcCellPerTol = 0.57;
 
 __device__ __forceinline__ bool ec_cell(const EcGeom& g, const float4& p, long long (&c)[3])
 {
@@ -126,19 +132,21 @@ __device__ __forceinline__ bool ec_cell(const EcGeom& g, const float4& p, long l
     c[2] = (long long)floor((double)p.z * g.inv_cell) - g.mb[2];
     return true;
 }
-// 21 bits per axis, offset by one so that the -1 neighbours of cell 0 stay non-negative
-__device__ __forceinline__ unsigned long long ec_pack(long long x, long long y, long long z) { return (unsigned long long)(x + 1) | ((unsigned long long)(y + 1) << 21) | ((unsigned long long)(z + 1) << 42); }
+__device__ __forceinline__ unsigned long long ec_pack(const EcGeom& g, long long x, long long y, long long z)
+{
+    return (unsigned long long)(x + 2) | ((unsigned long long)(y + 2) << g.bx) | ((unsigned long long)(z + 2) << (g.bx + g.by));
+}
 
 __global__ void __launch_bounds__(256) k_ec_keys(const float4* __restrict__ pts, int64_t n, EcGeom g, unsigned long long* __restrict__ keys, int* __restrict__ idx)
 {
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
         long long c[3];
-        keys[i] = ec_cell(g, pts[i], c) ? ec_pack(c[0], c[1], c[2]) : kEmptyKey;      // non-finite points sort to the end
+        keys[i] = ec_cell(g, pts[i], c) ? ec_pack(g, c[0], c[1], c[2]) : kEmptyKey;   // non-finite points sort to the end
         idx[i] = (int)i;
     }
 }
 
-// after the sort: one table entry per occupied cell -> first sorted position; cell_end by the next head
+// after the sort: one table entry per occupied cell -> first sorted position; the cell ends where the key changes
 __global__ void __launch_bounds__(256) k_ec_cells(const unsigned long long* __restrict__ skeys, int64_t n, unsigned long long* __restrict__ tkeys,
                                                   int* __restrict__ tstart, uint32_t cap)
 {
@@ -168,44 +176,69 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b)
     }
 }
 
-__global__ void __launch_bounds__(128) k_ec_union(const float4* __restrict__ pts, const unsigned long long* __restrict__ skeys, const int* __restrict__ sidx,
-                                                  int64_t n, EcGeom g, const unsigned long long* __restrict__ tkeys, const int* __restrict__ tstart,
-                                                  uint32_t cap, int* __restrict__ parent)
+// every point hangs under its cell's first point — the smallest index of the cell, the sort being stable
+__global__ void __launch_bounds__(256) k_ec_attach(const unsigned long long* __restrict__ skeys, const int* __restrict__ sidx, int64_t n,
+                                                   const unsigned long long* __restrict__ tkeys, const int* __restrict__ tstart, uint32_t cap, int* __restrict__ parent)
 {
-    for (int64_t s = blockIdx.x * 128ll + threadIdx.x; s < n; s += gridDim.x * 128ll) {
-        const unsigned long long k0 = skeys[s];
-        if (k0 == kEmptyKey) continue;
-        const int i = sidx[s];
-        const float4 p = pts[i];
-        const long long cx = (long long)(k0 & 0x1fffff) - 1, cy = (long long)((k0 >> 21) & 0x1fffff) - 1, cz = (long long)((k0 >> 42) & 0x1fffff) - 1;
-        for (int dz = -1; dz <= 1; ++dz)
-            for (int dy = -1; dy <= 1; ++dy)
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const unsigned long long k = ec_pack(cx + dx, cy + dy, cz + dz);
-                    const int slot = table_find(tkeys, cap, k);
-                    if (slot < 0) continue;
-                    for (int64_t t = tstart[slot]; t < n && skeys[t] == k; ++t) {
-                        const int j = sidx[t];
-                        if (j >= i) continue;                                        // every pair once
-                        const float4 q = pts[j];
-                        const float ex = __fsub_rn(p.x, q.x), ey = __fsub_rn(p.y, q.y), ez = __fsub_rn(p.z, q.z);
-                        float d = __fmul_rn(ex, ex);                                 // flann L2_Simple, in order
-                        d = __fadd_rn(d, __fmul_rn(ey, ey));
-                        d = __fadd_rn(d, __fmul_rn(ez, ez));
-                        if (d < g.r2) uf_union(parent, i, j);
-                    }
-                }
+    for (int64_t s = blockIdx.x * 256ll + threadIdx.x; s < n; s += gridDim.x * 256ll) {
+        const unsigned long long k = skeys[s];
+        if (k == kEmptyKey) continue;
+        parent[sidx[s]] = sidx[tstart[table_find(tkeys, cap, k)]];
+    }
+}
+
+// Cells are joined pairwise: one thread per (occupied cell A, one of the 62 cell offsets that come after the centre in the
+// 5 x 5 x 5 block, so every unordered pair of cells is looked at once). The pair is joined as soon as ONE point of A and one of
+// B pass FLANN's test (L2_Simple in float, in order; RadiusResultSet: dist < radius^2) — the partition is that of the full
+// radius graph, with a union-find over cells instead of points and a handful of distance tests per pair instead of all of them.
+constexpr int kEcOffsets = 62;
+__global__ void __launch_bounds__(128) k_ec_link(const float4* __restrict__ pts, const unsigned long long* __restrict__ skeys, const int* __restrict__ sidx,
+                                                 int64_t n, EcGeom g, const unsigned long long* __restrict__ tkeys, const int* __restrict__ tstart,
+                                                 uint32_t cap, int* __restrict__ parent)
+{
+    const unsigned long long mx = (1ull << g.bx) - 1, my = (1ull << g.by) - 1, mz = (1ull << g.bz) - 1;
+    for (int64_t t = blockIdx.x * 128ll + threadIdx.x; t < n * kEcOffsets; t += gridDim.x * 128ll) {
+        const int64_t a0 = t / kEcOffsets;
+        const int o = (int)(t - a0 * kEcOffsets) + 63;                                // linear offset index 63 .. 124 (62 is the centre)
+        const unsigned long long kA = skeys[a0];
+        if (kA == kEmptyKey || (a0 > 0 && skeys[a0 - 1] == kA)) continue;             // cell heads only
+        const long long cx = (long long)(kA & mx) - 2, cy = (long long)((kA >> g.bx) & my) - 2, cz = (long long)((kA >> (g.bx + g.by)) & mz) - 2;
+        const long long x = cx + (o % 5 - 2), y = cy + ((o / 5) % 5 - 2), z = cz + (o / 25 - 2);
+        if (x < -2 || y < -2 || z < -2 || (unsigned long long)(x + 2) > mx || (unsigned long long)(y + 2) > my || (unsigned long long)(z + 2) > mz) continue;
+        const unsigned long long kB = ec_pack(g, x, y, z);
+        const int slot = table_find(tkeys, cap, kB);
+        if (slot < 0) continue;
+        const int b0 = tstart[slot];
+        const int ra = sidx[a0], rb = sidx[b0];                                        // the cells' representatives
+        if (uf_find(parent, ra) == uf_find(parent, rb)) continue;                     // joined through other cells already
+        bool hit = false;
+        for (int64_t a = a0; !hit && a < n && skeys[a] == kA; ++a) {
+            const float4 p = pts[sidx[a]];
+            for (int64_t b = b0; b < n && skeys[b] == kB; ++b) {
+                const float4 q = pts[sidx[b]];
+                const float ex = __fsub_rn(p.x, q.x), ey = __fsub_rn(p.y, q.y), ez = __fsub_rn(p.z, q.z);
+                float d = __fmul_rn(ex, ex);                                         // flann L2_Simple, in order
+                d = __fadd_rn(d, __fmul_rn(ey, ey));
+                d = __fadd_rn(d, __fmul_rn(ez, ez));
+                if (d < g.r2) { hit = true; break; }
+            }
+        }
+        if (hit) uf_union(parent, ra, rb);
     }
 }
 
 __global__ void __launch_bounds__(256) k_iota(int* a, int64_t n) { for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) a[i] = (int)i; }
 
-__global__ void __launch_bounds__(256) k_ec_roots(const float4* __restrict__ pts, int64_t n, int* __restrict__ parent, int* __restrict__ size)
+// the root of every point (read-only walk: a compressing find running next to the store of a point's final root could leave that
+// point hanging under an inner node) and the size of every component
+__global__ void __launch_bounds__(256) k_ec_roots(const float4* __restrict__ pts, int64_t n, const int* __restrict__ parent, int* __restrict__ root,
+                                                  int* __restrict__ size)
 {
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
-        if (!finite3(pts[i])) { parent[i] = -1; continue; }
-        const int r = uf_find(parent, (int)i);
-        parent[i] = r;                    // (a concurrent find only ever shortens paths to the same root)
+        if (!finite3(pts[i])) { root[i] = -1; continue; }
+        int r = (int)i;
+        for (int p = parent[r]; p != r; p = parent[r]) r = p;
+        root[i] = r;
         atomicAdd(&size[r], 1);
     }
 }
@@ -227,7 +260,7 @@ __global__ void __launch_bounds__(256) k_ec_set_rank(const int2* __restrict__ ra
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k < n_ranked) rank_of[ranked[k].x] = ranked[k].y;
 }
-__global__ void __launch_bounds__(256) k_ec_labels(const int* __restrict__ root, const int* __restrict__ rank_of, int64_t n, int* __restrict__ label)
+__global__ void __launch_bounds__(256) k_ec_labels(const int* root, const int* __restrict__ rank_of, int64_t n, int* label)      // (in place)
 {
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) { const int r = root[i]; label[i] = r >= 0 ? rank_of[r] : -1; }
 }
@@ -292,7 +325,9 @@ int dev_uniform_sample(rclc_ctx* ctx, const float4* d_pts, int64_t n, double lea
     RCLC_CUDA(cudaMemcpyAsync(h_bb, d_cnt, 4, cudaMemcpyDeviceToHost, st));
     RCLC_CUDA(cudaStreamSynchronize(st));
     const int kept = h_bb[0];
-    RCLC_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, d_ok, d_ok2, d_oi, d_oi2, kept, 0, 64, st));
+    int key_bits = 1;                                                                          // voxel keys are below div0 * div1 * div2: sort those bits only
+    while (key_bits < 64 && (double)(1ull << key_bits) < (double)g.div[0] * (double)g.div[1] * (double)g.div[2]) ++key_bits;
+    RCLC_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, d_ok, d_ok2, d_oi, d_oi2, kept, 0, key_bits, st));
     ctx->launches += 1;
     *n_out = kept;
     *d_idx = d_oi2;
@@ -330,13 +365,18 @@ int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double 
         return RCLC_OK;
     }
     EcGeom g;
-    g.inv_cell = 1.0 / (tol * 1.0001);
+    g.inv_cell = 1.0 / (tol * kEcCellPerTol);
     g.r2 = (float)(tol * tol);
+    int bits[3];
     for (int d = 0; d < 3; ++d) {
         g.mb[d] = (long long)std::floor((double)o2f_h(h_bb[d]) * g.inv_cell);
-        const long long ext = (long long)std::floor((double)o2f_h(h_bb[3 + d]) * g.inv_cell) - g.mb[d] + 3;
-        RCLC_CHECK(ext < (1ll << 21), RCLC_ERR_UNSUPPORTED, "cloud extent / tolerance exceeds 2^21 cells per axis");
+        const long long ext = (long long)std::floor((double)o2f_h(h_bb[3 + d]) * g.inv_cell) - g.mb[d] + 6;      // + the bias of 2 and the two cells beyond
+        bits[d] = 1;
+        while ((1ll << bits[d]) <= ext) ++bits[d];
     }
+    g.bx = bits[0]; g.by = bits[1]; g.bz = bits[2];
+    const int key_bits = g.bx + g.by + g.bz;
+    RCLC_CHECK(key_bits <= 63, RCLC_ERR_UNSUPPORTED, "cloud extent / tolerance exceeds 2^63 cells");
     unsigned long long* d_k = reinterpret_cast<unsigned long long*>(base + o_k);
     unsigned long long* d_k2 = reinterpret_cast<unsigned long long*>(base + o_k2);
     int* d_i = reinterpret_cast<int*>(base + o_i);
@@ -346,18 +386,19 @@ int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double 
     int* d_par = reinterpret_cast<int*>(base + o_par);
     int* d_size = reinterpret_cast<int*>(base + o_size);
     k_ec_keys<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, g, d_k, d_i);
-    RCLC_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, d_k, d_k2, d_i, d_i2, (int)n, 0, 64, st));
+    RCLC_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, d_k, d_k2, d_i, d_i2, (int)n, 0, key_bits, st));     // (the empty key is all ones: it sorts last on any prefix)
     RCLC_CUDA(cudaMemsetAsync(d_tk, 0xff, (size_t)cap * 8, st));
     RCLC_CUDA(cudaMemsetAsync(d_size, 0, (size_t)n * 4, st));
     RCLC_CUDA(cudaMemsetAsync(d_bb, 0, 4, st));                 // (the bounding box is consumed: its first word becomes the root counter)
     k_ec_cells<<<grid_for(n, 256, sms), 256, 0, st>>>(d_k2, n, d_tk, d_ts, cap);
     k_iota<<<grid_for(n, 256, sms), 256, 0, st>>>(d_par, n);
-    k_ec_union<<<grid_for(n, 128, sms), 128, 0, st>>>(d_pts, d_k2, d_i2, n, g, d_tk, d_ts, cap, d_par);
-    k_ec_roots<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, d_par, d_size);
+    k_ec_attach<<<grid_for(n, 256, sms), 256, 0, st>>>(d_k2, d_i2, n, d_tk, d_ts, cap, d_par);
+    k_ec_link<<<grid_for(n * kEcOffsets, 128, sms), 128, 0, st>>>(d_pts, d_k2, d_i2, n, g, d_tk, d_ts, cap, d_par);
+    k_ec_roots<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, d_par, d_label, d_size);
     // the roots (a few, against n points) go to the host for the ranking; the sorted keys are dead by now: their space takes the list
     int2* d_roots = reinterpret_cast<int2*>(d_k);
     k_ec_collect_roots<<<grid_for(n, 256, sms), 256, 0, st>>>(d_size, n, d_roots, d_bb);
-    ctx->launches += 7;
+    ctx->launches += 8;
     RCLC_CUDA(cudaGetLastError());
     RCLC_CUDA(cudaMemcpyAsync(h_bb, d_bb, 4, cudaMemcpyDeviceToHost, st));
     RCLC_CUDA(cudaStreamSynchronize(st));
@@ -375,7 +416,7 @@ int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double 
         RCLC_CUDA(cudaMemcpyAsync(d_roots, h_roots, kept.size() * 8, cudaMemcpyHostToDevice, st));
         k_ec_set_rank<<<(unsigned)((kept.size() + 255) / 256), 256, 0, st>>>(d_roots, (int)kept.size(), d_size);
     }
-    k_ec_labels<<<grid_for(n, 256, sms), 256, 0, st>>>(d_par, d_size, n, d_label);
+    k_ec_labels<<<grid_for(n, 256, sms), 256, 0, st>>>(d_label, d_size, n, d_label);
     ctx->launches += 3;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;

@@ -41,9 +41,10 @@ def _to_cam(board):
 def test_segment_board_bit_exact(ctx, cfg, oracle, f):
     raw, _, _ = synth.raw_scan(f)
     rc, want = oracle.segment_board(oracle.config(), raw)
-    got = ctx.segment_board(cfg, raw)
     assert rc == 0 and len(want) > 30000
-    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    for _ in range(4):                                      # (repeated: the chain is a sequence of racy-by-nature parallel primitives)
+        got = ctx.segment_board(cfg, raw)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
 def test_segment_board_no_board_and_strided_input(ctx, cfg, oracle):

@@ -138,6 +138,7 @@ int rclc_ctx_destroy(rclc_ctx* c)
     cudaEventDestroy(c->evk0);
     cudaEventDestroy(c->evk1);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    if (c->ev_rank) cudaEventDestroy(c->ev_rank);
     for (cudaEvent_t e : c->ev_groups) cudaEventDestroy(e);
     for (cudaStream_t st : c->aux_streams) cudaStreamDestroy(st);
     for (int i = 0; i < 2; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); c->h_up[i].release(); }

@@ -29,6 +29,23 @@
 
 namespace rclc {
 
+#ifdef RCLC_LAB
+// lab build only (-DRCLC_LAB): wall time per stage of the chains, summed over the frames of a call (scripts/chain_timing.py)
+enum LabStage { LS_UPLOAD, LS_ROI_US, LS_PEEL, LS_SEG_CLUSTERS, LS_PLANE, LS_PROJECT_GMM, LS_BLOCKS, LS_FRAME, LS_COUNT };
+static std::atomic<long long> g_lab_ns[LS_COUNT];
+struct LabTimer {
+    int stage; std::chrono::steady_clock::time_point t0;
+    explicit LabTimer(int s) : stage(s), t0(std::chrono::steady_clock::now()) {}
+    void next(int s) { const auto t = std::chrono::steady_clock::now(); g_lab_ns[stage] += std::chrono::duration_cast<std::chrono::nanoseconds>(t - t0).count(); stage = s; t0 = t; }
+    ~LabTimer() { next(stage); }
+};
+#define LAB_TIMER(var, s) LabTimer var(s)
+#define LAB_NEXT(var, s) var.next(s)
+#else
+#define LAB_TIMER(var, s)
+#define LAB_NEXT(var, s)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // small device pieces
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -177,11 +194,12 @@ static int compact_range(rclc_ctx* ctx, const float4* src, int64_t n, const Rang
 }
 
 // EulerCluster (pc_process.h:59-79): the largest cluster (tolerance 3 cm, 500 .. 2.5 M points) of src, in src's order
-static int largest_cluster(rclc_ctx* ctx, const float4* src, int64_t n, float4* dst, int64_t* m)
+static int largest_cluster(rclc_ctx* ctx, const float4* src, int64_t n, float4* dst, int64_t* m, const float* bbox = nullptr)
 {
     *m = 0;
     if (n == 0) return RCLC_OK;
     ClusterSet cs;
+    if (bbox) { cs.have_bbox = true; for (int d = 0; d < 6; ++d) cs.bbox[d] = bbox[d]; }
     RCLC_TRY(dev_euclidean_cluster(ctx, src, n, 0.03, 500, 2500000, &cs));
     if (cs.sizes.empty()) return RCLC_OK;
     auto first = thrust::make_transform_iterator(cs.d_label, IsFirst());
@@ -236,6 +254,7 @@ static int ransac_replay(const std::vector<int32_t>& counts, const std::vector<i
 int seg_board_dev(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_scan, int64_t n, double x_min, double x_max, const float4** d_board, int64_t* m)
 {
     *m = 0; *d_board = nullptr;
+    LAB_TIMER(lab, LS_ROI_US);
     CHAIN_BUF(d_roi, CB_ROI, n);
     int64_t n_roi = 0;
     RCLC_TRY(compact_range(ctx, d_scan, n, field_range(0, (float)x_min, (float)x_max), d_roi, &n_roi));        // :48
@@ -250,6 +269,7 @@ int seg_board_dev(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_scan, i
     RCLC_TRY(dev_uniform_sample(ctx, d_roi, n_roi, (double)0.008f, &d_idx, &n_vox));
     RCLC_TRY(dev_gather(ctx, d_roi, d_idx, n_vox, d_vox_a));
     const size_t pt_size = (size_t)n_vox;
+    LAB_NEXT(lab, LS_PEEL);
     float4 *vox = d_vox_a, *vox_next = d_vox_b;
     // planes are peeled off until 5 % of the points are left (:81-113); the nearest large plane that faces the lidar is the candidate
     const int max_iterations = 800, H = max_iterations + 1;
@@ -298,6 +318,7 @@ int seg_board_dev(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_scan, i
         }
     }
     if (n_target == 0) return RCLC_OK;
+    LAB_NEXT(lab, LS_SEG_CLUSTERS);
     // the candidate's largest cluster gives the ROI box of the raw scan (:116-128)
     CHAIN_BUF(d_tc, CB_TC, n_target);
     int64_t n_tc = 0;
@@ -314,6 +335,7 @@ int seg_board_dev(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_scan, i
     RangePred box;
     box.use = 7;
     for (int d = 0; d < 3; ++d) { box.lo[d] = o2f(h_bb[d]); box.hi[d] = o2f(h_bb[3 + d]); }
+    const float roi_box[6] = {box.lo[0], box.lo[1], box.lo[2], box.hi[0], box.hi[1], box.hi[2]};      // holds every point of the cut scan
     box.lo[3] = box.hi[3] = 0.f;
     CHAIN_BUF(d_roi2, CB_ROI2, n_roi);
     int64_t n_roi2 = 0;
@@ -326,9 +348,9 @@ int seg_board_dev(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_scan, i
     float4* d_side = d_vox_a;                                                                                   // (the peeling buffers are free again)
     int64_t n_side = 0, n_white = 0, n_black = 0;
     RCLC_TRY(compact_range(ctx, d_roi2, n_roi2, field_range(3, (float)thd, 150.f), d_side, &n_side));
-    RCLC_TRY(largest_cluster(ctx, d_side, n_side, d_board_buf, &n_white));
+    RCLC_TRY(largest_cluster(ctx, d_side, n_side, d_board_buf, &n_white, roi_box));
     RCLC_TRY(compact_range(ctx, d_roi2, n_roi2, field_range(3, (float)cfg->noise_reflactivity_thd, (float)thd), d_side, &n_side));
-    RCLC_TRY(largest_cluster(ctx, d_side, n_side, d_board_buf + n_white, &n_black));
+    RCLC_TRY(largest_cluster(ctx, d_side, n_side, d_board_buf + n_white, &n_black, roi_box));
     *m = n_white + n_black;                                                                                     // *final_plane = *white + *black (:160)
     *d_board = d_board_buf;
     return RCLC_OK;
@@ -355,6 +377,8 @@ static int block_centroids_dev(rclc_ctx* ctx, const rclc_config* cfg, const floa
     std::vector<size_t> block_size;
     std::vector<int> block_num_pts;
     std::vector<float> sums;
+    bool have_box = false;
+    float blocks_box[6];                                 // of the first round: the later rounds cluster subsets of it
     for (int round = 0; round < max_rounds; ++round) {
         curr *= cfg->reflactivity_dec_step;
         int64_t kept = 0;
@@ -363,7 +387,9 @@ static int block_centroids_dev(rclc_ctx* ctx, const rclc_config* cfg, const floa
         nb = kept;
         if (nb == 0) return RCLC_OK;
         ClusterSet cs;
+        if (have_box) { cs.have_bbox = true; for (int d = 0; d < 6; ++d) cs.bbox[d] = blocks_box[d]; }
         RCLC_TRY(dev_euclidean_cluster(ctx, blocks, nb, cfg->black_pt_cluster_dst_thd, 3, 25000, &cs));
+        if (!have_box) { have_box = true; for (int d = 0; d < 6; ++d) blocks_box[d] = cs.bbox[d]; }
         const int nc = (int)cs.sizes.size();
         if (nc < block_num) continue;
         // pcl::compute3DCentroid of every cluster: float sums in point order
@@ -419,18 +445,22 @@ int board_frame_dev(rclc_ctx* ctx, const rclc_config* cfg, float4* d_cloud, int6
         const float T[16] = {-1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
         RCLC_TRY(dev_transform(ctx, d_cloud, n, T));
     }
+    LAB_TIMER(lab, LS_PLANE);
     double plane[4];
     int32_t its = 0;
     int64_t used = 0;
     const int rc = dev_plane_fit(ctx, cfg, d_cloud, n, plane, &its, &used);                                     // :598-600
     if (rc == RCLC_ERR_NUMERIC) { *stage = 1; return RCLC_OK; }
     RCLC_TRY(rc);
+    LAB_NEXT(lab, LS_PROJECT_GMM);
     RCLC_TRY(dev_plane_project(ctx, d_cloud, n, plane));                                                        // :601
     double mu[2] = {15, 100}, sigma[2] = {15, 15}, pri[2];
     RCLC_TRY(dev_gmm_fit(ctx, reinterpret_cast<const float*>(d_cloud) + 3, 4, n, cfg->gmm_iters, mu, sigma, pri));     // :604-611
     const double thd = mu[0] + 2.0 * sigma[0];                                                                  // :612
+    LAB_NEXT(lab, LS_BLOCKS);
     std::vector<double> cen;
     RCLC_TRY(block_centroids_dev(ctx, cfg, d_cloud, n, thd, cen, 200));                                         // :614
+    LAB_NEXT(lab, LS_FRAME);
     if ((int)(cen.size() / 3) < cfg->board_width * cfg->board_height / 2) { *stage = 2; return RCLC_OK; }
     if (rclc_calc_laser_coor(cfg, cen.data(), (int32_t)(cen.size() / 3), plane, Tbl) != RCLC_OK) { *stage = 3; return RCLC_OK; }      // :616
     float Tf[16];
@@ -624,7 +654,11 @@ int rclc_calibrate_frames(rclc_ctx* ctx, const rclc_config* cfg, const void* con
                 int rc_buf = RCLC_OK;
                 float4* d_scan = chain_buf(wc, CB_SCAN, n_pts[f], &rc_buf);
                 if (rc_buf != RCLC_OK) return rc_buf;
-                RCLC_TRY(upload_cloud_f4(wc, scans[f], stride, ioff, n_pts[f], d_scan));
+                {
+                    LAB_TIMER(lab_up, LS_UPLOAD);
+                    RCLC_TRY(upload_cloud_f4(wc, scans[f], stride, ioff, n_pts[f], d_scan));
+                    RCLC_CUDA(cudaStreamSynchronize(wc->stream));
+                }
                 const float4* d_board = nullptr;
                 int64_t mb = 0;
                 RCLC_TRY(seg_board_dev(wc, cfg, d_scan, n_pts[f], x_min, x_max, &d_board, &mb));
@@ -653,6 +687,14 @@ int rclc_calibrate_frames(rclc_ctx* ctx, const rclc_config* cfg, const void* con
             return rcs[(size_t)f];
         }
     const auto t1 = std::chrono::steady_clock::now();
+#ifdef RCLC_LAB
+    {
+        const char* names[LS_COUNT] = {"upload", "roi+us", "peel", "seg clusters+gmm", "plane fit", "project+gmm", "block centroids", "board frame+move"};
+        fprintf(stderr, "[rclc lab] %d frames, %d workers, chains %.2f ms wall; per frame (ms):", F, W, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        for (int k = 0; k < LS_COUNT; ++k) fprintf(stderr, " %s %.3f", names[k], g_lab_ns[k].exchange(0) * 1e-6 / F);
+        fprintf(stderr, "\n");
+    }
+#endif
     // ---- opt_grid_fitting for every frame that came through, together ----
     std::vector<int> ok_frames;
     int64_t max_m = 0;

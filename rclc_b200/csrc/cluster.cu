@@ -137,10 +137,12 @@ __device__ __forceinline__ unsigned long long ec_pack(const EcGeom& g, long long
     return (unsigned long long)(x + 2) | ((unsigned long long)(y + 2) << g.bx) | ((unsigned long long)(z + 2) << (g.bx + g.by));
 }
 
-__global__ void __launch_bounds__(256) k_ec_keys(const float4* __restrict__ pts, int64_t n, EcGeom g, unsigned long long* __restrict__ keys, int* __restrict__ idx)
+__global__ void __launch_bounds__(256) k_ec_keys(const float4* __restrict__ pts, int64_t n, EcGeom g, unsigned long long* __restrict__ keys, int* __restrict__ idx,
+                                                 int* __restrict__ parent)
 {
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) {
         long long c[3];
+        parent[i] = (int)i;
         keys[i] = ec_cell(g, pts[i], c) ? ec_pack(g, c[0], c[1], c[2]) : kEmptyKey;   // non-finite points sort to the end
         idx[i] = (int)i;
     }
@@ -178,8 +180,10 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b)
 
 // every point hangs under its cell's first point — the smallest index of the cell, the sort being stable
 __global__ void __launch_bounds__(256) k_ec_attach(const unsigned long long* __restrict__ skeys, const int* __restrict__ sidx, int64_t n,
-                                                   const unsigned long long* __restrict__ tkeys, const int* __restrict__ tstart, uint32_t cap, int* __restrict__ parent)
+                                                   const unsigned long long* __restrict__ tkeys, const int* __restrict__ tstart, uint32_t cap, int* __restrict__ parent,
+                                                   int* __restrict__ root_counter)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) root_counter[0] = 0;       // (the list of roots starts empty; its space was the sort's input until now)
     for (int64_t s = blockIdx.x * 256ll + threadIdx.x; s < n; s += gridDim.x * 256ll) {
         const unsigned long long k = skeys[s];
         if (k == kEmptyKey) continue;
@@ -341,7 +345,7 @@ int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double 
     size_t temp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, (int)n, 0, 64, st);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t o_bb = 0, o_k = 256, o_k2 = o_k + al((size_t)n * 8), o_i = o_k2 + al((size_t)n * 8), o_i2 = o_i + al((size_t)n * 4), o_tk = o_i2 + al((size_t)n * 4),
+    const size_t o_bb = 0, o_k = 256, o_k2 = o_k + al((size_t)(n + 1) * 8), o_i = o_k2 + al((size_t)n * 8), o_i2 = o_i + al((size_t)n * 4), o_tk = o_i2 + al((size_t)n * 4),
                  o_ts = o_tk + (size_t)cap * 8, o_par = o_ts + (size_t)cap * 4, o_size = o_par + al((size_t)n * 4), o_lab = o_size + al((size_t)n * 4),
                  o_tmp = o_lab + al((size_t)n * 4);
     RCLC_TRY(ctx->d_tmp.reserve(o_tmp + temp_bytes + 256));
@@ -351,15 +355,20 @@ int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double 
     const int sms = ctx->sm_count;
     out->d_label = d_label;
     out->sizes.clear();
-    k_bbox_init<<<1, 32, 0, st>>>(d_bb);
-    k_bbox<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, d_bb);
-    ctx->launches += 2;
-    RCLC_TRY(ctx->h_pin2.reserve((size_t)n * 8 + 64));
-    int* h_bb = ctx->h_pin2.as<int>();
-    RCLC_CUDA(cudaMemcpyAsync(h_bb, d_bb, 24, cudaMemcpyDeviceToHost, st));
-    RCLC_CUDA(cudaStreamSynchronize(st));
-    auto o2f_h = [](int i) { const int v = i >= 0 ? i : i ^ 0x7fffffff; float f; std::memcpy(&f, &v, 4); return f; };
-    if (o2f_h(h_bb[0]) > o2f_h(h_bb[3])) {                                                    // no finite point
+    constexpr int kRootsFirst = 2047;                                                         // roots that come back with the count in one copy
+    RCLC_TRY(ctx->h_pin2.reserve(std::max<size_t>((size_t)(n + 1) * 8, (size_t)(kRootsFirst + 1) * 8) + 64));
+    if (!out->have_bbox) {
+        k_bbox_init<<<1, 32, 0, st>>>(d_bb);
+        k_bbox<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, d_bb);
+        ctx->launches += 2;
+        int* h_bb = ctx->h_pin2.as<int>();
+        RCLC_CUDA(cudaMemcpyAsync(h_bb, d_bb, 24, cudaMemcpyDeviceToHost, st));
+        RCLC_CUDA(cudaStreamSynchronize(st));
+        auto o2f_h = [](int i) { const int v = i >= 0 ? i : i ^ 0x7fffffff; float f; std::memcpy(&f, &v, 4); return f; };
+        for (int d = 0; d < 6; ++d) out->bbox[d] = o2f_h(h_bb[d]);
+        out->have_bbox = true;
+    }
+    if (out->bbox[0] > out->bbox[3]) {                                                        // no finite point
         k_fill_int<<<grid_for(n, 256, sms), 256, 0, st>>>(d_label, n, -1);
         ctx->launches += 1;
         return RCLC_OK;
@@ -369,8 +378,8 @@ int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double 
     g.r2 = (float)(tol * tol);
     int bits[3];
     for (int d = 0; d < 3; ++d) {
-        g.mb[d] = (long long)std::floor((double)o2f_h(h_bb[d]) * g.inv_cell);
-        const long long ext = (long long)std::floor((double)o2f_h(h_bb[3 + d]) * g.inv_cell) - g.mb[d] + 6;      // + the bias of 2 and the two cells beyond
+        g.mb[d] = (long long)std::floor((double)out->bbox[d] * g.inv_cell);
+        const long long ext = (long long)std::floor((double)out->bbox[3 + d] * g.inv_cell) - g.mb[d] + 6;      // + the bias of 2 and the two cells beyond
         bits[d] = 1;
         while ((1ll << bits[d]) <= ext) ++bits[d];
     }
@@ -385,35 +394,44 @@ int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double 
     int* d_ts = reinterpret_cast<int*>(base + o_ts);
     int* d_par = reinterpret_cast<int*>(base + o_par);
     int* d_size = reinterpret_cast<int*>(base + o_size);
-    k_ec_keys<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, g, d_k, d_i);
+    // the roots (a few, against n points) go to the host for the ranking: slot 0 of the list is its counter, and the list takes
+    // the space of the unsorted keys, which are dead after the sort
+    int2* d_roots = reinterpret_cast<int2*>(d_k);
+    k_ec_keys<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, g, d_k, d_i, d_par);
     RCLC_CUDA(cub::DeviceRadixSort::SortPairs(base + o_tmp, temp_bytes, d_k, d_k2, d_i, d_i2, (int)n, 0, key_bits, st));     // (the empty key is all ones: it sorts last on any prefix)
     RCLC_CUDA(cudaMemsetAsync(d_tk, 0xff, (size_t)cap * 8, st));
     RCLC_CUDA(cudaMemsetAsync(d_size, 0, (size_t)n * 4, st));
-    RCLC_CUDA(cudaMemsetAsync(d_bb, 0, 4, st));                 // (the bounding box is consumed: its first word becomes the root counter)
     k_ec_cells<<<grid_for(n, 256, sms), 256, 0, st>>>(d_k2, n, d_tk, d_ts, cap);
-    k_iota<<<grid_for(n, 256, sms), 256, 0, st>>>(d_par, n);
-    k_ec_attach<<<grid_for(n, 256, sms), 256, 0, st>>>(d_k2, d_i2, n, d_tk, d_ts, cap, d_par);
+    k_ec_attach<<<grid_for(n, 256, sms), 256, 0, st>>>(d_k2, d_i2, n, d_tk, d_ts, cap, d_par, reinterpret_cast<int*>(d_roots));
     k_ec_link<<<grid_for(n * kEcOffsets, 128, sms), 128, 0, st>>>(d_pts, d_k2, d_i2, n, g, d_tk, d_ts, cap, d_par);
     k_ec_roots<<<grid_for(n, 256, sms), 256, 0, st>>>(d_pts, n, d_par, d_label, d_size);
-    // the roots (a few, against n points) go to the host for the ranking; the sorted keys are dead by now: their space takes the list
-    int2* d_roots = reinterpret_cast<int2*>(d_k);
-    k_ec_collect_roots<<<grid_for(n, 256, sms), 256, 0, st>>>(d_size, n, d_roots, d_bb);
-    ctx->launches += 8;
+    k_ec_collect_roots<<<grid_for(n, 256, sms), 256, 0, st>>>(d_size, n, d_roots + 1, reinterpret_cast<int*>(d_roots));
+    ctx->launches += 7;
     RCLC_CUDA(cudaGetLastError());
-    RCLC_CUDA(cudaMemcpyAsync(h_bb, d_bb, 4, cudaMemcpyDeviceToHost, st));
+    int2* h_list = reinterpret_cast<int2*>(ctx->h_pin2.as<char>() + 64);
+    const size_t first = (size_t)std::min<int64_t>(n, kRootsFirst) + 1;
+    RCLC_CUDA(cudaMemcpyAsync(h_list, d_roots, first * 8, cudaMemcpyDeviceToHost, st));
     RCLC_CUDA(cudaStreamSynchronize(st));
-    const int n_roots = h_bb[0];
-    int2* h_roots = reinterpret_cast<int2*>(ctx->h_pin2.as<char>() + 64);
-    RCLC_CUDA(cudaMemcpyAsync(h_roots, d_roots, (size_t)n_roots * 8, cudaMemcpyDeviceToHost, st));
-    RCLC_CUDA(cudaStreamSynchronize(st));
+    const int n_roots = h_list[0].x;
+    if ((size_t)n_roots + 1 > first) {
+        RCLC_CUDA(cudaMemcpyAsync(h_list + first, d_roots + first, ((size_t)n_roots + 1 - first) * 8, cudaMemcpyDeviceToHost, st));
+        RCLC_CUDA(cudaStreamSynchronize(st));
+    }
+    const int2* h_roots = h_list + 1;
     std::vector<int2> kept;
     for (int k = 0; k < n_roots; ++k) if (h_roots[k].y >= min_size && h_roots[k].y <= max_size) kept.push_back(h_roots[k]);
     std::sort(kept.begin(), kept.end(), [](const int2& a, const int2& b) { return a.y != b.y ? a.y > b.y : a.x < b.x; });
-    for (size_t k = 0; k < kept.size(); ++k) { out->sizes.push_back(kept[k].y); h_roots[k] = make_int2(kept[k].x, (int)k); }
-    // rank of every root (the size array is dead: it becomes the root -> rank table), then of every point
+    // rank of every root (the size array is dead: it becomes the root -> rank table), then of every point. The list goes up
+    // from its own page-locked buffer: nobody waits for that copy, and the next operator is free to reuse the read-back buffer.
     k_fill_int<<<grid_for(n, 256, sms), 256, 0, st>>>(d_size, n, -1);
     if (!kept.empty()) {
-        RCLC_CUDA(cudaMemcpyAsync(d_roots, h_roots, kept.size() * 8, cudaMemcpyHostToDevice, st));
+        RCLC_TRY(ctx->h_pin.reserve(kept.size() * 8 + 64));
+        if (!ctx->ev_rank) RCLC_CUDA(cudaEventCreateWithFlags(&ctx->ev_rank, cudaEventDisableTiming));
+        RCLC_CUDA(cudaEventSynchronize(ctx->ev_rank));                                        // the previous list has left the buffer
+        int2* h_rank = ctx->h_pin.as<int2>();
+        for (size_t k = 0; k < kept.size(); ++k) { out->sizes.push_back(kept[k].y); h_rank[k] = make_int2(kept[k].x, (int)k); }
+        RCLC_CUDA(cudaMemcpyAsync(d_roots, h_rank, kept.size() * 8, cudaMemcpyHostToDevice, st));
+        RCLC_CUDA(cudaEventRecord(ctx->ev_rank, st));
         k_ec_set_rank<<<(unsigned)((kept.size() + 255) / 256), 256, 0, st>>>(d_roots, (int)kept.size(), d_size);
     }
     k_ec_labels<<<grid_for(n, 256, sms), 256, 0, st>>>(d_label, d_size, n, d_label);

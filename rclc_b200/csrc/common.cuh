@@ -74,6 +74,7 @@ struct rclc_ctx {
     int solve_groups = 10;                             // independent frame groups (streams) of the grid-fit solve
     std::vector<cudaStream_t> aux_streams;             // extra streams of the grouped grid-fit solve
     cudaEvent_t ev_sync = nullptr;
+    cudaEvent_t ev_rank = nullptr;                     // "the cluster-rank list has left h_pin" (cluster.cu)
     std::vector<cudaEvent_t> ev_groups;                // one per solve group: "this group's last batch of rounds has finished"
     rclc::Buf d_pts, d_tmp, d_tmp2, d_out, d_flush;   // device scratch
     rclc::Buf h_pin, h_pin2;                           // pinned staging

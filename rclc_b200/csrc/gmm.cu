@@ -8,6 +8,10 @@
 #include "gridfit.cuh"
 #include "ops_dev.cuh"
 
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
 namespace rclc {
 
 constexpr int kGmmThreads = 256;
@@ -115,6 +119,121 @@ __global__ void __launch_bounds__(kGmmThreads) k_gmm_pass(GmmView v)
     }
 }
 
+// The shape for the clouds of the calibration chain (tens of thousands of points): the WHOLE fit in one launch on a thread-block
+// cluster. A thread keeps its points — and, up to kGmmCache of them, the posteriors of the current iteration — in registers, so the
+// cloud is read once and the second pass of an iteration (the variance about the new mean, GMMFit.cpp:79-85) costs no exp and no
+// division. The partial sums of a pass are exchanged through distributed shared memory and added in rank order by every CTA:
+// all CTAs hold the same state, nothing has to be published. Four cluster barriers per EM iteration.
+constexpr int kGmmCluster = 8;
+constexpr int kGmmCache = 24;
+constexpr int64_t kGmmClusterMaxPts = 200000;
+
+__device__ __forceinline__ void gmm_cluster_sum(cg::cluster_group& cluster, double (&a)[4], double (*s_red)[4], double* s_part, double* s_tot)
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = warp_sum(a[q]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) for (int q = 0; q < 4; ++q) s_red[warp][q] = a[q];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int w = 0; w < kGmmThreads / 32; ++w) t += s_red[w][threadIdx.x];
+        s_part[threadIdx.x] = t;
+    }
+    cluster.sync();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int r = 0; r < kGmmCluster; ++r) t += cluster.map_shared_rank(s_part, r)[threadIdx.x];
+        s_tot[threadIdx.x] = t;
+    }
+    cluster.sync();                                   // the partial sums are read: the next pass may overwrite them (and s_tot is visible)
+}
+
+template <bool CACHE>
+__global__ void __cluster_dims__(kGmmCluster, 1, 1) __launch_bounds__(kGmmThreads)
+k_gmm_fit_cluster(const float* __restrict__ x, int elem_stride, int64_t n, int iters, double mu0, double mu1, double sg0, double sg1, GmmState* __restrict__ out)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double s_par[12], s_red[kGmmThreads / 32][4], s_part[4], s_tot[4];
+    __shared__ GmmState s_st;
+    if (threadIdx.x == 0) {
+        s_st.mu[0] = mu0; s_st.mu[1] = mu1; s_st.sigma[0] = sg0; s_st.sigma[1] = sg1; s_st.prior[0] = 0.5; s_st.prior[1] = 0.5;
+        s_st.mu_new[0] = s_st.mu_new[1] = s_st.denom[0] = s_st.denom[1] = 0.0; s_st.counter = 0; s_st.pad = 0;
+    }
+    const int64_t stride = (int64_t)kGmmCluster * kGmmThreads, first = (int64_t)cluster.block_rank() * kGmmThreads + threadIdx.x;
+    const int mine = first < n ? (int)((n - first + stride - 1) / stride) : 0;
+    float xs[CACHE ? kGmmCache : 1];
+    double p0s[CACHE ? kGmmCache : 1], p1s[CACHE ? kGmmCache : 1];
+    if (CACHE) {
+#pragma unroll
+        for (int k = 0; k < kGmmCache; ++k) xs[k] = k < mine ? __ldg(x + (first + k * stride) * elem_stride) : 0.f;
+    }
+    for (int it = 0; it < iters; ++it) {
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const int k = threadIdx.x;
+            const double sg = s_st.sigma[k];
+            s_par[k] = s_st.mu[k];
+            s_par[2 + k] = __ddiv_rn(-1.0, __dmul_rn(2.0, __dmul_rn(sg, sg)));                 // -1.0 / (2*sigma_sqr)
+            s_par[4 + k] = __ddiv_rn(1.0, __dmul_rn(sg, sqrt(2.0 * 3.14159265358979323846)));  // 1/(sigma*sqrt(2 pi))
+            s_par[6 + k] = s_st.prior[k];
+        }
+        __syncthreads();
+        double a[4] = {0, 0, 0, 0};
+        if (CACHE) {
+#pragma unroll
+            for (int k = 0; k < kGmmCache; ++k)
+                if (k < mine) {
+                    const double xi = (double)xs[k];
+                    posterior(xi, s_par, s_par + 2, s_par + 4, s_par + 6, p0s[k], p1s[k]);
+                    a[0] += p0s[k]; a[1] += p1s[k];
+                    a[2] += __dmul_rn(p0s[k], xi); a[3] += __dmul_rn(p1s[k], xi);
+                }
+        } else {
+            for (int64_t i = first; i < n; i += stride) {
+                const double xi = (double)__ldg(x + i * elem_stride);
+                double p0, p1;
+                posterior(xi, s_par, s_par + 2, s_par + 4, s_par + 6, p0, p1);
+                a[0] += p0; a[1] += p1;
+                a[2] += __dmul_rn(p0, xi); a[3] += __dmul_rn(p1, xi);
+            }
+        }
+        gmm_cluster_sum(cluster, a, s_red, s_part, s_tot);
+        if (threadIdx.x < 2) { s_st.denom[threadIdx.x] = s_tot[threadIdx.x]; s_st.mu_new[threadIdx.x] = s_tot[2 + threadIdx.x] / s_tot[threadIdx.x]; }      // GMMFit.cpp:75-79
+        __syncthreads();
+        const double m0 = s_st.mu_new[0], m1 = s_st.mu_new[1];
+        a[0] = a[1] = a[2] = a[3] = 0;
+        if (CACHE) {
+#pragma unroll
+            for (int k = 0; k < kGmmCache; ++k)
+                if (k < mine) {
+                    const double xi = (double)xs[k];
+                    const double e0 = __dsub_rn(xi, m0), e1 = __dsub_rn(xi, m1);
+                    a[0] += __dmul_rn(p0s[k], __dmul_rn(e0, e0));
+                    a[1] += __dmul_rn(p1s[k], __dmul_rn(e1, e1));
+                }
+        } else {
+            for (int64_t i = first; i < n; i += stride) {
+                const double xi = (double)__ldg(x + i * elem_stride);
+                double p0, p1;
+                posterior(xi, s_par, s_par + 2, s_par + 4, s_par + 6, p0, p1);
+                const double e0 = __dsub_rn(xi, m0), e1 = __dsub_rn(xi, m1);
+                a[0] += __dmul_rn(p0, __dmul_rn(e0, e0));
+                a[1] += __dmul_rn(p1, __dmul_rn(e1, e1));
+            }
+        }
+        gmm_cluster_sum(cluster, a, s_red, s_part, s_tot);
+        if (threadIdx.x < 2) {
+            const int k = threadIdx.x;
+            s_st.mu[k] = s_st.mu_new[k];
+            s_st.sigma[k] = sqrt(s_tot[k] / s_st.denom[k]);                                      // :85-92
+            s_st.prior[k] = s_st.denom[k] / double(n);                                           // :98-101
+        }
+    }
+    __syncthreads();
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) *out = s_st;
+}
+
 // intensity plane of the resident float4 clouds: the 20 EM passes then read 4 B per point from a 40 MB array that stays in L2,
 // instead of striding through 16 B records in DRAM
 __global__ void __launch_bounds__(256) k_pack_intensity(const float4* __restrict__ cloud, int64_t frame_stride, const int64_t* __restrict__ n_pts,
@@ -169,6 +288,22 @@ static int gmm_solve(rclc_ctx* ctx, const float* d_x, int64_t frame_stride, int 
 
 int dev_gmm_fit(rclc_ctx* ctx, const float* d_x, int elem_stride, int64_t n, int iters, double* mu_io, double* sigma_io, double* priors_out)
 {
+    if (n > 0 && n <= kGmmClusterMaxPts) {
+        RCLC_TRY(ctx->d_out.reserve(sizeof(GmmState) + 256));
+        RCLC_TRY(ctx->h_pin2.reserve(sizeof(GmmState) + 64));
+        GmmState* d_st = ctx->d_out.as<GmmState>();
+        GmmState* h = ctx->h_pin2.as<GmmState>();
+        if (n <= (int64_t)kGmmCache * kGmmCluster * kGmmThreads)
+            k_gmm_fit_cluster<true><<<kGmmCluster, kGmmThreads, 0, ctx->stream>>>(d_x, elem_stride, n, iters, mu_io[0], mu_io[1], sigma_io[0], sigma_io[1], d_st);
+        else
+            k_gmm_fit_cluster<false><<<kGmmCluster, kGmmThreads, 0, ctx->stream>>>(d_x, elem_stride, n, iters, mu_io[0], mu_io[1], sigma_io[0], sigma_io[1], d_st);
+        ctx->launches += 1;
+        RCLC_CUDA(cudaGetLastError());
+        RCLC_CUDA(cudaMemcpyAsync(h, d_st, sizeof(GmmState), cudaMemcpyDeviceToHost, ctx->stream));
+        RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 2; ++k) { mu_io[k] = h->mu[k]; sigma_io[k] = h->sigma[k]; if (priors_out) priors_out[k] = h->prior[k]; }
+        return RCLC_OK;
+    }
     // the point count lives next to the solver state (gmm_solve reserves d_out first; the count goes behind everything it uses)
     const size_t o_n = sizeof(GmmState) + 256 + (size_t)kGmmMaxCtas * 4 * 8 + 512;
     RCLC_TRY(ctx->d_out.reserve(o_n + 64));
@@ -198,12 +333,8 @@ int rclc_gmm_fit_1d(rclc_ctx* ctx, const void* intensity, int stride, int64_t n,
     const char* src = static_cast<const char*>(intensity);
     if (stride == 4) std::memcpy(hp, src, (size_t)n * 4);
     else for (int64_t i = 0; i < n; ++i) std::memcpy(hp + i, src + i * (int64_t)stride, 4);
-    int64_t* h_n = reinterpret_cast<int64_t*>(hp + ((n + 1) & ~(int64_t)1));
-    *h_n = n;
-    char* dbase = static_cast<char*>(ctx->d_pts.p);
-    RCLC_CUDA(cudaMemcpyAsync(dbase, hp, (size_t)n * 4 + 16, cudaMemcpyHostToDevice, ctx->stream));
-    const int64_t* d_n = reinterpret_cast<const int64_t*>(dbase + ((n + 1) & ~(int64_t)1) * 4);
-    return gmm_solve(ctx, reinterpret_cast<const float*>(dbase), 0, 1, d_n, 1, n, iters, mu_io, sigma_io, priors_out);
+    RCLC_CUDA(cudaMemcpyAsync(ctx->d_pts.p, hp, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return dev_gmm_fit(ctx, ctx->d_pts.as<float>(), 1, n, iters, mu_io, sigma_io, priors_out);
 }
 
 int rclc_batch_gmm_fit(rclc_batch* b, double* mu_io, double* sigma_io, double* priors_out)

@@ -26,6 +26,10 @@ int dev_gather(rclc_ctx* ctx, const float4* d_src, const int* d_idx, int64_t n, 
 struct ClusterSet {
     const int* d_label = nullptr;
     std::vector<int> sizes;
+    // in: a box that holds every finite point, when the caller knows one (saves the bounding-box pass and its read-back);
+    // out: the box that was used. Any such box gives the same partition: it only anchors the cell grid.
+    bool have_bbox = false;
+    float bbox[6] = {0, 0, 0, 0, 0, 0};
 };
 int dev_euclidean_cluster(rclc_ctx* ctx, const float4* d_pts, int64_t n, double tol, int64_t min_size, int64_t max_size, ClusterSet* out);
 

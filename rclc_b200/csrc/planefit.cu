@@ -11,6 +11,9 @@
 #include "ops_dev.cuh"
 
 #include <cfloat>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace rclc {
 
@@ -169,21 +172,14 @@ __device__ void plane_lm_advance(PlaneLm& s, const PlaneEval& e, double ftol, in
     s.phase = 3;
 }
 
-// One evaluation: cost + normal equations at st->eval_x over the points with intensity >= thd; the last CTA adds the per-CTA
-// partial sums (integers: any order) and advances the LM state.
-__global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restrict__ pts, int64_t n, double thd, double huber_a, double ftol, int max_iters,
-                                                           PlaneLm* __restrict__ st, unsigned long long* __restrict__ partials)
+// The terms of the points i = first, first + stride, ... of one evaluation at (a, b, c, d), added to the caller's exact sums.
+__device__ __forceinline__ void plane_accumulate(const float4* __restrict__ pts, int64_t n, int64_t first, int64_t stride, const double* x, double thd,
+                                                 double huber_a, Fix128 (&acc)[kPfSums], unsigned long long& cnt, bool& bad)
 {
-    if (st->phase == 3) return;
-    const xd a{st->eval_x[0]}, b{st->eval_x[1]}, c{st->eval_x[2]}, d{st->eval_x[3]};
+    const xd a{x[0]}, b{x[1]}, c{x[2]}, d{x[3]};
     const xd nn = (a * a + b * b) + c * c, nrm = xsqrt(nn), den = nn * nrm;
     const xd ha{huber_a}, hb = ha * ha;
-    Fix128 acc[kPfSums];
-#pragma unroll
-    for (int k = 0; k < kPfSums; ++k) { acc[k].hi = 0; acc[k].lo = 0; }
-    unsigned long long cnt = 0;
-    bool bad = false;
-    for (int64_t i = blockIdx.x * (int64_t)kPfThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kPfThreads) {
+    for (int64_t i = first; i < n; i += stride) {
         const float4 p = __ldg(pts + i);
         if ((double)p.w < thd) continue;                                   // opt_plane_param.hpp:56 (float < double)
         const xd X{(double)p.x}, Y{(double)p.y}, Z{(double)p.z};
@@ -214,11 +210,15 @@ __global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restr
         for (int u = 0; u < 4; ++u) fix128_add_double(acc[11 + u], (j[u] * r).v);
         ++cnt;
     }
-    __shared__ unsigned long long s_red[kPfThreads / 32][kPfWords];
-    __shared__ int s_bad, s_last;
-    if (threadIdx.x == 0) s_bad = 0;
+}
+
+// The CTA's share of the sums: warp shuffles, then the warps' partials through shared memory into out[kPfWords] (shared or global).
+__device__ __forceinline__ void plane_cta_fold(Fix128 (&acc)[kPfSums], unsigned long long cnt, bool bad, unsigned long long (*s_red)[kPfWords], int* s_bad,
+                                               unsigned long long* out)
+{
+    if (threadIdx.x == 0) *s_bad = 0;
     __syncthreads();
-    if (bad) s_bad = 1;
+    if (bad) *s_bad = 1;
 #pragma unroll
     for (int k = 0; k < kPfSums; ++k) fix128_warp_sum(acc[k]);
 #pragma unroll
@@ -228,19 +228,36 @@ __global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restr
         s_red[threadIdx.x >> 5][2 * kPfSums] = cnt;
     }
     __syncthreads();
-    unsigned long long* mine = partials + (size_t)blockIdx.x * kPfWords;
     if (threadIdx.x < kPfSums) {
         Fix128 t;
         t.hi = 0; t.lo = 0;
         for (int w = 0; w < kPfThreads / 32; ++w) fix128_add(t, (long long)s_red[w][2 * threadIdx.x], s_red[w][2 * threadIdx.x + 1]);
-        mine[2 * threadIdx.x] = (unsigned long long)t.hi;
-        mine[2 * threadIdx.x + 1] = t.lo;
+        out[2 * threadIdx.x] = (unsigned long long)t.hi;
+        out[2 * threadIdx.x + 1] = t.lo;
     } else if (threadIdx.x == kPfSums) {
         unsigned long long t = 0;
         for (int w = 0; w < kPfThreads / 32; ++w) t += s_red[w][2 * kPfSums];
-        mine[2 * kPfSums] = t;
-        mine[2 * kPfSums + 1] = s_bad ? 1ull : 0ull;
+        out[2 * kPfSums] = t;
+        out[2 * kPfSums + 1] = *s_bad ? 1ull : 0ull;
     }
+}
+
+// One evaluation: cost + normal equations at st->eval_x over the points with intensity >= thd; the last CTA adds the per-CTA
+// partial sums (integers: any order) and advances the LM state. The shape for large clouds: one launch per evaluation.
+__global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restrict__ pts, int64_t n, double thd, double huber_a, double ftol, int max_iters,
+                                                           PlaneLm* __restrict__ st, unsigned long long* __restrict__ partials)
+{
+    if (st->phase == 3) return;
+    Fix128 acc[kPfSums];
+#pragma unroll
+    for (int k = 0; k < kPfSums; ++k) { acc[k].hi = 0; acc[k].lo = 0; }
+    unsigned long long cnt = 0;
+    bool bad = false;
+    const double x[4] = {st->eval_x[0], st->eval_x[1], st->eval_x[2], st->eval_x[3]};
+    plane_accumulate(pts, n, blockIdx.x * (int64_t)kPfThreads + threadIdx.x, (int64_t)gridDim.x * kPfThreads, x, thd, huber_a, acc, cnt, bad);
+    __shared__ unsigned long long s_red[kPfThreads / 32][kPfWords];
+    __shared__ int s_bad, s_last;
+    plane_cta_fold(acc, cnt, bad, s_red, &s_bad, partials + (size_t)blockIdx.x * kPfWords);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->counter, 1u) == gridDim.x - 1);
@@ -275,14 +292,77 @@ __global__ void __launch_bounds__(kPfThreads) k_plane_eval(const float4* __restr
     }
 }
 
-__global__ void k_plane_init(PlaneLm* st)
+// The shape for the clouds of the calibration chain (tens of thousands of points): the WHOLE solve in one launch on a thread-block
+// cluster. Every CTA sums its share of an evaluation, the partial sums are exchanged through distributed shared memory, and
+// every CTA adds them up (integers: the same total everywhere) and advances its own copy of the LM state — identical inputs,
+// identical code, so no decision has to be published. Two cluster barriers per evaluation. The sums being exact, the solve
+// returns the bits of the one-launch-per-evaluation shape.
+__device__ void plane_init_state(PlaneLm& s);
+constexpr int kPfCluster = 8;
+constexpr int64_t kPfClusterMaxPts = 200000;      // above: one launch per evaluation over up to 592 CTAs
+__global__ void __cluster_dims__(kPfCluster, 1, 1) __launch_bounds__(kPfThreads)
+k_plane_fit_cluster(const float4* __restrict__ pts, int64_t n, double thd, double huber_a, double ftol, int max_iters, PlaneLm* __restrict__ st_out)
 {
-    PlaneLm s;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    __shared__ unsigned long long s_red[kPfThreads / 32][kPfWords];
+    __shared__ unsigned long long s_part[kPfWords];
+    __shared__ double s_tot[kPfSums];
+    __shared__ unsigned long long s_cnt, s_anybad;
+    __shared__ int s_bad;
+    __shared__ PlaneLm s_lm;
+    if (threadIdx.x == 0) plane_init_state(s_lm);
+    __syncthreads();
+    while (s_lm.phase != 3) {
+        Fix128 acc[kPfSums];
+#pragma unroll
+        for (int k = 0; k < kPfSums; ++k) { acc[k].hi = 0; acc[k].lo = 0; }
+        unsigned long long cnt = 0;
+        bool bad = false;
+        const double x[4] = {s_lm.eval_x[0], s_lm.eval_x[1], s_lm.eval_x[2], s_lm.eval_x[3]};
+        plane_accumulate(pts, n, rank * (int64_t)kPfThreads + threadIdx.x, (int64_t)kPfCluster * kPfThreads, x, thd, huber_a, acc, cnt, bad);
+        plane_cta_fold(acc, cnt, bad, s_red, &s_bad, s_part);
+        cluster.sync();                                                        // every CTA's partial sums are in its shared memory
+        if (threadIdx.x < kPfSums) {
+            Fix128 t;
+            t.hi = 0; t.lo = 0;
+            for (int r = 0; r < kPfCluster; ++r) {
+                const unsigned long long* rp = cluster.map_shared_rank(s_part, r);
+                fix128_add(t, (long long)rp[2 * threadIdx.x], rp[2 * threadIdx.x + 1]);
+            }
+            s_tot[threadIdx.x] = fix128_to_double(t.hi, t.lo);
+        } else if (threadIdx.x == kPfSums) {
+            unsigned long long t = 0, bd = 0;
+            for (int r = 0; r < kPfCluster; ++r) { const unsigned long long* rp = cluster.map_shared_rank(s_part, r); t += rp[2 * kPfSums]; bd |= rp[2 * kPfSums + 1]; }
+            s_cnt = t; s_anybad = bd;
+        }
+        cluster.sync();                                                        // all reads of the partial sums are done: the next evaluation may overwrite them
+        if (threadIdx.x == 0) {
+            PlaneEval e;
+            e.cost = s_tot[0];
+            for (int k = 0; k < 10; ++k) e.A[k] = s_tot[1 + k];
+            for (int k = 0; k < 4; ++k) e.g[k] = s_tot[11 + k];
+            e.valid = s_anybad == 0ull;
+            s_lm.n_used = (long long)s_cnt;
+            plane_lm_advance(s_lm, e, ftol, max_iters);
+        }
+        __syncthreads();
+    }
+    if (rank == 0 && threadIdx.x == 0) *st_out = s_lm;
+}
+
+__device__ void plane_init_state(PlaneLm& s)
+{
     memset(&s, 0, sizeof(s));
     const double x0[4] = {0.1, 0.1, 1.0, 1.0};                                 // opt_plane_param.hpp:49
     for (int k = 0; k < 4; ++k) { s.x[k] = x0[k]; s.eval_x[k] = x0[k]; s.best[k] = x0[k]; }
     s.phase = 1;
     s.termination = 1;
+}
+__global__ void k_plane_init(PlaneLm* st)
+{
+    PlaneLm s;
+    plane_init_state(s);
     *st = s;
 }
 
@@ -292,26 +372,35 @@ int dev_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_pts, in
     RCLC_TRY(ctx->d_tmp.reserve(sizeof(PlaneLm) + 256 + (size_t)kPfMaxCtas * kPfWords * 8));
     PlaneLm* d_st = ctx->d_tmp.as<PlaneLm>();
     unsigned long long* d_part = reinterpret_cast<unsigned long long*>(ctx->d_tmp.as<char>() + ((sizeof(PlaneLm) + 255) & ~(size_t)255));
-    k_plane_init<<<1, 1, 0, ctx->stream>>>(d_st);
-    ctx->launches += 1;
     // Ceres defaults for this solve (opt_plane_param.hpp:75-77 sets only DENSE_QR): 50 iterations, function_tolerance 1e-6.
     const int max_iters = 50;
     const double ftol = 1e-6;
     RCLC_TRY(ctx->h_pin2.reserve(sizeof(PlaneLm)));
     PlaneLm* h = ctx->h_pin2.as<PlaneLm>();
-    const int max_launches = 2 * (max_iters + 8) + 8;
-    int launched = 0;
-    for (;;) {
-        for (int r = 0; r < 8; ++r) {
-            k_plane_eval<<<ctas, kPfThreads, 0, ctx->stream>>>(d_pts, n, cfg->plane_reflactive_thd, cfg->plane_huber_a, ftol, max_iters, d_st, d_part);
-            ctx->launches += 1;
-        }
-        launched += 8;
+    if (n <= kPfClusterMaxPts) {
+        k_plane_fit_cluster<<<kPfCluster, kPfThreads, 0, ctx->stream>>>(d_pts, n, cfg->plane_reflactive_thd, cfg->plane_huber_a, ftol, max_iters, d_st);
+        ctx->launches += 1;
         RCLC_CUDA(cudaGetLastError());
         RCLC_CUDA(cudaMemcpyAsync(h, d_st, sizeof(PlaneLm), cudaMemcpyDeviceToHost, ctx->stream));
         RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (h->phase == 3) break;
-        RCLC_CHECK(launched < max_launches, RCLC_ERR_NUMERIC, "plane-fit state machine did not terminate");
+        RCLC_CHECK(h->phase == 3, RCLC_ERR_NUMERIC, "plane-fit state machine did not terminate");
+    } else {
+        k_plane_init<<<1, 1, 0, ctx->stream>>>(d_st);
+        ctx->launches += 1;
+        const int max_launches = 2 * (max_iters + 8) + 8;
+        int launched = 0;
+        for (;;) {
+            for (int r = 0; r < 8; ++r) {
+                k_plane_eval<<<ctas, kPfThreads, 0, ctx->stream>>>(d_pts, n, cfg->plane_reflactive_thd, cfg->plane_huber_a, ftol, max_iters, d_st, d_part);
+                ctx->launches += 1;
+            }
+            launched += 8;
+            RCLC_CUDA(cudaGetLastError());
+            RCLC_CUDA(cudaMemcpyAsync(h, d_st, sizeof(PlaneLm), cudaMemcpyDeviceToHost, ctx->stream));
+            RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (h->phase == 3) break;
+            RCLC_CHECK(launched < max_launches, RCLC_ERR_NUMERIC, "plane-fit state machine did not terminate");
+        }
     }
     // solver.cc: the user state is only overwritten when the solution is usable
     const double x0[4] = {0.1, 0.1, 1.0, 1.0};

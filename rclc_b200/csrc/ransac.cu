@@ -26,10 +26,11 @@ __device__ __forceinline__ float plane_dot(float a, float b, float c, float d, f
 
 // sac_model_plane.hpp computeModelCoefficients
 __global__ void k_planes(const float4* __restrict__ pts, const int* __restrict__ trip, int H, float4* __restrict__ planes,
-                         int* __restrict__ valid)
+                         int* __restrict__ valid, int* __restrict__ counts)
 {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
+    counts[h] = 0;                                              // (k_score, next on the stream, adds into it)
     const float4 p0 = pts[trip[3 * h]], p1 = pts[trip[3 * h + 1]], p2 = pts[trip[3 * h + 2]];
     const float a0 = __fsub_rn(p1.x, p0.x), a1 = __fsub_rn(p1.y, p0.y), a2 = __fsub_rn(p1.z, p0.z);
     const float b0 = __fsub_rn(p2.x, p0.x), b1 = __fsub_rn(p2.y, p0.y), b2 = __fsub_rn(p2.z, p0.z);
@@ -48,12 +49,12 @@ __global__ void k_planes(const float4* __restrict__ pts, const int* __restrict__
 
 // countWithinDistance for all hypotheses: a CTA stages a tile of points in shared memory (SoA, broadcast
 // reads), each thread owns hypotheses h = tid, tid+T, ... and keeps their coefficients in registers.
-__global__ void __launch_bounds__(kScoreThreads) k_score(const float4* __restrict__ pts, int64_t n, const float4* __restrict__ planes,
+__global__ void __launch_bounds__(kScoreThreads) k_score(const float4* __restrict__ pts, int64_t n, int tile, const float4* __restrict__ planes,
                                                          const int* __restrict__ valid, int H, float thr_le, int* __restrict__ counts)
 {
     __shared__ float sx[kScoreTile], sy[kScoreTile], sz[kScoreTile];
-    const int64_t base = (int64_t)blockIdx.x * kScoreTile;
-    const int m = (int)min((int64_t)kScoreTile, n - base);
+    const int64_t base = (int64_t)blockIdx.x * tile;                          // tile <= kScoreTile: small clouds take small tiles (more CTAs, shorter loops)
+    const int m = (int)min((int64_t)tile, n - base);
     for (int i = threadIdx.x; i < m; i += kScoreThreads) {
         const float4 q = __ldg(pts + base + i);
         sx[i] = q.x; sy[i] = q.y; sz[i] = q.z;
@@ -165,16 +166,22 @@ int dev_ransac_score(rclc_ctx* ctx, const float4* d_pts, int64_t n, const int32_
     float4* d_planes = reinterpret_cast<float4*>(base + o_pl);
     int* d_valid = reinterpret_cast<int*>(base + o_va);
     int* d_counts = reinterpret_cast<int*>(base + o_cn);
-    RCLC_CUDA(cudaMemcpyAsync(d_trip, triplets, (size_t)H * 12, cudaMemcpyHostToDevice, ctx->stream));
-    RCLC_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)H * 4, ctx->stream));
-    k_planes<<<(H + 127) / 128, 128, 0, ctx->stream>>>(d_pts, d_trip, H, d_planes, d_valid);
-    k_score<<<(unsigned)((n + kScoreTile - 1) / kScoreTile), kScoreThreads, 0, ctx->stream>>>(d_pts, n, d_planes, d_valid, H, threshold_le(thr), d_counts);
+    // page-locked staging both ways: a copy to or from pageable memory goes through the driver's own staging buffer under its lock,
+    // which serialises the frames of the batched chain
+    RCLC_TRY(ctx->h_pin2.reserve(total + 256));
+    char* hb = ctx->h_pin2.as<char>();
+    std::memcpy(hb, triplets, (size_t)H * 12);
+    RCLC_CUDA(cudaMemcpyAsync(d_trip, hb, (size_t)H * 12, cudaMemcpyHostToDevice, ctx->stream));
+    const int tile = n <= 262144 ? 512 : kScoreTile;
+    k_planes<<<(H + 127) / 128, 128, 0, ctx->stream>>>(d_pts, d_trip, H, d_planes, d_valid, d_counts);
+    k_score<<<(unsigned)((n + tile - 1) / tile), kScoreThreads, 0, ctx->stream>>>(d_pts, n, tile, d_planes, d_valid, H, threshold_le(thr), d_counts);
     ctx->launches += 2;
     RCLC_CUDA(cudaGetLastError());
-    if (planes_out) RCLC_CUDA(cudaMemcpyAsync(planes_out, d_planes, (size_t)H * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    if (valid_out) RCLC_CUDA(cudaMemcpyAsync(valid_out, d_valid, (size_t)H * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    RCLC_CUDA(cudaMemcpyAsync(counts_out, d_counts, (size_t)H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RCLC_CUDA(cudaMemcpyAsync(hb + o_pl, base + o_pl, total - o_pl, cudaMemcpyDeviceToHost, ctx->stream));      // planes | valid | counts
     RCLC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (planes_out) std::memcpy(planes_out, hb + o_pl, (size_t)H * 16);
+    if (valid_out) std::memcpy(valid_out, hb + o_va, (size_t)H * 4);
+    std::memcpy(counts_out, hb + o_cn, (size_t)H * 4);
     return RCLC_OK;
 }
 

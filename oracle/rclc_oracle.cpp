@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <random>
@@ -847,6 +849,7 @@ int orc_pose_refine(const rclc_config* cfg, const double* pc_corners, const doub
     opt.max_num_iterations = cfg->pose_max_lm_iters;
     opt.function_tolerance = cfg->pose_function_tol;
     const orc::LMSummary sum = orc::lm_minimize(P, opt, Tcl_io);
+    if (std::getenv("RCLC_ORC_DEBUG")) std::fprintf(stderr, "[orc] pose_refine: %d iterations, %d successful steps, %d cost evaluations\n", sum.num_iterations, sum.num_successful_steps, sum.num_cost_evals);
     if (initial_cost) *initial_cost = sum.initial_cost;
     if (final_cost) *final_cost = sum.final_cost;
     if (iterations) *iterations = sum.num_iterations;

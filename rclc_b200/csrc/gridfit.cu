@@ -94,8 +94,8 @@ static int build_geom(const rclc_config& c, HostGeom& hg)
     // Lattice: all targets sit on sites of the half-square lattice (unit g = side/2); its cells are the coarse sort key.
     g.g = c.gride_side_length / 2.0;
     g.inv_g = 1.0 / g.g;
-    // The lattice box keeps a margin of 2 cells around the outermost targets; points outside it are dropped, which is exact
-    // only while no dropped point can be a kd-tree neighbour of a target (board_fitting_cost.h:273).
+    // The lattice box keeps a margin of 2 cells around the outermost targets; points outside it are filed in the border cells
+    // (fine_of), so the window of an outer target reaches them once they have moved into its neighbourhood (board_fitting_cost.h:273).
     RCLC_CHECK(neighbour_radius < 1.98 * g.g, RCLC_ERR_UNSUPPORTED, "neighbour_radius_rate must be < 0.99 (lattice margin)");
     RCLC_CHECK(c.uniform_sampling_radius == 0.0, RCLC_ERR_UNSUPPORTED,
                "uniform_sampling_radius != 0 is not implemented on device (shipped config uses 0)");
@@ -144,16 +144,22 @@ static PoseCoef host_pose_coef(const double pose[3])
 // Device helpers
 // ------------------------------------------------------------------------------------------------
 // Sort key of a point: lattice cell (the unit the candidate tables are built on) and, inside it, one of sub x sub
-// sub-cells, so that consecutive points of a cell's segment are spatial neighbours. Returns cell * sub^2 + sub-cell,
-// or -1 outside the lattice.
+// sub-cells, so that consecutive points of a cell's segment are spatial neighbours. Returns cell * sub^2 + sub-cell.
+// A point outside the lattice box (the outermost targets plus two cells: holder, surroundings in the board's plane) is
+// kept in the BORDER cell next to it, with its own coordinates: the reference rebuilds its kd-tree on the full cloud in
+// every outer iteration (opt_grid_fitting.h:75-76, 107), so a point that starts out of every target's reach can come
+// into reach once the accumulated motion exceeds the 2 cm of slack between the box and the neighbour radius. The border
+// cell is the right place for it: a target's cell window is its disc widened by the motion since the sort, clamped to
+// the grid, so it covers the border cell of every outside point that has moved into the disc; row boxes come from the
+// coordinates themselves. -1 only for non-finite coordinates.
 __device__ __forceinline__ int fine_of(const GridGeom& g, float x, float y)
 {
     // (fp32: a point within rounding of a sub-cell border may fall on either side — every use of the cell tolerates that:
     //  row boxes come from the coordinates themselves, candidate windows have 2 cm of slack)
+    if (!(isfinite(x) && isfinite(y))) return -1;
     const float sc = (float)(g.inv_g * g.sub);
-    const int fi = __float2int_rd(x * sc) - g.i0 * g.sub;
-    const int fj = __float2int_rd(y * sc) - g.j0 * g.sub;
-    if (fi < 0 || fj < 0 || fi >= g.ncx * g.sub || fj >= g.ncy * g.sub) return -1;
+    const int fi = min(max(__float2int_rd(x * sc) - g.i0 * g.sub, 0), g.ncx * g.sub - 1);
+    const int fj = min(max(__float2int_rd(y * sc) - g.j0 * g.sub, 0), g.ncy * g.sub - 1);
     const int ci = fi / g.sub, cj = fj / g.sub;
     return (cj * g.ncx + ci) * (g.sub * g.sub) + (fj - cj * g.sub) * g.sub + (fi - ci * g.sub);
 }

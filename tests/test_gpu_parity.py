@@ -442,3 +442,32 @@ def test_fast_sweep_equals_exact_sweep(capi, ctx, cfg, oracle, ocfg, monkeypatch
     for poses, acc in tables["0"][:6]:
         for f in (0, 3):
             assert np.array_equal(acc[f], oracle.gridfit_eval(ocfg, frames[f], poses[f], want_acc=True)[2])
+
+
+def test_gridfit_points_beyond_the_lattice_box_come_into_reach(ctx, cfg, oracle, ocfg):
+    """The reference rebuilds its kd-tree on the FULL cloud in every outer iteration (opt_grid_fitting.h:75-76, 107): points
+    that start beyond the lattice box (board holder, surroundings in the board's plane) become neighbours of the outer targets
+    once the accumulated motion exceeds the 2 cm between the box and the neighbour radius. They are kept in the border cells
+    of the sort, so the solve sees them exactly when the oracle does: same accumulators, same LM path, same corners."""
+    rng = np.random.default_rng(41)
+    x0, x1, y0, y1 = synth.board_extent(8, 6, 0.1)
+    for pert in ((0.034, -0.031, 0.9), (-0.04, 0.035, -1.2)):
+        board = synth.board_frame_cloud(120000, 77, pert=pert, pattern="rosette")
+        # a frame of surroundings on the plane, out to 30 cm beyond the board, mid reflectance
+        m = 60000
+        u = rng.uniform(x0 - 0.3, x1 + 0.3, m); v = rng.uniform(y0 - 0.3, y1 + 0.3, m)
+        keep = (u < x0) | (u > x1) | (v < y0) | (v > y1)
+        th = np.deg2rad(pert[2]); c, s = np.cos(th), np.sin(th)
+        ring = np.stack([c * u + s * v - pert[0], -s * u + c * v - pert[1], rng.normal(0, 0.002, m), rng.uniform(30, 90, m)], axis=1)[keep]
+        pts = np.concatenate([board, ring.astype(np.float32)])[rng.permutation(len(board) + int(keep.sum()))]
+        # accumulators at a pose that pulls outside points into the outer discs
+        for pose in ((0.0, 0.0, 0.0), (pert[0], pert[1], pert[2]), (0.05, -0.045, 1.5)):
+            _, _, a1 = ctx.gridfit_eval(cfg, pts, pose, want_acc=True)
+            _, _, a0 = oracle.gridfit_eval(ocfg, pts, pose, want_acc=True)
+            assert np.array_equal(a0, a1), pose
+        c1, r1 = ctx.gridfit_solve(cfg, pts)
+        rc, c0, r0, _ = oracle.gridfit_solve(ocfg, pts)
+        assert rc == 0 and r1.status == 0
+        assert r1.pose_evals == r0.pose_evals and r1.outer_iterations == r0.outer_iterations
+        assert np.abs(c1 - c0).max() < 1e-6
+        assert r1.outer_iterations >= 2                    # the cloud was moved at least once: the motion is what brings them in

@@ -161,6 +161,12 @@ int rclc_pose_eval(rclc_ctx* ctx, const double* pc_corners, const double* img_no
 int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_corners, const double* img_norm,
                      int32_t F, int32_t C, double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations);
 
+/* Test hooks of the pose refine (set per context, never read from the environment): shape 0 = automatic (a thread-block cluster from
+ * 512 corner observations up), 1 = one CTA, 2 = the cluster at any size — both shapes return the same bits; cluster_debug 1 = whole-frame
+ * evaluation on the cluster, 2 = the one-CTA reduction on rank 0; eval_split 1 = rclc_pose_eval through the cluster's per-corner /
+ * per-frame split. tests/test_gpu_parity.py uses them to prove the bit-identity of the shapes. */
+int rclc_ctx_set_pose_test_hooks(rclc_ctx* ctx, int32_t shape, int32_t cluster_debug, int32_t eval_split);
+
 /* ---- colourise loop (Calibrate.cpp:134-148, PinholeCam.h:93-110) ---- */
 int rclc_project_colorize(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int64_t n,
                           const float T_cl[16], const uint8_t* bgr, uint8_t* rgb_out, int32_t* pix_out, uint8_t* infov_out);
@@ -203,6 +209,28 @@ int rclc_calibrate_frames(rclc_ctx* ctx, const rclc_config* cfg, const void* con
 int rclc_ctx_set_calib_workers(rclc_ctx* ctx, int32_t workers);
 /* Eigen::Quaterniond(Matrix3d) as at apps/Calibrate.cpp:61; R row-major, q = (x, y, z, w). Host code. */
 int rclc_quat_from_R(const double R[9], double q_xyzw[4]);
+
+/* ---- multi-GPU exchanges (csrc/comm.cu): NCCL called from C++ on the context's stream; one process (one rclc_ctx) per GPU ----
+ * NCCL is loaded at run time (libnccl.so.2, or the copy the process already holds); RCLC_ERR_UNSUPPORTED if there is none. */
+typedef struct rclc_comm rclc_comm;
+#define RCLC_COMM_ID_BYTES 128
+/* rank 0 creates the id and hands it to the other ranks by any host means (MPI, a file, torch.distributed's store) */
+int rclc_comm_get_unique_id(void* id_out_128);
+int rclc_comm_create(rclc_ctx* ctx, const void* id_128, int32_t rank, int32_t world, rclc_comm** out);
+int rclc_comm_destroy(rclc_comm* comm);
+int64_t rclc_comm_collectives(rclc_comm* comm);         /* NCCL collectives issued so far */
+/* calib_opt with the frames sharded over the ranks (apps/Calibrate.cpp:90-107 -> :12-67, include/opt/opt_reprj_calib.h:21-66):
+ * every rank passes ITS frames' corners [F_local][C][3] and normalised image points [F_local][C][2] (F_local may differ between
+ * ranks, and may be 0); ONE all-gather of C * 5 doubles per frame, then every rank runs the same deterministic solve over all
+ * frames in rank-major order: the same bits on every rank, and the bits of rclc_pose_refine on the concatenated input.
+ * Collective: every rank of the communicator must call it. */
+int rclc_pose_refine_sharded(rclc_comm* comm, const rclc_config* cfg, const double* pc_local, const double* img_local, int32_t F_local, int32_t C,
+                             double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations, int32_t* F_total_out);
+/* ONE frame's points split across ranks (include/opt/board_fitting_cost.h:211-235): every rank holds a share of the points of
+ * each frame of its batch (same frames, same poses on all ranks); between rclc_batch_sweep and rclc_batch_read_eval this adds the
+ * ranks' accumulator tables (82 x 16 doubles per frame). The accumulators are exact sums, so the result equals the unsplit
+ * sweep bit for bit. Collective. */
+int rclc_batch_allreduce_acc(rclc_batch* b, rclc_comm* comm);
 
 #ifdef __cplusplus
 }

@@ -269,6 +269,9 @@ class Context:
         _chk(lib().rclc_est_board_corner(self.h, C.byref(cfg), _p(pts), C.c_int64(len(pts)), _p(corners), _p(T), C.byref(rep), C.byref(st)))
         return st.value, corners, rep, pts
 
+    def set_pose_test_hooks(self, shape=0, cluster_debug=0, eval_split=0):
+        _chk(lib().rclc_ctx_set_pose_test_hooks(self.h, int(shape), int(cluster_debug), int(eval_split)))
+
     def set_calib_workers(self, n):
         _chk(lib().rclc_ctx_set_calib_workers(self.h, int(n)))
 
@@ -292,6 +295,46 @@ class Context:
                                          C.byref(its), _p(ms)))
         return dict(corners=corners, status=status, n_board=n_board, reports=reports, Tcl=Tcl, pose_costs=costs, pose_iterations=its.value,
                     stage_ms=ms)
+
+
+class Comm:
+    """rclc_comm: NCCL communicator of the library (one per context / GPU)."""
+
+    def __init__(self, ctx: Context, unique_id: bytes, rank: int, world: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = C.c_void_p()
+        assert len(unique_id) == 128
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        _chk(lib().rclc_comm_create(ctx.h, buf, int(rank), int(world), C.byref(self.h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_char * 128)()
+        _chk(lib().rclc_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def close(self):
+        if self.h:
+            lib().rclc_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def collectives(self):
+        lib().rclc_comm_collectives.restype = C.c_int64
+        return lib().rclc_comm_collectives(self.h)
+
+    def pose_refine_sharded(self, cfg, pc_local, img_local, Tcl):
+        pc = np.ascontiguousarray(pc_local, np.float64); img = np.ascontiguousarray(img_local, np.float64)
+        F = pc.shape[0] if pc.size else 0
+        Cn = pc.shape[1] if pc.size else cfg.n_corners()
+        Tcl = np.array(Tcl, np.float64); c0 = C.c_double(); c1 = C.c_double(); it = C.c_int32(); ft = C.c_int32()
+        rc = lib().rclc_pose_refine_sharded(self.h, C.byref(cfg), _p(pc) if F else None, _p(img) if F else None, F, Cn, _p(Tcl), C.byref(c0),
+                                            C.byref(c1), C.byref(it), C.byref(ft))
+        if rc not in (0, 4):
+            _chk(rc)
+        return rc, Tcl, c0.value, c1.value, it.value, ft.value
+
+    def allreduce_acc(self, batch):
+        _chk(lib().rclc_batch_allreduce_acc(batch.h, self.h))
 
 
 class Batch:

@@ -86,6 +86,7 @@ struct rclc_ctx {
     rclc::Buf d_chain[10], d_boards, h_chain;
     struct rclc_batch* calib_batch = nullptr;
     void* calib_pool = nullptr;
+    int pose_shape = 0, pose_debug = 0, pose_eval_split = 0;      // rclc_ctx_set_pose_test_hooks
     int calib_workers = 0;                             // 0: one per host core (at most one per frame)
     rclc_ctx() { h_pin.pinned = true; h_pin2.pinned = true; h_up[0].pinned = true; h_up[1].pinned = true; h_chain.pinned = true; }
 };

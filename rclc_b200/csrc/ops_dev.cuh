@@ -46,6 +46,10 @@ int dev_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const float4* d_pts, in
 // GMMFit::fit_1d on n floats `elem_stride` floats apart
 int dev_gmm_fit(rclc_ctx* ctx, const float* d_x, int elem_stride, int64_t n, int iters, double* mu_io, double* sigma_io, double* priors_out);
 
+// pose_reprj_opt with corners [F][C][3], image points [F][C][2] and the start (7 doubles) on the device
+int pose_refine_dev(rclc_ctx* ctx, const rclc_config* cfg, const double* d_pc, const double* d_img, int32_t F, int32_t C, const double* d_T, double* Tcl_io,
+                    double* initial_cost, double* final_cost, int32_t* iterations);
+
 int dev_plane_project(rclc_ctx* ctx, float4* d_pts, int64_t n, const double plane[4]);
 int dev_transform(rclc_ctx* ctx, float4* d_pts, int64_t n, const float T[16]);
 

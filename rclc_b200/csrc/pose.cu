@@ -14,7 +14,7 @@
 // factors in corner order and rank 0 reduces the frames in the one-CTA kernel's order, so both shapes return the same bits
 // (tests/test_gpu_parity.py::test_pose_refine_cluster_equals_one_cta). That matters because this solve wanders for its whole
 // 1000-iteration budget around a non-smooth minimum and the capped iterate depends on the last bit of every sum.
-#include "common.cuh"
+#include "ops_dev.cuh"
 
 #include <cfloat>
 #include <cstdlib>
@@ -608,8 +608,7 @@ static int upload_pose_inputs(rclc_ctx* ctx, const double* pc, const double* img
 static int launch_pose_cluster(rclc_ctx* ctx, const double* pc, const double* img, int F, int C, double huber_a, double ftol, int max_iters,
                                const double* T0, PoseOut* out)
 {
-    const char* dm = std::getenv("RCLC_POSE_CLUSTER_DEBUG");
-    const int mode = dm ? std::atoi(dm) : 0;
+    const int mode = ctx->pose_debug;                 // test hook (rclc_ctx_set_pose_test_hooks): 0 in production
     for (int n_cta : {16, 8}) {
         const int S = kPoseThreads / n_cta;
         const size_t dyn = ((size_t)kCornerVals * S * C + (size_t)kSvStride * 30) * sizeof(double);
@@ -648,8 +647,7 @@ int rclc_pose_eval(rclc_ctx* ctx, const double* pc_corners, const double* img_no
     RCLC_TRY(ctx->d_out.reserve((size_t)F * 7 * 8));
     double* d_res = ctx->d_out.as<double>();
     double* d_jac = d_res + F;
-    const char* dbg = std::getenv("RCLC_POSE_EVAL_SPLIT");
-    if (dbg && dbg[0] == '1') {
+    if (ctx->pose_eval_split) {                       // test hook: the per-corner / per-frame split of the cluster shape, on the plain grid
         RCLC_TRY(ctx->d_tmp2.reserve((size_t)F * kCornerVals * C * 8));
         k_pose_eval_split<<<(F + 127) / 128, 128, 0, ctx->stream>>>(d_pc, d_img, F, C, d_T, d_res, d_jac, ctx->d_tmp2.as<double>());
     } else
@@ -669,11 +667,20 @@ int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_cor
     RCLC_CUDA(cudaSetDevice(ctx->device));
     double *d_pc, *d_img, *d_T;
     RCLC_TRY(upload_pose_inputs(ctx, pc_corners, img_norm, F, C, Tcl_io, &d_pc, &d_img, &d_T));
+    return rclc::pose_refine_dev(ctx, cfg, d_pc, d_img, F, C, d_T, Tcl_io, initial_cost, final_cost, iterations);
+}
+
+} // extern "C"
+
+// corners, image points and the start (7 doubles) already on the device
+int rclc::pose_refine_dev(rclc_ctx* ctx, const rclc_config* cfg, const double* d_pc, const double* d_img, int32_t F, int32_t C, const double* d_T,
+                          double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations)
+{
     RCLC_TRY(ctx->d_out.reserve(sizeof(PoseOut)));
-    // RCLC_POSE_CLUSTER=0 keeps the one-CTA kernel, =2 takes the cluster at any size (the A/B switch of the bit-identity test)
-    const char* e = std::getenv("RCLC_POSE_CLUSTER");
+    // pose_shape (rclc_ctx_set_pose_test_hooks): 1 keeps the one-CTA kernel, 2 takes the cluster at any size — the A/B switch of the
+    // bit-identity test; both shapes return the same bits
     bool launched = false;
-    if (!(e && e[0] == '0') && ((int64_t)F * C >= 2 * kPoseThreads || (e && e[0] == '2')))      // '2': the cluster for any size
+    if (ctx->pose_shape != 1 && ((int64_t)F * C >= 2 * kPoseThreads || ctx->pose_shape == 2))
         launched = launch_pose_cluster(ctx, d_pc, d_img, F, C, cfg->pose_huber_a, cfg->pose_function_tol, cfg->pose_max_lm_iters, d_T,
                                        ctx->d_out.as<PoseOut>()) == RCLC_OK;
     if (!launched)
@@ -704,4 +711,9 @@ int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_cor
     return h.termination == 2 ? RCLC_ERR_NUMERIC : RCLC_OK;
 }
 
-} // extern "C"
+extern "C" int rclc_ctx_set_pose_test_hooks(rclc_ctx* ctx, int32_t shape, int32_t cluster_debug, int32_t eval_split)
+{
+    RCLC_CHECK(ctx && shape >= 0 && shape <= 2 && cluster_debug >= 0 && cluster_debug <= 2, RCLC_ERR_INVALID, "bad pose test hook");
+    ctx->pose_shape = shape; ctx->pose_debug = cluster_debug; ctx->pose_eval_split = eval_split ? 1 : 0;
+    return RCLC_OK;
+}

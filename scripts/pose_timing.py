@@ -8,5 +8,5 @@ ctx = capi.Context(0); cfg = capi.config()
 for F, seed in ((64, 3), (256, 9), (700, 5)):
     pc, img, T0, _ = _pose_problem(oracle, F, seed=seed)
     for cl in ("0", "2"):
-        os.environ['RCLC_POSE_CLUSTER'] = cl
+        ctx.set_pose_test_hooks(shape=2 if cl == "2" else 1)
         ctx.pose_refine(cfg, pc, img, T0)

@@ -354,17 +354,20 @@ def test_pose_refine_cluster_frame_split_is_exact(ctx, cfg, oracle, F, seed, mon
     must not change one bit of a frame's residual or Jacobian: the same cluster solve with every frame evaluated by ONE thread
     (the one-CTA kernel's routine) has to return identical bits after up to 1000 iterations."""
     pc, img, T0, _ = _pose_problem(oracle, F, seed=seed)
-    monkeypatch.setenv("RCLC_POSE_CLUSTER", "2")
     out = []
-    for dbg in ("0", "1", "2"):      # 1: whole-frame evaluation by one thread; 2: the one-CTA kernel's block reduction on rank 0
-        monkeypatch.setenv("RCLC_POSE_CLUSTER_DEBUG", dbg)
-        rc, T, c0, c1, it = ctx.pose_refine(cfg, pc, img, T0)
-        out.append((rc, T.tobytes(), c0, c1, it))
-    assert out[0] == out[1] == out[2]
-    r0, j0 = ctx.pose_eval(pc, img, T0)
-    monkeypatch.setenv("RCLC_POSE_EVAL_SPLIT", "1")
-    r1, j1 = ctx.pose_eval(pc, img, T0)
-    assert r0.tobytes() == r1.tobytes() and j0.tobytes() == j1.tobytes()
+    try:
+        for dbg in (0, 1, 2):        # 1: whole-frame evaluation by one thread; 2: the one-CTA kernel's block reduction on rank 0
+            ctx.set_pose_test_hooks(shape=2, cluster_debug=dbg)
+            rc, T, c0, c1, it = ctx.pose_refine(cfg, pc, img, T0)
+            out.append((rc, T.tobytes(), c0, c1, it))
+        assert out[0] == out[1] == out[2]
+        ctx.set_pose_test_hooks()
+        r0, j0 = ctx.pose_eval(pc, img, T0)
+        ctx.set_pose_test_hooks(eval_split=1)
+        r1, j1 = ctx.pose_eval(pc, img, T0)
+        assert r0.tobytes() == r1.tobytes() and j0.tobytes() == j1.tobytes()
+    finally:
+        ctx.set_pose_test_hooks()
 
 
 @pytest.mark.parametrize("F,seed", [(5, 9), (20, 9), (64, 3), (256, 9), (300, 4), (700, 5)])
@@ -376,15 +379,18 @@ def test_pose_refine_cluster_equals_one_cta(ctx, cfg, oracle, ocfg, F, seed, mon
     import time
     pc, img, T0, _ = _pose_problem(oracle, F, seed=seed)
     out = {}
-    for mode in ("0", "2"):
-        monkeypatch.setenv("RCLC_POSE_CLUSTER", mode)
-        ctx.pose_refine(cfg, pc, img, T0)
-        t0 = time.perf_counter()
-        rc, T, c0, c1, it = ctx.pose_refine(cfg, pc, img, T0)
-        out[mode + "ms"] = (time.perf_counter() - t0) * 1e3
-        out[mode] = (rc, T.tobytes(), c0, c1, it)
-    print(f"pose refine F={F}: one CTA {out['0ms']:.2f} ms, cluster {out['2ms']:.2f} ms, {out['0'][4]} iterations")
-    assert out["0"] == out["2"]
+    try:
+        for mode in (1, 2):          # one CTA | the cluster at any size
+            ctx.set_pose_test_hooks(shape=mode)
+            ctx.pose_refine(cfg, pc, img, T0)
+            t0 = time.perf_counter()
+            rc, T, c0, c1, it = ctx.pose_refine(cfg, pc, img, T0)
+            out[str(mode) + "ms"] = (time.perf_counter() - t0) * 1e3
+            out[mode] = (rc, T.tobytes(), c0, c1, it)
+    finally:
+        ctx.set_pose_test_hooks()
+    print(f"pose refine F={F}: one CTA {out['1ms']:.2f} ms, cluster {out['2ms']:.2f} ms, {out[1][4]} iterations")
+    assert out[1] == out[2]
     if F in (64, 300, 700):
         rco, To, c0o, c1o, ito = oracle.pose_refine(ocfg, pc, img, T0)
         assert rc == rco == 0
@@ -471,3 +477,25 @@ def test_gridfit_points_beyond_the_lattice_box_come_into_reach(ctx, cfg, oracle,
         assert r1.pose_evals == r0.pose_evals and r1.outer_iterations == r0.outer_iterations
         assert np.abs(c1 - c0).max() < 1e-6
         assert r1.outer_iterations >= 2                    # the cloud was moved at least once: the motion is what brings them in
+
+
+def test_comm_world_of_one(capi, ctx, cfg, oracle):
+    """The library's NCCL layer (csrc/comm.cu) on a communicator of one rank: the sharded extrinsic solve returns the bits of
+    rclc_pose_refine, the accumulator all-reduce leaves a sweep's tables as they are. (Two ranks: scripts/multi_gpu_check.py.)"""
+    comm = capi.Comm(ctx, capi.Comm.unique_id(), 0, 1)
+    try:
+        pc, img, T0, _ = _pose_problem(oracle, 20)
+        rc0, Ta, a0, a1, ita = ctx.pose_refine(cfg, pc, img, T0)
+        rc1, Tb, b0, b1, itb, ft = comm.pose_refine_sharded(cfg, pc, img, T0)
+        assert ft == 20 and (rc0, Ta.tobytes(), a0, a1, ita) == (rc1, Tb.tobytes(), b0, b1, itb)
+        pts = synth.board_frame_cloud(60000, 5, pert=(0.004, -0.003, 0.4))
+        b = capi.Batch(ctx, cfg, 1, len(pts))
+        b.upload(0, pts); b.bin(); b.sweep(np.array([[0.002, 0.001, 0.2]]))
+        r0, j0, t0 = b.read_eval(want_acc=True)
+        b.sweep(np.array([[0.002, 0.001, 0.2]])); comm.allreduce_acc(b)
+        r1, j1, t1 = b.read_eval(want_acc=True)
+        assert np.array_equal(t0, t1) and np.array_equal(r0, r1)
+        assert comm.collectives() == 3
+        b.close()
+    finally:
+        comm.close()

@@ -105,6 +105,12 @@ int rclc_batch_bin(rclc_batch* b);
  * board_fitting_cost.h:132-151) instead of the fp32 body with exact re-evaluation near decision boundaries. Same results bit for
  * bit, several times slower: the A/B reference of the fast body. */
 int rclc_batch_set_exact_sweep(rclc_batch* b, int32_t on);
+/* on != 0: plain sweeps and the solve of this batch run the streaming kernel (k_sweep_stream: one CTA per range of rows, fed by a
+ * TMA bulk-copy ring, every row read from L2 once) instead of the gather kernel (k_sweep: one warp per target). Same accumulator
+ * tables and LM trajectory bit for bit — the two kernels are each other's A/B check (tests/test_gpu_parity.py) — but the gather
+ * kernel is the faster one on B200 (profiles/r02_stream_history.md) and stays the default. The all-fp64 body and the multi-start
+ * search always use the gather kernel. */
+int rclc_batch_set_stream_sweep(rclc_batch* b, int32_t on);
 int rclc_batch_sweep(rclc_batch* b, const double* poses /* F*3 */);           /* accumulate only (async) */
 int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* acc); /* F*nt[, *3, *16] */
 /* full solve for all frames (async LM state machine on device); outputs on host */

@@ -373,6 +373,10 @@ class Batch:
         """All-fp64 sweep body (the A/B reference of the fast body) for every later sweep / solve of this batch."""
         _chk(lib().rclc_batch_set_exact_sweep(self.h, 1 if on else 0))
 
+    def set_stream_sweep(self, on=True):
+        """The streaming kernel (CTA per range of rows, TMA ring) instead of the gather kernel: each other's A/B check."""
+        _chk(lib().rclc_batch_set_stream_sweep(self.h, 1 if on else 0))
+
     def sweep(self, poses):
         poses = np.ascontiguousarray(poses, np.float64)
         assert poses.shape == (self.n_frames, 3)

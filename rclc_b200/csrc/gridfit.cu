@@ -24,6 +24,7 @@
 #include "gridfit.cuh"
 
 #include <thread>
+#include <type_traits>
 
 #include <algorithm>
 #include <cfloat>
@@ -1140,7 +1141,8 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr)
 }
 
 struct SweepConst {            // fp32 constants of one (target, pose)
-    float cx, cy;                         // disc centre in the stored frame
+    float cx, cy;                         // disc centre in the stored frame (row-box tests)
+    float nkx, nky;                       // -(ref - R t): w = R p - k = x' - ref
     float r00, r01, r10, r11;             // rotation
     float rg2, rc2;                       // radii^2
     float E, E2;                          // error bounds: rotated offsets, squared distance
@@ -1148,45 +1150,64 @@ struct SweepConst {            // fp32 constants of one (target, pose)
 };
 
 // fp32 geometry of one point — the SAME intrinsics in the hot loop and in the correction, so both see identical values.
-// wx, wy = R (p - c) = x' - ref_x, y' - ref_y: the point is right / down of the target when wx / wy > 0.
+// wx, wy = R p - k = x' - ref_x, y' - ref_y (k = ref - R t, folded into one constant per target): the point is right / down of
+// the target when wx / wy > 0; d^2 = |w|^2 (a rotation keeps the norm). Six instructions: two FFMA chains, FMUL, FFMA.
 __device__ __forceinline__ void point_geom(const SweepConst& k, float qx, float qy, float& wx, float& wy, float& d2)
 {
-    const float ex = __fsub_rn(qx, k.cx), ey = __fsub_rn(qy, k.cy);
-    d2 = __fmaf_rn(ex, ex, __fmul_rn(ey, ey));
-    wx = __fmaf_rn(k.r00, ex, __fmul_rn(k.r01, ey));
-    wy = __fmaf_rn(k.r10, ex, __fmul_rn(k.r11, ey));
+    wx = __fmaf_rn(k.r00, qx, __fmaf_rn(k.r01, qy, k.nkx));
+    wy = __fmaf_rn(k.r10, qx, __fmaf_rn(k.r11, qy, k.nky));
+    d2 = __fmaf_rn(wx, wx, __fmul_rn(wy, wy));
 }
 
 // One point update. ptxas turns predicated fp64 adds into add + two selects (12 ALU-pipe selects per point), so the
-// class is applied as a MULTIPLIER instead: m = +-1.0 / +-0.0 built from two compares, two selects and four
-// sign-xors on the high word (the low word is a constant zero), then six DFMAs:
+// class is applied as a MULTIPLIER instead: m = +-2^-7 / +-0.0, whose high word is what FSET writes for a float compare
+// (1.0f = 0x3f800000 read as the high word of a double is 2^-7) and whose sign is mixed in by ONE LOP3, h ^ (~w & signbit);
+// then six DFMAs:
 //   a[0] += [in] v          a[1] += [in] s_y v          a[2] += [in] s_x v        (s = -1 when down / right)
-//   a[3] += [cost] v        a[4] += [cost] s_y v        a[5] += [cost] s_x v
-// All products and sums are exact, so down = (a0 - a1) / 2 etc. are exact too (to_nested_totals).
+//   a[3] += [cost] v        a[4] += [cost] s_y v        a[5] += [cost] s_x v      (all times 2^-7)
+// All products and sums are exact, so down = 64 (a0 - a1) etc. are exact too (to_nested_totals).
+__device__ __forceinline__ uint32_t fset_le_bits(float a, float b)      // 0x3f800000 when a <= b, else 0
+{
+    uint32_t r;
+    asm("set.le.f32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t fset_lt_bits(float a, float b)
+{
+    uint32_t r;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t sign_mix_bits(uint32_t h, float w)   // h ^ (~w & 0x80000000)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD2;" : "=r"(r) : "r"(h), "r"(__float_as_uint(w)));
+    return r;
+}
 __device__ __forceinline__ void accumulate6(double (&a)[6], float d2, float wx, float wy, float rg2, float rc2, double v, bool member, int zlo)
 {
-    const uint32_t one = 0x3ff00000u;
-    const uint32_t hin = (member && d2 <= rg2) ? one : 0u;
-    const uint32_t hc = (member && d2 < rc2) ? one : 0u;
-    // s = -1 (sign bit set) when down / right, i.e. when w is positive (sign bit clear)
-    const uint32_t sy = ~__float_as_uint(wy) & 0x80000000u, sx = ~__float_as_uint(wx) & 0x80000000u;
+    uint32_t hin = fset_le_bits(d2, rg2), hc = fset_lt_bits(d2, rc2);
+    hin = member ? hin : 0u;              // (member is a compile-time true outside the masked body)
+    hc = member ? hc : 0u;
     // zlo: a zero the compiler cannot see through (stream_rows), so the six multipliers share ONE low word held in a register
     // instead of six freshly zeroed ones per point
     a[0] = fma(__hiloint2double((int)hin, zlo), v, a[0]);
-    a[1] = fma(__hiloint2double((int)(hin ^ sy), zlo), v, a[1]);
-    a[2] = fma(__hiloint2double((int)(hin ^ sx), zlo), v, a[2]);
+    a[1] = fma(__hiloint2double((int)sign_mix_bits(hin, wy), zlo), v, a[1]);
+    a[2] = fma(__hiloint2double((int)sign_mix_bits(hin, wx), zlo), v, a[2]);
     a[3] = fma(__hiloint2double((int)hc, zlo), v, a[3]);
-    a[4] = fma(__hiloint2double((int)(hc ^ sy), zlo), v, a[4]);
-    a[5] = fma(__hiloint2double((int)(hc ^ sx), zlo), v, a[5]);
+    a[4] = fma(__hiloint2double((int)sign_mix_bits(hc, wy), zlo), v, a[4]);
+    a[5] = fma(__hiloint2double((int)sign_mix_bits(hc, wx), zlo), v, a[5]);
 }
 
-// signed sums -> the six nested totals (in, in&down, in&right, cost, cost&down, cost&right); exact
+// signed sums (times 2^-7) -> the six nested totals (in, in&down, in&right, cost, cost&down, cost&right); exact
 __device__ __forceinline__ void to_nested_totals(double (&a)[6])
 {
-    a[1] = 0.5 * (a[0] - a[1]);
-    a[2] = 0.5 * (a[0] - a[2]);
-    a[4] = 0.5 * (a[3] - a[4]);
-    a[5] = 0.5 * (a[3] - a[5]);
+    a[1] = 64.0 * (a[0] - a[1]);
+    a[2] = 64.0 * (a[0] - a[2]);
+    a[0] = 128.0 * a[0];
+    a[4] = 64.0 * (a[3] - a[4]);
+    a[5] = 64.0 * (a[3] - a[5]);
+    a[3] = 128.0 * a[3];
 }
 
 // Everything the cold paths need about the warp's task, in the warp's slice of shared memory.
@@ -1222,7 +1243,7 @@ __device__ __noinline__ Corr6 correct_point(float4 q, const WarpCtx* wc, bool ma
     const ExactClass e = classify_exact(q.x, q.y, pc, wc->ref.x, wc->ref.y, wc->rg2, wc->rc2);
     const double e_in = e.in ? 1.0 : 0.0, e_c = (e.in && e.cost) ? 1.0 : 0.0;
     const double e_sy = e.down ? -1.0 : 1.0, e_sx = e.right ? -1.0 : 1.0;
-    const double v = (double)q.z + kCntUnit;
+    const double v = ((double)q.z + kCntUnit) * 0.0078125;        // the accumulators carry 2^-7 of the sums
     a.d[0] = (e_in - f_in) * v;
     a.d[1] = (e_in * e_sy - f_in * f_sy) * v;
     a.d[2] = (e_in * e_sx - f_in * f_sx) * v;
@@ -1433,12 +1454,15 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
     const double rgd = sqrt(g.rg2);
     SweepConst k;
     k.cx = (float)cxd; k.cy = (float)cyd;
+    k.nkx = (float)(-(ref.x - (pc.r00 * pc.tx + pc.r01 * pc.ty)));
+    k.nky = (float)(-(ref.y - (pc.r10 * pc.tx + pc.r11 * pc.ty)));
     k.r00 = (float)pc.r00; k.r01 = (float)pc.r01; k.r10 = (float)pc.r10; k.r11 = (float)pc.r11;
     k.rg2 = (float)g.rg2; k.rc2 = (float)g.rc2;
     k.tqx = tq.x; k.tqy = tq.y; k.rn2 = g.rn2f;
     {
-        // |fp32 offsets - reference's| <= E for every point that can matter (|p - c| <= 2 rg): rounding of c, of p - c, of the
-        // 2x2 product, plus the reference's own rounding of R (p + t) at coordinate magnitude Bc
+        // |fp32 offsets - reference's| <= E for every point that can matter (|p - c| <= 2 rg). w = fl(r00 x + fl(r01 y - k)) with
+        // r00, r01, k rounded to fp32: |error| <= u (|x| + |y| + |k| + |r01 y - k| + |w|), u = 2^-24, and |x| + |y| <= |c| + 4 rg,
+        // |k| <= |ref| + |t|: at most 4.1 u Bc, plus the reference's own (double) rounding of R (p + t) at magnitude Bc
         const double Bc = fabs(cxd) + fabs(cyd) + fabs(pc.tx) + fabs(pc.ty) + fabs(ref.x) + fabs(ref.y) + 0.2;
         k.E = (float)(6.0 * 5.9604644775390625e-8 * Bc + 1e-9);
         k.E2 = 1.05f * (2.9f * (float)rgd * k.E + 3e-7f * k.rg2 + 2.f * k.E * k.E + 1e-9f);
@@ -1600,6 +1624,8 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
     lm_frame_step(bv, f, stage);
 }
 
+#include "sweep_stream.cuh"
+
 __global__ void k_set_pose(BatchView bv, const PoseCoef* __restrict__ poses)
 {
     const int f = blockIdx.x;
@@ -1758,8 +1784,28 @@ static int sweep_parts(const rclc_batch* b, int n_frames, bool fused)
     return (int)std::max(1.0, std::min(8.0, std::floor(0.9 * slots / tasks + 0.5)));
 }
 
+// k_sweep_stream: CTAs per (frame, pose slot), each a contiguous share of the frame's rows. A plain sweep fills the machine once
+// (3 CTAs per SM); inside the solve most pose slots of a round are in use and the groups' launches overlap, so a launch asks for
+// about twice its share.
+static int stream_ctas(const rclc_batch* b, int n_frames, bool fused)
+{
+    const double slots = (double)b->ctx->sm_count * 3.0;
+    const double units = (double)std::max(n_frames, 1) * (fused ? 0.75 * kSpec : 1.0);
+    const int64_t rows = b->v.frame_stride / 32;
+    const double k = fused ? std::ceil(2.0 * slots / units) : std::floor(slots / units);
+    return (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)k, std::max<int64_t>(1, rows / 64)));
+}
+
 static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames, cudaStream_t st, int frames_in_flight)
 {
+    if (v.fixed_frame < 0 && !v.force_exact && b->stream_sweep) {
+        v.npose_max = v.fuse_lm ? kSpec : 1;
+        const int k = stream_ctas(b, frames_in_flight, v.fuse_lm != 0);
+        k_sweep_stream<<<dim3((unsigned)k, (unsigned)n_frames, (unsigned)v.npose_max), kStThreads, st_smem_bytes(v.geom.nt, v.geom.ncells), st>>>(v);
+        b->ctx->launches += 1;
+        RCLC_CUDA(cudaGetLastError());
+        return RCLC_OK;
+    }
     v.parts = sweep_parts(b, frames_in_flight, v.fuse_lm != 0);
     v.npose_max = v.fuse_lm ? kSpec : 1;
     const int gx = (v.geom.nt * v.parts * v.npose_max + kSweepWarps - 1) / kSweepWarps;
@@ -1837,6 +1883,8 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.parts = 1;
     RCLC_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
     RCLC_CUDA(cudaFuncSetAttribute(k_sweep_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
+    RCLC_CHECK(st_smem_bytes(hg.g.nt, hg.g.ncells) <= 110 * 1024, RCLC_ERR_UNSUPPORTED, "board too large for the streaming sweep's shared memory");
+    RCLC_CUDA(cudaFuncSetAttribute(k_sweep_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem_bytes(hg.g.nt, hg.g.ncells)));
     const size_t F = n_frames, nt = hg.g.nt, ncell = hg.g.ncells, nfine = hg.g.nfine;
     auto fail = [&](const char* what) { set_last_error(what); rclc_batch_destroy(b); return RCLC_ERR_CUDA; };
     const size_t big = F * (size_t)v.frame_stride * 16;
@@ -2034,6 +2082,25 @@ int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* 
         if (residuals) residuals[k] = h[4 * k];
         if (jac) { jac[3 * k] = h[4 * k + 1]; jac[3 * k + 1] = h[4 * k + 2]; jac[3 * k + 2] = h[4 * k + 3]; }
     }
+    return RCLC_OK;
+}
+
+#ifdef RCLC_ST_TIMING
+int rclc_lab_st_timing(long long* out, int32_t n_warps)          // lab build only
+{
+    RCLC_CUDA(cudaDeviceSynchronize());
+    RCLC_CUDA(cudaMemcpyFromSymbol(out, g_st_dbg, sizeof(long long) * kStDbgSlots * std::min(n_warps, 4096)));
+    return RCLC_OK;
+}
+#endif
+
+int rclc_batch_set_stream_sweep(rclc_batch* b, int32_t on)
+{
+    RCLC_CHECK(b, RCLC_ERR_INVALID, "null batch");
+    b->stream_sweep = on != 0;
+    for (cudaGraphExec_t ge : b->round_graphs) cudaGraphExecDestroy(ge);      // the graphs hold the launches
+    b->round_graphs.clear();
+    b->graphs_groups = 0;
     return RCLC_OK;
 }
 

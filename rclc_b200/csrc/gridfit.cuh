@@ -161,6 +161,7 @@ struct rclc_batch {
     void* d_block = nullptr;          // one allocation for the small arrays
     int64_t* d_npts = nullptr;
     bool binned_valid = false;
+    bool stream_sweep = false;        // rclc_batch_set_stream_sweep: plain sweeps and the solve use k_sweep_stream (CTA per range of rows, TMA ring) instead of k_sweep
     int round = 0;                    // parity of the re-bin list the next round consumes
     // one instantiated CUDA graph per solve group: kRoundsPerGraph rounds of {k_move, k_sweep} (the steady state of the solve)
     std::vector<cudaGraphExec_t> round_graphs;

@@ -450,6 +450,61 @@ def test_fast_sweep_equals_exact_sweep(capi, ctx, cfg, oracle, ocfg, monkeypatch
             assert np.array_equal(acc[f], oracle.gridfit_eval(ocfg, frames[f], poses[f], want_acc=True)[2])
 
 
+def test_stream_sweep_equals_gather_sweep(capi, ctx, cfg, oracle, ocfg):
+    """Two independent kernels for board_fitting_cost.h:74-262 — k_sweep (a warp per target gathers the rows of its discs) and
+    k_sweep_stream (a CTA per range of rows behind a TMA ring, candidates per lattice cell) — must leave the SAME accumulator
+    tables, bit for bit: small poses, poses where the kd-tree neighbour test matters (centimetres), a frame whose intensities
+    cannot carry the riding count (all-fp64 rows), ragged sizes down to a handful of points; and the oracle on a few of them."""
+    rng = np.random.default_rng(78)
+    sizes = [150000, 90000, 40, 20000, 3]
+    frames = [synth.board_frame_cloud(max(n, 64), 700 + i, pert=(0.004 * i, -0.003 * i, 0.3 * i), pattern="rosette" if i % 2 else "raster")[:n]
+              for i, n in enumerate(sizes)]
+    frames[3] = frames[3].copy()
+    frames[3][::7, 3] = 300.0 + rng.uniform(0, 50, len(frames[3][::7]))          # beyond [2^-3, 256): this frame takes the exact rows
+    tables = {}
+    for mode in ("gather", "stream"):
+        b = capi.Batch(ctx, cfg, len(sizes), max(sizes))
+        b.set_stream_sweep(mode == "stream")
+        for f, p in enumerate(frames):
+            b.upload(f, p)
+        b.bin()
+        out = []
+        prng = np.random.default_rng(6)
+        for trial in range(12):
+            scale = [1e-4, 2e-3, 0.012, 0.035][trial % 4]
+            poses = np.stack([prng.uniform(-scale, scale, len(sizes)), prng.uniform(-scale, scale, len(sizes)),
+                              prng.uniform(-100 * scale, 100 * scale, len(sizes))], axis=1)
+            b.sweep(poses)
+            out.append((poses, b.read_eval(want_acc=True)[2].copy()))
+        tables[mode] = out
+        b.close()
+    for (p0, a0), (p1, a1) in zip(tables["gather"], tables["stream"]):
+        assert np.array_equal(p0, p1)
+        assert np.array_equal(a0, a1), np.abs(a0 - a1).max()
+    for poses, acc in tables["stream"][:4]:
+        for f in (0, 3):
+            assert np.array_equal(acc[f], oracle.gridfit_eval(ocfg, frames[f], poses[f], want_acc=True)[2])
+
+
+def test_stream_sweep_solve_equals_gather_solve(capi, ctx, cfg):
+    """The full solve (fused LM steps, speculative rounds, in-place moves) through either kernel: identical reports and corners."""
+    frames = [synth.board_frame_cloud(60000 + 7000 * i, 300 + i, pert=(0.003 * i, -0.002 * i, 0.25 * i), pattern="rosette" if i % 2 else "raster")
+              for i in range(5)]
+    res = {}
+    for mode in ("gather", "stream"):
+        b = capi.Batch(ctx, cfg, len(frames), max(len(p) for p in frames))
+        b.set_stream_sweep(mode == "stream")
+        for f, p in enumerate(frames):
+            b.upload(f, p)
+        res[mode] = b.gridfit_solve()
+        b.close()
+    (c0, r0), (c1, r1) = res["gather"], res["stream"]
+    assert np.array_equal(c0, c1)
+    for a, bb in zip(r0, r1):
+        assert (a.status, a.outer_iterations, a.pose_evals, a.lm_iterations) == (bb.status, bb.outer_iterations, bb.pose_evals, bb.lm_iterations)
+        assert a.last_final_cost == bb.last_final_cost
+
+
 def test_gridfit_points_beyond_the_lattice_box_come_into_reach(ctx, cfg, oracle, ocfg):
     """The reference rebuilds its kd-tree on the FULL cloud in every outer iteration (opt_grid_fitting.h:75-76, 107): points
     that start beyond the lattice box (board holder, surroundings in the board's plane) become neighbours of the outer targets

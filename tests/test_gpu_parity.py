@@ -416,7 +416,7 @@ def test_kernel_launch_counter(ctx, cfg):
     assert ctx.kernel_launches() - before == 1             # the whole EM of a small cloud is one cluster launch
     before = ctx.kernel_launches()
     ctx.gmm_fit_1d(np.linspace(5, 120, 300000, dtype=np.float32), [15, 100], [15, 15])
-    assert ctx.kernel_launches() - before == 20            # large clouds: two passes per iteration, ten iterations
+    assert ctx.kernel_launches() - before == 10            # large clouds: one pass per iteration, ten iterations
 
 
 def test_fast_sweep_equals_exact_sweep(capi, ctx, cfg, oracle, ocfg, monkeypatch):

@@ -112,6 +112,39 @@ def test_calibrate_frames_equals_single_frame_calls_and_oracle_extrinsic(ctx, cf
     assert ang < 3e-3 and np.abs(T1[4:] - Tgt[:3, 3]).max() < 0.02
 
 
+def test_calibration_of_configs0_in_full_against_the_oracle(ctx, cfg, oracle):
+    """BASELINE configs[0] at its full size — 20 raw MID-40 scans x 100 k points through both stages and the extrinsic solve —
+    against the oracle's chains on every frame (a thread per frame on the host): the same board points, corners within 1 um,
+    the extrinsic within the north star's 1e-4 rad / 0.1 mm."""
+    from concurrent.futures import ThreadPoolExecutor
+    F = 20
+    ocfg = oracle.config()
+    scans, imgs, _ = zip(*[synth.raw_scan(f) for f in range(F)])
+    out = ctx.calibrate_frames(cfg, list(scans), np.stack(imgs))
+    assert (out["status"] == 0).all()
+
+    def chain(raw):
+        rc, board = oracle.segment_board(ocfg, raw)
+        assert rc == 0
+        rc, c0, r0, _ = oracle.est_board_corner(ocfg, _to_cam(board))
+        assert rc == 0
+        return len(board), c0, r0
+
+    with ThreadPoolExecutor(max_workers=F) as ex:
+        ref = list(ex.map(chain, scans))
+    for f, (nb, c0, r0) in enumerate(ref):
+        assert out["n_board"][f] == nb
+        assert out["reports"][f].pose_evals == r0.pose_evals and out["reports"][f].outer_iterations == r0.outer_iterations
+        assert np.abs(out["corners"][f] - c0).max() < 1e-6
+    oc = np.stack([r[1] for r in ref])
+    rc, T0, _, c1o, _ = oracle.pose_refine(ocfg, oc, np.stack(imgs), out_start(ctx, cfg, oc, np.stack(imgs)))
+    T1 = out["Tcl"]
+    q0, q1 = T0[:4] / np.linalg.norm(T0[:4]), T1[:4] / np.linalg.norm(T1[:4])
+    if q0 @ q1 < 0:
+        q1 = -q1
+    assert 2 * np.abs(q0 - q1).max() < 1e-4 and np.abs(T0[4:] - T1[4:]).max() < 1e-4
+
+
 def out_start(ctx, cfg, corners, imgs):
     """The PnP start rclc_calibrate_frames uses (apps/Calibrate.cpp:41-62), rebuilt through the same entry points."""
     from rclc_b200 import capi

@@ -101,6 +101,28 @@ def test_solve_is_deterministic_and_independent_of_grouping(capi, ctx, cfg, orac
     assert all(r.status == 0 for r in r0)
 
 
+def test_all_20_frames_of_configs1_follow_the_oracles_trajectory(capi, ctx, cfg, oracle, ocfg, batch20):
+    """configs[1] in full against the oracle: every one of the 20 x 500 k frames — same number of pose evaluations, LM iterations
+    and outer iterations, corners within 1 um. (The oracle runs a thread per frame: a few seconds on the box's host cores.)"""
+    from concurrent.futures import ThreadPoolExecutor
+    b, frames, perts = batch20
+    corners, reps = b.gridfit_solve()
+    with ThreadPoolExecutor(max_workers=20) as ex:
+        ref = list(ex.map(lambda p: oracle.gridfit_solve(ocfg, p), frames))
+    for f, (rc_o, co, ro, _) in enumerate(ref):
+        assert rc_o == 0 and reps[f].status == 0
+        assert (ro.pose_evals, ro.lm_iterations, ro.outer_iterations) == (reps[f].pose_evals, reps[f].lm_iterations, reps[f].outer_iterations), f
+        np.testing.assert_allclose(corners[f], co, atol=1e-6)
+    # and the accumulator tables of all 20 frames at their full misalignment, bit for bit
+    b.bin()
+    b.sweep(perts)
+    acc = b.read_eval(want_acc=True)[2]
+    with ThreadPoolExecutor(max_workers=20) as ex:
+        ref_acc = list(ex.map(lambda fp: oracle.gridfit_eval(ocfg, fp[0], fp[1], want_acc=True)[2], zip(frames, perts)))
+    for f in range(20):
+        assert np.array_equal(acc[f], ref_acc[f]), f
+
+
 def test_multistart_4096_hypotheses_200k_points(capi, ctx, cfg, oracle, ocfg):
     """configs[2]: all 4096 costs finite, the oracle on a sample of hypotheses, and the minimum at the lattice point nearest the
     cloud's true misalignment."""
@@ -111,8 +133,11 @@ def test_multistart_4096_hypotheses_200k_points(capi, ctx, cfg, oracle, ocfg):
     cost = ctx.gridfit_multistart(cfg, pts, P)
     assert np.isfinite(cost).all()
     rng = np.random.default_rng(0)
-    for k in np.r_[rng.choice(len(P), 6, replace=False), int(np.argmin(cost))]:
-        np.testing.assert_allclose(cost[k], oracle.gridfit_cost(ocfg, pts, P[k]), rtol=1e-12)
+    from concurrent.futures import ThreadPoolExecutor
+    ks = np.r_[rng.choice(len(P), 64, replace=False), int(np.argmin(cost))]
+    with ThreadPoolExecutor(max_workers=16) as ex:
+        ref = list(ex.map(lambda k: oracle.gridfit_cost(ocfg, pts, P[k]), ks))
+    np.testing.assert_allclose(cost[ks], ref, rtol=1e-12)
     best = P[int(np.argmin(cost))]
     assert abs(best[0] - true[0]) <= 0.004 and abs(best[1] - true[1]) <= 0.004 and abs(best[2] - true[2]) <= 0.54
 

@@ -345,7 +345,13 @@ def test_pose_eval_and_refine(ctx, cfg, oracle, ocfg, F):
     dq = 2 * np.linalg.norm(Tb[:4] * np.sign(Tb[3]) - Ta[:4] * np.sign(Ta[3]))
     assert dq < 1e-4
     # iteration counts may differ: this LM wanders ~1000 iterations around a non-smooth minimum (sum of norms),
-    # so 1e-16 differences in summation order change when it stops; the bar is on the extrinsic itself.
+    # so 1e-16 differences in summation order change when it stops; the bar is on the extrinsic itself — and on the CONVERGED
+    # COST: both solves end in the same valley, at the same objective value to the flatness of its floor (the oracle's own
+    # value is pinned against scipy's minimiser in tests/test_oracle_scipy_pins.py)
+    print(f"pose refine F={F}: final cost {c1b:.12e} (oracle {c1a:.12e}), {itb} / {ita} iterations")
+    # (measured on B200: 3e-3 relative at 5 frames — the reference's cap, under-determined, SURVEY F7 — 9e-4 at 20; neither solve
+    #  converges in Ceres' sense, both stop at the iteration cap while wandering over the kinks of the floor)
+    assert abs(c1b - c1a) <= 5e-3 * c1a and c1b < 0.01 * c0b
 
 
 @pytest.mark.parametrize("F,seed", [(5, 9), (20, 9), (64, 3), (256, 9), (300, 4), (700, 5)])

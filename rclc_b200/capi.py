@@ -12,7 +12,7 @@ import numpy as np
 from .config import RclcConfig, default_config
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librclc_b200.so")
+LIB_PATH = os.environ.get("RCLC_B200_LIB") or os.path.join(_HERE, "librclc_b200.so")      # (the override: A/B of experimental builds, scripts/ only)
 _lib = None
 
 

@@ -1413,8 +1413,9 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv);
 
 __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const __grid_constant__ BatchView bv) { sweep_body<3>(bv); }
 // The multi-start search reads one frame (L2-resident) under thousands of poses: it is bound by issue slots and L2 latency,
-// not by DRAM, and wants more resident warps — the same body at 5 CTAs per SM (96 registers).
-__global__ void __launch_bounds__(kSweepThreads, 5) k_sweep_dense(const __grid_constant__ BatchView bv) { sweep_body<5>(bv); }
+// not by DRAM, and wants more resident warps — the same body at 4 CTAs per SM (128 registers, no spills; 5 CTAs / 96 registers
+// spilled 316 bytes per thread into the hot loop and was 4 % slower: 4.27 vs 4.12 ms per 4096 x 200 k search).
+__global__ void __launch_bounds__(kSweepThreads, 4) k_sweep_dense(const __grid_constant__ BatchView bv) { sweep_body<4>(bv); }
 
 template <int CTAS>
 __device__ __forceinline__ void sweep_body(const BatchView& bv)

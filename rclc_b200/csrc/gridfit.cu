@@ -1417,9 +1417,21 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_sweep(const __grid_constan
 // spilled 316 bytes per thread into the hot loop and was 4 % slower: 4.27 vs 4.12 ms per 4096 x 200 k search).
 __global__ void __launch_bounds__(kSweepThreads, 4) k_sweep_dense(const __grid_constant__ BatchView bv) { sweep_body<4>(bv); }
 
+#ifdef RCLC_SWEEP_TIMING
+// lab build only (scripts/sweep_timeline.py): stage clocks of every task of the last sweep
+__device__ long long g_sw_dbg[8192 * 8];
+#define SW_STAMP(k) do { if (lane == 0) sw_t[k] = clock64(); } while (0)
+#else
+#define SW_STAMP(k)
+#endif
+
 template <int CTAS>
 __device__ __forceinline__ void sweep_body(const BatchView& bv)
 {
+#ifdef RCLC_SWEEP_TIMING
+    long long sw_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); sw_t[7] = gt; sw_t[0] = clock64(); }
+#endif
     const int f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int parts = bv.parts;
@@ -1471,6 +1483,7 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
     if (lane == 0) { wc->k = k; wc->pc = pc; wc->ref = ref; wc->rg2 = g.rg2; wc->rc2 = g.rc2; }
     if (lane < 12) tot[lane] = 0.0;
     __syncwarp();
+    SW_STAMP(1);                 // control block, pose and target have arrived; constants computed
 
     // kd-tree neighbour mask (3-D distance < neighbour_radius at pose 0, board_fitting_cost.h:273): it can exclude a point
     // that the pose moves into the gradient disc only if (rg + displacement)^2 + z^2 >= rn^2
@@ -1513,6 +1526,7 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
             }
         }
         if (mode < 0) {
+            SW_STAMP(2);         // cell table entries have arrived
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) z2max = fmaxf(z2max, __shfl_xor_sync(0xffffffffu, z2max, o));
             const bool masked = !((rgf + disp) * (rgf + disp) + z2max < g.rn2f * 0.9999f);
@@ -1564,7 +1578,9 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
         }
         gbase += n_groups;
     }
+    SW_STAMP(3);                 // last row-box batch tested (streaming of earlier lists included)
     drain_list(mode, src, list, n_list, lane, ring, k, wc, acc, mA, mB, tot, rows_since_split);
+    SW_STAMP(4);                 // last list streamed
 
     // ---- the target's 16 accumulators ----
     if (mode != 2 && rows_since_split > 0) reduce_totals(acc, tot, lane);
@@ -1576,6 +1592,13 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
         if (parts > 1) { if (v != 0.0) atomicAdd(acc_t + lane, v); }
         else acc_t[lane] = v;
     }
+#ifdef RCLC_SWEEP_TIMING
+    if (lane == 0) {
+        sw_t[5] = clock64();
+        const int w = (blockIdx.y * gridDim.x + blockIdx.x) * kSweepWarps + warp;
+        if (w < 8192) for (int q = 0; q < 8; ++q) g_sw_dbg[w * 8 + q] = sw_t[q];
+    }
+#endif
     if (!bv.fuse_lm) return;
     // ---- fused LM step, part 1: the warp that adds the (pose, target)'s last share turns its 16 accumulators into the LM terms
     //      (in parallel over the targets, overlapped with the tasks still sweeping) and clears them for the next sweep ----
@@ -2086,6 +2109,14 @@ int rclc_batch_read_eval(rclc_batch* b, double* residuals, double* jac, double* 
     return RCLC_OK;
 }
 
+#ifdef RCLC_SWEEP_TIMING
+int rclc_lab_sweep_timing(long long* out, int32_t n_warps)       // lab build only
+{
+    RCLC_CUDA(cudaDeviceSynchronize());
+    RCLC_CUDA(cudaMemcpyFromSymbol(out, g_sw_dbg, sizeof(long long) * 8 * std::min(n_warps, 8192)));
+    return RCLC_OK;
+}
+#endif
 #ifdef RCLC_ST_TIMING
 int rclc_lab_st_timing(long long* out, int32_t n_warps)          // lab build only
 {

@@ -4,8 +4,8 @@
 # the capture to gpurun_out/ (the .ncu-rep stays scratch).
 set -e
 mkdir -p gpurun_out
-python scripts/profile_sweep.py 20 500000 6 > gpurun_out/sweep_plain.log 2>&1          # the command exits 0 without ncu first
-ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 3 -c 2 -f -o gpurun_out/r02_sweep python scripts/profile_sweep.py 20 500000 6 > gpurun_out/ncu_sweep.log 2>&1
+python scripts/profile_sweep.py 128 500000 5 > gpurun_out/sweep_plain.log 2>&1          # the command exits 0 without ncu first
+ncu --set full --clock-control none --import-source on -k regex:k_sweep -s 3 -c 2 -f -o gpurun_out/r02_sweep python scripts/profile_sweep.py 128 500000 5 > gpurun_out/ncu_sweep.log 2>&1
 ncu -i gpurun_out/r02_sweep.ncu-rep --page raw --csv > gpurun_out/r02_sweep_raw.csv
 python - <<'PY'
 import csv, json, sys, os, datetime
@@ -13,14 +13,14 @@ sys.path.insert(0, os.getcwd())
 import bench
 rows = list(csv.reader(open("gpurun_out/r02_sweep_raw.csv")))
 h = rows[0]
-def col(name, r): return float(r[h.index(name)].replace(",", ""))
-rd = [col("dram__bytes_read.sum", r) for r in rows[2:]]
-wr = [col("dram__bytes_write.sum", r) for r in rows[2:]]
-unit = rows[1][h.index("dram__bytes_read.sum")]
-k = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
-out = {"dram_bytes_per_launch": int((sum(rd) + sum(wr)) / len(rd) * k), "dram_bytes_read": int(sum(rd) / len(rd) * k),
-       "dram_bytes_write": int(sum(wr) / len(wr) * k), "kernel_source_sha": bench.kernel_source_sha(),
-       "source": "ncu --set full --clock-control none, %d launches of k_sweep on 20 x 500k points, L2 flushed before each (scripts/capture_sweep_traffic.sh, %s)" % (len(rd), datetime.date.today().isoformat())}
+K = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+def col(name):                       # (every column has its own unit)
+    i = h.index(name)
+    return [float(r[i].replace(",", "")) * K[rows[1][i]] for r in rows[2:]]
+rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+out = {"dram_bytes_per_launch": int((sum(rd) + sum(wr)) / len(rd)), "dram_bytes_read": int(sum(rd) / len(rd)),
+       "dram_bytes_write": int(sum(wr) / len(wr)), "kernel_source_sha": bench.kernel_source_sha(),
+       "source": "ncu --set full --clock-control none, %d launches of k_sweep on 128 x 500k points (the bench's roofline batch), L2 flushed before each (scripts/capture_sweep_traffic.sh, %s)" % (len(rd), datetime.date.today().isoformat())}
 json.dump(out, open("gpurun_out/sweep_traffic.json", "w"))
 print(out)
 PY

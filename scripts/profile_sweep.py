@@ -8,7 +8,9 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 500000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 cfg = capi.config()
 ctx = capi.Context(0)
-frames, perts = synth.gridfit_batch(F, N, seed0=1000)
+F0 = min(F, 20)                      # (larger batches repeat the 20 frames: every copy has its own memory)
+frames, perts = synth.gridfit_batch(F0, N, seed0=1000)
+frames = [frames[f % F0] for f in range(F)]; perts = [perts[f % F0] for f in range(F)]
 b = capi.Batch(ctx, cfg, F, N)
 for f, p in enumerate(frames):
     b.upload(f, p)

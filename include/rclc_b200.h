@@ -132,8 +132,12 @@ int rclc_plane_project(rclc_ctx* ctx, void* pts_io, int stride, int64_t n, const
 int rclc_plane_fit(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, int stride, int ioff, int64_t n, double plane_out[4],
                    int32_t* iterations, int64_t* n_used);
 /* ---- pcl::UniformSampling (pc_process.h:111-115, apps/BoardSegmentation.cpp:58-61): per voxel of side `leaf` (grid anchored at
- * the cloud's min corner) the input point nearest the voxel centre. idx_out (room for n) receives the kept point indices in
- * ascending voxel-key order (PCL's order is its hash map's; the SET is the same). ---- */
+ * the cloud's min corner) the input point nearest the voxel centre (SURVEY.md Appendix A's definition of the filter, which the
+ * oracle restates). idx_out (room for n) receives the kept point indices in ascending voxel-key order (PCL's order is its hash
+ * map's). One voxel keeps one point in every PCL release, so the occupied voxels and the count are PCL's; WHICH point of a
+ * voxel survives is pinned by the survey's definition, not by PCL's sources (not vendored: some releases measure the distance
+ * against the voxel's integer index vector rather than its metric centre — a change of one expression in us_key /
+ * orc_uniform_sample if a given PCL build has to be matched point for point). ---- */
 int rclc_uniform_sample(rclc_ctx* ctx, const void* pts, int stride, int ioff, int64_t n, double leaf, int32_t* idx_out, int64_t* n_out);
 /* ---- pcl::EuclideanClusterExtraction (pc_process.h:62-72, 131-139): connected components of "distance < tol", components with
  * min_size <= size <= max_size ranked by size descending (ties: smallest member index first). labels_out[i] = rank or -1;

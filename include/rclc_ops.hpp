@@ -491,7 +491,8 @@ private:
 };
 
 // pcl::UniformSampling<PoinT> drop-in (the calls the reference makes: setInputCloud, setRadiusSearch, filter).
-// Output order: ascending voxel key (PCL's is its hash map's iteration order); the kept SET is PCL's.
+// Output order: ascending voxel key (PCL's is its hash map's iteration order). Occupied voxels and count are PCL's; which point of a
+// voxel is kept follows SURVEY.md Appendix A (nearest the metric voxel centre) — see rclc_uniform_sample in rclc_b200.h.
 class UniformSampling {
 public:
     void setInputCloud(typename PointCloud<PoinT>::Ptr c) { cloud_ = c; }

@@ -73,7 +73,12 @@ __device__ void pose_block_dev(const double* Tcl, const double* pc, const double
         const J7 depth_norm = jsqrt(X * X + (Y * Y + Z * Z));
         if (depth_norm.a > depth_max.a) depth_max = depth_norm;
         const J7 e0 = jconst(img[2 * i]) - X / Z, e1 = jconst(img[2 * i + 1]) - Y / Z;
-        res = res + jsqrt(e0 * e0 + e1 * e1) / depth_norm;
+        // res += |e| / depth_norm, spelled out operation by operation: the cluster kernel rebuilds the same sum from per-corner
+        // factors (pose_corner_dev / pose_frame_from_corners) and must see the same roundings whatever nvcc would contract here
+        const J7 en = jsqrt(e0 * e0 + e1 * e1);
+        const double gi = 1.0 / depth_norm.a, fg = en.a * gi;
+        res.a = fg + res.a;
+        for (int k = 0; k < 7; ++k) res.v[k] = fma(fma(-fg, depth_norm.v[k], en.v[k]), gi, res.v[k]);
     }
     res = res * depth_max;
     r = res.a;

@@ -486,7 +486,14 @@ def run_ours(args):
     launches = ctx.kernel_launches() - l0
     barrier()
     clocks = sampler.stop()
+    ms_own = ms
     ms = max_over_ranks(ms)
+    per_rank = [ms_own / args.steps]
+    if world > 1:                                   # every rank has its own frames: the slowest LM trajectory sets the step
+        t = torch.tensor([ms_own / args.steps], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(x.item()) for x in allt]
     work_all = sum_over_ranks(float(work))
     value = work_all / (ms * 1e-3) / 1e6
 
@@ -552,7 +559,8 @@ def run_ours(args):
                     "ms_per_step": ms_e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "gmm_plus_grid_fit_ms_per_step": ms / args.steps}
+            "gmm_plus_grid_fit_ms_per_step": ms / args.steps,
+            "per_rank_ms_per_step": per_rank}
     if not args.no_calib:
         line["calib_wall_ms"] = calib_leg(args, ctx, cfg, rank, world, barrier, max_over_ranks)
     if not args.no_config4:

@@ -33,6 +33,7 @@ WORKLOAD = "configs[1]: 20 synthetic Avia/Horizon raster frames x 500k pts, 8x6 
 def bench_config(frames_per_gpu, pts):
     """The same dict on both arms (the driver compares them)."""
     return {"workload": WORKLOAD, "frames_per_gpu": frames_per_gpu, "pts_per_frame": pts,
+            "per_gpu_data": "every rank works on its own copy of the same frames (identical work per GPU)",
             "l2": "steps: working set 2 x %d MB per GPU exceeds the 126 MB L2, no flush between steps; roofline launches: L2 flushed "
                   "(read of 2 x L2 of foreign data) before each" % (frames_per_gpu * pts * 16 // 2**20)}
 
@@ -63,8 +64,11 @@ def parse():
 
 
 def make_frames(n_frames, n_pts, rank):
+    """Weak scaling means the same work per GPU at every N. The work of a frame is its LM trajectory (10 to 332 pose evaluations
+    in this set), so every rank gets its own copy of the SAME 20 frames; with per-rank seeds the step of an N-GPU run was set by
+    whichever rank drew the longest trajectory (9.3 to 11.6 ms per rank at N = 8), which measures the draw, not the scaling."""
     from rclc_b200 import synth
-    frames, perts = synth.gridfit_batch(n_frames, n_pts, seed0=1000 + 100 * rank, pattern="raster")
+    frames, perts = synth.gridfit_batch(n_frames, n_pts, seed0=1000, pattern="raster")
     return frames, perts
 
 
@@ -251,7 +255,7 @@ def calib_leg(args, ctx, cfg, rank, world, barrier, max_over_ranks):
     """End-to-end calibration wall time through the C ABI with HOST buffers: rclc_calibrate_frames uploads every raw scan once,
     runs stage 1 + stage 2 and returns corners + extrinsic. Every rank calibrates its own 20 scans (weak scaling, no collective)."""
     import torch
-    scans, imgs = make_scans(args.calib_frames, args.calib_pts, first=rank * args.calib_frames)
+    scans, imgs = make_scans(args.calib_frames, args.calib_pts)          # the same 20 scans on every rank (see make_frames)
     pinned = [torch.from_numpy(s).pin_memory() for s in scans]
     host = [t.numpy() for t in pinned]
     for _ in range(3):

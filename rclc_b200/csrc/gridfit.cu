@@ -1432,10 +1432,15 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
     long long sw_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); sw_t[7] = gt; sw_t[0] = clock64(); }
 #endif
-    const int f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int parts = bv.parts;
-    const int task = blockIdx.x * kSweepWarps + warp;
+    // a frame's tasks live in grid column blockIdx.y (the solve: a CTA's warps then share the frame's LM staging area), or — plain
+    // sweeps — the tasks of all frames are packed into consecutive warps
+    const int per_frame = bv.geom.nt * parts * bv.npose_max;
+    const long long flat = (long long)blockIdx.x * kSweepWarps + warp;
+    const int f = bv.flat_tasks ? (int)(flat / per_frame) : (int)blockIdx.y;
+    const int task = bv.flat_tasks ? (int)(flat - (long long)f * per_frame) : (int)flat;
+    if (f >= bv.n_frames) return;
     // tasks of a frame: pose slot (slowest), target, part — the slots a round does not use are the CTAs at the end of the grid
     const int slot = task / (bv.geom.nt * parts), t = (task - slot * bv.geom.nt * parts) / parts, part = task % parts;
     if (slot >= bv.npose_max) return;
@@ -1595,7 +1600,7 @@ __device__ __forceinline__ void sweep_body(const BatchView& bv)
 #ifdef RCLC_SWEEP_TIMING
     if (lane == 0) {
         sw_t[5] = clock64();
-        const int w = (blockIdx.y * gridDim.x + blockIdx.x) * kSweepWarps + warp;
+        const int w = bv.flat_tasks ? (int)flat : (int)((blockIdx.y * gridDim.x + blockIdx.x) * kSweepWarps + warp);
         if (w < 8192) for (int q = 0; q < 8; ++q) g_sw_dbg[w * 8 + q] = sw_t[q];
     }
 #endif
@@ -1832,9 +1837,13 @@ static int launch_sweep_view(rclc_batch* b, BatchView& v, int n_frames, cudaStre
     }
     v.parts = sweep_parts(b, frames_in_flight, v.fuse_lm != 0);
     v.npose_max = v.fuse_lm ? kSpec : 1;
-    const int gx = (v.geom.nt * v.parts * v.npose_max + kSweepWarps - 1) / kSweepWarps;
-    if (v.fixed_frame >= 0) k_sweep_dense<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
-    else k_sweep<<<dim3((unsigned)gx, (unsigned)n_frames), kSweepThreads, kSweepSmem, st>>>(v);
+    v.flat_tasks = v.fuse_lm ? 0 : 1;
+    v.n_frames = n_frames;
+    const int per_frame = v.geom.nt * v.parts * v.npose_max;
+    dim3 grid((unsigned)((per_frame + kSweepWarps - 1) / kSweepWarps), (unsigned)n_frames);
+    if (v.flat_tasks) grid = dim3((unsigned)(((long long)per_frame * n_frames + kSweepWarps - 1) / kSweepWarps), 1u);
+    if (v.fixed_frame >= 0) k_sweep_dense<<<grid, kSweepThreads, kSweepSmem, st>>>(v);
+    else k_sweep<<<grid, kSweepThreads, kSweepSmem, st>>>(v);
     b->ctx->launches += 1;
     RCLC_CUDA(cudaGetLastError());
     return RCLC_OK;

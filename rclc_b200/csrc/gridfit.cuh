@@ -134,6 +134,8 @@ struct BatchView {
     double* evsum;                 // [F][kSpec][12] the summed terms of every pose slot: what Ceres' evaluation returns
     int* bin_done;                 // [F] CTAs of k_count that have finished their share of the histogram
     int* sweep_done;               // [F] pose slots of the current sweep that are summed (the last one runs the LM step)
+    int flat_tasks;                // plain sweeps: the tasks of ALL frames packed into consecutive warps (gridDim.y == 1) — no two idle
+                                   // warps per frame, and six full waves instead of 6.05 on a 128-frame batch
     int fuse_lm;                   // 1: k_sweep's last warp per frame advances the Ceres state machine
     int force_exact;               // all-fp64 sweep body for every frame (rclc_batch_set_exact_sweep: the A/B reference of the fast body)
     // geometry tables

@@ -68,7 +68,8 @@ int rclc_ctx_timer_start(rclc_ctx* ctx);
 int rclc_ctx_timer_stop_ms(rclc_ctx* ctx, float* ms_out);   /* records stop, synchronises, returns ms */
 int rclc_ctx_flush_l2(rclc_ctx* ctx);               /* writes a buffer larger than L2            */
 int64_t rclc_ctx_kernel_launches(rclc_ctx* ctx);    /* kernels launched by this ctx so far       */
-/* the batched grid-fit solve runs its frames as `groups` independent groups on as many streams (default 10, 1..32) */
+/* the batched grid-fit solve runs its frames as `groups` independent groups on as many streams (1..32; default: chosen per batch,
+ * 20 for frames of 200 k points and more, 10 for board-sized frames) */
 int rclc_ctx_set_solve_groups(rclc_ctx* ctx, int32_t groups);
 /* device time of the k_sweep kernel launched by the last rclc_batch_sweep (CUDA events recorded on the ctx stream
  * immediately before and after that launch; synchronises on the second one) */

@@ -71,7 +71,7 @@ struct rclc_ctx {
     int64_t l2_bytes = 0;
     int64_t launches = 0;
     int flush_parity = 0;
-    int solve_groups = 20;                             // independent frame groups (streams) of the grid-fit solve (one frame per group at 20 frames: a frame starts solving when IT has arrived)
+    int solve_groups = 0;                              // independent frame groups (streams) of the grid-fit solve; 0 = chosen per batch (gridfit.cu: solve_groups)
     std::vector<cudaStream_t> aux_streams;             // extra streams of the grouped grid-fit solve
     cudaEvent_t ev_sync = nullptr;
     cudaEvent_t ev_rank = nullptr;                     // "the cluster-rank list has left h_pin" (cluster.cu)

@@ -1916,8 +1916,10 @@ int rclc_batch_create(rclc_ctx* ctx, const rclc_config* cfg, int32_t n_frames, i
     v.parts = 1;
     RCLC_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
     RCLC_CUDA(cudaFuncSetAttribute(k_sweep_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem));
-    RCLC_CHECK(st_smem_bytes(hg.g.nt, hg.g.ncells) <= 110 * 1024, RCLC_ERR_UNSUPPORTED, "board too large for the streaming sweep's shared memory");
-    RCLC_CUDA(cudaFuncSetAttribute(k_sweep_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem_bytes(hg.g.nt, hg.g.ncells)));
+    // (the streaming kernel keeps a per-target table and the LM staging area in shared memory: boards beyond ~400 targets only get the
+    //  gather kernel — rclc_batch_set_stream_sweep then reports RCLC_ERR_UNSUPPORTED)
+    if (st_smem_bytes(hg.g.nt, hg.g.ncells) <= 72 * 1024)
+        RCLC_CUDA(cudaFuncSetAttribute(k_sweep_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem_bytes(hg.g.nt, hg.g.ncells)));
     const size_t F = n_frames, nt = hg.g.nt, ncell = hg.g.ncells, nfine = hg.g.nfine;
     auto fail = [&](const char* what) { set_last_error(what); rclc_batch_destroy(b); return RCLC_ERR_CUDA; };
     const size_t big = F * (size_t)v.frame_stride * 16;
@@ -2144,6 +2146,8 @@ int rclc_lab_st_timing(long long* out, int32_t n_warps)          // lab build on
 int rclc_batch_set_stream_sweep(rclc_batch* b, int32_t on)
 {
     RCLC_CHECK(b, RCLC_ERR_INVALID, "null batch");
+    RCLC_CHECK(!on || st_smem_bytes(b->v.geom.nt, b->v.geom.ncells) <= 72 * 1024, RCLC_ERR_UNSUPPORTED,
+               "board too large for the streaming sweep's shared memory (three CTAs per SM)");
     b->stream_sweep = on != 0;
     for (cudaGraphExec_t ge : b->round_graphs) cudaGraphExecDestroy(ge);      // the graphs hold the launches
     b->round_graphs.clear();

@@ -511,6 +511,29 @@ def test_stream_sweep_solve_equals_gather_solve(capi, ctx, cfg):
         assert a.last_final_cost == bb.last_final_cost
 
 
+def test_large_board_is_served_by_the_gather_sweep_only(capi, ctx, cfg, oracle, ocfg):
+    """A 16 x 12 board (356 targets): the streaming kernel's per-target table no longer fits three CTAs per SM, so the batch
+    refuses to switch to it (RCLC_ERR_UNSUPPORTED) and the gather kernel serves the board — bit-exact against the oracle. On a board
+    half way (12 x 8, 172 targets) both kernels run and agree."""
+    for W, H, stream_ok in ((16, 12, False), (12, 8, True)):
+        cw, ow = copy.copy(cfg), copy.copy(ocfg)
+        cw.board_width = W; cw.board_height = H; ow.board_width = W; ow.board_height = H
+        pts = synth.board_frame_cloud(200000, 9, W=W, H=H, pert=(0.004, -0.003, 0.25))
+        pose = np.array([[0.002, -0.001, 0.15]])
+        b = capi.Batch(ctx, cw, 1, len(pts))
+        b.upload(0, pts); b.bin(); b.sweep(pose)
+        acc = b.read_eval(want_acc=True)[2][0].copy()
+        assert np.array_equal(acc, oracle.gridfit_eval(ow, pts, pose[0], want_acc=True)[2])
+        if stream_ok:
+            b.set_stream_sweep(True)
+            b.sweep(pose)
+            assert np.array_equal(b.read_eval(want_acc=True)[2][0], acc)
+        else:
+            with pytest.raises(capi.RclcError):
+                b.set_stream_sweep(True)
+        b.close()
+
+
 def test_gridfit_points_beyond_the_lattice_box_come_into_reach(ctx, cfg, oracle, ocfg):
     """The reference rebuilds its kd-tree on the FULL cloud in every outer iteration (opt_grid_fitting.h:75-76, 107): points
     that start beyond the lattice box (board holder, surroundings in the board's plane) become neighbours of the outer targets

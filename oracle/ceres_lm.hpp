@@ -7,8 +7,10 @@
 // Ceres is a third-party dependency that is NOT vendored in /root/reference and NOT pinned
 // (CMakeLists.txt:12 `find_package(Ceres REQUIRED)`), so this follows the published algorithm of
 // Ceres 1.14 / 2.x `TrustRegionMinimizer` + `LevenbergMarquardtStrategy` + `TrustRegionStepEvaluator`
-// + `Corrector` + `HuberLoss`.  PARITY UNPINNED: the reference holds no test
-// or golden vector for any of this.
+// + `Corrector` + `HuberLoss`.  PARITY UNPINNED against the reference: it holds no
+// test or golden vector for any of this. What there is: the minimiser reproduces the two solver logs the Ceres tutorial
+// prints, digit for digit (tests/test_oracle_ceres_logs.py), and reaches scipy's minimum on the plane fit and the extrinsic
+// solve (tests/test_oracle_scipy_pins.py).
 //
 // All residual blocks in the reference have exactly ONE residual, which this restatement exploits:
 // a problem is `m` scalar residual blocks over one dense parameter vector.
@@ -48,6 +50,9 @@ struct LMSummary {
     int num_successful_steps = 0;
     int num_cost_evals = 0;          // distinct points at which residuals were evaluated
     int num_jac_evals = 0;           // evaluations with Jacobians
+    // One entry per Ceres IterationSummary (iteration 0 included): its `cost` and `trust_region_radius`
+    // columns, so that a run can be laid beside a published Ceres log (tests/test_oracle_ceres_logs.py).
+    std::vector<double> trace_cost, trace_radius;
 };
 
 // HuberLoss::Evaluate (ceres loss_function.cc).
@@ -250,6 +255,8 @@ inline LMSummary lm_minimize(const LMProblem& P, const LMOptions& opt, double* x
         return sum;
     }
     sum.initial_cost = x_cost;
+    sum.trace_cost.push_back(x_cost);
+    sum.trace_radius.push_back(radius);
     double min_iter_cost = x_cost;          // SetSummaryFinalCost: min over iteration summaries
     double minimum_cost = std::numeric_limits<double>::max();
     bool step_is_successful = true;         // iteration 0 is marked successful
@@ -313,6 +320,8 @@ inline LMSummary lm_minimize(const LMProblem& P, const LMOptions& opt, double* x
             radius *= 0.5;                      // StepIsInvalid
             reuse_diagonal = true;
             min_iter_cost = std::min(min_iter_cost, x_cost);
+            sum.trace_cost.push_back(x_cost);
+            sum.trace_radius.push_back(radius);
             continue;
         }
         for (int c = 0; c < nl; ++c) delta[c] = step[c] * scale[c];
@@ -351,11 +360,15 @@ inline LMSummary lm_minimize(const LMProblem& P, const LMOptions& opt, double* x
             decrease_factor = 2.0;
             reuse_diagonal = false;
             min_iter_cost = std::min(min_iter_cost, x_cost);
+            sum.trace_cost.push_back(x_cost);
+            sum.trace_radius.push_back(radius);
         } else {
             min_iter_cost = std::min(min_iter_cost, cand_cost);   // iteration_summary_.cost = candidate_cost_
             radius = radius / decrease_factor;                    // StepRejected
             decrease_factor *= 2.0;
             reuse_diagonal = true;
+            sum.trace_cost.push_back(cand_cost);
+            sum.trace_radius.push_back(radius);
         }
     }
     // Final bookkeeping for early `return`s inside the loop: the last successful iterate may not

@@ -239,3 +239,13 @@ def eular_cluster_iter(cfg, pts, thd):
     cen = np.zeros((cfg.board_width * cfg.board_height, 3)); n = C.c_int32()
     rc = lib().orc_eular_cluster_iter(C.byref(cfg), _p(pts), stride, ioff, C.c_int64(len(pts)), C.c_double(thd), _p(cen), C.byref(n))
     return rc, cen[:n.value].copy()
+
+
+def lm_tutorial(which, x0, linear_solver=0, max_iterations=100):
+    """ceres_lm.hpp on a Ceres tutorial problem (0: f(x) = 10 - x, 1: Powell's function): (x, cost per iteration, trust-region
+    radius per iteration, termination) — the columns a Ceres log prints, iteration 0 first."""
+    x = np.array(x0, np.float64); cost = np.zeros(256); rad = np.zeros(256); n = C.c_int32(); term = C.c_int32()
+    rc = lib().orc_lm_tutorial(C.c_int(which), C.c_int(linear_solver), _p(x), C.c_int(max_iterations), _p(cost), _p(rad), C.c_int32(256),
+                               C.byref(n), C.byref(term))
+    assert rc == 0 and n.value <= 256
+    return x, cost[:n.value].copy(), rad[:n.value].copy(), term.value

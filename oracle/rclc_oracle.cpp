@@ -1268,4 +1268,54 @@ int orc_calc_laser_coor(const rclc_config* cfg, const double* cen, int32_t n, co
     return 0;
 }
 
+// The two problems of the Ceres tutorial whose solver logs are printed in the Ceres documentation
+// (docs/source/nnls_tutorial.rst: "Hello World!" f(x) = 10 - x from x = 0.5, and Powell's function
+// from (3, -1, 0, 1); DENSE_QR there, one residual per block like every block of the reference;
+// linear_solver 1 runs the same problem through the DENSE_NORMAL_CHOLESKY branch the pose refinement uses).
+// Runs the restated minimiser on them and hands back the per-iteration `cost` and `tr_radius`
+// columns, which tests/test_oracle_ceres_logs.py lays beside the published ones.
+int orc_lm_tutorial(int which, int linear_solver, double* x_io, int max_iterations, double* cost_trace, double* radius_trace, int32_t cap,
+                    int32_t* n_trace, int32_t* termination)
+{
+    orc::LMProblem P;
+    if (which == 0) {
+        P.m = 1; P.n = 1; P.nl = 1;
+        P.evaluate = [](const double* x, double* cost, double* res, double* jac) {
+            const double r = 10.0 - x[0];
+            if (res) res[0] = r;
+            if (jac) jac[0] = -1.0;
+            *cost = 0.5 * r * r;
+            return true;
+        };
+    } else if (which == 1) {
+        P.m = 4; P.n = 4; P.nl = 4;
+        P.evaluate = [](const double* x, double* cost, double* res, double* jac) {
+            const double s5 = std::sqrt(5.0), s10 = std::sqrt(10.0);
+            const double f[4] = {x[0] + 10.0 * x[1], s5 * (x[2] - x[3]), (x[1] - 2.0 * x[2]) * (x[1] - 2.0 * x[2]),
+                                 s10 * (x[0] - x[3]) * (x[0] - x[3])};
+            if (res) for (int i = 0; i < 4; ++i) res[i] = f[i];
+            if (jac) {
+                for (int i = 0; i < 16; ++i) jac[i] = 0.0;
+                jac[0] = 1.0; jac[1] = 10.0;
+                jac[4 + 2] = s5; jac[4 + 3] = -s5;
+                jac[8 + 1] = 2.0 * (x[1] - 2.0 * x[2]); jac[8 + 2] = -4.0 * (x[1] - 2.0 * x[2]);
+                jac[12 + 0] = 2.0 * s10 * (x[0] - x[3]); jac[12 + 3] = -2.0 * s10 * (x[0] - x[3]);
+            }
+            *cost = 0.5 * (f[0] * f[0] + f[1] * f[1] + f[2] * f[2] + f[3] * f[3]);
+            return true;
+        };
+    } else {
+        return 1;
+    }
+    orc::LMOptions opt;
+    opt.linear_solver = linear_solver == 1 ? orc::DENSE_NORMAL_CHOLESKY : orc::DENSE_QR;
+    opt.max_num_iterations = max_iterations;
+    const orc::LMSummary sum = orc::lm_minimize(P, opt, x_io);
+    const int32_t n = (int32_t)std::min<size_t>(sum.trace_cost.size(), (size_t)cap);
+    for (int32_t i = 0; i < n; ++i) { cost_trace[i] = sum.trace_cost[(size_t)i]; radius_trace[i] = sum.trace_radius[(size_t)i]; }
+    *n_trace = (int32_t)sum.trace_cost.size();
+    *termination = sum.termination;
+    return 0;
+}
+
 } // extern "C"

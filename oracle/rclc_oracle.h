@@ -117,6 +117,12 @@ int orc_euclidean_cluster(const void* pts, int stride, int64_t n, double tol, in
  * board frame T_bl (row-major 4x4, board <- laser) from the centroids of the black blocks and the board plane. Returns 0. */
 int orc_calc_laser_coor(const rclc_config* cfg, const double* centroids, int32_t n, const double plane[4], double Tbl_out[16]);
 
+/* The two Ceres tutorial problems whose solver logs the Ceres documentation prints (0: f(x) = 10 - x, 1: Powell's function), run
+ * through ceres_lm.hpp (linear_solver 0 = DENSE_QR as published, 1 = DENSE_NORMAL_CHOLESKY): the `cost` and `tr_radius` column of every iteration, iteration 0 included. The pin of
+ * the restated minimiser against published output of the dependency itself. Returns 0. */
+int orc_lm_tutorial(int which, int linear_solver, double* x_io, int max_iterations, double* cost_trace, double* radius_trace, int32_t cap,
+                    int32_t* n_trace, int32_t* termination);
+
 /* The reference's host-side chains over the primitives above (rclc_pipeline.cpp): eular_cluster_iter (pc_process.h:104-211;
  * centroids_out has room for board_width * board_height doubles x 3), est_board_corner (pc_process.h:583-646; pts_io float4
  * {x, y, z, I}, stride 16, modified like the reference's cloud), the per-cloud body of apps/BoardSegmentation.cpp:45-165 (out:

@@ -41,7 +41,52 @@ struct LMOptions {
     double max_lm_diagonal = 1e32;
     int max_num_consecutive_invalid_steps = 5;
     bool jacobi_scaling = true;
+    // The radius update takes pow(2 rho - 1, 3) from libm in Ceres. true: the correctly rounded cube instead (rn::cube) — what a
+    // correctly rounding libm returns (glibc <= 2.27 did; glibc 2.39 here differs from it by one ulp in 0.08 % of calls), and a
+    // value a GPU can reproduce bit for bit. Set by the extrinsic solve only (rclc_oracle.cpp orc_pose_refine).
+    bool correctly_rounded_libm = false;
 };
+
+// Correctly rounded stand-ins for the three libm calls of the extrinsic solve (pow(q, 3), sin, cos), in double-double arithmetic:
+// the values libm is specified to approximate, independent of the libm at hand. tests/test_oracle_restatement.py counts how often
+// this glibc differs from them (by one ulp, in 1e-3 .. 1e-6 of calls) and what that does to the solve.
+namespace rn {
+struct dd { double h, l; };
+inline dd norm(double s, double e) { const double h = s + e; return {h, e - (h - s)}; }
+inline dd mul(dd a, dd b) { const double p = a.h * b.h; double e = std::fma(a.h, b.h, -p); e = e + (a.h * b.l + a.l * b.h); return norm(p, e); }
+inline dd add(dd a, dd b) { const double s = a.h + b.h, v = s - a.h; double e = (a.h - (s - v)) + (b.h - v); e = e + (a.l + b.l); return norm(s, e); }
+inline double cube(double q)
+{
+    const double q2h = q * q, q2l = std::fma(q, q, -q2h), ph = q2h * q, pl = std::fma(q2h, q, -ph);
+    return ph + (pl + q2l * q);
+}
+// (-1)^k / (2k+1)! and (-1)^k / (2k)! as double-doubles
+static const dd kSin[15] = {
+    {0x1.0000000000000p+0, 0x0.0p+0}, {-0x1.5555555555555p-3, -0x1.5555555555555p-57}, {0x1.1111111111111p-7, 0x1.1111111111111p-63},
+    {-0x1.a01a01a01a01ap-13, -0x1.a01a01a01a01ap-73}, {0x1.71de3a556c734p-19, -0x1.c154f8ddc6c00p-73}, {-0x1.ae64567f544e4p-26, 0x1.c062e06d1f209p-80},
+    {0x1.6124613a86d09p-33, 0x1.f28e0cc748ebep-87}, {-0x1.ae7f3e733b81fp-41, -0x1.1d8656b0ee8cbp-97}, {0x1.952c77030ad4ap-49, 0x1.ac981465ddc6cp-103},
+    {-0x1.2f49b46814157p-57, -0x1.2650f61dbdcb4p-112}, {0x1.71b8ef6dcf572p-66, -0x1.d043ae40c4647p-120}, {-0x1.761b41316381ap-75, 0x1.3423c7d91404fp-130},
+    {0x1.3f3ccdd165fa9p-84, -0x1.58ddadf344487p-139}, {-0x1.d1ab1c2dccea3p-94, -0x1.054d0c78aea14p-149}, {0x1.259f98b4358adp-103, 0x1.eaf8c39dd9bc5p-157}};
+static const dd kCos[15] = {
+    {0x1.0000000000000p+0, 0x0.0p+0}, {-0x1.0000000000000p-1, 0x0.0p+0}, {0x1.5555555555555p-5, 0x1.5555555555555p-59},
+    {-0x1.6c16c16c16c17p-10, 0x1.f49f49f49f49fp-65}, {0x1.a01a01a01a01ap-16, 0x1.a01a01a01a01ap-76}, {-0x1.27e4fb7789f5cp-22, -0x1.cbbc05b4fa99ap-76},
+    {0x1.1eed8eff8d898p-29, -0x1.2aec959e14c06p-83}, {-0x1.93974a8c07c9dp-37, -0x1.05d6f8a2efd1fp-92}, {0x1.ae7f3e733b81fp-45, 0x1.1d8656b0ee8cbp-101},
+    {-0x1.6827863b97d97p-53, -0x1.eec01221a8b0bp-107}, {0x1.e542ba4020225p-62, 0x1.ea72b4afe3c2fp-120}, {-0x1.0ce396db7f853p-70, 0x1.aebcdbd20331cp-124},
+    {0x1.f2cf01972f578p-80, -0x1.9ada5fcc1ab14p-135}, {-0x1.88e85fc6a4e5ap-89, 0x1.71c37ebd16540p-143}, {0x1.0a18a2635085dp-98, 0x1.b9e2e28e1aa54p-153}};
+// sin and cos of 0 <= x <= 0.5 by their Taylor series in double-double (2^-100 and better), rounded once; libm beyond
+inline void sincos(double x, double* sn, double* cs)
+{
+    if (!(x <= 0.5)) { *sn = std::sin(x); *cs = std::cos(x); return; }
+    const double uh = x * x;
+    const dd u = {uh, std::fma(x, x, -uh)};
+    const int n = uh < 0x1p-36 ? 3 : (uh < 0x1p-20 ? 5 : (uh < 0x1p-8 ? 9 : 14));    // terms to 2^-110 of the sum
+    dd S = kSin[n], Cc = kCos[n];
+    for (int k = n - 1; k >= 0; --k) { S = add(mul(S, u), kSin[k]); Cc = add(mul(Cc, u), kCos[k]); }
+    const dd xs = mul(S, dd{x, 0.0});
+    *sn = xs.h + xs.l;
+    *cs = Cc.h + Cc.l;
+}
+} // namespace rn
 
 struct LMSummary {
     double initial_cost = 0, final_cost = 0;
@@ -355,7 +400,7 @@ inline LMSummary lm_minimize(const LMProblem& P, const LMOptions& opt, double* x
             x_norm = norm(x);
             if (!eval_grad_jac(false, false)) { sum.termination = FAILURE; break; }
             step_is_successful = true;
-            radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+            radius = radius / std::max(1.0 / 3.0, 1.0 - (opt.correctly_rounded_libm ? rn::cube(2.0 * rel - 1.0) : std::pow(2.0 * rel - 1.0, 3)));
             radius = std::min(opt.max_trust_region_radius, radius);
             decrease_factor = 2.0;
             reuse_diagonal = false;

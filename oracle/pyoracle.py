@@ -164,6 +164,20 @@ def pose_refine(cfg, pc_corners, img_norm, Tcl):
     return rc, Tcl, c0.value, c1.value, it.value
 
 
+def pose_refine_ex(cfg, pc_corners, img_norm, Tcl, libm_mode=0, linear_solver=0):
+    """pose_refine with a choice of libm (0: correctly rounded pow / sin / cos, pose_refine's definition; 1: this machine's), of the linear solver (0: DENSE_NORMAL_CHOLESKY, 1: DENSE_QR)
+    and the iteration log: (rc, Tcl, initial cost, final cost, iterations, cost per iteration, trust-region radius per iteration)."""
+    pc = np.ascontiguousarray(pc_corners, np.float64); im = np.ascontiguousarray(img_norm, np.float64)
+    F, Cn = pc.shape[0], pc.shape[1]
+    Tcl = np.array(Tcl, np.float64)
+    c0 = C.c_double(); c1 = C.c_double(); it = C.c_int32(); n = C.c_int32()
+    cost = np.zeros(1100); rad = np.zeros(1100)
+    rc = lib().orc_pose_refine_ex(C.byref(cfg), _p(pc), _p(im), F, Cn, _p(Tcl), C.byref(c0), C.byref(c1), C.byref(it), C.c_int(libm_mode), C.c_int(linear_solver),
+                                  _p(cost), _p(rad), C.c_int32(1100), C.byref(n))
+    m = min(n.value, 1100)
+    return rc, Tcl, c0.value, c1.value, it.value, cost[:m].copy(), rad[:m].copy()
+
+
 def project_colorize(cfg, pts, T_cl, bgr):
     pts, stride, _ = _cloud(pts); n = pts.shape[0]
     T = np.ascontiguousarray(T_cl, np.float32); bgr = np.ascontiguousarray(bgr, np.uint8)

@@ -391,12 +391,16 @@ T pose_residual(const T* q, const T* t, const double* pc, const double* img, int
 }
 
 // ceres::EigenQuaternionParameterization (storage x,y,z,w)
-void quat_plus(const double* x, const double* delta, double* out)
+// rn_libm: sin and cos correctly rounded (ceres_lm.hpp rn::sincos) instead of this libm's
+void quat_plus(const double* x, const double* delta, double* out, bool rn_libm)
 {
     const double norm_delta = std::sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
     if (norm_delta > 0.0) {
-        const double s = std::sin(norm_delta) / norm_delta;
-        const double dw = std::cos(norm_delta), dx = s * delta[0], dy = s * delta[1], dz = s * delta[2];
+        double sin_nd, cos_nd;
+        if (rn_libm) orc::rn::sincos(norm_delta, &sin_nd, &cos_nd);
+        else { sin_nd = std::sin(norm_delta); cos_nd = std::cos(norm_delta); }
+        const double s = sin_nd / norm_delta;
+        const double dw = cos_nd, dx = s * delta[0], dy = s * delta[1], dz = s * delta[2];
         const double xw = x[3], xx = x[0], xy = x[1], xz = x[2];
         // Eigen quaternion product a*b
         const double w = dw * xw - dx * xx - dy * xy - dz * xz;
@@ -820,9 +824,16 @@ int orc_pose_eval(const double* pc_corners, const double* img_norm, int F, int C
 }
 
 // include/opt/opt_reprj_calib.h:21-66
-int orc_pose_refine(const rclc_config* cfg, const double* pc_corners, const double* img_norm, int F, int C,
-                    double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations)
+// libm_mode 0: pow / sin / cos of the solve correctly rounded (ceres_lm.hpp rn::) — the oracle's definition, reproducible on a
+// GPU bit for bit; 1: this machine's libm, as a Ceres build here would call it (differs by one ulp in 1e-3 .. 1e-6 of calls; on
+// few-frame problems that is enough to end the capped solve elsewhere — tests/test_oracle_restatement.py measures it).
+// linear_solver 0: DENSE_NORMAL_CHOLESKY as the reference sets it; 1: DENSE_QR — the same steps up to rounding, for the sensitivity test.
+// cost_trace / radius_trace (cap entries, may be null): the iteration log's `cost` and `tr_radius` columns.
+int orc_pose_refine_ex(const rclc_config* cfg, const double* pc_corners, const double* img_norm, int F, int C,
+                       double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations, int libm_mode, int linear_solver,
+                       double* cost_trace, double* radius_trace, int32_t cap, int32_t* n_trace)
 {
+    const bool rn_libm = libm_mode == 0;
     orc::LMProblem P;
     P.m = F; P.n = 7; P.nl = 6;
     const double huber_a = cfg->pose_huber_a;
@@ -840,20 +851,32 @@ int orc_pose_refine(const rclc_config* cfg, const double* pc_corners, const doub
         *cost = total;
         return true;
     };
-    P.plus = [](const double* x, const double* d, double* out) {
-        quat_plus(x, d, out);
+    P.plus = [rn_libm](const double* x, const double* d, double* out) {
+        quat_plus(x, d, out, rn_libm);
         for (int k = 0; k < 3; ++k) out[4 + k] = x[4 + k] + d[3 + k];
     };
     orc::LMOptions opt;
-    opt.linear_solver = orc::DENSE_NORMAL_CHOLESKY;
+    opt.linear_solver = linear_solver == 1 ? orc::DENSE_QR : orc::DENSE_NORMAL_CHOLESKY;      // the reference: DENSE_NORMAL_CHOLESKY (opt_reprj_calib.h:55)
     opt.max_num_iterations = cfg->pose_max_lm_iters;
     opt.function_tolerance = cfg->pose_function_tol;
+    opt.correctly_rounded_libm = rn_libm;
     const orc::LMSummary sum = orc::lm_minimize(P, opt, Tcl_io);
     if (std::getenv("RCLC_ORC_DEBUG")) std::fprintf(stderr, "[orc] pose_refine: %d iterations, %d successful steps, %d cost evaluations\n", sum.num_iterations, sum.num_successful_steps, sum.num_cost_evals);
     if (initial_cost) *initial_cost = sum.initial_cost;
     if (final_cost) *final_cost = sum.final_cost;
     if (iterations) *iterations = sum.num_iterations;
+    if (n_trace) *n_trace = (int32_t)sum.trace_cost.size();
+    for (int32_t i = 0; i < cap && i < (int32_t)sum.trace_cost.size(); ++i) {
+        if (cost_trace) cost_trace[i] = sum.trace_cost[(size_t)i];
+        if (radius_trace) radius_trace[i] = sum.trace_radius[(size_t)i];
+    }
     return sum.termination == orc::FAILURE ? 1 : 0;
+}
+
+int orc_pose_refine(const rclc_config* cfg, const double* pc_corners, const double* img_norm, int F, int C,
+                    double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations)
+{
+    return orc_pose_refine_ex(cfg, pc_corners, img_norm, F, C, Tcl_io, initial_cost, final_cost, iterations, 0, 0, nullptr, nullptr, 0, nullptr);
 }
 
 // apps/Calibrate.cpp:134-148, include/PinholeCam.h:93-110

@@ -87,6 +87,11 @@ int orc_pose_eval(const double* pc_corners, const double* img_norm, int F, int C
 /* opt_reprj_calib.h:21-66 */
 int orc_pose_refine(const rclc_config* cfg, const double* pc_corners, const double* img_norm, int F, int C,
                     double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations);
+/* The same solve with a choice of libm (0: pow / sin / cos correctly rounded, the definition orc_pose_refine uses; 1: this machine's
+ * libm), of the linear solver (0: DENSE_NORMAL_CHOLESKY, the reference's; 1: DENSE_QR) and the iteration log's cost / trust-region-radius columns (cap entries each, may be null). */
+int orc_pose_refine_ex(const rclc_config* cfg, const double* pc_corners, const double* img_norm, int F, int C,
+                       double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations, int libm_mode, int linear_solver,
+                       double* cost_trace, double* radius_trace, int32_t cap, int32_t* n_trace);
 
 /* Calibrate.cpp:134-148 + PinholeCam.h:93-110 : transform (float), project, FoV, gather BGR->RGB.
  * xyz stride as above; rgb_out[n*3] (untouched when not in FoV), pix_out[n*2] int32 (cvRound), infov_out[n]. */

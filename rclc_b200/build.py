@@ -11,6 +11,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function,-fopenmp", "-ccbin", "/usr/bin/g++"] + \
     os.environ.get("RCLC_EXTRA_NVCC_FLAGS", "").split()          # experiments only (e.g. -DRCLC_SWEEP_TIMING)
+# pose.cu spells out the oracle's arithmetic operation by operation: no multiply-add is fused that the source does not fuse
+FILE_FLAGS = {"pose.cu": ["-fmad=false"]}
 
 
 def _stale():
@@ -35,7 +37,7 @@ def build(force=False, verbose=False):
                 os.path.getmtime(d) for d in [s] + glob.glob(os.path.join(CSRC, "*.cuh")) +
                 glob.glob(os.path.join(HERE, "..", "include", "*.h"))):
             continue
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [NVCC] + FLAGS + FILE_FLAGS.get(os.path.basename(s), []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for s, p in procs:
         out, _ = p.communicate()

@@ -330,28 +330,35 @@ def _pose_problem(oracle, F, seed=9, noise=1e-4):
     return pc, img, T0, np.r_[q, t]
 
 
-@pytest.mark.parametrize("F", [5, 20, 256])
-def test_pose_eval_and_refine(ctx, cfg, oracle, ocfg, F):
-    pc, img, T0, Tgt = _pose_problem(oracle, F)
+@pytest.mark.parametrize("F,seed", [(5, 9), (20, 9), (64, 3), (256, 9), (300, 4), (700, 5), (1700, 6)])
+def test_pose_refine_is_the_oracles_bit_for_bit(ctx, cfg, oracle, ocfg, F, seed):
+    """The extrinsic solve is held to the oracle BIT FOR BIT: every frame's residual and local Jacobian, and then the whole
+    Levenberg-Marquardt run - iteration count, initial and final cost, the extrinsic's seven doubles - in both launch shapes.
+    Nothing weaker is stable: on few-frame problems the solve spends its 1000-iteration cap wandering over a non-smooth floor and
+    the capped iterate follows the last bit of every sum (tests/test_pose_sensitivity.py: the oracle itself moves by 0.1 - 6 mm
+    under a rounding-level change of its own arithmetic). pose.cu therefore runs the oracle's operations in the oracle's order
+    (no fused multiply-add, frame-order sums, correctly rounded pow / sin / cos on both sides). 1700 frames: the frames' rows no
+    longer fit shared memory and live in global memory."""
+    pc, img, T0, Tgt = _pose_problem(oracle, F, seed=seed)
     r0, j0 = oracle.pose_eval(pc, img, T0)
     r1, j1 = ctx.pose_eval(pc, img, T0)
-    np.testing.assert_allclose(r1, r0, rtol=1e-12); np.testing.assert_allclose(j1, j0, rtol=1e-9, atol=1e-12)
+    assert r1.tobytes() == r0.tobytes() and j1.tobytes() == j0.tobytes()
     rc0, Ta, c0a, c1a, ita = oracle.pose_refine(ocfg, pc, img, T0)
-    rc1, Tb, c0b, c1b, itb = ctx.pose_refine(cfg, pc, img, T0)
-    assert rc0 == rc1 == 0
-    np.testing.assert_allclose(c0b, c0a, rtol=1e-11)
-    # bar: extrinsic within 1e-4 rad and 0.1 mm of the reference path
-    assert np.abs(Tb[4:] - Ta[4:]).max() < 1e-4
-    dq = 2 * np.linalg.norm(Tb[:4] * np.sign(Tb[3]) - Ta[:4] * np.sign(Ta[3]))
-    assert dq < 1e-4
-    # iteration counts may differ: this LM wanders ~1000 iterations around a non-smooth minimum (sum of norms),
-    # so 1e-16 differences in summation order change when it stops; the bar is on the extrinsic itself — and on the CONVERGED
-    # COST: both solves end in the same valley, at the same objective value to the flatness of its floor (the oracle's own
-    # value is pinned against scipy's minimiser in tests/test_oracle_scipy_pins.py)
-    print(f"pose refine F={F}: final cost {c1b:.12e} (oracle {c1a:.12e}), {itb} / {ita} iterations")
-    # (measured on B200: 3e-3 relative at 5 frames — the reference's cap, under-determined, SURVEY F7 — 9e-4 at 20; neither solve
-    #  converges in Ceres' sense, both stop at the iteration cap while wandering over the kinks of the floor)
-    assert abs(c1b - c1a) <= 5e-3 * c1a and c1b < 0.01 * c0b
+    assert rc0 == 0
+    try:
+        for shape in (0, 1, 2):      # the default choice | one CTA | the cluster at any size
+            ctx.set_pose_test_hooks(shape=shape)
+            rc1, Tb, c0b, c1b, itb = ctx.pose_refine(cfg, pc, img, T0)
+            assert rc1 == 0
+            assert (itb, c0b, c1b) == (ita, c0a, c1a), (shape, itb, ita, c1b, c1a)
+            assert Tb.tobytes() == Ta.tobytes(), (shape, np.abs(Tb - Ta).max())
+    finally:
+        ctx.set_pose_test_hooks()
+    # and the solve does its job: the cost falls by three orders; from 64 frames on the extrinsic is the synthetic truth to 0.2 mm /
+    # 1e-4 rad (20 frames: 0.9 mm, 5 frames: 3 cm - under-determined, SURVEY F7)
+    assert c1a < 0.01 * c0a
+    if F >= 64:
+        assert np.abs(Ta[4:] - Tgt[4:]).max() < 2e-4 and 2 * np.linalg.norm(Ta[:4] * np.sign(Ta[3]) - Tgt[:4] * np.sign(Tgt[3])) < 1e-4
 
 
 @pytest.mark.parametrize("F,seed", [(5, 9), (20, 9), (64, 3), (256, 9), (300, 4), (700, 5)])
@@ -362,11 +369,11 @@ def test_pose_refine_cluster_frame_split_is_exact(ctx, cfg, oracle, F, seed, mon
     pc, img, T0, _ = _pose_problem(oracle, F, seed=seed)
     out = []
     try:
-        for dbg in (0, 1, 2):        # 1: whole-frame evaluation by one thread; 2: the one-CTA kernel's block reduction on rank 0
+        for dbg in (0, 1):           # 1: whole-frame evaluation by one thread
             ctx.set_pose_test_hooks(shape=2, cluster_debug=dbg)
             rc, T, c0, c1, it = ctx.pose_refine(cfg, pc, img, T0)
             out.append((rc, T.tobytes(), c0, c1, it))
-        assert out[0] == out[1] == out[2]
+        assert out[0] == out[1]
         ctx.set_pose_test_hooks()
         r0, j0 = ctx.pose_eval(pc, img, T0)
         ctx.set_pose_test_hooks(eval_split=1)

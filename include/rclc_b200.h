@@ -166,7 +166,9 @@ int rclc_ransac_plane_score(rclc_ctx* ctx, const void* pts, int stride, int64_t 
 int rclc_ransac_plane_select(rclc_ctx* ctx, const void* pts, int stride, int64_t n, const float plane[4], double thr,
                              uint8_t* mask_out, float refined_out[4], float centroid_out[3], int64_t* n_inliers);
 
-/* ---- pose_reprj_opt (opt_reprj_calib.h:21-66). Tcl = (qx,qy,qz,qw,tx,ty,tz) in/out ---- */
+/* ---- pose_reprj_opt (opt_reprj_calib.h:21-66). Tcl = (qx,qy,qz,qw,tx,ty,tz) in/out. The solve runs Ceres' Levenberg-Marquardt on the
+ * device in the arithmetic of the CPU oracle, operation by operation (no fused multiply-add, sums in frame order, correctly rounded
+ * pow / sin / cos): iteration count, costs and extrinsic are the oracle's bit for bit. ---- */
 int rclc_pose_eval(rclc_ctx* ctx, const double* pc_corners, const double* img_norm, int32_t F, int32_t C,
                    const double Tcl[7], double* residuals, double* jac6);
 int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_corners, const double* img_norm,
@@ -174,8 +176,8 @@ int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_cor
 
 /* Test hooks of the pose refine (set per context, never read from the environment): shape 0 = automatic (a thread-block cluster from
  * 512 corner observations up), 1 = one CTA, 2 = the cluster at any size — both shapes return the same bits; cluster_debug 1 = whole-frame
- * evaluation on the cluster, 2 = the one-CTA reduction on rank 0; eval_split 1 = rclc_pose_eval through the cluster's per-corner /
- * per-frame split. tests/test_gpu_parity.py uses them to prove the bit-identity of the shapes. */
+ * evaluation on the cluster (one thread per frame instead of the per-corner / per-frame split); eval_split 1 = rclc_pose_eval through
+ * the cluster's per-corner / per-frame split. tests/test_gpu_parity.py uses them to prove the bit-identity of the shapes. */
 int rclc_ctx_set_pose_test_hooks(rclc_ctx* ctx, int32_t shape, int32_t cluster_debug, int32_t eval_split);
 
 /* ---- colourise loop (Calibrate.cpp:134-148, PinholeCam.h:93-110) ---- */

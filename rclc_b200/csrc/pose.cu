@@ -306,17 +306,30 @@ __device__ __noinline__ void pose_frame_phase(const double* Tcl, const double* c
 #define FRAME_TICK(k) do { } while (0)
 #endif
     const int i_add = comp == 0 ? 0 : (1 + comp) * os, i_dc = (9 + comp) * os;      // comp 0: fg | d.a; k + 1: numerator k | d.v[k]
-    double res = 0.0, dmax_a = 0.0, dmax_c = 0.0;
+    // depth_max: the running "if (d > depth_max) depth_max = d" ends on the FIRST corner that attains the largest norm (nothing, if
+    // none exceeds 0). Found here without the 35-long chain: every lane scans a stride of the corners, three exchanges settle it
+    // (larger norm wins, the smaller index on a tie). The norms are >= +0, so their bit patterns order like their values and
+    // the comparisons are integer ones (a NaN norm wins here and loses there; the frame's residual is NaN either way).
+    long long best = 0;                                             // bits of +0.0
+    int bi = -1;
+    for (int i = comp; i < C; i += 8) {
+        const long long da = __double_as_longlong(c0[9 * os + i]);
+        if (da > best) { best = da; bi = i; }
+    }
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1) {
+        const long long ob = __shfl_xor_sync(kAll, best, o, 8);
+        const int oi = __shfl_xor_sync(kAll, bi, o, 8);
+        const bool take = ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi));
+        best = take ? ob : best;
+        bi = take ? oi : bi;
+    }
+    const double dmax_a = __longlong_as_double(best), dmax_c = bi >= 0 ? c0[i_dc + bi] : 0.0;
+    double res = 0.0;
 #pragma unroll 5
     for (int i = 0; i < C; ++i) {
         const double* o = c0 + i;
-        const double da = o[9 * os], dc = o[i_dc], num = o[i_add], gi = comp == 0 ? 1.0 : o[os];
-        // da > dmax_a on the bit patterns: both are norms (>= +0), for which the integer order is the floating-point order, and an
-        // integer compare-and-select is a short link in this 35-long chain where DSETP is a long one (a NaN norm wins here and
-        // loses there; the frame's residual is NaN either way)
-        const bool farther = __double_as_longlong(da) > __double_as_longlong(dmax_a);
-        dmax_a = farther ? da : dmax_a;
-        dmax_c = farther ? dc : dmax_c;
+        const double num = o[i_add], gi = comp == 0 ? 1.0 : o[os];
         res = res + num * gi;                                       // comp 0: res.a + fg (times 1.0: exact)
     }
     FRAME_TICK(6);

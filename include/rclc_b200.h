@@ -175,7 +175,7 @@ int rclc_pose_refine(rclc_ctx* ctx, const rclc_config* cfg, const double* pc_cor
                      int32_t F, int32_t C, double* Tcl_io, double* initial_cost, double* final_cost, int32_t* iterations);
 
 /* Test hooks of the pose refine (set per context, never read from the environment): shape 0 = automatic (a thread-block cluster from
- * 512 corner observations up), 1 = one CTA, 2 = the cluster at any size — both shapes return the same bits; cluster_debug 1 = whole-frame
+ * 64 corner observations up), 1 = one CTA, 2 = the cluster at any size — both shapes return the same bits; cluster_debug 1 = whole-frame
  * evaluation on the cluster (one thread per frame instead of the per-corner / per-frame split); eval_split 1 = rclc_pose_eval through
  * the cluster's per-corner / per-frame split. tests/test_gpu_parity.py uses them to prove the bit-identity of the shapes. */
 int rclc_ctx_set_pose_test_hooks(rclc_ctx* ctx, int32_t shape, int32_t cluster_debug, int32_t eval_split);

@@ -385,10 +385,8 @@ def test_pose_refine_cluster_frame_split_is_exact(ctx, cfg, oracle, F, seed, mon
 
 @pytest.mark.parametrize("F,seed", [(5, 9), (20, 9), (64, 3), (256, 9), (300, 4), (700, 5)])
 def test_pose_refine_cluster_equals_one_cta(ctx, cfg, oracle, ocfg, F, seed, monkeypatch):
-    """The cluster shape (the default from 512 corner observations up) keeps each frame's arithmetic and the frames' reduction
-    order, and thread 0's solver code is the same text: in this build the two shapes return the same bits - extrinsic, costs,
-    iteration count - which is what one wants of a solve whose capped iterate depends on the last bit of every sum. Sizes the
-    other pose test does not cover are also held to the bar against the oracle."""
+    """The two launch shapes of the extrinsic solve return the same bits (each is also held to the oracle's bits in
+    test_pose_refine_is_the_oracles_bit_for_bit); this one prints their wall times."""
     import time
     pc, img, T0, _ = _pose_problem(oracle, F, seed=seed)
     out = {}

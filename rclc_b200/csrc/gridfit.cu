@@ -594,9 +594,19 @@ __device__ void mat4f_mul_dev(const float* A, const float* B, float* C)
     for (int k = 0; k < 16; ++k) C[k] = out[k];
 }
 
-__device__ bool inverse4_dev(const double* m, double* o)
+// A double whose products, sums and differences are rounded one by one (no multiply-add is fused): the final composition of the
+// board frame and the corners (opt_grid_fitting.h:129-131, utils.h:47-66) are written with it, in the oracle's text, and come
+// out with the oracle's bits.
+struct Xd { double v; };
+__device__ __forceinline__ Xd operator*(Xd a, Xd b) { return {__dmul_rn(a.v, b.v)}; }
+__device__ __forceinline__ Xd operator+(Xd a, Xd b) { return {__dadd_rn(a.v, b.v)}; }
+__device__ __forceinline__ Xd operator-(Xd a, Xd b) { return {__dsub_rn(a.v, b.v)}; }
+__device__ __forceinline__ Xd operator-(Xd a) { return {-a.v}; }
+
+__device__ bool inverse4_dev(const double* m_in, double* o)
 {
-    double inv[16];
+    Xd m[16], inv[16];
+    for (int i = 0; i < 16; ++i) m[i].v = m_in[i];
     inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
     inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
     inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
@@ -613,10 +623,10 @@ __device__ bool inverse4_dev(const double* m, double* o)
     inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
     inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
     inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
-    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
-    if (det == 0) return false;
-    const double id = 1.0 / det;
-    for (int i = 0; i < 16; i++) o[i] = inv[i] * id;
+    const Xd det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    if (det.v == 0) return false;
+    const Xd id = {1.0 / det.v};
+    for (int i = 0; i < 16; i++) o[i] = (inv[i] * id).v;
     return true;
 }
 
@@ -806,22 +816,22 @@ __device__ void outer_finish(const GridGeom& g, LmState& st, FrameCtl& c, int te
         for (int k = 0; k < 16; ++k) Tb[k] = (double)st.T_base_laser[k];
         for (int r = 0; r < 4; ++r)
             for (int cc = 0; cc < 4; ++cc) {
-                double v = 0;
-                for (int k = 0; k < 4; ++k) v += Tb[r * 4 + k] * st.T_bl[k * 4 + cc];
-                Fm[r * 4 + cc] = v;
+                Xd v = {0.0};
+                for (int k = 0; k < 4; ++k) v = v + Xd{Tb[r * 4 + k]} * Xd{st.T_bl[k * 4 + cc]};
+                Fm[r * 4 + cc] = v.v;
             }
         if (!inverse4_dev(Fm, Fi)) { st.status = 3; st.rep.status = 3; for (int k = 0; k < 16; ++k) Fi[k] = nan(""); }
         // utils.h:47-66
         const double sd = g.side;
-        const double fcx = double(int((g.board_w - 1) / 2)) * sd, fcy = double(int((g.board_h - 1) / 2)) * sd;
+        const Xd fcx = Xd{double(int((g.board_w - 1) / 2))} * Xd{sd}, fcy = Xd{double(int((g.board_h - 1) / 2))} * Xd{sd};
         int kk = 0;
         for (int row = 0; row < g.board_h - 1; ++row)
             for (int col = 0; col < g.board_w - 1; ++col) {
-                const double p[4] = {fcx - double(col) * sd, fcy - double(row) * sd, 0.0, 1.0};
+                const Xd p[4] = {fcx - Xd{double(col)} * Xd{sd}, fcy - Xd{double(row)} * Xd{sd}, {0.0}, {1.0}};
                 for (int r = 0; r < 3; ++r) {
-                    double v = 0;
-                    for (int q = 0; q < 4; ++q) v += Fi[r * 4 + q] * p[q];
-                    corners[kk * 3 + r] = v;
+                    Xd v = {0.0};
+                    for (int q = 0; q < 4; ++q) v = v + Xd{Fi[r * 4 + q]} * p[q];
+                    corners[kk * 3 + r] = v.v;
                 }
                 ++kk;
             }

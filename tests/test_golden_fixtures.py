@@ -118,7 +118,7 @@ def test_cuda_solve_gmm_ransac_pose_project_match_fixtures(gpu):
     for k, (seed, pert, pat) in enumerate(SOLVE_CASES):
         p = synth.board_frame_cloud(30000, seed, pert=pert, pattern=pat)
         corners, rep = ctx.gridfit_solve(cfg, p)
-        assert np.abs(corners - g[f"corners{k}"]).max() < 1e-4                     # 0.1 mm
+        assert np.abs(corners - g[f"corners{k}"]).max() <= 2e-15                  # bar 0.1 mm; they are the oracle's to an ulp
         assert [rep.outer_iterations, rep.pose_evals] == list(g[f"counters{k}"][:2])
     g = load("gmm")
     inten = synth.board_frame_cloud(50000, 31)[:, 3]

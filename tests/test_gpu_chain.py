@@ -77,7 +77,9 @@ def test_est_board_corner_matches_oracle(ctx, cfg, oracle, f):
     assert rc0 == 0 and st == 0
     assert np.array_equal(cloud1.view(np.uint32), cloud0.view(np.uint32))          # projected + moved cloud: the same floats
     assert r1.pose_evals == r0.pose_evals and r1.outer_iterations == r0.outer_iterations
-    assert np.abs(c1 - c0).max() < 1e-6
+    assert np.abs(c1 - c0).max() <= 2e-15                                           # the corners: the oracle's to an ulp
+    if np.array_equal(np.array(r1.T_base_laser, np.float32), np.array(r0.T_base_laser, np.float32)):
+        assert c1.tobytes() == c0.tobytes()                                         # (bit for bit when the float frame agrees)
     assert np.linalg.norm(c1 - truth, axis=1).max() < 6e-3                          # and they are the board's corners
 
 
@@ -96,7 +98,7 @@ def test_calibrate_frames_equals_single_frame_calls_and_oracle_extrinsic(ctx, cf
         assert out["reports"][f].pose_evals == r1.pose_evals
         rc, ob = oracle.segment_board(ocfg, scans[f])
         rc, c0, _, _ = oracle.est_board_corner(ocfg, _to_cam(ob))
-        assert rc == 0 and np.abs(c1 - c0).max() < 1e-6
+        assert rc == 0 and np.abs(c1 - c0).max() <= 2e-15                           # the oracle's corners to an ulp
         oc.append(c0)
     # the extrinsic: the same PnP start, pose_reprj_opt on the oracle's corners by the oracle
     rc, T0, _, _, _ = oracle.pose_refine(ocfg, np.stack(oc), np.stack(imgs), out_start(ctx, cfg, np.stack(oc), np.stack(imgs)))
@@ -104,7 +106,11 @@ def test_calibrate_frames_equals_single_frame_calls_and_oracle_extrinsic(ctx, cf
     q0, q1 = T0[:4] / np.linalg.norm(T0[:4]), T1[:4] / np.linalg.norm(T1[:4])
     if q0 @ q1 < 0:
         q1 = -q1
-    assert 2 * np.abs(q0 - q1).max() < 1e-4 and np.abs(T0[4:] - T1[4:]).max() < 1e-4
+    assert 2 * np.abs(q0 - q1).max() < 1e-4 and np.abs(T0[4:] - T1[4:]).max() < 1e-4          # the bar
+    # the solve itself is the oracle's bit for bit (tests/test_gpu_parity.py): fed the ORACLE's corners and the same start it
+    # returns the oracle's extrinsic exactly; what separates T1 from T0 is the ulp in the corners of a few frames
+    rc2, T2, _, _, _ = ctx.pose_refine(cfg, np.stack(oc), np.stack(imgs), out_start(ctx, cfg, np.stack(oc), np.stack(imgs)))
+    assert rc2 == 0 and T2.tobytes() == T0.tobytes()
     # and it is the rig's extrinsic
     Tgt = synth.scan_extrinsic()
     R1 = oracle.quat_to_R([q1[3], q1[0], q1[1], q1[2]])
@@ -135,14 +141,19 @@ def test_calibration_of_configs0_in_full_against_the_oracle(ctx, cfg, oracle):
     for f, (nb, c0, r0) in enumerate(ref):
         assert out["n_board"][f] == nb
         assert out["reports"][f].pose_evals == r0.pose_evals and out["reports"][f].outer_iterations == r0.outer_iterations
-        assert np.abs(out["corners"][f] - c0).max() < 1e-6
+        assert np.abs(out["corners"][f] - c0).max() <= 2e-15, (f, np.abs(out["corners"][f] - c0).max())
+    print("frames whose corners are the oracle's bit for bit:", sum(out["corners"][f].tobytes() == ref[f][1].tobytes() for f in range(len(ref))), "of", len(ref))
     oc = np.stack([r[1] for r in ref])
     rc, T0, _, c1o, _ = oracle.pose_refine(ocfg, oc, np.stack(imgs), out_start(ctx, cfg, oc, np.stack(imgs)))
     T1 = out["Tcl"]
     q0, q1 = T0[:4] / np.linalg.norm(T0[:4]), T1[:4] / np.linalg.norm(T1[:4])
     if q0 @ q1 < 0:
         q1 = -q1
-    assert 2 * np.abs(q0 - q1).max() < 1e-4 and np.abs(T0[4:] - T1[4:]).max() < 1e-4
+    assert 2 * np.abs(q0 - q1).max() < 1e-4 and np.abs(T0[4:] - T1[4:]).max() < 1e-4          # the bar
+    # the solve itself is the oracle's bit for bit (tests/test_gpu_parity.py): fed the ORACLE's corners and the same start it
+    # returns the oracle's extrinsic exactly; what separates T1 from T0 is the ulp in the corners of a few frames
+    rc2, T2, _, _, _ = ctx.pose_refine(cfg, oc, np.stack(imgs), out_start(ctx, cfg, oc, np.stack(imgs)))
+    assert rc2 == 0 and T2.tobytes() == T0.tobytes()
 
 
 def out_start(ctx, cfg, corners, imgs):

@@ -89,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -100,6 +100,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
+    def up(self):
+        """nvidia-smi takes 0.2 - 1 s to print its first line on a fresh box; the timed region must not start before it has."""
+        return self.proc is None or len(self.lines) > 0
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -109,7 +113,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         timed = [ln for (t, ln) in self.lines if self.t0 is None or t >= self.t0]
         window = "timed region"
-        if not timed:               # nvidia-smi reports every 100 ms: a sub-100-ms region can fall between two lines
+        if not timed:               # nvidia-smi reports every 50 ms: a shorter region can fall between two lines
             timed, window = [ln for (_, ln) in self.lines[-3:]], "warm-up, same workload (timed region shorter than the sampling period)"
         for ln in timed:
             f = [x.strip() for x in ln.split(",")]
@@ -477,6 +481,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()                                  # nvidia-smi needs a few hundred ms to come up: start it before the warm-up
     for _ in range(args.warmup):
+        step_resident()
+    t_up = time.time()
+    while not sampler.up() and time.time() - t_up < 5.0:       # more warm-up steps until the clock sampler reports (bounded)
         step_resident()
     barrier()
     sampler.mark()

@@ -263,3 +263,14 @@ def lm_tutorial(which, x0, linear_solver=0, max_iterations=100):
                                C.byref(n), C.byref(term))
     assert rc == 0 and n.value <= 256
     return x, cost[:n.value].copy(), rad[:n.value].copy(), term.value
+
+
+def rn_cube(q):
+    lib().orc_rn_cube.restype = C.c_double
+    return lib().orc_rn_cube(C.c_double(q))
+
+
+def rn_sincos(x):
+    s = C.c_double(); c = C.c_double()
+    lib().orc_rn_sincos(C.c_double(x), C.byref(s), C.byref(c))
+    return s.value, c.value

@@ -1341,4 +1341,8 @@ int orc_lm_tutorial(int which, int linear_solver, double* x_io, int max_iteratio
     return 0;
 }
 
+// the correctly rounded stand-ins of ceres_lm.hpp, for tests/test_oracle_restatement.py (which holds them to exact rational arithmetic)
+double orc_rn_cube(double q) { return orc::rn::cube(q); }
+int orc_rn_sincos(double x, double* sin_out, double* cos_out) { orc::rn::sincos(x, sin_out, cos_out); return 0; }
+
 } // extern "C"

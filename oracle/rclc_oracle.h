@@ -122,6 +122,10 @@ int orc_euclidean_cluster(const void* pts, int stride, int64_t n, double tol, in
  * board frame T_bl (row-major 4x4, board <- laser) from the centroids of the black blocks and the board plane. Returns 0. */
 int orc_calc_laser_coor(const rclc_config* cfg, const double* centroids, int32_t n, const double plane[4], double Tbl_out[16]);
 
+/* ceres_lm.hpp's correctly rounded pow(q, 3), sin and cos (what the extrinsic solve uses in place of libm's). */
+double orc_rn_cube(double q);
+int orc_rn_sincos(double x, double* sin_out, double* cos_out);
+
 /* The two Ceres tutorial problems whose solver logs the Ceres documentation prints (0: f(x) = 10 - x, 1: Powell's function), run
  * through ceres_lm.hpp (linear_solver 0 = DENSE_QR as published, 1 = DENSE_NORMAL_CHOLESKY): the `cost` and `tr_radius` column of every iteration, iteration 0 included. The pin of
  * the restated minimiser against published output of the dependency itself. Returns 0. */

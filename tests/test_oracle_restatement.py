@@ -334,3 +334,43 @@ def test_calc_laser_coor_library_matches_oracle(oracle, ocfg):
         assert np.abs(back[:, 2]).max() < 5e-3
         xs = np.sort(np.unique(np.round(back[:, 0], 2))); ys = np.sort(np.unique(np.round(back[:, 1], 2)))
         np.testing.assert_allclose(xs, np.arange(-0.35, 0.36, 0.1), atol=1e-9); np.testing.assert_allclose(ys, np.arange(-0.25, 0.26, 0.1), atol=1e-9)
+
+
+def _nearest_double(fr):
+    """The double nearest to an exact rational (ties cannot occur for the irrational / non-representable values tested here)."""
+    import math
+    from fractions import Fraction
+    a = float(fr)
+    best, err = a, abs(Fraction(a) - fr)
+    for b in (math.nextafter(a, math.inf), math.nextafter(a, -math.inf)):
+        e = abs(Fraction(b) - fr)
+        if e < err:
+            best, err = b, e
+    return best
+
+
+def test_correctly_rounded_cube_sin_cos(oracle):
+    """oracle/ceres_lm.hpp namespace rn (and, operation for operation, pose.cu): pow(q, 3), sin and cos as the extrinsic solve takes
+    them are the CORRECTLY ROUNDED values - checked here against exact rational arithmetic (the cube exactly, the Taylor series to
+    2^-200) on a few thousand arguments of the sizes the solve produces. This machine's libm is counted beside them."""
+    import math
+    from fractions import Fraction
+    rng = np.random.default_rng(5)
+    libm_pow = libm_sin = libm_cos = 0
+    qs = rng.uniform(-1, 1, 1500)
+    for q in qs:
+        q = float(q)
+        want = _nearest_double(Fraction(q) ** 3)
+        assert oracle.rn_cube(q) == want
+        libm_pow += math.pow(q, 3) != want
+    xs = 10.0 ** rng.uniform(-8, np.log10(0.5), 1500)
+    for x in xs:
+        x = float(x)
+        X = Fraction(x)
+        s = sum(Fraction((-1) ** k) * X ** (2 * k + 1) / math.factorial(2 * k + 1) for k in range(40))
+        c = sum(Fraction((-1) ** k) * X ** (2 * k) / math.factorial(2 * k) for k in range(40))
+        got_s, got_c = oracle.rn_sincos(x)
+        assert got_s == _nearest_double(s) and got_c == _nearest_double(c), x
+        libm_sin += math.sin(x) != got_s
+        libm_cos += math.cos(x) != got_c
+    print(f"this libm differs from the correctly rounded value in {libm_pow} of {len(qs)} cubes, {libm_sin} / {libm_cos} of {len(xs)} sines / cosines")

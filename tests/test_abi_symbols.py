@@ -74,3 +74,20 @@ def test_product_does_not_reference_oracle():
                     if re.search(r"(pyoracle|rclc_oracle|librclc_oracle|from oracle|import oracle)", txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_pose_kernel_is_built_without_fused_multiply_adds():
+    """pose.cu reproduces the oracle's arithmetic operation by operation; that holds only while nvcc fuses no
+    multiply-add the source does not spell out. The flag is per file in rclc_b200/build.py - and the built library shows it: the
+    extrinsic solve's kernels hold separate DMUL / DADD where a contracting build would hold DFMA almost everywhere."""
+    import shutil
+    import subprocess
+    from rclc_b200 import build as b
+    assert "-fmad=false" in b.FILE_FLAGS.get("pose.cu", [])
+    lib = os.path.join(ROOT, "rclc_b200", "librclc_b200.so")
+    if not (os.path.exists(lib) and shutil.which("cuobjdump")):
+        pytest.skip("no built library or no cuobjdump here")
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4rclc11k_pose_evalEPKdS1_iiS1_PdS2_", lib], capture_output=True, text=True).stdout
+    n = {op: sass.count(" " + op + " ") for op in ("DFMA", "DMUL", "DADD")}
+    assert n["DMUL"] > 200 and n["DADD"] > 200, n
+    assert n["DFMA"] < n["DMUL"] // 2, n          # what DFMA there is belongs to the division and square-root sequences

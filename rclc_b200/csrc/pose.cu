@@ -248,7 +248,8 @@ __device__ __forceinline__ void pose_corner_dev(const J7* R, const J7* t, const 
     for (int i = 0; i < 7; ++i) out[(10 + i) * os] = depth_norm.v[i];
 }
 
-// One frame from its corners' factors, in corner order: pose_block_dev's running sum, arg-max and epilogue.
+// One frame from its corners' factors, in corner order: pose_block_dev's running sum, arg-max and epilogue - by ONE thread (the
+// form rclc_pose_eval's split test hook runs; the solve uses pose_frame_phase, eight lanes per frame).
 __device__ __forceinline__ void pose_frame_from_corners(const double* Tcl, const double* c0, int os, int C, double& r, double* j6)
 {
     J7 res = jconst(0.0), depth_max = jconst(0.0);

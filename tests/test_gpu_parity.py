@@ -317,16 +317,16 @@ def test_ransac_counts_masks_bit_exact(ctx, oracle):
     assert np.array_equal(r0, r1)
 
 
-def _pose_problem(oracle, F, seed=9, noise=1e-4):
+def _pose_problem(oracle, F, seed=9, noise=1e-4, grid=(5, 7)):
     rng = np.random.default_rng(seed)
-    Cn = 35
+    Cn = grid[0] * grid[1]
     q = np.array([0.02, -0.015, 0.01, 0.0]); q[3] = np.sqrt(1 - (q[:3] ** 2).sum())
     t = np.array([0.07, -0.08, 0.02])
     R = oracle.quat_to_R([q[3], q[0], q[1], q[2]])
     pc = np.zeros((F, Cn, 3)); img = np.zeros((F, Cn, 2))
     for f in range(F):
         base = np.array([rng.uniform(-1, 1), rng.uniform(-0.6, 0.6), rng.uniform(3.5, 5.5)])
-        g = np.array([[0.3 - 0.1 * c, 0.2 - 0.1 * r, 0.0] for r in range(5) for c in range(7)])
+        g = np.array([[0.3 - 0.1 * c, 0.2 - 0.1 * r, 0.0] for r in range(grid[0]) for c in range(grid[1])])
         a = rng.uniform(-0.3, 0.3, 3)
         Rb = oracle.quat_to_R(np.r_[np.sqrt(1 - (a ** 2).sum() / 4), a / 2])
         pc[f] = g @ Rb.T + base
@@ -366,6 +366,23 @@ def test_pose_refine_is_the_oracles_bit_for_bit(ctx, cfg, oracle, ocfg, F, seed)
         assert c1a < 0.01 * c0a
     if F in (64, 256, 300, 700, 1700):
         assert np.abs(Ta[4:] - Tgt[4:]).max() < 2e-4 and 2 * np.linalg.norm(Ta[:4] * np.sign(Ta[3]) - Tgt[:4] * np.sign(Tgt[3])) < 1e-4
+
+
+@pytest.mark.parametrize("F,grid", [(12, (3, 4)), (40, (2, 2)), (6, (9, 11)), (3, (1, 1))])
+def test_pose_refine_other_board_sizes_bit_for_bit(ctx, cfg, oracle, ocfg, F, grid):
+    """Boards with 12, 4, 99 and 1 corner(s) per frame: the per-corner / per-frame split, the eight-lane frame assembly and the strided
+    arg-max do not depend on the 35 corners of the 8 x 6 board."""
+    pc, img, T0, _ = _pose_problem(oracle, F, seed=17, grid=grid)
+    rc0, Ta, c0a, c1a, ita = oracle.pose_refine(ocfg, pc, img, T0)
+    try:
+        for shape in (1, 2):
+            ctx.set_pose_test_hooks(shape=shape)
+            rc1, Tb, c0b, c1b, itb = ctx.pose_refine(cfg, pc, img, T0)
+            assert (rc1 != 0) == (rc0 != 0)
+            assert (itb, c0b, c1b) == (ita, c0a, c1a) or (np.isnan(c0a) and np.isnan(c0b)), (shape, itb, ita)
+            assert Tb.tobytes() == Ta.tobytes(), (shape, np.abs(Tb - Ta).max())
+    finally:
+        ctx.set_pose_test_hooks()
 
 
 @pytest.mark.parametrize("F,seed", [(5, 9), (20, 9), (64, 3), (256, 9), (300, 4), (700, 5)])

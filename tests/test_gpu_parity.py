@@ -385,6 +385,30 @@ def test_pose_refine_other_board_sizes_bit_for_bit(ctx, cfg, oracle, ocfg, F, gr
         ctx.set_pose_test_hooks()
 
 
+@pytest.mark.parametrize("where", ["start", "later"])
+def test_pose_refine_failure_paths_like_the_oracle(ctx, cfg, oracle, ocfg, where):
+    """A non-finite residual: at the start Ceres fails the solve and leaves the parameters alone; at a candidate it rejects the step
+    and goes on. Both shapes do what the oracle does."""
+    pc, img, T0, _ = _pose_problem(oracle, 6, seed=23)
+    if where == "start":
+        pc[2, 7, :] = np.nan
+    else:
+        # a corner that sits in the camera plane for the start but not for its neighbours: X / Z blows up only along the way
+        R = oracle.quat_to_R([T0[3], T0[0], T0[1], T0[2]])
+        p = np.linalg.solve(R, np.array([0.1, 0.1, 1e-9]) - T0[4:])
+        pc[2, 7, :] = p
+    rc0, Ta, c0a, c1a, ita = oracle.pose_refine(ocfg, pc, img, T0)
+    try:
+        for shape in (1, 2):
+            ctx.set_pose_test_hooks(shape=shape)
+            rc1, Tb, c0b, c1b, itb = ctx.pose_refine(cfg, pc, img, T0)
+            assert (rc1 != 0) == (rc0 != 0), (rc0, rc1)
+            assert Tb.tobytes() == Ta.tobytes() and itb == ita, (shape, itb, ita, Tb, Ta)
+            assert (c0b == c0a or (np.isnan(c0a) and np.isnan(c0b))) and (c1b == c1a or (np.isnan(c1a) and np.isnan(c1b)))
+    finally:
+        ctx.set_pose_test_hooks()
+
+
 @pytest.mark.parametrize("F,seed", [(5, 9), (20, 9), (64, 3), (256, 9), (300, 4), (700, 5)])
 def test_pose_refine_cluster_frame_split_is_exact(ctx, cfg, oracle, F, seed, monkeypatch):
     """The cluster shape deals (frame, corner) pairs over 16 CTAs and rebuilds each frame's sums from per-corner factors. That

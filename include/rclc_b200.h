@@ -40,7 +40,8 @@ typedef struct rclc_batch rclc_batch;
 /* Mirrors what opt_grid_fitting prints/returns (opt_grid_fitting.h:112-131) plus solver counters. */
 typedef struct rclc_gridfit_report {
     int32_t outer_iterations;     /* executions of the while body, opt_grid_fitting.h:68        */
-    int32_t status;               /* 0 ok; 1 = a Ceres solve ended in FAILURE (NaN residual)     */
+    int32_t status;               /* 0 ok; 1 = a Ceres solve ended in FAILURE (NaN residual; the reference goes on, and so do the
+                                     corners); 2 = a frame without points; 3 = the composed frame has no inverse */
     int64_t pose_evals;           /* distinct (x,y,yaw) poses at which all residuals were evaluated */
     int64_t lm_iterations;        /* Ceres iterations summed over outer iterations                */
     double  first_initial_cost;   /* Summary::initial_cost of the first solve                     */
@@ -199,7 +200,8 @@ int rclc_segment_board(rclc_ctx* ctx, const rclc_config* cfg, const void* pts, i
 /* est_board_corner (include/pc_process.h:583-646): one board-only cloud (float4 {x, y, z, I}, the T_base'd laser frame) in, the
  * (W-1) x (H-1) corners in that frame out [nc][3]. The cloud comes back as the reference leaves it (projected onto its plane, moved
  * into the board frame). T_bl_out (16, may be NULL): the refined board <- laser transform; report may be NULL.
- * *stage_failed (may be NULL): 0, or the stage that gave up: 1 plane fit, 2 block centroids, 3 board frame, 4 grid fit. */
+ * *stage_failed (may be NULL): 0, or the stage that gave up: 1 plane fit, 2 block centroids, 3 board frame, 4 grid fit (no points or
+ * no inverse; a Ceres FAILURE inside the fit is report->status 1 and, as in opt_grid_fitting.h:96-131, not a failed stage). */
 int rclc_est_board_corner(rclc_ctx* ctx, const rclc_config* cfg, void* pts_io_xyzi, int64_t n, double* corners_out, double* T_bl_out,
                           rclc_gridfit_report* report, int32_t* stage_failed);
 /* Stage 1 + stage 2 for F raw scans (apps/BoardSegmentation.cpp:31-165 -> apps/Calibrate.cpp:90-107 -> calib_opt :12-67): every scan

@@ -610,7 +610,9 @@ int rclc_est_board_corner(rclc_ctx* ctx, const rclc_config* cfg, void* pts_io_xy
         rclc_gridfit_report rep;
         RCLC_TRY(rclc_batch_gridfit_solve(ctx->calib_batch, Tbl, T_bl_out, corners_out, &rep));
         if (report) *report = rep;
-        if (rep.status != 0) stage = 4;
+        // A Ceres solve that ended in FAILURE (report.status 1: a NaN residual) is NOT a failed stage: opt_grid_fitting.h:96-131 never
+        // looks at the summary and goes on to the corners of the pose it has. Only a frame without points or without an inverse is.
+        if (rep.status >= 2) stage = 4;
         else if (cfg->board_order == 1) flip_corners(cfg, corners_out);
     }
     RCLC_CUDA(cudaMemcpyAsync(pts_io_xyzi, d_cloud, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -718,7 +720,7 @@ int rclc_calibrate_frames(rclc_ctx* ctx, const rclc_config* cfg, const void* con
         for (int k = 0; k < K; ++k) {
             const int f = ok_frames[(size_t)k];
             if (reports) reports[f] = rk[(size_t)k];
-            if (rk[(size_t)k].status != 0) { frame_status[f] = 24; continue; }
+            if (rk[(size_t)k].status >= 2) { frame_status[f] = 24; continue; }     // (a Ceres FAILURE, status 1, is not: see rclc_est_board_corner)
             if (cfg->board_order == 1) flip_corners(cfg, &ck[(size_t)k * nc * 3]);
             std::memcpy(&corners_out[(size_t)f * nc * 3], &ck[(size_t)k * nc * 3], (size_t)nc * 24);
         }

@@ -83,6 +83,25 @@ def test_est_board_corner_matches_oracle(ctx, cfg, oracle, f):
     assert np.linalg.norm(c1 - truth, axis=1).max() < 6e-3                          # and they are the board's corners
 
 
+def test_est_board_corner_on_degenerate_boards_like_the_oracle(ctx, cfg, oracle):
+    """Thinned-out boards stop at the block centroids on both sides; a board without its black squares runs into NaN residuals - a
+    Ceres FAILURE, which the reference never looks at (opt_grid_fitting.h:96-131): no failed stage, status 1 in the report, and the
+    corners of the pose the fit started from, the oracle's to an ulp."""
+    raw, _, _ = synth.raw_scan(0)
+    rc, board = oracle.segment_board(oracle.config(), raw)
+    board = _to_cam(board)
+    for thin in (board[::50], board[:100]):
+        rc0 = oracle.est_board_corner(oracle.config(), thin)[0]
+        st = ctx.est_board_corner(cfg, thin)[0]
+        assert rc0 == st == 2
+    white = board[board[:, 3] > 60]
+    rc0, c0, r0, cloud0 = oracle.est_board_corner(oracle.config(), white)
+    st, c1, r1, cloud1 = ctx.est_board_corner(cfg, white)
+    assert rc0 == 0 and st == 0 and r0.status == r1.status == 1
+    assert np.array_equal(cloud1.view(np.uint32), cloud0.view(np.uint32))
+    assert np.abs(c1 - c0).max() <= 2e-15
+
+
 def test_calibrate_frames_equals_single_frame_calls_and_oracle_extrinsic(ctx, cfg, oracle):
     F = 6
     ocfg = oracle.config()

@@ -73,3 +73,19 @@ def test_projection_of_points_in_and_behind_the_camera_plane(ctx, cfg, oracle, o
     img = synth.noise_image(3)
     T = np.eye(4, dtype=np.float32)
     assert all(_same(x, y) for x, y in zip(oracle.project_colorize(ocfg, pts, T, img), ctx.project_colorize(cfg, pts, T, img)))
+
+
+@pytest.mark.parametrize("which", ["one point", "ten points", "300 points", "far from the board"])
+def test_grid_fit_on_clouds_that_cannot_be_fitted(ctx, cfg, oracle, ocfg, which):
+    """Clouds that leave half-discs empty: NaN residuals, a Ceres FAILURE in every outer iteration (status 1), max_iter_time + 1 outer
+    iterations, the corners of the pose the fit started from - the same on both sides, accumulators and NaN pattern included."""
+    pts = synth.board_frame_cloud(40000, 3, pert=(0.004, -0.002, 0.2))
+    p = {"one point": pts[:1], "ten points": pts[:10], "300 points": pts[::133], "far from the board": pts + np.array([5, 5, 0, 0], np.float32)}[which]
+    rc, oc, orep, _ = oracle.gridfit_solve(ocfg, p)
+    c, rep = ctx.gridfit_solve(cfg, p)
+    assert rc == 0 and (rep.status, rep.outer_iterations, rep.pose_evals) == (orep.status, orep.outer_iterations, orep.pose_evals) and rep.status == 1
+    assert np.abs(c - oc).max() <= 2e-15
+    r0, j0, a0 = oracle.gridfit_eval(ocfg, p, (0.001, 0.002, 0.1), want_acc=True)
+    r1, j1, a1 = ctx.gridfit_eval(cfg, p, (0.001, 0.002, 0.1), want_acc=True)
+    assert np.array_equal(a0, a1) and np.array_equal(np.isnan(r0), np.isnan(r1))
+    assert np.allclose(r0[~np.isnan(r0)], r1[~np.isnan(r1)], rtol=1e-10, atol=0)

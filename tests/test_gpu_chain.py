@@ -102,6 +102,33 @@ def test_est_board_corner_on_degenerate_boards_like_the_oracle(ctx, cfg, oracle)
     assert np.abs(c1 - c0).max() <= 2e-15
 
 
+def test_calibrate_frames_with_scans_that_hold_no_board(ctx, cfg, oracle):
+    """Two of six scans yield no board (nothing in the region of interest; a scan too thin for a plane): status 10 for them, exactly
+    where the oracle's BoardSegmentation gives up, and the extrinsic over the four that remain - the oracle's solve over its own
+    corners of those four, from the same start - within the bar."""
+    F = 6
+    ocfg = oracle.config()
+    scans, imgs, _ = zip(*[synth.raw_scan(f) for f in range(F)])
+    scans = list(scans)
+    scans[2] = scans[2] + np.array([100, 0, 0, 0], np.float32)
+    scans[4] = scans[4][::40].copy()
+    out = ctx.calibrate_frames(cfg, scans, np.stack(imgs))
+    oc, keep = [], []
+    for f in range(F):
+        rc, ob = oracle.segment_board(ocfg, scans[f])
+        assert (rc != 0) == (out["status"][f] == 10), f
+        if rc != 0:
+            continue
+        rc, c0, _, _ = oracle.est_board_corner(ocfg, _to_cam(ob))
+        assert rc == 0 and out["status"][f] == 0 and out["n_board"][f] == len(ob)
+        assert np.abs(out["corners"][f] - c0).max() <= 2e-15
+        oc.append(c0); keep.append(f)
+    assert keep == [0, 1, 3, 5]
+    C0, I0 = np.stack(oc), np.stack([imgs[f] for f in keep])
+    rc, T0, _, _, it0 = oracle.pose_refine(ocfg, C0, I0, out_start(ctx, cfg, C0, I0))
+    assert rc == 0 and np.abs(out["Tcl"] - T0).max() < 1e-4
+
+
 def test_calibrate_frames_equals_single_frame_calls_and_oracle_extrinsic(ctx, cfg, oracle):
     F = 6
     ocfg = oracle.config()
